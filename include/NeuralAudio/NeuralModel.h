@@ -1,0 +1,192 @@
+// Public C++ surface of neuralaudio-b200.
+//
+// Source-compatible with the reference's NeuralAudio/NeuralModel.h (NeuralModel virtuals :33-146,
+// NeuralModelLoader :148-231, enums :20-31): same class, method and enum names, same argument meaning and
+// defaults, so a caller of the reference recompiles against this header unchanged.  Behind it, Process() runs
+// hand-written sm_100a CUDA kernels; a model additionally owns S independent *stream slots* (additive API at the
+// bottom of NeuralModel) so thousands of streams advance per launch.
+//
+// ABI note: the classes live in an inline namespace so that this library and a build of the reference can be
+// loaded into one process (the parity tests do exactly that) without symbol interposition.
+#pragma once
+
+#include <cstddef>
+#include <filesystem>
+#include <istream>
+#include <string>
+#include <utility>
+#include <vector>
+
+#if __has_include(<nlohmann/json.hpp>)
+#include <nlohmann/json.hpp>
+#define NEURALAUDIO_B200_HAVE_NLOHMANN 1
+#elif __has_include("json.hpp")
+#include "json.hpp"
+#define NEURALAUDIO_B200_HAVE_NLOHMANN 1
+#endif
+
+#ifndef DEFAULT_QUALITY_SCALE
+#define DEFAULT_QUALITY_SCALE 1.0
+#endif
+
+#ifndef DEFAULT_INPUT_DBU
+#define DEFAULT_INPUT_DBU 12
+#endif
+
+namespace NeuralAudio
+{
+inline namespace b200
+{
+	// reference NeuralModel.h:20-25.  This build only has the Internal (here: CUDA) back-end; the other two values
+	// exist so callers compile, and are refused by Set*LoadMode exactly like an unsupported mode is there.
+	enum EModelLoadMode
+	{
+		Internal,
+		RTNeural,
+		NAMCore
+	};
+
+	// reference NeuralModel.h:27-31
+	enum ECompositeModelLoadMode
+	{
+		LoadAll,
+		OnDemand
+	};
+
+	// Batch memory layouts for ProcessBatch
+	enum EBatchLayout
+	{
+		StreamMajor = 0,   // element (stream s, frame f) at buffer[s * numFrames + f]
+		FrameMajor = 1     // element (stream s, frame f) at buffer[f * numStreams + s]
+	};
+
+	class NeuralModel
+	{
+	public:
+		virtual ~NeuralModel() {}
+
+		virtual EModelLoadMode GetLoadMode() { return EModelLoadMode::Internal; }
+		virtual bool HasQualityScaling() { return false; }
+		virtual float GetQualityScaleFactor() { return 1.0f; }
+		virtual bool IsQualityChangeRealtimeSafe(float) { return true; }
+		virtual void SetQualityScaleFactor(float) {}
+		virtual bool IsStatic() { return false; }
+		virtual void SetMaxAudioBufferSize(const int) {}
+		virtual void SetAudioInputLevelDBu(float audioDBu) { audioInputLevelDBu = audioDBu; }
+		virtual float GetAudioInputLevelDBu() { return audioInputLevelDBu; }
+		virtual float GetRecommendedInputDBAdjustment() { return audioInputLevelDBu - modelInputLevelDBu; }
+		virtual float GetRecommendedOutputDBAdjustment() { return -18 - modelLoudnessDB; }
+		virtual float GetSampleRate() { return sampleRate; }
+		virtual int GetReceptiveFieldSize() { return -1; }   // -1: no fixed receptive field (LSTM)
+		virtual std::string GetModelVersion() { return modelVersion; }
+		virtual std::string GetMetadata(const std::string& fieldName)
+		{
+			for (const auto& kv : metadata)
+				if (kv.first == fieldName) return kv.second;
+			return "";
+		}
+
+		// One mono stream (stream slot 0), host OR device pointers, in == out allowed.  Synchronous: `output` is
+		// complete on return, like the reference (NeuralModel.h:127).
+		virtual void Process(float* input, float* output, size_t numSamples)
+		{
+			(void)input; (void)output; (void)numSamples;
+		}
+
+		// WaveNet: full state reset to "silence forever"; LSTM: 2048 more zero samples (reference semantics).
+		// Applies to every stream slot.
+		virtual void Prewarm() {}
+
+		// ---- additive batch API (no counterpart in the reference) -------------------------------------------
+		// Allocate and prewarm `numStreams` independent stream slots (default 1).  Returns false on failure
+		// (GetLastError() has the reason).
+		virtual bool SetNumStreams(size_t numStreams) { (void)numStreams; return false; }
+		virtual size_t GetNumStreams() { return 0; }
+
+		// Advance stream slots [0, numStreams) by numFrames.  Pointers may be host or device memory (detected with
+		// cudaPointerGetAttributes); device pointers are used in place and the call is asynchronous on the model's
+		// CUDA stream (Synchronize() or stream-ordered consumers), host pointers are staged and the call blocks.
+		virtual bool ProcessBatch(const float* input, float* output, size_t numStreams, size_t numFrames, EBatchLayout layout = StreamMajor)
+		{
+			(void)input; (void)output; (void)numStreams; (void)numFrames; (void)layout;
+			return false;
+		}
+		virtual bool Synchronize() { return false; }
+		virtual void* GetCudaStream() { return nullptr; }
+		virtual int GetDevice() { return -1; }
+		virtual size_t GetStateBytesPerStream() { return 0; }
+		virtual std::string GetLastError() { return ""; }
+
+	protected:
+		float audioInputLevelDBu = (float)DEFAULT_INPUT_DBU;
+		float modelInputLevelDBu = 12;
+		float modelOutputLevelDBu = 12;
+		float modelLoudnessDB = -18;
+		float sampleRate = 48000;
+		std::string modelVersion = "";
+		std::vector<std::pair<std::string, std::string>> metadata;
+	};
+
+	class NeuralModelLoader
+	{
+	public:
+		// nullptr when the file does not exist or the model cannot be placed on the GPU; throws std::runtime_error
+		// for malformed files (wrong weight count, bad JSON), like the reference (WaveNet.h:704-709).
+		NeuralModel* CreateFromFile(const std::filesystem::path& modelPath, bool doPrewarm = true);
+		NeuralModel* CreateFromStream(std::basic_istream<char>& stream, const std::filesystem::path& extension, bool doPrewarm = true);
+		NeuralModel* CreateFromJsonText(const std::string& jsonText, const std::filesystem::path& extension, bool doPrewarm = true);
+#ifdef NEURALAUDIO_B200_HAVE_NLOHMANN
+		NeuralModel* CreateFromJson(nlohmann::json& modelJson, const std::filesystem::path& extension, bool doPrewarm = true)
+		{
+			return CreateFromJsonText(modelJson.dump(), extension, doPrewarm);
+		}
+#endif
+
+		bool SetLSTMLoadMode(EModelLoadMode val)
+		{
+			if (!SupportsLSTMLoadMode(val)) return false;
+			lstmLoadMode = val;
+			return true;
+		}
+
+		bool SetWaveNetLoadMode(EModelLoadMode val)
+		{
+			if (!SupportsWaveNetLoadMode(val)) return false;
+			wavenetLoadMode = val;
+			return true;
+		}
+
+		ECompositeModelLoadMode GetCompositeModelLoadMode() { return compositeLoadMode; }
+		void SetCompositeModelLoadMode(ECompositeModelLoadMode loadMode) { compositeLoadMode = loadMode; }
+
+		bool SupportsWaveNetLoadMode(EModelLoadMode mode) { return mode == EModelLoadMode::Internal; }
+		bool SupportsLSTMLoadMode(EModelLoadMode mode) { return mode == EModelLoadMode::Internal; }
+
+		void SetAudioInputLevelDBu(float audioDBu) { audioInputLevelDBu = audioDBu; }
+		float GetAudioInputLevelDBu() { return audioInputLevelDBu; }
+		void SetDefaultMaxAudioBufferSize(int maxSize) { defaultMaxAudioBufferSize = maxSize; }
+		int GetDefaultMaxAudioBufferSize() { return defaultMaxAudioBufferSize; }
+		void SetDefaultQualityScaleFactor(float scaleFactor) { defaultQualityScaleFactor = scaleFactor; }
+		float GetDefaultQualityScaleFactor() { return defaultQualityScaleFactor; }
+		void SetExternalSampleRate(int sampleRate) { this->externalSampleRate = sampleRate; }
+
+		// ---- additive ---------------------------------------------------------------------------------------
+		void SetDevice(int cudaDevice) { device = cudaDevice; }   // -1 (default): the calling thread's current device
+		int GetDevice() { return device; }
+		void SetDefaultNumStreams(size_t numStreams) { defaultNumStreams = numStreams; }
+		size_t GetDefaultNumStreams() { return defaultNumStreams; }
+		int GetExternalSampleRate() { return externalSampleRate; }
+
+	protected:
+		EModelLoadMode lstmLoadMode = EModelLoadMode::Internal;
+		EModelLoadMode wavenetLoadMode = EModelLoadMode::Internal;
+		ECompositeModelLoadMode compositeLoadMode = ECompositeModelLoadMode::LoadAll;
+		float audioInputLevelDBu = (float)DEFAULT_INPUT_DBU;
+		int defaultMaxAudioBufferSize = 128;
+		float defaultQualityScaleFactor = (float)DEFAULT_QUALITY_SCALE;
+		int externalSampleRate = 48000;
+		int device = -1;
+		size_t defaultNumStreams = 1;
+	};
+}
+}

@@ -1,0 +1,417 @@
+// extern "C" boundary: the reference's 15 exports (NeuralAudioCAPI/NeuralAudioCApi.cpp:14-97) plus the additive
+// batched entry points declared in include/NeuralAudioCApi.h.  No exception crosses this boundary.
+#include <cstring>
+#include <filesystem>
+#include <fstream>
+#include <sstream>
+#include <string>
+#include "NeuralAudioCApi.h"
+#include "NeuralAudio/NeuralModel.h"
+#include "neural_model_internal.h"
+#include "model_desc.h"
+
+// opaque handles: a heap struct around one C++ object, caller-owned (same shape as NeuralAudioCApi.cpp:4-12)
+struct NeuralModel
+{
+	NeuralAudio::NeuralModel* model;
+};
+
+struct NeuralModelLoader
+{
+	NeuralAudio::NeuralModelLoader* loader;
+};
+
+namespace
+{
+	using Impl = NeuralAudio::B200ModelImpl;
+
+	Impl* impl(NeuralModel* m)
+	{
+		return (m && m->model) ? static_cast<Impl*>(m->model) : nullptr;
+	}
+
+	template <typename F>
+	NeuralModel* guarded_create(F&& f)
+	{
+		try
+		{
+			NeuralAudio::NeuralModel* inner = f();
+			if (!inner)
+			{
+				if (nab200::LastError().empty()) nab200::SetLastError("model could not be loaded");
+				return nullptr;
+			}
+			NeuralModel* model = new NeuralModel();
+			model->model = inner;
+			return model;
+		}
+		catch (const std::exception& e)
+		{
+			nab200::SetLastError(e.what());
+		}
+		catch (...)
+		{
+			nab200::SetLastError("unknown error while loading model");
+		}
+		return nullptr;
+	}
+
+	int copy_out(const std::string& v, char* out, int capacity)
+	{
+		if (out && capacity > 0)
+		{
+			int n = (int)v.size() < capacity - 1 ? (int)v.size() : capacity - 1;
+			memcpy(out, v.data(), (size_t)n);
+			out[n] = 0;
+		}
+		return (int)v.size();
+	}
+}
+
+extern "C" {
+
+// ---- PART 1 --------------------------------------------------------------------------------------------
+
+NeuralModelLoader* CreateLoader(void)
+{
+	NeuralModelLoader* loader = new NeuralModelLoader();
+	loader->loader = new NeuralAudio::NeuralModelLoader();
+	return loader;
+}
+
+void DeleteLoader(NeuralModelLoader* loader)
+{
+	if (!loader) return;
+	delete loader->loader;
+	delete loader;
+}
+
+NeuralModel* CreateModelFromFile(NeuralModelLoader* loader, const wchar_t* modelPath)
+{
+	if (!loader || !modelPath) { nab200::SetLastError("null argument"); return nullptr; }
+	nab200::SetLastError("");
+	return guarded_create([&]() { return loader->loader->CreateFromFile(std::filesystem::path(modelPath)); });
+}
+
+void DeleteModel(NeuralModel* model)
+{
+	if (!model) return;
+	delete model->model;
+	delete model;
+}
+
+void SetLSTMLoadMode(NeuralModelLoader* loader, int loadMode)
+{
+	if (loader) loader->loader->SetLSTMLoadMode((NeuralAudio::EModelLoadMode)loadMode);
+}
+
+void SetWaveNetLoadMode(NeuralModelLoader* loader, int loadMode)
+{
+	if (loader) loader->loader->SetWaveNetLoadMode((NeuralAudio::EModelLoadMode)loadMode);
+}
+
+void SetAudioInputLevelDBu(NeuralModelLoader* loader, float audioDBu)
+{
+	if (loader) loader->loader->SetAudioInputLevelDBu(audioDBu);
+}
+
+void SetDefaultMaxAudioBufferSize(NeuralModelLoader* loader, int maxSize)
+{
+	if (loader) loader->loader->SetDefaultMaxAudioBufferSize(maxSize);
+}
+
+int GetLoadMode(NeuralModel* model)
+{
+	return impl(model) ? (int)model->model->GetLoadMode() : 0;
+}
+
+bool IsStatic(NeuralModel* model)
+{
+	return impl(model) ? model->model->IsStatic() : false;
+}
+
+void SetMaxAudioBufferSize(NeuralModel* model, int maxSize)
+{
+	if (impl(model)) model->model->SetMaxAudioBufferSize(maxSize);
+}
+
+float GetRecommendedInputDBAdjustment(NeuralModel* model)
+{
+	return impl(model) ? model->model->GetRecommendedInputDBAdjustment() : 0.0f;
+}
+
+float GetRecommendedOutputDBAdjustment(NeuralModel* model)
+{
+	return impl(model) ? model->model->GetRecommendedOutputDBAdjustment() : 0.0f;
+}
+
+float GetSampleRate(NeuralModel* model)
+{
+	return impl(model) ? model->model->GetSampleRate() : 0.0f;
+}
+
+void Process(NeuralModel* model, float* input, float* output, size_t numSamples)
+{
+	if (!impl(model)) return;
+	try
+	{
+		model->model->Process(input, output, numSamples);
+	}
+	catch (...)
+	{
+		nab200::SetLastError("exception in Process");
+	}
+}
+
+// ---- PART 2 --------------------------------------------------------------------------------------------
+
+const char* NA_GetLastError(void)
+{
+	return nab200::LastError().c_str();
+}
+
+const char* NA_GetVersion(void)
+{
+	return "neuralaudio-b200 0.1 (sm_100a)";
+}
+
+int NA_GetDeviceCount(void)
+{
+	int count = 0;
+	cudaError_t err = cudaGetDeviceCount(&count);
+	if (err != cudaSuccess)
+	{
+		cudaGetLastError();
+		nab200::SetLastError(std::string("cudaGetDeviceCount: ") + cudaGetErrorString(err));
+		return 0;
+	}
+	return count;
+}
+
+void NA_SetLoaderDevice(NeuralModelLoader* loader, int cudaDevice)
+{
+	if (loader) loader->loader->SetDevice(cudaDevice);
+}
+
+void NA_SetDefaultNumStreams(NeuralModelLoader* loader, size_t numStreams)
+{
+	if (loader) loader->loader->SetDefaultNumStreams(numStreams);
+}
+
+void NA_SetDefaultQualityScaleFactor(NeuralModelLoader* loader, float scale)
+{
+	if (loader) loader->loader->SetDefaultQualityScaleFactor(scale);
+}
+
+void NA_SetExternalSampleRate(NeuralModelLoader* loader, int sampleRate)
+{
+	if (loader) loader->loader->SetExternalSampleRate(sampleRate);
+}
+
+void NA_SetCompositeModelLoadMode(NeuralModelLoader* loader, int loadMode)
+{
+	if (loader) loader->loader->SetCompositeModelLoadMode((NeuralAudio::ECompositeModelLoadMode)loadMode);
+}
+
+NeuralModel* NA_CreateModelFromMemory(NeuralModelLoader* loader, const char* data, size_t size, const char* extension, int doPrewarm)
+{
+	if (!loader || !data || !extension) { nab200::SetLastError("null argument"); return nullptr; }
+	nab200::SetLastError("");
+	return guarded_create([&]() { return loader->loader->CreateFromJsonText(std::string(data, size), std::filesystem::path(extension), doPrewarm != 0); });
+}
+
+NeuralModel* NA_CreateModelFromFileEx(NeuralModelLoader* loader, const wchar_t* modelPath, int doPrewarm)
+{
+	if (!loader || !modelPath) { nab200::SetLastError("null argument"); return nullptr; }
+	nab200::SetLastError("");
+	return guarded_create([&]() { return loader->loader->CreateFromFile(std::filesystem::path(modelPath), doPrewarm != 0); });
+}
+
+void NA_Prewarm(NeuralModel* model)
+{
+	if (impl(model)) model->model->Prewarm();
+}
+
+int NA_ResetStreams(NeuralModel* model)
+{
+	return (impl(model) && impl(model)->ResetStreams()) ? 0 : -1;
+}
+
+int NA_HasQualityScaling(NeuralModel* model)
+{
+	return (impl(model) && model->model->HasQualityScaling()) ? 1 : 0;
+}
+
+float NA_GetQualityScaleFactor(NeuralModel* model)
+{
+	return impl(model) ? model->model->GetQualityScaleFactor() : 1.0f;
+}
+
+void NA_SetQualityScaleFactor(NeuralModel* model, float scale)
+{
+	if (impl(model)) model->model->SetQualityScaleFactor(scale);
+}
+
+int NA_GetReceptiveFieldSize(NeuralModel* model)
+{
+	return impl(model) ? model->model->GetReceptiveFieldSize() : -1;
+}
+
+int NA_GetModelVersion(NeuralModel* model, char* out, int capacity)
+{
+	return copy_out(impl(model) ? model->model->GetModelVersion() : std::string(), out, capacity);
+}
+
+int NA_GetMetadata(NeuralModel* model, const char* key, char* out, int capacity)
+{
+	return copy_out((impl(model) && key) ? model->model->GetMetadata(key) : std::string(), out, capacity);
+}
+
+int NA_SetNumStreams(NeuralModel* model, size_t numStreams)
+{
+	if (!impl(model)) { nab200::SetLastError("null model"); return -1; }
+	return model->model->SetNumStreams(numStreams) ? 0 : -1;
+}
+
+size_t NA_GetNumStreams(NeuralModel* model)
+{
+	return impl(model) ? model->model->GetNumStreams() : 0;
+}
+
+size_t NA_GetStateBytesPerStream(NeuralModel* model)
+{
+	return impl(model) ? model->model->GetStateBytesPerStream() : 0;
+}
+
+int NA_GetDevice(NeuralModel* model)
+{
+	return impl(model) ? model->model->GetDevice() : -1;
+}
+
+int NA_ProcessBatch(NeuralModel* model, const float* input, float* output, size_t numStreams, size_t numFrames, int layout)
+{
+	if (!impl(model)) { nab200::SetLastError("null model"); return -1; }
+	if (layout != 0 && layout != 1) { nab200::SetLastError("bad layout"); return -1; }
+	try
+	{
+		return model->model->ProcessBatch(input, output, numStreams, numFrames, (NeuralAudio::EBatchLayout)layout) ? 0 : -1;
+	}
+	catch (...)
+	{
+		nab200::SetLastError("exception in ProcessBatch");
+		return -1;
+	}
+}
+
+int NA_Synchronize(NeuralModel* model)
+{
+	if (!impl(model)) return -1;
+	return model->model->Synchronize() ? 0 : -1;
+}
+
+void* NA_GetCudaStream(NeuralModel* model)
+{
+	return impl(model) ? model->model->GetCudaStream() : nullptr;
+}
+
+int NA_GetDeviceBlob(NeuralModel* model, void** devicePtr, size_t* bytes)
+{
+	if (!impl(model) || !devicePtr || !bytes) return -1;
+	return impl(model)->GetBlob(devicePtr, bytes) ? 0 : -1;
+}
+
+int NA_CopyStreamState(NeuralModel* model, size_t stream, float* hostOut, size_t capacityFloats)
+{
+	if (!impl(model) || !hostOut) return -1;
+	size_t written = 0;
+	if (!impl(model)->CopyStreamState(stream, hostOut, capacityFloats, &written)) return -1;
+	return (int)written;
+}
+
+int NA_DescribeModelFile(const wchar_t* modelPath, int externalSampleRate, char* out, int capacity)
+{
+	// host-only: runs the same parse / dispatch / packing as a real load and reports what a load would build
+	try
+	{
+		std::filesystem::path path(modelPath);
+		if (!std::filesystem::exists(path)) { nab200::SetLastError("model file not found"); return -1; }
+		std::ifstream f(path, std::ifstream::binary);
+		std::stringstream ss;
+		ss << f.rdbuf();
+		nab200::Json j = nab200::Json::parse(ss.str());
+		const std::string ext = path.extension().string();
+		std::stringstream o;
+		auto describe = [&](nab200::Json& mj, std::stringstream& os)
+		{
+			if (ext == ".nam")
+			{
+				nab200::OversampleNamConfig(mj, externalSampleRate);
+				const std::string arch = mj.at("architecture").as_string();
+				if (arch == "WaveNet")
+				{
+					nab200::WaveNetDesc d = nab200::ParseNamWaveNet(mj);
+					nab200::PackedWaveNet p = nab200::PackWaveNet(d);
+					os << "{\"kind\":\"wavenet\",\"static\":" << (d.isStatic ? "true" : "false") << ",\"receptive_field\":" << d.receptiveField
+					   << ",\"num_weights\":" << d.weights.size() << ",\"packed_floats\":" << p.weights.size() << ",\"state_floats\":" << p.dev.stateStride
+					   << ",\"num_rings\":" << p.dev.numRings << ",\"num_layers\":" << p.dev.numLayers << ",\"max_block\":" << p.dev.maxBlock
+					   << ",\"head_scale\":" << p.dev.headScale << ",\"arrays\":[";
+					for (size_t a = 0; a < d.arrays.size(); a++)
+					{
+						if (a) os << ",";
+						os << "{\"channels\":" << d.arrays[a].channels << ",\"padded\":" << p.dev.arrays[a].C << ",\"head_size\":" << d.arrays[a].headSize
+						   << ",\"head_kernel\":" << d.arrays[a].headKernel << ",\"activation\":" << d.arrays[a].activation << ",\"layers\":" << d.arrays[a].dilations.size() << "}";
+					}
+					os << "],\"ring_lp\":[";
+					for (int r = 0; r < p.dev.numRings; r++) os << (r ? "," : "") << p.dev.ringLp[r];
+					os << "]}";
+					return;
+				}
+				if (arch == "LSTM")
+				{
+					nab200::LstmDesc d = nab200::ParseNamLstm(mj);
+					nab200::PackedLstm p = nab200::PackLstm(d);
+					os << "{\"kind\":\"lstm\",\"static\":" << (d.isStatic ? "true" : "false") << ",\"layers\":" << d.numLayers << ",\"hidden\":" << d.hiddenSize
+					   << ",\"lanes\":" << p.dev.G << ",\"packed_floats\":" << p.weights.size() << ",\"state_floats\":" << p.dev.stateStride << "}";
+					return;
+				}
+				throw std::runtime_error("unsupported model: architecture '" + arch + "'");
+			}
+			nab200::LstmDesc d = nab200::ParseKerasLstm(mj);
+			nab200::PackedLstm p = nab200::PackLstm(d);
+			os << "{\"kind\":\"lstm\",\"static\":" << (d.isStatic ? "true" : "false") << ",\"layers\":" << d.numLayers << ",\"hidden\":" << d.hiddenSize
+			   << ",\"lanes\":" << p.dev.G << ",\"packed_floats\":" << p.weights.size() << ",\"state_floats\":" << p.dev.stateStride << "}";
+		};
+		if (ext == ".nam" && j.at("architecture").as_string() == "SlimmableContainer")
+		{
+			o << "{\"kind\":\"container\",\"submodels\":[";
+			bool first = true;
+			for (nab200::Json& sub : j.obj["config"].obj["submodels"].arr)
+			{
+				if (!first) o << ",";
+				first = false;
+				o << "{\"max_value\":" << sub.at("max_value").as_double() << ",\"model\":";
+				describe(sub.obj["model"], o);
+				o << "}";
+			}
+			o << "]}";
+		}
+		else describe(j, o);
+		return copy_out(o.str(), out, capacity);
+	}
+	catch (const std::exception& e)
+	{
+		nab200::SetLastError(e.what());
+	}
+	catch (...)
+	{
+		nab200::SetLastError("unknown error");
+	}
+	return -1;
+}
+
+int NA_SetOption(const char* name, int value)
+{
+	return name ? nab200::SetOption(name, value) : -1;
+}
+
+}

@@ -1,0 +1,386 @@
+#include "engine.h"
+#include <cstring>
+#include <sstream>
+
+namespace nab200
+{
+	static thread_local std::string g_lastError;
+
+	void SetLastError(const std::string& msg) { g_lastError = msg; }
+	const std::string& LastError() { return g_lastError; }
+
+	Options& GetOptions()
+	{
+		static Options o;
+		return o;
+	}
+
+	int SetOption(const char* name, int value)
+	{
+		Options& o = GetOptions();
+		int prev = -1;
+		if (strcmp(name, "use_tma") == 0) { prev = o.useTma; o.useTma = value; }
+		else if (strcmp(name, "max_grid_ctas") == 0) { prev = o.maxGridCtas; o.maxGridCtas = value; }
+		return prev;
+	}
+
+	bool CudaOk(cudaError_t err, const char* what)
+	{
+		if (err == cudaSuccess) return true;
+		std::stringstream ss;
+		ss << "CUDA error in " << what << ": " << cudaGetErrorName(err) << " (" << cudaGetErrorString(err) << ")";
+		SetLastError(ss.str());
+		return false;
+	}
+
+	// ---- StreamEngine -------------------------------------------------------------------------------------
+	StreamEngine::StreamEngine(int dev) : device(dev) {}
+
+	StreamEngine::~StreamEngine()
+	{
+		if (device >= 0) cudaSetDevice(device);
+		if (pinnedIn) cudaFreeHost(pinnedIn);
+		if (pinnedOut) cudaFreeHost(pinnedOut);
+		if (devIn) cudaFree(devIn);
+		if (devOut) cudaFree(devOut);
+		if (stream) cudaStreamDestroy(stream);
+	}
+
+	bool StreamEngine::Init()
+	{
+		int count = 0;
+		cudaError_t err = cudaGetDeviceCount(&count);
+		if (err != cudaSuccess || count <= 0)
+		{
+			cudaGetLastError();
+			SetLastError(std::string("no CUDA device available (") + cudaGetErrorString(err) + "): neuralaudio-b200 has no CPU fallback");
+			return false;
+		}
+		if (device < 0)
+		{
+			if (!CudaOk(cudaGetDevice(&device), "cudaGetDevice")) return false;
+		}
+		if (device >= count)
+		{
+			SetLastError("requested CUDA device index out of range");
+			return false;
+		}
+		if (!CudaOk(cudaSetDevice(device), "cudaSetDevice")) return false;
+		cudaDeviceProp prop;
+		if (!CudaOk(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties")) return false;
+		if (prop.major < 10)
+		{
+			SetLastError(std::string("device '") + prop.name + "' is not sm_100-class; this library ships sm_100a kernels only");
+			return false;
+		}
+		numSMs = prop.multiProcessorCount;
+		if (!CudaOk(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking), "cudaStreamCreate")) return false;
+		return true;
+	}
+
+	bool StreamEngine::EnsureStaging(size_t floats)
+	{
+		if (floats <= stagingFloats) return true;
+		if (pinnedIn) cudaFreeHost(pinnedIn);
+		if (pinnedOut) cudaFreeHost(pinnedOut);
+		if (devIn) cudaFree(devIn);
+		if (devOut) cudaFree(devOut);
+		pinnedIn = pinnedOut = devIn = devOut = nullptr;
+		stagingFloats = 0;
+		size_t cap = floats < 4096 ? 4096 : floats;
+		if (!CudaOk(cudaMallocHost(&pinnedIn, cap * 4), "cudaMallocHost")) return false;
+		if (!CudaOk(cudaMallocHost(&pinnedOut, cap * 4), "cudaMallocHost")) return false;
+		if (!CudaOk(cudaMalloc(&devIn, cap * 4), "cudaMalloc(staging)")) return false;
+		if (!CudaOk(cudaMalloc(&devOut, cap * 4), "cudaMalloc(staging)")) return false;
+		stagingFloats = cap;
+		return true;
+	}
+
+	static bool IsDevicePointer(const void* p)
+	{
+		cudaPointerAttributes attr;
+		cudaError_t err = cudaPointerGetAttributes(&attr, p);
+		if (err != cudaSuccess)
+		{
+			cudaGetLastError();
+			return false;
+		}
+		return attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged;
+	}
+
+	static bool IsPinnedHost(const void* p)
+	{
+		cudaPointerAttributes attr;
+		cudaError_t err = cudaPointerGetAttributes(&attr, p);
+		if (err != cudaSuccess)
+		{
+			cudaGetLastError();
+			return false;
+		}
+		return attr.type == cudaMemoryTypeHost;
+	}
+
+	bool StreamEngine::Process(const float* in, float* out, size_t S, size_t n, int layout)
+	{
+		if (S == 0 || n == 0) return true;   // n = 0 is a no-op in the reference too
+		if (S > numStreams)
+		{
+			SetLastError("ProcessBatch: numStreams exceeds the allocated stream slots (call SetNumStreams first)");
+			return false;
+		}
+		if (in == nullptr || out == nullptr)
+		{
+			SetLastError("ProcessBatch: null buffer");
+			return false;
+		}
+		if (!CudaOk(cudaSetDevice(device), "cudaSetDevice")) return false;
+		const long long SS = layout == 0 ? (long long)n : 1;
+		const long long FS = layout == 0 ? 1 : (long long)S;
+		const bool inDev = IsDevicePointer(in), outDev = IsDevicePointer(out);
+		if (inDev && outDev) return ProcessDevice(in, out, SS, FS, SS, FS, S, n);
+		if (inDev != outDev)
+		{
+			SetLastError("ProcessBatch: input and output must both be host or both be device memory");
+			return false;
+		}
+		// host path: H2D -> kernels -> D2H, all on the model's stream, then wait (the reference's Process is synchronous)
+		const size_t total = S * n;
+		if (!EnsureStaging(total)) return false;
+		const float* hsrc = in;
+		if (!IsPinnedHost(in))
+		{
+			memcpy(pinnedIn, in, total * 4);
+			hsrc = pinnedIn;
+		}
+		if (!CudaOk(cudaMemcpyAsync(devIn, hsrc, total * 4, cudaMemcpyHostToDevice, stream), "cudaMemcpyAsync(H2D)")) return false;
+		if (!ProcessDevice(devIn, devOut, SS, FS, SS, FS, S, n)) return false;
+		const bool outPinned = IsPinnedHost(out);
+		float* hdst = outPinned ? out : pinnedOut;
+		if (!CudaOk(cudaMemcpyAsync(hdst, devOut, total * 4, cudaMemcpyDeviceToHost, stream), "cudaMemcpyAsync(D2H)")) return false;
+		if (!CudaOk(cudaStreamSynchronize(stream), "cudaStreamSynchronize")) return false;
+		if (!outPinned) memcpy(out, pinnedOut, total * 4);
+		return true;
+	}
+
+	bool StreamEngine::Synchronize()
+	{
+		if (!stream) return true;
+		return CudaOk(cudaStreamSynchronize(stream), "cudaStreamSynchronize");
+	}
+
+	// ---- WaveNetEngine ------------------------------------------------------------------------------------
+	WaveNetEngine::WaveNetEngine(int dev, PackedWaveNet&& p) : StreamEngine(dev), packed(std::move(p)) {}
+
+	WaveNetEngine::~WaveNetEngine()
+	{
+		if (device >= 0) cudaSetDevice(device);
+		if (dBlob) cudaFree(dBlob);
+		if (dState) cudaFree(dState);
+		if (dHeads) cudaFree(dHeads);
+	}
+
+	bool WaveNetEngine::Upload()
+	{
+		const WnModelDev& M = packed.dev;
+		const int C0 = M.arrays[0].C, C1 = M.numArrays > 1 ? M.arrays[1].C : 0;
+		if (!wavenet_variant_supported(C0, C1, M.arrays[0].act))
+		{
+			std::stringstream ss;
+			ss << "unsupported model: no sm_100a WaveNet kernel for channel layout (" << M.arrays[0].realC << ", "
+			   << (M.numArrays > 1 ? M.arrays[1].realC : 0) << ") with activation " << M.arrays[0].act << "; no CPU fallback";
+			SetLastError(ss.str());
+			return false;
+		}
+		weightFloats = (packed.weights.size() + 3) & ~(size_t)3;
+		const size_t blobFloats = weightFloats + (size_t)M.stateStride;
+		if (!CudaOk(cudaMalloc(&dBlob, blobFloats * 4), "cudaMalloc(weights)")) return false;
+		if (!CudaOk(cudaMemsetAsync(dBlob, 0, blobFloats * 4, stream), "cudaMemset")) return false;   // template = zeros until Prewarm()
+		if (!CudaOk(cudaMemcpyAsync(dBlob, packed.weights.data(), packed.weights.size() * 4, cudaMemcpyHostToDevice, stream), "cudaMemcpy(weights)")) return false;
+		return CudaOk(cudaStreamSynchronize(stream), "cudaStreamSynchronize");
+	}
+
+	bool WaveNetEngine::SetNumStreams(size_t S)
+	{
+		if (!CudaOk(cudaSetDevice(device), "cudaSetDevice")) return false;
+		if (!CudaOk(cudaStreamSynchronize(stream), "cudaStreamSynchronize")) return false;
+		if (S != numStreams)
+		{
+			if (dState) cudaFree(dState);
+			if (dHeads) cudaFree(dHeads);
+			dState = nullptr; dHeads = nullptr; numStreams = 0;
+			if (S > 0)
+			{
+				if (!CudaOk(cudaMalloc(&dState, S * (size_t)packed.dev.stateStride * 4), "cudaMalloc(stream state)")) return false;
+				if (!CudaOk(cudaMalloc(&dHeads, S * (size_t)packed.dev.numRings * 4), "cudaMalloc(ring heads)")) { cudaFree(dState); dState = nullptr; return false; }
+			}
+			numStreams = S;
+		}
+		return ResetStreams();
+	}
+
+	bool WaveNetEngine::ResetStreams()
+	{
+		if (numStreams == 0) return true;
+		if (!CudaOk(cudaSetDevice(device), "cudaSetDevice")) return false;
+		if (!CudaOk(state_fill_launch(dState, dBlob + weightFloats, packed.dev.stateStride, (long long)numStreams, stream), "state_fill")) return false;
+		return CudaOk(int_fill_launch(dHeads, 0, (long long)numStreams * packed.dev.numRings, stream), "int_fill");
+	}
+
+	bool WaveNetEngine::Prewarm()
+	{
+		if (!CudaOk(cudaSetDevice(device), "cudaSetDevice")) return false;
+		if (!CudaOk(wavenet_prewarm_launch(packed.dev, dBlob, dBlob + weightFloats, stream), "wavenet_prewarm")) return false;
+		return ResetStreams();
+	}
+
+	bool WaveNetEngine::ProcessDevice(const float* in, float* out, long long inSS, long long inFS, long long outSS, long long outFS, size_t S, size_t n)
+	{
+		const int maxPass = wavenet_max_frames_per_pass(packed.dev.arrays[0].C);
+		const Options& opt = GetOptions();
+		size_t done = 0;
+		while (done < n)
+		{
+			const size_t chunk = (n - done) < (size_t)maxPass ? (n - done) : (size_t)maxPass;
+			WnLaunch a;
+			a.weights = dBlob;
+			a.state = dState;
+			a.heads = dHeads;
+			a.in = in + (long long)done * inFS;
+			a.out = out + (long long)done * outFS;
+			a.inSS = inSS; a.inFS = inFS; a.outSS = outSS; a.outFS = outFS;
+			a.S = (int)S;
+			a.n = (int)chunk;
+			a.numSMs = (opt.maxGridCtas > 0) ? opt.maxGridCtas : numSMs;
+			a.useTma = opt.useTma != 0;
+			a.stream = stream;
+			if (!CudaOk(wavenet_launch(packed.dev, a), "wavenet_fwd_kernel launch")) return false;
+			done += chunk;
+		}
+		return true;
+	}
+
+	bool WaveNetEngine::CopyStreamState(size_t s, float* hostOut, size_t capFloats, size_t* written)
+	{
+		if (s >= numStreams) { SetLastError("CopyStreamState: stream out of range"); return false; }
+		const size_t nState = (size_t)packed.dev.stateStride, nHeads = (size_t)packed.dev.numRings;
+		if (capFloats < nState + nHeads) { SetLastError("CopyStreamState: buffer too small"); return false; }
+		if (!CudaOk(cudaSetDevice(device), "cudaSetDevice")) return false;
+		if (!CudaOk(cudaStreamSynchronize(stream), "cudaStreamSynchronize")) return false;
+		if (!CudaOk(cudaMemcpy(hostOut, dState + s * nState, nState * 4, cudaMemcpyDeviceToHost), "cudaMemcpy(state)")) return false;
+		if (!CudaOk(cudaMemcpy(hostOut + nState, dHeads + s * nHeads, nHeads * 4, cudaMemcpyDeviceToHost), "cudaMemcpy(heads)")) return false;
+		*written = nState + nHeads;
+		return true;
+	}
+
+	bool WaveNetEngine::GetBlob(void** devPtr, size_t* bytes)
+	{
+		*devPtr = dBlob;
+		*bytes = (weightFloats + (size_t)packed.dev.stateStride) * 4;
+		return true;
+	}
+
+	// ---- LstmEngine ---------------------------------------------------------------------------------------
+	LstmEngine::LstmEngine(int dev, PackedLstm&& p) : StreamEngine(dev), packed(std::move(p)) {}
+
+	LstmEngine::~LstmEngine()
+	{
+		if (device >= 0) cudaSetDevice(device);
+		if (dBlob) cudaFree(dBlob);
+		if (dState) cudaFree(dState);
+	}
+
+	bool LstmEngine::Upload()
+	{
+		if (!lstm_variant_supported(packed.dev.L, packed.dev.G))
+		{
+			SetLastError("unsupported model: no sm_100a LSTM kernel for this (layers, hidden size); no CPU fallback");
+			return false;
+		}
+		weightFloats = (packed.weights.size() + 3) & ~(size_t)3;
+		const size_t blobFloats = weightFloats + (size_t)packed.dev.stateStride;
+		if (!CudaOk(cudaMalloc(&dBlob, blobFloats * 4), "cudaMalloc(weights)")) return false;
+		if (!CudaOk(cudaMemsetAsync(dBlob, 0, blobFloats * 4, stream), "cudaMemset")) return false;
+		if (!CudaOk(cudaMemcpyAsync(dBlob, packed.weights.data(), packed.weights.size() * 4, cudaMemcpyHostToDevice, stream), "cudaMemcpy(weights)")) return false;
+		// template = the file's (h0, c0) (LSTM.h:50-55); Prewarm() advances it together with the slots
+		if (!CudaOk(cudaMemcpyAsync(dBlob + weightFloats, packed.initState.data(), packed.initState.size() * 4, cudaMemcpyHostToDevice, stream), "cudaMemcpy(state)")) return false;
+		return CudaOk(cudaStreamSynchronize(stream), "cudaStreamSynchronize");
+	}
+
+	bool LstmEngine::SetNumStreams(size_t S)
+	{
+		if (!CudaOk(cudaSetDevice(device), "cudaSetDevice")) return false;
+		if (!CudaOk(cudaStreamSynchronize(stream), "cudaStreamSynchronize")) return false;
+		if (S != numStreams)
+		{
+			if (dState) cudaFree(dState);
+			dState = nullptr; numStreams = 0;
+			if (S > 0 && !CudaOk(cudaMalloc(&dState, S * (size_t)packed.dev.stateStride * 4), "cudaMalloc(stream state)")) return false;
+			numStreams = S;
+		}
+		return ResetStreams();
+	}
+
+	bool LstmEngine::ResetStreams()
+	{
+		if (numStreams == 0) return true;
+		if (!CudaOk(cudaSetDevice(device), "cudaSetDevice")) return false;
+		return CudaOk(state_fill_launch(dState, dBlob + weightFloats, packed.dev.stateStride, (long long)numStreams, stream), "state_fill");
+	}
+
+	bool LstmEngine::Prewarm()
+	{
+		// InternalLSTMModelT::Prewarm (InternalModel.h:368-371): 2048 zero samples from the CURRENT state, for every slot
+		// and for the template (so slots created later start where a freshly prewarmed model would)
+		if (!CudaOk(cudaSetDevice(device), "cudaSetDevice")) return false;
+		LstmLaunch a;
+		memset(&a, 0, sizeof(a));
+		a.weights = dBlob;
+		a.in = nullptr; a.out = nullptr;
+		a.n = 2048;
+		a.zeroInput = true;
+		a.stream = stream;
+		a.state = dBlob + weightFloats;
+		a.S = 1;
+		if (!CudaOk(lstm_launch(packed.dev, a), "lstm prewarm")) return false;
+		if (numStreams > 0)
+		{
+			a.state = dState;
+			a.S = (int)numStreams;
+			if (!CudaOk(lstm_launch(packed.dev, a), "lstm prewarm")) return false;
+		}
+		return true;
+	}
+
+	bool LstmEngine::ProcessDevice(const float* in, float* out, long long inSS, long long inFS, long long outSS, long long outFS, size_t S, size_t n)
+	{
+		LstmLaunch a;
+		a.weights = dBlob;
+		a.state = dState;
+		a.in = in; a.out = out;
+		a.inSS = inSS; a.inFS = inFS; a.outSS = outSS; a.outFS = outFS;
+		a.S = (int)S;
+		a.n = (int)n;
+		a.zeroInput = false;
+		a.stream = stream;
+		return CudaOk(lstm_launch(packed.dev, a), "lstm_fwd_kernel launch");
+	}
+
+	bool LstmEngine::CopyStreamState(size_t s, float* hostOut, size_t capFloats, size_t* written)
+	{
+		if (s >= numStreams) { SetLastError("CopyStreamState: stream out of range"); return false; }
+		const size_t nState = (size_t)packed.dev.stateStride;
+		if (capFloats < nState) { SetLastError("CopyStreamState: buffer too small"); return false; }
+		if (!CudaOk(cudaSetDevice(device), "cudaSetDevice")) return false;
+		if (!CudaOk(cudaStreamSynchronize(stream), "cudaStreamSynchronize")) return false;
+		if (!CudaOk(cudaMemcpy(hostOut, dState + s * nState, nState * 4, cudaMemcpyDeviceToHost), "cudaMemcpy(state)")) return false;
+		*written = nState;
+		return true;
+	}
+
+	bool LstmEngine::GetBlob(void** devPtr, size_t* bytes)
+	{
+		*devPtr = dBlob;
+		*bytes = (weightFloats + (size_t)packed.dev.stateStride) * 4;
+		return true;
+	}
+}

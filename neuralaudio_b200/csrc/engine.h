@@ -1,0 +1,115 @@
+// Device-side owners of one model's weights and of the per-stream state of S stream slots.
+// This is the layer SURVEY.md section 1 calls "a new thin layer under L2": it replaces the state that the
+// reference keeps inside each model object (one stream per object) with S slots resident in HBM.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstddef>
+#include <string>
+#include "model_desc.h"
+#include "na_kernels.h"
+
+namespace nab200
+{
+	void SetLastError(const std::string& msg);
+	const std::string& LastError();
+
+	struct Options
+	{
+		int useTma = 1;         // stage history windows with cp.async.bulk + mbarrier (0: plain loads, debugging aid)
+		int maxGridCtas = 0;    // 0: one CTA per SM
+	};
+	Options& GetOptions();
+	int SetOption(const char* name, int value);
+
+	bool CudaOk(cudaError_t err, const char* what);
+
+	class StreamEngine
+	{
+	public:
+		StreamEngine(int device);
+		virtual ~StreamEngine();
+
+		bool Init();   // picks the device, creates the stream; false (with LastError) when there is no usable GPU
+
+		virtual bool SetNumStreams(size_t numStreams) = 0;
+		virtual bool Prewarm() = 0;        // NeuralModel::Prewarm semantics for every slot
+		virtual bool ResetStreams() = 0;   // refill every slot from the template
+		virtual size_t StateBytesPerStream() const = 0;
+		virtual bool CopyStreamState(size_t stream, float* hostOut, size_t capFloats, size_t* written) = 0;
+		virtual bool GetBlob(void** devPtr, size_t* bytes) = 0;
+
+		// host or device pointers; layout 0 = [stream][frame], 1 = [frame][stream]
+		bool Process(const float* in, float* out, size_t numStreams, size_t numFrames, int layout);
+		bool Synchronize();
+
+		size_t NumStreams() const { return numStreams; }
+		int Device() const { return device; }
+		cudaStream_t Stream() const { return stream; }
+
+	protected:
+		// device pointers, element (s, f) at p[s*SS + f*FS]
+		virtual bool ProcessDevice(const float* in, float* out, long long inSS, long long inFS, long long outSS, long long outFS,
+			size_t numStreams, size_t numFrames) = 0;
+		bool EnsureStaging(size_t floats);
+
+		int device = -1;
+		int numSMs = 148;
+		cudaStream_t stream = nullptr;
+		size_t numStreams = 0;
+		// staging for host-pointer calls
+		float* pinnedIn = nullptr;
+		float* pinnedOut = nullptr;
+		float* devIn = nullptr;
+		float* devOut = nullptr;
+		size_t stagingFloats = 0;
+	};
+
+	class WaveNetEngine : public StreamEngine
+	{
+	public:
+		WaveNetEngine(int device, PackedWaveNet&& packed);
+		~WaveNetEngine() override;
+		bool Upload();
+		bool SetNumStreams(size_t numStreams) override;
+		bool Prewarm() override;
+		bool ResetStreams() override;
+		size_t StateBytesPerStream() const override { return (size_t)packed.dev.stateStride * 4 + (size_t)packed.dev.numRings * 4; }
+		bool CopyStreamState(size_t stream, float* hostOut, size_t capFloats, size_t* written) override;
+		bool GetBlob(void** devPtr, size_t* bytes) override;
+
+	protected:
+		bool ProcessDevice(const float* in, float* out, long long inSS, long long inFS, long long outSS, long long outFS, size_t numStreams,
+			size_t numFrames) override;
+
+	private:
+		PackedWaveNet packed;
+		float* dBlob = nullptr;      // [weights | template], one allocation
+		size_t weightFloats = 0;     // padded to a multiple of 4
+		float* dState = nullptr;     // [S][stateStride]
+		int* dHeads = nullptr;       // [S][numRings]
+	};
+
+	class LstmEngine : public StreamEngine
+	{
+	public:
+		LstmEngine(int device, PackedLstm&& packed);
+		~LstmEngine() override;
+		bool Upload();
+		bool SetNumStreams(size_t numStreams) override;
+		bool Prewarm() override;
+		bool ResetStreams() override;
+		size_t StateBytesPerStream() const override { return (size_t)packed.dev.stateStride * 4; }
+		bool CopyStreamState(size_t stream, float* hostOut, size_t capFloats, size_t* written) override;
+		bool GetBlob(void** devPtr, size_t* bytes) override;
+
+	protected:
+		bool ProcessDevice(const float* in, float* out, long long inSS, long long inFS, long long outSS, long long outFS, size_t numStreams,
+			size_t numFrames) override;
+
+	private:
+		PackedLstm packed;
+		float* dBlob = nullptr;      // [weights | template state]
+		size_t weightFloats = 0;
+		float* dState = nullptr;     // [S][stateStride]
+	};
+}

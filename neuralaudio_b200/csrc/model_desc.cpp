@@ -1,0 +1,513 @@
+#include "model_desc.h"
+#include <cmath>
+#include <sstream>
+
+namespace nab200
+{
+	// the reference's official architecture tables, NeuralModel.cpp:71-76
+	static const std::vector<int> kStdDilations = { 1, 2, 4, 8, 16, 32, 64, 128, 256, 512 };
+	static const std::vector<int> kLiteDilations = { 1, 2, 4, 8, 16, 32, 64 };
+	static const std::vector<int> kLiteDilations2 = { 128, 256, 512, 1, 2, 4, 8, 16, 32, 64, 128, 256, 512 };
+	static const std::vector<int> kA2KernelSizes = { 6, 6, 6, 6, 6, 6, 6, 6, 6, 6, 6, 6, 6, 6, 15, 15, 6, 6, 6, 6, 6, 6, 6 };
+	static const std::vector<int> kA2Dilations = { 1, 3, 7, 17, 41, 101, 239, 1, 3, 7, 17, 41, 101, 239, 1, 13, 1, 3, 7, 17, 41, 101, 239 };
+
+	static std::vector<int> IntList(const Json& j)
+	{
+		std::vector<int> v;
+		for (size_t i = 0; i < j.size(); i++) v.push_back(j.at(i).as_int());
+		return v;
+	}
+
+	static bool SameSequence(const Json& j, const std::vector<int>& ref)
+	{
+		if (!j.is_array() || j.size() != ref.size()) return false;
+		for (size_t i = 0; i < ref.size(); i++)
+			if (!j.at(i).is_number() || j.at(i).as_double() != (double)ref[i]) return false;
+		return true;
+	}
+
+	void OversampleNamConfig(Json& modelJson, int externalSampleRate)
+	{
+		if (modelJson.at("architecture").as_string() != "WaveNet") return;
+		int modelSampleRate = 48000;
+		if (modelJson.contains("sample_rate") && modelJson.at("sample_rate").is_number())
+			modelSampleRate = (int)modelJson.at("sample_rate").as_float();
+		if (modelSampleRate == externalSampleRate) return;
+		if (modelSampleRate <= 0 || (externalSampleRate % modelSampleRate) != 0) return;   // not an integer multiple
+		const int factor = externalSampleRate / modelSampleRate;
+		Json& layers = modelJson.obj["config"].obj["layers"];
+		for (Json& layer : layers.arr)
+		{
+			for (Json& dil : layer.obj["dilations"].arr)
+			{
+				const int v = dil.as_int() * factor;
+				dil = Json();
+				dil.type = Json::Int;
+				dil.i = v;
+			}
+			if (layer.contains("head"))
+			{
+				Json hd;
+				hd.type = Json::Int;
+				hd.i = factor;
+				layer.obj["head"].obj["head_dilation"] = hd;
+			}
+		}
+	}
+
+	bool NamIsA2(const std::string& version)
+	{
+		int major = 0, minor = 0, patch = 0;
+		char dot;
+		std::stringstream ss(version);
+		ss >> major >> dot >> minor >> dot >> patch;
+		return (major > 0) || (minor > 5) || ((minor == 5) && (patch > 4));
+	}
+
+	static bool IsActive(const Json& j, const char* name)
+	{
+		if (!j.contains(name)) return true;
+		const Json& v = j.at(name);
+		return v.is_object() ? v.value_bool("active", false) : false;
+	}
+
+	static bool HasNonNull(const Json& j, const char* name)
+	{
+		return j.contains(name) && !j.at(name).is_null();
+	}
+
+	bool NamIsA2Standard(const Json& modelJson)
+	{
+		if (!modelJson.contains("architecture") || !modelJson.at("architecture").is_string()) return false;
+		if (modelJson.at("architecture").as_string() != "WaveNet") return false;
+		if (!modelJson.contains("config")) return false;
+		const Json& config = modelJson.at("config");
+		if (HasNonNull(config, "head")) return false;
+		if (config.contains("condition_dsp")) return false;
+		if (config.value_int("in_channels", 1) != 1) return false;
+		if (!config.contains("layers") || config.at("layers").size() != 1) return false;
+		const Json& lc = config.at("layers").at(0);
+		if (lc.value_int("input_size", 0) != 1) return false;
+		if (lc.value_int("condition_size", 0) != 1) return false;
+		const int channels = lc.value_int("channels", 0);
+		if (channels != 3 && channels != 8) return false;
+		if (lc.value_int("bottleneck", channels) != channels) return false;
+		if (!lc.contains("kernel_sizes") || !SameSequence(lc.at("kernel_sizes"), kA2KernelSizes)) return false;
+		if (!lc.contains("dilations") || !SameSequence(lc.at("dilations"), kA2Dilations)) return false;
+		if (!lc.contains("activation")) return false;
+		for (const Json& act : lc.at("activation").arr)
+		{
+			if (!act.contains("type") || !act.at("type").is_string() || act.at("type").as_string() != "LeakyReLU") return false;
+			if (std::fabs((float)act.value_double("negative_slope", 0.01) - 0.01f) > 1e-5f) return false;
+		}
+		if (lc.contains("secondary_activation"))
+			for (const Json& a : lc.at("secondary_activation").arr)
+				if (!a.is_null()) return false;
+		if (lc.contains("gating_mode"))
+			for (const Json& g : lc.at("gating_mode").arr)
+				if (!g.is_null() && !(g.is_string() && g.as_string() == "none")) return false;
+		if (!lc.contains("head")) return false;
+		const Json& head = lc.at("head");
+		if (head.value_int("out_channels", 1) != 1) return false;
+		if (head.value_int("kernel_size", 16) != 16) return false;
+		if (head.value_int("head_dilation", 1) != 1) return false;
+		if (!head.value_bool("bias", true)) return false;
+		if (!IsActive(lc, "layer1x1")) return false;
+		if (lc.contains("layer1x1") && lc.at("layer1x1").value_int("groups", 1) != 1) return false;
+		for (const char* key : { "head1x1", "conv_pre_film", "conv_post_film", "input_mixin_pre_film", "input_mixin_post_film",
+				 "activation_pre_film", "activation_post_film", "layer1x1_post_film", "head1x1_post_film" })
+			if (IsActive(lc, key)) return false;
+		if (lc.value_int("groups_input", 1) != 1) return false;
+		if (lc.value_int("groups_input_mixin", 1) != 1) return false;
+		if (HasNonNull(lc, "slimmable")) return false;
+		return true;
+	}
+
+	static std::vector<float> FloatList(const Json& j)
+	{
+		std::vector<float> v;
+		v.reserve(j.size());
+		for (const Json& e : j.arr) v.push_back(e.as_float());
+		return v;
+	}
+
+	static size_t ExpectedWaveNetWeights(const WaveNetDesc& d)
+	{
+		size_t n = 1;   // head scale
+		for (const auto& a : d.arrays)
+		{
+			n += (size_t)a.channels * a.inputSize;
+			for (size_t l = 0; l < a.dilations.size(); l++)
+				n += (size_t)a.channels * a.channels * a.kernelSizes[l] + a.channels + a.channels + (size_t)a.channels * a.channels + a.channels;
+			n += (size_t)a.headSize * a.channels * a.headKernel + (a.headBias ? a.headSize : 0);
+		}
+		return n;
+	}
+
+	WaveNetDesc ParseNamWaveNet(const Json& modelJson)
+	{
+		WaveNetDesc d;
+		const std::string version = modelJson.at("version").as_string();
+		const Json& config = modelJson.at("config");
+		const Json& layers = config.at("layers");
+
+		// NeuralModel.cpp:365-380: A2-generation files that are not the "standard" A2 need NAM Core in the reference
+		if (NamIsA2(version) && !NamIsA2Standard(modelJson))
+			throw std::runtime_error("unsupported model: A2-generation WaveNet with non-standard features (the reference loads it with NAM Core; "
+									 "this build has no CPU fallback)");
+
+		if (layers.size() == 1 && layers.at(0).contains("kernel_sizes"))
+		{
+			// NeuralModel.cpp:389-421: the static A2 types (3 or 8 channels, LeakyReLU, head K=16 with bias)
+			const Json& lc = layers.at(0);
+			if (!SameSequence(lc.at("dilations"), kA2Dilations))
+				throw std::runtime_error("unsupported model: A2 WaveNet with non-standard dilations (oversampled A2 is NAM-Core-only in the reference)");
+			const int ch = lc.at("channels").as_int();
+			if (ch != 3 && ch != 8) throw std::runtime_error("unsupported model: A2 WaveNet must have 3 or 8 channels");
+			WaveNetArrayDesc a;
+			a.inputSize = 1; a.channels = ch; a.headSize = 1; a.headKernel = 16; a.headBias = true; a.activation = 1;
+			a.kernelSizes = kA2KernelSizes;
+			a.dilations = kA2Dilations;
+			d.arrays.push_back(a);
+			d.isStatic = true;
+		}
+		else
+		{
+			for (size_t i = 0; i < layers.size(); i++)
+			{
+				const Json& lc = layers.at(i);
+				WaveNetArrayDesc a;
+				a.inputSize = lc.at("input_size").as_int();
+				if (lc.value_int("condition_size", 1) != 1) throw std::runtime_error("unsupported model: WaveNet condition_size != 1");
+				a.channels = lc.at("channels").as_int();
+				a.headSize = lc.at("head_size").as_int();
+				a.headKernel = 1;
+				a.headBias = lc.at("head_bias").as_bool();
+				a.activation = 0;   // the Internal path is Tanh for every A1-style file (InternalModel.h:152-159, WaveNetDynamic.h:236)
+				if (lc.contains("gated") && lc.at("gated").as_bool()) throw std::runtime_error("unsupported model: gated WaveNet");
+				if (lc.contains("activation") && lc.at("activation").is_string() && lc.at("activation").as_string() != "Tanh")
+					throw std::runtime_error("unsupported model: WaveNet activation " + lc.at("activation").as_string());
+				a.dilations = IntList(lc.at("dilations"));
+				a.kernelSizes.assign(a.dilations.size(), lc.at("kernel_size").as_int());
+				d.arrays.push_back(a);
+			}
+			// NeuralModel.cpp:423-464: official A1 shapes
+			if (d.arrays.size() == 2 && !d.arrays[0].headBias && d.arrays[1].headBias && d.arrays[0].kernelSizes.size() > 0)
+			{
+				const Json& l0 = layers.at(0);
+				const Json& l1 = layers.at(1);
+				bool official = false;
+				if (d.arrays[0].channels == 16) official = SameSequence(l0.at("dilations"), kStdDilations) && SameSequence(l1.at("dilations"), kStdDilations);
+				else official = SameSequence(l0.at("dilations"), kLiteDilations) && SameSequence(l1.at("dilations"), kLiteDilations2);
+				const int c = d.arrays[0].channels, h = d.arrays[0].headSize;
+				const bool shape = (c == 16 && h == 8) || (c == 12 && h == 6) || (c == 8 && h == 4) || (c == 4 && h == 2);
+				d.isStatic = official && shape && l0.at("kernel_size").as_int() == 3 && l1.at("kernel_size").as_int() == 3;
+			}
+		}
+
+		// structural checks the kernels rely on
+		if (d.arrays.empty() || d.arrays.size() > (size_t)kMaxArrays) throw std::runtime_error("unsupported model: WaveNet must have 1 or 2 layer arrays");
+		size_t totalLayers = 0;
+		for (size_t a = 0; a < d.arrays.size(); a++)
+		{
+			const auto& A = d.arrays[a];
+			if (A.dilations.empty()) throw std::runtime_error("unsupported model: empty layer array");
+			if (A.channels < 1 || A.channels > 16) throw std::runtime_error("unsupported model: WaveNet channels must be 1..16");
+			if (a == 0 && A.inputSize != 1) throw std::runtime_error("unsupported model: first layer array input_size != 1");
+			if (a > 0 && A.inputSize != d.arrays[a - 1].channels) throw std::runtime_error("malformed model: layer array input_size does not match previous channels");
+			if (a + 1 < d.arrays.size() && A.headSize != d.arrays[a + 1].channels) throw std::runtime_error("malformed model: head_size does not match next array's channels");
+			if (a + 1 == d.arrays.size() && A.headSize != 1) throw std::runtime_error("unsupported model: final head_size != 1");
+			if (a + 1 < d.arrays.size() && A.headKernel != 1) throw std::runtime_error("unsupported model: head kernel > 1 on a non-final array");
+			for (size_t l = 0; l < A.dilations.size(); l++)
+				if (A.kernelSizes[l] < 1 || A.dilations[l] < 1) throw std::runtime_error("malformed model: kernel size / dilation < 1");
+			totalLayers += A.dilations.size();
+		}
+		if (totalLayers > (size_t)kMaxLayers) throw std::runtime_error("unsupported model: more than 32 WaveNet layers");
+
+		d.weights = FloatList(modelJson.at("weights"));
+		const size_t expect = ExpectedWaveNetWeights(d);
+		if (expect != d.weights.size())
+		{
+			// same wording as WaveNetModelT::SetWeights, WaveNet.h:704-709
+			std::stringstream str;
+			str << "Wrong number of weights. Expected " << expect << " but got " << d.weights.size();
+			throw std::runtime_error(str.str());
+		}
+		d.receptiveField = 0;
+		for (const auto& A : d.arrays)
+		{
+			for (size_t l = 0; l < A.dilations.size(); l++) d.receptiveField += (A.kernelSizes[l] - 1) * A.dilations[l];
+			d.receptiveField += (A.headKernel - 1);
+		}
+		return d;
+	}
+
+	static bool IsStaticLstmShape(int layers, int hidden)
+	{
+		// NeuralModel.cpp:30-38 (BUILD_INTERNAL_STATIC_LSTM set, the CI configuration)
+		if (layers == 1) return hidden == 8 || hidden == 12 || hidden == 16 || hidden == 24;
+		if (layers == 2) return hidden == 8 || hidden == 12 || hidden == 16;
+		return false;
+	}
+
+	LstmDesc ParseNamLstm(const Json& modelJson)
+	{
+		LstmDesc d;
+		const Json& config = modelJson.at("config");
+		d.numLayers = config.at("num_layers").as_int();
+		d.hiddenSize = config.at("hidden_size").as_int();
+		if (config.value_int("input_size", 1) != 1) throw std::runtime_error("unsupported model: LSTM input_size != 1");
+		if (d.numLayers < 1 || d.numLayers > 2) throw std::runtime_error("unsupported model: LSTM num_layers must be 1 or 2");
+		if (d.hiddenSize < 1 || d.hiddenSize > 32) throw std::runtime_error("unsupported model: LSTM hidden_size must be 1..32");
+		const std::vector<float> w = FloatList(modelJson.at("weights"));
+		const int H = d.hiddenSize;
+		size_t expect = (size_t)H + 1;
+		for (int l = 0; l < d.numLayers; l++)
+		{
+			const int I = l == 0 ? 1 : H;
+			expect += (size_t)4 * H * (I + H) + 4 * H + 2 * H;
+		}
+		if (expect != w.size())
+		{
+			std::stringstream str;
+			str << "Wrong number of weights. Expected " << expect << " but got " << w.size();
+			throw std::runtime_error(str.str());
+		}
+		// LSTMLayerT::SetNAMWeights, LSTM.h:42-56
+		size_t p = 0;
+		for (int l = 0; l < d.numLayers; l++)
+		{
+			LstmLayerWeights Ly;
+			Ly.inputSize = l == 0 ? 1 : H;
+			const size_t nW = (size_t)4 * H * (Ly.inputSize + H);
+			Ly.W.assign(w.begin() + p, w.begin() + p + nW); p += nW;
+			Ly.b.assign(w.begin() + p, w.begin() + p + 4 * H); p += 4 * H;
+			Ly.h0.assign(w.begin() + p, w.begin() + p + H); p += H;
+			Ly.c0.assign(w.begin() + p, w.begin() + p + H); p += H;
+			d.layers.push_back(Ly);
+		}
+		d.headW.assign(w.begin() + p, w.begin() + p + H); p += H;
+		d.headB = w[p];
+		d.isStatic = IsStaticLstmShape(d.numLayers, H);
+		return d;
+	}
+
+	static void Flatten(const Json& j, std::vector<float>& out)
+	{
+		// InternalModel.h:277-295 FlattenWeights
+		if (j.is_array())
+			for (const Json& e : j.arr) Flatten(e, out);
+		else
+			out.push_back(j.as_float());
+	}
+
+	LstmDesc ParseKerasLstm(const Json& modelJson)
+	{
+		// InternalLSTMModelT::CreateModelFromKerasJson (InternalModel.h:297-356) + LSTMLayerT::SetWeights (LSTM.h:58-85)
+		LstmDesc d;
+		const Json& layers = modelJson.at("layers");
+		const size_t numLayers = layers.size();
+		if (numLayers < 2) throw std::runtime_error("unsupported model: keras model needs an lstm and a dense layer");
+		const Json& last = layers.at(numLayers - 1);
+		if (last.at("type").as_string() != "dense") throw std::runtime_error("unsupported model: keras model must end in a dense layer");
+		d.numLayers = (int)numLayers - 1;
+		const Json& shape = layers.at(0).at("shape");
+		d.hiddenSize = shape.at(shape.size() - 1).as_int();
+		if (d.numLayers > 2) throw std::runtime_error("unsupported model: keras LSTM with more than 2 layers");
+		if (d.hiddenSize < 1 || d.hiddenSize > 32) throw std::runtime_error("unsupported model: LSTM hidden_size must be 1..32");
+		const int H = d.hiddenSize;
+		for (int l = 0; l < d.numLayers; l++)
+			if (layers.at(l).at("type").as_string() != "lstm")
+				throw std::runtime_error("unsupported model: keras layer type '" + layers.at(l).at("type").as_string() + "' (the reference runs it on RTNeural; no CPU fallback here)");
+		Flatten(last.at("weights").at(0), d.headW);
+		if ((int)d.headW.size() != H) throw std::runtime_error("malformed model: dense head size mismatch");
+		d.headB = last.at("weights").at(1).at(0).as_float();
+		for (int l = 0; l < d.numLayers; l++)
+		{
+			const Json& layer = layers.at(l);
+			LstmLayerWeights Ly;
+			Ly.inputSize = l == 0 ? 1 : H;
+			std::vector<float> kernel, recurrent, bias;
+			Flatten(layer.at("weights").at(0), kernel);
+			Flatten(layer.at("weights").at(1), recurrent);
+			Flatten(layer.at("weights").at(2), bias);
+			const int I = Ly.inputSize, cols = I + H;
+			if ((int)kernel.size() != I * 4 * H || (int)recurrent.size() != H * 4 * H || (int)bias.size() != 4 * H)
+				throw std::runtime_error("malformed model: keras lstm weight shapes");
+			Ly.W.assign((size_t)4 * H * cols, 0.0f);
+			size_t it = 0;
+			for (int j = 0; j < I; j++)
+				for (int i = 0; i < 4 * H; i++) Ly.W[(size_t)i * cols + j] = kernel[it++];
+			it = 0;
+			for (int j = 0; j < H; j++)
+				for (int i = 0; i < 4 * H; i++) Ly.W[(size_t)i * cols + j + I] = recurrent[it++];
+			Ly.b = bias;
+			Ly.h0.assign(H, 0.0f);
+			Ly.c0.assign(H, 0.0f);
+			d.layers.push_back(Ly);
+		}
+		// the reference only has static keras definitions for one layer (NeuralModel.cpp:537-551)
+		d.isStatic = d.numLayers == 1 && IsStaticLstmShape(1, H);
+		return d;
+	}
+
+	int PadChannels(int c)
+	{
+		if (c <= 2) return 2;
+		if (c <= 4) return 4;
+		if (c <= 8) return 8;
+		if (c <= 12) return 12;
+		return 16;
+	}
+
+	static int Align4(int v) { return (v + 3) & ~3; }
+
+	PackedWaveNet PackWaveNet(const WaveNetDesc& desc)
+	{
+		PackedWaveNet P;
+		WnModelDev& M = P.dev;
+		memset(&M, 0, sizeof(M));
+		M.numArrays = (int)desc.arrays.size();
+		const float* w = desc.weights.data();
+		int layerIdx = 0, ringIdx = 0, ringOff = 0;
+
+		for (int a = 0; a < M.numArrays; a++)
+		{
+			const WaveNetArrayDesc& A = desc.arrays[a];
+			WnArray& DA = M.arrays[a];
+			const int C = A.channels, CP = PadChannels(C);
+			const int last = a + 1 == M.numArrays;
+			const int inC = A.inputSize, inCP = a == 0 ? 1 : PadChannels(inC);
+			const int H = A.headSize, HP = last ? 1 : PadChannels(H);
+			const int nL = (int)A.dilations.size();
+			DA.C = CP; DA.inC = inCP; DA.H = HP; DA.Kh = A.headKernel; DA.act = A.activation;
+			DA.firstLayer = layerIdx; DA.numLayers = nL; DA.realC = C; DA.realH = H;
+
+			// file order (WaveNet.h:570-580): rechannel, layers..., head
+			const float* wRe = w; w += (size_t)C * inC;
+			std::vector<const float*> wLayer(nL);
+			for (int l = 0; l < nL; l++)
+			{
+				wLayer[l] = w;
+				w += (size_t)C * C * A.kernelSizes[l] + C + C + (size_t)C * C + C;
+			}
+			const float* wHead = w; w += (size_t)H * C * A.headKernel + (A.headBias ? H : 0);
+
+			for (int l = 0; l < nL; l++)
+			{
+				WnLayer& L = M.layers[layerIdx];
+				const int K = A.kernelSizes[l], d = A.dilations[l];
+				L.K = K; L.d = d; L.array = a;
+				L.Lp = Align4((K - 1) * d);
+				if (L.Lp == 0) L.Lp = 4;
+				L.ringOff = ringOff; L.ringIdx = ringIdx;
+				M.ringLp[ringIdx] = L.Lp;
+				ringOff += CP * L.Lp; ringIdx++;
+				L.flags = 0;
+				if (l == 0) L.flags |= kFirstInArray;
+				if (l == nL - 1) L.flags |= kLastInArray;
+				// NeedOutput=false only for the last layer of the last array of a multi-array model (WaveNet.h:486,785)
+				if (!(last && M.numArrays > 1 && l == nL - 1)) L.flags |= kNeedOutput;
+
+				// block layout (na_device.h)
+				int off = 0;
+				const int oConvW = off; off += K * CP * CP;
+				L.oConvB = off; off += Align4(CP);
+				L.oMix = off; off += Align4(CP);
+				L.oOneW = off; off += Align4(CP * CP);
+				L.oOneB = off; off += Align4(CP);
+				L.oRe = off; if (l == 0) off += Align4(inCP * CP);
+				L.oHeadW = off; if (l == nL - 1) off += Align4(A.headKernel * CP * HP);
+				L.oHeadB = off; if (l == nL - 1) off += Align4(HP);
+				L.wSize = Align4(off);
+				L.wOff = (int)P.weights.size();
+				P.weights.resize(P.weights.size() + L.wSize, 0.0f);
+				float* blk = P.weights.data() + L.wOff;
+				if (L.wSize > M.maxBlock) M.maxBlock = L.wSize;
+
+				const float* src = wLayer[l];
+				// conv: file [out][in][k] (WaveNet.h:99-105) -> [k][in][out]
+				for (int i = 0; i < C; i++)
+					for (int j = 0; j < C; j++)
+						for (int k = 0; k < K; k++) blk[oConvW + (k * CP + j) * CP + i] = *src++;
+				for (int i = 0; i < C; i++) blk[L.oConvB + i] = *src++;
+				for (int i = 0; i < C; i++) blk[L.oMix + i] = *src++;          // mix-in [C][1]
+				for (int i = 0; i < C; i++)
+					for (int j = 0; j < C; j++) blk[L.oOneW + j * CP + i] = *src++;   // 1x1 file [out][in] -> [in][out]
+				for (int i = 0; i < C; i++) blk[L.oOneB + i] = *src++;
+				if (l == 0)
+					for (int i = 0; i < C; i++)
+						for (int j = 0; j < inC; j++) blk[L.oRe + j * CP + i] = wRe[i * inC + j];   // rechannel file [out][in]
+				if (l == nL - 1)
+				{
+					const float* hs = wHead;
+					for (int i = 0; i < H; i++)
+						for (int j = 0; j < C; j++)
+							for (int k = 0; k < A.headKernel; k++) blk[L.oHeadW + (k * CP + j) * HP + i] = *hs++;   // file [H][C][Kh]
+					if (A.headBias)
+						for (int i = 0; i < H; i++) blk[L.oHeadB + i] = *hs++;
+				}
+				layerIdx++;
+			}
+			if (A.headKernel > 1)
+			{
+				DA.headLp = Align4(A.headKernel - 1);
+				DA.headRingOff = ringOff;
+				DA.headRingIdx = ringIdx;
+				M.ringLp[ringIdx] = DA.headLp;
+				ringOff += CP * DA.headLp;
+				ringIdx++;
+			}
+		}
+		M.headScale = *w;   // the LAST weight (WaveNet.h:718), not config.head_scale
+		M.numLayers = layerIdx;
+		M.numRings = ringIdx;
+		M.stateStride = Align4(ringOff);
+		return P;
+	}
+
+	PackedLstm PackLstm(const LstmDesc& desc)
+	{
+		PackedLstm P;
+		LstmModelDev& M = P.dev;
+		memset(&M, 0, sizeof(M));
+		const int H = desc.hiddenSize;
+		int G = 4;
+		while (G < H) G *= 2;
+		M.L = desc.numLayers; M.H = H; M.G = G;
+		M.stateStride = M.L * 2 * G;
+		P.initState.assign(M.stateStride, 0.0f);
+		for (int l = 0; l < M.L; l++)
+		{
+			const LstmLayerWeights& Ly = desc.layers[l];
+			const int I = Ly.inputSize;           // real
+			const int IP = l == 0 ? 1 : G;        // padded
+			const int cols = I + H, colsP = IP + G;
+			M.wOff[l] = (int)P.weights.size();
+			P.weights.resize(P.weights.size() + (size_t)4 * colsP * G, 0.0f);
+			float* W = P.weights.data() + M.wOff[l];
+			for (int q = 0; q < 4; q++)
+				for (int u = 0; u < H; u++)
+				{
+					const float* row = Ly.W.data() + (size_t)(q * H + u) * cols;
+					for (int j = 0; j < I; j++) W[(size_t)(q * colsP + j) * G + u] = row[j];
+					for (int j = 0; j < H; j++) W[(size_t)(q * colsP + IP + j) * G + u] = row[I + j];
+				}
+			M.bOff[l] = (int)P.weights.size();
+			P.weights.resize(P.weights.size() + (size_t)4 * G, 0.0f);
+			float* b = P.weights.data() + M.bOff[l];
+			for (int q = 0; q < 4; q++)
+				for (int u = 0; u < H; u++) b[q * G + u] = Ly.b[q * H + u];
+			for (int u = 0; u < H; u++)
+			{
+				P.initState[(2 * l) * G + u] = Ly.h0[u];
+				P.initState[(2 * l + 1) * G + u] = Ly.c0[u];
+			}
+		}
+		M.headOff = (int)P.weights.size();
+		P.weights.resize(P.weights.size() + G + 4, 0.0f);
+		for (int u = 0; u < H; u++) P.weights[M.headOff + u] = desc.headW[u];
+		P.weights[M.headOff + G] = desc.headB;
+		return P;
+	}
+}

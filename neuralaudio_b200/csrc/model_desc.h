@@ -1,0 +1,74 @@
+// Host-side model ingest: model-file JSON -> validated architecture descriptor -> packed device weights.
+// Restates the Internal branch of NeuralModelLoader::CreateFromJson (reference NeuralModel.cpp:338-581);
+// the NAM Core and RTNeural branches are refused loudly instead of falling back to a CPU path.
+#pragma once
+#include <string>
+#include <vector>
+#include "json_min.h"
+#include "na_device.h"
+
+namespace nab200
+{
+	struct WaveNetArrayDesc
+	{
+		int inputSize = 1, channels = 0, headSize = 1, headKernel = 1;
+		bool headBias = false;
+		int activation = 0;   // 0 tanh, 1 leaky relu
+		std::vector<int> kernelSizes, dilations;
+	};
+
+	struct WaveNetDesc
+	{
+		std::vector<WaveNetArrayDesc> arrays;
+		std::vector<float> weights;   // file order
+		bool isStatic = false;        // one of the reference's compile-time architectures
+		int receptiveField = 0;
+	};
+
+	struct LstmLayerWeights
+	{
+		int inputSize = 1;
+		std::vector<float> W;    // [4H][I+H] row-major, gate rows i,f,g,o (LSTM.h:26,33-37)
+		std::vector<float> b;    // [4H]
+		std::vector<float> h0, c0;
+	};
+
+	struct LstmDesc
+	{
+		int numLayers = 0, hiddenSize = 0;
+		std::vector<LstmLayerWeights> layers;
+		std::vector<float> headW;
+		float headB = 0.0f;
+		bool isStatic = false;
+	};
+
+	// reference NeuralModel.cpp:92-130
+	void OversampleNamConfig(Json& modelJson, int externalSampleRate);
+	// reference NeuralModel.cpp:159-168
+	bool NamIsA2(const std::string& version);
+	// reference NeuralModel.cpp:188-317
+	bool NamIsA2Standard(const Json& modelJson);
+
+	// throw std::runtime_error with a clear message for anything outside the supported set
+	WaveNetDesc ParseNamWaveNet(const Json& modelJson);
+	LstmDesc ParseNamLstm(const Json& modelJson);
+	LstmDesc ParseKerasLstm(const Json& modelJson);
+
+	struct PackedWaveNet
+	{
+		WnModelDev dev;
+		std::vector<float> weights;   // packed blocks
+	};
+
+	struct PackedLstm
+	{
+		LstmModelDev dev;
+		std::vector<float> weights;
+		std::vector<float> initState;   // [stateStride] from the file's h0/c0 (zeros for keras)
+	};
+
+	PackedWaveNet PackWaveNet(const WaveNetDesc& desc);
+	PackedLstm PackLstm(const LstmDesc& desc);
+
+	int PadChannels(int c);   // 2, 4, 8, 12, 16
+}

@@ -1,0 +1,74 @@
+// Shared host/device descriptors for the batched Process() kernels.
+//
+// Everything here describes ONE model (weights + architecture) and the per-stream state that the reference keeps
+// inside its model objects (ChannelHistoryBuffer, WaveNet.h:30-83; LSTMLayerT::state/cellState, LSTM.h:27-31),
+// re-laid-out for thousands of independent streams resident in HBM.
+#pragma once
+#include <cstdint>
+
+namespace nab200
+{
+	constexpr int kMaxLayers = 32;   // layers over all arrays (A1 Standard 20, A1 Lite-pattern 20, A2 23)
+	constexpr int kMaxArrays = 2;
+	constexpr int kMaxRings = kMaxLayers + kMaxArrays;
+
+	enum : int
+	{
+		kFirstInArray = 1,   // block also carries the array's rechannel weights
+		kLastInArray = 2,    // block also carries the array's head-conv weights
+		kNeedOutput = 4      // 1x1 + residual is computed (WaveNet.h:486; false only for the very last layer of a 2-array model)
+	};
+
+	// One dilated-conv layer == one weight block (staged to shared memory as a unit).
+	// Block layout in floats (every sub-array starts 16-byte aligned, C = padded channel count of the array):
+	//   convW[K][C][C] (tap, in, out)  | convB[C] | mix[C] | oneW[C][C] (in, out) | oneB[C]
+	//   | re[inC][C] (in, out)          -- only when kFirstInArray
+	//   | headW[Kh][C][H] (tap, in, out) | headB[H]  -- only when kLastInArray
+	struct WnLayer
+	{
+		int K, d;
+		int Lp;        // ring capacity in frames, multiple of 4, >= (K-1)*d
+		int ringOff;   // float offset of this layer's ring inside one stream's state
+		int ringIdx;   // index into the per-stream ring-head array
+		int flags;
+		int wOff;      // float offset of the block inside the packed weights
+		int wSize;     // block size in floats (multiple of 4)
+		int oConvB, oMix, oOneW, oOneB, oRe, oHeadW, oHeadB;
+		int array;     // index of the owning layer array
+	};
+
+	struct WnArray
+	{
+		int C;          // padded channels
+		int inC;        // padded input channels of the rechannel (1 for the first array)
+		int H;          // padded head size (== next array's C; 1 for the last array)
+		int Kh;         // head conv kernel size (1 for A1, 16 for A2)
+		int act;        // 0 = FastMath tanh, 1 = LeakyReLU(0.01)
+		int firstLayer, numLayers;
+		int headLp, headRingOff, headRingIdx;   // head-conv history ring (Kh > 1 only)
+		int realC, realH;
+	};
+
+	struct WnModelDev
+	{
+		int numArrays, numLayers, numRings;
+		int stateStride;     // floats of ring state per stream (multiple of 4)
+		int maxBlock;        // largest weight block in floats
+		float headScale;
+		WnArray arrays[kMaxArrays];
+		WnLayer layers[kMaxLayers];
+		int ringLp[kMaxRings];
+	};
+
+	// LSTM: lane == hidden unit, G = pow2 >= H lanes per stream, weights zero-padded to G.
+	// Packed per layer l (I = 1 for l == 0 else G):  W[4][I + G][G] (gate, column, unit) | b[4][G]
+	// then headW[G], headB.  State per stream: [layer][2][G] (h then c).
+	struct LstmModelDev
+	{
+		int L, H, G;
+		int wOff[2];       // float offset of layer l's W
+		int bOff[2];
+		int headOff;       // headW[G] then headB
+		int stateStride;   // floats per stream = L * 2 * G
+	};
+}

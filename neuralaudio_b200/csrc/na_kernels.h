@@ -1,0 +1,45 @@
+// Host-callable launchers of the CUDA kernels (wavenet_kernels.cu, lstm_kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include "na_device.h"
+
+namespace nab200
+{
+	struct WnLaunch
+	{
+		const float* weights;   // packed weight blocks (device)
+		float* state;           // [S][stateStride] ring state (device)
+		int* heads;             // [S][numRings] ring heads (device)
+		const float* in;        // device pointer; element (stream s, frame f) at in[s*inSS + f*inFS]
+		float* out;
+		long long inSS, inFS, outSS, outFS;
+		int S;                  // streams
+		int n;                  // frames this pass (<= wavenet_max_frames_per_pass)
+		int numSMs;
+		bool useTma;
+		cudaStream_t stream;
+	};
+
+	cudaError_t wavenet_launch(const WnModelDev& M, const WnLaunch& a);
+	cudaError_t wavenet_prewarm_launch(const WnModelDev& M, const float* weights, float* tmpl, cudaStream_t stream);
+	cudaError_t state_fill_launch(float* state, const float* tmpl, int strideFloats, long long numStreams, cudaStream_t stream);
+	cudaError_t int_fill_launch(int* p, int v, long long total, cudaStream_t stream);
+	int wavenet_max_frames_per_pass(int C0);
+	bool wavenet_variant_supported(int C0, int C1, int act);
+
+	struct LstmLaunch
+	{
+		const float* weights;
+		float* state;           // [S][stateStride]
+		const float* in;
+		float* out;             // may be null (prewarm: outputs discarded)
+		long long inSS, inFS, outSS, outFS;
+		int S;
+		int n;
+		bool zeroInput;         // ignore `in`, feed zeros (prewarm)
+		cudaStream_t stream;
+	};
+
+	cudaError_t lstm_launch(const LstmModelDev& M, const LstmLaunch& a);
+	bool lstm_variant_supported(int L, int G);
+}

@@ -1,0 +1,901 @@
+// Batched WaveNet Process() for sm_100a: thousands of independent audio streams per launch.
+//
+// What the reference does per model object, one stream at a time on one CPU thread
+// (WaveNetModelT::Process WaveNet.h:768-799 -> WaveNetLayerArrayT::Process :632-661 -> WaveNetLayerT::Process
+// :462-494 -> Conv1DT::Process :139-290 / DenseLayerT::Process :336-383 / FastMath Activation.h:83-118),
+// this kernel does for a whole batch:
+//
+//   * one WARP owns one stream for the whole call; lane L owns frames L, L+32, ... (R frames per lane),
+//     all channels of a frame live in that lane's registers, so bias / mix-in / activation / head sum /
+//     1x1 / residual are thread-local -- only the dilated taps cross lanes, through shared memory;
+//   * the per-stream dilation history (ChannelHistoryBuffer, WaveNet.h:30-83) lives in HBM as one circular
+//     buffer per layer, channel-major [C][Lp] with Lp a multiple of 4 frames, so that the window a tap needs is,
+//     per channel, one 16-byte-aligned contiguous run (two at the wrap) -> staged by TMA bulk copies
+//     (cp.async.bulk + mbarrier), double-buffered one tap ahead of the FMA loop;
+//   * a CTA (8 warps = 8 streams) walks the layers in lock-step and stages each layer's weights
+//     (<= 4.8 KB) into shared memory with cp.async, double-buffered, so weights are read from L2 once per 8 streams;
+//   * persistent grid: CTAs loop over groups of 8 streams.
+//
+// Only the algorithmically required history columns are read (the union of the taps' windows) and only the
+// columns a later call can tap are written back (SURVEY.md section 8d byte model).
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "na_device.h"
+#include "na_kernels.h"
+
+namespace nab200
+{
+	// ---- FastMath (Activation.h:83-118), same formulas, fp32 ---------------------------------------------
+	__device__ __forceinline__ float fast_tanh_div(float x)
+	{
+		const float ax = fabsf(x);
+		const float x2 = x * x;
+		const float num = x * (2.45550750702956f + 2.45550750702956f * ax + (0.893229853513558f + 0.821226666969744f * ax) * x2);
+		const float den = 2.44506634652299f + (2.44506634652299f + x2) * fabsf(x + 0.814642734961073f * x * ax);
+		return __fdividef(num, den);   // den >= 2.445: reciprocal-multiply is within 2 ulp of the IEEE quotient
+	}
+
+	template <int ACT>
+	__device__ __forceinline__ float activate(float x)
+	{
+		if (ACT == 0) return fast_tanh_div(x);
+		return x > 0.0f ? x : 0.01f * x;   // LeakyReLU(0.01), Activation.h:110-118
+	}
+
+	// ---- async-copy / mbarrier primitives -------------------------------------------------------------------
+	__device__ __forceinline__ uint32_t smem_u32(const void* p)
+	{
+		return (uint32_t)__cvta_generic_to_shared(p);
+	}
+
+	__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+	{
+		asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+	}
+
+	__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+	{
+		asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+	}
+
+	__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+	{
+		asm volatile(
+			"{\n"
+			".reg .pred P1;\n"
+			"LAB_WAIT:\n"
+			"mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+			"@P1 bra DONE;\n"
+			"bra LAB_WAIT;\n"
+			"DONE:\n"
+			"}" ::"r"(bar),
+			"r"(parity)
+			: "memory");
+	}
+
+	// TMA 1-D bulk copy global -> shared, completion counted on an mbarrier (SASS: UBLKCP)
+	__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar)
+	{
+		asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+			"r"(bytes), "r"(bar)
+			: "memory");
+	}
+
+	__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src)
+	{
+		asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+	}
+
+	__device__ __forceinline__ void cp_async_commit()
+	{
+		asm volatile("cp.async.commit_group;" ::: "memory");
+	}
+
+	__device__ __forceinline__ void cp_async_wait_all()
+	{
+		asm volatile("cp.async.wait_group 0;" ::: "memory");
+	}
+
+	// ---- history-window pipeline ----------------------------------------------------------------------------
+	// A "job" is one history window: either everything one tap needs from before this call (per-tap mode) or
+	// the layer's whole history (whole-window mode), plus one job for a K>1 head conv.  Jobs are consumed in
+	// network order; the producer runs exactly one job ahead into the other of two window buffers.
+	struct JobParams
+	{
+		const float* ring;   // this stream's ring for the layer, [C][Lp]
+		int Lp, a0, len, shift, C;
+	};
+
+	template <int R, bool TMA>
+	struct WindowPipe
+	{
+		const WnModelDev* M;
+		float* st;            // this stream's ring state
+		const int* hd;        // this stream's ring heads (shared memory copy)
+		float* sm;            // per-warp float arena: xcur | win0 | win1
+		uint32_t bar[2];
+		int winOff[2];        // float offsets of the two window buffers inside sm
+		int stride;           // channel stride (floats) of xcur / win
+		int n, lane;
+		int pl, pt;           // producer cursor (layer, job-in-layer); pl == numLayers -> exhausted
+		uint32_t issued, consumed, phase;
+
+		// a layer whose whole history fits one window buffer stages it once and shares it between all taps;
+		// otherwise each tap gets its own window of min((K-1-k)*d, n) frames
+		static __device__ __forceinline__ bool is_whole(int hist) { return hist <= 32 * R; }
+
+		__device__ __forceinline__ int jobs_in_layer(int l) const
+		{
+			const WnLayer& L = M->layers[l];
+			const int hist = (L.K - 1) * L.d;
+			int nj = hist == 0 ? 0 : (is_whole(hist) ? 1 : (L.K - 1));
+			if ((L.flags & kLastInArray) && M->arrays[L.array].Kh > 1) nj++;
+			return nj;
+		}
+
+		// (l, t) -> window geometry.  t < convJobs: conv window; t == convJobs: head-conv window.
+		__device__ __forceinline__ JobParams params(int l, int t) const
+		{
+			const WnLayer& L = M->layers[l];
+			const WnArray& A = M->arrays[L.array];
+			const int hist = (L.K - 1) * L.d;
+			const int convJobs = hist == 0 ? 0 : (is_whole(hist) ? 1 : (L.K - 1));
+			JobParams p;
+			int D, count, head;
+			if (t < convJobs)
+			{
+				p.ring = st + L.ringOff;
+				p.Lp = L.Lp;
+				head = hd[L.ringIdx];
+				if (is_whole(hist)) { D = hist; count = hist; }
+				else { D = (L.K - 1 - t) * L.d; count = D < n ? D : n; }
+			}
+			else
+			{
+				p.ring = st + A.headRingOff;
+				p.Lp = A.headLp;
+				head = hd[A.headRingIdx];
+				D = A.Kh - 1;
+				count = D;
+			}
+			p.C = A.C;
+			int idx0 = head - D;
+			if (idx0 < 0) idx0 += p.Lp;
+			p.shift = idx0 & 3;
+			p.a0 = idx0 & ~3;
+			p.len = (p.shift + count + 3) & ~3;
+			return p;
+		}
+
+		__device__ __forceinline__ void start()
+		{
+			pl = 0; pt = 0;
+			while (pl < M->numLayers && jobs_in_layer(pl) == 0) pl++;
+			issue_next();
+		}
+
+		// issue the producer cursor's job (if any) into the next buffer and advance the cursor
+		__device__ __forceinline__ void issue_next()
+		{
+			if (pl >= M->numLayers) return;
+			if (TMA)
+			{
+				const JobParams p = params(pl, pt);
+				const int buf = issued & 1;
+				const int seg1 = min(p.len, p.Lp - p.a0);
+				const int seg2 = p.len - seg1;
+				if (lane == 0) mbar_expect_tx(bar[buf], (uint32_t)(p.C * p.len * 4));
+				if (lane < p.C)
+				{
+					const float* src = p.ring + (size_t)lane * p.Lp;
+					const uint32_t dst = smem_u32(sm + winOff[buf] + lane * stride);
+					bulk_g2s(dst, src + p.a0, (uint32_t)seg1 * 4u, bar[buf]);
+					if (seg2 > 0) bulk_g2s(dst + (uint32_t)seg1 * 4u, src, (uint32_t)seg2 * 4u, bar[buf]);
+				}
+			}
+			issued++;
+			pt++;
+			while (pl < M->numLayers && pt >= jobs_in_layer(pl)) { pl++; pt = 0; }
+		}
+
+		// wait for job (l, t) -- which must be the next one in order -- then prefetch the one after it.
+		// returns the float offset inside sm of the window's element for (channel 0, first history frame).
+		__device__ __forceinline__ int acquire(int l, int t)
+		{
+			const int buf = consumed & 1;
+			const JobParams p = params(l, t);
+			__syncwarp();   // every lane is done with the buffer the NEXT issue will overwrite
+			if (TMA)
+			{
+				mbar_wait(bar[buf], (phase >> buf) & 1u);
+				phase ^= (1u << buf);
+			}
+			else
+			{
+				for (int c = 0; c < p.C; c++)
+				{
+					const float* src = p.ring + (size_t)c * p.Lp;
+					float* dst = sm + winOff[buf] + c * stride;
+					for (int i = lane; i < p.len; i += 32)
+					{
+						int idx = p.a0 + i;
+						if (idx >= p.Lp) idx -= p.Lp;
+						dst[i] = src[idx];
+					}
+				}
+				__syncwarp();
+			}
+			consumed++;
+			issue_next();
+			return winOff[buf] + p.shift;
+		}
+	};
+
+	// ---- per-array compute ----------------------------------------------------------------------------------
+	template <int N>
+	__device__ __forceinline__ void load_row(float (&w)[N], const float* __restrict__ p)
+	{
+		if (N % 4 == 0)
+		{
+#pragma unroll
+			for (int q = 0; q < N / 4; q++)
+			{
+				const float4 v = *reinterpret_cast<const float4*>(p + 4 * q);
+				w[4 * q + 0] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
+			}
+		}
+		else if (N % 2 == 0)
+		{
+#pragma unroll
+			for (int q = 0; q < N / 2; q++)
+			{
+				const float2 v = *reinterpret_cast<const float2*>(p + 2 * q);
+				w[2 * q + 0] = v.x; w[2 * q + 1] = v.y;
+			}
+		}
+		else
+		{
+#pragma unroll
+			for (int q = 0; q < N; q++) w[q] = p[q];
+		}
+	}
+
+	struct CtaCtx
+	{
+		const WnModelDev* M;
+		const float* Wg;       // packed weights (global)
+		float* wbuf;           // shared: [2][maxBlock]
+		int wbStride;
+		int q;                 // running weight-block counter (buffer parity), uniform over the CTA
+		int tid, nthreads;
+	};
+
+	__device__ __forceinline__ void issue_weight_block(const CtaCtx& cx, int b, int buf)
+	{
+		const WnLayer& L = cx.M->layers[b];
+		const float4* src = reinterpret_cast<const float4*>(cx.Wg + L.wOff);
+		const uint32_t dst = smem_u32(cx.wbuf + (size_t)buf * cx.wbStride);
+		const int nchunks = L.wSize >> 2;
+		for (int i = cx.tid; i < nchunks; i += cx.nthreads) cp_async16(dst + 16u * (uint32_t)i, src + i);
+		cp_async_commit();
+	}
+
+	// One layer array for one stream (warp).  C = channels, INC = rechannel input width (1: from `cond`,
+	// otherwise the previous array's output still sitting in xcur), H = head size.
+	// head[r][c] enters as the running head accumulator (zeros for the first array, previous headOutputs after)
+	// and leaves holding the summed head; hout receives the head conv's output.
+	template <int C, int INC, int H, int R, int ACT, bool TMA>
+	__device__ __forceinline__ void run_array(CtaCtx& cx, WindowPipe<R, TMA>& pipe, const WnArray& A, bool active, int n, int lane,
+		const float (&cond)[R], float (&head)[R][C], float (&hout)[R][H])
+	{
+		constexpr int STR = 32 * R + 4;
+		float* const sm = pipe.sm;   // xcur at offset 0
+		const WnModelDev& M = *cx.M;
+
+		for (int li = 0; li < A.numLayers; li++)
+		{
+			const int l = A.firstLayer + li;
+			// weights of block l have landed (each thread waits for its own cp.async, then the CTA barrier
+			// publishes them); the same barrier proves every warp is done with the other buffer.
+			cp_async_wait_all();
+			__syncthreads();
+			issue_weight_block(cx, (l + 1 < M.numLayers) ? l + 1 : 0, (cx.q + 1) & 1);
+			const float* __restrict__ wb = cx.wbuf + (size_t)(cx.q & 1) * cx.wbStride;
+			cx.q++;
+			if (!active) continue;
+
+			const WnLayer& L = M.layers[l];
+			const int K = L.K, d = L.d, flags = L.flags;
+
+			// ---- rechannel into xcur (WaveNet.h:637) -- first layer of the array only
+			if (flags & kFirstInArray)
+			{
+				const float* __restrict__ re = wb + L.oRe;   // [INC][C]
+				float xin[R][C];
+#pragma unroll
+				for (int r = 0; r < R; r++)
+#pragma unroll
+					for (int c = 0; c < C; c++) xin[r][c] = 0.0f;
+				if (INC == 1)
+				{
+					float w[C];
+					load_row<C>(w, re);
+#pragma unroll
+					for (int r = 0; r < R; r++)
+#pragma unroll
+						for (int c = 0; c < C; c++) xin[r][c] = w[c] * cond[r];
+				}
+				else
+				{
+#pragma unroll
+					for (int ci = 0; ci < INC; ci++)
+					{
+						float w[C];
+						load_row<C>(w, re + ci * C);
+#pragma unroll
+						for (int r = 0; r < R; r++)
+						{
+							const float a = sm[ci * STR + lane + 32 * r];
+#pragma unroll
+							for (int c = 0; c < C; c++) xin[r][c] = fmaf(w[c], a, xin[r][c]);
+						}
+					}
+					__syncwarp();   // all lanes have read the previous array's output before it is overwritten
+				}
+#pragma unroll
+				for (int r = 0; r < R; r++)
+#pragma unroll
+					for (int c = 0; c < C; c++) sm[c * STR + lane + 32 * r] = xin[r][c];
+				__syncwarp();
+			}
+
+			// ---- dilated conv (WaveNet.h:250-289): z = b + sum_k W_k x[t - (K-1-k) d]
+			float z[R][C];
+			{
+				float b[C];
+				load_row<C>(b, wb + L.oConvB);
+#pragma unroll
+				for (int r = 0; r < R; r++)
+#pragma unroll
+					for (int c = 0; c < C; c++) z[r][c] = b[c];
+			}
+			const int hist = (K - 1) * d;
+			const bool whole = WindowPipe<R, TMA>::is_whole(hist);
+			int winBase = 0;
+			for (int k = 0; k < K; k++)
+			{
+				const int D = (K - 1 - k) * d;
+				int src[R];
+				if (D == 0)
+				{
+#pragma unroll
+					for (int r = 0; r < R; r++) src[r] = lane + 32 * r;
+				}
+				else
+				{
+					if (!whole) winBase = pipe.acquire(l, k);
+					else if (k == 0) winBase = pipe.acquire(l, 0);
+					const int hb = whole ? (winBase + hist - D) : winBase;
+#pragma unroll
+					for (int r = 0; r < R; r++)
+					{
+						const int f = lane + 32 * r;
+						src[r] = (f >= D) ? (f - D) : (hb + f);
+					}
+				}
+				const float* __restrict__ wk = wb + k * C * C;
+#pragma unroll
+				for (int ci = 0; ci < C; ci++)
+				{
+					float a[R];
+#pragma unroll
+					for (int r = 0; r < R; r++) a[r] = sm[src[r] + ci * STR];
+					float w[C];
+					load_row<C>(w, wk + ci * C);
+#pragma unroll
+					for (int r = 0; r < R; r++)
+#pragma unroll
+						for (int c = 0; c < C; c++) z[r][c] = fmaf(w[c], a[r], z[r][c]);
+				}
+			}
+
+			// ---- mix-in, activation, head accumulation (WaveNet.h:471-482)
+			{
+				float w[C];
+				load_row<C>(w, wb + L.oMix);
+#pragma unroll
+				for (int r = 0; r < R; r++)
+#pragma unroll
+					for (int c = 0; c < C; c++)
+					{
+						const float v = activate<ACT>(fmaf(w[c], cond[r], z[r][c]));
+						z[r][c] = v;
+						head[r][c] += v;
+					}
+			}
+
+			// ---- history write-back: this layer's input frames become the newest ring columns (AdvanceFrames,
+			//      WaveNet.h:59-65).  Only the last min(n, Lp) frames can ever be tapped again.
+			if (hist > 0)
+			{
+				float* __restrict__ ring = pipe.st + L.ringOff;
+				const int Lp = L.Lp;
+				const int hd = pipe.hd[L.ringIdx];
+				const int first = n > Lp ? n - Lp : 0;
+				if (((hd | n) & 3) == 0)
+				{
+					// 16-byte path: lane j moves frames 4j..4j+3 (+128, ...) of every channel
+#pragma unroll
+					for (int rr = 0; rr < (R + 3) / 4; rr++)
+					{
+						const int f0 = 4 * (lane + 32 * rr);
+						if (f0 < n && f0 >= first && f0 < 32 * R)
+						{
+							const int idx = (hd + f0) % Lp;
+#pragma unroll
+							for (int c = 0; c < C; c++)
+							{
+								const float4 v = *reinterpret_cast<const float4*>(sm + c * STR + f0);
+								*reinterpret_cast<float4*>(ring + (size_t)c * Lp + idx) = v;
+							}
+						}
+					}
+				}
+				else
+				{
+#pragma unroll
+					for (int r = 0; r < R; r++)
+					{
+						const int f = lane + 32 * r;
+						if (f < n && f >= first)
+						{
+							const int idx = (hd + f) % Lp;
+#pragma unroll
+							for (int c = 0; c < C; c++) ring[(size_t)c * Lp + idx] = sm[c * STR + f];
+						}
+					}
+				}
+			}
+
+			// ---- 1x1 + residual -> next layer's input (WaveNet.h:486-491)
+			if (flags & kNeedOutput)
+			{
+				const float* __restrict__ w1 = wb + L.oOneW;   // [ci][co]
+				float bo[C];
+				load_row<C>(bo, wb + L.oOneB);
+				constexpr int RH = (R >= 2) ? R / 2 : 1;        // half the frames at a time to bound registers
+				__syncwarp();   // every lane has finished reading xcur (taps + write-back) for this layer
+#pragma unroll
+				for (int half = 0; half < R / RH; half++)
+				{
+					float o[RH][C];
+#pragma unroll
+					for (int r = 0; r < RH; r++)
+#pragma unroll
+						for (int c = 0; c < C; c++) o[r][c] = bo[c];
+#pragma unroll
+					for (int ci = 0; ci < C; ci++)
+					{
+						float w[C];
+						load_row<C>(w, w1 + ci * C);
+#pragma unroll
+						for (int r = 0; r < RH; r++)
+#pragma unroll
+							for (int c = 0; c < C; c++) o[r][c] = fmaf(w[c], z[half * RH + r][ci], o[r][c]);
+					}
+					// own-frame elements only: no cross-lane hazard until the next layer's taps
+#pragma unroll
+					for (int r = 0; r < RH; r++)
+#pragma unroll
+						for (int c = 0; c < C; c++)
+						{
+							const int a = c * STR + lane + 32 * (half * RH + r);
+							sm[a] = o[r][c] + sm[a];
+						}
+				}
+				__syncwarp();
+			}
+
+			// ---- head conv over the summed head (WaveNet.h:658-660) -- last layer of the array
+			if (flags & kLastInArray)
+			{
+				const float* __restrict__ hw = wb + L.oHeadW;   // [Kh][C][H]
+				{
+					float hbv[H];
+					load_row<H>(hbv, wb + L.oHeadB);
+#pragma unroll
+					for (int r = 0; r < R; r++)
+#pragma unroll
+						for (int h = 0; h < H; h++) hout[r][h] = hbv[h];
+				}
+				const int Kh = A.Kh;
+				if (Kh == 1)
+				{
+#pragma unroll
+					for (int c = 0; c < C; c++)
+					{
+						float w[H];
+						load_row<H>(w, hw + c * H);
+#pragma unroll
+						for (int r = 0; r < R; r++)
+#pragma unroll
+							for (int h = 0; h < H; h++) hout[r][h] = fmaf(w[h], head[r][c], hout[r][h]);
+					}
+				}
+				else
+				{
+					// K>1 head (A2: 8->1, K=16): the summed head is a conv input with its own history ring
+					__syncwarp();
+#pragma unroll
+					for (int r = 0; r < R; r++)
+#pragma unroll
+						for (int c = 0; c < C; c++) sm[c * STR + lane + 32 * r] = head[r][c];
+					const int convJobs = hist == 0 ? 0 : (whole ? 1 : (K - 1));
+					const int hwin = pipe.acquire(l, convJobs);   // whole head history: Kh-1 frames (also syncs the warp)
+					const int Hh = Kh - 1;
+					for (int k = 0; k < Kh; k++)
+					{
+						const int D = Hh - k;
+						int src[R];
+#pragma unroll
+						for (int r = 0; r < R; r++)
+						{
+							const int f = lane + 32 * r;
+							src[r] = (f >= D) ? (f - D) : (hwin + Hh - D + f);
+						}
+#pragma unroll
+						for (int c = 0; c < C; c++)
+						{
+							float w[H];
+							load_row<H>(w, hw + (k * C + c) * H);
+#pragma unroll
+							for (int r = 0; r < R; r++)
+							{
+								const float a = sm[src[r] + c * STR];
+#pragma unroll
+								for (int h = 0; h < H; h++) hout[r][h] = fmaf(w[h], a, hout[r][h]);
+							}
+						}
+					}
+					// head history write-back
+					float* __restrict__ ring = pipe.st + A.headRingOff;
+					const int Lp = A.headLp;
+					const int hd = pipe.hd[A.headRingIdx];
+					const int first = n > Lp ? n - Lp : 0;
+#pragma unroll
+					for (int r = 0; r < R; r++)
+					{
+						const int f = lane + 32 * r;
+						if (f < n && f >= first)
+						{
+							const int idx = (hd + f) % Lp;
+#pragma unroll
+							for (int c = 0; c < C; c++) ring[(size_t)c * Lp + idx] = head[r][c];
+						}
+					}
+					__syncwarp();
+				}
+			}
+		}
+	}
+
+	constexpr int kWnWarps = 8;
+
+	template <int C0, int C1, int R>
+	struct WnSmem
+	{
+		static constexpr int CM = C0 > C1 ? C0 : C1;
+		static constexpr int STR = 32 * R + 4;
+		static constexpr int kArenaFloats = 3 * CM * STR;
+		static constexpr int kWarpBytes = ((kArenaFloats * 4 + kMaxRings * 4 + 16 + 15) / 16) * 16;
+	};
+
+	// C1 == 0: single-array model (A2).  ACT: 0 tanh, 1 LeakyReLU.
+	template <int C0, int C1, int R, int ACT, bool TMA>
+	__global__ void __launch_bounds__(kWnWarps * 32, 1)
+		wavenet_fwd_kernel(const __grid_constant__ WnModelDev M, const float* __restrict__ Wg, float* __restrict__ state,
+			int* __restrict__ heads, const float* in, float* out, long long inSS, long long inFS, long long outSS, long long outFS,
+			int S, int n)
+	{
+		using SM = WnSmem<C0, C1, R>;
+		constexpr int STR = SM::STR;
+		constexpr int CM = SM::CM;
+		extern __shared__ __align__(16) unsigned char smem_raw[];
+
+		const int tid = threadIdx.x;
+		const int warp = tid >> 5;
+		const int lane = tid & 31;
+
+		CtaCtx cx;
+		cx.M = &M;
+		cx.Wg = Wg;
+		cx.wbuf = reinterpret_cast<float*>(smem_raw);
+		cx.wbStride = M.maxBlock;
+		cx.q = 0;
+		cx.tid = tid;
+		cx.nthreads = kWnWarps * 32;
+
+		unsigned char* wbase = smem_raw + (size_t)2 * M.maxBlock * 4 + (size_t)warp * SM::kWarpBytes;
+		float* sm = reinterpret_cast<float*>(wbase);
+		int* hd = reinterpret_cast<int*>(wbase + SM::kArenaFloats * 4);
+		unsigned long long* bars = reinterpret_cast<unsigned long long*>(wbase + SM::kArenaFloats * 4 + kMaxRings * 4);
+
+		WindowPipe<R, TMA> pipe;
+		pipe.M = &M;
+		pipe.sm = sm;
+		pipe.hd = hd;
+		pipe.bar[0] = smem_u32(&bars[0]);
+		pipe.bar[1] = smem_u32(&bars[1]);
+		pipe.winOff[0] = CM * STR;
+		pipe.winOff[1] = 2 * CM * STR;
+		pipe.stride = STR;
+		pipe.n = n;
+		pipe.lane = lane;
+		pipe.issued = 0;
+		pipe.consumed = 0;
+		pipe.phase = 0;
+		pipe.pl = M.numLayers;
+		pipe.pt = 0;
+
+		if (TMA)
+		{
+			if (lane == 0)
+			{
+				mbar_init(pipe.bar[0], 1);
+				mbar_init(pipe.bar[1], 1);
+				asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+			}
+			asm volatile("fence.proxy.async;" ::: "memory");
+		}
+		__syncthreads();
+
+		issue_weight_block(cx, 0, 0);
+
+		const int numGroups = (S + kWnWarps - 1) / kWnWarps;
+		for (int g = blockIdx.x; g < numGroups; g += gridDim.x)
+		{
+			const int s = g * kWnWarps + warp;
+			const bool active = s < S;
+			float cond[R];
+#pragma unroll
+			for (int r = 0; r < R; r++) cond[r] = 0.0f;
+			if (active)
+			{
+				pipe.st = state + (size_t)s * M.stateStride;
+				__syncwarp();
+				for (int i = lane; i < M.numRings; i += 32) hd[i] = heads[(size_t)s * M.numRings + i];
+				__syncwarp();
+#pragma unroll
+				for (int r = 0; r < R; r++)
+				{
+					const int f = lane + 32 * r;
+					if (f < n) cond[r] = in[(long long)s * inSS + (long long)f * inFS];
+				}
+				pipe.start();
+			}
+
+			float head0[R][C0];
+#pragma unroll
+			for (int r = 0; r < R; r++)
+#pragma unroll
+				for (int c = 0; c < C0; c++) head0[r][c] = 0.0f;
+
+			float y[R];
+			if (C1 == 0)
+			{
+				float hout[R][1];
+				run_array<C0, 1, 1, R, ACT, TMA>(cx, pipe, M.arrays[0], active, n, lane, cond, head0, hout);
+#pragma unroll
+				for (int r = 0; r < R; r++) y[r] = hout[r][0];
+			}
+			else
+			{
+				constexpr int C1x = C1 > 0 ? C1 : 1;
+				float head1[R][C1x];
+				run_array<C0, 1, C1x, R, ACT, TMA>(cx, pipe, M.arrays[0], active, n, lane, cond, head0, head1);
+				float hout[R][1];
+				run_array<C1x, C0, 1, R, ACT, TMA>(cx, pipe, M.arrays[1], active, n, lane, cond, head1, hout);
+#pragma unroll
+				for (int r = 0; r < R; r++) y[r] = hout[r][0];
+			}
+
+			if (active)
+			{
+#pragma unroll
+				for (int r = 0; r < R; r++)
+				{
+					const int f = lane + 32 * r;
+					if (f < n) out[(long long)s * outSS + (long long)f * outFS] = M.headScale * y[r];   // WaveNet.h:793-798
+				}
+				// advance every ring head by n frames
+				for (int i = lane; i < M.numRings; i += 32)
+				{
+					const int Lp = M.ringLp[i];
+					int h = hd[i] + (n % Lp);
+					if (h >= Lp) h -= Lp;
+					heads[(size_t)s * M.numRings + i] = h;
+				}
+			}
+		}
+		cp_async_wait_all();
+	}
+
+	// ---- prewarm: steady state under silence (WaveNetModelT::Prewarm WaveNet.h:746-766, LayerArrayT::Prewarm :607-630)
+	// One warp computes the single zero-input frame; lane == output channel.  Fills a one-stream state TEMPLATE
+	// (every ring column = the layer's steady-state input) that state_fill_kernel replicates to all stream slots.
+	__global__ void wavenet_prewarm_kernel(const __grid_constant__ WnModelDev M, const float* __restrict__ Wg, float* __restrict__ tmpl)
+	{
+		__shared__ float x[32], z[32], head[32], xin[32], hnext[32];
+		const int lane = threadIdx.x;
+		x[lane] = 0.0f; z[lane] = 0.0f; head[lane] = 0.0f; xin[lane] = 0.0f; hnext[lane] = 0.0f;
+		__syncwarp();
+		for (int a = 0; a < M.numArrays; a++)
+		{
+			const WnArray& A = M.arrays[a];
+			const int C = A.C;
+			for (int li = 0; li < A.numLayers; li++)
+			{
+				const WnLayer& L = M.layers[A.firstLayer + li];
+				const float* wb = Wg + L.wOff;
+				if (L.flags & kFirstInArray)
+				{
+					// rechannel of the (zero) input / previous array output; condition is zero
+					float acc = 0.0f;
+					if (lane < C)
+						for (int ci = 0; ci < A.inC; ci++) acc = fmaf(wb[L.oRe + ci * C + lane], xin[ci], acc);
+					__syncwarp();
+					x[lane] = (lane < C) ? acc : 0.0f;
+					__syncwarp();
+				}
+				// history := this layer's input column everywhere (CopyBuffer, WaveNet.h:74-82)
+				if (lane < C)
+					for (int i = 0; i < L.Lp; i++) tmpl[L.ringOff + lane * L.Lp + i] = x[lane];
+				float acc = 0.0f;
+				if (lane < C)
+				{
+					acc = wb[L.oConvB + lane];
+					for (int k = 0; k < L.K; k++)
+						for (int ci = 0; ci < C; ci++) acc = fmaf(wb[(k * C + ci) * C + lane], x[ci], acc);
+					acc = (A.act == 0) ? fast_tanh_div(acc) : (acc > 0.0f ? acc : 0.01f * acc);   // mix-in term is W*0
+					head[lane] += acc;
+				}
+				z[lane] = acc;
+				__syncwarp();
+				float o = 0.0f;
+				if (lane < C)
+				{
+					o = wb[L.oOneB + lane];
+					for (int ci = 0; ci < C; ci++) o = fmaf(wb[L.oOneW + ci * C + lane], z[ci], o);
+					o += x[lane];
+				}
+				__syncwarp();
+				x[lane] = o;
+				__syncwarp();
+				if (L.flags & kLastInArray)
+				{
+					if (A.Kh > 1 && lane < C)
+						for (int i = 0; i < A.headLp; i++) tmpl[A.headRingOff + lane * A.headLp + i] = head[lane];
+					// head conv output feeds the next array's head accumulator
+					float ho = 0.0f;
+					if (lane < A.H)
+					{
+						ho = wb[L.oHeadB + lane];
+						for (int k = 0; k < A.Kh; k++)
+							for (int c = 0; c < C; c++) ho = fmaf(wb[L.oHeadW + (k * C + c) * A.H + lane], head[c], ho);
+					}
+					hnext[lane] = ho;
+					__syncwarp();
+					xin[lane] = x[lane];      // arrayOutputs -> next array's rechannel input
+					head[lane] = hnext[lane]; // headOutputs  -> next array's running head
+					__syncwarp();
+				}
+			}
+		}
+	}
+
+	// replicate a one-stream template into stream slots [s0, s0 + count) and zero their ring heads
+	__global__ void state_fill_kernel(float4* __restrict__ state, const float4* __restrict__ tmpl, int strideVec, long long totalVec)
+	{
+		const long long stride = (long long)gridDim.x * blockDim.x;
+		for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < totalVec; i += stride)
+			state[i] = tmpl[i % strideVec];
+	}
+
+	__global__ void int_fill_kernel(int* __restrict__ p, int v, long long total)
+	{
+		const long long stride = (long long)gridDim.x * blockDim.x;
+		for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) p[i] = v;
+	}
+
+	// ---- host-side launchers ---------------------------------------------------------------------------------
+	template <int C0, int C1, int R, int ACT>
+	static cudaError_t launch_variant(const WnModelDev& M, const WnLaunch& a)
+	{
+		using SM = WnSmem<C0, C1, R>;
+		const size_t smem = (size_t)2 * M.maxBlock * 4 + (size_t)kWnWarps * SM::kWarpBytes;
+		const int numGroups = (a.S + kWnWarps - 1) / kWnWarps;
+		int grid = numGroups < a.numSMs ? numGroups : a.numSMs;
+		if (grid < 1) grid = 1;
+		cudaError_t err;
+		if (a.useTma)
+		{
+			auto kfn = wavenet_fwd_kernel<C0, C1, R, ACT, true>;
+			err = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+			if (err != cudaSuccess) return err;
+			kfn<<<grid, kWnWarps * 32, smem, a.stream>>>(M, a.weights, a.state, a.heads, a.in, a.out, a.inSS, a.inFS, a.outSS, a.outFS, a.S, a.n);
+		}
+		else
+		{
+			auto kfn = wavenet_fwd_kernel<C0, C1, R, ACT, false>;
+			err = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+			if (err != cudaSuccess) return err;
+			kfn<<<grid, kWnWarps * 32, smem, a.stream>>>(M, a.weights, a.state, a.heads, a.in, a.out, a.inSS, a.inFS, a.outSS, a.outFS, a.S, a.n);
+		}
+		return cudaGetLastError();
+	}
+
+	template <int C0, int C1, int ACT>
+	static cudaError_t launch_by_frames(const WnModelDev& M, const WnLaunch& a)
+	{
+		if (a.n <= 32) return launch_variant<C0, C1, 1, ACT>(M, a);
+		if (a.n <= 128) return launch_variant<C0, C1, 4, ACT>(M, a);
+		if (C0 <= 8 && a.n <= 256) return launch_variant<C0, C1, (C0 <= 8 ? 8 : 4), ACT>(M, a);
+		return cudaErrorInvalidValue;
+	}
+
+	int wavenet_max_frames_per_pass(int C0)
+	{
+		return C0 <= 8 ? 256 : 128;
+	}
+
+	bool wavenet_variant_supported(int C0, int C1, int act)
+	{
+		if (act == 0) return (C0 == 16 && C1 == 8) || (C0 == 12 && C1 == 8) || (C0 == 8 && C1 == 4) || (C0 == 4 && C1 == 2);
+		return (C0 == 8 && C1 == 0) || (C0 == 4 && C1 == 0);
+	}
+
+	cudaError_t wavenet_launch(const WnModelDev& M, const WnLaunch& a)
+	{
+		const int C0 = M.arrays[0].C;
+		const int C1 = M.numArrays > 1 ? M.arrays[1].C : 0;
+		const int act = M.arrays[0].act;
+		if (act == 0)
+		{
+			if (C0 == 16 && C1 == 8) return launch_by_frames<16, 8, 0>(M, a);
+			if (C0 == 12 && C1 == 8) return launch_by_frames<12, 8, 0>(M, a);
+			if (C0 == 8 && C1 == 4) return launch_by_frames<8, 4, 0>(M, a);
+			if (C0 == 4 && C1 == 2) return launch_by_frames<4, 2, 0>(M, a);
+		}
+		else
+		{
+			if (C0 == 8 && C1 == 0) return launch_by_frames<8, 0, 1>(M, a);
+			if (C0 == 4 && C1 == 0) return launch_by_frames<4, 0, 1>(M, a);
+		}
+		return cudaErrorNotSupported;
+	}
+
+	cudaError_t wavenet_prewarm_launch(const WnModelDev& M, const float* weights, float* tmpl, cudaStream_t stream)
+	{
+		wavenet_prewarm_kernel<<<1, 32, 0, stream>>>(M, weights, tmpl);
+		return cudaGetLastError();
+	}
+
+	cudaError_t state_fill_launch(float* state, const float* tmpl, int strideFloats, long long numStreams, cudaStream_t stream)
+	{
+		const long long totalVec = numStreams * (long long)(strideFloats / 4);
+		if (totalVec == 0) return cudaSuccess;
+		long long blocks = (totalVec + 255) / 256;
+		if (blocks > 148 * 16) blocks = 148 * 16;
+		state_fill_kernel<<<(int)blocks, 256, 0, stream>>>(reinterpret_cast<float4*>(state), reinterpret_cast<const float4*>(tmpl), strideFloats / 4, totalVec);
+		return cudaGetLastError();
+	}
+
+	cudaError_t int_fill_launch(int* p, int v, long long total, cudaStream_t stream)
+	{
+		if (total == 0) return cudaSuccess;
+		long long blocks = (total + 255) / 256;
+		if (blocks > 148 * 8) blocks = 148 * 8;
+		int_fill_kernel<<<(int)blocks, 256, 0, stream>>>(p, v, total);
+		return cudaGetLastError();
+	}
+}

@@ -312,6 +312,9 @@ def _ref():
         L.RefX_BenchProcess.restype = ctypes.c_double
         L.RefX_BenchProcess.argtypes = [ctypes.c_wchar_p, ctypes.c_float, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                         ctypes.c_double, ctypes.c_uint, ctypes.POINTER(ctypes.c_double)]
+        L.RefX_BenchSteps.restype = ctypes.c_double
+        L.RefX_BenchSteps.argtypes = [ctypes.c_wchar_p, ctypes.c_float, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                      ctypes.c_int, ctypes.c_int, ctypes.c_uint]
         _ref_lib = L
     return _ref_lib
 
@@ -403,6 +406,12 @@ def ref_bench(path, frames, seconds, threads, instances_per_thread=64, quality=1
     total = L.RefX_BenchProcess(os.path.abspath(path), quality, threads, instances_per_thread, frames,
                                 float(seconds), seed, per)
     return total, list(per)
+
+
+def ref_bench_steps(path, frames, threads, instances_per_thread, warmup, steps, quality=1.0, seed=1234):
+    """Seconds for `steps` steps; one step = every one of threads*instances_per_thread reference model objects
+    processes one `frames`-sample block (its own stream of white noise)."""
+    return _ref().RefX_BenchSteps(os.path.abspath(path), quality, threads, instances_per_thread, frames, warmup, steps, seed)
 
 
 def model_path(name):

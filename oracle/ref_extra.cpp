@@ -56,6 +56,54 @@ NeuralModel* RefX_CreateModelFromFileNoPrewarm(NeuralModelLoader* l, const wchar
 	return m;
 }
 
+// Step-based variant for bench.py --impl reference: every thread owns `instancesPerThread` models; one STEP = each
+// instance processes one `frames`-sample block of white noise.  Runs `warmup` untimed steps, then `steps` timed steps
+// (all threads released together, time = slowest thread).  Returns seconds for the timed steps.
+double RefX_BenchSteps(const wchar_t* path, float quality, int numThreads, int instancesPerThread, int frames, int warmup, int steps,
+	unsigned seed)
+{
+	std::vector<std::thread> threads;
+	std::vector<double> elapsed((size_t)numThreads, 0.0);
+	std::atomic<int> ready{0};
+	std::atomic<bool> go{false};
+	std::filesystem::path p(path);
+	for (int t = 0; t < numThreads; t++)
+	{
+		threads.emplace_back([&, t]()
+		{
+			NeuralAudio::NeuralModelLoader loader;
+			loader.SetDefaultQualityScaleFactor(quality);
+			loader.SetDefaultMaxAudioBufferSize(frames);
+			std::vector<NeuralAudio::NeuralModel*> models;
+			for (int i = 0; i < instancesPerThread; i++) models.push_back(loader.CreateFromFile(p));
+			std::mt19937 rng(seed + 7919u * (unsigned)t);
+			std::uniform_real_distribution<float> dist(-1.0f, 1.0f);
+			std::vector<std::vector<float>> in((size_t)instancesPerThread), out((size_t)instancesPerThread);
+			for (int i = 0; i < instancesPerThread; i++)
+			{
+				in[i].resize((size_t)frames);
+				out[i].resize((size_t)frames);
+				for (auto& v : in[i]) v = dist(rng);
+			}
+			for (int w = 0; w < warmup; w++)
+				for (int i = 0; i < instancesPerThread; i++) if (models[i]) models[i]->Process(in[i].data(), out[i].data(), (size_t)frames);
+			ready.fetch_add(1);
+			while (!go.load()) std::this_thread::yield();
+			auto start = std::chrono::steady_clock::now();
+			for (int s = 0; s < steps; s++)
+				for (int i = 0; i < instancesPerThread; i++) if (models[i]) models[i]->Process(in[i].data(), out[i].data(), (size_t)frames);
+			elapsed[t] = std::chrono::duration<double>(std::chrono::steady_clock::now() - start).count();
+			for (auto m : models) delete m;
+		});
+	}
+	while (ready.load() < numThreads) std::this_thread::yield();
+	go.store(true);
+	for (auto& th : threads) th.join();
+	double worst = 0;
+	for (double e : elapsed) if (e > worst) worst = e;
+	return worst;
+}
+
 // Multi-instance, multi-thread timing of NeuralModel::Process on seeded U[-1,1) white noise.
 // Each thread owns `instancesPerThread` private model objects and calls Process(frames) round-robin over them
 // for at least `seconds`. Returns aggregate samples/second; *outThreadsUsed reports the thread count.

@@ -1,0 +1,254 @@
+"""GPU: parity of the CUDA path against the oracle, called through the C ABI (neuralaudio_b200 mirrors the binding).
+
+Checker = committed golden vectors (outputs of the unmodified reference) + the plain-C oracle on fresh seeded inputs.
+Tolerances are stated in conftest.py (WaveNet 1e-5 max-abs per BASELINE.json north_star; LSTM 5e-5)."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+from conftest import WAVENET_TOL, LSTM_TOL, golden_files, golden_id, load_golden, model_file_for, tol_for, is_lstm_case
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import oracle
+    return oracle
+
+
+def _load(na, mf, quality=1.0, streams=1, prewarm=True):
+    ld = na.NeuralModelLoader()
+    ld.SetDefaultQualityScaleFactor(quality)
+    ld.SetDefaultNumStreams(streams)
+    return ld.CreateFromFile(mf, prewarm)
+
+
+def _blocks(model, x, block):
+    y = np.empty_like(x)
+    for i in range(0, x.size, block):
+        y[i:i + block] = model.Process(np.ascontiguousarray(x[i:i + block]))
+    return y
+
+
+@pytest.mark.parametrize("path", golden_files(), ids=golden_id)
+def test_single_stream_process_matches_reference_golden(na, path, tmp_path):
+    """cfg 1 (and every other shape): the reference's own Process() call sequence, 128-frame host buffers."""
+    g = load_golden(path)
+    mf = model_file_for(g, tmp_path)
+    if mf is None:
+        pytest.skip("fixture model not staged")
+    q = float(g.get("quality", 1.0))
+    m = _load(na, mf, q)
+    y = _blocks(m, g["x"], 128)
+    err = float(np.abs(y - g["y"]).max())
+    assert err <= tol_for(g), "max-abs vs reference %.3g" % err
+    # boundary metadata equals the reference's answers for the same file
+    info = g["info"]
+    assert m.IsStatic() == info["static"]
+    assert m.GetReceptiveFieldSize() == info["rf"]
+    assert m.GetLoadMode() == 0
+    assert abs(m.GetSampleRate() - info["sample_rate"]) < 1e-3
+    assert abs(m.GetRecommendedInputDBAdjustment() - info["in_adj"]) < 1e-4
+    assert abs(m.GetRecommendedOutputDBAdjustment() - info["out_adj"]) < 1e-4
+    assert m.HasQualityScaling() == info["has_quality"]
+    # zero input after load: the prewarmed steady state
+    m2 = _load(na, mf, q)
+    dc = _blocks(m2, np.zeros(512, dtype=np.float32), 128)
+    assert float(np.abs(dc - g["dc"]).max()) <= tol_for(g)
+
+
+@pytest.mark.parametrize("name", ["syn_a1_standard", "syn_a1_nano", "syn_a2_full", "syn_lstm_1x16", "syn_lstm_2x8"])
+def test_chunking_invariance_and_inplace(na, name, tmp_path):
+    g = load_golden(golden_files(name)[0])
+    mf = model_file_for(g, tmp_path)
+    x = g["x"][:3000]
+    ref = _blocks(_load(na, mf), x, 128)
+    assert float(np.abs(ref - g["y"][:3000]).max()) <= tol_for(g)
+    for block in (1, 37, 64, 200, 3000):
+        if block == 1:
+            y = _blocks(_load(na, mf), x[:300], 1)
+            assert np.array_equal(y, ref[:300]), "block 1"
+            continue
+        y = _blocks(_load(na, mf), x, block)
+        assert np.array_equal(y, ref), "block %d differs by %.3g" % (block, np.abs(y - ref).max())
+    # n = 0 is a no-op; in == out is allowed (WaveNet.h:770, LSTM.h:168,184)
+    m = _load(na, mf)
+    m.Process(np.zeros(0, dtype=np.float32))
+    buf = x.copy()
+    for i in range(0, buf.size, 128):
+        seg = buf[i:i + 128]
+        m.Process(seg, seg)
+    assert np.array_equal(buf, ref)
+
+
+@pytest.mark.parametrize("name,streams,calls,frames", [("syn_a1_standard", 40, 12, 128), ("syn_a1_feather", 19, 10, 128),
+                                                        ("syn_a2_full", 24, 6, 256), ("syn_a2_lite", 9, 6, 256),
+                                                        ("syn_lstm_1x16", 70, 8, 128), ("syn_lstm_2x12", 21, 6, 128),
+                                                        ("syn_a1_lite", 11, 8, 96)])
+def test_batch_matches_oracle_per_stream(na, O, name, streams, calls, frames, tmp_path):
+    """Many independent streams per launch, state carried across calls, ragged stream counts; every stream is checked
+    against its own oracle instance on the same seeded white noise."""
+    g = load_golden(golden_files(name)[0])
+    mf = model_file_for(g, tmp_path)
+    rng = np.random.default_rng(4242)
+    amp = 0.5 if is_lstm_case(g) else 1.0
+    x = (rng.uniform(-1, 1, (calls, streams, frames)) * amp).astype(np.float32)
+    m = _load(na, mf, streams=streams)
+    assert m.GetNumStreams() == streams
+    y = np.empty_like(x)
+    for c in range(calls):
+        m.ProcessBatch(x[c], y[c], streams, frames, na.STREAM_MAJOR)
+    worst = 0.0
+    for s in range(streams):
+        om = O.PortModel.from_file(mf)
+        ys = om.process(np.ascontiguousarray(x[:, s, :]).reshape(-1))
+        worst = max(worst, float(np.abs(ys - y[:, s, :].reshape(-1)).max()))
+    assert worst <= tol_for(g), "worst stream max-abs %.3g" % worst
+
+
+@pytest.mark.parametrize("name", ["syn_a1_standard", "syn_lstm_1x16", "syn_a2_full"])
+def test_layouts_and_device_pointers_agree(na, name, tmp_path):
+    import torch
+    g = load_golden(golden_files(name)[0])
+    mf = model_file_for(g, tmp_path)
+    S, n, calls = 33, 128, 4
+    rng = np.random.default_rng(7)
+    x = rng.uniform(-1, 1, (calls, S, n)).astype(np.float32)
+    a = _load(na, mf, streams=S)
+    b = _load(na, mf, streams=S)
+    c = _load(na, mf, streams=S)
+    ya = np.empty_like(x)
+    yb = np.empty((calls, n, S), dtype=np.float32)
+    yc = torch.empty((calls, S, n), dtype=torch.float32, device="cuda")
+    xc = torch.from_numpy(x).cuda()
+    for k in range(calls):
+        a.ProcessBatch(x[k], ya[k], S, n, na.STREAM_MAJOR)
+        b.ProcessBatch(np.ascontiguousarray(x[k].T), yb[k], S, n, na.FRAME_MAJOR)
+        c.ProcessBatch(xc[k], yc[k], S, n, na.STREAM_MAJOR)   # device pointers, asynchronous
+    c.Synchronize()
+    assert np.array_equal(ya, np.transpose(yb, (0, 2, 1)))
+    assert np.array_equal(ya, yc.cpu().numpy())
+
+
+def test_prewarm_semantics(na, tmp_path):
+    # WaveNet: Prewarm() again == full reset; no-prewarm load starts from zero history
+    g = load_golden(golden_files("syn_a1_feather")[0])
+    mf = model_file_for(g, tmp_path)
+    m = _load(na, mf)
+    y1 = _blocks(m, g["x"][:1024], 128)
+    m.Prewarm()
+    y2 = _blocks(m, g["x"][:1024], 128)
+    assert np.array_equal(y1, y2)
+    cold = _blocks(_load(na, mf, prewarm=False), g["x"][:1024], 128)
+    assert float(np.abs(cold - y1).max()) > 1e-3
+    # LSTM: Prewarm() again == 2048 more zero samples from the current state, not a reset
+    g = load_golden(golden_files("syn_lstm_1x16")[0])
+    mf = model_file_for(g, tmp_path)
+    m = _load(na, mf)
+    a = _blocks(m, g["x"][:512], 128)
+    m.Prewarm()
+    b = _blocks(m, g["x"][:512], 128)
+    ref = _load(na, mf)
+    a2 = _blocks(ref, g["x"][:512], 128)
+    _blocks(ref, np.zeros(2048, dtype=np.float32), 64)
+    b2 = _blocks(ref, g["x"][:512], 128)
+    assert np.array_equal(a, a2)
+    assert float(np.abs(b - b2).max()) <= 1e-6
+
+
+def test_a2_container_quality_switch(na, O, tmp_path):
+    p = O.model_path("BossWN-a2.nam")
+    if p is None:
+        pytest.skip("fixture not staged")
+    full = load_golden(golden_files("ref_BossWN_a2.")[0])
+    lite = load_golden(golden_files("ref_BossWN_a2_q0")[0])
+    m = _load(na, p, 1.0)
+    assert m.HasQualityScaling() and m.GetReceptiveFieldSize() == 6346
+    y = _blocks(m, full["x"][:2048], 256)
+    assert float(np.abs(y - full["y"][:2048]).max()) <= WAVENET_TOL
+    # quality 0.0..0.5 selects the 3-channel sub-model, whose state is still the prewarmed one (LoadAll)
+    m.SetQualityScaleFactor(0.3)
+    assert abs(m.GetQualityScaleFactor() - 0.3) < 1e-7
+    y = _blocks(m, lite["x"][:2048], 256)
+    assert float(np.abs(y - lite["y"][:2048]).max()) <= WAVENET_TOL
+    # container-level metadata (CompositeModel.h:130-135)
+    assert abs(m.GetRecommendedOutputDBAdjustment() - full["info"]["out_adj"]) < 1e-4
+    assert m.GetMetadata("gear_type") == '"pedal"' and m.GetMetadata("nope") == ""
+    assert m.GetModelVersion() == "0.7.0"
+
+
+def test_metadata_matches_reference(na, O, tmp_path):
+    p = O.model_path("BossWN-standard.nam")
+    if p is None or not O.ref_available():
+        pytest.skip("fixture / compiled reference not staged")
+    r = O.RefModel(p)
+    m = _load(na, p)
+    for key in ("name", "loudness", "gain", "date", "modeled_by", "input_level_dbu", "training", "missing"):
+        assert m.GetMetadata(key) == r.metadata(key), key
+    assert m.GetModelVersion() == r.version()
+
+
+def test_tma_and_plain_window_paths_are_bit_identical(na, tmp_path):
+    g = load_golden(golden_files("syn_a1_standard")[0])
+    mf = model_file_for(g, tmp_path)
+    S, n = 16, 128
+    x = np.random.default_rng(3).uniform(-1, 1, (6, S, n)).astype(np.float32)
+    outs = []
+    for tma in (1, 0):
+        prev = na.set_option("use_tma", tma)
+        try:
+            m = _load(na, mf, streams=S)
+            y = np.empty_like(x)
+            for k in range(x.shape[0]):
+                m.ProcessBatch(x[k], y[k], S, n)
+            outs.append(y)
+        finally:
+            na.set_option("use_tma", prev)
+    assert np.array_equal(outs[0], outs[1])
+
+
+def test_full_size_config_properties(na, O, tmp_path):
+    """BASELINE.json cfg 2 (A1 Standard, 4096 streams x 128 frames) at full size, through size-independent
+    properties: identical inputs => bit-identical streams (independence + determinism), a tile of streams checked
+    sample-by-sample against the oracle, and linearity of the stream <-> slot mapping (reversed batch => reversed output)."""
+    import torch
+    g = load_golden(golden_files("syn_a1_standard")[0])
+    mf = model_file_for(g, tmp_path)
+    S, n, calls = 4096, 128, 6
+    rng = np.random.default_rng(11)
+    base = rng.uniform(-1, 1, (calls, 8, n)).astype(np.float32)
+    x = np.tile(base, (1, S // 8, 1))           # stream s carries pattern s % 8
+    m = _load(na, mf, streams=S)
+    assert m.GetStateBytesPerStream() >= 196416
+    xd = torch.from_numpy(x).cuda()
+    yd = torch.empty_like(xd)
+    for k in range(calls):
+        m.ProcessBatch(xd[k], yd[k], S, n)
+    m.Synchronize()
+    y = yd.cpu().numpy()
+    for p in range(8):
+        assert np.array_equal(y[:, p::8, :], np.broadcast_to(y[:, p:p + 1, :], y[:, p::8, :].shape))
+        om = O.PortModel.from_file(mf)
+        ys = om.process(np.ascontiguousarray(base[:, p, :]).reshape(-1))
+        assert float(np.abs(ys - y[:, p, :].reshape(-1)).max()) <= WAVENET_TOL
+    m2 = _load(na, mf, streams=S)
+    xr = torch.flip(xd, dims=[1]).contiguous()
+    yr = torch.empty_like(xr)
+    for k in range(calls):
+        m2.ProcessBatch(xr[k], yr[k], S, n)
+    m2.Synchronize()
+    assert torch.equal(torch.flip(yr, dims=[1]), yd)
+
+
+def test_errors_are_loud(na, tmp_path):
+    g = load_golden(golden_files("syn_a1_nano")[0])
+    mf = model_file_for(g, tmp_path)
+    m = _load(na, mf, streams=4)
+    x = np.zeros((8, 16), dtype=np.float32)
+    with pytest.raises(na.NeuralAudioError, match="stream slots"):
+        m.ProcessBatch(x, np.empty_like(x), 8, 16)
+    with pytest.raises(na.NeuralAudioError):
+        na.NeuralModelLoader().CreateFromFile(str(tmp_path / "missing.nam"))

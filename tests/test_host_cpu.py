@@ -1,0 +1,151 @@
+"""CPU: the C-ABI library loads, exports every declared symbol, and the host-side logic (JSON ingest, architecture
+dispatch, weight packing, error paths) behaves -- without any compute call (there is no GPU here)."""
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, golden_files, golden_id, load_golden, model_file_for
+
+
+def _declared_symbols():
+    names = []
+    with open(os.path.join(ROOT, "include", "NeuralAudioCApi.h")) as f:
+        for line in f:
+            m = re.match(r"\s*NA_EXTERN\s+[\w\s\*]+?\b(\w+)\s*\(", line)
+            if m:
+                names.append(m.group(1))
+    return names
+
+
+REFERENCE_EXPORTS = ["CreateLoader", "DeleteLoader", "CreateModelFromFile", "DeleteModel", "SetLSTMLoadMode", "SetWaveNetLoadMode",
+                     "SetAudioInputLevelDBu", "SetDefaultMaxAudioBufferSize", "GetLoadMode", "IsStatic", "SetMaxAudioBufferSize",
+                     "GetRecommendedInputDBAdjustment", "GetRecommendedOutputDBAdjustment", "GetSampleRate", "Process"]
+
+
+def test_library_exports_every_declared_symbol(na):
+    L = na.load_library()
+    declared = _declared_symbols()
+    assert set(REFERENCE_EXPORTS) <= set(declared)      # the reference's 15 exports, NeuralAudioCApi.h:18-46
+    assert len(declared) >= 40
+    for name in declared:
+        assert hasattr(L, name), "missing export " + name
+    # the Python mirror binds exactly the declared set
+    assert set(L._na_signatures) == set(declared)
+
+
+def test_only_c_abi_symbols_are_exported(na):
+    import subprocess
+    out = subprocess.check_output(["nm", "-D", "--defined-only", na.library_path()], text=True)
+    syms = [l.split()[-1] for l in out.splitlines() if " T " in l]
+    assert sorted(syms) == sorted(_declared_symbols())
+
+
+def test_loader_handles_work_without_gpu(na):
+    L = na.load_library()
+    h = L.CreateLoader()
+    assert h
+    L.SetLSTMLoadMode(h, 1)       # RTNeural: refused silently, like an unsupported mode in the reference
+    L.SetWaveNetLoadMode(h, 2)
+    L.SetAudioInputLevelDBu(h, 6.0)
+    L.SetDefaultMaxAudioBufferSize(h, 256)
+    L.DeleteLoader(h)
+
+
+@pytest.mark.parametrize("path", golden_files(), ids=golden_id)
+def test_describe_matches_reference_dispatch(na, path, tmp_path):
+    g = load_golden(path)
+    mf = model_file_for(g, tmp_path)
+    if mf is None:
+        pytest.skip("fixture model not staged")
+    d = na.describe_model_file(mf)
+    info = g["info"]
+    if d["kind"] == "container":
+        assert info["has_quality"]
+        subs = d["submodels"]
+        assert [s["max_value"] for s in subs] == [0.5, 1.0]
+        assert [s["model"]["arrays"][0]["channels"] for s in subs] == [3, 8]
+        assert all(s["model"]["receptive_field"] == 6346 and s["model"]["static"] for s in subs)
+        return
+    assert d["static"] == info["static"]                   # IsStatic() of the reference for the same file
+    if d["kind"] == "wavenet":
+        if info["static"]:
+            assert d["receptive_field"] == info["rf"]      # 4092 (A1) / 6346 (A2)
+        assert d["num_layers"] == sum(a["layers"] for a in d["arrays"])
+        assert d["state_floats"] % 4 == 0 and all(lp % 4 == 0 for lp in d["ring_lp"])
+    else:
+        assert info["rf"] == -1
+        assert d["lanes"] >= d["hidden"] and d["lanes"] in (4, 8, 16, 32)
+
+
+def test_state_size_close_to_algorithmic_minimum(na, tmp_path):
+    # A1 Standard keeps 49104 floats of history per stream; ring padding may add < 0.2 %
+    g = load_golden(golden_files("syn_a1_standard")[0])
+    d = na.describe_model_file(model_file_for(g, tmp_path))
+    assert 49104 <= d["state_floats"] <= 49104 * 1.002
+    assert d["num_weights"] == 13802
+
+
+def test_wrong_weight_count_is_reported(na, tmp_path):
+    g = load_golden(golden_files("syn_a1_feather")[0])
+    d = dict(g["model"])
+    d["weights"] = [float(x) for x in g["weights"]][:-1]
+    p = tmp_path / "short.nam"
+    p.write_text(json.dumps(d))
+    with pytest.raises(na.NeuralAudioError, match="Wrong number of weights. Expected 3026 but got 3025"):   # WaveNet.h:704-709 wording
+        na.describe_model_file(str(p))
+
+
+def test_unsupported_models_fail_loudly(na, tmp_path):
+    g = load_golden(golden_files("syn_a1_nano")[0])
+    d = json.loads(json.dumps(g["model"]))
+    d["weights"] = [float(x) for x in g["weights"]]
+    d["config"]["layers"][0]["gated"] = True
+    p = tmp_path / "gated.nam"
+    p.write_text(json.dumps(d))
+    with pytest.raises(na.NeuralAudioError, match="gated"):
+        na.describe_model_file(str(p))
+    p2 = tmp_path / "gru.json"
+    p2.write_text(json.dumps({"layers": [{"type": "gru", "shape": [None, None, 8], "weights": []}, {"type": "dense", "shape": [None, None, 1], "weights": []}]}))
+    with pytest.raises(na.NeuralAudioError, match="no CPU fallback"):
+        na.describe_model_file(str(p2))
+    p3 = tmp_path / "bad.nam"
+    p3.write_text("{ not json")
+    with pytest.raises(na.NeuralAudioError, match="json"):
+        na.describe_model_file(str(p3))
+
+
+def test_oversampling_leaves_the_static_path(na, tmp_path):
+    # OversampleNAMConfig (NeuralModel.cpp:92-130): at 96 kHz the dilations double, the file stops being an official shape
+    g = load_golden(golden_files("syn_a1_nano")[0])
+    mf = model_file_for(g, tmp_path)
+    d = na.describe_model_file(mf, 96000)
+    assert d["static"] is False and d["receptive_field"] == 2 * 4092
+
+
+def test_no_gpu_means_loud_failure_not_fallback(na, tmp_path):
+    if na.device_count() > 0:
+        pytest.skip("a GPU is present")
+    g = load_golden(golden_files("syn_a1_nano")[0])
+    mf = model_file_for(g, tmp_path)
+    with pytest.raises(na.NeuralAudioError, match="no CPU fallback"):
+        na.NeuralModelLoader().CreateFromFile(mf)
+    L = na.load_library()
+    h = L.CreateLoader()
+    assert not L.CreateModelFromFile(h, mf)     # NULL, never a half-built model
+    assert not L.CreateModelFromFile(h, str(tmp_path / "nope.nam"))
+    L.DeleteLoader(h)
+
+
+def test_product_never_touches_the_oracle():
+    # the product path must not import, load or link anything under oracle/
+    pkg = os.path.join(ROOT, "neuralaudio_b200")
+    for dirpath, _dirs, files in os.walk(pkg):
+        if "build" in dirpath:
+            continue
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cpp", ".h", "Makefile")):
+                txt = open(os.path.join(dirpath, fn), errors="replace").read()
+                assert "na_oracle" not in txt and "libna_ref" not in txt and "import oracle" not in txt and "from oracle" not in txt, fn
