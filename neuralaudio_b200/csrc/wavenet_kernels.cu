@@ -32,7 +32,10 @@ namespace nab200
 		const float x2 = x * x;
 		const float num = x * (2.45550750702956f + 2.45550750702956f * ax + (0.893229853513558f + 0.821226666969744f * ax) * x2);
 		const float den = 2.44506634652299f + (2.44506634652299f + x2) * fabsf(x + 0.814642734961073f * x * ax);
-		return __fdividef(num, den);   // den >= 2.445: reciprocal-multiply is within 2 ulp of the IEEE quotient
+		// den >= 2.445 and finite: one MUFU.RCP (<= 1 ulp) and a multiply, within 2 ulp of the IEEE quotient
+		float rden;
+		asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rden) : "f"(den));
+		return num * rden;
 	}
 
 	template <int ACT>
@@ -96,6 +99,23 @@ namespace nab200
 		asm volatile("cp.async.wait_group 0;" ::: "memory");
 	}
 
+	// ---- packed fp32x2 arithmetic (Blackwell FFMA2: two IEEE fused multiply-adds per issue slot) -----------------
+	__device__ __forceinline__ void ffma2(float2& d, const float2 a, const float2 b)
+	{
+		asm("fma.rn.f32x2 %0, %1, %2, %0;"
+			: "+l"(reinterpret_cast<unsigned long long&>(d))
+			: "l"(reinterpret_cast<const unsigned long long&>(a)), "l"(reinterpret_cast<const unsigned long long&>(b)));
+	}
+
+	// ---- stream-team synchronisation ---------------------------------------------------------------------------
+	// WPS warps cooperate on one stream.  WPS == 1: __syncwarp.  WPS == 2: a named barrier private to the pair.
+	template <int WPS>
+	__device__ __forceinline__ void team_sync(int barId)
+	{
+		if (WPS == 1) __syncwarp();
+		else asm volatile("bar.sync %0, %1;" ::"r"(barId), "n"(WPS * 32) : "memory");
+	}
+
 	// ---- history-window pipeline ----------------------------------------------------------------------------
 	// A "job" is one history window: either everything one tap needs from before this call (per-tap mode) or
 	// the layer's whole history (whole-window mode), plus one job for a K>1 head conv.  Jobs are consumed in
@@ -106,23 +126,24 @@ namespace nab200
 		int Lp, a0, len, shift, C;
 	};
 
-	template <int R, bool TMA>
+	// RT = frame rows (of 32) per stream per pass, WPS = warps per stream
+	template <int RT, int WPS, bool TMA>
 	struct WindowPipe
 	{
 		const WnModelDev* M;
 		float* st;            // this stream's ring state
 		const int* hd;        // this stream's ring heads (shared memory copy)
-		float* sm;            // per-warp float arena: xcur | win0 | win1
-		uint32_t bar[2];
-		int winOff[2];        // float offsets of the two window buffers inside sm
+		float* sm;            // per-stream float arena: xcur | win0 | win1
+		uint32_t bar0;        // shared address of the first of two adjacent mbarriers
+		int winOff0, winStep; // float offset of window buffer 0 inside sm, and distance to buffer 1
 		int stride;           // channel stride (floats) of xcur / win
-		int n, lane;
+		int n, lane, half, barId;
 		int pl, pt;           // producer cursor (layer, job-in-layer); pl == numLayers -> exhausted
 		uint32_t issued, consumed, phase;
 
 		// a layer whose whole history fits one window buffer stages it once and shares it between all taps;
 		// otherwise each tap gets its own window of min((K-1-k)*d, n) frames
-		static __device__ __forceinline__ bool is_whole(int hist) { return hist <= 32 * R; }
+		static __device__ __forceinline__ bool is_whole(int hist) { return hist <= 32 * RT; }
 
 		__device__ __forceinline__ int jobs_in_layer(int l) const
 		{
@@ -184,13 +205,16 @@ namespace nab200
 				const int buf = issued & 1;
 				const int seg1 = min(p.len, p.Lp - p.a0);
 				const int seg2 = p.len - seg1;
-				if (lane == 0) mbar_expect_tx(bar[buf], (uint32_t)(p.C * p.len * 4));
-				if (lane < p.C)
+				const uint32_t barA = bar0 + 8u * (uint32_t)buf;
+				if (half == 0 && lane == 0) mbar_expect_tx(barA, (uint32_t)(p.C * p.len * 4));
+				// the team's warps split the channel rows
+				const int c = lane * WPS + half;
+				if (c < p.C)
 				{
-					const float* src = p.ring + (size_t)lane * p.Lp;
-					const uint32_t dst = smem_u32(sm + winOff[buf] + lane * stride);
-					bulk_g2s(dst, src + p.a0, (uint32_t)seg1 * 4u, bar[buf]);
-					if (seg2 > 0) bulk_g2s(dst + (uint32_t)seg1 * 4u, src, (uint32_t)seg2 * 4u, bar[buf]);
+					const float* src = p.ring + (size_t)c * p.Lp;
+					const uint32_t dst = smem_u32(sm + winOff0 + buf * winStep + c * stride);
+					bulk_g2s(dst, src + p.a0, (uint32_t)seg1 * 4u, barA);
+					if (seg2 > 0) bulk_g2s(dst + (uint32_t)seg1 * 4u, src, (uint32_t)seg2 * 4u, barA);
 				}
 			}
 			issued++;
@@ -204,18 +228,18 @@ namespace nab200
 		{
 			const int buf = consumed & 1;
 			const JobParams p = params(l, t);
-			__syncwarp();   // every lane is done with the buffer the NEXT issue will overwrite
+			team_sync<WPS>(barId);   // every lane of the team is done with the buffer the NEXT issue will overwrite
 			if (TMA)
 			{
-				mbar_wait(bar[buf], (phase >> buf) & 1u);
+				mbar_wait(bar0 + 8u * (uint32_t)buf, (phase >> buf) & 1u);
 				phase ^= (1u << buf);
 			}
 			else
 			{
-				for (int c = 0; c < p.C; c++)
+				for (int c = half; c < p.C; c += WPS)
 				{
 					const float* src = p.ring + (size_t)c * p.Lp;
-					float* dst = sm + winOff[buf] + c * stride;
+					float* dst = sm + winOff0 + buf * winStep + c * stride;
 					for (int i = lane; i < p.len; i += 32)
 					{
 						int idx = p.a0 + i;
@@ -223,11 +247,11 @@ namespace nab200
 						dst[i] = src[idx];
 					}
 				}
-				__syncwarp();
+				team_sync<WPS>(barId);
 			}
 			consumed++;
 			issue_next();
-			return winOff[buf] + p.shift;
+			return winOff0 + buf * winStep + p.shift;
 		}
 	};
 
@@ -260,6 +284,27 @@ namespace nab200
 		}
 	}
 
+	// N consecutive floats as N/2 register pairs (N even)
+	template <int N>
+	__device__ __forceinline__ void load_row2(float2 (&w)[N / 2], const float* __restrict__ p)
+	{
+		if (N % 4 == 0)
+		{
+#pragma unroll
+			for (int q = 0; q < N / 4; q++)
+			{
+				const float4 v = *reinterpret_cast<const float4*>(p + 4 * q);
+				w[2 * q + 0] = make_float2(v.x, v.y);
+				w[2 * q + 1] = make_float2(v.z, v.w);
+			}
+		}
+		else
+		{
+#pragma unroll
+			for (int q = 0; q < N / 2; q++) w[q] = *reinterpret_cast<const float2*>(p + 2 * q);
+		}
+	}
+
 	struct CtaCtx
 	{
 		const WnModelDev* M;
@@ -280,17 +325,24 @@ namespace nab200
 		cp_async_commit();
 	}
 
-	// One layer array for one stream (warp).  C = channels, INC = rechannel input width (1: from `cond`,
-	// otherwise the previous array's output still sitting in xcur), H = head size.
-	// head[r][c] enters as the running head accumulator (zeros for the first array, previous headOutputs after)
+	// One layer array for one stream.  C = channels (even), INC = rechannel input width (1: from `cond`, otherwise the
+	// previous array's output still sitting in xcur), H = head size, RW = frame rows owned by THIS warp, WPS = warps
+	// per stream (row r of this warp is stream row r*WPS + half, i.e. frame lane + 32*(r*WPS + half)).
+	// head2[r][c/2] enters as the running head accumulator (zeros for the first array, previous headOutputs after)
 	// and leaves holding the summed head; hout receives the head conv's output.
-	template <int C, int INC, int H, int R, int ACT, bool TMA>
-	__device__ __forceinline__ void run_array(CtaCtx& cx, WindowPipe<R, TMA>& pipe, const WnArray& A, bool active, int n, int lane,
-		const float (&cond)[R], float (&head)[R][C], float (&hout)[R][H])
+	template <int C, int INC, int H, int RW, int WPS, int ACT, bool TMA>
+	__device__ __forceinline__ void run_array(CtaCtx& cx, WindowPipe<RW * WPS, WPS, TMA>& pipe, const WnArray& A, bool active, int n, int lane,
+		int half, const float (&cond)[RW], float2 (&head2)[RW][C / 2], float (&hout)[RW][H])
 	{
-		constexpr int STR = 32 * R + 4;
+		constexpr int RT = RW * WPS;
+		constexpr int STR = 32 * RT + 4;
+		constexpr int C2 = C / 2;
 		float* const sm = pipe.sm;   // xcur at offset 0
 		const WnModelDev& M = *cx.M;
+		const int barId = pipe.barId;
+		int fr[RW];   // this warp's frames
+#pragma unroll
+		for (int r = 0; r < RW; r++) fr[r] = lane + 32 * (r * WPS + half);
 
 		for (int li = 0; li < A.numLayers; li++)
 		{
@@ -311,65 +363,65 @@ namespace nab200
 			if (flags & kFirstInArray)
 			{
 				const float* __restrict__ re = wb + L.oRe;   // [INC][C]
-				float xin[R][C];
-#pragma unroll
-				for (int r = 0; r < R; r++)
-#pragma unroll
-					for (int c = 0; c < C; c++) xin[r][c] = 0.0f;
+				float xin[RW][C];
 				if (INC == 1)
 				{
 					float w[C];
 					load_row<C>(w, re);
 #pragma unroll
-					for (int r = 0; r < R; r++)
+					for (int r = 0; r < RW; r++)
 #pragma unroll
 						for (int c = 0; c < C; c++) xin[r][c] = w[c] * cond[r];
 				}
 				else
 				{
 #pragma unroll
+					for (int r = 0; r < RW; r++)
+#pragma unroll
+						for (int c = 0; c < C; c++) xin[r][c] = 0.0f;
+#pragma unroll 4
 					for (int ci = 0; ci < INC; ci++)
 					{
 						float w[C];
 						load_row<C>(w, re + ci * C);
 #pragma unroll
-						for (int r = 0; r < R; r++)
+						for (int r = 0; r < RW; r++)
 						{
-							const float a = sm[ci * STR + lane + 32 * r];
+							const float a = sm[ci * STR + fr[r]];
 #pragma unroll
 							for (int c = 0; c < C; c++) xin[r][c] = fmaf(w[c], a, xin[r][c]);
 						}
 					}
-					__syncwarp();   // all lanes have read the previous array's output before it is overwritten
+					team_sync<WPS>(barId);   // the whole team has read the previous array's output before it is overwritten
 				}
 #pragma unroll
-				for (int r = 0; r < R; r++)
+				for (int r = 0; r < RW; r++)
 #pragma unroll
-					for (int c = 0; c < C; c++) sm[c * STR + lane + 32 * r] = xin[r][c];
-				__syncwarp();
+					for (int c = 0; c < C; c++) sm[c * STR + fr[r]] = xin[r][c];
+				team_sync<WPS>(barId);
 			}
 
 			// ---- dilated conv (WaveNet.h:250-289): z = b + sum_k W_k x[t - (K-1-k) d]
-			float z[R][C];
+			float2 z2[RW][C2];
 			{
-				float b[C];
-				load_row<C>(b, wb + L.oConvB);
+				float2 b2[C2];
+				load_row2<C>(b2, wb + L.oConvB);
 #pragma unroll
-				for (int r = 0; r < R; r++)
+				for (int r = 0; r < RW; r++)
 #pragma unroll
-					for (int c = 0; c < C; c++) z[r][c] = b[c];
+					for (int c = 0; c < C2; c++) z2[r][c] = b2[c];
 			}
 			const int hist = (K - 1) * d;
-			const bool whole = WindowPipe<R, TMA>::is_whole(hist);
+			const bool whole = WindowPipe<RT, WPS, TMA>::is_whole(hist);
 			int winBase = 0;
 			for (int k = 0; k < K; k++)
 			{
 				const int D = (K - 1 - k) * d;
-				int src[R];
+				int src[RW];
 				if (D == 0)
 				{
 #pragma unroll
-					for (int r = 0; r < R; r++) src[r] = lane + 32 * r;
+					for (int r = 0; r < RW; r++) src[r] = fr[r];
 				}
 				else
 				{
@@ -377,25 +429,25 @@ namespace nab200
 					else if (k == 0) winBase = pipe.acquire(l, 0);
 					const int hb = whole ? (winBase + hist - D) : winBase;
 #pragma unroll
-					for (int r = 0; r < R; r++)
-					{
-						const int f = lane + 32 * r;
-						src[r] = (f >= D) ? (f - D) : (hb + f);
-					}
+					for (int r = 0; r < RW; r++) src[r] = (fr[r] >= D) ? (fr[r] - D) : (hb + fr[r]);
 				}
 				const float* __restrict__ wk = wb + k * C * C;
-#pragma unroll
+#pragma unroll 4
 				for (int ci = 0; ci < C; ci++)
 				{
-					float a[R];
+					float2 a2[RW];
 #pragma unroll
-					for (int r = 0; r < R; r++) a[r] = sm[src[r] + ci * STR];
-					float w[C];
-					load_row<C>(w, wk + ci * C);
+					for (int r = 0; r < RW; r++)
+					{
+						const float a = sm[src[r] + ci * STR];
+						a2[r] = make_float2(a, a);
+					}
+					float2 w2[C2];
+					load_row2<C>(w2, wk + ci * C);
 #pragma unroll
-					for (int r = 0; r < R; r++)
+					for (int r = 0; r < RW; r++)
 #pragma unroll
-						for (int c = 0; c < C; c++) z[r][c] = fmaf(w[c], a[r], z[r][c]);
+						for (int c = 0; c < C2; c++) ffma2(z2[r][c], w2[c], a2[r]);
 				}
 			}
 
@@ -404,13 +456,15 @@ namespace nab200
 				float w[C];
 				load_row<C>(w, wb + L.oMix);
 #pragma unroll
-				for (int r = 0; r < R; r++)
+				for (int r = 0; r < RW; r++)
 #pragma unroll
-					for (int c = 0; c < C; c++)
+					for (int c = 0; c < C2; c++)
 					{
-						const float v = activate<ACT>(fmaf(w[c], cond[r], z[r][c]));
-						z[r][c] = v;
-						head[r][c] += v;
+						const float v0 = activate<ACT>(fmaf(w[2 * c], cond[r], z2[r][c].x));
+						const float v1 = activate<ACT>(fmaf(w[2 * c + 1], cond[r], z2[r][c].y));
+						z2[r][c] = make_float2(v0, v1);
+						head2[r][c].x += v0;
+						head2[r][c].y += v1;
 					}
 			}
 
@@ -424,16 +478,16 @@ namespace nab200
 				const int first = n > Lp ? n - Lp : 0;
 				if (((hd | n) & 3) == 0)
 				{
-					// 16-byte path: lane j moves frames 4j..4j+3 (+128, ...) of every channel
+					// 16-byte path: lane j moves frames 4j..4j+3 of the channels this warp owns (c = half, half+WPS, ...)
 #pragma unroll
-					for (int rr = 0; rr < (R + 3) / 4; rr++)
+					for (int rr = 0; rr < (RT + 3) / 4; rr++)
 					{
 						const int f0 = 4 * (lane + 32 * rr);
-						if (f0 < n && f0 >= first && f0 < 32 * R)
+						if (f0 < n && f0 >= first && f0 < 32 * RT)
 						{
 							const int idx = (hd + f0) % Lp;
 #pragma unroll
-							for (int c = 0; c < C; c++)
+							for (int c = half; c < C; c += WPS)
 							{
 								const float4 v = *reinterpret_cast<const float4*>(sm + c * STR + f0);
 								*reinterpret_cast<float4*>(ring + (size_t)c * Lp + idx) = v;
@@ -444,9 +498,9 @@ namespace nab200
 				else
 				{
 #pragma unroll
-					for (int r = 0; r < R; r++)
+					for (int r = 0; r < RW; r++)
 					{
-						const int f = lane + 32 * r;
+						const int f = fr[r];
 						if (f < n && f >= first)
 						{
 							const int idx = (hd + f) % Lp;
@@ -461,39 +515,35 @@ namespace nab200
 			if (flags & kNeedOutput)
 			{
 				const float* __restrict__ w1 = wb + L.oOneW;   // [ci][co]
-				float bo[C];
-				load_row<C>(bo, wb + L.oOneB);
-				constexpr int RH = (R >= 2) ? R / 2 : 1;        // half the frames at a time to bound registers
-				__syncwarp();   // every lane has finished reading xcur (taps + write-back) for this layer
+				float2 bo2[C2];
+				load_row2<C>(bo2, wb + L.oOneB);
+				team_sync<WPS>(barId);   // the whole team has finished reading xcur (taps + write-back) for this layer
 #pragma unroll
-				for (int half = 0; half < R / RH; half++)
+				for (int r = 0; r < RW; r++)
 				{
-					float o[RH][C];
+					float2 o2[C2];
 #pragma unroll
-					for (int r = 0; r < RH; r++)
-#pragma unroll
-						for (int c = 0; c < C; c++) o[r][c] = bo[c];
+					for (int c = 0; c < C2; c++) o2[c] = bo2[c];
 #pragma unroll
 					for (int ci = 0; ci < C; ci++)
 					{
-						float w[C];
-						load_row<C>(w, w1 + ci * C);
+						float2 w2[C2];
+						load_row2<C>(w2, w1 + ci * C);
+						const float zv = (ci & 1) ? z2[r][ci >> 1].y : z2[r][ci >> 1].x;
+						const float2 zz = make_float2(zv, zv);
 #pragma unroll
-						for (int r = 0; r < RH; r++)
-#pragma unroll
-							for (int c = 0; c < C; c++) o[r][c] = fmaf(w[c], z[half * RH + r][ci], o[r][c]);
+						for (int c = 0; c < C2; c++) ffma2(o2[c], w2[c], zz);
 					}
 					// own-frame elements only: no cross-lane hazard until the next layer's taps
 #pragma unroll
-					for (int r = 0; r < RH; r++)
-#pragma unroll
-						for (int c = 0; c < C; c++)
-						{
-							const int a = c * STR + lane + 32 * (half * RH + r);
-							sm[a] = o[r][c] + sm[a];
-						}
+					for (int c = 0; c < C2; c++)
+					{
+						const int a0 = (2 * c) * STR + fr[r];
+						sm[a0] = o2[c].x + sm[a0];
+						sm[a0 + STR] = o2[c].y + sm[a0 + STR];
+					}
 				}
-				__syncwarp();
+				team_sync<WPS>(barId);
 			}
 
 			// ---- head conv over the summed head (WaveNet.h:658-660) -- last layer of the array
@@ -504,7 +554,7 @@ namespace nab200
 					float hbv[H];
 					load_row<H>(hbv, wb + L.oHeadB);
 #pragma unroll
-					for (int r = 0; r < R; r++)
+					for (int r = 0; r < RW; r++)
 #pragma unroll
 						for (int h = 0; h < H; h++) hout[r][h] = hbv[h];
 				}
@@ -517,39 +567,42 @@ namespace nab200
 						float w[H];
 						load_row<H>(w, hw + c * H);
 #pragma unroll
-						for (int r = 0; r < R; r++)
+						for (int r = 0; r < RW; r++)
+						{
+							const float hv = (c & 1) ? head2[r][c >> 1].y : head2[r][c >> 1].x;
 #pragma unroll
-							for (int h = 0; h < H; h++) hout[r][h] = fmaf(w[h], head[r][c], hout[r][h]);
+							for (int h = 0; h < H; h++) hout[r][h] = fmaf(w[h], hv, hout[r][h]);
+						}
 					}
 				}
 				else
 				{
 					// K>1 head (A2: 8->1, K=16): the summed head is a conv input with its own history ring
-					__syncwarp();
+					team_sync<WPS>(barId);
 #pragma unroll
-					for (int r = 0; r < R; r++)
+					for (int r = 0; r < RW; r++)
 #pragma unroll
-						for (int c = 0; c < C; c++) sm[c * STR + lane + 32 * r] = head[r][c];
+						for (int c = 0; c < C2; c++)
+						{
+							sm[(2 * c) * STR + fr[r]] = head2[r][c].x;
+							sm[(2 * c + 1) * STR + fr[r]] = head2[r][c].y;
+						}
 					const int convJobs = hist == 0 ? 0 : (whole ? 1 : (K - 1));
-					const int hwin = pipe.acquire(l, convJobs);   // whole head history: Kh-1 frames (also syncs the warp)
+					const int hwin = pipe.acquire(l, convJobs);   // whole head history: Kh-1 frames (also syncs the team)
 					const int Hh = Kh - 1;
 					for (int k = 0; k < Kh; k++)
 					{
 						const int D = Hh - k;
-						int src[R];
+						int src[RW];
 #pragma unroll
-						for (int r = 0; r < R; r++)
-						{
-							const int f = lane + 32 * r;
-							src[r] = (f >= D) ? (f - D) : (hwin + Hh - D + f);
-						}
+						for (int r = 0; r < RW; r++) src[r] = (fr[r] >= D) ? (fr[r] - D) : (hwin + Hh - D + fr[r]);
 #pragma unroll
 						for (int c = 0; c < C; c++)
 						{
 							float w[H];
 							load_row<H>(w, hw + (k * C + c) * H);
 #pragma unroll
-							for (int r = 0; r < R; r++)
+							for (int r = 0; r < RW; r++)
 							{
 								const float a = sm[src[r] + c * STR];
 #pragma unroll
@@ -563,48 +616,56 @@ namespace nab200
 					const int hd = pipe.hd[A.headRingIdx];
 					const int first = n > Lp ? n - Lp : 0;
 #pragma unroll
-					for (int r = 0; r < R; r++)
+					for (int r = 0; r < RW; r++)
 					{
-						const int f = lane + 32 * r;
+						const int f = fr[r];
 						if (f < n && f >= first)
 						{
 							const int idx = (hd + f) % Lp;
 #pragma unroll
-							for (int c = 0; c < C; c++) ring[(size_t)c * Lp + idx] = head[r][c];
+							for (int c = 0; c < C2; c++)
+							{
+								ring[(size_t)(2 * c) * Lp + idx] = head2[r][c].x;
+								ring[(size_t)(2 * c + 1) * Lp + idx] = head2[r][c].y;
+							}
 						}
 					}
-					__syncwarp();
+					team_sync<WPS>(barId);
 				}
 			}
 		}
 	}
 
-	constexpr int kWnWarps = 8;
+	constexpr int kWnStreamsPerCta = 4;   // two CTAs per SM: each has its own weight pipeline, so the CTAs drift out of phase
+	constexpr int kWnCtasPerSm = 2;
 
-	template <int C0, int C1, int R>
+	template <int C0, int C1, int RT>
 	struct WnSmem
 	{
 		static constexpr int CM = C0 > C1 ? C0 : C1;
-		static constexpr int STR = 32 * R + 4;
+		static constexpr int STR = 32 * RT + 4;
 		static constexpr int kArenaFloats = 3 * CM * STR;
-		static constexpr int kWarpBytes = ((kArenaFloats * 4 + kMaxRings * 4 + 16 + 15) / 16) * 16;
+		static constexpr int kStreamBytes = ((kArenaFloats * 4 + kMaxRings * 4 + 16 + 15) / 16) * 16;
 	};
 
-	// C1 == 0: single-array model (A2).  ACT: 0 tanh, 1 LeakyReLU.
-	template <int C0, int C1, int R, int ACT, bool TMA>
-	__global__ void __launch_bounds__(kWnWarps * 32, 1)
+	// C1 == 0: single-array model (A2).  ACT: 0 tanh, 1 LeakyReLU.  RT frame rows per stream, WPS warps per stream.
+	template <int C0, int C1, int RT, int WPS, int ACT, bool TMA>
+	__global__ void __launch_bounds__(kWnStreamsPerCta * WPS * 32, (WPS == 2 ? kWnCtasPerSm : 1))
 		wavenet_fwd_kernel(const __grid_constant__ WnModelDev M, const float* __restrict__ Wg, float* __restrict__ state,
 			int* __restrict__ heads, const float* in, float* out, long long inSS, long long inFS, long long outSS, long long outFS,
 			int S, int n)
 	{
-		using SM = WnSmem<C0, C1, R>;
+		using SM = WnSmem<C0, C1, RT>;
 		constexpr int STR = SM::STR;
 		constexpr int CM = SM::CM;
+		constexpr int RW = RT / WPS;
 		extern __shared__ __align__(16) unsigned char smem_raw[];
 
 		const int tid = threadIdx.x;
 		const int warp = tid >> 5;
 		const int lane = tid & 31;
+		const int team = warp / WPS;      // stream slot inside the CTA
+		const int half = warp % WPS;
 
 		CtaCtx cx;
 		cx.M = &M;
@@ -613,36 +674,38 @@ namespace nab200
 		cx.wbStride = M.maxBlock;
 		cx.q = 0;
 		cx.tid = tid;
-		cx.nthreads = kWnWarps * 32;
+		cx.nthreads = kWnStreamsPerCta * WPS * 32;
 
-		unsigned char* wbase = smem_raw + (size_t)2 * M.maxBlock * 4 + (size_t)warp * SM::kWarpBytes;
+		unsigned char* wbase = smem_raw + (size_t)2 * M.maxBlock * 4 + (size_t)team * SM::kStreamBytes;
 		float* sm = reinterpret_cast<float*>(wbase);
 		int* hd = reinterpret_cast<int*>(wbase + SM::kArenaFloats * 4);
 		unsigned long long* bars = reinterpret_cast<unsigned long long*>(wbase + SM::kArenaFloats * 4 + kMaxRings * 4);
 
-		WindowPipe<R, TMA> pipe;
+		WindowPipe<RT, WPS, TMA> pipe;
 		pipe.M = &M;
 		pipe.sm = sm;
 		pipe.hd = hd;
-		pipe.bar[0] = smem_u32(&bars[0]);
-		pipe.bar[1] = smem_u32(&bars[1]);
-		pipe.winOff[0] = CM * STR;
-		pipe.winOff[1] = 2 * CM * STR;
+		pipe.bar0 = smem_u32(&bars[0]);
+		pipe.winOff0 = CM * STR;
+		pipe.winStep = CM * STR;
 		pipe.stride = STR;
 		pipe.n = n;
 		pipe.lane = lane;
+		pipe.half = half;
+		pipe.barId = 1 + team;   // named barrier 0 is __syncthreads
 		pipe.issued = 0;
 		pipe.consumed = 0;
 		pipe.phase = 0;
 		pipe.pl = M.numLayers;
 		pipe.pt = 0;
+		pipe.st = state;
 
 		if (TMA)
 		{
-			if (lane == 0)
+			if (half == 0 && lane == 0)
 			{
-				mbar_init(pipe.bar[0], 1);
-				mbar_init(pipe.bar[1], 1);
+				mbar_init(pipe.bar0, 1);
+				mbar_init(pipe.bar0 + 8u, 1);
 				asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 			}
 			asm volatile("fence.proxy.async;" ::: "memory");
@@ -651,70 +714,77 @@ namespace nab200
 
 		issue_weight_block(cx, 0, 0);
 
-		const int numGroups = (S + kWnWarps - 1) / kWnWarps;
+		const int numGroups = (S + kWnStreamsPerCta - 1) / kWnStreamsPerCta;
 		for (int g = blockIdx.x; g < numGroups; g += gridDim.x)
 		{
-			const int s = g * kWnWarps + warp;
+			const int s = g * kWnStreamsPerCta + team;
 			const bool active = s < S;
-			float cond[R];
+			float cond[RW];
 #pragma unroll
-			for (int r = 0; r < R; r++) cond[r] = 0.0f;
+			for (int r = 0; r < RW; r++) cond[r] = 0.0f;
 			if (active)
 			{
 				pipe.st = state + (size_t)s * M.stateStride;
-				__syncwarp();
-				for (int i = lane; i < M.numRings; i += 32) hd[i] = heads[(size_t)s * M.numRings + i];
-				__syncwarp();
+				team_sync<WPS>(pipe.barId);   // previous stream's last readers of hd are done
+				if (half == 0)
+					for (int i = lane; i < M.numRings; i += 32) hd[i] = heads[(size_t)s * M.numRings + i];
+				team_sync<WPS>(pipe.barId);
 #pragma unroll
-				for (int r = 0; r < R; r++)
+				for (int r = 0; r < RW; r++)
 				{
-					const int f = lane + 32 * r;
+					const int f = lane + 32 * (r * WPS + half);
 					if (f < n) cond[r] = in[(long long)s * inSS + (long long)f * inFS];
 				}
 				pipe.start();
 			}
 
-			float head0[R][C0];
+			float2 head0[RW][C0 / 2];
 #pragma unroll
-			for (int r = 0; r < R; r++)
+			for (int r = 0; r < RW; r++)
 #pragma unroll
-				for (int c = 0; c < C0; c++) head0[r][c] = 0.0f;
+				for (int c = 0; c < C0 / 2; c++) head0[r][c] = make_float2(0.0f, 0.0f);
 
-			float y[R];
+			float y[RW];
 			if (C1 == 0)
 			{
-				float hout[R][1];
-				run_array<C0, 1, 1, R, ACT, TMA>(cx, pipe, M.arrays[0], active, n, lane, cond, head0, hout);
+				float hout[RW][1];
+				run_array<C0, 1, 1, RW, WPS, ACT, TMA>(cx, pipe, M.arrays[0], active, n, lane, half, cond, head0, hout);
 #pragma unroll
-				for (int r = 0; r < R; r++) y[r] = hout[r][0];
+				for (int r = 0; r < RW; r++) y[r] = hout[r][0];
 			}
 			else
 			{
-				constexpr int C1x = C1 > 0 ? C1 : 1;
-				float head1[R][C1x];
-				run_array<C0, 1, C1x, R, ACT, TMA>(cx, pipe, M.arrays[0], active, n, lane, cond, head0, head1);
-				float hout[R][1];
-				run_array<C1x, C0, 1, R, ACT, TMA>(cx, pipe, M.arrays[1], active, n, lane, cond, head1, hout);
+				constexpr int C1x = C1 > 0 ? C1 : 2;
+				float h1[RW][C1x];
+				run_array<C0, 1, C1x, RW, WPS, ACT, TMA>(cx, pipe, M.arrays[0], active, n, lane, half, cond, head0, h1);
+				float2 head1[RW][C1x / 2];
 #pragma unroll
-				for (int r = 0; r < R; r++) y[r] = hout[r][0];
+				for (int r = 0; r < RW; r++)
+#pragma unroll
+					for (int c = 0; c < C1x / 2; c++) head1[r][c] = make_float2(h1[r][2 * c], h1[r][2 * c + 1]);
+				float hout[RW][1];
+				run_array<C1x, C0, 1, RW, WPS, ACT, TMA>(cx, pipe, M.arrays[1], active, n, lane, half, cond, head1, hout);
+#pragma unroll
+				for (int r = 0; r < RW; r++) y[r] = hout[r][0];
 			}
 
 			if (active)
 			{
 #pragma unroll
-				for (int r = 0; r < R; r++)
+				for (int r = 0; r < RW; r++)
 				{
-					const int f = lane + 32 * r;
+					const int f = lane + 32 * (r * WPS + half);
 					if (f < n) out[(long long)s * outSS + (long long)f * outFS] = M.headScale * y[r];   // WaveNet.h:793-798
 				}
 				// advance every ring head by n frames
-				for (int i = lane; i < M.numRings; i += 32)
-				{
-					const int Lp = M.ringLp[i];
-					int h = hd[i] + (n % Lp);
-					if (h >= Lp) h -= Lp;
-					heads[(size_t)s * M.numRings + i] = h;
-				}
+				if (half == 0)
+					for (int i = lane; i < M.numRings; i += 32)
+					{
+						const int Lp = M.ringLp[i];
+						int h = hd[i] + (n % Lp);
+						if (h >= Lp) h -= Lp;
+						heads[(size_t)s * M.numRings + i] = h;
+					}
 			}
 		}
 		cp_async_wait_all();
@@ -808,28 +878,30 @@ namespace nab200
 	}
 
 	// ---- host-side launchers ---------------------------------------------------------------------------------
-	template <int C0, int C1, int R, int ACT>
+	template <int C0, int C1, int RT, int WPS, int ACT>
 	static cudaError_t launch_variant(const WnModelDev& M, const WnLaunch& a)
 	{
-		using SM = WnSmem<C0, C1, R>;
-		const size_t smem = (size_t)2 * M.maxBlock * 4 + (size_t)kWnWarps * SM::kWarpBytes;
-		const int numGroups = (a.S + kWnWarps - 1) / kWnWarps;
-		int grid = numGroups < a.numSMs ? numGroups : a.numSMs;
+		using SM = WnSmem<C0, C1, RT>;
+		const size_t smem = (size_t)2 * M.maxBlock * 4 + (size_t)kWnStreamsPerCta * SM::kStreamBytes;
+		const int numGroups = (a.S + kWnStreamsPerCta - 1) / kWnStreamsPerCta;
+		const int maxCtas = a.numSMs * kWnCtasPerSm;
+		int grid = numGroups < maxCtas ? numGroups : maxCtas;
 		if (grid < 1) grid = 1;
+		const int threads = kWnStreamsPerCta * WPS * 32;
 		cudaError_t err;
 		if (a.useTma)
 		{
-			auto kfn = wavenet_fwd_kernel<C0, C1, R, ACT, true>;
+			auto kfn = wavenet_fwd_kernel<C0, C1, RT, WPS, ACT, true>;
 			err = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 			if (err != cudaSuccess) return err;
-			kfn<<<grid, kWnWarps * 32, smem, a.stream>>>(M, a.weights, a.state, a.heads, a.in, a.out, a.inSS, a.inFS, a.outSS, a.outFS, a.S, a.n);
+			kfn<<<grid, threads, smem, a.stream>>>(M, a.weights, a.state, a.heads, a.in, a.out, a.inSS, a.inFS, a.outSS, a.outFS, a.S, a.n);
 		}
 		else
 		{
-			auto kfn = wavenet_fwd_kernel<C0, C1, R, ACT, false>;
+			auto kfn = wavenet_fwd_kernel<C0, C1, RT, WPS, ACT, false>;
 			err = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 			if (err != cudaSuccess) return err;
-			kfn<<<grid, kWnWarps * 32, smem, a.stream>>>(M, a.weights, a.state, a.heads, a.in, a.out, a.inSS, a.inFS, a.outSS, a.outFS, a.S, a.n);
+			kfn<<<grid, threads, smem, a.stream>>>(M, a.weights, a.state, a.heads, a.in, a.out, a.inSS, a.inFS, a.outSS, a.outFS, a.S, a.n);
 		}
 		return cudaGetLastError();
 	}
@@ -837,9 +909,9 @@ namespace nab200
 	template <int C0, int C1, int ACT>
 	static cudaError_t launch_by_frames(const WnModelDev& M, const WnLaunch& a)
 	{
-		if (a.n <= 32) return launch_variant<C0, C1, 1, ACT>(M, a);
-		if (a.n <= 128) return launch_variant<C0, C1, 4, ACT>(M, a);
-		if (C0 <= 8 && a.n <= 256) return launch_variant<C0, C1, (C0 <= 8 ? 8 : 4), ACT>(M, a);
+		if (a.n <= 32) return launch_variant<C0, C1, 1, 1, ACT>(M, a);                 // one warp per stream, one frame per lane
+		if (a.n <= 128) return launch_variant<C0, C1, 4, 2, ACT>(M, a);                // two warps per stream, two frames per lane
+		if (C0 <= 8 && a.n <= 256) return launch_variant<C0, C1, (C0 <= 8 ? 8 : 4), 2, ACT>(M, a);
 		return cudaErrorInvalidValue;
 	}
 

@@ -3,7 +3,7 @@
 mkdir -p gpurun_out
 timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -25 > gpurun_out/pytest_gpu.log
 cat gpurun_out/pytest_gpu.log
-timeout 600 python bench.py --steps 50 --warmup 5 > gpurun_out/bench_a1_standard.json 2> gpurun_out/bench_a1_standard.err; cat gpurun_out/bench_a1_standard.json; tail -3 gpurun_out/bench_a1_standard.err
+timeout 600 python bench.py > gpurun_out/bench_a1_standard.json 2> gpurun_out/bench_a1_standard.err; cat gpurun_out/bench_a1_standard.json; tail -3 gpurun_out/bench_a1_standard.err
 timeout 300 python bench.py --workload lstm_1x16 --steps 50 --warmup 5 --cpu-seconds 4 > gpurun_out/bench_lstm_1x16.json 2>/dev/null; cat gpurun_out/bench_lstm_1x16.json
 timeout 300 python bench.py --workload a2_full --steps 30 --warmup 5 --cpu-seconds 4 > gpurun_out/bench_a2_full.json 2>/dev/null; cat gpurun_out/bench_a2_full.json
 timeout 300 python bench.py --workload a1_nano --steps 50 --warmup 5 --cpu-seconds 4 > gpurun_out/bench_a1_nano.json 2>/dev/null; cat gpurun_out/bench_a1_nano.json
