@@ -20,6 +20,7 @@ namespace nab200
 		Options& o = GetOptions();
 		int prev = -1;
 		if (strcmp(name, "use_tma") == 0) { prev = o.useTma; o.useTma = value; }
+		else if (strcmp(name, "use_tc") == 0) { prev = o.useTc; o.useTc = value; }
 		else if (strcmp(name, "max_grid_ctas") == 0) { prev = o.maxGridCtas; o.maxGridCtas = value; }
 		return prev;
 	}
@@ -183,7 +184,8 @@ namespace nab200
 	{
 		const WnModelDev& M = packed.dev;
 		const int C0 = M.arrays[0].C, C1 = M.numArrays > 1 ? M.arrays[1].C : 0;
-		if (!wavenet_variant_supported(C0, C1, M.arrays[0].act))
+		const bool ok = M.tc ? wavenet_tc_variant_supported(C0, C1, M.arrays[0].act) : wavenet_variant_supported(C0, C1, M.arrays[0].act);
+		if (!ok)
 		{
 			std::stringstream ss;
 			ss << "unsupported model: no sm_100a WaveNet kernel for channel layout (" << M.arrays[0].realC << ", "
@@ -235,7 +237,7 @@ namespace nab200
 
 	bool WaveNetEngine::ProcessDevice(const float* in, float* out, long long inSS, long long inFS, long long outSS, long long outFS, size_t S, size_t n)
 	{
-		const int maxPass = wavenet_max_frames_per_pass(packed.dev.arrays[0].C);
+		const int maxPass = packed.dev.tc ? 128 : wavenet_max_frames_per_pass(packed.dev.arrays[0].C);
 		const Options& opt = GetOptions();
 		size_t done = 0;
 		while (done < n)
@@ -253,7 +255,7 @@ namespace nab200
 			a.numSMs = (opt.maxGridCtas > 0) ? opt.maxGridCtas : numSMs;
 			a.useTma = opt.useTma != 0;
 			a.stream = stream;
-			if (!CudaOk(wavenet_launch(packed.dev, a), "wavenet_fwd_kernel launch")) return false;
+			if (!CudaOk(packed.dev.tc ? wavenet_tc_launch(packed.dev, a) : wavenet_launch(packed.dev, a), "wavenet kernel launch")) return false;
 			done += chunk;
 		}
 		return true;

@@ -16,6 +16,7 @@ namespace nab200
 	struct Options
 	{
 		int useTma = 1;         // stage history windows with cp.async.bulk + mbarrier (0: plain loads, debugging aid)
+		int useTc = 1;          // tensor-core (tcgen05) WaveNet kernel where the architecture fits; 0: CUDA-core kernel
 		int maxGridCtas = 0;    // 0: one CTA per SM
 	};
 	Options& GetOptions();

@@ -68,6 +68,9 @@ namespace nab200
 	};
 
 	PackedWaveNet PackWaveNet(const WaveNetDesc& desc);
+	// tensor-core (tcgen05) packing; TcSupported tells whether the architecture fits that kernel
+	bool WaveNetTcSupported(const WaveNetDesc& desc);
+	PackedWaveNet PackWaveNetTc(const WaveNetDesc& desc);
 	PackedLstm PackLstm(const LstmDesc& desc);
 
 	int PadChannels(int c);   // 2, 4, 8, 12, 16

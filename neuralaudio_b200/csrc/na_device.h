@@ -35,6 +35,7 @@ namespace nab200
 		int wSize;     // block size in floats (multiple of 4)
 		int oConvB, oMix, oOneW, oOneB, oRe, oHeadW, oHeadB;
 		int array;     // index of the owning layer array
+		int oConvLo, oOneLo;   // tensor-core packing only: low parts of the 3xTF32 split (see below)
 	};
 
 	struct WnArray
@@ -49,12 +50,19 @@ namespace nab200
 		int realC, realH;
 	};
 
+	// Tensor-core packing (WnModelDev::tc == 1), used by wavenet_tc_kernels.cu:
+	//   rings are [C/4][Lp][4] (channel-group major, a frame's 4 channels contiguous) so a window lands in shared memory
+	//   directly in the tcgen05 K-major operand layout and a tap shift is a 16-byte row offset;
+	//   block = convHi[K][C/4][C][4] | convLo | oneHi[C/4][C][4] | oneLo | convB[C] | mix[C] | oneB[C] | re[inC][C] | headW[C][H] | headB[H]
+	//   where X[kc][n][i] = W[out n][in 4*kc+i], hi = tf32-rounded weight, lo = weight - hi.
 	struct WnModelDev
 	{
 		int numArrays, numLayers, numRings;
 		int stateStride;     // floats of ring state per stream (multiple of 4)
 		int maxBlock;        // largest weight block in floats
 		float headScale;
+		int tc;              // 1: tensor-core packing / ring layout
+		int pad0;
 		WnArray arrays[kMaxArrays];
 		WnLayer layers[kMaxLayers];
 		int ringLp[kMaxRings];

@@ -21,6 +21,9 @@ namespace nab200
 	};
 
 	cudaError_t wavenet_launch(const WnModelDev& M, const WnLaunch& a);
+	// tcgen05 path (WnModelDev::tc == 1 packing), n <= 128
+	cudaError_t wavenet_tc_launch(const WnModelDev& M, const WnLaunch& a);
+	bool wavenet_tc_variant_supported(int C0, int C1, int act);
 	cudaError_t wavenet_prewarm_launch(const WnModelDev& M, const float* weights, float* tmpl, cudaStream_t stream);
 	cudaError_t state_fill_launch(float* state, const float* tmpl, int strideFloats, long long numStreams, cudaStream_t stream);
 	cudaError_t int_fill_launch(int* p, int v, long long total, cudaStream_t stream);

@@ -248,7 +248,8 @@ inline namespace b200
 		model->isStatic = desc.isStatic;
 		// only the static adapters override GetReceptiveFieldSize (InternalModel.h:99-102); dynamic models report -1
 		model->receptiveField = desc.isStatic ? desc.receptiveField : -1;
-		auto* engine = new nab200::WaveNetEngine(loader->GetDevice(), nab200::PackWaveNet(desc));
+		const bool useTc = nab200::GetOptions().useTc != 0 && nab200::WaveNetTcSupported(desc);
+		auto* engine = new nab200::WaveNetEngine(loader->GetDevice(), useTc ? nab200::PackWaveNetTc(desc) : nab200::PackWaveNet(desc));
 		model->engine = engine;
 		if (!engine->Init() || !engine->Upload()) { delete model; return nullptr; }
 		return model;

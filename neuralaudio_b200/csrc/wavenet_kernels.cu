@@ -807,6 +807,29 @@ namespace nab200
 			{
 				const WnLayer& L = M.layers[A.firstLayer + li];
 				const float* wb = Wg + L.wOff;
+				// weight accessors for the two packings (na_device.h); the tensor-core packing stores hi + lo
+				auto convW = [&](int k, int ci, int co) -> float
+				{
+					if (M.tc)
+					{
+						const int at = ((k * (C >> 2) + (ci >> 2)) * C + co) * 4 + (ci & 3);
+						return wb[at] + wb[L.oConvLo + at];
+					}
+					return wb[(k * C + ci) * C + co];
+				};
+				auto oneW = [&](int ci, int co) -> float
+				{
+					if (M.tc)
+					{
+						const int at = ((ci >> 2) * C + co) * 4 + (ci & 3);
+						return wb[L.oOneW + at] + wb[L.oOneLo + at];
+					}
+					return wb[L.oOneW + ci * C + co];
+				};
+				auto ringAt = [&](int ringOff, int Lp, int c, int i) -> int
+				{
+					return M.tc ? ringOff + (((c >> 2) * Lp + i) << 2) + (c & 3) : ringOff + c * Lp + i;
+				};
 				if (L.flags & kFirstInArray)
 				{
 					// rechannel of the (zero) input / previous array output; condition is zero
@@ -819,13 +842,13 @@ namespace nab200
 				}
 				// history := this layer's input column everywhere (CopyBuffer, WaveNet.h:74-82)
 				if (lane < C)
-					for (int i = 0; i < L.Lp; i++) tmpl[L.ringOff + lane * L.Lp + i] = x[lane];
+					for (int i = 0; i < L.Lp; i++) tmpl[ringAt(L.ringOff, L.Lp, lane, i)] = x[lane];
 				float acc = 0.0f;
 				if (lane < C)
 				{
 					acc = wb[L.oConvB + lane];
 					for (int k = 0; k < L.K; k++)
-						for (int ci = 0; ci < C; ci++) acc = fmaf(wb[(k * C + ci) * C + lane], x[ci], acc);
+						for (int ci = 0; ci < C; ci++) acc = fmaf(convW(k, ci, lane), x[ci], acc);
 					acc = (A.act == 0) ? fast_tanh_div(acc) : (acc > 0.0f ? acc : 0.01f * acc);   // mix-in term is W*0
 					head[lane] += acc;
 				}
@@ -835,7 +858,7 @@ namespace nab200
 				if (lane < C)
 				{
 					o = wb[L.oOneB + lane];
-					for (int ci = 0; ci < C; ci++) o = fmaf(wb[L.oOneW + ci * C + lane], z[ci], o);
+					for (int ci = 0; ci < C; ci++) o = fmaf(oneW(ci, lane), z[ci], o);
 					o += x[lane];
 				}
 				__syncwarp();
@@ -844,7 +867,7 @@ namespace nab200
 				if (L.flags & kLastInArray)
 				{
 					if (A.Kh > 1 && lane < C)
-						for (int i = 0; i < A.headLp; i++) tmpl[A.headRingOff + lane * A.headLp + i] = head[lane];
+						for (int i = 0; i < A.headLp; i++) tmpl[ringAt(A.headRingOff, A.headLp, lane, i)] = head[lane];
 					// head conv output feeds the next array's head accumulator
 					float ho = 0.0f;
 					if (lane < A.H)

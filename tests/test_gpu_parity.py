@@ -210,6 +210,32 @@ def test_tma_and_plain_window_paths_are_bit_identical(na, tmp_path):
     assert np.array_equal(outs[0], outs[1])
 
 
+@pytest.mark.parametrize("name", ["syn_a1_standard", "syn_a1_lite"])
+def test_tensor_core_and_cuda_core_kernels_agree(na, O, name, tmp_path):
+    """The tcgen05 (3xTF32) kernel and the CUDA-core fp32 kernel are two independent implementations of the same
+    path with different state layouts; both must sit within tolerance of the oracle and of each other."""
+    g = load_golden(golden_files(name)[0])
+    mf = model_file_for(g, tmp_path)
+    S, n, calls = 12, 128, 10
+    x = np.random.default_rng(17).uniform(-1, 1, (calls, S, n)).astype(np.float32)
+    outs = []
+    for tc in (1, 0):
+        prev = na.set_option("use_tc", tc)
+        try:
+            m = _load(na, mf, streams=S)
+            y = np.empty_like(x)
+            for k in range(calls):
+                m.ProcessBatch(x[k], y[k], S, n)
+            outs.append(y)
+        finally:
+            na.set_option("use_tc", prev)
+    assert float(np.abs(outs[0] - outs[1]).max()) <= 2e-6
+    for s in (0, S - 1):
+        ys = O.PortModel.from_file(mf).process(np.ascontiguousarray(x[:, s, :]).reshape(-1))
+        for y in outs:
+            assert float(np.abs(ys - y[:, s, :].reshape(-1)).max()) <= WAVENET_TOL
+
+
 def test_full_size_config_properties(na, O, tmp_path):
     """BASELINE.json cfg 2 (A1 Standard, 4096 streams x 128 frames) at full size, through size-independent
     properties: identical inputs => bit-identical streams (independence + determinism), a tile of streams checked

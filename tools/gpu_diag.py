@@ -46,7 +46,18 @@ def run(name, tma, streams, frames, calls):
     sys.stdout.flush()
 
 
+def tc_first():
+    for name in ["syn_a1_standard", "syn_a1_lite", "ref_BossWN_standard"]:
+        run(name, 1, 1, 128, 16)
+        run(name, 1, 1, 37, 16)
+    run("syn_a1_standard", 1, 40, 128, 8)
+    run("syn_a1_standard", 1, 700, 128, 3)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "tc":
+        tc_first()
+        sys.exit(0)
     subprocess.run(["nvidia-smi", "--query-gpu=name,driver_version,memory.total", "--format=csv"])
     for name in ["syn_lstm_1x16", "syn_lstm_2x8", "ref_tw40"]:
         run(name, 0, 1, 128, 16)
