@@ -231,7 +231,45 @@ namespace nab200
 	bool WaveNetEngine::Prewarm()
 	{
 		if (!CudaOk(cudaSetDevice(device), "cudaSetDevice")) return false;
+		// steady state under silence (WaveNetModelT::Prewarm, WaveNet.h:746-766), computed analytically in fp32
 		if (!CudaOk(wavenet_prewarm_launch(packed.dev, dBlob, dBlob + weightFloats, stream), "wavenet_prewarm")) return false;
+		if (packed.dev.tc)
+		{
+			// The tensor-core kernel evaluates the contractions as 3xTF32, whose silence fixed point differs from the
+			// fp32 one in the last bits; a high-gain model turns that step into a visible start-up transient.  Let the
+			// template settle under the kernel's own arithmetic: one scratch stream, zero input, one receptive field.
+			const WnModelDev& M = packed.dev;
+			int rf = 0;
+			for (int i = 0; i < M.numRings; i++) rf += M.ringLp[i];
+			const int frames = 128;
+			const int passes = (rf + frames - 1) / frames + 2;
+			float* scratch = nullptr;
+			int* scratchHeads = nullptr;
+			float* io = nullptr;
+			if (!CudaOk(cudaMalloc(&scratch, (size_t)M.stateStride * 4), "cudaMalloc(prewarm scratch)")) return false;
+			bool ok = CudaOk(cudaMalloc(&scratchHeads, (size_t)M.numRings * 4), "cudaMalloc(prewarm scratch)") &&
+				CudaOk(cudaMalloc(&io, (size_t)frames * 2 * 4), "cudaMalloc(prewarm scratch)");
+			ok = ok && CudaOk(cudaMemcpyAsync(scratch, dBlob + weightFloats, (size_t)M.stateStride * 4, cudaMemcpyDeviceToDevice, stream), "cudaMemcpy");
+			ok = ok && CudaOk(cudaMemsetAsync(scratchHeads, 0, (size_t)M.numRings * 4, stream), "cudaMemset");
+			ok = ok && CudaOk(cudaMemsetAsync(io, 0, (size_t)frames * 2 * 4, stream), "cudaMemset");
+			for (int p = 0; ok && p < passes; p++)
+			{
+				WnLaunch a;
+				a.weights = dBlob; a.state = scratch; a.heads = scratchHeads;
+				a.in = io; a.out = io + frames;
+				a.inSS = frames; a.inFS = 1; a.outSS = frames; a.outFS = 1;
+				a.S = 1; a.n = frames; a.numSMs = numSMs; a.useTma = true; a.stream = stream;
+				ok = CudaOk(wavenet_tc_launch(M, a), "wavenet_tc prewarm settle");
+			}
+			// under constant input every ring column holds the same value, so the settled rings are a valid template
+			// for ring head 0 whatever position the scratch heads ended at
+			ok = ok && CudaOk(cudaMemcpyAsync(dBlob + weightFloats, scratch, (size_t)M.stateStride * 4, cudaMemcpyDeviceToDevice, stream), "cudaMemcpy");
+			ok = ok && CudaOk(cudaStreamSynchronize(stream), "cudaStreamSynchronize");
+			cudaFree(scratch);
+			if (scratchHeads) cudaFree(scratchHeads);
+			if (io) cudaFree(io);
+			if (!ok) return false;
+		}
 		return ResetStreams();
 	}
 

@@ -29,6 +29,8 @@ namespace nab200
 		constexpr int kRows = 256;      // rows per XE plane
 		constexpr int kCur = 128;       // first row of the current frames
 		constexpr int kWbRows = 128;    // rows per plane of the second tap-window buffer
+		constexpr int kIssuers = 3;     // MMA-issuing threads (lane 0 of warps 0..2), one TMEM accumulator each
+		constexpr int kTmemCols = 128;  // D0[3] | D1[3] | Zhi | Zlo, 16 columns each
 
 		__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -43,6 +45,58 @@ namespace nab200
 		}
 
 		__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+		{
+			asm volatile(
+				"{\n"
+				".reg .pred P1;\n"
+				"LAB_WAIT:\n"
+				"mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+				"@P1 bra DONE;\n"
+				"bra LAB_WAIT;\n"
+				"DONE:\n"
+				"}" ::"r"(bar), "r"(parity) : "memory");
+		}
+
+		__device__ __forceinline__ void mbar_wait_weights(uint32_t bar, uint32_t parity)
+		{
+			asm volatile(
+				"{\n"
+				".reg .pred P1;\n"
+				"LAB_WAIT:\n"
+				"mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+				"@P1 bra DONE;\n"
+				"bra LAB_WAIT;\n"
+				"DONE:\n"
+				"}" ::"r"(bar), "r"(parity) : "memory");
+		}
+
+		__device__ __forceinline__ void mbar_wait_window(uint32_t bar, uint32_t parity)
+		{
+			asm volatile(
+				"{\n"
+				".reg .pred P1;\n"
+				"LAB_WAIT:\n"
+				"mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+				"@P1 bra DONE;\n"
+				"bra LAB_WAIT;\n"
+				"DONE:\n"
+				"}" ::"r"(bar), "r"(parity) : "memory");
+		}
+
+		__device__ __forceinline__ void mbar_wait_conv(uint32_t bar, uint32_t parity)
+		{
+			asm volatile(
+				"{\n"
+				".reg .pred P1;\n"
+				"LAB_WAIT:\n"
+				"mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+				"@P1 bra DONE;\n"
+				"bra LAB_WAIT;\n"
+				"DONE:\n"
+				"}" ::"r"(bar), "r"(parity) : "memory");
+		}
+
+		__device__ __forceinline__ void mbar_wait_one(uint32_t bar, uint32_t parity)
 		{
 			asm volatile(
 				"{\n"
@@ -165,9 +219,13 @@ namespace nab200
 			return x > 0.0f ? x : 0.01f * x;
 		}
 
+		// low part of the 3xTF32 split.  The tensor core TRUNCATES its inputs to TF32, so hi is fed as the raw fp32
+		// value and lo = x - trunc(x) is exact; adding half a TF32 ulp to lo's bit pattern makes the hardware's
+		// truncation of lo a round-to-nearest, which removes the systematic (DC) bias of the split.
 		__device__ __forceinline__ float tf32_lo(float v)
 		{
-			return v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);   // exact: what the tensor core drops
+			const float lo = v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+			return __uint_as_float(__float_as_uint(lo) + 0x1000u);
 		}
 
 		__device__ __forceinline__ float4 tf32_lo4(float4 v)
@@ -175,107 +233,102 @@ namespace nab200
 			return make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
 		}
 
+		// descriptor = {lo: start>>4 | (LBO>>4)<<16, hi: SBO>>4 | version 1 << 14}; SBO is 128 bytes everywhere here
+		__device__ __forceinline__ uint64_t desc_of(uint32_t saddr, uint32_t lboBytes)
+		{
+			const uint32_t lo = ((saddr >> 4) & 0x3FFFu) | ((lboBytes >> 4) << 16);
+			const uint32_t hi = (128u >> 4) | (1u << 14);
+			return ((uint64_t)hi << 32) | lo;
+		}
+
 		struct Ctx
 		{
 			const WnModelDev* M;
+			const WnLayer* Ls;   // layer table copy in shared memory
 			const float* Wg;
 			float* XEhi;     // [CG0][kRows][4]
 			float* XElo;
 			float* WBhi;     // [CG0][kWbRows][4]
 			float* WBlo;
 			float* wbuf;     // [2][maxBlock]
-			int* hd;
-			uint32_t barWin, barW0, barMma;   // barW0: two adjacent mbarriers (weight buffers 0 and 1)
+			int* hdb;        // [2][36] ring heads: current stream / next stream
+			uint32_t barWin, barW0, barMma;   // barW0: two adjacent mbarriers (weight buffers 0 and 1); barMma expects kIssuers arrivals
 			uint32_t tmem;   // TMEM base (column 0, lane 0)
-			float* st;       // this stream's ring state
-			int n, tid;
+			float* state;
+			int n, tid, S, gstride;
 			uint32_t wq;     // running weight-block counter
 			uint32_t winq;   // running window-phase counter
 			uint32_t mmaq;   // running MMA-commit counter
+			int cur;         // which hdb half belongs to the current stream
 		};
 
-		// thread 0: one bulk copy of layer b's weight block into buffer (wq' & 1)
+		// one lane: one bulk copy of layer b's weight block into buffer (slot & 1)
 		__device__ __forceinline__ void issue_weights(const Ctx& cx, int b, uint32_t slot)
 		{
-			const WnLayer& L = cx.M->layers[b];
+			const WnLayer& L = cx.Ls[b];
 			const uint32_t bar = cx.barW0 + 8u * (slot & 1u);
 			mbar_expect_tx(bar, (uint32_t)L.wSize * 4u);
 			bulk_g2s(smem_u32(cx.wbuf + (size_t)(slot & 1u) * cx.M->maxBlock), cx.Wg + L.wOff, (uint32_t)L.wSize * 4u, bar);
 		}
 
-		// thread 0: TMA the history window(s) of layer l into the operand planes
-		__device__ __forceinline__ void issue_windows(const Ctx& cx, int l)
+		// one WARP (all 32 lanes call it): TMA the history window(s) of layer l of stream `s` into the operand planes.
+		// lane g + CG*tap issues the copies of channel group g of tap window `tap`; lane 0 posts the byte count first.
+		__device__ __forceinline__ void issue_windows(const Ctx& cx, int l, int s, const int* hd, int lane)
 		{
-			const WnLayer& L = cx.M->layers[l];
+			const WnLayer& L = cx.Ls[l];
 			const int CG = cx.M->arrays[L.array].C >> 2;
 			const int hist = (L.K - 1) * L.d;
 			const int Lp = L.Lp;
-			const int head = cx.hd[L.ringIdx];
-			const float* ring = cx.st + L.ringOff;
-			if (hist <= kCur)
+			const int head = hd[L.ringIdx];
+			const float* ring = cx.state + (size_t)s * cx.M->stateStride + L.ringOff;
+			const bool whole = hist <= kCur;
+			const int cnt = whole ? hist : cx.n;
+			const int ntap = whole ? 1 : 2;
+			if (lane == 0) mbar_expect_tx(cx.barWin, (uint32_t)(ntap * CG * cnt * 16));
+			__syncwarp();
+			if (lane < ntap * CG)
 			{
-				// whole history -> XE rows [128-hist, 128)
-				int idx0 = head - hist;
+				const int tap = lane / CG, g = lane - tap * CG;
+				const int D = whole ? hist : (2 - tap) * L.d;
+				int idx0 = head - D;
 				if (idx0 < 0) idx0 += Lp;
-				const int seg1 = min(hist, Lp - idx0), seg2 = hist - seg1;
-				mbar_expect_tx(cx.barWin, (uint32_t)(CG * hist * 16));
-				for (int g = 0; g < CG; g++)
-				{
-					const uint32_t dst = smem_u32(cx.XEhi + ((size_t)g * kRows + (kCur - hist)) * 4);
-					const float* src = ring + (size_t)g * Lp * 4;
-					bulk_g2s(dst, src + (size_t)idx0 * 4, (uint32_t)seg1 * 16u, cx.barWin);
-					if (seg2 > 0) bulk_g2s(dst + (uint32_t)seg1 * 16u, src, (uint32_t)seg2 * 16u, cx.barWin);
-				}
-			}
-			else
-			{
-				// K == 3, d >= 128: tap 0 (delay 2d) -> XE rows [0, n), tap 1 (delay d) -> WB rows [0, n)
-				const int cnt = cx.n;
-				mbar_expect_tx(cx.barWin, (uint32_t)(2 * CG * cnt * 16));
-				for (int tap = 0; tap < 2; tap++)
-				{
-					const int D = (2 - tap) * L.d;
-					int idx0 = head - D;
-					if (idx0 < 0) idx0 += Lp;
-					const int seg1 = min(cnt, Lp - idx0), seg2 = cnt - seg1;
-					for (int g = 0; g < CG; g++)
-					{
-						const uint32_t dst = tap == 0 ? smem_u32(cx.XEhi + (size_t)g * kRows * 4) : smem_u32(cx.WBhi + (size_t)g * kWbRows * 4);
-						const float* src = ring + (size_t)g * Lp * 4;
-						bulk_g2s(dst, src + (size_t)idx0 * 4, (uint32_t)seg1 * 16u, cx.barWin);
-						if (seg2 > 0) bulk_g2s(dst + (uint32_t)seg1 * 16u, src, (uint32_t)seg2 * 16u, cx.barWin);
-					}
-				}
+				const int seg1 = min(cnt, Lp - idx0), seg2 = cnt - seg1;
+				uint32_t dst;
+				if (whole) dst = smem_u32(cx.XEhi + ((size_t)g * kRows + (kCur - hist)) * 4);
+				else dst = tap == 0 ? smem_u32(cx.XEhi + (size_t)g * kRows * 4) : smem_u32(cx.WBhi + (size_t)g * kWbRows * 4);
+				const float* src = ring + (size_t)g * Lp * 4;
+				bulk_g2s(dst, src + (size_t)idx0 * 4, (uint32_t)seg1 * 16u, cx.barWin);
+				if (seg2 > 0) bulk_g2s(dst + (uint32_t)seg1 * 16u, src, (uint32_t)seg2 * 16u, cx.barWin);
 			}
 		}
 
 		// One layer array for the CTA's stream.  C in {8, 16}; INC: rechannel input width (1 -> from cond, else previous x');
-		// H: head size.  xo[] carries the previous array's output in, this array's out; head[] likewise for the head sums.
+		// H: head size.  xin carries the previous array's output in, xout this array's out; head[] the head sums.
 		template <int C, int INC, int H, int ACT>
-		__device__ __forceinline__ void run_array(Ctx& cx, const WnArray& A, float cond, const float (&xin)[INC], float (&head)[C], float (&xout)[C],
-			float (&hout)[H])
+		__device__ __forceinline__ void run_array(Ctx& cx, const WnArray& A, int s, float cond, const float (&xin)[INC], float (&head)[C],
+			float (&xout)[C], float (&hout)[H])
 		{
 			constexpr int CG = C / 4;
 			const WnModelDev& M = *cx.M;
 			const int tid = cx.tid;
-			const int warp = tid >> 5;
+			const int warp = tid >> 5, lane = tid & 31;
 			const uint32_t lanebase = cx.tmem + ((uint32_t)(warp * 32) << 16);
-			const uint32_t tD0 = 0, tD1 = 16, tZhi = 32, tZlo = 48;   // TMEM column map
+			constexpr uint32_t tD0 = 0, tD1 = 48, tZhi = 96, tZlo = 112;   // TMEM column map (accumulator j at +16*j)
 			const uint32_t idesc = make_idesc(C);
+			const int* hd = cx.hdb + cx.cur * 36;
+			float* const st = cx.state + (size_t)s * M.stateStride;
 
 			for (int li = 0; li < A.numLayers; li++)
 			{
 				const int l = A.firstLayer + li;
-				const WnLayer& L = M.layers[l];
+				const WnLayer& L = cx.Ls[l];
 				const int K = L.K, d = L.d, flags = L.flags;
 				const int hist = (K - 1) * d;
 				const bool whole = hist <= kCur;
 
-				// ---- this layer's weights (prefetched), then prefetch the next block into the other buffer
-				mbar_wait(cx.barW0 + 8u * (cx.wq & 1u), (cx.wq >> 1) & 1u);
-				if (tid == 0) issue_weights(cx, (l + 1 < M.numLayers) ? l + 1 : 0, cx.wq + 1);
+				// ---- this layer's weights were prefetched one layer ago
+				mbar_wait_weights(cx.barW0 + 8u * (cx.wq & 1u), (cx.wq >> 1) & 1u);
 				const float* __restrict__ wb = cx.wbuf + (size_t)(cx.wq & 1u) * M.maxBlock;
-				cx.wq++;
 
 				// ---- rechannel -> XE current rows (WaveNet.h:637), first layer of the array
 				if (flags & kFirstInArray)
@@ -305,7 +358,7 @@ namespace nab200
 				}
 
 				// ---- history window(s) landed: compute their low parts
-				mbar_wait(cx.barWin, cx.winq & 1u);
+				mbar_wait_window(cx.barWin, cx.winq & 1u);
 				cx.winq++;
 				if (whole)
 				{
@@ -333,16 +386,19 @@ namespace nab200
 				}
 				fence_async_smem();   // generic-proxy writes of the operand planes -> visible to the tensor core
 				fence_before();
-				__syncthreads();
+				__syncthreads();      // (S1) operands complete; every thread is done with the previous layer
 
-				// ---- dilated conv on the tensor core (WaveNet.h:250-289): 3 split-products per tap and K-step
-				if (tid == 0)
+				// ---- dilated conv on the tensor core (WaveNet.h:250-289): 3 split-products per tap and K-step.
+				// A single thread sustains only one tcgen05.mma per ~50 cycles (measured, tools/tc_timing.cu), so the taps
+				// are dealt round-robin to kIssuers threads, each accumulating into its own TMEM tile; the epilogue adds them.
+				if (lane == 0 && warp < kIssuers)
 				{
 					fence_after();
 					const uint32_t xeHi = smem_u32(cx.XEhi), xeLo = smem_u32(cx.XElo), wbHi = smem_u32(cx.WBhi), wbLo = smem_u32(cx.WBlo);
 					const uint32_t bHi = smem_u32(wb), bLo = smem_u32(wb + L.oConvLo);
+					const uint32_t dacc = cx.tmem + tD0 + 16u * (uint32_t)warp;
 					uint32_t acc = 0;
-					for (int k = 0; k < K; k++)
+					for (int k = warp; k < K; k += kIssuers)
 					{
 						const int D = (K - 1 - k) * d;
 						uint32_t aHi, aLo, lbo;
@@ -350,20 +406,23 @@ namespace nab200
 						else if (k == 0) { aHi = xeHi; aLo = xeLo; lbo = kRows * 16; }
 						else { aHi = wbHi; aLo = wbLo; lbo = kWbRows * 16; }
 #pragma unroll
-						for (int s = 0; s < C / 8; s++)
+						for (int sIdx = 0; sIdx < C / 8; sIdx++)
 						{
-							const uint32_t aoff = (uint32_t)(2 * s) * lbo;
-							const uint32_t boff = (uint32_t)((k * CG + 2 * s) * C) * 16u;
-							const uint64_t dAh = make_desc(aHi + aoff, lbo, 128), dAl = make_desc(aLo + aoff, lbo, 128);
-							const uint64_t dBh = make_desc(bHi + boff, C * 16, 128), dBl = make_desc(bLo + boff, C * 16, 128);
-							mma_ss(cx.tmem + tD0, dAh, dBh, idesc, acc);
+							const uint32_t aoff = (uint32_t)(2 * sIdx) * lbo;
+							const uint32_t boff = (uint32_t)((k * CG + 2 * sIdx) * C) * 16u;
+							const uint64_t dAh = desc_of(aHi + aoff, lbo), dAl = desc_of(aLo + aoff, lbo);
+							const uint64_t dBh = desc_of(bHi + boff, C * 16), dBl = desc_of(bLo + boff, C * 16);
+							mma_ss(dacc, dAh, dBh, idesc, acc);
 							acc = 1;
-							mma_ss(cx.tmem + tD0, dAl, dBh, idesc, 1);
-							mma_ss(cx.tmem + tD0, dAh, dBl, idesc, 1);
+							mma_ss(dacc, dAl, dBh, idesc, 1);
+							mma_ss(dacc, dAh, dBl, idesc, 1);
 						}
 					}
-					mma_commit(cx.barMma);
+					mma_commit(cx.barMma);   // arrives even when this issuer had no tap (K < kIssuers)
 				}
+				// next layer's weight block -> the buffer the previous layer used (free since S1)
+				if (tid == 63) issue_weights(cx, (l + 1 < M.numLayers) ? l + 1 : 0, cx.wq + 1);
+				cx.wq++;
 
 				// this thread's own input frame: residual + the ring column it becomes
 				float4 xr[CG];
@@ -384,22 +443,35 @@ namespace nab200
 					const int first = cx.n > Lp ? cx.n - Lp : 0;
 					if (tid < cx.n && tid >= first)
 					{
-						const int idx = (cx.hd[L.ringIdx] + tid) % Lp;
-						float* ring = cx.st + L.ringOff;
+						const int idx = (hd[L.ringIdx] + tid) % Lp;
+						float* ring = st + L.ringOff;
 #pragma unroll
 						for (int q = 0; q < CG; q++) *reinterpret_cast<float4*>(ring + ((size_t)q * Lp + idx) * 4) = xr[q];
 					}
 				}
 
-				mbar_wait(cx.barMma, cx.mmaq & 1u);
+				mbar_wait_conv(cx.barMma, cx.mmaq & 1u);
 				cx.mmaq++;
 				fence_after();
-				// the conv has consumed the window planes: prefetch the next layer's windows into them
-				if (tid == 0 && l + 1 < M.numLayers) issue_windows(cx, l + 1);
+				// the conv has consumed the window planes: warp 1 prefetches the next layer's windows (or the next
+				// stream's first layer) into them
+				if (warp == 1)
+				{
+					if (l + 1 < M.numLayers) issue_windows(cx, l + 1, s, hd, lane);
+					else if (s + cx.gstride < cx.S) issue_windows(cx, 0, s + cx.gstride, cx.hdb + (cx.cur ^ 1) * 36, lane);
+				}
 
 				// ---- bias, mix-in, activation, head sum (WaveNet.h:471-482); z -> TMEM as the 1x1's A operand
 				float z[C];
 				tmem_ld<C>(lanebase + tD0, z);
+				const int nacc = K < kIssuers ? K : kIssuers;
+				for (int j = 1; j < nacc; j++)
+				{
+					float zj[C];
+					tmem_ld<C>(lanebase + tD0 + 16u * (uint32_t)j, zj);
+#pragma unroll
+					for (int c = 0; c < C; c++) z[c] += zj[c];
+				}
 				uint32_t zh[C], zl[C];
 #pragma unroll
 				for (int c = 0; c < C; c++)
@@ -416,22 +488,20 @@ namespace nab200
 					tmem_st<C>(lanebase + tZlo, zl);
 					asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 					fence_before();
-					__syncthreads();
-					// ---- 1x1 (WaveNet.h:486-491) on the tensor core, A from TMEM
-					if (tid == 0)
+					__syncthreads();   // (S2)
+					// ---- 1x1 (WaveNet.h:486-491) on the tensor core, A from TMEM; issuer j computes split-product j
+					if (lane == 0 && warp < kIssuers)
 					{
 						fence_after();
 						const uint32_t bHi = smem_u32(wb + L.oOneW), bLo = smem_u32(wb + L.oOneLo);
-						uint32_t acc = 0;
+						const uint32_t aT = cx.tmem + (warp == 1 ? tZlo : tZhi);
+						const uint32_t bB = warp == 2 ? bLo : bHi;
+						const uint32_t dacc = cx.tmem + tD1 + 16u * (uint32_t)warp;
 #pragma unroll
-						for (int s = 0; s < C / 8; s++)
+						for (int sIdx = 0; sIdx < C / 8; sIdx++)
 						{
-							const uint32_t boff = (uint32_t)(2 * s * C) * 16u;
-							const uint64_t dBh = make_desc(bHi + boff, C * 16, 128), dBl = make_desc(bLo + boff, C * 16, 128);
-							mma_ts(cx.tmem + tD1, cx.tmem + tZhi + 8 * s, dBh, idesc, acc);
-							acc = 1;
-							mma_ts(cx.tmem + tD1, cx.tmem + tZlo + 8 * s, dBh, idesc, 1);
-							mma_ts(cx.tmem + tD1, cx.tmem + tZhi + 8 * s, dBl, idesc, 1);
+							const uint32_t boff = (uint32_t)(2 * sIdx * C) * 16u;
+							mma_ts(dacc, aT + 8 * sIdx, desc_of(bB + boff, C * 16), idesc, sIdx > 0 ? 1u : 0u);
 						}
 						mma_commit(cx.barMma);
 					}
@@ -442,11 +512,19 @@ namespace nab200
 						const float4 b = *reinterpret_cast<const float4*>(wb + L.oOneB + 4 * q);
 						b1[4 * q] = b.x; b1[4 * q + 1] = b.y; b1[4 * q + 2] = b.z; b1[4 * q + 3] = b.w;
 					}
-					mbar_wait(cx.barMma, cx.mmaq & 1u);
+					mbar_wait_one(cx.barMma, cx.mmaq & 1u);
 					cx.mmaq++;
 					fence_after();
 					float o[C];
 					tmem_ld<C>(lanebase + tD1, o);
+#pragma unroll
+					for (int j = 1; j < kIssuers; j++)
+					{
+						float oj[C];
+						tmem_ld<C>(lanebase + tD1 + 16u * (uint32_t)j, oj);
+#pragma unroll
+						for (int c = 0; c < C; c++) o[c] += oj[c];
+					}
 #pragma unroll
 					for (int q = 0; q < CG; q++)
 					{
@@ -475,9 +553,8 @@ namespace nab200
 #pragma unroll
 						for (int h = 0; h < H; h++) hout[h] = fmaf(hw[c * H + h], head[c], hout[h]);
 				}
-				// end of layer: every thread is done with this layer's weights, TMEM accumulators and operand rows
+				// no barrier here: (S1) of the next layer orders this layer's TMEM / shared-memory reads before their reuse
 				fence_before();
-				__syncthreads();
 			}
 		}
 
@@ -486,6 +563,8 @@ namespace nab200
 		{
 			return (size_t)2 * (C0 / 4) * kRows * 4 + (size_t)2 * (C0 / 4) * kWbRows * 4;
 		}
+
+		constexpr int kTableBytes = ((kMaxLayers * (int)sizeof(WnLayer) + 15) / 16) * 16;
 
 		// C0 / C1: padded channels of the two arrays (16 / 8)
 		template <int C0, int C1, int ACT>
@@ -503,47 +582,67 @@ namespace nab200
 			cx.WBhi = cx.XElo + CG0 * kRows * 4;
 			cx.WBlo = cx.WBhi + CG0 * kWbRows * 4;
 			cx.wbuf = cx.WBlo + CG0 * kWbRows * 4;
-			cx.hd = reinterpret_cast<int*>(cx.wbuf + (size_t)2 * M.maxBlock);
-			unsigned long long* bars = reinterpret_cast<unsigned long long*>(cx.hd + 36);
+			WnLayer* Ls = reinterpret_cast<WnLayer*>(cx.wbuf + (size_t)2 * M.maxBlock);
+			cx.Ls = Ls;
+			cx.hdb = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(Ls) + kTableBytes);
+			unsigned long long* bars = reinterpret_cast<unsigned long long*>(cx.hdb + 72);
 			uint32_t* tmemSlot = reinterpret_cast<uint32_t*>(bars + 4);
 			cx.barWin = smem_u32(&bars[0]);
 			cx.barW0 = smem_u32(&bars[1]);
 			cx.barMma = smem_u32(&bars[3]);
 			cx.n = n;
 			cx.tid = threadIdx.x;
-			cx.wq = 0; cx.winq = 0; cx.mmaq = 0;
-			cx.st = state;
+			cx.S = S;
+			cx.gstride = gridDim.x;
+			cx.state = state;
+			cx.wq = 0; cx.winq = 0; cx.mmaq = 0; cx.cur = 0;
 			const int tid = threadIdx.x;
+			const int warp = tid >> 5, lane = tid & 31;
 
+			// layer table -> shared memory (constant-bank loads with a runtime index are slow and sit on the critical path)
+			{
+				const int* src = reinterpret_cast<const int*>(&M.layers[0]);
+				int* dst = reinterpret_cast<int*>(Ls);
+				for (int i = tid; i < (int)(kMaxLayers * sizeof(WnLayer) / 4); i += kThreads) dst[i] = src[i];
+			}
 			if (tid == 0)
 			{
 				mbar_init(cx.barWin, 1);
 				mbar_init(cx.barW0, 1);
 				mbar_init(cx.barW0 + 8u, 1);
-				mbar_init(cx.barMma, 1);
+				mbar_init(cx.barMma, kIssuers);
 				asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 			}
-			if ((tid >> 5) == 0)
+			if (warp == 0)
 			{
-				asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 64;" ::"r"(smem_u32(tmemSlot)) : "memory");
+				asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(smem_u32(tmemSlot)) : "memory");
 				asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
 			}
+			// ring heads of the first stream
+			const int s0 = blockIdx.x;
+			if (tid < M.numRings && s0 < S) cx.hdb[tid] = heads[(size_t)s0 * M.numRings + tid];
 			fence_async_smem();
 			fence_before();
 			__syncthreads();
 			fence_after();
 			cx.tmem = *tmemSlot;
 
-			if (tid == 0) issue_weights(cx, 0, 0);
+			if (tid == 63) issue_weights(cx, 0, 0);
+			if (warp == 1 && s0 < S) issue_windows(cx, 0, s0, cx.hdb, lane);
+			float cond = 0.0f;
+			if (tid < n && s0 < S) cond = in[(long long)s0 * inSS + (long long)tid * inFS];
 
-			for (int s = blockIdx.x; s < S; s += gridDim.x)
+			for (int s = s0; s < S; s += gridDim.x)
 			{
-				cx.st = state + (size_t)s * M.stateStride;
-				if (tid < M.numRings) cx.hd[tid] = heads[(size_t)s * M.numRings + tid];
-				float cond = 0.0f;
-				if (tid < n) cond = in[(long long)s * inSS + (long long)tid * inFS];
-				__syncthreads();
-				if (tid == 0) issue_windows(cx, 0);
+				const int sn = s + gridDim.x;
+				// next stream's ring heads and input frame, fetched while this stream computes
+				int* hdNext = cx.hdb + (cx.cur ^ 1) * 36;
+				float condNext = 0.0f;
+				if (sn < S)
+				{
+					if (tid < M.numRings) hdNext[tid] = heads[(size_t)sn * M.numRings + tid];
+					if (tid < n) condNext = in[(long long)sn * inSS + (long long)tid * inFS];
+				}
 
 				float head0[C0];
 #pragma unroll
@@ -551,27 +650,29 @@ namespace nab200
 				float x0[C0];
 				float head1[C1];
 				const float xin0[1] = { cond };
-				run_array<C0, 1, C1, ACT>(cx, M.arrays[0], cond, xin0, head0, x0, head1);
+				run_array<C0, 1, C1, ACT>(cx, M.arrays[0], s, cond, xin0, head0, x0, head1);
 				float x1[C1];
 				float y[1];
-				run_array<C1, C0, 1, ACT>(cx, M.arrays[1], cond, x0, head1, x1, y);
+				run_array<C1, C0, 1, ACT>(cx, M.arrays[1], s, cond, x0, head1, x1, y);
 
 				if (tid < n) out[(long long)s * outSS + (long long)tid * outFS] = M.headScale * y[0];   // WaveNet.h:793-798
 				if (tid < M.numRings)
 				{
 					const int Lp = M.ringLp[tid];
-					int h = cx.hd[tid] + (n % Lp);
+					int h = cx.hdb[cx.cur * 36 + tid] + (n % Lp);
 					if (h >= Lp) h -= Lp;
 					heads[(size_t)s * M.numRings + tid] = h;
 				}
-				__syncthreads();   // hd is rewritten by the next stream
+				cx.cur ^= 1;
+				cond = condNext;
+				// the next stream's first (S1) barrier orders these hdb reads before the slot is refilled two streams later
 			}
 
 			// drain the weight prefetch that ran ahead of the last layer, then release TMEM
 			mbar_wait(cx.barW0 + 8u * (cx.wq & 1u), (cx.wq >> 1) & 1u);
 			fence_before();
 			__syncthreads();
-			if ((tid >> 5) == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 64;" ::"r"(cx.tmem) : "memory");
+			if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(cx.tmem) : "memory");
 		}
 	}
 
@@ -585,7 +686,7 @@ namespace nab200
 		if (!wavenet_tc_variant_supported(M.arrays[0].C, M.numArrays > 1 ? M.arrays[1].C : 0, M.arrays[0].act)) return cudaErrorNotSupported;
 		if (a.n > tc::kCur) return cudaErrorInvalidValue;
 		auto kfn = tc::wavenet_tc_kernel<16, 8, 0>;
-		const size_t smem = tc::smem_floats_fixed<16>() * 4 + (size_t)2 * M.maxBlock * 4 + 36 * 4 + 4 * 8 + 16;
+		const size_t smem = tc::smem_floats_fixed<16>() * 4 + (size_t)2 * M.maxBlock * 4 + tc::kTableBytes + 72 * 4 + 4 * 8 + 16;
 		cudaError_t err = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 		if (err != cudaSuccess) return err;
 		int grid = a.numSMs * 3;
