@@ -1,4 +1,5 @@
 #include "engine.h"
+#include <cstdlib>
 #include <cstring>
 #include <sstream>
 
@@ -11,7 +12,17 @@ namespace nab200
 
 	Options& GetOptions()
 	{
-		static Options o;
+		static Options o = []
+		{
+			// tuning knobs can also come from the environment (NAB200_USE_TC, NAB200_TS_ISSUERS, NAB200_USE_TMA, NAB200_MAX_GRID_CTAS)
+			Options v;
+			auto env = [](const char* name, int& dst) { const char* e = getenv(name); if (e && *e) dst = atoi(e); };
+			env("NAB200_USE_TC", v.useTc);
+			env("NAB200_TS_ISSUERS", v.tsIssuers);
+			env("NAB200_USE_TMA", v.useTma);
+			env("NAB200_MAX_GRID_CTAS", v.maxGridCtas);
+			return v;
+		}();
 		return o;
 	}
 
@@ -21,6 +32,7 @@ namespace nab200
 		int prev = -1;
 		if (strcmp(name, "use_tma") == 0) { prev = o.useTma; o.useTma = value; }
 		else if (strcmp(name, "use_tc") == 0) { prev = o.useTc; o.useTc = value; }
+		else if (strcmp(name, "ts_issuers") == 0) { prev = o.tsIssuers; o.tsIssuers = value; }
 		else if (strcmp(name, "max_grid_ctas") == 0) { prev = o.maxGridCtas; o.maxGridCtas = value; }
 		return prev;
 	}
@@ -184,7 +196,8 @@ namespace nab200
 	{
 		const WnModelDev& M = packed.dev;
 		const int C0 = M.arrays[0].C, C1 = M.numArrays > 1 ? M.arrays[1].C : 0;
-		const bool ok = M.tc ? wavenet_tc_variant_supported(C0, C1, M.arrays[0].act) : wavenet_variant_supported(C0, C1, M.arrays[0].act);
+		const bool ok = M.tc == 2 ? wavenet_ts_variant_supported(C0, C1, M.arrays[0].act)
+			: M.tc ? wavenet_tc_variant_supported(C0, C1, M.arrays[0].act) : wavenet_variant_supported(C0, C1, M.arrays[0].act);
 		if (!ok)
 		{
 			std::stringstream ss;
@@ -232,7 +245,13 @@ namespace nab200
 	{
 		if (!CudaOk(cudaSetDevice(device), "cudaSetDevice")) return false;
 		// steady state under silence (WaveNetModelT::Prewarm, WaveNet.h:746-766), computed analytically in fp32
-		if (!CudaOk(wavenet_prewarm_launch(packed.dev, dBlob, dBlob + weightFloats, stream), "wavenet_prewarm")) return false;
+		if (packed.dev.tc == 2)
+		{
+			// the TMEM-operand packing keeps biases / mix-in inside tensor-core operands; its template is produced by the
+			// settle pass below alone, starting from silence-in, zero-state (a finite receptive field forgets the start)
+			if (!CudaOk(cudaMemsetAsync(dBlob + weightFloats, 0, (size_t)packed.dev.stateStride * 4, stream), "cudaMemset(template)")) return false;
+		}
+		else if (!CudaOk(wavenet_prewarm_launch(packed.dev, dBlob, dBlob + weightFloats, stream), "wavenet_prewarm")) return false;
 		if (packed.dev.tc)
 		{
 			// The tensor-core kernel evaluates the contractions as 3xTF32, whose silence fixed point differs from the
@@ -259,7 +278,8 @@ namespace nab200
 				a.in = io; a.out = io + frames;
 				a.inSS = frames; a.inFS = 1; a.outSS = frames; a.outFS = 1;
 				a.S = 1; a.n = frames; a.numSMs = numSMs; a.useTma = true; a.stream = stream;
-				ok = CudaOk(wavenet_tc_launch(M, a), "wavenet_tc prewarm settle");
+				a.tsIssuers = GetOptions().tsIssuers;
+				ok = CudaOk(M.tc == 2 ? wavenet_ts_launch(M, a) : wavenet_tc_launch(M, a), "wavenet tensor-core prewarm settle");
 			}
 			// under constant input every ring column holds the same value, so the settled rings are a valid template
 			// for ring head 0 whatever position the scratch heads ended at
@@ -293,7 +313,9 @@ namespace nab200
 			a.numSMs = (opt.maxGridCtas > 0) ? opt.maxGridCtas : numSMs;
 			a.useTma = opt.useTma != 0;
 			a.stream = stream;
-			if (!CudaOk(packed.dev.tc ? wavenet_tc_launch(packed.dev, a) : wavenet_launch(packed.dev, a), "wavenet kernel launch")) return false;
+			a.tsIssuers = opt.tsIssuers;
+			const cudaError_t lerr = packed.dev.tc == 2 ? wavenet_ts_launch(packed.dev, a) : packed.dev.tc ? wavenet_tc_launch(packed.dev, a) : wavenet_launch(packed.dev, a);
+			if (!CudaOk(lerr, "wavenet kernel launch")) return false;
 			done += chunk;
 		}
 		return true;

@@ -16,7 +16,9 @@ namespace nab200
 	struct Options
 	{
 		int useTma = 1;         // stage history windows with cp.async.bulk + mbarrier (0: plain loads, debugging aid)
-		int useTc = 1;          // tensor-core (tcgen05) WaveNet kernel where the architecture fits; 0: CUDA-core kernel
+		int useTc = 2;          // WaveNet kernel choice where the architecture fits: 2 tcgen05 with TMEM operands (default),
+		                        // 1 tcgen05 with shared-memory operands (round-1 kernel), 0 CUDA-core kernel
+		int tsIssuers = 4;      // TS kernel: warps sharing the MMA issue
 		int maxGridCtas = 0;    // 0: one CTA per SM
 	};
 	Options& GetOptions();

@@ -600,6 +600,207 @@ namespace nab200
 		return P;
 	}
 
+	// ---- TMEM-operand packing (wavenet_ts_kernels.cu) --------------------------------------------------------------
+	bool WaveNetTsSupported(const WaveNetDesc& desc)
+	{
+		// two arrays of (<=16, <=8) channels, tanh, kernel size 3 everywhere, 1x1 heads, head of array 0 feeding array 1
+		if (desc.arrays.size() != 2) return false;
+		const WaveNetArrayDesc& A0 = desc.arrays[0];
+		const WaveNetArrayDesc& A1 = desc.arrays[1];
+		if (A0.channels <= 8 || A0.channels > 16 || A1.channels > 8) return false;
+		if (A0.inputSize != 1 || A1.inputSize != A0.channels || A0.headSize != A1.channels || A1.headSize != 1) return false;
+		for (const auto& A : desc.arrays)
+		{
+			if (A.activation != 0 || A.headKernel != 1) return false;
+			if (A.dilations.empty()) return false;
+			for (size_t l = 0; l < A.dilations.size(); l++)
+				if (A.kernelSizes[l] != 3 || A.dilations[l] < 1) return false;
+		}
+		return (int)(A0.dilations.size() + A1.dilations.size()) <= kMaxLayers;
+	}
+
+	// w = hi + lo + lolo with hi tf32-rounded and lo what the tensor core keeps of the remainder (it truncates to tf32)
+	static void Split3(float v, float& hi, float& lo, float& lolo)
+	{
+		hi = RoundTf32(v);
+		const float r = v - hi;
+		uint32_t u;
+		memcpy(&u, &r, 4);
+		u &= 0xFFFFE000u;
+		memcpy(&lo, &u, 4);
+		lolo = r - lo;
+	}
+
+	PackedWaveNet PackWaveNetTs(const WaveNetDesc& desc)
+	{
+		PackedWaveNet P;
+		WnModelDev& M = P.dev;
+		memset(&M, 0, sizeof(M));
+		M.tc = 2;
+		M.numArrays = (int)desc.arrays.size();
+		const float* w = desc.weights.data();
+		int layerIdx = 0, ringIdx = 0, ringOff = 0;
+		int prevCP = 1;
+		const float* prevHeadW = nullptr;   // unused; the carry uses THIS array's head conv
+		(void)prevHeadW;
+		for (int a = 0; a < M.numArrays; a++)
+		{
+			const WaveNetArrayDesc& A = desc.arrays[a];
+			WnArray& DA = M.arrays[a];
+			const int C = A.channels, CP = TcPad(C), KC = CP / 4, N1 = CP + 8;
+			const int last = a + 1 == M.numArrays;
+			const int inC = A.inputSize, inCP = a == 0 ? 1 : prevCP;
+			const int H = A.headSize;
+			const int nL = (int)A.dilations.size();
+			DA.C = CP; DA.inC = inCP; DA.H = 8; DA.Kh = 1; DA.act = A.activation;
+			DA.firstLayer = layerIdx; DA.numLayers = nL; DA.realC = C; DA.realH = H;
+			const float* wRe = w; w += (size_t)C * inC;
+			std::vector<const float*> wLayer(nL);
+			for (int l = 0; l < nL; l++)
+			{
+				wLayer[l] = w;
+				w += (size_t)C * C * A.kernelSizes[l] + C + C + (size_t)C * C + C;
+			}
+			const float* wHead = w; w += (size_t)H * C + (A.headBias ? H : 0);   // file [H][C] then bias
+			for (int l = 0; l < nL; l++)
+			{
+				WnLayer& L = M.layers[layerIdx];
+				const int K = A.kernelSizes[l], d = A.dilations[l];
+				L.K = K; L.d = d; L.array = a;
+				L.Lp = (K - 1) * d;
+				L.ringOff = ringOff; L.ringIdx = ringIdx;
+				M.ringLp[ringIdx] = L.Lp;
+				ringOff += CP * L.Lp; ringIdx++;
+				L.flags = 0;
+				if (l == 0) L.flags |= kFirstInArray;
+				if (l == nL - 1) L.flags |= kLastInArray;
+				const bool needOut = !(last && M.numArrays > 1 && l == nL - 1);
+				if (needOut) L.flags |= kNeedOutput;
+				int off = 0;
+				const int oConvHi = off; off += K * KC * CP * 4;
+				L.oConvLo = off; off += K * KC * CP * 4;
+				L.oConvB = off; off += 2 * CP * 4;
+				L.oOneW = off; off += KC * N1 * 4;
+				L.oOneLo = off; off += KC * N1 * 4;
+				L.oOneB = off; off += 2 * N1 * 4;
+				L.oRe = off;
+				int oReLo = 0, oChHi = 0, oChLo = 0, oHdC = 0;
+				if (l == 0)
+				{
+					if (a == 0) { off += 2 * CP * 4; oHdC = off; off += 2 * 8 * 4; }
+					else
+					{
+						off += (inCP / 4) * CP * 4; oReLo = off; off += (inCP / 4) * CP * 4;
+						oChHi = off; off += 2 * 8 * 4; oChLo = off; off += 2 * 8 * 4;
+						oHdC = off; off += 2 * 8 * 4;
+					}
+				}
+				L.oMix = oReLo; L.oHeadW = oChHi; L.oHeadB = oHdC;   // tc == 2: offsets of reLo / chHi / hdC (chLo = chHi + 64)
+				(void)oChLo;
+				L.wSize = Align4(off);
+				L.wOff = (int)P.weights.size();
+				P.weights.resize(P.weights.size() + L.wSize, 0.0f);
+				float* blk = P.weights.data() + L.wOff;
+				if (L.wSize > M.maxBlock) M.maxBlock = L.wSize;
+				const float* src = wLayer[l];
+				float hi, lo, lolo;
+				// conv file order [out][in][k] (WaveNet.h:99-105) -> B operand [k][in/4][out][in%4]
+				for (int i = 0; i < C; i++)
+					for (int j = 0; j < C; j++)
+						for (int k = 0; k < K; k++)
+						{
+							Split3(*src++, hi, lo, lolo);
+							const int at = ((k * KC + j / 4) * CP + i) * 4 + (j % 4);
+							blk[oConvHi + at] = hi;
+							blk[L.oConvLo + at] = RoundTf32(lo + lolo);
+						}
+				// constant-operand rows: k = 0 mix_hi, 1 mix_hi, 2 mix_lo, 3 b_hi, 4 b_lo, 5 b_lolo  ([k/4][n][k%4])
+				const float* convB = src; src += C;
+				const float* mix = src; src += C;
+				for (int i = 0; i < C; i++)
+				{
+					float* c0 = blk + L.oConvB + i * 4;
+					float* c1 = blk + L.oConvB + (CP + i) * 4;
+					Split3(mix[i], hi, lo, lolo);
+					c0[0] = hi; c0[1] = hi; c0[2] = RoundTf32(lo + lolo);
+					Split3(convB[i], hi, lo, lolo);
+					c0[3] = hi; c1[0] = lo; c1[1] = lolo;
+				}
+				// 1x1 file [out][in] (zero when the layer has no output) | head conv of this array, file [H][C]
+				for (int i = 0; i < C; i++)
+					for (int j = 0; j < C; j++)
+					{
+						Split3(*src++, hi, lo, lolo);
+						const int at = ((j / 4) * N1 + i) * 4 + (j % 4);
+						if (needOut) { blk[L.oOneW + at] = hi; blk[L.oOneLo + at] = RoundTf32(lo + lolo); }
+					}
+				for (int h = 0; h < H; h++)
+					for (int j = 0; j < C; j++)
+					{
+						Split3(wHead[h * C + j], hi, lo, lolo);
+						const int at = ((j / 4) * N1 + CP + h) * 4 + (j % 4);
+						blk[L.oOneW + at] = hi; blk[L.oOneLo + at] = RoundTf32(lo + lolo);
+					}
+				for (int i = 0; i < C; i++)
+				{
+					Split3(*src++, hi, lo, lolo);
+					if (!needOut) continue;
+					blk[L.oOneB + i * 4 + 3] = hi;
+					blk[L.oOneB + (N1 + i) * 4 + 0] = lo;
+					blk[L.oOneB + (N1 + i) * 4 + 1] = lolo;
+				}
+				if (l == 0)
+				{
+					if (a == 0)
+					{
+						// rechannel 1 -> C from the constant operand: rows 0 re_hi, 1 re_hi, 2 re_lo
+						for (int i = 0; i < C; i++)
+						{
+							Split3(wRe[i], hi, lo, lolo);
+							float* c0 = blk + L.oRe + i * 4;
+							c0[0] = hi; c0[1] = hi; c0[2] = RoundTf32(lo + lolo);
+						}
+					}
+					else
+					{
+						// rechannel Cprev -> C, file [out][in]
+						for (int i = 0; i < C; i++)
+							for (int j = 0; j < inC; j++)
+							{
+								Split3(wRe[i * inC + j], hi, lo, lolo);
+								const int at = ((j / 4) * CP + i) * 4 + (j % 4);
+								blk[L.oRe + at] = hi; blk[oReLo + at] = RoundTf32(lo + lolo);
+							}
+						// carry: this array's head conv applied to the previous array's head output (8 padded channels in)
+						const int Hprev = desc.arrays[a - 1].headSize;
+						for (int h = 0; h < H; h++)
+							for (int j = 0; j < Hprev && j < C; j++)
+							{
+								Split3(wHead[h * C + j], hi, lo, lolo);
+								const int at = ((j / 4) * 8 + h) * 4 + (j % 4);
+								blk[oChHi + at] = hi; blk[oChLo + at] = RoundTf32(lo + lolo);
+							}
+					}
+					if (A.headBias)
+						for (int h = 0; h < H; h++)
+						{
+							Split3(wHead[(size_t)H * C + h], hi, lo, lolo);
+							blk[oHdC + h * 4 + 3] = hi;
+							blk[oHdC + (8 + h) * 4 + 0] = lo;
+							blk[oHdC + (8 + h) * 4 + 1] = lolo;
+						}
+				}
+				layerIdx++;
+			}
+			prevCP = CP;
+		}
+		M.headScale = *w;
+		M.numLayers = layerIdx;
+		M.numRings = ringIdx;
+		M.stateStride = Align4(ringOff);
+		return P;
+	}
+
 	PackedLstm PackLstm(const LstmDesc& desc)
 	{
 		PackedLstm P;

@@ -55,6 +55,17 @@ namespace nab200
 	//   directly in the tcgen05 K-major operand layout and a tap shift is a 16-byte row offset;
 	//   block = convHi[K][C/4][C][4] | convLo | oneHi[C/4][C][4] | oneLo | convB[C] | mix[C] | oneB[C] | re[inC][C] | headW[C][H] | headB[H]
 	//   where X[kc][n][i] = W[out n][in 4*kc+i], hi = tf32-rounded weight, lo = weight - hi.
+	//
+	// TMEM-operand packing (WnModelDev::tc == 2), used by wavenet_ts_kernels.cu.  Rings as for tc == 1.  Every matrix is a
+	// tcgen05 B operand [k/4][n][4] (K-major, no swizzle), split hi = tf32-rounded / lo = w - hi.  N1 = C + 8 (1x1 | head).
+	//   block = convHi[K][C/4][C][4] | convLo (oConvLo) | convC[2][C][4] (oConvB) | oneHi[C/4][N1][4] (oOneW) | oneLo (oOneLo)
+	//           | oneC[2][N1][4] (oOneB) | first layer of an array only (oRe): array 0: reC[2][C][4] | hdC[2][8][4]
+	//                                                                     array a>0: reHi[Cprev/4][C][4] | reLo | chHi[2][8][4] | chLo | hdC[2][8][4]
+	//   The "C" matrices multiply the per-frame constant operand [cond, cond_lo, cond, 1, 1, 1, 0, 0]:
+	//   convC rows = (mix_hi, mix_hi, mix_lo, b_hi, b_lo, b_lolo, 0, 0) fold the mix-in (WaveNet.h:476) and the conv bias into the
+	//   contraction; oneC carries the 1x1 bias, reC the 1 -> C rechannel (WaveNet.h:637), hdC the head bias.  oneHi/oneLo columns
+	//   n >= C hold the head conv (WaveNet.h:658-660) so the head sum accumulates on the tensor core; ch* = the head conv applied to
+	//   the previous array's head output (WaveNet.h:785-788).  A layer without kNeedOutput has a zero 1x1.
 	struct WnModelDev
 	{
 		int numArrays, numLayers, numRings;

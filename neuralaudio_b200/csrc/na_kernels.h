@@ -17,6 +17,7 @@ namespace nab200
 		int n;                  // frames this pass (<= wavenet_max_frames_per_pass)
 		int numSMs;
 		bool useTma;
+		int tsIssuers = 4;      // TS kernel: warps sharing the tcgen05.mma issue (1..4)
 		cudaStream_t stream;
 	};
 
@@ -24,6 +25,9 @@ namespace nab200
 	// tcgen05 path (WnModelDev::tc == 1 packing), n <= 128
 	cudaError_t wavenet_tc_launch(const WnModelDev& M, const WnLaunch& a);
 	bool wavenet_tc_variant_supported(int C0, int C1, int act);
+	// tcgen05 path with TMEM A operands (WnModelDev::tc == 2 packing), n <= 128
+	cudaError_t wavenet_ts_launch(const WnModelDev& M, const WnLaunch& a);
+	bool wavenet_ts_variant_supported(int C0, int C1, int act);
 	cudaError_t wavenet_prewarm_launch(const WnModelDev& M, const float* weights, float* tmpl, cudaStream_t stream);
 	cudaError_t state_fill_launch(float* state, const float* tmpl, int strideFloats, long long numStreams, cudaStream_t stream);
 	cudaError_t int_fill_launch(int* p, int v, long long total, cudaStream_t stream);

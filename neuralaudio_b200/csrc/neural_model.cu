@@ -248,8 +248,11 @@ inline namespace b200
 		model->isStatic = desc.isStatic;
 		// only the static adapters override GetReceptiveFieldSize (InternalModel.h:99-102); dynamic models report -1
 		model->receptiveField = desc.isStatic ? desc.receptiveField : -1;
-		const bool useTc = nab200::GetOptions().useTc != 0 && nab200::WaveNetTcSupported(desc);
-		auto* engine = new nab200::WaveNetEngine(loader->GetDevice(), useTc ? nab200::PackWaveNetTc(desc) : nab200::PackWaveNet(desc));
+		const int tcOpt = nab200::GetOptions().useTc;
+		const bool useTs = tcOpt >= 2 && nab200::WaveNetTsSupported(desc);
+		const bool useTc = !useTs && tcOpt != 0 && nab200::WaveNetTcSupported(desc);
+		auto* engine = new nab200::WaveNetEngine(loader->GetDevice(),
+			useTs ? nab200::PackWaveNetTs(desc) : useTc ? nab200::PackWaveNetTc(desc) : nab200::PackWaveNet(desc));
 		model->engine = engine;
 		if (!engine->Init() || !engine->Upload()) { delete model; return nullptr; }
 		return model;

@@ -1,0 +1,716 @@
+// Batched WaveNet Process() with every contraction on the Blackwell tensor cores and every A operand in TMEM
+// ("TS" form of tcgen05.mma), sm_100a.  Same contract as the other WaveNet kernels (one call advances S independent
+// streams by n <= 128 frames; reference path WaveNetModelT::Process, WaveNet.h:768-799).
+//
+// Why this shape (measured with tools/mma_bench.cu on B200, M = 128 frames, N = 8..32 channels):
+//   * an MMA whose A operand is a shared-memory descriptor costs ~32-37 cycles per SM whatever N is (its 4 KB A tile is
+//     re-read from shared memory for each of the three 3xTF32 split products), the same MMA with A in TMEM ~4-7 cycles;
+//   * the round-1 kernel spent 246 M warp instructions per 4096x128 call (ncu), most of them bias / mix-in / residual /
+//     head-sum / accumulator-merge arithmetic around the MMAs and the MMA issue code of diverged lanes.
+// So here:
+//   * a CTA of 128 threads owns one stream at a time: thread t <-> frame t <-> TMEM lane t; 4 CTAs per SM;
+//   * per layer the threads build the tap operands [x(t-2d) | x(t-d)] directly in TMEM: history rows come from the HBM
+//     ring through TMA into a shared-memory window, current rows from the previous layer's output, each thread reads its
+//     own row (LDS.128), derives the low part of the 3xTF32 split with one LOP3 + one packed FFMA2 per two values, and
+//     stores [hi | lo] with one tcgen05.st; the undelayed tap's high part IS the residual accumulator (below);
+//   * the residual stream x lives in a TMEM accumulator for the whole array: x += W1x1 z + b is the 1x1 MMA itself
+//     (WaveNet.h:486-491), and the same columns are the A operand of the next layer's undelayed tap (the tensor core
+//     truncates fp32 to tf32 on its own, which is exactly the high part of the split);
+//   * a constant operand [cond, cond_lo, cond, 1, 1, 1, 0, 0] per frame turns the mix-in, all biases and the 1 -> C
+//     rechannel into one more K = 8 MMA each (na_device.h, tc == 2 packing); the head sum accumulates on the tensor core
+//     as extra N columns of the 1x1 (WaveNet.h:482,658-660);
+//   * what is left for the CUDA cores is the FastMath tanh (Horner form, packed FFMA2) and the splits.
+// fp32 parity comes from the 3xTF32 split (hi*Whi + lo*Whi + hi*Wlo, weights pre-split on the host); measured error vs the
+// reference is at the 1e-7 level (tests/, tools/ts_numerics.py emulates this arithmetic on the CPU).
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "na_device.h"
+#include "na_kernels.h"
+
+namespace nab200
+{
+	namespace ts
+	{
+		constexpr int kThreads = 128;
+		constexpr int kRows = 256;      // rows per XE plane: [0,128) history, [128,256) current frames
+		constexpr int kCur = 128;
+		constexpr int kWbRows = 128;    // rows per plane of the second window buffer
+		constexpr int kTmemCols = 128;
+		typedef unsigned long long u64;
+
+		// TMEM column maps.  Array 0 (16 channels) and array 1 (8 channels); array 1 lives in columns array 0 no longer needs.
+		// CONST: [cond, cond_lo, cond, 1, 1, 1, 0, 0].  T0/T1: delayed taps [hi | lo]; Z (activated layer output) aliases T0.
+		// T2L: low part of the undelayed tap (its high part is XR).  D: conv accumulator.  XR: residual stream.  HD: head sum.
+		constexpr uint32_t kConst = 0;
+		template <int ARRAY> struct Cols;
+		template <> struct Cols<0>
+		{
+			static constexpr int C = 16;
+			static constexpr uint32_t T0 = 8, T1 = 40, T2L = 72, D = 88, XR = 104, HD = 120;
+		};
+		template <> struct Cols<1>
+		{
+			static constexpr int C = 8;
+			static constexpr uint32_t T0 = 8, T1 = 24, T2L = 40, D = 48, XR = 88, HD = 96;
+		};
+		constexpr uint32_t kHdLo = 56;   // low part of array 0's head output during the array transition
+
+		__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+		__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+		{
+			asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+		}
+
+		__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+		{
+			asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+		}
+
+		// try_wait suspends the thread in hardware up to the hinted time, so a waiting warp costs almost no issue slots
+		__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+		{
+			asm volatile(
+				"{\n"
+				".reg .pred P1;\n"
+				"LAB_WAIT:\n"
+				"mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n"
+				"@P1 bra DONE;\n"
+				"bra LAB_WAIT;\n"
+				"DONE:\n"
+				"}" ::"r"(bar), "r"(parity), "r"(0x989680u) : "memory");
+		}
+
+		__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar)
+		{
+			asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+				"r"(bytes), "r"(bar) : "memory");
+		}
+
+		__device__ __forceinline__ uint4 lds128(uint32_t saddr)
+		{
+			uint4 v;
+			asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
+			return v;
+		}
+
+		__device__ __forceinline__ void sts128(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d)
+		{
+			asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+		}
+
+		// B operand descriptor: shared memory, no swizzle, K-major, [k/4][n][4 floats]: LBO = bytes between k groups, SBO = 128.
+		// Low word = (address >> 4) | (LBO >> 4) << 16, high word constant; moving the operand by x bytes adds x >> 4.
+		constexpr uint32_t kDescHi = (128u >> 4) | (1u << 14);
+		__device__ __forceinline__ u64 desc_at(uint32_t addr16, uint32_t lbo16) { return ((u64)kDescHi << 32) | (addr16 | (lbo16 << 16)); }
+
+		// D = F32, A = B = TF32, K-major, M = 128
+		__device__ __forceinline__ constexpr uint32_t idesc_of(int N)
+		{
+			return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+		}
+
+		template <uint32_t ACC>
+		__device__ __forceinline__ void mma_ts(uint32_t tmemD, uint32_t tmemA, u64 db, uint32_t idesc)
+		{
+			asm volatile(
+				"{\n\t"
+				".reg .pred p;\n\t"
+				"setp.ne.b32 p, %4, 0;\n\t"
+				"tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+				"}\n" ::"r"(tmemD), "r"(tmemA), "l"(db), "r"(idesc), "n"(ACC) : "memory");
+		}
+
+		__device__ __forceinline__ void mma_commit(uint32_t bar)
+		{
+			asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+		}
+
+		__device__ __forceinline__ bool elect_one()
+		{
+			uint32_t p;
+			asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(p));
+			return p != 0;
+		}
+
+		__device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+		__device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+		__device__ __forceinline__ void wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+		__device__ __forceinline__ void wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+		template <int N>
+		__device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t (&r)[N])
+		{
+			static_assert(N == 8 || N == 16, "tmem_ld width");
+			if constexpr (N == 16)
+				asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+							 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+							   "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+							 : "r"(taddr));
+			else
+				asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+							 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+							 : "r"(taddr));
+			wait_ld();
+		}
+
+		template <int N>
+		__device__ __forceinline__ void tmem_st(uint32_t taddr, const uint32_t (&r)[N])
+		{
+			static_assert(N == 8 || N == 16 || N == 32, "tmem_st width");
+			if constexpr (N == 32)
+				asm volatile(
+					"tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,"
+					"%26,%27,%28,%29,%30,%31,%32};" ::"r"(taddr),
+					"r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]),
+					"r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]),
+					"r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]) : "memory");
+			else if constexpr (N == 16)
+				asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+					"r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+					"r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+			else
+				asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]),
+					"r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+		}
+
+		template <int N>
+		__device__ __forceinline__ void tmem_zero(uint32_t taddr)
+		{
+			uint32_t z[N];
+#pragma unroll
+			for (int i = 0; i < N; i++) z[i] = 0u;
+			tmem_st<N>(taddr, z);
+		}
+
+		// ---- packed fp32x2 arithmetic (FFMA2 / FMUL2: two IEEE operations per issue slot) -----------------------------
+		__device__ __forceinline__ u64 pack2(uint32_t a, uint32_t b)
+		{
+			u64 r;
+			asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(a), "r"(b));
+			return r;
+		}
+		__device__ __forceinline__ u64 pack2f(float a, float b) { return pack2(__float_as_uint(a), __float_as_uint(b)); }
+		__device__ __forceinline__ void unpack2(u64 v, uint32_t& a, uint32_t& b) { asm("mov.b64 {%0, %1}, %2;" : "=r"(a), "=r"(b) : "l"(v)); }
+		__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c)
+		{
+			u64 d;
+			asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+			return d;
+		}
+		__device__ __forceinline__ u64 mul2(u64 a, u64 b)
+		{
+			u64 d;
+			asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+			return d;
+		}
+
+		// Low parts of the 3xTF32 split for two values.  The tensor core truncates its fp32 inputs to tf32, so the high part is
+		// the raw value and lo = x - trunc(x).  lo is itself truncated to tf32 by the hardware, which would bias it toward
+		// zero; computing it as fma(trunc(x), -(1 - 2^-23), x) = lo + 2^-23 trunc(x) adds the mean truncation loss back
+		// (tools/ts_numerics.py).  One LOP3 per value + one FFMA2 per pair.
+		__device__ __forceinline__ void split_lo2(uint32_t x0, uint32_t x1, uint32_t& l0, uint32_t& l1)
+		{
+			const u64 k = pack2(0xBF7FFFFEu, 0xBF7FFFFEu);   // -(1 - 2^-23)
+			unpack2(fma2(pack2(x0 & 0xFFFFE000u, x1 & 0xFFFFE000u), k, pack2(x0, x1)), l0, l1);
+		}
+
+		// FastMath<T>::Tanh (Activation.h:83-91) for two values.  With a = |x|: tanh ~ x * P(a) / Q(a),
+		// P = c0 + c0 a + c1 a^2 + c2 a^3 and Q = c3 + c3 a + c3 c4 a^2 + a^3 + c4 a^4 are the reference's numerator and
+		// denominator expanded (|x + c4 x a| = a (1 + c4 a)), evaluated by Horner; Q >= 2.445, one MUFU.RCP each.
+		__device__ __forceinline__ void fast_tanh2(uint32_t x0, uint32_t x1, uint32_t& y0, uint32_t& y1)
+		{
+			const float c0 = 2.45550750702956f, c1 = 0.893229853513558f, c2 = 0.821226666969744f;
+			const float c3 = 2.44506634652299f, c4 = 0.814642734961073f;
+			const u64 a = pack2(x0 & 0x7FFFFFFFu, x1 & 0x7FFFFFFFu);
+			u64 p = fma2(pack2f(c2, c2), a, pack2f(c1, c1));
+			p = fma2(p, a, pack2f(c0, c0));
+			p = fma2(p, a, pack2f(c0, c0));
+			u64 q = fma2(pack2f(c4, c4), a, pack2f(1.0f, 1.0f));
+			q = fma2(q, a, pack2f(c3 * c4, c3 * c4));
+			q = fma2(q, a, pack2f(c3, c3));
+			q = fma2(q, a, pack2f(c3, c3));
+			uint32_t q0, q1;
+			unpack2(q, q0, q1);
+			float r0, r1;
+			asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(__uint_as_float(q0)));
+			asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(__uint_as_float(q1)));
+			unpack2(mul2(mul2(pack2(x0, x1), p), pack2f(r0, r1)), y0, y1);
+		}
+
+		// Per-layer plan, built once per CTA in shared memory from the WnLayer table.
+		// A K = 3 layer has two delayed taps (delays 2d and d).  A tap with delay D >= 128 is pure history: its n rows get their
+		// own window (XE rows [0,n) or WB).  A tap with D < 128 mixes history and current frames: it reads XE row 128 + t - D,
+		// with the last D history rows staged at XE rows [128 - D, 128).  WB follows XE in shared memory, so both are
+		// addressed relative to XE.
+		struct TsLayer
+		{
+			uint32_t tap0Off, tap0Stride, tap1Off, tap1Stride;   // bytes: frame t's row of channel group g at XE + off + 16 t + g stride
+			int mixed;          // some tap reads current frames
+			int d, Lp, ringOff, ringIdx;
+			int wOff, wBytes;
+			uint32_t convLo16, convC16, oneHi16, oneLo16, oneC16;   // operand offsets inside the weight block, 16-byte units
+			int C;
+			int pad[3];
+		};
+		static_assert(sizeof(TsLayer) == 80, "TsLayer layout");
+
+		struct Ctx
+		{
+			const WnModelDev* M;
+			const TsLayer* Ls;
+			const float* Wg;
+			uint32_t xe;       // shared address of XE: [4][kRows][4] floats, then WB: [4][kWbRows][4]
+			uint32_t wbuf;     // shared address of the two weight buffers
+			uint32_t wbufStride;   // bytes
+			int* hdb;          // [2][2][36]: ring heads (head, head after this call) of the current / next stream
+			uint32_t barWin, barW0, barMma;   // barW0: two adjacent mbarriers (weight buffers 0 and 1)
+			uint32_t tmem;     // TMEM base (column 0, lane 0)
+			float* state;
+			int n, tid, warp, lane, S, gstride;
+			bool el;           // this lane is warp's elected MMA / TMA issuer
+			uint32_t wq;       // running weight-block counter (current layer's slot)
+			uint32_t winq;     // running window-phase counter
+			uint32_t mmaq;     // running MMA-commit counter
+			int cur;           // which hdb half belongs to the current stream
+		};
+		constexpr int kHdbHalf = 72;   // ints per stream in hdb: heads[36] | heads after the call[36]
+		constexpr uint32_t kWbOff = 4 * kRows * 16;   // WB relative to XE, bytes
+
+		// one lane: one bulk copy of layer b's weight block into buffer (slot & 1)
+		__device__ __forceinline__ void issue_weights(const Ctx& cx, int b, uint32_t slot)
+		{
+			const TsLayer& L = cx.Ls[b];
+			const uint32_t bar = cx.barW0 + 8u * (slot & 1u);
+			mbar_expect_tx(bar, (uint32_t)L.wBytes);
+			bulk_g2s(cx.wbuf + (slot & 1u) * cx.wbufStride, cx.Wg + L.wOff, (uint32_t)L.wBytes, bar);
+		}
+
+		// one WARP (all 32 lanes call it): TMA the history window(s) of layer l of stream `s` into XE / WB.
+		__device__ __forceinline__ void issue_windows(const Ctx& cx, int l, int s, const int* hd, int lane)
+		{
+			const TsLayer& L = cx.Ls[l];
+			const int CG = L.C >> 2;
+			const int D0 = 2 * L.d, D1 = L.d;
+			const bool pure0 = D0 >= kCur, pure1 = D1 >= kCur;
+			const int nwin = pure0 ? 2 : 1;
+			// window 0 <-> tap 0, window 1 <-> tap 1 (only when tap 0 is pure; otherwise tap 0's mixed window covers tap 1's rows)
+			const int cnt0 = pure0 ? cx.n : D0;
+			const int cnt1 = !pure0 ? 0 : (pure1 ? cx.n : D1);
+			if (lane == 0) mbar_expect_tx(cx.barWin, (uint32_t)(CG * (cnt0 + cnt1) * 16));
+			__syncwarp();
+			if (lane < nwin * CG)
+			{
+				const int w = lane >= CG ? 1 : 0, g = lane - w * CG;
+				const int cnt = w ? cnt1 : cnt0;
+				const int D = w ? D1 : D0;
+				// destination of row 0 of the window: pure windows start at their buffer's row 0, mixed ones end at row 128
+				const uint32_t off = w ? L.tap1Off : L.tap0Off;
+				const uint32_t stride = w ? L.tap1Stride : L.tap0Stride;
+				const int Lp = L.Lp;
+				int idx0 = hd[L.ringIdx] - D;
+				if (idx0 < 0) idx0 += Lp;
+				const int seg1 = min(cnt, Lp - idx0), seg2 = cnt - seg1;
+				const uint32_t dst = cx.xe + off + (uint32_t)g * stride;
+				const float* src = cx.state + (size_t)s * cx.M->stateStride + L.ringOff + (size_t)g * Lp * 4;
+				bulk_g2s(dst, src + (size_t)idx0 * 4, (uint32_t)seg1 * 16u, cx.barWin);
+				if (seg2 > 0) bulk_g2s(dst + (uint32_t)seg1 * 16u, src, (uint32_t)seg2 * 16u, cx.barWin);
+			}
+		}
+
+		// this thread's row of one delayed tap: shared memory -> [hi | lo] -> TMEM
+		template <int C>
+		__device__ __forceinline__ void stage_tap(uint32_t rowAddr, uint32_t planeStride, uint32_t taddr)
+		{
+			uint32_t v[2 * C];
+#pragma unroll
+			for (int q = 0; q < C / 4; q++)
+			{
+				const uint4 x = lds128(rowAddr + (uint32_t)q * planeStride);
+				v[4 * q + 0] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
+			}
+#pragma unroll
+			for (int c = 0; c < C; c += 2) split_lo2(v[c], v[c + 1], v[C + c], v[C + c + 1]);
+			tmem_st<2 * C>(taddr, v);
+		}
+
+		// One layer array for the CTA's stream.
+		template <int ARRAY>
+		__device__ __forceinline__ void run_array(Ctx& cx, const int firstLayer, const int numLayers, int s)
+		{
+			typedef Cols<ARRAY> TC;
+			constexpr int C = TC::C, CG = C / 4, KS = C / 8, N1 = C + 8;
+			const WnModelDev& M = *cx.M;
+			const int tid = cx.tid, warp = cx.warp;
+			const uint32_t tm = cx.tmem;
+			const uint32_t lanebase = tm + ((uint32_t)(warp * 32) << 16);
+			const int* hd = cx.hdb + cx.cur * kHdbHalf;
+			float* const st = cx.state + (size_t)s * M.stateStride;
+			constexpr uint32_t idC = idesc_of(C), idN1 = idesc_of(N1);
+
+			for (int li = 0; li < numLayers; li++)
+			{
+				const int l = firstLayer + li;
+				const TsLayer& L = cx.Ls[l];
+				const bool mixed = L.mixed != 0;
+				const uint32_t wb16 = (cx.wbuf + (cx.wq & 1u) * cx.wbufStride) >> 4;
+
+				// ================= stage the operands of this layer ====================================================
+				// the MMAs that produced XR (previous layer's 1x1, or the rechannel) are complete
+				mbar_wait(cx.barMma, cx.mmaq & 1u);
+				cx.mmaq++;
+				fence_after();
+				// next layer's weight block -> the other buffer (its last readers, the previous layer's MMAs, are complete)
+				if (tid == 96) issue_weights(cx, (l + 1 < M.numLayers) ? l + 1 : 0, cx.wq + 1);
+
+				uint32_t x[C];
+				tmem_ld<C>(lanebase + TC::XR, x);
+				if (mixed)
+				{
+					const uint32_t cur = cx.xe + (uint32_t)(kCur + tid) * 16u;
+#pragma unroll
+					for (int q = 0; q < CG; q++) sts128(cur + (uint32_t)q * (kRows * 16), x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
+				}
+				{
+					uint32_t xl[C];
+#pragma unroll
+					for (int c = 0; c < C; c += 2) split_lo2(x[c], x[c + 1], xl[c], xl[c + 1]);
+					tmem_st<C>(lanebase + TC::T2L, xl);
+				}
+				if (mixed) __syncthreads();   // current frames visible to the threads whose taps read them
+				mbar_wait(cx.barWin, cx.winq & 1u);   // this layer's history window(s) have landed
+				cx.winq++;
+				// history write-back (AdvanceFrames, WaveNet.h:59-65): frame t becomes ring column (head + t) mod Lp.  After the
+				// window wait: the TMA that read this ring must not race with the rows being replaced.
+				{
+					const int Lp = L.Lp;
+					const int first = cx.n > Lp ? cx.n - Lp : 0;
+					if (tid < cx.n && tid >= first)
+					{
+						// (head + t) mod Lp without a division: head + first is hdb's "head after the call" when n > Lp
+						int idx = (cx.n > Lp ? hd[36 + L.ringIdx] : hd[L.ringIdx]) + (tid - first);
+						if (idx >= Lp) idx -= Lp;
+						uint4* ring = reinterpret_cast<uint4*>(st + L.ringOff) + idx;
+#pragma unroll
+						for (int q = 0; q < CG; q++) ring[(size_t)q * Lp] = make_uint4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
+					}
+				}
+				{
+					const uint32_t row = cx.xe + (uint32_t)tid * 16u;
+					stage_tap<C>(row + L.tap0Off, L.tap0Stride, lanebase + TC::T0);
+					stage_tap<C>(row + L.tap1Off, L.tap1Stride, lanebase + TC::T1);
+				}
+				wait_st();
+				fence_before();
+				__syncthreads();   // operands complete in TMEM; shared-memory windows consumed
+				fence_after();
+				// the windows are free: warp 3 prefetches the next layer's (or the next stream's first layer's)
+				if (warp == 3)
+				{
+					if (l + 1 < M.numLayers) issue_windows(cx, l + 1, s, hd, cx.lane);
+					else if (s + cx.gstride < cx.S) issue_windows(cx, 0, s + cx.gstride, cx.hdb + (cx.cur ^ 1) * kHdbHalf, cx.lane);
+				}
+
+				// ================= dilated conv + mix-in + bias on the tensor core (WaveNet.h:250-289,471-476) ================
+				// warp 0 issues everything, in a fixed order: results do not depend on how a buffer is chunked into calls
+				if (warp == 0)
+				{
+					if (li > 0) mbar_wait(cx.barW0 + 8u * (cx.wq & 1u), (cx.wq >> 1) & 1u);   // (first layer: the array's entry code waited)
+					const u64 dHi = desc_at(wb16, C), dLo = desc_at(wb16 + L.convLo16, C);
+					if (cx.el)
+					{
+#pragma unroll
+						for (int k = 0; k < 3; k++)
+#pragma unroll
+							for (int ks = 0; ks < KS; ks++)
+							{
+								const uint32_t aHi = tm + (k == 0 ? TC::T0 : k == 1 ? TC::T1 : TC::XR) + 8u * ks;
+								const uint32_t aLo = tm + (k == 0 ? TC::T0 + C : k == 1 ? TC::T1 + C : TC::T2L) + 8u * ks;
+								const u64 boff = (u64)((k * CG + 2 * ks) * C);
+								mma_ts<1>(tm + TC::D, aHi, dHi + boff, idC);
+								mma_ts<1>(tm + TC::D, aLo, dHi + boff, idC);
+								mma_ts<1>(tm + TC::D, aHi, dLo + boff, idC);
+							}
+						mma_ts<1>(tm + TC::D, tm + kConst, desc_at(wb16 + L.convC16, C), idC);
+						mma_commit(cx.barMma);
+					}
+					__syncwarp();
+				}
+
+				// ================= activation (WaveNet.h:477-480); z -> TMEM as the A operand of the 1x1 =====================
+				mbar_wait(cx.barMma, cx.mmaq & 1u);
+				cx.mmaq++;
+				fence_after();
+				{
+					uint32_t z[2 * C];
+					{
+						uint32_t dv[C];
+						tmem_ld<C>(lanebase + TC::D, dv);
+						tmem_zero<C>(lanebase + TC::D);   // every conv MMA accumulates; the accumulator starts each layer at zero
+#pragma unroll
+						for (int c = 0; c < C; c += 2) fast_tanh2(dv[c], dv[c + 1], z[c], z[c + 1]);
+					}
+#pragma unroll
+					for (int c = 0; c < C; c += 2) split_lo2(z[c], z[c + 1], z[C + c], z[C + c + 1]);
+					tmem_st<2 * C>(lanebase + TC::T0, z);
+				}
+				wait_st();
+				fence_before();
+				__syncthreads();
+				fence_after();
+
+				// ================= 1x1 + bias + residual, head sum (WaveNet.h:482-491): XR|HD += [Zhi|Zlo] [W1x1 | Whead] ======
+				if (warp == 0)
+				{
+					const u64 dHi = desc_at(wb16 + L.oneHi16, N1), dLo = desc_at(wb16 + L.oneLo16, N1);
+					if (cx.el)
+					{
+#pragma unroll
+						for (int ks = 0; ks < KS; ks++)
+						{
+							const u64 boff = (u64)(2 * ks * N1);
+							mma_ts<1>(tm + TC::XR, tm + TC::T0 + 8u * ks, dHi + boff, idN1);
+							mma_ts<1>(tm + TC::XR, tm + TC::T0 + C + 8u * ks, dHi + boff, idN1);
+							mma_ts<1>(tm + TC::XR, tm + TC::T0 + 8u * ks, dLo + boff, idN1);
+						}
+						mma_ts<1>(tm + TC::XR, tm + kConst, desc_at(wb16 + L.oneC16, N1), idN1);
+						mma_commit(cx.barMma);
+					}
+					__syncwarp();
+				}
+				cx.wq++;
+			}
+		}
+
+		constexpr int kTableBytes = kMaxLayers * (int)sizeof(TsLayer);
+
+		__host__ __device__ constexpr size_t smem_fixed_bytes() { return (size_t)4 * kRows * 16 + (size_t)4 * kWbRows * 16; }
+
+		__global__ void __launch_bounds__(kThreads, 4)
+			wavenet_ts_kernel(const __grid_constant__ WnModelDev M, const float* __restrict__ Wg, float* __restrict__ state, int* __restrict__ heads,
+				const float* in, float* out, long long inSS, long long inFS, long long outSS, long long outFS, int S, int n)
+		{
+			extern __shared__ __align__(128) unsigned char smem[];
+			Ctx cx;
+			cx.M = &M;
+			cx.Wg = Wg;
+			cx.xe = smem_u32(smem);
+			cx.wbuf = cx.xe + (uint32_t)smem_fixed_bytes();
+			cx.wbufStride = (uint32_t)M.maxBlock * 4u;
+			TsLayer* Ls = reinterpret_cast<TsLayer*>(smem + smem_fixed_bytes() + (size_t)2 * M.maxBlock * 4);
+			cx.Ls = Ls;
+			cx.hdb = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(Ls) + kTableBytes);
+			unsigned long long* bars = reinterpret_cast<unsigned long long*>(cx.hdb + 2 * kHdbHalf);
+			uint32_t* tmemSlot = reinterpret_cast<uint32_t*>(bars + 4);
+			cx.barWin = smem_u32(&bars[0]);
+			cx.barW0 = smem_u32(&bars[1]);
+			cx.barMma = smem_u32(&bars[3]);
+			cx.n = n;
+			cx.tid = threadIdx.x;
+			cx.warp = threadIdx.x >> 5;
+			cx.lane = threadIdx.x & 31;
+			cx.S = S;
+			cx.gstride = gridDim.x;
+			cx.state = state;
+			cx.wq = 0; cx.winq = 0; cx.mmaq = 0; cx.cur = 0;
+			cx.el = elect_one();
+			const int tid = threadIdx.x;
+			const int warp = cx.warp, lane = cx.lane;
+
+			// per-layer plan
+			if (tid < M.numLayers)
+			{
+				const WnLayer& W = M.layers[tid];
+				TsLayer T;
+				const int C = M.arrays[W.array].C;
+				const int D0 = 2 * W.d, D1 = W.d;
+				const bool pure0 = D0 >= kCur, pure1 = D1 >= kCur;
+				if (pure1) { T.tap0Off = 0; T.tap0Stride = kRows * 16; T.tap1Off = kWbOff; T.tap1Stride = kWbRows * 16; }
+				else if (pure0) { T.tap0Off = kWbOff; T.tap0Stride = kWbRows * 16; T.tap1Off = (uint32_t)(kCur - D1) * 16u; T.tap1Stride = kRows * 16; }
+				else { T.tap0Off = (uint32_t)(kCur - D0) * 16u; T.tap0Stride = kRows * 16; T.tap1Off = (uint32_t)(kCur - D1) * 16u; T.tap1Stride = kRows * 16; }
+				T.mixed = pure1 ? 0 : 1;
+				T.d = W.d; T.Lp = W.Lp; T.ringOff = W.ringOff; T.ringIdx = W.ringIdx;
+				T.wOff = W.wOff; T.wBytes = W.wSize * 4;
+				T.convLo16 = (uint32_t)W.oConvLo >> 2; T.convC16 = (uint32_t)W.oConvB >> 2;
+				T.oneHi16 = (uint32_t)W.oOneW >> 2; T.oneLo16 = (uint32_t)W.oOneLo >> 2; T.oneC16 = (uint32_t)W.oOneB >> 2;
+				T.C = C;
+				T.pad[0] = T.pad[1] = T.pad[2] = 0;
+				Ls[tid] = T;
+			}
+			if (tid == 0)
+			{
+				mbar_init(cx.barWin, 1);
+				mbar_init(cx.barW0, 1);
+				mbar_init(cx.barW0 + 8u, 1);
+				mbar_init(cx.barMma, 1);
+				asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+			}
+			if (warp == 0)
+			{
+				asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(smem_u32(tmemSlot)) : "memory");
+				asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+			}
+			const int s0 = blockIdx.x;
+			if (tid < M.numRings && s0 < S)
+			{
+				const int Lp = M.ringLp[tid];
+				const int h = heads[(size_t)s0 * M.numRings + tid];
+				int hn = h + (n % Lp);
+				if (hn >= Lp) hn -= Lp;
+				cx.hdb[tid] = h;
+				cx.hdb[36 + tid] = hn;
+			}
+			fence_before();
+			__syncthreads();
+			fence_after();
+			cx.tmem = *tmemSlot;
+			const uint32_t tm = cx.tmem;
+			const uint32_t lanebase = tm + ((uint32_t)(warp * 32) << 16);
+			const int first0 = M.arrays[0].firstLayer, num0 = M.arrays[0].numLayers;
+			const int first1 = M.arrays[1].firstLayer, num1 = M.arrays[1].numLayers;
+			// entry / transition operands sit in the first block of each array (na_device.h, tc == 2), 16-byte units
+			const uint32_t re0 = (uint32_t)M.layers[first0].oRe >> 2, hd0 = (uint32_t)M.layers[first0].oHeadB >> 2;
+			const uint32_t re1 = (uint32_t)M.layers[first1].oRe >> 2, re1Lo = (uint32_t)M.layers[first1].oMix >> 2;
+			const uint32_t ch1 = (uint32_t)M.layers[first1].oHeadW >> 2, hd1 = (uint32_t)M.layers[first1].oHeadB >> 2;
+
+			if (tid == 96) issue_weights(cx, 0, 0);
+			if (warp == 3 && s0 < S) issue_windows(cx, 0, s0, cx.hdb, lane);
+			float cond = 0.0f;
+			if (tid < n && s0 < S) cond = in[(long long)s0 * inSS + (long long)tid * inFS];
+
+			for (int s = s0; s < S; s += gridDim.x)
+			{
+				const int sn = s + gridDim.x;
+				int* hdNext = cx.hdb + (cx.cur ^ 1) * kHdbHalf;
+				float condNext = 0.0f;
+				if (sn < S)
+				{
+					if (tid < M.numRings)
+					{
+						const int Lp = M.ringLp[tid];
+						const int h = heads[(size_t)sn * M.numRings + tid];
+						int hn = h + (n % Lp);
+						if (hn >= Lp) hn -= Lp;
+						hdNext[tid] = h;
+						hdNext[36 + tid] = hn;
+					}
+					if (tid < n) condNext = in[(long long)sn * inSS + (long long)tid * inFS];
+				}
+
+				// ---- entry: constant operand, zero conv accumulator, rechannel 1 -> C0 and head bias on the tensor core ----
+				{
+					uint32_t cv[8];
+					uint32_t cl, dummy;
+					split_lo2(__float_as_uint(cond), 0u, cl, dummy);
+					cv[0] = __float_as_uint(cond); cv[1] = cl; cv[2] = cv[0];
+					cv[3] = 0x3F800000u; cv[4] = 0x3F800000u; cv[5] = 0x3F800000u; cv[6] = 0u; cv[7] = 0u;
+					tmem_st<8>(lanebase + kConst, cv);
+					tmem_zero<16>(lanebase + Cols<0>::D);
+				}
+				wait_st();
+				fence_before();
+				__syncthreads();
+				fence_after();
+				if (warp == 0)
+				{
+					mbar_wait(cx.barW0 + 8u * (cx.wq & 1u), (cx.wq >> 1) & 1u);
+					const uint32_t wb16 = (cx.wbuf + (cx.wq & 1u) * cx.wbufStride) >> 4;
+					if (cx.el)
+					{
+						mma_ts<0>(tm + Cols<0>::XR, tm + kConst, desc_at(wb16 + re0, 16), idesc_of(16));
+						mma_ts<0>(tm + Cols<0>::HD, tm + kConst, desc_at(wb16 + hd0, 8), idesc_of(8));
+						mma_commit(cx.barMma);
+					}
+					__syncwarp();
+				}
+				run_array<0>(cx, first0, num0, s);
+
+				// ---- array transition (WaveNet.h:785-789): rechannel C0 -> C1 of the array output, head carry ----
+				mbar_wait(cx.barMma, cx.mmaq & 1u);
+				cx.mmaq++;
+				fence_after();
+				{
+					uint32_t x[16], xl[16];
+					tmem_ld<16>(lanebase + Cols<0>::XR, x);
+#pragma unroll
+					for (int c = 0; c < 16; c += 2) split_lo2(x[c], x[c + 1], xl[c], xl[c + 1]);
+					tmem_st<16>(lanebase + Cols<0>::T2L, xl);
+					uint32_t h[8], hl[8];
+					tmem_ld<8>(lanebase + Cols<0>::HD, h);
+#pragma unroll
+					for (int c = 0; c < 8; c += 2) split_lo2(h[c], h[c + 1], hl[c], hl[c + 1]);
+					tmem_st<8>(lanebase + kHdLo, hl);
+					tmem_zero<8>(lanebase + Cols<1>::D);
+				}
+				wait_st();
+				fence_before();
+				__syncthreads();
+				fence_after();
+				if (warp == 0)
+				{
+					mbar_wait(cx.barW0 + 8u * (cx.wq & 1u), (cx.wq >> 1) & 1u);
+					const uint32_t wb16 = (cx.wbuf + (cx.wq & 1u) * cx.wbufStride) >> 4;
+					if (cx.el)
+					{
+						const u64 dHi = desc_at(wb16 + re1, 8), dLo = desc_at(wb16 + re1Lo, 8);
+						mma_ts<0>(tm + Cols<1>::XR, tm + Cols<0>::XR, dHi, idesc_of(8));
+						mma_ts<1>(tm + Cols<1>::XR, tm + Cols<0>::T2L, dHi, idesc_of(8));
+						mma_ts<1>(tm + Cols<1>::XR, tm + Cols<0>::XR, dLo, idesc_of(8));
+						mma_ts<1>(tm + Cols<1>::XR, tm + Cols<0>::XR + 8u, dHi + 16u, idesc_of(8));
+						mma_ts<1>(tm + Cols<1>::XR, tm + Cols<0>::T2L + 8u, dHi + 16u, idesc_of(8));
+						mma_ts<1>(tm + Cols<1>::XR, tm + Cols<0>::XR + 8u, dLo + 16u, idesc_of(8));
+						const u64 cHi = desc_at(wb16 + ch1, 8), cLo = desc_at(wb16 + ch1 + 16u, 8);
+						mma_ts<0>(tm + Cols<1>::HD, tm + Cols<0>::HD, cHi, idesc_of(8));
+						mma_ts<1>(tm + Cols<1>::HD, tm + kHdLo, cHi, idesc_of(8));
+						mma_ts<1>(tm + Cols<1>::HD, tm + Cols<0>::HD, cLo, idesc_of(8));
+						mma_ts<1>(tm + Cols<1>::HD, tm + kConst, desc_at(wb16 + hd1, 8), idesc_of(8));
+						mma_commit(cx.barMma);
+					}
+					__syncwarp();
+				}
+				run_array<1>(cx, first1, num1, s);
+
+				// ---- output (WaveNet.h:793-798) ----
+				mbar_wait(cx.barMma, cx.mmaq & 1u);
+				cx.mmaq++;
+				fence_after();
+				{
+					uint32_t h[8];
+					tmem_ld<8>(lanebase + Cols<1>::HD, h);
+					if (tid < n) out[(long long)s * outSS + (long long)tid * outFS] = M.headScale * __uint_as_float(h[0]);
+				}
+				if (tid < M.numRings) heads[(size_t)s * M.numRings + tid] = cx.hdb[cx.cur * kHdbHalf + 36 + tid];
+				cx.cur ^= 1;
+				cond = condNext;
+				// the entry barrier of the next stream orders these TMEM / hdb reads before they are overwritten
+				fence_before();
+			}
+
+			// drain the weight prefetch that ran ahead of the last layer, then release TMEM
+			mbar_wait(cx.barW0 + 8u * (cx.wq & 1u), (cx.wq >> 1) & 1u);
+			fence_before();
+			__syncthreads();
+			if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(cx.tmem) : "memory");
+		}
+	}
+
+	bool wavenet_ts_variant_supported(int C0, int C1, int act)
+	{
+		return C0 == 16 && C1 == 8 && act == 0;
+	}
+
+	cudaError_t wavenet_ts_launch(const WnModelDev& M, const WnLaunch& a)
+	{
+		if (!wavenet_ts_variant_supported(M.arrays[0].C, M.numArrays > 1 ? M.arrays[1].C : 0, M.arrays[0].act)) return cudaErrorNotSupported;
+		if (a.n > ts::kCur) return cudaErrorInvalidValue;
+		auto kfn = ts::wavenet_ts_kernel;
+		const size_t smem = ts::smem_fixed_bytes() + (size_t)2 * M.maxBlock * 4 + ts::kTableBytes + 2 * ts::kHdbHalf * 4 + 4 * 8 + 16;
+		cudaError_t err = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		if (err != cudaSuccess) return err;
+		int grid = a.numSMs * 4;
+		if (grid > a.S) grid = a.S;
+		if (grid < 1) grid = 1;
+		kfn<<<grid, ts::kThreads, smem, a.stream>>>(M, a.weights, a.state, a.heads, a.in, a.out, a.inSS, a.inFS, a.outSS, a.outFS, a.S, a.n);
+		return cudaGetLastError();
+	}
+}
