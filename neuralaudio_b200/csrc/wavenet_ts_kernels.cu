@@ -31,7 +31,6 @@ namespace nab200
 {
 	namespace ts
 	{
-		constexpr int kThreads = 128;
 		constexpr int kRows = 256;      // rows per XE plane: [0,128) history, [128,256) current frames
 		constexpr int kCur = 128;
 		constexpr int kWbRows = 128;    // rows per plane of the second window buffer
@@ -67,18 +66,20 @@ namespace nab200
 			asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 		}
 
-		// try_wait suspends the thread in hardware up to the hinted time, so a waiting warp costs almost no issue slots
+		// try_wait blocks in hardware for a bounded time before it reports failure, so the loop rarely iterates.  (Passing
+		// an explicit suspend-time hint made ptxas emit TRYWAIT + NANOSLEEP.SYNCS + PHASECHK per iteration and the waiting
+		// warps then spent a third of the SM's issue slots spinning - ncu, round 1.)
 		__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 		{
 			asm volatile(
 				"{\n"
 				".reg .pred P1;\n"
 				"LAB_WAIT:\n"
-				"mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n"
+				"mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
 				"@P1 bra DONE;\n"
 				"bra LAB_WAIT;\n"
 				"DONE:\n"
-				"}" ::"r"(bar), "r"(parity), "r"(0x989680u) : "memory");
+				"}" ::"r"(bar), "r"(parity) : "memory");
 		}
 
 		__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar)
@@ -245,37 +246,108 @@ namespace nab200
 		// addressed relative to XE.
 		struct TsLayer
 		{
-			uint32_t tap0Off, tap0Stride, tap1Off, tap1Stride;   // bytes: frame t's row of channel group g at XE + off + 16 t + g stride
+			// group 0 (stagers, uint4): frame t's row of channel group g of tap j is at XE + tapOff + 16 t + g tapStride (bytes)
+			uint32_t tap0Off, tap0Stride, tap1Off, tap1Stride;
+			// group 1 (stagers, uint4)
 			int mixed;          // some tap reads current frames
-			int d, Lp, ringOff, ringIdx;
-			int wOff, wBytes;
-			uint32_t convLo16, convC16, oneHi16, oneLo16, oneC16;   // operand offsets inside the weight block, 16-byte units
-			int C;
-			int pad[3];
+			int Lp, ringOff, ringIdx;
+			// groups 2, 3 (stagers, history prefetch, uint4 each): thread u < cnt copies ring row (head - D + u) to window row u of
+			// (off, stride); cnt < 0 means n
+			int cpCnt0, cpD0; uint32_t cpOff0, cpStride0;
+			int cpCnt1, cpD1; uint32_t cpOff1, cpStride1;
+			// group 4 (issuer, uint4): operand offsets inside the weight block, 16-byte units
+			uint32_t convLo16, convC16, oneHi16, oneLo16;
+			// group 5
+			uint32_t oneC16; int wOff, wBytes, C;
+			int d, pad[3];
 		};
-		static_assert(sizeof(TsLayer) == 80, "TsLayer layout");
+		static_assert(sizeof(TsLayer) == 112 && sizeof(TsLayer) % 16 == 0, "TsLayer layout");
+
+#ifdef NAB_TS_TIMING
+		// tools/ts_timing.cu: cycle stamps of one thread per warp of a few CTAs, [cta][warp][stream][layer][stamp]
+		__device__ long long g_stamps[4][5][4][32][12];
+#define TS_STAMP(i) do { if (cx.stampOn) g_stamps[cx.stampCta][cx.warp][cx.stampStream][l][i] = clock64(); } while (0)
+#else
+#define TS_STAMP(i) do { } while (0)
+#endif
+
+		// Roles: warps 0..3 ("stagers") own the TMEM lanes = frames: they build operands and run the activation;
+		// warp 4 (the "issuer") issues every tcgen05.mma and the weight TMA.
+		// Hand-offs never spin in the stagers: stagers -> issuer is a named hardware barrier the stagers only ARRIVE on
+		// (bar.arrive, non-blocking) and the issuer SYNCs on; MMA completion reaches the issuer through the mbarrier of
+		// tcgen05.commit (the only try_wait loops of the kernel, one warp, short waits) and the issuer then releases the
+		// stagers through another named barrier they block on in hardware.  (With every warp polling mbarriers a third of
+		// the SM's issue slots went to try_wait loops - ncu, round 1.)
+		constexpr int kStagerThreads = 128;
+		constexpr int kThreads = 160;
+		enum : int
+		{
+			kBarMix = 1,      // stagers only: current frames visible to the stagers whose taps read them
+			kBarE = 2,        // stagers -> issuer: entry / transition operands staged
+			kBarT2 = 3,       // stagers -> issuer: low part of the undelayed tap staged
+			kBarT0 = 4,       // stagers -> issuer: tap 0 staged
+			kBarT1 = 5,       // stagers -> issuer: tap 1 staged
+			kBarZ = 6,        // stagers -> issuer: activated output staged
+			kBarDReady = 7,   // issuer -> stagers: conv accumulator complete
+			kBarXReady = 8    // issuer -> stagers: residual / head accumulators complete
+		};
+		__device__ __forceinline__ void nbar_arrive(int id) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(kThreads) : "memory"); }
+		__device__ __forceinline__ void nbar_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(kThreads) : "memory"); }
 
 		struct Ctx
 		{
 			const WnModelDev* M;
 			const TsLayer* Ls;
+			uint32_t lsAddr;   // shared address of the TsLayer table
 			const float* Wg;
 			uint32_t xe;       // shared address of XE: [4][kRows][4] floats, then WB: [4][kWbRows][4]
 			uint32_t wbuf;     // shared address of the two weight buffers
 			uint32_t wbufStride;   // bytes
 			int* hdb;          // [2][2][36]: ring heads (head, head after this call) of the current / next stream
-			uint32_t barWin, barW0, barMma;   // barW0: two adjacent mbarriers (weight buffers 0 and 1)
+			// mbarriers: barD / barX tcgen05.commit of the conv / 1x1 MMAs (waited by the issuer only), barW0 (+8) weight buffers
+			uint32_t barW0, barD, barX;
 			uint32_t tmem;     // TMEM base (column 0, lane 0)
 			float* state;
 			int n, tid, warp, lane, S, gstride;
-			bool el;           // this lane is warp's elected MMA / TMA issuer
-			uint32_t wq;       // running weight-block counter (current layer's slot)
-			uint32_t winq;     // running window-phase counter
-			uint32_t mmaq;     // running MMA-commit counter
+			bool el;           // this lane is its warp's elected lane
+			uint32_t wq;       // issuer: running weight-block counter (current layer's slot)
+			uint32_t dq, xq;   // issuer: running barD / barX phases
 			int cur;           // which hdb half belongs to the current stream
+#ifdef NAB_TS_TIMING
+			bool stampOn; int stampCta, stampStream;
+#endif
 		};
 		constexpr int kHdbHalf = 72;   // ints per stream in hdb: heads[36] | heads after the call[36]
 		constexpr uint32_t kWbOff = 4 * kRows * 16;   // WB relative to XE, bytes
+
+		// stager: my TMEM stores are done and ordered before the issuer's MMAs, then a non-blocking arrival
+		__device__ __forceinline__ void stager_arrive(int id)
+		{
+			wait_st();
+			fence_before();
+			nbar_arrive(id);
+		}
+
+		// issuer: wait (blocked in hardware) until all stagers have arrived
+		__device__ __forceinline__ void issuer_sync(int id)
+		{
+			nbar_sync(id);
+			fence_after();
+		}
+
+		// issuer: the MMAs committed to `bar` are complete -> release the stagers blocked on named barrier `id`
+		__device__ __forceinline__ void issuer_release(uint32_t bar, uint32_t parity, int id)
+		{
+			mbar_wait(bar, parity);
+			nbar_arrive(id);
+		}
+
+		// stager: block until the issuer has seen the accumulator complete
+		__device__ __forceinline__ void stager_wait(int id)
+		{
+			nbar_sync(id);
+			fence_after();
+		}
 
 		// one lane: one bulk copy of layer b's weight block into buffer (slot & 1)
 		__device__ __forceinline__ void issue_weights(const Ctx& cx, int b, uint32_t slot)
@@ -286,36 +358,49 @@ namespace nab200
 			bulk_g2s(cx.wbuf + (slot & 1u) * cx.wbufStride, cx.Wg + L.wOff, (uint32_t)L.wBytes, bar);
 		}
 
-		// one WARP (all 32 lanes call it): TMA the history window(s) of layer l of stream `s` into XE / WB.
-		__device__ __forceinline__ void issue_windows(const Ctx& cx, int l, int s, const int* hd, int lane)
+		__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src)
 		{
-			const TsLayer& L = cx.Ls[l];
-			const int CG = L.C >> 2;
-			const int D0 = 2 * L.d, D1 = L.d;
-			const bool pure0 = D0 >= kCur, pure1 = D1 >= kCur;
-			const int nwin = pure0 ? 2 : 1;
-			// window 0 <-> tap 0, window 1 <-> tap 1 (only when tap 0 is pure; otherwise tap 0's mixed window covers tap 1's rows)
-			const int cnt0 = pure0 ? cx.n : D0;
-			const int cnt1 = !pure0 ? 0 : (pure1 ? cx.n : D1);
-			if (lane == 0) mbar_expect_tx(cx.barWin, (uint32_t)(CG * (cnt0 + cnt1) * 16));
-			__syncwarp();
-			if (lane < nwin * CG)
+			asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+		}
+
+		// Every stager thread (all 128 call it): copy my rows of the history window(s) of layer l of stream `s` from the HBM
+		// ring into XE / WB with cp.async (16 bytes per channel group and row; consecutive threads <-> consecutive rows, so a
+		// warp's copies are one contiguous 512-byte run per channel group); one cp.async group per layer.
+		// The windows are tens of small strided runs per layer: per-thread LDGSTS moves them with ~10 instructions per
+		// thread, where one TMA bulk copy per run cost the issuing warp ~1000 cycles per layer (tools/ts_timing.cu).
+		template <int CG>
+		__device__ __forceinline__ void prefetch_windows(const Ctx& cx, int l, int s, const int* hd)
+		{
+			const uint32_t la = cx.lsAddr + (uint32_t)l * (uint32_t)sizeof(TsLayer);
+			const uint4 g1 = lds128(la + 16), j0 = lds128(la + 32), j1 = lds128(la + 48);
+			const int Lp = (int)g1.y;
+			const int head = hd[g1.w];
+			const uint4* ring = reinterpret_cast<const uint4*>(cx.state + (size_t)s * cx.M->stateStride + (int)g1.z);
+			const int u = cx.tid;
+			const uint32_t dstRow = cx.xe + (uint32_t)u * 16u;
 			{
-				const int w = lane >= CG ? 1 : 0, g = lane - w * CG;
-				const int cnt = w ? cnt1 : cnt0;
-				const int D = w ? D1 : D0;
-				// destination of row 0 of the window: pure windows start at their buffer's row 0, mixed ones end at row 128
-				const uint32_t off = w ? L.tap1Off : L.tap0Off;
-				const uint32_t stride = w ? L.tap1Stride : L.tap0Stride;
-				const int Lp = L.Lp;
-				int idx0 = hd[L.ringIdx] - D;
-				if (idx0 < 0) idx0 += Lp;
-				const int seg1 = min(cnt, Lp - idx0), seg2 = cnt - seg1;
-				const uint32_t dst = cx.xe + off + (uint32_t)g * stride;
-				const float* src = cx.state + (size_t)s * cx.M->stateStride + L.ringOff + (size_t)g * Lp * 4;
-				bulk_g2s(dst, src + (size_t)idx0 * 4, (uint32_t)seg1 * 16u, cx.barWin);
-				if (seg2 > 0) bulk_g2s(dst + (uint32_t)seg1 * 16u, src, (uint32_t)seg2 * 16u, cx.barWin);
+				const int cnt = (int)j0.x < 0 ? cx.n : (int)j0.x;
+				if (u < cnt)
+				{
+					int idx = head - (int)j0.y + u;
+					if (idx < 0) idx += Lp;
+					const uint4* src = ring + idx;
+#pragma unroll
+					for (int g = 0; g < CG; g++) cp_async16(dstRow + j0.z + (uint32_t)g * j0.w, src + (size_t)g * Lp);
+				}
 			}
+			{
+				const int cnt = (int)j1.x < 0 ? cx.n : (int)j1.x;
+				if (u < cnt)
+				{
+					int idx = head - (int)j1.y + u;
+					if (idx < 0) idx += Lp;
+					const uint4* src = ring + idx;
+#pragma unroll
+					for (int g = 0; g < CG; g++) cp_async16(dstRow + j1.z + (uint32_t)g * j1.w, src + (size_t)g * Lp);
+				}
+			}
+			asm volatile("cp.async.commit_group;" ::: "memory");
 		}
 
 		// this thread's row of one delayed tap: shared memory -> [hi | lo] -> TMEM
@@ -334,35 +419,29 @@ namespace nab200
 			tmem_st<2 * C>(taddr, v);
 		}
 
-		// One layer array for the CTA's stream.
+		// ---- stager warps: one layer array of the CTA's stream ------------------------------------------------------
 		template <int ARRAY>
-		__device__ __forceinline__ void run_array(Ctx& cx, const int firstLayer, const int numLayers, int s)
+		__device__ __forceinline__ void stage_array(Ctx& cx, const int firstLayer, const int numLayers, int s)
 		{
 			typedef Cols<ARRAY> TC;
-			constexpr int C = TC::C, CG = C / 4, KS = C / 8, N1 = C + 8;
+			constexpr int C = TC::C, CG = C / 4;
 			const WnModelDev& M = *cx.M;
-			const int tid = cx.tid, warp = cx.warp;
-			const uint32_t tm = cx.tmem;
-			const uint32_t lanebase = tm + ((uint32_t)(warp * 32) << 16);
+			const int tid = cx.tid;
+			const uint32_t lanebase = cx.tmem + ((uint32_t)(cx.warp * 32) << 16);
 			const int* hd = cx.hdb + cx.cur * kHdbHalf;
 			float* const st = cx.state + (size_t)s * M.stateStride;
-			constexpr uint32_t idC = idesc_of(C), idN1 = idesc_of(N1);
 
 			for (int li = 0; li < numLayers; li++)
 			{
 				const int l = firstLayer + li;
-				const TsLayer& L = cx.Ls[l];
-				const bool mixed = L.mixed != 0;
-				const uint32_t wb16 = (cx.wbuf + (cx.wq & 1u) * cx.wbufStride) >> 4;
+				const uint32_t la = cx.lsAddr + (uint32_t)l * (uint32_t)sizeof(TsLayer);
+				const uint4 g0 = lds128(la), g1 = lds128(la + 16);
+				const bool mixed = g1.x != 0;
 
-				// ================= stage the operands of this layer ====================================================
-				// the MMAs that produced XR (previous layer's 1x1, or the rechannel) are complete
-				mbar_wait(cx.barMma, cx.mmaq & 1u);
-				cx.mmaq++;
-				fence_after();
-				// next layer's weight block -> the other buffer (its last readers, the previous layer's MMAs, are complete)
-				if (tid == 96) issue_weights(cx, (l + 1 < M.numLayers) ? l + 1 : 0, cx.wq + 1);
-
+				// ---- the residual stream after the previous layer: its low part is the undelayed tap's second operand ----
+				TS_STAMP(0);
+				stager_wait(kBarXReady);
+				TS_STAMP(1);
 				uint32_t x[C];
 				tmem_ld<C>(lanebase + TC::XR, x);
 				if (mixed)
@@ -377,70 +456,50 @@ namespace nab200
 					for (int c = 0; c < C; c += 2) split_lo2(x[c], x[c + 1], xl[c], xl[c + 1]);
 					tmem_st<C>(lanebase + TC::T2L, xl);
 				}
-				if (mixed) __syncthreads();   // current frames visible to the threads whose taps read them
-				mbar_wait(cx.barWin, cx.winq & 1u);   // this layer's history window(s) have landed
-				cx.winq++;
-				// history write-back (AdvanceFrames, WaveNet.h:59-65): frame t becomes ring column (head + t) mod Lp.  After the
-				// window wait: the TMA that read this ring must not race with the rows being replaced.
+				stager_arrive(kBarT2);
+				TS_STAMP(2);
+				// my copies of this layer's history window(s) have landed; where a tap mixes history and current frames the rows
+				// other threads copied / produced must be visible too (named barrier among the stagers)
+				asm volatile("cp.async.wait_group 0;" ::: "memory");
+				TS_STAMP(3);
+				if (mixed) asm volatile("bar.sync 1, 128;" ::: "memory");   // kBarMix, kStagerThreads
+				TS_STAMP(4);
+				const uint32_t row = cx.xe + (uint32_t)tid * 16u;
+				stage_tap<C>(row + g0.x, g0.y, lanebase + TC::T0);
+				stager_arrive(kBarT0);
+				TS_STAMP(5);
+				stage_tap<C>(row + g0.z, g0.w, lanebase + TC::T1);
+				stager_arrive(kBarT1);
+				TS_STAMP(6);
+				// history write-back (AdvanceFrames, WaveNet.h:59-65): frame t becomes ring column (head + t) mod Lp.  Off the
+				// critical path (the issuer is busy with the conv now) and after the window wait: the copies that read this ring
+				// must not race with the rows being replaced (a row is replaced by the thread that copied it or, behind the
+				// barrier, after its copy has landed).
 				{
-					const int Lp = L.Lp;
+					const int Lp = (int)g1.y;
 					const int first = cx.n > Lp ? cx.n - Lp : 0;
 					if (tid < cx.n && tid >= first)
 					{
 						// (head + t) mod Lp without a division: head + first is hdb's "head after the call" when n > Lp
-						int idx = (cx.n > Lp ? hd[36 + L.ringIdx] : hd[L.ringIdx]) + (tid - first);
+						int idx = (cx.n > Lp ? hd[36 + g1.w] : hd[g1.w]) + (tid - first);
 						if (idx >= Lp) idx -= Lp;
-						uint4* ring = reinterpret_cast<uint4*>(st + L.ringOff) + idx;
+						uint4* ring = reinterpret_cast<uint4*>(st + (int)g1.z) + idx;
 #pragma unroll
 						for (int q = 0; q < CG; q++) ring[(size_t)q * Lp] = make_uint4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
 					}
 				}
-				{
-					const uint32_t row = cx.xe + (uint32_t)tid * 16u;
-					stage_tap<C>(row + L.tap0Off, L.tap0Stride, lanebase + TC::T0);
-					stage_tap<C>(row + L.tap1Off, L.tap1Stride, lanebase + TC::T1);
-				}
-				wait_st();
-				fence_before();
-				__syncthreads();   // operands complete in TMEM; shared-memory windows consumed
-				fence_after();
-				// the windows are free: warp 3 prefetches the next layer's (or the next stream's first layer's)
-				if (warp == 3)
-				{
-					if (l + 1 < M.numLayers) issue_windows(cx, l + 1, s, hd, cx.lane);
-					else if (s + cx.gstride < cx.S) issue_windows(cx, 0, s + cx.gstride, cx.hdb + (cx.cur ^ 1) * kHdbHalf, cx.lane);
-				}
 
-				// ================= dilated conv + mix-in + bias on the tensor core (WaveNet.h:250-289,471-476) ================
-				// warp 0 issues everything, in a fixed order: results do not depend on how a buffer is chunked into calls
-				if (warp == 0)
+				// ---- activation (WaveNet.h:477-480); z -> TMEM as the A operand of the 1x1 ----
+				stager_wait(kBarDReady);
+				TS_STAMP(7);
+				// every stager has staged both taps (the conv could not complete otherwise): the shared-memory windows are free,
+				// prefetch the next layer's (or the next stream's first layer's) history
+				if (l + 1 < M.numLayers)
 				{
-					if (li > 0) mbar_wait(cx.barW0 + 8u * (cx.wq & 1u), (cx.wq >> 1) & 1u);   // (first layer: the array's entry code waited)
-					const u64 dHi = desc_at(wb16, C), dLo = desc_at(wb16 + L.convLo16, C);
-					if (cx.el)
-					{
-#pragma unroll
-						for (int k = 0; k < 3; k++)
-#pragma unroll
-							for (int ks = 0; ks < KS; ks++)
-							{
-								const uint32_t aHi = tm + (k == 0 ? TC::T0 : k == 1 ? TC::T1 : TC::XR) + 8u * ks;
-								const uint32_t aLo = tm + (k == 0 ? TC::T0 + C : k == 1 ? TC::T1 + C : TC::T2L) + 8u * ks;
-								const u64 boff = (u64)((k * CG + 2 * ks) * C);
-								mma_ts<1>(tm + TC::D, aHi, dHi + boff, idC);
-								mma_ts<1>(tm + TC::D, aLo, dHi + boff, idC);
-								mma_ts<1>(tm + TC::D, aHi, dLo + boff, idC);
-							}
-						mma_ts<1>(tm + TC::D, tm + kConst, desc_at(wb16 + L.convC16, C), idC);
-						mma_commit(cx.barMma);
-					}
-					__syncwarp();
+					if (ARRAY == 0 && li + 1 < numLayers) prefetch_windows<4>(cx, l + 1, s, hd);
+					else prefetch_windows<2>(cx, l + 1, s, hd);
 				}
-
-				// ================= activation (WaveNet.h:477-480); z -> TMEM as the A operand of the 1x1 =====================
-				mbar_wait(cx.barMma, cx.mmaq & 1u);
-				cx.mmaq++;
-				fence_after();
+				else if (s + cx.gstride < cx.S) prefetch_windows<4>(cx, 0, s + cx.gstride, cx.hdb + (cx.cur ^ 1) * kHdbHalf);
 				{
 					uint32_t z[2 * C];
 					{
@@ -454,35 +513,141 @@ namespace nab200
 					for (int c = 0; c < C; c += 2) split_lo2(z[c], z[c + 1], z[C + c], z[C + c + 1]);
 					tmem_st<2 * C>(lanebase + TC::T0, z);
 				}
-				wait_st();
-				fence_before();
-				__syncthreads();
-				fence_after();
+				stager_arrive(kBarZ);
+				TS_STAMP(8);
+			}
+		}
 
-				// ================= 1x1 + bias + residual, head sum (WaveNet.h:482-491): XR|HD += [Zhi|Zlo] [W1x1 | Whead] ======
-				if (warp == 0)
+		// ---- issuer warp: one layer array of the CTA's stream --------------------------------------------------------
+		// MMAs into one accumulator are always issued in the same order (undelayed tap, constant operand, tap 0, tap 1), so
+		// results do not depend on timing or on how a buffer is chunked into calls.
+		template <int ARRAY>
+		__device__ __forceinline__ void issue_array(Ctx& cx, const int firstLayer, const int numLayers, int s)
+		{
+			typedef Cols<ARRAY> TC;
+			constexpr int C = TC::C, CG = C / 4, KS = C / 8, N1 = C + 8;
+			const WnModelDev& M = *cx.M;
+			const uint32_t tm = cx.tmem;
+			constexpr uint32_t idC = idesc_of(C), idN1 = idesc_of(N1);
+
+			// weight blocks: layer 0 of the array was awaited by the entry / transition code, layer li + 1 is awaited inside layer li
+			for (int li = 0; li < numLayers; li++)
+			{
+				const int l = firstLayer + li;
+				const uint32_t la = cx.lsAddr + (uint32_t)l * (uint32_t)sizeof(TsLayer);
+				const uint4 g4 = lds128(la + 64);       // convLo16, convC16, oneHi16, oneLo16
+				const uint32_t oneC16 = lds128(la + 80).x;
+				const uint32_t wb16 = (cx.wbuf + (cx.wq & 1u) * cx.wbufStride) >> 4;
+				const u64 dHi = desc_at(wb16, C), dLo = desc_at(wb16 + g4.x, C);
+
+				// ---- dilated conv + mix-in + bias (WaveNet.h:250-289,471-476), operands as the stagers deliver them ----
+				TS_STAMP(0);
+				issuer_sync(kBarT2);
+				TS_STAMP(1);
+				if (cx.el)
 				{
-					const u64 dHi = desc_at(wb16 + L.oneHi16, N1), dLo = desc_at(wb16 + L.oneLo16, N1);
-					if (cx.el)
+					// the stagers have seen the previous layer complete: the other weight buffer is free
+					issue_weights(cx, (l + 1 < M.numLayers) ? l + 1 : 0, cx.wq + 1);
+					if (li == 0)
 					{
+						// (later layers: these were issued right behind the previous layer's 1x1, see below)
 #pragma unroll
 						for (int ks = 0; ks < KS; ks++)
 						{
-							const u64 boff = (u64)(2 * ks * N1);
-							mma_ts<1>(tm + TC::XR, tm + TC::T0 + 8u * ks, dHi + boff, idN1);
-							mma_ts<1>(tm + TC::XR, tm + TC::T0 + C + 8u * ks, dHi + boff, idN1);
-							mma_ts<1>(tm + TC::XR, tm + TC::T0 + 8u * ks, dLo + boff, idN1);
+							const u64 boff = (u64)((2 * CG + 2 * ks) * C);
+							mma_ts<1>(tm + TC::D, tm + TC::XR + 8u * ks, dHi + boff, idC);
+							mma_ts<1>(tm + TC::D, tm + TC::XR + 8u * ks, dLo + boff, idC);
 						}
-						mma_ts<1>(tm + TC::XR, tm + kConst, desc_at(wb16 + L.oneC16, N1), idN1);
-						mma_commit(cx.barMma);
+						mma_ts<1>(tm + TC::D, tm + kConst, desc_at(wb16 + g4.y, C), idC);
 					}
-					__syncwarp();
+#pragma unroll
+					for (int ks = 0; ks < KS; ks++) mma_ts<1>(tm + TC::D, tm + TC::T2L + 8u * ks, dHi + (u64)((2 * CG + 2 * ks) * C), idC);
 				}
+				__syncwarp();
+				TS_STAMP(2);
+				issuer_sync(kBarT0);
+				TS_STAMP(3);
+				if (cx.el)
+				{
+#pragma unroll
+					for (int ks = 0; ks < KS; ks++)
+					{
+						const u64 boff = (u64)((2 * ks) * C);
+						mma_ts<1>(tm + TC::D, tm + TC::T0 + 8u * ks, dHi + boff, idC);
+						mma_ts<1>(tm + TC::D, tm + TC::T0 + C + 8u * ks, dHi + boff, idC);
+						mma_ts<1>(tm + TC::D, tm + TC::T0 + 8u * ks, dLo + boff, idC);
+					}
+				}
+				__syncwarp();
+				TS_STAMP(4);
+				issuer_sync(kBarT1);
+				TS_STAMP(5);
+				if (cx.el)
+				{
+#pragma unroll
+					for (int ks = 0; ks < KS; ks++)
+					{
+						const u64 boff = (u64)((CG + 2 * ks) * C);
+						mma_ts<1>(tm + TC::D, tm + TC::T1 + 8u * ks, dHi + boff, idC);
+						mma_ts<1>(tm + TC::D, tm + TC::T1 + C + 8u * ks, dHi + boff, idC);
+						mma_ts<1>(tm + TC::D, tm + TC::T1 + 8u * ks, dLo + boff, idC);
+					}
+					mma_commit(cx.barD);
+				}
+				__syncwarp();
+				TS_STAMP(6);
+				issuer_release(cx.barD, cx.dq & 1u, kBarDReady);
+				cx.dq++;
+				TS_STAMP(7);
+				// the next layer's weights are needed right behind the 1x1 (below); they were requested a whole layer ago
+				const bool more = li + 1 < numLayers;
+				if (more) mbar_wait(cx.barW0 + 8u * ((cx.wq + 1) & 1u), ((cx.wq + 1) >> 1) & 1u);
+
+				// ---- 1x1 + bias + residual, head sum (WaveNet.h:482-491): XR|HD += [Zhi|Zlo] [W1x1 | Whead] ----
+				issuer_sync(kBarZ);
+				TS_STAMP(8);
+				if (cx.el)
+				{
+					const u64 oHi = desc_at(wb16 + g4.z, N1), oLo = desc_at(wb16 + g4.w, N1);
+#pragma unroll
+					for (int ks = 0; ks < KS; ks++)
+					{
+						const u64 boff = (u64)(2 * ks * N1);
+						mma_ts<1>(tm + TC::XR, tm + TC::T0 + 8u * ks, oHi + boff, idN1);
+						mma_ts<1>(tm + TC::XR, tm + TC::T0 + C + 8u * ks, oHi + boff, idN1);
+						mma_ts<1>(tm + TC::XR, tm + TC::T0 + 8u * ks, oLo + boff, idN1);
+					}
+					mma_ts<1>(tm + TC::XR, tm + kConst, desc_at(wb16 + oneC16, N1), idN1);
+					mma_commit(cx.barX);
+					if (more)
+					{
+						// The next layer's undelayed tap reads the residual accumulator itself as its high part, so those products (and
+						// the constant-operand one) need nothing from the stagers: issue them right behind the 1x1, in pipeline order.
+						// D is zero again (the stagers cleared it before they delivered z).
+						const uint32_t nb16 = (cx.wbuf + ((cx.wq + 1) & 1u) * cx.wbufStride) >> 4;
+						const uint4 n4 = lds128(la + (uint32_t)sizeof(TsLayer) + 64);
+						const u64 nHi = desc_at(nb16, C), nLo = desc_at(nb16 + n4.x, C);
+#pragma unroll
+						for (int ks = 0; ks < KS; ks++)
+						{
+							const u64 boff = (u64)((2 * CG + 2 * ks) * C);
+							mma_ts<1>(tm + TC::D, tm + TC::XR + 8u * ks, nHi + boff, idC);
+							mma_ts<1>(tm + TC::D, tm + TC::XR + 8u * ks, nLo + boff, idC);
+						}
+						mma_ts<1>(tm + TC::D, tm + kConst, desc_at(nb16 + n4.y, C), idC);
+					}
+				}
+				__syncwarp();
+				TS_STAMP(9);
+				issuer_release(cx.barX, cx.xq & 1u, kBarXReady);
+				cx.xq++;
+				TS_STAMP(10);
 				cx.wq++;
 			}
 		}
 
 		constexpr int kTableBytes = kMaxLayers * (int)sizeof(TsLayer);
+		constexpr int kNumBars = 4;
 
 		__host__ __device__ constexpr size_t smem_fixed_bytes() { return (size_t)4 * kRows * 16 + (size_t)4 * kWbRows * 16; }
 
@@ -499,12 +664,13 @@ namespace nab200
 			cx.wbufStride = (uint32_t)M.maxBlock * 4u;
 			TsLayer* Ls = reinterpret_cast<TsLayer*>(smem + smem_fixed_bytes() + (size_t)2 * M.maxBlock * 4);
 			cx.Ls = Ls;
+			cx.lsAddr = smem_u32(Ls);
 			cx.hdb = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(Ls) + kTableBytes);
 			unsigned long long* bars = reinterpret_cast<unsigned long long*>(cx.hdb + 2 * kHdbHalf);
-			uint32_t* tmemSlot = reinterpret_cast<uint32_t*>(bars + 4);
-			cx.barWin = smem_u32(&bars[0]);
-			cx.barW0 = smem_u32(&bars[1]);
-			cx.barMma = smem_u32(&bars[3]);
+			uint32_t* tmemSlot = reinterpret_cast<uint32_t*>(bars + kNumBars);
+			cx.barW0 = smem_u32(&bars[0]);
+			cx.barD = smem_u32(&bars[2]);
+			cx.barX = smem_u32(&bars[3]);
 			cx.n = n;
 			cx.tid = threadIdx.x;
 			cx.warp = threadIdx.x >> 5;
@@ -512,10 +678,11 @@ namespace nab200
 			cx.S = S;
 			cx.gstride = gridDim.x;
 			cx.state = state;
-			cx.wq = 0; cx.winq = 0; cx.mmaq = 0; cx.cur = 0;
+			cx.wq = 0; cx.dq = 0; cx.xq = 0; cx.cur = 0;
 			cx.el = elect_one();
 			const int tid = threadIdx.x;
 			const int warp = cx.warp, lane = cx.lane;
+			const bool stager = warp < 4;
 
 			// per-layer plan
 			if (tid < M.numLayers)
@@ -534,18 +701,22 @@ namespace nab200
 				T.convLo16 = (uint32_t)W.oConvLo >> 2; T.convC16 = (uint32_t)W.oConvB >> 2;
 				T.oneHi16 = (uint32_t)W.oOneW >> 2; T.oneLo16 = (uint32_t)W.oOneLo >> 2; T.oneC16 = (uint32_t)W.oOneB >> 2;
 				T.C = C;
+				// job 0 <-> tap 0's window; job 1 <-> tap 1's own window (only when tap 0 is pure history: otherwise tap 0's mixed
+				// window already covers the rows tap 1 reads)
+				T.cpCnt0 = pure0 ? -1 : D0; T.cpD0 = D0; T.cpOff0 = T.tap0Off; T.cpStride0 = T.tap0Stride;
+				T.cpCnt1 = !pure0 ? 0 : (pure1 ? -1 : D1); T.cpD1 = D1; T.cpOff1 = T.tap1Off; T.cpStride1 = T.tap1Stride;
 				T.pad[0] = T.pad[1] = T.pad[2] = 0;
 				Ls[tid] = T;
 			}
 			if (tid == 0)
 			{
-				mbar_init(cx.barWin, 1);
 				mbar_init(cx.barW0, 1);
 				mbar_init(cx.barW0 + 8u, 1);
-				mbar_init(cx.barMma, 1);
+				mbar_init(cx.barD, 1);
+				mbar_init(cx.barX, 1);
 				asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 			}
-			if (warp == 0)
+			if (warp == 4)
 			{
 				asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(smem_u32(tmemSlot)) : "memory");
 				asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -565,93 +736,48 @@ namespace nab200
 			fence_after();
 			cx.tmem = *tmemSlot;
 			const uint32_t tm = cx.tmem;
-			const uint32_t lanebase = tm + ((uint32_t)(warp * 32) << 16);
 			const int first0 = M.arrays[0].firstLayer, num0 = M.arrays[0].numLayers;
 			const int first1 = M.arrays[1].firstLayer, num1 = M.arrays[1].numLayers;
-			// entry / transition operands sit in the first block of each array (na_device.h, tc == 2), 16-byte units
-			const uint32_t re0 = (uint32_t)M.layers[first0].oRe >> 2, hd0 = (uint32_t)M.layers[first0].oHeadB >> 2;
-			const uint32_t re1 = (uint32_t)M.layers[first1].oRe >> 2, re1Lo = (uint32_t)M.layers[first1].oMix >> 2;
-			const uint32_t ch1 = (uint32_t)M.layers[first1].oHeadW >> 2, hd1 = (uint32_t)M.layers[first1].oHeadB >> 2;
 
-			if (tid == 96) issue_weights(cx, 0, 0);
-			if (warp == 3 && s0 < S) issue_windows(cx, 0, s0, cx.hdb, lane);
-			float cond = 0.0f;
-			if (tid < n && s0 < S) cond = in[(long long)s0 * inSS + (long long)tid * inFS];
-
-			for (int s = s0; s < S; s += gridDim.x)
+			if (!stager)
 			{
-				const int sn = s + gridDim.x;
-				int* hdNext = cx.hdb + (cx.cur ^ 1) * kHdbHalf;
-				float condNext = 0.0f;
-				if (sn < S)
+				// =================================== issuer warp ===================================
+				// entry / transition operands sit in the first block of each array (na_device.h, tc == 2), 16-byte units
+				const uint32_t re0 = (uint32_t)M.layers[first0].oRe >> 2, hd0 = (uint32_t)M.layers[first0].oHeadB >> 2;
+				const uint32_t re1 = (uint32_t)M.layers[first1].oRe >> 2, re1Lo = (uint32_t)M.layers[first1].oMix >> 2;
+				const uint32_t ch1 = (uint32_t)M.layers[first1].oHeadW >> 2, hd1 = (uint32_t)M.layers[first1].oHeadB >> 2;
+				if (cx.el) issue_weights(cx, 0, 0);
+				for (int s = s0; s < S; s += gridDim.x)
 				{
-					if (tid < M.numRings)
+#ifdef NAB_TS_TIMING
 					{
-						const int Lp = M.ringLp[tid];
-						const int h = heads[(size_t)sn * M.numRings + tid];
-						int hn = h + (n % Lp);
-						if (hn >= Lp) hn -= Lp;
-						hdNext[tid] = h;
-						hdNext[36 + tid] = hn;
+						const int k = (s - s0) / (int)gridDim.x;
+						const int c = blockIdx.x == 0 ? 0 : blockIdx.x == 1 ? 1 : blockIdx.x == 300 ? 2 : blockIdx.x == gridDim.x - 1 ? 3 : -1;
+						cx.stampOn = lane == 0 && c >= 0 && k >= 1 && k < 5;
+						cx.stampCta = c < 0 ? 0 : c; cx.stampStream = k - 1;
 					}
-					if (tid < n) condNext = in[(long long)sn * inSS + (long long)tid * inFS];
-				}
-
-				// ---- entry: constant operand, zero conv accumulator, rechannel 1 -> C0 and head bias on the tensor core ----
-				{
-					uint32_t cv[8];
-					uint32_t cl, dummy;
-					split_lo2(__float_as_uint(cond), 0u, cl, dummy);
-					cv[0] = __float_as_uint(cond); cv[1] = cl; cv[2] = cv[0];
-					cv[3] = 0x3F800000u; cv[4] = 0x3F800000u; cv[5] = 0x3F800000u; cv[6] = 0u; cv[7] = 0u;
-					tmem_st<8>(lanebase + kConst, cv);
-					tmem_zero<16>(lanebase + Cols<0>::D);
-				}
-				wait_st();
-				fence_before();
-				__syncthreads();
-				fence_after();
-				if (warp == 0)
-				{
+#endif
+					// ---- entry: rechannel 1 -> C0 and head bias from the constant operand ----
 					mbar_wait(cx.barW0 + 8u * (cx.wq & 1u), (cx.wq >> 1) & 1u);
-					const uint32_t wb16 = (cx.wbuf + (cx.wq & 1u) * cx.wbufStride) >> 4;
+					issuer_sync(kBarE);
 					if (cx.el)
 					{
+						const uint32_t wb16 = (cx.wbuf + (cx.wq & 1u) * cx.wbufStride) >> 4;
 						mma_ts<0>(tm + Cols<0>::XR, tm + kConst, desc_at(wb16 + re0, 16), idesc_of(16));
 						mma_ts<0>(tm + Cols<0>::HD, tm + kConst, desc_at(wb16 + hd0, 8), idesc_of(8));
-						mma_commit(cx.barMma);
+						mma_commit(cx.barX);
 					}
 					__syncwarp();
-				}
-				run_array<0>(cx, first0, num0, s);
+					issuer_release(cx.barX, cx.xq & 1u, kBarXReady);
+					cx.xq++;
+					issue_array<0>(cx, first0, num0, s);
 
-				// ---- array transition (WaveNet.h:785-789): rechannel C0 -> C1 of the array output, head carry ----
-				mbar_wait(cx.barMma, cx.mmaq & 1u);
-				cx.mmaq++;
-				fence_after();
-				{
-					uint32_t x[16], xl[16];
-					tmem_ld<16>(lanebase + Cols<0>::XR, x);
-#pragma unroll
-					for (int c = 0; c < 16; c += 2) split_lo2(x[c], x[c + 1], xl[c], xl[c + 1]);
-					tmem_st<16>(lanebase + Cols<0>::T2L, xl);
-					uint32_t h[8], hl[8];
-					tmem_ld<8>(lanebase + Cols<0>::HD, h);
-#pragma unroll
-					for (int c = 0; c < 8; c += 2) split_lo2(h[c], h[c + 1], hl[c], hl[c + 1]);
-					tmem_st<8>(lanebase + kHdLo, hl);
-					tmem_zero<8>(lanebase + Cols<1>::D);
-				}
-				wait_st();
-				fence_before();
-				__syncthreads();
-				fence_after();
-				if (warp == 0)
-				{
+					// ---- array transition (WaveNet.h:785-789): rechannel C0 -> C1 of the array output, head carry ----
 					mbar_wait(cx.barW0 + 8u * (cx.wq & 1u), (cx.wq >> 1) & 1u);
-					const uint32_t wb16 = (cx.wbuf + (cx.wq & 1u) * cx.wbufStride) >> 4;
+					issuer_sync(kBarE);
 					if (cx.el)
 					{
+						const uint32_t wb16 = (cx.wbuf + (cx.wq & 1u) * cx.wbufStride) >> 4;
 						const u64 dHi = desc_at(wb16 + re1, 8), dLo = desc_at(wb16 + re1Lo, 8);
 						mma_ts<0>(tm + Cols<1>::XR, tm + Cols<0>::XR, dHi, idesc_of(8));
 						mma_ts<1>(tm + Cols<1>::XR, tm + Cols<0>::T2L, dHi, idesc_of(8));
@@ -664,33 +790,99 @@ namespace nab200
 						mma_ts<1>(tm + Cols<1>::HD, tm + kHdLo, cHi, idesc_of(8));
 						mma_ts<1>(tm + Cols<1>::HD, tm + Cols<0>::HD, cLo, idesc_of(8));
 						mma_ts<1>(tm + Cols<1>::HD, tm + kConst, desc_at(wb16 + hd1, 8), idesc_of(8));
-						mma_commit(cx.barMma);
+						mma_commit(cx.barX);
 					}
 					__syncwarp();
+					issuer_release(cx.barX, cx.xq & 1u, kBarXReady);
+					cx.xq++;
+					issue_array<1>(cx, first1, num1, s);
+					cx.cur ^= 1;
 				}
-				run_array<1>(cx, first1, num1, s);
-
-				// ---- output (WaveNet.h:793-798) ----
-				mbar_wait(cx.barMma, cx.mmaq & 1u);
-				cx.mmaq++;
-				fence_after();
+				// drain the weight prefetch that ran ahead of the last layer
+				mbar_wait(cx.barW0 + 8u * (cx.wq & 1u), (cx.wq >> 1) & 1u);
+			}
+			else
+			{
+				// =================================== stager warps ===================================
+				const uint32_t lanebase = tm + ((uint32_t)(warp * 32) << 16);
+				float cond = 0.0f;
+				if (tid < n && s0 < S) cond = in[(long long)s0 * inSS + (long long)tid * inFS];
+				if (s0 < S) prefetch_windows<4>(cx, 0, s0, cx.hdb);
+				for (int s = s0; s < S; s += gridDim.x)
 				{
-					uint32_t h[8];
-					tmem_ld<8>(lanebase + Cols<1>::HD, h);
-					if (tid < n) out[(long long)s * outSS + (long long)tid * outFS] = M.headScale * __uint_as_float(h[0]);
+					const int sn = s + gridDim.x;
+					int* hdNext = cx.hdb + (cx.cur ^ 1) * kHdbHalf;
+					float condNext = 0.0f;
+					if (sn < S)
+					{
+						if (tid < M.numRings)
+						{
+							const int Lp = M.ringLp[tid];
+							const int h = heads[(size_t)sn * M.numRings + tid];
+							int hn = h + (n % Lp);
+							if (hn >= Lp) hn -= Lp;
+							hdNext[tid] = h;
+							hdNext[36 + tid] = hn;
+						}
+						if (tid < n) condNext = in[(long long)sn * inSS + (long long)tid * inFS];
+					}
+#ifdef NAB_TS_TIMING
+					{
+						const int k = (s - s0) / (int)gridDim.x;
+						const int c = blockIdx.x == 0 ? 0 : blockIdx.x == 1 ? 1 : blockIdx.x == 300 ? 2 : blockIdx.x == gridDim.x - 1 ? 3 : -1;
+						cx.stampOn = lane == 0 && c >= 0 && k >= 1 && k < 5;
+						cx.stampCta = c < 0 ? 0 : c; cx.stampStream = k - 1;
+					}
+#endif
+					// ---- entry: constant operand [cond, cond_lo, cond, 1, 1, 1, 0, 0], zero conv accumulator ----
+					{
+						uint32_t cv[8];
+						uint32_t cl, dummy;
+						split_lo2(__float_as_uint(cond), 0u, cl, dummy);
+						cv[0] = __float_as_uint(cond); cv[1] = cl; cv[2] = cv[0];
+						cv[3] = 0x3F800000u; cv[4] = 0x3F800000u; cv[5] = 0x3F800000u; cv[6] = 0u; cv[7] = 0u;
+						tmem_st<8>(lanebase + kConst, cv);
+						tmem_zero<16>(lanebase + Cols<0>::D);
+					}
+					stager_arrive(kBarE);
+					stage_array<0>(cx, first0, num0, s);
+
+					// ---- array transition: low parts of the array output and of the head output, zero the next accumulator ----
+					stager_wait(kBarXReady);
+					{
+						uint32_t x[16], xl[16];
+						tmem_ld<16>(lanebase + Cols<0>::XR, x);
+#pragma unroll
+						for (int c = 0; c < 16; c += 2) split_lo2(x[c], x[c + 1], xl[c], xl[c + 1]);
+						tmem_st<16>(lanebase + Cols<0>::T2L, xl);
+						uint32_t h[8], hl[8];
+						tmem_ld<8>(lanebase + Cols<0>::HD, h);
+#pragma unroll
+						for (int c = 0; c < 8; c += 2) split_lo2(h[c], h[c + 1], hl[c], hl[c + 1]);
+						tmem_st<8>(lanebase + kHdLo, hl);
+						tmem_zero<8>(lanebase + Cols<1>::D);
+					}
+					stager_arrive(kBarE);
+					stage_array<1>(cx, first1, num1, s);
+
+					// ---- output (WaveNet.h:793-798) ----
+					stager_wait(kBarXReady);
+					{
+						uint32_t h[8];
+						tmem_ld<8>(lanebase + Cols<1>::HD, h);
+						if (tid < n) out[(long long)s * outSS + (long long)tid * outFS] = M.headScale * __uint_as_float(h[0]);
+					}
+					if (tid < M.numRings) heads[(size_t)s * M.numRings + tid] = cx.hdb[cx.cur * kHdbHalf + 36 + tid];
+					cx.cur ^= 1;
+					cond = condNext;
+					// a thread's TMEM reads above complete before its own stores of the next stream's entry; hdb slots are
+					// rewritten two streams later, after many hand-offs
 				}
-				if (tid < M.numRings) heads[(size_t)s * M.numRings + tid] = cx.hdb[cx.cur * kHdbHalf + 36 + tid];
-				cx.cur ^= 1;
-				cond = condNext;
-				// the entry barrier of the next stream orders these TMEM / hdb reads before they are overwritten
-				fence_before();
 			}
 
-			// drain the weight prefetch that ran ahead of the last layer, then release TMEM
-			mbar_wait(cx.barW0 + 8u * (cx.wq & 1u), (cx.wq >> 1) & 1u);
 			fence_before();
 			__syncthreads();
-			if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(cx.tmem) : "memory");
+			if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(cx.tmem) : "memory");
 		}
 	}
 
@@ -704,7 +896,7 @@ namespace nab200
 		if (!wavenet_ts_variant_supported(M.arrays[0].C, M.numArrays > 1 ? M.arrays[1].C : 0, M.arrays[0].act)) return cudaErrorNotSupported;
 		if (a.n > ts::kCur) return cudaErrorInvalidValue;
 		auto kfn = ts::wavenet_ts_kernel;
-		const size_t smem = ts::smem_fixed_bytes() + (size_t)2 * M.maxBlock * 4 + ts::kTableBytes + 2 * ts::kHdbHalf * 4 + 4 * 8 + 16;
+		const size_t smem = ts::smem_fixed_bytes() + (size_t)2 * M.maxBlock * 4 + ts::kTableBytes + 2 * ts::kHdbHalf * 4 + ts::kNumBars * 8 + 16;
 		cudaError_t err = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 		if (err != cudaSuccess) return err;
 		int grid = a.numSMs * 4;
