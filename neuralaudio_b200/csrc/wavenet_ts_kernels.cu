@@ -289,7 +289,8 @@ namespace nab200
 			kBarT1 = 5,       // stagers -> issuer: tap 1 staged
 			kBarZ = 6,        // stagers -> issuer: activated output staged
 			kBarDReady = 7,   // issuer -> stagers: conv accumulator complete
-			kBarXReady = 8    // issuer -> stagers: residual / head accumulators complete
+			kBarXReady = 8,   // issuer -> stagers: residual / head accumulators complete
+			kBarZ0 = 9        // stagers -> issuer: first K-step of the activated output staged (16-channel arrays)
 		};
 		__device__ __forceinline__ void nbar_arrive(int id) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(kThreads) : "memory"); }
 		__device__ __forceinline__ void nbar_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(kThreads) : "memory"); }
@@ -368,15 +369,26 @@ namespace nab200
 		// warp's copies are one contiguous 512-byte run per channel group); one cp.async group per layer.
 		// The windows are tens of small strided runs per layer: per-thread LDGSTS moves them with ~10 instructions per
 		// thread, where one TMA bulk copy per run cost the issuing warp ~1000 cycles per layer (tools/ts_timing.cu).
-		template <int CG>
+		__device__ __forceinline__ void l2_prefetch(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+		// MODE 0: the copies described above.  MODE 1: only pull the same rows into L2 (one hint per 128-byte line, i.e. every
+		// 8th thread), issued one layer earlier still, so that the MODE 0 copies hit L2 instead of HBM - that keeps a whole
+		// layer of HBM latency off the per-stream dependency chain without double-buffering the shared-memory windows.
+		template <int CG, int MODE>
 		__device__ __forceinline__ void prefetch_windows(const Ctx& cx, int l, int s, const int* hd)
 		{
+#ifdef NAB_TS_NO_PREFETCH
+			return;   // timing experiment only (tools/ts_timing.cu): results are wrong
+#endif
+			const int u = cx.tid;
+			if (MODE == 1 && (u & 7) != 0) return;
 			const uint32_t la = cx.lsAddr + (uint32_t)l * (uint32_t)sizeof(TsLayer);
 			const uint4 g1 = lds128(la + 16), j0 = lds128(la + 32), j1 = lds128(la + 48);
 			const int Lp = (int)g1.y;
 			const int head = hd[g1.w];
-			const uint4* ring = reinterpret_cast<const uint4*>(cx.state + (size_t)s * cx.M->stateStride + (int)g1.z);
-			const int u = cx.tid;
+			// 16-byte units from the stream's state base: one 64-bit multiply-add per copy
+			const uint4* base = reinterpret_cast<const uint4*>(cx.state + (size_t)s * cx.M->stateStride);
+			const int ring16 = (int)g1.z >> 2;
 			const uint32_t dstRow = cx.xe + (uint32_t)u * 16u;
 			{
 				const int cnt = (int)j0.x < 0 ? cx.n : (int)j0.x;
@@ -384,9 +396,13 @@ namespace nab200
 				{
 					int idx = head - (int)j0.y + u;
 					if (idx < 0) idx += Lp;
-					const uint4* src = ring + idx;
+					idx += ring16;
 #pragma unroll
-					for (int g = 0; g < CG; g++) cp_async16(dstRow + j0.z + (uint32_t)g * j0.w, src + (size_t)g * Lp);
+					for (int g = 0; g < CG; g++)
+					{
+						if (MODE == 0) cp_async16(dstRow + j0.z + (uint32_t)g * j0.w, base + (idx + g * Lp));
+						else l2_prefetch(base + (idx + g * Lp));
+					}
 				}
 			}
 			{
@@ -395,12 +411,33 @@ namespace nab200
 				{
 					int idx = head - (int)j1.y + u;
 					if (idx < 0) idx += Lp;
-					const uint4* src = ring + idx;
+					idx += ring16;
 #pragma unroll
-					for (int g = 0; g < CG; g++) cp_async16(dstRow + j1.z + (uint32_t)g * j1.w, src + (size_t)g * Lp);
+					for (int g = 0; g < CG; g++)
+					{
+						if (MODE == 0) cp_async16(dstRow + j1.z + (uint32_t)g * j1.w, base + (idx + g * Lp));
+						else l2_prefetch(base + (idx + g * Lp));
+					}
 				}
 			}
-			asm volatile("cp.async.commit_group;" ::: "memory");
+			if (MODE == 0) asm volatile("cp.async.commit_group;" ::: "memory");
+		}
+
+		// history of layer `l` counted from the first layer of stream s (l may run past the last layer: next stream)
+		template <int MODE>
+		__device__ __forceinline__ void prefetch_layer(const Ctx& cx, int l, int s, int array1First)
+		{
+			const int numLayers = cx.M->numLayers;
+			const int* hd = cx.hdb + cx.cur * kHdbHalf;
+			if (l >= numLayers)
+			{
+				l -= numLayers;
+				s += cx.gstride;
+				hd = cx.hdb + (cx.cur ^ 1) * kHdbHalf;
+				if (s >= cx.S) { if (MODE == 0) asm volatile("cp.async.commit_group;" ::: "memory"); return; }
+			}
+			if (l < array1First) prefetch_windows<4, MODE>(cx, l, s, hd);
+			else prefetch_windows<2, MODE>(cx, l, s, hd);
 		}
 
 		// this thread's row of one delayed tap: shared memory -> [hi | lo] -> TMEM
@@ -421,7 +458,7 @@ namespace nab200
 
 		// ---- stager warps: one layer array of the CTA's stream ------------------------------------------------------
 		template <int ARRAY>
-		__device__ __forceinline__ void stage_array(Ctx& cx, const int firstLayer, const int numLayers, int s)
+		__device__ __forceinline__ void stage_array(Ctx& cx, const int firstLayer, const int numLayers, int s, const int array1First)
 		{
 			typedef Cols<ARRAY> TC;
 			constexpr int C = TC::C, CG = C / 4;
@@ -478,40 +515,58 @@ namespace nab200
 				{
 					const int Lp = (int)g1.y;
 					const int first = cx.n > Lp ? cx.n - Lp : 0;
+#ifndef NAB_TS_NO_RINGWRITE   // (timing experiment only)
 					if (tid < cx.n && tid >= first)
+#else
+					if (false)
+#endif
 					{
 						// (head + t) mod Lp without a division: head + first is hdb's "head after the call" when n > Lp
 						int idx = (cx.n > Lp ? hd[36 + g1.w] : hd[g1.w]) + (tid - first);
 						if (idx >= Lp) idx -= Lp;
-						uint4* ring = reinterpret_cast<uint4*>(st + (int)g1.z) + idx;
+						idx += (int)g1.z >> 2;
+						uint4* base = reinterpret_cast<uint4*>(st);
 #pragma unroll
-						for (int q = 0; q < CG; q++) ring[(size_t)q * Lp] = make_uint4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
+						for (int q = 0; q < CG; q++) base[idx + q * Lp] = make_uint4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
 					}
 				}
 
 				// ---- activation (WaveNet.h:477-480); z -> TMEM as the A operand of the 1x1 ----
 				stager_wait(kBarDReady);
 				TS_STAMP(7);
-				// every stager has staged both taps (the conv could not complete otherwise): the shared-memory windows are free,
-				// prefetch the next layer's (or the next stream's first layer's) history
-				if (l + 1 < M.numLayers)
 				{
-					if (ARRAY == 0 && li + 1 < numLayers) prefetch_windows<4>(cx, l + 1, s, hd);
-					else prefetch_windows<2>(cx, l + 1, s, hd);
-				}
-				else if (s + cx.gstride < cx.S) prefetch_windows<4>(cx, 0, s + cx.gstride, cx.hdb + (cx.cur ^ 1) * kHdbHalf);
-				{
-					uint32_t z[2 * C];
+					uint32_t dv[C];
+					// accumulator load in flight while the next layer's history prefetch is issued
+					if constexpr (C == 16)
+						asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+									 : "=r"(dv[0]), "=r"(dv[1]), "=r"(dv[2]), "=r"(dv[3]), "=r"(dv[4]), "=r"(dv[5]), "=r"(dv[6]), "=r"(dv[7]), "=r"(dv[8]),
+									   "=r"(dv[9]), "=r"(dv[10]), "=r"(dv[11]), "=r"(dv[12]), "=r"(dv[13]), "=r"(dv[14]), "=r"(dv[15])
+									 : "r"(lanebase + TC::D));
+					else
+						asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+									 : "=r"(dv[0]), "=r"(dv[1]), "=r"(dv[2]), "=r"(dv[3]), "=r"(dv[4]), "=r"(dv[5]), "=r"(dv[6]), "=r"(dv[7])
+									 : "r"(lanebase + TC::D));
+					// Every stager has staged both taps (the conv could not complete otherwise), so the shared-memory windows are free:
+					// copy the next layer's (or the next stream's first layer's) history while the accumulator load is in flight.
+					// (Tried: an L2 hint two layers ahead plus this copy after the hand-off below - no gain, the kernel is bound
+					// by issue slots under contention, not by this latency; tools/ts_timing.cu.)
+					prefetch_layer<0>(cx, l + 1, s, array1First);
+					wait_ld();
+					tmem_zero<C>(lanebase + TC::D);   // every conv MMA accumulates; the accumulator starts each layer at zero
+					// z is the 1x1's A operand [hi | lo]; it is delivered in K-steps of 8 channels so that the issuer starts on the
+					// first while the second is still being activated
+#pragma unroll
+					for (int h = 0; h < C / 8; h++)
 					{
-						uint32_t dv[C];
-						tmem_ld<C>(lanebase + TC::D, dv);
-						tmem_zero<C>(lanebase + TC::D);   // every conv MMA accumulates; the accumulator starts each layer at zero
+						uint32_t z[8], zl[8];
 #pragma unroll
-						for (int c = 0; c < C; c += 2) fast_tanh2(dv[c], dv[c + 1], z[c], z[c + 1]);
+						for (int c = 0; c < 8; c += 2) fast_tanh2(dv[8 * h + c], dv[8 * h + c + 1], z[c], z[c + 1]);
+#pragma unroll
+						for (int c = 0; c < 8; c += 2) split_lo2(z[c], z[c + 1], zl[c], zl[c + 1]);
+						tmem_st<8>(lanebase + TC::T0 + 8u * h, z);
+						tmem_st<8>(lanebase + TC::T0 + C + 8u * h, zl);
+						if (h + 1 < C / 8) stager_arrive(kBarZ0);
 					}
-#pragma unroll
-					for (int c = 0; c < C; c += 2) split_lo2(z[c], z[c + 1], z[C + c], z[C + c + 1]);
-					tmem_st<2 * C>(lanebase + TC::T0, z);
 				}
 				stager_arrive(kBarZ);
 				TS_STAMP(8);
@@ -546,8 +601,6 @@ namespace nab200
 				TS_STAMP(1);
 				if (cx.el)
 				{
-					// the stagers have seen the previous layer complete: the other weight buffer is free
-					issue_weights(cx, (l + 1 < M.numLayers) ? l + 1 : 0, cx.wq + 1);
 					if (li == 0)
 					{
 						// (later layers: these were issued right behind the previous layer's 1x1, see below)
@@ -598,49 +651,53 @@ namespace nab200
 				TS_STAMP(6);
 				issuer_release(cx.barD, cx.dq & 1u, kBarDReady);
 				cx.dq++;
+				// the stagers saw the previous layer complete long ago: the other weight buffer is free for the next block
+				if (cx.el) issue_weights(cx, (l + 1 < M.numLayers) ? l + 1 : 0, cx.wq + 1);
+				__syncwarp();
 				TS_STAMP(7);
 				// the next layer's weights are needed right behind the 1x1 (below); they were requested a whole layer ago
 				const bool more = li + 1 < numLayers;
 				if (more) mbar_wait(cx.barW0 + 8u * ((cx.wq + 1) & 1u), ((cx.wq + 1) >> 1) & 1u);
 
-				// ---- 1x1 + bias + residual, head sum (WaveNet.h:482-491): XR|HD += [Zhi|Zlo] [W1x1 | Whead] ----
-				issuer_sync(kBarZ);
-				TS_STAMP(8);
-				if (cx.el)
-				{
-					const u64 oHi = desc_at(wb16 + g4.z, N1), oLo = desc_at(wb16 + g4.w, N1);
+				// ---- 1x1 + bias + residual, head sum (WaveNet.h:482-491): XR|HD += [Zhi|Zlo] [W1x1 | Whead], per K-step as z arrives ----
+				const u64 oHi = desc_at(wb16 + g4.z, N1), oLo = desc_at(wb16 + g4.w, N1);
 #pragma unroll
-					for (int ks = 0; ks < KS; ks++)
+				for (int ks = 0; ks < KS; ks++)
+				{
+					issuer_sync(ks + 1 < KS ? kBarZ0 : kBarZ);
+					if (ks == 0) TS_STAMP(8);
+					if (cx.el)
 					{
 						const u64 boff = (u64)(2 * ks * N1);
+						if (ks == 0) mma_ts<1>(tm + TC::XR, tm + kConst, desc_at(wb16 + oneC16, N1), idN1);
 						mma_ts<1>(tm + TC::XR, tm + TC::T0 + 8u * ks, oHi + boff, idN1);
 						mma_ts<1>(tm + TC::XR, tm + TC::T0 + C + 8u * ks, oHi + boff, idN1);
 						mma_ts<1>(tm + TC::XR, tm + TC::T0 + 8u * ks, oLo + boff, idN1);
+						if (ks + 1 == KS) mma_commit(cx.barX);
 					}
-					mma_ts<1>(tm + TC::XR, tm + kConst, desc_at(wb16 + oneC16, N1), idN1);
-					mma_commit(cx.barX);
-					if (more)
-					{
-						// The next layer's undelayed tap reads the residual accumulator itself as its high part, so those products (and
-						// the constant-operand one) need nothing from the stagers: issue them right behind the 1x1, in pipeline order.
-						// D is zero again (the stagers cleared it before they delivered z).
-						const uint32_t nb16 = (cx.wbuf + ((cx.wq + 1) & 1u) * cx.wbufStride) >> 4;
-						const uint4 n4 = lds128(la + (uint32_t)sizeof(TsLayer) + 64);
-						const u64 nHi = desc_at(nb16, C), nLo = desc_at(nb16 + n4.x, C);
-#pragma unroll
-						for (int ks = 0; ks < KS; ks++)
-						{
-							const u64 boff = (u64)((2 * CG + 2 * ks) * C);
-							mma_ts<1>(tm + TC::D, tm + TC::XR + 8u * ks, nHi + boff, idC);
-							mma_ts<1>(tm + TC::D, tm + TC::XR + 8u * ks, nLo + boff, idC);
-						}
-						mma_ts<1>(tm + TC::D, tm + kConst, desc_at(nb16 + n4.y, C), idC);
-					}
+					__syncwarp();
 				}
-				__syncwarp();
 				TS_STAMP(9);
 				issuer_release(cx.barX, cx.xq & 1u, kBarXReady);
 				cx.xq++;
+				if (more && cx.el)
+				{
+					// The next layer's undelayed tap reads the residual accumulator itself as its high part, so those products (and
+					// the constant-operand one) need nothing from the stagers: issue them while the stagers wake up.  D is zero again
+					// (the stagers cleared it before they delivered z).
+					const uint32_t nb16 = (cx.wbuf + ((cx.wq + 1) & 1u) * cx.wbufStride) >> 4;
+					const uint4 n4 = lds128(la + (uint32_t)sizeof(TsLayer) + 64);
+					const u64 nHi = desc_at(nb16, C), nLo = desc_at(nb16 + n4.x, C);
+#pragma unroll
+					for (int ks = 0; ks < KS; ks++)
+					{
+						const u64 boff = (u64)((2 * CG + 2 * ks) * C);
+						mma_ts<1>(tm + TC::D, tm + TC::XR + 8u * ks, nHi + boff, idC);
+						mma_ts<1>(tm + TC::D, tm + TC::XR + 8u * ks, nLo + boff, idC);
+					}
+					mma_ts<1>(tm + TC::D, tm + kConst, desc_at(nb16 + n4.y, C), idC);
+				}
+				__syncwarp();
 				TS_STAMP(10);
 				cx.wq++;
 			}
@@ -807,7 +864,10 @@ namespace nab200
 				const uint32_t lanebase = tm + ((uint32_t)(warp * 32) << 16);
 				float cond = 0.0f;
 				if (tid < n && s0 < S) cond = in[(long long)s0 * inSS + (long long)tid * inFS];
-				if (s0 < S) prefetch_windows<4>(cx, 0, s0, cx.hdb);
+				if (s0 < S)
+				{
+					prefetch_windows<4, 0>(cx, 0, s0, cx.hdb);
+				}
 				for (int s = s0; s < S; s += gridDim.x)
 				{
 					const int sn = s + gridDim.x;
@@ -845,7 +905,7 @@ namespace nab200
 						tmem_zero<16>(lanebase + Cols<0>::D);
 					}
 					stager_arrive(kBarE);
-					stage_array<0>(cx, first0, num0, s);
+					stage_array<0>(cx, first0, num0, s, first1);
 
 					// ---- array transition: low parts of the array output and of the head output, zero the next accumulator ----
 					stager_wait(kBarXReady);
@@ -863,7 +923,7 @@ namespace nab200
 						tmem_zero<8>(lanebase + Cols<1>::D);
 					}
 					stager_arrive(kBarE);
-					stage_array<1>(cx, first1, num1, s);
+					stage_array<1>(cx, first1, num1, s, first1);
 
 					// ---- output (WaveNet.h:793-798) ----
 					stager_wait(kBarXReady);

@@ -25,10 +25,12 @@ int main(int argc, char** argv)
 	srand(1);
 	for (size_t i = 0; i < nw; i++) desc.weights.push_back(0.2f * ((float)rand() / RAND_MAX - 0.5f));
 	PackedWaveNet P = PackWaveNetTs(desc);
-	const WnModelDev& M = P.dev;
+	WnModelDev M = P.dev;
+	const bool alias = argc > 2 && atoi(argv[2]) == 1;   // all streams share stream 0's state: L2-resident, for timing only
 	float *dW, *dState, *dIn, *dOut; int* dHeads;
 	cudaMalloc(&dW, P.weights.size() * 4); cudaMemcpy(dW, P.weights.data(), P.weights.size() * 4, cudaMemcpyHostToDevice);
 	cudaMalloc(&dState, (size_t)S * M.stateStride * 4); cudaMemset(dState, 0, (size_t)S * M.stateStride * 4);
+	if (alias) M.stateStride = 0;
 	cudaMalloc(&dHeads, (size_t)S * M.numRings * 4); cudaMemset(dHeads, 0, (size_t)S * M.numRings * 4);
 	cudaMalloc(&dIn, (size_t)S * n * 4); cudaMalloc(&dOut, (size_t)S * n * 4);
 	std::vector<float> hin((size_t)S * n);
