@@ -111,6 +111,15 @@ inline namespace b200
 			(void)input; (void)output; (void)numStreams; (void)numFrames; (void)layout;
 			return false;
 		}
+		// Pipelined form for page-locked host buffers: queues copy-in, kernels and copy-out and returns; consecutive calls
+		// overlap their transfers with each other's kernels (two calls in flight).  Buffers must stay untouched until
+		// WaitBatches(lag) reports at most `lag` calls in flight, or Synchronize().
+		virtual bool ProcessBatchAsync(const float* input, float* output, size_t numStreams, size_t numFrames, EBatchLayout layout = StreamMajor)
+		{
+			(void)input; (void)output; (void)numStreams; (void)numFrames; (void)layout;
+			return false;
+		}
+		virtual bool WaitBatches(int lag) { (void)lag; return false; }
 		virtual bool Synchronize() { return false; }
 		virtual void* GetCudaStream() { return nullptr; }
 		virtual int GetDevice() { return -1; }

@@ -90,6 +90,11 @@ NA_EXTERN int NA_GetDevice(NeuralModel* model);
  * Host pointers: staged through pinned memory, returns when `output` is complete.
  * Device pointers: used in place, asynchronous on the model's CUDA stream (NA_Synchronize to wait). */
 NA_EXTERN int NA_ProcessBatch(NeuralModel* model, const float* input, float* output, size_t numStreams, size_t numFrames, int layout);
+/* Pipelined form for page-locked host buffers: queues copy-in, kernels and copy-out on three CUDA streams and returns.
+ * Two calls can be in flight, so the transfers of one call overlap the kernels of its neighbours.  Buffers must stay
+ * untouched until NA_WaitBatches(model, lag) has returned with lag < (calls queued since), or NA_Synchronize. */
+NA_EXTERN int NA_ProcessBatchAsync(NeuralModel* model, const float* input, float* output, size_t numStreams, size_t numFrames, int layout);
+NA_EXTERN int NA_WaitBatches(NeuralModel* model, int lag);   /* wait until at most `lag` queued calls are still in flight */
 NA_EXTERN int NA_Synchronize(NeuralModel* model);
 NA_EXTERN void* NA_GetCudaStream(NeuralModel* model);    /* the cudaStream_t ProcessBatch launches on (as void*) */
 

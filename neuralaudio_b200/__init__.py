@@ -100,6 +100,8 @@ def load_library():
         "NA_GetStateBytesPerStream": (sz, [vp]),
         "NA_GetDevice": (ci, [vp]),
         "NA_ProcessBatch": (ci, [vp, vp, vp, sz, sz, ci]),
+        "NA_ProcessBatchAsync": (ci, [vp, vp, vp, sz, sz, ci]),
+        "NA_WaitBatches": (ci, [vp, ci]),
         "NA_Synchronize": (ci, [vp]),
         "NA_GetCudaStream": (vp, [vp]),
         "NA_GetDeviceBlob": (ci, [vp, ctypes.POINTER(vp), ctypes.POINTER(sz)]),
@@ -318,6 +320,20 @@ class NeuralModel:
         if self._L.NA_ProcessBatch(self._h, pi, po, int(numStreams), int(numFrames), int(layout)) != 0:
             raise NeuralAudioError(_last_error(self._L))
         return output
+
+    def ProcessBatchAsync(self, input, output, numStreams, numFrames, layout=STREAM_MAJOR):
+        """Pipelined ProcessBatch for page-locked host buffers (or device buffers): returns once queued."""
+        pi, ni, _k1 = _pointer_of(input)
+        po, no, _k2 = _pointer_of(output, True)
+        if ni < numStreams * numFrames or no < numStreams * numFrames:
+            raise NeuralAudioError("buffer smaller than numStreams * numFrames")
+        if self._L.NA_ProcessBatchAsync(self._h, pi, po, int(numStreams), int(numFrames), int(layout)) != 0:
+            raise NeuralAudioError(_last_error(self._L))
+        return output
+
+    def WaitBatches(self, lag=0):
+        if self._L.NA_WaitBatches(self._h, int(lag)) != 0:
+            raise NeuralAudioError(_last_error(self._L))
 
     def Synchronize(self):
         if self._L.NA_Synchronize(self._h) != 0:

@@ -303,6 +303,27 @@ int NA_ProcessBatch(NeuralModel* model, const float* input, float* output, size_
 	}
 }
 
+int NA_ProcessBatchAsync(NeuralModel* model, const float* input, float* output, size_t numStreams, size_t numFrames, int layout)
+{
+	if (!impl(model)) { nab200::SetLastError("null model"); return -1; }
+	if (layout != 0 && layout != 1) { nab200::SetLastError("bad layout"); return -1; }
+	try
+	{
+		return model->model->ProcessBatchAsync(input, output, numStreams, numFrames, (NeuralAudio::EBatchLayout)layout) ? 0 : -1;
+	}
+	catch (...)
+	{
+		nab200::SetLastError("exception in ProcessBatchAsync");
+		return -1;
+	}
+}
+
+int NA_WaitBatches(NeuralModel* model, int lag)
+{
+	if (!impl(model)) return -1;
+	return model->model->WaitBatches(lag) ? 0 : -1;
+}
+
 int NA_Synchronize(NeuralModel* model)
 {
 	if (!impl(model)) return -1;

@@ -56,6 +56,16 @@ namespace nab200
 		if (pinnedOut) cudaFreeHost(pinnedOut);
 		if (devIn) cudaFree(devIn);
 		if (devOut) cudaFree(devOut);
+		for (int i = 0; i < 2; i++)
+		{
+			if (slotIn[i]) cudaFree(slotIn[i]);
+			if (slotOut[i]) cudaFree(slotOut[i]);
+			if (evIn[i]) cudaEventDestroy(evIn[i]);
+			if (evKernel[i]) cudaEventDestroy(evKernel[i]);
+			if (evDone[i]) cudaEventDestroy(evDone[i]);
+		}
+		if (h2dStream) cudaStreamDestroy(h2dStream);
+		if (d2hStream) cudaStreamDestroy(d2hStream);
 		if (stream) cudaStreamDestroy(stream);
 	}
 
@@ -175,9 +185,101 @@ namespace nab200
 		return true;
 	}
 
+	bool StreamEngine::EnsurePipeline(size_t floats)
+	{
+		if (!h2dStream)
+		{
+			if (!CudaOk(cudaStreamCreateWithFlags(&h2dStream, cudaStreamNonBlocking), "cudaStreamCreate")) return false;
+			if (!CudaOk(cudaStreamCreateWithFlags(&d2hStream, cudaStreamNonBlocking), "cudaStreamCreate")) return false;
+			for (int i = 0; i < 2; i++)
+			{
+				if (!CudaOk(cudaEventCreateWithFlags(&evIn[i], cudaEventDisableTiming), "cudaEventCreate")) return false;
+				if (!CudaOk(cudaEventCreateWithFlags(&evKernel[i], cudaEventDisableTiming), "cudaEventCreate")) return false;
+				if (!CudaOk(cudaEventCreateWithFlags(&evDone[i], cudaEventDisableTiming), "cudaEventCreate")) return false;
+			}
+		}
+		if (floats <= slotFloats) return true;
+		if (!WaitBatches(0)) return false;
+		for (int i = 0; i < 2; i++)
+		{
+			if (slotIn[i]) cudaFree(slotIn[i]);
+			if (slotOut[i]) cudaFree(slotOut[i]);
+			slotIn[i] = slotOut[i] = nullptr;
+		}
+		slotFloats = 0;
+		const size_t cap = floats < 4096 ? 4096 : floats;
+		for (int i = 0; i < 2; i++)
+		{
+			if (!CudaOk(cudaMalloc(&slotIn[i], cap * 4), "cudaMalloc(pipeline staging)")) return false;
+			if (!CudaOk(cudaMalloc(&slotOut[i], cap * 4), "cudaMalloc(pipeline staging)")) return false;
+		}
+		slotFloats = cap;
+		return true;
+	}
+
+	bool StreamEngine::ProcessAsync(const float* in, float* out, size_t S, size_t n, int layout)
+	{
+		if (S == 0 || n == 0) return true;
+		if (S > numStreams) { SetLastError("ProcessBatchAsync: numStreams exceeds the allocated stream slots (call SetNumStreams first)"); return false; }
+		if (in == nullptr || out == nullptr) { SetLastError("ProcessBatchAsync: null buffer"); return false; }
+		if (!CudaOk(cudaSetDevice(device), "cudaSetDevice")) return false;
+		const bool inDev = IsDevicePointer(in), outDev = IsDevicePointer(out);
+		if (inDev || outDev) return Process(in, out, S, n, layout);   // device pointers are already asynchronous
+		if (!IsPinnedHost(in) || !IsPinnedHost(out))
+		{
+			SetLastError("ProcessBatchAsync: host buffers must be page-locked (cudaHostAlloc / cudaHostRegister); use ProcessBatch for pageable memory");
+			return false;
+		}
+		const size_t total = S * n;
+		if (!EnsurePipeline(total)) return false;
+		const int slot = (int)(asyncSeq & 1ull);
+		// the slot's previous user (two calls ago) must have finished its copy-out
+		if (asyncSeq >= 2 && asyncWaited + 2 <= asyncSeq)
+		{
+			if (!CudaOk(cudaEventSynchronize(evDone[slot]), "cudaEventSynchronize")) return false;
+			asyncWaited = asyncSeq - 1;
+		}
+		const long long SS = layout == 0 ? (long long)n : 1;
+		const long long FS = layout == 0 ? 1 : (long long)S;
+		if (!CudaOk(cudaMemcpyAsync(slotIn[slot], in, total * 4, cudaMemcpyHostToDevice, h2dStream), "cudaMemcpyAsync(H2D)")) return false;
+		if (!CudaOk(cudaEventRecord(evIn[slot], h2dStream), "cudaEventRecord")) return false;
+		if (!CudaOk(cudaStreamWaitEvent(stream, evIn[slot], 0), "cudaStreamWaitEvent")) return false;
+		if (!ProcessDevice(slotIn[slot], slotOut[slot], SS, FS, SS, FS, S, n)) return false;
+		if (!CudaOk(cudaEventRecord(evKernel[slot], stream), "cudaEventRecord")) return false;
+		if (!CudaOk(cudaStreamWaitEvent(d2hStream, evKernel[slot], 0), "cudaStreamWaitEvent")) return false;
+		if (!CudaOk(cudaMemcpyAsync(out, slotOut[slot], total * 4, cudaMemcpyDeviceToHost, d2hStream), "cudaMemcpyAsync(D2H)")) return false;
+		if (!CudaOk(cudaEventRecord(evDone[slot], d2hStream), "cudaEventRecord")) return false;
+		// the next call's copy-in into this slot's input staging may only start after this call's kernels: the slot is
+		// reused two calls later, after evDone was awaited above, which implies evKernel
+		asyncSeq++;
+		return true;
+	}
+
+	bool StreamEngine::WaitBatches(int lag)
+	{
+		if (lag < 0) lag = 0;
+		if (asyncSeq == 0 || !h2dStream) return true;
+		if (!CudaOk(cudaSetDevice(device), "cudaSetDevice")) return false;
+		// calls complete in order; wait for call number (asyncSeq - lag), 1-based
+		if (asyncSeq <= (unsigned long long)lag) return true;
+		const unsigned long long target = asyncSeq - (unsigned long long)lag;
+		if (target <= asyncWaited) return true;
+		if (asyncSeq - target >= 2)
+		{
+			// older than the two slots we track: it completed before its slot was reused
+			asyncWaited = target;
+			return true;
+		}
+		const int slot = (int)((target - 1) & 1ull);
+		if (!CudaOk(cudaEventSynchronize(evDone[slot]), "cudaEventSynchronize")) return false;
+		asyncWaited = target;
+		return true;
+	}
+
 	bool StreamEngine::Synchronize()
 	{
 		if (!stream) return true;
+		if (!WaitBatches(0)) return false;
 		return CudaOk(cudaStreamSynchronize(stream), "cudaStreamSynchronize");
 	}
 

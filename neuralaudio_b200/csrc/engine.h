@@ -43,6 +43,12 @@ namespace nab200
 
 		// host or device pointers; layout 0 = [stream][frame], 1 = [frame][stream]
 		bool Process(const float* in, float* out, size_t numStreams, size_t numFrames, int layout);
+		// Pipelined form for PINNED host buffers: returns once the work is queued; copy-in, kernels and copy-out run on three
+		// CUDA streams with two staging slots, so the transfers of consecutive calls overlap the kernels.  `out` (and `in`)
+		// must stay untouched until WaitBatches() says the call is done.  Device pointers behave like Process().
+		bool ProcessAsync(const float* in, float* out, size_t numStreams, size_t numFrames, int layout);
+		// wait until at most `lag` of the queued async calls are still in flight (0: all done)
+		bool WaitBatches(int lag);
 		bool Synchronize();
 
 		size_t NumStreams() const { return numStreams; }
@@ -65,6 +71,15 @@ namespace nab200
 		float* devIn = nullptr;
 		float* devOut = nullptr;
 		size_t stagingFloats = 0;
+		// async pipeline: slot = call sequence number & 1
+		bool EnsurePipeline(size_t floats);
+		cudaStream_t h2dStream = nullptr, d2hStream = nullptr;
+		cudaEvent_t evIn[2] = { nullptr, nullptr }, evKernel[2] = { nullptr, nullptr }, evDone[2] = { nullptr, nullptr };
+		float* slotIn[2] = { nullptr, nullptr };
+		float* slotOut[2] = { nullptr, nullptr };
+		size_t slotFloats = 0;
+		unsigned long long asyncSeq = 0;      // calls queued so far
+		unsigned long long asyncWaited = 0;   // calls known complete
 	};
 
 	class WaveNetEngine : public StreamEngine

@@ -79,6 +79,20 @@ inline namespace b200
 		return true;
 	}
 
+	bool B200EngineModel::ProcessBatchAsync(const float* input, float* output, size_t numStreams, size_t numFrames, EBatchLayout layout)
+	{
+		if (!engine) return false;
+		if (!engine->ProcessAsync(input, output, numStreams, numFrames, (int)layout)) { lastError = nab200::LastError(); return false; }
+		return true;
+	}
+
+	bool B200EngineModel::WaitBatches(int lag)
+	{
+		if (!engine) return false;
+		if (!engine->WaitBatches(lag)) { lastError = nab200::LastError(); return false; }
+		return true;
+	}
+
 	bool B200EngineModel::Synchronize()
 	{
 		if (!engine) return false;
@@ -203,6 +217,19 @@ inline namespace b200
 	{
 		auto* m = Current();
 		return m ? m->ProcessBatch(input, output, numStreams, numFrames, layout) : false;
+	}
+
+	bool B200CompositeModel::ProcessBatchAsync(const float* input, float* output, size_t numStreams, size_t numFrames, EBatchLayout layout)
+	{
+		B200ModelImpl* m = Current();
+		return m ? m->ProcessBatchAsync(input, output, numStreams, numFrames, layout) : false;
+	}
+
+	bool B200CompositeModel::WaitBatches(int lag)
+	{
+		bool ok = true;
+		for (auto* m : models) ok = m->WaitBatches(lag) && ok;
+		return ok;
 	}
 
 	bool B200CompositeModel::Synchronize()

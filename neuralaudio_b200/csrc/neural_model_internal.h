@@ -43,6 +43,8 @@ inline namespace b200
 		bool SetNumStreams(size_t numStreams) override;
 		size_t GetNumStreams() override;
 		bool ProcessBatch(const float* input, float* output, size_t numStreams, size_t numFrames, EBatchLayout layout) override;
+		bool ProcessBatchAsync(const float* input, float* output, size_t numStreams, size_t numFrames, EBatchLayout layout) override;
+		bool WaitBatches(int lag) override;
 		bool Synchronize() override;
 		void* GetCudaStream() override;
 		int GetDevice() override;
@@ -74,6 +76,8 @@ inline namespace b200
 		bool SetNumStreams(size_t numStreams) override;
 		size_t GetNumStreams() override;
 		bool ProcessBatch(const float* input, float* output, size_t numStreams, size_t numFrames, EBatchLayout layout) override;
+		bool ProcessBatchAsync(const float* input, float* output, size_t numStreams, size_t numFrames, EBatchLayout layout) override;
+		bool WaitBatches(int lag) override;
 		bool Synchronize() override;
 		void* GetCudaStream() override;
 		int GetDevice() override;
