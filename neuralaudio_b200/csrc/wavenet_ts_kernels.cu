@@ -552,7 +552,6 @@ namespace nab200
 					// by issue slots under contention, not by this latency; tools/ts_timing.cu.)
 					prefetch_layer<0>(cx, l + 1, s, array1First);
 					wait_ld();
-					tmem_zero<C>(lanebase + TC::D);   // every conv MMA accumulates; the accumulator starts each layer at zero
 					// z is the 1x1's A operand [hi | lo]; it is delivered in K-steps of 8 channels so that the issuer starts on the
 					// first while the second is still being activated
 #pragma unroll
@@ -604,11 +603,13 @@ namespace nab200
 					if (li == 0)
 					{
 						// (later layers: these were issued right behind the previous layer's 1x1, see below)
+						// The first MMA of a layer overwrites the accumulator, everything after it accumulates.
 #pragma unroll
 						for (int ks = 0; ks < KS; ks++)
 						{
 							const u64 boff = (u64)((2 * CG + 2 * ks) * C);
-							mma_ts<1>(tm + TC::D, tm + TC::XR + 8u * ks, dHi + boff, idC);
+							if (ks == 0) mma_ts<0>(tm + TC::D, tm + TC::XR + 8u * ks, dHi + boff, idC);
+							else mma_ts<1>(tm + TC::D, tm + TC::XR + 8u * ks, dHi + boff, idC);
 							mma_ts<1>(tm + TC::D, tm + TC::XR + 8u * ks, dLo + boff, idC);
 						}
 						mma_ts<1>(tm + TC::D, tm + kConst, desc_at(wb16 + g4.y, C), idC);
@@ -683,8 +684,8 @@ namespace nab200
 				if (more && cx.el)
 				{
 					// The next layer's undelayed tap reads the residual accumulator itself as its high part, so those products (and
-					// the constant-operand one) need nothing from the stagers: issue them while the stagers wake up.  D is zero again
-					// (the stagers cleared it before they delivered z).
+					// the constant-operand one) need nothing from the stagers: issue them while the stagers wake up.  D is free: the
+					// stagers read it before they delivered z.
 					const uint32_t nb16 = (cx.wbuf + ((cx.wq + 1) & 1u) * cx.wbufStride) >> 4;
 					const uint4 n4 = lds128(la + (uint32_t)sizeof(TsLayer) + 64);
 					const u64 nHi = desc_at(nb16, C), nLo = desc_at(nb16 + n4.x, C);
@@ -692,7 +693,8 @@ namespace nab200
 					for (int ks = 0; ks < KS; ks++)
 					{
 						const u64 boff = (u64)((2 * CG + 2 * ks) * C);
-						mma_ts<1>(tm + TC::D, tm + TC::XR + 8u * ks, nHi + boff, idC);
+						if (ks == 0) mma_ts<0>(tm + TC::D, tm + TC::XR + 8u * ks, nHi + boff, idC);   // overwrites: the stagers have read D
+						else mma_ts<1>(tm + TC::D, tm + TC::XR + 8u * ks, nHi + boff, idC);
 						mma_ts<1>(tm + TC::D, tm + TC::XR + 8u * ks, nLo + boff, idC);
 					}
 					mma_ts<1>(tm + TC::D, tm + kConst, desc_at(nb16 + n4.y, C), idC);
@@ -894,7 +896,7 @@ namespace nab200
 						cx.stampCta = c < 0 ? 0 : c; cx.stampStream = k - 1;
 					}
 #endif
-					// ---- entry: constant operand [cond, cond_lo, cond, 1, 1, 1, 0, 0], zero conv accumulator ----
+					// ---- entry: constant operand [cond, cond_lo, cond, 1, 1, 1, 0, 0] ----
 					{
 						uint32_t cv[8];
 						uint32_t cl, dummy;
@@ -902,12 +904,11 @@ namespace nab200
 						cv[0] = __float_as_uint(cond); cv[1] = cl; cv[2] = cv[0];
 						cv[3] = 0x3F800000u; cv[4] = 0x3F800000u; cv[5] = 0x3F800000u; cv[6] = 0u; cv[7] = 0u;
 						tmem_st<8>(lanebase + kConst, cv);
-						tmem_zero<16>(lanebase + Cols<0>::D);
 					}
 					stager_arrive(kBarE);
 					stage_array<0>(cx, first0, num0, s, first1);
 
-					// ---- array transition: low parts of the array output and of the head output, zero the next accumulator ----
+					// ---- array transition: low parts of the array output and of the head output ----
 					stager_wait(kBarXReady);
 					{
 						uint32_t x[16], xl[16];
@@ -920,7 +921,6 @@ namespace nab200
 #pragma unroll
 						for (int c = 0; c < 8; c += 2) split_lo2(h[c], h[c + 1], hl[c], hl[c + 1]);
 						tmem_st<8>(lanebase + kHdLo, hl);
-						tmem_zero<8>(lanebase + Cols<1>::D);
 					}
 					stager_arrive(kBarE);
 					stage_array<1>(cx, first1, num1, s, first1);
