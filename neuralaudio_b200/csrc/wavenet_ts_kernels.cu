@@ -480,7 +480,12 @@ namespace nab200
 				stager_wait(kBarXReady);
 				TS_STAMP(1);
 				uint32_t x[C];
+#ifdef NAB_TS_NO_XRLOAD   // timing experiment only (tools/ts_timing.cu): results are wrong
+#pragma unroll
+				for (int c = 0; c < C; c++) x[c] = (uint32_t)(tid + c + l) << 20;
+#else
 				tmem_ld<C>(lanebase + TC::XR, x);
+#endif
 				if (mixed)
 				{
 					const uint32_t cur = cx.xe + (uint32_t)(kCur + tid) * 16u;
