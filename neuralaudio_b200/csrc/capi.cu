@@ -1,5 +1,7 @@
 // extern "C" boundary: the reference's 15 exports (NeuralAudioCAPI/NeuralAudioCApi.cpp:14-97) plus the additive
 // batched entry points declared in include/NeuralAudioCApi.h.  No exception crosses this boundary.
+#include <cmath>
+#include <cstring>
 #include <cstring>
 #include <filesystem>
 #include <fstream>
@@ -384,7 +386,50 @@ int NA_DescribeModelFile(const wchar_t* modelPath, int externalSampleRate, char*
 					}
 					os << "],\"ring_lp\":[";
 					for (int r = 0; r < p.dev.numRings; r++) os << (r ? "," : "") << p.dev.ringLp[r];
-					os << "]}";
+					os << "]";
+					// which kernel a load would pick, and the TMEM-operand packing checked against the file's weights:
+					// every conv tap matrix must reconstruct as hi + lo, with hi exactly representable in tf32
+					const bool ts = nab200::GetOptions().useTc >= 2 && nab200::WaveNetTsSupported(d);
+					const bool tc = !ts && nab200::GetOptions().useTc != 0 && nab200::WaveNetTcSupported(d);
+					os << ",\"kernel\":\"" << (ts ? "tcgen05_tmem_operands" : tc ? "tcgen05_smem_operands" : "cuda_cores") << "\"";
+					if (nab200::WaveNetTsSupported(d))
+					{
+						nab200::PackedWaveNet q = nab200::PackWaveNetTs(d);
+						double worst = 0.0;
+						long long badHi = 0;
+						const float* w = d.weights.data();
+						int layer = 0;
+						for (size_t a = 0; a < d.arrays.size(); a++)
+						{
+							const auto& A = d.arrays[a];
+							const int C = A.channels, CP = q.dev.arrays[a].C, KC = CP / 4;
+							w += (size_t)C * A.inputSize;
+							for (size_t l = 0; l < A.dilations.size(); l++, layer++)
+							{
+								const nab200::WnLayer& L = q.dev.layers[layer];
+								const float* blk = q.weights.data() + L.wOff;
+								const int K = A.kernelSizes[l];
+								const float* src = w;
+								for (int i = 0; i < C; i++)
+									for (int jn = 0; jn < C; jn++)
+										for (int k = 0; k < K; k++)
+										{
+											const int at = ((k * KC + jn / 4) * CP + i) * 4 + (jn % 4);
+											const float hi = blk[at], lo = blk[L.oConvLo + at];
+											uint32_t u;
+											memcpy(&u, &hi, 4);
+											if (u & 0x1FFFu) badHi++;
+											const double e = fabs((double)hi + (double)lo - (double)*src++);
+											if (e > worst) worst = e;
+										}
+								w += (size_t)C * C * K + C + C + (size_t)C * C + C;
+							}
+							w += (size_t)A.headSize * C + (A.headBias ? A.headSize : 0);
+						}
+						os << ",\"ts\":{\"packed_floats\":" << q.weights.size() << ",\"state_floats\":" << q.dev.stateStride << ",\"max_block\":" << q.dev.maxBlock
+						   << ",\"num_rings\":" << q.dev.numRings << ",\"conv_split_max_error\":" << worst << ",\"conv_hi_not_tf32\":" << badHi << "}";
+					}
+					os << "}";
 					return;
 				}
 				if (arch == "LSTM")

@@ -149,3 +149,26 @@ def test_product_never_touches_the_oracle():
             if fn.endswith((".py", ".cu", ".cpp", ".h", "Makefile")):
                 txt = open(os.path.join(dirpath, fn), errors="replace").read()
                 assert "na_oracle" not in txt and "libna_ref" not in txt and "import oracle" not in txt and "from oracle" not in txt, fn
+
+
+def test_tmem_operand_packing_reconstructs_weights(na, tmp_path):
+    """Host logic of the TMEM-operand (tcgen05) WaveNet kernel, no GPU: A1 Standard / Lite shapes select it, its packing keeps
+    the reference's state size (WaveNet.h:30-83: (K-1)*d columns per conv) with channels padded to (16, 8), and every conv
+    tap matrix splits as hi + lo with hi exactly representable in tf32 and |hi + lo - w| at fp32 rounding level."""
+    for name, state_floats in (("syn_a1_standard", 49104), ("syn_a1_lite", None)):
+        g = load_golden(golden_files(name)[0])
+        mf = model_file_for(g, tmp_path)
+        d = na.describe_model_file(mf)
+        assert d["kernel"] == "tcgen05_tmem_operands"
+        ts = d["ts"]
+        assert ts["num_rings"] == d["num_rings"] == d["num_layers"]
+        pad = [a["padded"] for a in d["arrays"]]
+        cfg = g["model"]["config"]["layers"]
+        assert ts["state_floats"] == sum(cpad * (a["kernel_size"] - 1) * dil for cpad, a in zip((16, 8), cfg) for dil in a["dilations"])
+        if state_floats:
+            assert ts["state_floats"] == state_floats and pad[0] >= 16
+        assert ts["conv_hi_not_tf32"] == 0
+        assert ts["conv_split_max_error"] <= 1e-7
+        assert ts["max_block"] * 4 * 2 <= 48 * 1024      # two weight buffers per CTA, 4 CTAs per SM
+    g = load_golden(golden_files("syn_a1_nano")[0])
+    assert na.describe_model_file(model_file_for(g, tmp_path))["kernel"] == "cuda_cores"
