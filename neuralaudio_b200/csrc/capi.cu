@@ -390,8 +390,10 @@ int NA_DescribeModelFile(const wchar_t* modelPath, int externalSampleRate, char*
 					// which kernel a load would pick, and the TMEM-operand packing checked against the file's weights:
 					// every conv tap matrix must reconstruct as hi + lo, with hi exactly representable in tf32
 					const bool ts = nab200::GetOptions().useTc >= 2 && nab200::WaveNetTsSupported(d);
-					const bool tc = !ts && nab200::GetOptions().useTc != 0 && nab200::WaveNetTcSupported(d);
-					os << ",\"kernel\":\"" << (ts ? "tcgen05_tmem_operands" : tc ? "tcgen05_smem_operands" : "cuda_cores") << "\"";
+					const bool tc = !ts && nab200::GetOptions().useTc >= 1 && nab200::WaveNetTcSupported(d);
+					const int pc0 = p.dev.arrays[0].C, pc1 = p.dev.numArrays > 1 ? p.dev.arrays[1].C : 0;
+					const bool shaped = nab200::GetOptions().useTc >= 0 && nab200::wavenet_variant_supported(pc0, pc1, p.dev.arrays[0].act);
+					os << ",\"kernel\":\"" << (ts ? "tcgen05_tmem_operands" : tc ? "tcgen05_smem_operands" : shaped ? "cuda_cores" : nab200::wavenet_generic_supported(p.dev) ? "cuda_cores_runtime_shaped" : "none") << "\"";
 					if (nab200::WaveNetTsSupported(d))
 					{
 						nab200::PackedWaveNet q = nab200::PackWaveNetTs(d);

@@ -298,8 +298,14 @@ namespace nab200
 	{
 		const WnModelDev& M = packed.dev;
 		const int C0 = M.arrays[0].C, C1 = M.numArrays > 1 ? M.arrays[1].C : 0;
-		const bool ok = M.tc == 2 ? wavenet_ts_variant_supported(C0, C1, M.arrays[0].act)
+		bool ok = M.tc == 2 ? wavenet_ts_variant_supported(C0, C1, M.arrays[0].act)
 			: M.tc ? wavenet_tc_variant_supported(C0, C1, M.arrays[0].act) : wavenet_variant_supported(C0, C1, M.arrays[0].act);
+		if (M.tc == 0 && (!ok || GetOptions().useTc < 0) && wavenet_generic_supported(M))
+		{
+			// no compile-time-shaped kernel (or the generic one was asked for): the run-time-shaped kernel
+			useGeneric = true;
+			ok = true;
+		}
 		if (!ok)
 		{
 			std::stringstream ss;
@@ -397,7 +403,7 @@ namespace nab200
 
 	bool WaveNetEngine::ProcessDevice(const float* in, float* out, long long inSS, long long inFS, long long outSS, long long outFS, size_t S, size_t n)
 	{
-		const int maxPass = packed.dev.tc ? 128 : wavenet_max_frames_per_pass(packed.dev.arrays[0].C);
+		const int maxPass = (packed.dev.tc || useGeneric) ? 128 : wavenet_max_frames_per_pass(packed.dev.arrays[0].C);
 		const Options& opt = GetOptions();
 		size_t done = 0;
 		while (done < n)
@@ -416,7 +422,8 @@ namespace nab200
 			a.useTma = opt.useTma != 0;
 			a.stream = stream;
 			a.tsIssuers = opt.tsIssuers;
-			const cudaError_t lerr = packed.dev.tc == 2 ? wavenet_ts_launch(packed.dev, a) : packed.dev.tc ? wavenet_tc_launch(packed.dev, a) : wavenet_launch(packed.dev, a);
+			const cudaError_t lerr = packed.dev.tc == 2 ? wavenet_ts_launch(packed.dev, a) : packed.dev.tc ? wavenet_tc_launch(packed.dev, a)
+				: useGeneric ? wavenet_generic_launch(packed.dev, a) : wavenet_launch(packed.dev, a);
 			if (!CudaOk(lerr, "wavenet kernel launch")) return false;
 			done += chunk;
 		}

@@ -17,7 +17,8 @@ namespace nab200
 	{
 		int useTma = 1;         // stage history windows with cp.async.bulk + mbarrier (0: plain loads, debugging aid)
 		int useTc = 2;          // WaveNet kernel choice where the architecture fits: 2 tcgen05 with TMEM operands (default),
-		                        // 1 tcgen05 with shared-memory operands (round-1 kernel), 0 CUDA-core kernel
+		                        // 1 tcgen05 with shared-memory operands (round-1 kernel), 0 CUDA-core kernel,
+		                        // -1 the run-time-shaped kernel even for shapes that have a specialised one (tests)
 		int tsIssuers = 4;      // TS kernel: warps sharing the MMA issue
 		int maxGridCtas = 0;    // 0: one CTA per SM
 	};
@@ -105,6 +106,7 @@ namespace nab200
 		size_t weightFloats = 0;     // padded to a multiple of 4
 		float* dState = nullptr;     // [S][stateStride]
 		int* dHeads = nullptr;       // [S][numRings]
+		bool useGeneric = false;     // no compile-time-shaped kernel for this architecture: run-time-shaped kernel
 	};
 
 	class LstmEngine : public StreamEngine

@@ -212,7 +212,7 @@ namespace nab200
 		{
 			const auto& A = d.arrays[a];
 			if (A.dilations.empty()) throw std::runtime_error("unsupported model: empty layer array");
-			if (A.channels < 1 || A.channels > 16) throw std::runtime_error("unsupported model: WaveNet channels must be 1..16");
+			if (A.channels < 1 || A.channels > 32) throw std::runtime_error("unsupported model: WaveNet channels must be 1..32");
 			if (a == 0 && A.inputSize != 1) throw std::runtime_error("unsupported model: first layer array input_size != 1");
 			if (a > 0 && A.inputSize != d.arrays[a - 1].channels) throw std::runtime_error("malformed model: layer array input_size does not match previous channels");
 			if (a + 1 < d.arrays.size() && A.headSize != d.arrays[a + 1].channels) throw std::runtime_error("malformed model: head_size does not match next array's channels");
@@ -357,7 +357,8 @@ namespace nab200
 		if (c <= 4) return 4;
 		if (c <= 8) return 8;
 		if (c <= 12) return 12;
-		return 16;
+		if (c <= 16) return 16;
+		return (c + 3) & ~3;   // run-time-shaped kernel only
 	}
 
 	static int Align4(int v) { return (v + 3) & ~3; }

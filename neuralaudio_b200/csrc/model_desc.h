@@ -76,5 +76,5 @@ namespace nab200
 	PackedWaveNet PackWaveNetTs(const WaveNetDesc& desc);
 	PackedLstm PackLstm(const LstmDesc& desc);
 
-	int PadChannels(int c);   // 2, 4, 8, 12, 16
+	int PadChannels(int c);   // 2, 4, 8, 12, 16, then multiples of 4 up to 32
 }

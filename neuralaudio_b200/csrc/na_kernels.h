@@ -28,6 +28,9 @@ namespace nab200
 	// tcgen05 path with TMEM A operands (WnModelDev::tc == 2 packing), n <= 128
 	cudaError_t wavenet_ts_launch(const WnModelDev& M, const WnLaunch& a);
 	bool wavenet_ts_variant_supported(int C0, int C1, int act);
+	// run-time-shaped fallback (CUDA-core packing, any channel count up to 32, 1x1 heads), n <= 128
+	cudaError_t wavenet_generic_launch(const WnModelDev& M, const WnLaunch& a);
+	bool wavenet_generic_supported(const WnModelDev& M);
 	cudaError_t wavenet_prewarm_launch(const WnModelDev& M, const float* weights, float* tmpl, cudaStream_t stream);
 	cudaError_t state_fill_launch(float* state, const float* tmpl, int strideFloats, long long numStreams, cudaStream_t stream);
 	cudaError_t int_fill_launch(int* p, int v, long long total, cudaStream_t stream);

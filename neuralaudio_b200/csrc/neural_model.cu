@@ -277,7 +277,7 @@ inline namespace b200
 		model->receptiveField = desc.isStatic ? desc.receptiveField : -1;
 		const int tcOpt = nab200::GetOptions().useTc;
 		const bool useTs = tcOpt >= 2 && nab200::WaveNetTsSupported(desc);
-		const bool useTc = !useTs && tcOpt != 0 && nab200::WaveNetTcSupported(desc);
+		const bool useTc = !useTs && tcOpt >= 1 && nab200::WaveNetTcSupported(desc);
 		auto* engine = new nab200::WaveNetEngine(loader->GetDevice(),
 			useTs ? nab200::PackWaveNetTs(desc) : useTc ? nab200::PackWaveNetTc(desc) : nab200::PackWaveNet(desc));
 		model->engine = engine;

@@ -102,6 +102,32 @@ def synthetic_cases():
     return cases
 
 
+def dyn_config(arrays):
+    """Run-time-shaped A1-style stacks (the reference's dynamic path, WaveNetDynamic.h): arrays = [(channels, kernel, dilations), ...]"""
+    layers = []
+    for i, (c, k, dil) in enumerate(arrays):
+        last = i + 1 == len(arrays)
+        layers.append({"input_size": 1 if i == 0 else arrays[i - 1][0], "condition_size": 1, "head_size": 1 if last else arrays[i + 1][0],
+                       "channels": c, "kernel_size": k, "dilations": dil, "activation": "Tanh", "gated": False, "head_bias": last})
+    return {"layers": layers, "head": None, "head_scale": 0.02}
+
+
+def dynamic_cases():
+    rng = np.random.default_rng(20261018)
+    shapes = {"dyn_20x10": [(20, 3, [1, 2, 4, 8, 16, 32, 64]), (10, 3, [128, 1, 2, 4, 8])],
+              "dyn_single6_k2": [(6, 2, [1, 3, 9, 27])],
+              "dyn_16x16_k5": [(16, 5, [1, 2, 4, 8]), (16, 5, [1, 2, 4, 8])],
+              "dyn_7x3": [(7, 3, [1, 2, 4, 8, 16]), (3, 3, [1, 2, 4])]}
+    cases = {}
+    for name, arrays in shapes.items():
+        cfg = dyn_config(arrays)
+        c, k = arrays[0][0], arrays[0][1]
+        w = synth_wavenet_weights(rng, a1_num_weights(cfg), 1.1 / np.sqrt(k * c), 1.0)
+        cases[name] = {"version": "0.5.4", "architecture": "WaveNet", "config": cfg, "weights": w, "sample_rate": 48000,
+                       "metadata": {"loudness": -11.0, "name": "syn-" + name}}
+    return cases
+
+
 def nam_text(case):
     d = dict(case)
     d["weights"] = [float(x) for x in np.asarray(case["weights"], dtype=np.float32)]
@@ -125,7 +151,7 @@ def main():
     tmpdir = os.path.join(HERE, "_tmp")
     os.makedirs(tmpdir, exist_ok=True)
     made = []
-    fixtures = [("BossWN-nano.nam", 1.0), ("BossWN-feather.nam", 1.0), ("BossWN-standard.nam", 1.0), ("BossWN-a2.nam", 1.0),
+    fixtures = [] if "--dynamic-only" in sys.argv else [("BossWN-nano.nam", 1.0), ("BossWN-feather.nam", 1.0), ("BossWN-standard.nam", 1.0), ("BossWN-a2.nam", 1.0),
                 ("BossWN-a2.nam", 0.0), ("BossLSTM-1x16.nam", 1.0), ("BossLSTM-2x8.nam", 1.0),
                 ("tw40_blues_deluxe_deerinkstudios.json", 1.0), ("namcore_wavenet.nam", 1.0), ("namcore_lstm.nam", 1.0),
                 ("namcore_wavenet_a1_standard.nam", 1.0)]
@@ -141,7 +167,13 @@ def main():
         out = os.path.join(HERE, "ref_%s.npz" % tag)
         np.savez_compressed(out, x=x, y=y, dc=dc, fixture=name, quality=np.float32(q), info=json.dumps(info))
         made.append(out)
-    for j, (name, case) in enumerate(synthetic_cases().items()):
+    only_dynamic = "--dynamic-only" in sys.argv   # adds the run-time-shaped cases without touching the earlier vectors
+    if only_dynamic:
+        made = []
+    allcases = list(synthetic_cases().items()) + list(dynamic_cases().items())
+    for j, (name, case) in enumerate(allcases):
+        if only_dynamic and not name.startswith("dyn_"):
+            continue
         path = os.path.join(tmpdir, name + ".nam")
         with open(path, "w") as f:
             f.write(nam_text(case))

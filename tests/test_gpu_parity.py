@@ -264,6 +264,32 @@ def test_tensor_core_and_cuda_core_kernels_agree(na, O, name, tmp_path):
             assert float(np.abs(ys - y[:, s, :].reshape(-1)).max()) <= WAVENET_TOL
 
 
+@pytest.mark.parametrize("name", ["syn_a1_standard", "syn_a1_feather", "syn_a2_full", "syn_dyn_20x10", "syn_dyn_16x16_k5"])
+def test_runtime_shaped_kernel(na, O, name, tmp_path):
+    """The run-time-shaped kernel (the batched counterpart of the reference's dynamic path, WaveNetDynamic.h) against the
+    oracle per stream, for shapes that only it can run and - forced with use_tc = -1 - for official shapes, where it must
+    also agree with the specialised kernels."""
+    g = load_golden(golden_files(name)[0])
+    mf = model_file_for(g, tmp_path)
+    S, n, calls = 9, 100, 11     # ragged: 100-frame calls
+    x = np.random.default_rng(29).uniform(-1, 1, (calls, S, n)).astype(np.float32)
+    outs = []
+    for tc in (-1, 2):
+        prev = na.set_option("use_tc", tc)
+        try:
+            m = _load(na, mf, streams=S)
+            y = np.empty_like(x)
+            for k in range(calls):
+                m.ProcessBatch(x[k], y[k], S, n)
+            outs.append(y)
+        finally:
+            na.set_option("use_tc", prev)
+    assert float(np.abs(outs[0] - outs[1]).max()) <= 4e-6
+    for s in (0, S // 2, S - 1):
+        ys = O.PortModel.from_file(mf).process(np.ascontiguousarray(x[:, s, :]).reshape(-1))
+        assert float(np.abs(ys - outs[0][:, s, :].reshape(-1)).max()) <= WAVENET_TOL
+
+
 def test_full_size_config_properties(na, O, tmp_path):
     """BASELINE.json cfg 2 (A1 Standard, 4096 streams x 128 frames) at full size, through size-independent
     properties: identical inputs => bit-identical streams (independence + determinism), a tile of streams checked
