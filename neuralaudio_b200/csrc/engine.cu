@@ -19,6 +19,7 @@ namespace nab200
 			auto env = [](const char* name, int& dst) { const char* e = getenv(name); if (e && *e) dst = atoi(e); };
 			env("NAB200_USE_TC", v.useTc);
 			env("NAB200_TS_ISSUERS", v.tsIssuers);
+			env("NAB200_TS_SPLIT", v.tsSplit);
 			env("NAB200_USE_TMA", v.useTma);
 			env("NAB200_MAX_GRID_CTAS", v.maxGridCtas);
 			return v;
@@ -33,6 +34,7 @@ namespace nab200
 		if (strcmp(name, "use_tma") == 0) { prev = o.useTma; o.useTma = value; }
 		else if (strcmp(name, "use_tc") == 0) { prev = o.useTc; o.useTc = value; }
 		else if (strcmp(name, "ts_issuers") == 0) { prev = o.tsIssuers; o.tsIssuers = value; }
+		else if (strcmp(name, "ts_split") == 0) { prev = o.tsSplit; o.tsSplit = value; }
 		else if (strcmp(name, "max_grid_ctas") == 0) { prev = o.maxGridCtas; o.maxGridCtas = value; }
 		return prev;
 	}
@@ -292,6 +294,7 @@ namespace nab200
 		if (dBlob) cudaFree(dBlob);
 		if (dState) cudaFree(dState);
 		if (dHeads) cudaFree(dHeads);
+		if (dScratch) cudaFree(dScratch);
 	}
 
 	bool WaveNetEngine::Upload()
@@ -330,9 +333,11 @@ namespace nab200
 		{
 			if (dState) cudaFree(dState);
 			if (dHeads) cudaFree(dHeads);
-			dState = nullptr; dHeads = nullptr; numStreams = 0;
+			if (dScratch) cudaFree(dScratch);
+			dState = nullptr; dHeads = nullptr; dScratch = nullptr; numStreams = 0;
 			if (S > 0)
 			{
+				if (packed.dev.tc == 2 && !CudaOk(cudaMalloc(&dScratch, S * wavenet_ts_scratch_floats_per_stream() * 4), "cudaMalloc(array hand-over scratch)")) return false;
 				if (!CudaOk(cudaMalloc(&dState, S * (size_t)packed.dev.stateStride * 4), "cudaMalloc(stream state)")) return false;
 				if (!CudaOk(cudaMalloc(&dHeads, S * (size_t)packed.dev.numRings * 4), "cudaMalloc(ring heads)")) { cudaFree(dState); dState = nullptr; return false; }
 			}
@@ -373,6 +378,8 @@ namespace nab200
 			float* scratch = nullptr;
 			int* scratchHeads = nullptr;
 			float* io = nullptr;
+			float* handover = nullptr;
+			if (M.tc == 2 && !CudaOk(cudaMalloc(&handover, wavenet_ts_scratch_floats_per_stream() * 4), "cudaMalloc(prewarm scratch)")) return false;
 			if (!CudaOk(cudaMalloc(&scratch, (size_t)M.stateStride * 4), "cudaMalloc(prewarm scratch)")) return false;
 			bool ok = CudaOk(cudaMalloc(&scratchHeads, (size_t)M.numRings * 4), "cudaMalloc(prewarm scratch)") &&
 				CudaOk(cudaMalloc(&io, (size_t)frames * 2 * 4), "cudaMalloc(prewarm scratch)");
@@ -387,6 +394,7 @@ namespace nab200
 				a.inSS = frames; a.inFS = 1; a.outSS = frames; a.outFS = 1;
 				a.S = 1; a.n = frames; a.numSMs = numSMs; a.useTma = true; a.stream = stream;
 				a.tsIssuers = GetOptions().tsIssuers;
+				a.tsSplit = GetOptions().tsSplit; a.scratch = handover;
 				ok = CudaOk(M.tc == 2 ? wavenet_ts_launch(M, a) : wavenet_tc_launch(M, a), "wavenet tensor-core prewarm settle");
 			}
 			// under constant input every ring column holds the same value, so the settled rings are a valid template
@@ -394,6 +402,7 @@ namespace nab200
 			ok = ok && CudaOk(cudaMemcpyAsync(dBlob + weightFloats, scratch, (size_t)M.stateStride * 4, cudaMemcpyDeviceToDevice, stream), "cudaMemcpy");
 			ok = ok && CudaOk(cudaStreamSynchronize(stream), "cudaStreamSynchronize");
 			cudaFree(scratch);
+			if (handover) cudaFree(handover);
 			if (scratchHeads) cudaFree(scratchHeads);
 			if (io) cudaFree(io);
 			if (!ok) return false;
@@ -422,6 +431,7 @@ namespace nab200
 			a.useTma = opt.useTma != 0;
 			a.stream = stream;
 			a.tsIssuers = opt.tsIssuers;
+			a.tsSplit = opt.tsSplit; a.scratch = dScratch;
 			const cudaError_t lerr = packed.dev.tc == 2 ? wavenet_ts_launch(packed.dev, a) : packed.dev.tc ? wavenet_tc_launch(packed.dev, a)
 				: useGeneric ? wavenet_generic_launch(packed.dev, a) : wavenet_launch(packed.dev, a);
 			if (!CudaOk(lerr, "wavenet kernel launch")) return false;

@@ -19,7 +19,9 @@ namespace nab200
 		int useTc = 2;          // WaveNet kernel choice where the architecture fits: 2 tcgen05 with TMEM operands (default),
 		                        // 1 tcgen05 with shared-memory operands (round-1 kernel), 0 CUDA-core kernel,
 		                        // -1 the run-time-shaped kernel even for shapes that have a specialised one (tests)
-		int tsIssuers = 4;      // TS kernel: warps sharing the MMA issue
+		int tsIssuers = 4;      // (unused since the TS kernel has a dedicated issuer warp)
+		int tsSplit = 0;        // TS kernel: 1 = one launch per layer array, the 8-channel one with 6 CTAs per SM (measured 5 % slower
+		                        // than the fused kernel: 144 + 90 us vs 208 us; kept as an option, its head sum is exact fp32)
 		int maxGridCtas = 0;    // 0: one CTA per SM
 	};
 	Options& GetOptions();
@@ -106,6 +108,7 @@ namespace nab200
 		size_t weightFloats = 0;     // padded to a multiple of 4
 		float* dState = nullptr;     // [S][stateStride]
 		int* dHeads = nullptr;       // [S][numRings]
+		float* dScratch = nullptr;   // TS split launch: per-stream hand-over between the two array kernels
 		bool useGeneric = false;     // no compile-time-shaped kernel for this architecture: run-time-shaped kernel
 	};
 

@@ -793,6 +793,15 @@ namespace nab200
 				}
 				layerIdx++;
 			}
+			// plain copy of this array's head conv [8 padded] | bias, for the kernel variant that keeps the head sum in registers
+			// (split launch); its float offset inside the packed weights travels in headRingOff (unused otherwise: 1x1 heads only)
+			DA.headRingOff = (int)P.weights.size();
+			P.weights.resize(P.weights.size() + 12, 0.0f);
+			if (H == 1)
+			{
+				for (int j = 0; j < C; j++) P.weights[DA.headRingOff + j] = wHead[j];
+				if (A.headBias) P.weights[DA.headRingOff + 8] = wHead[C];
+			}
 			prevCP = CP;
 		}
 		M.headScale = *w;

@@ -17,7 +17,9 @@ namespace nab200
 		int n;                  // frames this pass (<= wavenet_max_frames_per_pass)
 		int numSMs;
 		bool useTma;
-		int tsIssuers = 4;      // TS kernel: warps sharing the tcgen05.mma issue (1..4)
+		int tsIssuers = 4;      // (unused since the TS kernel has a dedicated issuer warp)
+		int tsSplit = 0;        // TS kernel: one launch per layer array (needs `scratch`)
+		float* scratch = nullptr;   // TS split launch: [S][wavenet_ts_scratch_floats_per_stream()] floats
 		cudaStream_t stream;
 	};
 
@@ -28,6 +30,7 @@ namespace nab200
 	// tcgen05 path with TMEM A operands (WnModelDev::tc == 2 packing), n <= 128
 	cudaError_t wavenet_ts_launch(const WnModelDev& M, const WnLaunch& a);
 	bool wavenet_ts_variant_supported(int C0, int C1, int act);
+	size_t wavenet_ts_scratch_floats_per_stream();
 	// run-time-shaped fallback (CUDA-core packing, any channel count up to 32, 1x1 heads), n <= 128
 	cudaError_t wavenet_generic_launch(const WnModelDev& M, const WnLaunch& a);
 	bool wavenet_generic_supported(const WnModelDev& M);

@@ -52,6 +52,13 @@ namespace nab200
 			static constexpr int C = 8;
 			static constexpr uint32_t T0 = 8, T1 = 24, T2L = 40, D = 48, XR = 88, HD = 96;
 		};
+		// array 1 in its own kernel (split launch): 64 columns per CTA, so more streams are in flight per SM; the head sum stays
+		// in registers there (no HD columns)
+		template <> struct Cols<2>
+		{
+			static constexpr int C = 8;
+			static constexpr uint32_t T0 = 8, T1 = 24, T2L = 40, D = 48, XR = 56, HD = 56;
+		};
 		constexpr uint32_t kHdLo = 56;   // low part of array 0's head output during the array transition
 
 		__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -314,12 +321,13 @@ namespace nab200
 			uint32_t wq;       // issuer: running weight-block counter (current layer's slot)
 			uint32_t dq, xq;   // issuer: running barD / barX phases
 			int cur;           // which hdb half belongs to the current stream
+			int lBegin, lEnd;  // layers this kernel runs (the fused kernel: all; the split kernels: one array each)
+			int a1First;       // first layer of array 1
 #ifdef NAB_TS_TIMING
 			bool stampOn; int stampCta, stampStream;
 #endif
 		};
 		constexpr int kHdbHalf = 72;   // ints per stream in hdb: heads[36] | heads after the call[36]
-		constexpr uint32_t kWbOff = 4 * kRows * 16;   // WB relative to XE, bytes
 
 		// stager: my TMEM stores are done and ordered before the issuer's MMAs, then a non-blocking arrival
 		__device__ __forceinline__ void stager_arrive(int id)
@@ -425,18 +433,17 @@ namespace nab200
 
 		// history of layer `l` counted from the first layer of stream s (l may run past the last layer: next stream)
 		template <int MODE>
-		__device__ __forceinline__ void prefetch_layer(const Ctx& cx, int l, int s, int array1First)
+		__device__ __forceinline__ void prefetch_layer(const Ctx& cx, int l, int s)
 		{
-			const int numLayers = cx.M->numLayers;
 			const int* hd = cx.hdb + cx.cur * kHdbHalf;
-			if (l >= numLayers)
+			if (l >= cx.lEnd)
 			{
-				l -= numLayers;
+				l = cx.lBegin + (l - cx.lEnd);
 				s += cx.gstride;
 				hd = cx.hdb + (cx.cur ^ 1) * kHdbHalf;
 				if (s >= cx.S) { if (MODE == 0) asm volatile("cp.async.commit_group;" ::: "memory"); return; }
 			}
-			if (l < array1First) prefetch_windows<4, MODE>(cx, l, s, hd);
+			if (l < cx.a1First) prefetch_windows<4, MODE>(cx, l, s, hd);
 			else prefetch_windows<2, MODE>(cx, l, s, hd);
 		}
 
@@ -458,10 +465,11 @@ namespace nab200
 
 		// ---- stager warps: one layer array of the CTA's stream ------------------------------------------------------
 		template <int ARRAY>
-		__device__ __forceinline__ void stage_array(Ctx& cx, const int firstLayer, const int numLayers, int s, const int array1First)
+		__device__ __forceinline__ void stage_array(Ctx& cx, const int firstLayer, const int numLayers, int s, float (&headSum)[8])
 		{
 			typedef Cols<ARRAY> TC;
 			constexpr int C = TC::C, CG = C / 4;
+			constexpr bool kHeadInRegs = ARRAY == 2;   // standalone array-1 kernel: head sum (WaveNet.h:482) on the CUDA cores
 			const WnModelDev& M = *cx.M;
 			const int tid = cx.tid;
 			const uint32_t lanebase = cx.tmem + ((uint32_t)(cx.warp * 32) << 16);
@@ -555,7 +563,7 @@ namespace nab200
 					// copy the next layer's (or the next stream's first layer's) history while the accumulator load is in flight.
 					// (Tried: an L2 hint two layers ahead plus this copy after the hand-off below - no gain, the kernel is bound
 					// by issue slots under contention, not by this latency; tools/ts_timing.cu.)
-					prefetch_layer<0>(cx, l + 1, s, array1First);
+					prefetch_layer<0>(cx, l + 1, s);
 					wait_ld();
 					// z is the 1x1's A operand [hi | lo]; it is delivered in K-steps of 8 channels so that the issuer starts on the
 					// first while the second is still being activated
@@ -565,6 +573,12 @@ namespace nab200
 						uint32_t z[8], zl[8];
 #pragma unroll
 						for (int c = 0; c < 8; c += 2) fast_tanh2(dv[8 * h + c], dv[8 * h + c + 1], z[c], z[c + 1]);
+						if constexpr (kHeadInRegs)
+						{
+#pragma unroll
+							for (int c = 0; c < 8; c++) headSum[c] += __uint_as_float(z[c]);
+							if (li + 1 == numLayers) break;   // the last layer has no 1x1 (WaveNet.h:486): nothing to hand over
+						}
 #pragma unroll
 						for (int c = 0; c < 8; c += 2) split_lo2(z[c], z[c + 1], zl[c], zl[c + 1]);
 						tmem_st<8>(lanebase + TC::T0 + 8u * h, z);
@@ -572,7 +586,7 @@ namespace nab200
 						if (h + 1 < C / 8) stager_arrive(kBarZ0);
 					}
 				}
-				stager_arrive(kBarZ);
+				if (!(kHeadInRegs && li + 1 == numLayers)) stager_arrive(kBarZ);
 				TS_STAMP(8);
 			}
 		}
@@ -581,11 +595,12 @@ namespace nab200
 		// MMAs into one accumulator are always issued in the same order (undelayed tap, constant operand, tap 0, tap 1), so
 		// results do not depend on timing or on how a buffer is chunked into calls.
 		template <int ARRAY>
-		__device__ __forceinline__ void issue_array(Ctx& cx, const int firstLayer, const int numLayers, int s)
+		__device__ __forceinline__ void issue_array(Ctx& cx, const int firstLayer, const int numLayers)
 		{
 			typedef Cols<ARRAY> TC;
-			constexpr int C = TC::C, CG = C / 4, KS = C / 8, N1 = C + 8;
-			const WnModelDev& M = *cx.M;
+			constexpr int C = TC::C, CG = C / 4, KS = C / 8;
+			constexpr int N1P = C + 8;                      // rows per k group of the packed 1x1 | head operand
+			constexpr int N1 = ARRAY == 2 ? C : N1P;        // standalone array-1 kernel: 1x1 only, the head sum is in registers
 			const uint32_t tm = cx.tmem;
 			constexpr uint32_t idC = idesc_of(C), idN1 = idesc_of(N1);
 
@@ -658,15 +673,22 @@ namespace nab200
 				issuer_release(cx.barD, cx.dq & 1u, kBarDReady);
 				cx.dq++;
 				// the stagers saw the previous layer complete long ago: the other weight buffer is free for the next block
-				if (cx.el) issue_weights(cx, (l + 1 < M.numLayers) ? l + 1 : 0, cx.wq + 1);
+				if (cx.el) issue_weights(cx, (l + 1 < cx.lEnd) ? l + 1 : cx.lBegin, cx.wq + 1);
 				__syncwarp();
 				TS_STAMP(7);
 				// the next layer's weights are needed right behind the 1x1 (below); they were requested a whole layer ago
 				const bool more = li + 1 < numLayers;
 				if (more) mbar_wait(cx.barW0 + 8u * ((cx.wq + 1) & 1u), ((cx.wq + 1) >> 1) & 1u);
 
+				if (ARRAY == 2 && !more)
+				{
+					// standalone array-1 kernel, last layer: no 1x1, the stagers go straight to the output
+					TS_STAMP(8); TS_STAMP(9); TS_STAMP(10);
+					cx.wq++;
+					continue;
+				}
 				// ---- 1x1 + bias + residual, head sum (WaveNet.h:482-491): XR|HD += [Zhi|Zlo] [W1x1 | Whead], per K-step as z arrives ----
-				const u64 oHi = desc_at(wb16 + g4.z, N1), oLo = desc_at(wb16 + g4.w, N1);
+				const u64 oHi = desc_at(wb16 + g4.z, N1P), oLo = desc_at(wb16 + g4.w, N1P);
 #pragma unroll
 				for (int ks = 0; ks < KS; ks++)
 				{
@@ -674,8 +696,8 @@ namespace nab200
 					if (ks == 0) TS_STAMP(8);
 					if (cx.el)
 					{
-						const u64 boff = (u64)(2 * ks * N1);
-						if (ks == 0) mma_ts<1>(tm + TC::XR, tm + kConst, desc_at(wb16 + oneC16, N1), idN1);
+						const u64 boff = (u64)(2 * ks * N1P);
+						if (ks == 0) mma_ts<1>(tm + TC::XR, tm + kConst, desc_at(wb16 + oneC16, N1P), idN1);
 						mma_ts<1>(tm + TC::XR, tm + TC::T0 + 8u * ks, oHi + boff, idN1);
 						mma_ts<1>(tm + TC::XR, tm + TC::T0 + C + 8u * ks, oHi + boff, idN1);
 						mma_ts<1>(tm + TC::XR, tm + TC::T0 + 8u * ks, oLo + boff, idN1);
@@ -713,20 +735,32 @@ namespace nab200
 		constexpr int kTableBytes = kMaxLayers * (int)sizeof(TsLayer);
 		constexpr int kNumBars = 4;
 
-		__host__ __device__ constexpr size_t smem_fixed_bytes() { return (size_t)4 * kRows * 16 + (size_t)4 * kWbRows * 16; }
+		// shared-memory windows: XE = [planes][kRows][4] floats then WB = [planes][kWbRows][4]; 4 planes when the kernel runs the
+		// 16-channel array, 2 for the standalone 8-channel kernel
+		__host__ __device__ constexpr size_t smem_fixed_bytes(int planes) { return (size_t)planes * kRows * 16 + (size_t)planes * kWbRows * 16; }
 
-		__global__ void __launch_bounds__(kThreads, 4)
+		constexpr int kScratchFloats = 6 * kCur * 4;   // split launch: per stream [6][128][4] = array 0's output (16) | head output (8) per frame
+
+		// MODE 0: both arrays in one kernel.  MODE 1 / 2: array 0 / array 1 only (split launch): array 0's per-frame output and
+		// head output travel through a scratch buffer; the 8-channel kernel needs 64 TMEM columns, 64 registers and a third of
+		// the shared memory, so 6 of its CTAs fit on an SM instead of 4 - the per-stream dependency chain, not bandwidth, is
+		// what binds, and the chain of the 8-channel layers is as long as that of the 16-channel ones.
+		template <int MODE>
+		__global__ void __launch_bounds__(kThreads, MODE == 2 ? 6 : 4)
 			wavenet_ts_kernel(const __grid_constant__ WnModelDev M, const float* __restrict__ Wg, float* __restrict__ state, int* __restrict__ heads,
-				const float* in, float* out, long long inSS, long long inFS, long long outSS, long long outFS, int S, int n)
+				const float* in, float* out, long long inSS, long long inFS, long long outSS, long long outFS, int S, int n,
+				float* __restrict__ scratch, int wbufFloats)
 		{
+			constexpr int kPlanes = MODE == 2 ? 2 : 4;
+			constexpr uint32_t kTmem = MODE == 2 ? 64 : 128;
 			extern __shared__ __align__(128) unsigned char smem[];
 			Ctx cx;
 			cx.M = &M;
 			cx.Wg = Wg;
 			cx.xe = smem_u32(smem);
-			cx.wbuf = cx.xe + (uint32_t)smem_fixed_bytes();
-			cx.wbufStride = (uint32_t)M.maxBlock * 4u;
-			TsLayer* Ls = reinterpret_cast<TsLayer*>(smem + smem_fixed_bytes() + (size_t)2 * M.maxBlock * 4);
+			cx.wbuf = cx.xe + (uint32_t)smem_fixed_bytes(kPlanes);
+			cx.wbufStride = (uint32_t)wbufFloats * 4u;
+			TsLayer* Ls = reinterpret_cast<TsLayer*>(smem + smem_fixed_bytes(kPlanes) + (size_t)2 * wbufFloats * 4);
 			cx.Ls = Ls;
 			cx.lsAddr = smem_u32(Ls);
 			cx.hdb = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(Ls) + kTableBytes);
@@ -747,6 +781,12 @@ namespace nab200
 			const int tid = threadIdx.x;
 			const int warp = cx.warp, lane = cx.lane;
 			const bool stager = warp < 4;
+			const int first0 = M.arrays[0].firstLayer, num0 = M.arrays[0].numLayers;
+			const int first1 = M.arrays[1].firstLayer, num1 = M.arrays[1].numLayers;
+			cx.a1First = first1;
+			cx.lBegin = MODE == 2 ? first1 : first0;
+			cx.lEnd = MODE == 1 ? first0 + num0 : first1 + num1;
+			(void)lane;
 
 			// per-layer plan
 			if (tid < M.numLayers)
@@ -756,8 +796,9 @@ namespace nab200
 				const int C = M.arrays[W.array].C;
 				const int D0 = 2 * W.d, D1 = W.d;
 				const bool pure0 = D0 >= kCur, pure1 = D1 >= kCur;
-				if (pure1) { T.tap0Off = 0; T.tap0Stride = kRows * 16; T.tap1Off = kWbOff; T.tap1Stride = kWbRows * 16; }
-				else if (pure0) { T.tap0Off = kWbOff; T.tap0Stride = kWbRows * 16; T.tap1Off = (uint32_t)(kCur - D1) * 16u; T.tap1Stride = kRows * 16; }
+				constexpr uint32_t wbOff = (uint32_t)kPlanes * kRows * 16;   // WB relative to XE, bytes
+				if (pure1) { T.tap0Off = 0; T.tap0Stride = kRows * 16; T.tap1Off = wbOff; T.tap1Stride = kWbRows * 16; }
+				else if (pure0) { T.tap0Off = wbOff; T.tap0Stride = kWbRows * 16; T.tap1Off = (uint32_t)(kCur - D1) * 16u; T.tap1Stride = kRows * 16; }
 				else { T.tap0Off = (uint32_t)(kCur - D0) * 16u; T.tap0Stride = kRows * 16; T.tap1Off = (uint32_t)(kCur - D1) * 16u; T.tap1Stride = kRows * 16; }
 				T.mixed = pure1 ? 0 : 1;
 				T.d = W.d; T.Lp = W.Lp; T.ringOff = W.ringOff; T.ringIdx = W.ringIdx;
@@ -782,7 +823,7 @@ namespace nab200
 			}
 			if (warp == 4)
 			{
-				asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(smem_u32(tmemSlot)) : "memory");
+				asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmemSlot)), "n"(kTmem) : "memory");
 				asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
 			}
 			const int s0 = blockIdx.x;
@@ -800,8 +841,6 @@ namespace nab200
 			fence_after();
 			cx.tmem = *tmemSlot;
 			const uint32_t tm = cx.tmem;
-			const int first0 = M.arrays[0].firstLayer, num0 = M.arrays[0].numLayers;
-			const int first1 = M.arrays[1].firstLayer, num1 = M.arrays[1].numLayers;
 
 			if (!stager)
 			{
@@ -810,7 +849,7 @@ namespace nab200
 				const uint32_t re0 = (uint32_t)M.layers[first0].oRe >> 2, hd0 = (uint32_t)M.layers[first0].oHeadB >> 2;
 				const uint32_t re1 = (uint32_t)M.layers[first1].oRe >> 2, re1Lo = (uint32_t)M.layers[first1].oMix >> 2;
 				const uint32_t ch1 = (uint32_t)M.layers[first1].oHeadW >> 2, hd1 = (uint32_t)M.layers[first1].oHeadB >> 2;
-				if (cx.el) issue_weights(cx, 0, 0);
+				if (cx.el) issue_weights(cx, cx.lBegin, 0);
 				for (int s = s0; s < S; s += gridDim.x)
 				{
 #ifdef NAB_TS_TIMING
@@ -821,45 +860,73 @@ namespace nab200
 						cx.stampCta = c < 0 ? 0 : c; cx.stampStream = k - 1;
 					}
 #endif
-					// ---- entry: rechannel 1 -> C0 and head bias from the constant operand ----
-					mbar_wait(cx.barW0 + 8u * (cx.wq & 1u), (cx.wq >> 1) & 1u);
-					issuer_sync(kBarE);
-					if (cx.el)
+					if constexpr (MODE != 2)
 					{
-						const uint32_t wb16 = (cx.wbuf + (cx.wq & 1u) * cx.wbufStride) >> 4;
-						mma_ts<0>(tm + Cols<0>::XR, tm + kConst, desc_at(wb16 + re0, 16), idesc_of(16));
-						mma_ts<0>(tm + Cols<0>::HD, tm + kConst, desc_at(wb16 + hd0, 8), idesc_of(8));
-						mma_commit(cx.barX);
+						// ---- entry: rechannel 1 -> C0 and head bias from the constant operand ----
+						mbar_wait(cx.barW0 + 8u * (cx.wq & 1u), (cx.wq >> 1) & 1u);
+						issuer_sync(kBarE);
+						if (cx.el)
+						{
+							const uint32_t wb16 = (cx.wbuf + (cx.wq & 1u) * cx.wbufStride) >> 4;
+							mma_ts<0>(tm + Cols<0>::XR, tm + kConst, desc_at(wb16 + re0, 16), idesc_of(16));
+							mma_ts<0>(tm + Cols<0>::HD, tm + kConst, desc_at(wb16 + hd0, 8), idesc_of(8));
+							mma_commit(cx.barX);
+						}
+						__syncwarp();
+						issuer_release(cx.barX, cx.xq & 1u, kBarXReady);
+						cx.xq++;
+						issue_array<0>(cx, first0, num0);
 					}
-					__syncwarp();
-					issuer_release(cx.barX, cx.xq & 1u, kBarXReady);
-					cx.xq++;
-					issue_array<0>(cx, first0, num0, s);
-
-					// ---- array transition (WaveNet.h:785-789): rechannel C0 -> C1 of the array output, head carry ----
-					mbar_wait(cx.barW0 + 8u * (cx.wq & 1u), (cx.wq >> 1) & 1u);
-					issuer_sync(kBarE);
-					if (cx.el)
+					if constexpr (MODE == 0)
 					{
-						const uint32_t wb16 = (cx.wbuf + (cx.wq & 1u) * cx.wbufStride) >> 4;
-						const u64 dHi = desc_at(wb16 + re1, 8), dLo = desc_at(wb16 + re1Lo, 8);
-						mma_ts<0>(tm + Cols<1>::XR, tm + Cols<0>::XR, dHi, idesc_of(8));
-						mma_ts<1>(tm + Cols<1>::XR, tm + Cols<0>::T2L, dHi, idesc_of(8));
-						mma_ts<1>(tm + Cols<1>::XR, tm + Cols<0>::XR, dLo, idesc_of(8));
-						mma_ts<1>(tm + Cols<1>::XR, tm + Cols<0>::XR + 8u, dHi + 16u, idesc_of(8));
-						mma_ts<1>(tm + Cols<1>::XR, tm + Cols<0>::T2L + 8u, dHi + 16u, idesc_of(8));
-						mma_ts<1>(tm + Cols<1>::XR, tm + Cols<0>::XR + 8u, dLo + 16u, idesc_of(8));
-						const u64 cHi = desc_at(wb16 + ch1, 8), cLo = desc_at(wb16 + ch1 + 16u, 8);
-						mma_ts<0>(tm + Cols<1>::HD, tm + Cols<0>::HD, cHi, idesc_of(8));
-						mma_ts<1>(tm + Cols<1>::HD, tm + kHdLo, cHi, idesc_of(8));
-						mma_ts<1>(tm + Cols<1>::HD, tm + Cols<0>::HD, cLo, idesc_of(8));
-						mma_ts<1>(tm + Cols<1>::HD, tm + kConst, desc_at(wb16 + hd1, 8), idesc_of(8));
-						mma_commit(cx.barX);
+						// ---- array transition (WaveNet.h:785-789): rechannel C0 -> C1 of the array output, head carry ----
+						mbar_wait(cx.barW0 + 8u * (cx.wq & 1u), (cx.wq >> 1) & 1u);
+						issuer_sync(kBarE);
+						if (cx.el)
+						{
+							const uint32_t wb16 = (cx.wbuf + (cx.wq & 1u) * cx.wbufStride) >> 4;
+							const u64 dHi = desc_at(wb16 + re1, 8), dLo = desc_at(wb16 + re1Lo, 8);
+							mma_ts<0>(tm + Cols<1>::XR, tm + Cols<0>::XR, dHi, idesc_of(8));
+							mma_ts<1>(tm + Cols<1>::XR, tm + Cols<0>::T2L, dHi, idesc_of(8));
+							mma_ts<1>(tm + Cols<1>::XR, tm + Cols<0>::XR, dLo, idesc_of(8));
+							mma_ts<1>(tm + Cols<1>::XR, tm + Cols<0>::XR + 8u, dHi + 16u, idesc_of(8));
+							mma_ts<1>(tm + Cols<1>::XR, tm + Cols<0>::T2L + 8u, dHi + 16u, idesc_of(8));
+							mma_ts<1>(tm + Cols<1>::XR, tm + Cols<0>::XR + 8u, dLo + 16u, idesc_of(8));
+							const u64 cHi = desc_at(wb16 + ch1, 8), cLo = desc_at(wb16 + ch1 + 16u, 8);
+							mma_ts<0>(tm + Cols<1>::HD, tm + Cols<0>::HD, cHi, idesc_of(8));
+							mma_ts<1>(tm + Cols<1>::HD, tm + kHdLo, cHi, idesc_of(8));
+							mma_ts<1>(tm + Cols<1>::HD, tm + Cols<0>::HD, cLo, idesc_of(8));
+							mma_ts<1>(tm + Cols<1>::HD, tm + kConst, desc_at(wb16 + hd1, 8), idesc_of(8));
+							mma_commit(cx.barX);
+						}
+						__syncwarp();
+						issuer_release(cx.barX, cx.xq & 1u, kBarXReady);
+						cx.xq++;
+						issue_array<1>(cx, first1, num1);
 					}
-					__syncwarp();
-					issuer_release(cx.barX, cx.xq & 1u, kBarXReady);
-					cx.xq++;
-					issue_array<1>(cx, first1, num1, s);
+					if constexpr (MODE == 2)
+					{
+						// ---- entry: rechannel C0 -> C1 of array 0's output, staged [hi 16 | lo 16] at the tap columns ----
+						mbar_wait(cx.barW0 + 8u * (cx.wq & 1u), (cx.wq >> 1) & 1u);
+						issuer_sync(kBarE);
+						if (cx.el)
+						{
+							const uint32_t wb16 = (cx.wbuf + (cx.wq & 1u) * cx.wbufStride) >> 4;
+							const u64 dHi = desc_at(wb16 + re1, 8), dLo = desc_at(wb16 + re1Lo, 8);
+							constexpr uint32_t XH = Cols<2>::T0, XL = Cols<2>::T0 + 16;
+							mma_ts<0>(tm + Cols<2>::XR, tm + XH, dHi, idesc_of(8));
+							mma_ts<1>(tm + Cols<2>::XR, tm + XL, dHi, idesc_of(8));
+							mma_ts<1>(tm + Cols<2>::XR, tm + XH, dLo, idesc_of(8));
+							mma_ts<1>(tm + Cols<2>::XR, tm + XH + 8u, dHi + 16u, idesc_of(8));
+							mma_ts<1>(tm + Cols<2>::XR, tm + XL + 8u, dHi + 16u, idesc_of(8));
+							mma_ts<1>(tm + Cols<2>::XR, tm + XH + 8u, dLo + 16u, idesc_of(8));
+							mma_commit(cx.barX);
+						}
+						__syncwarp();
+						issuer_release(cx.barX, cx.xq & 1u, kBarXReady);
+						cx.xq++;
+						issue_array<2>(cx, first1, num1);
+					}
 					cx.cur ^= 1;
 				}
 				// drain the weight prefetch that ran ahead of the last layer
@@ -873,8 +940,10 @@ namespace nab200
 				if (tid < n && s0 < S) cond = in[(long long)s0 * inSS + (long long)tid * inFS];
 				if (s0 < S)
 				{
-					prefetch_windows<4, 0>(cx, 0, s0, cx.hdb);
+					if (MODE == 2) prefetch_windows<2, 0>(cx, cx.lBegin, s0, cx.hdb);
+					else prefetch_windows<4, 0>(cx, cx.lBegin, s0, cx.hdb);
 				}
+				float headSum[8];
 				for (int s = s0; s < S; s += gridDim.x)
 				{
 					const int sn = s + gridDim.x;
@@ -892,6 +961,8 @@ namespace nab200
 							hdNext[36 + tid] = hn;
 						}
 						if (tid < n) condNext = in[(long long)sn * inSS + (long long)tid * inFS];
+						// the next stream's scratch rows -> L2 (they were written by the previous kernel, possibly evicted since)
+						if (MODE == 2 && tid < 96) l2_prefetch(scratch + (size_t)sn * kScratchFloats + (size_t)tid * 32);
 					}
 #ifdef NAB_TS_TIMING
 					{
@@ -910,34 +981,80 @@ namespace nab200
 						cv[3] = 0x3F800000u; cv[4] = 0x3F800000u; cv[5] = 0x3F800000u; cv[6] = 0u; cv[7] = 0u;
 						tmem_st<8>(lanebase + kConst, cv);
 					}
-					stager_arrive(kBarE);
-					stage_array<0>(cx, first0, num0, s, first1);
-
-					// ---- array transition: low parts of the array output and of the head output ----
-					stager_wait(kBarXReady);
+					if constexpr (MODE == 2)
 					{
-						uint32_t x[16], xl[16];
+						// array 0's output of this frame -> [hi 16 | lo 16] at the tap columns (the rechannel's A operand); its head
+						// output starts this array's head sum (WaveNet.h:785-788)
+						const uint4* sc = reinterpret_cast<const uint4*>(scratch + (size_t)s * kScratchFloats) + tid;
+						uint32_t v[32];
+#pragma unroll
+						for (int q = 0; q < 4; q++)
+						{
+							const uint4 a = sc[q * kCur];
+							v[4 * q + 0] = a.x; v[4 * q + 1] = a.y; v[4 * q + 2] = a.z; v[4 * q + 3] = a.w;
+						}
+#pragma unroll
+						for (int c = 0; c < 16; c += 2) split_lo2(v[c], v[c + 1], v[16 + c], v[16 + c + 1]);
+						tmem_st<32>(lanebase + Cols<2>::T0, v);
+						const uint4 h0 = sc[4 * kCur], h1 = sc[5 * kCur];
+						headSum[0] = __uint_as_float(h0.x); headSum[1] = __uint_as_float(h0.y); headSum[2] = __uint_as_float(h0.z); headSum[3] = __uint_as_float(h0.w);
+						headSum[4] = __uint_as_float(h1.x); headSum[5] = __uint_as_float(h1.y); headSum[6] = __uint_as_float(h1.z); headSum[7] = __uint_as_float(h1.w);
+					}
+					stager_arrive(kBarE);
+					if constexpr (MODE != 2) stage_array<0>(cx, first0, num0, s, headSum);
+
+					if constexpr (MODE == 0)
+					{
+						// ---- array transition: low parts of the array output and of the head output ----
+						stager_wait(kBarXReady);
+						{
+							uint32_t x[16], xl[16];
+							tmem_ld<16>(lanebase + Cols<0>::XR, x);
+#pragma unroll
+							for (int c = 0; c < 16; c += 2) split_lo2(x[c], x[c + 1], xl[c], xl[c + 1]);
+							tmem_st<16>(lanebase + Cols<0>::T2L, xl);
+							uint32_t h[8], hl[8];
+							tmem_ld<8>(lanebase + Cols<0>::HD, h);
+#pragma unroll
+							for (int c = 0; c < 8; c += 2) split_lo2(h[c], h[c + 1], hl[c], hl[c + 1]);
+							tmem_st<8>(lanebase + kHdLo, hl);
+						}
+						stager_arrive(kBarE);
+						stage_array<1>(cx, first1, num1, s, headSum);
+
+						// ---- output (WaveNet.h:793-798) ----
+						stager_wait(kBarXReady);
+						{
+							uint32_t h[8];
+							tmem_ld<8>(lanebase + Cols<1>::HD, h);
+							if (tid < n) out[(long long)s * outSS + (long long)tid * outFS] = M.headScale * __uint_as_float(h[0]);
+						}
+					}
+					if constexpr (MODE == 1)
+					{
+						// ---- array 0's output and head output of this frame -> scratch, for the array-1 kernel ----
+						stager_wait(kBarXReady);
+						uint32_t x[16], h[8];
 						tmem_ld<16>(lanebase + Cols<0>::XR, x);
-#pragma unroll
-						for (int c = 0; c < 16; c += 2) split_lo2(x[c], x[c + 1], xl[c], xl[c + 1]);
-						tmem_st<16>(lanebase + Cols<0>::T2L, xl);
-						uint32_t h[8], hl[8];
 						tmem_ld<8>(lanebase + Cols<0>::HD, h);
+						uint4* sc = reinterpret_cast<uint4*>(scratch + (size_t)s * kScratchFloats) + tid;
 #pragma unroll
-						for (int c = 0; c < 8; c += 2) split_lo2(h[c], h[c + 1], hl[c], hl[c + 1]);
-						tmem_st<8>(lanebase + kHdLo, hl);
+						for (int q = 0; q < 4; q++) sc[q * kCur] = make_uint4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
+						sc[4 * kCur] = make_uint4(h[0], h[1], h[2], h[3]);
+						sc[5 * kCur] = make_uint4(h[4], h[5], h[6], h[7]);
 					}
-					stager_arrive(kBarE);
-					stage_array<1>(cx, first1, num1, s, first1);
-
-					// ---- output (WaveNet.h:793-798) ----
-					stager_wait(kBarXReady);
+					if constexpr (MODE == 2)
 					{
-						uint32_t h[8];
-						tmem_ld<8>(lanebase + Cols<1>::HD, h);
-						if (tid < n) out[(long long)s * outSS + (long long)tid * outFS] = M.headScale * __uint_as_float(h[0]);
+						stage_array<2>(cx, first1, num1, s, headSum);
+						// ---- output (WaveNet.h:658-660, 793-798): head conv of the summed head, on the CUDA cores ----
+						const float* __restrict__ hv = Wg + M.arrays[1].headRingOff;   // tc == 2 packing: plain head weights [8] | bias
+						float acc = __ldg(hv + 8);
+#pragma unroll
+						for (int c = 0; c < 8; c++) acc = fmaf(__ldg(hv + c), headSum[c], acc);
+						if (tid < n) out[(long long)s * outSS + (long long)tid * outFS] = M.headScale * acc;
 					}
-					if (tid < M.numRings) heads[(size_t)s * M.numRings + tid] = cx.hdb[cx.cur * kHdbHalf + 36 + tid];
+					// ring heads of the layers this kernel ran (ring index == layer index in this packing)
+					if (tid >= cx.lBegin && tid < cx.lEnd) heads[(size_t)s * M.numRings + tid] = cx.hdb[cx.cur * kHdbHalf + 36 + tid];
 					cx.cur ^= 1;
 					cond = condNext;
 					// a thread's TMEM reads above complete before its own stores of the next stream's entry; hdb slots are
@@ -947,7 +1064,7 @@ namespace nab200
 
 			fence_before();
 			__syncthreads();
-			if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(cx.tmem) : "memory");
+			if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(cx.tmem), "n"(kTmem) : "memory");
 		}
 	}
 
@@ -956,18 +1073,40 @@ namespace nab200
 		return C0 == 16 && C1 == 8 && act == 0;
 	}
 
+	size_t wavenet_ts_scratch_floats_per_stream() { return ts::kScratchFloats; }
+
+	template <int MODE>
+	static cudaError_t ts_launch_mode(const WnModelDev& M, const WnLaunch& a, int wbufFloats, int ctasPerSM)
+	{
+		auto kfn = ts::wavenet_ts_kernel<MODE>;
+		const size_t smem = ts::smem_fixed_bytes(MODE == 2 ? 2 : 4) + (size_t)2 * wbufFloats * 4 + ts::kTableBytes + 2 * ts::kHdbHalf * 4 + ts::kNumBars * 8 + 16;
+		cudaError_t err = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		if (err != cudaSuccess) return err;
+		int grid = a.numSMs * ctasPerSM;
+		if (grid > a.S) grid = a.S;
+		if (grid < 1) grid = 1;
+		kfn<<<grid, ts::kThreads, smem, a.stream>>>(M, a.weights, a.state, a.heads, a.in, a.out, a.inSS, a.inFS, a.outSS, a.outFS, a.S, a.n,
+			a.scratch, wbufFloats);
+		return cudaGetLastError();
+	}
+
 	cudaError_t wavenet_ts_launch(const WnModelDev& M, const WnLaunch& a)
 	{
 		if (!wavenet_ts_variant_supported(M.arrays[0].C, M.numArrays > 1 ? M.arrays[1].C : 0, M.arrays[0].act)) return cudaErrorNotSupported;
 		if (a.n > ts::kCur) return cudaErrorInvalidValue;
-		auto kfn = ts::wavenet_ts_kernel;
-		const size_t smem = ts::smem_fixed_bytes() + (size_t)2 * M.maxBlock * 4 + ts::kTableBytes + 2 * ts::kHdbHalf * 4 + ts::kNumBars * 8 + 16;
-		cudaError_t err = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-		if (err != cudaSuccess) return err;
-		int grid = a.numSMs * 4;
-		if (grid > a.S) grid = a.S;
-		if (grid < 1) grid = 1;
-		kfn<<<grid, ts::kThreads, smem, a.stream>>>(M, a.weights, a.state, a.heads, a.in, a.out, a.inSS, a.inFS, a.outSS, a.outFS, a.S, a.n);
-		return cudaGetLastError();
+		if (a.tsSplit && a.scratch)
+		{
+			// two launches: the 16-channel array, then the 8-channel one with more CTAs per SM
+			int w0 = 0, w1 = 0;
+			for (int l = 0; l < M.numLayers; l++)
+			{
+				int& w = M.layers[l].array == 0 ? w0 : w1;
+				if (M.layers[l].wSize > w) w = M.layers[l].wSize;
+			}
+			cudaError_t err = ts_launch_mode<1>(M, a, w0, 4);
+			if (err != cudaSuccess) return err;
+			return ts_launch_mode<2>(M, a, w1, 6);
+		}
+		return ts_launch_mode<0>(M, a, M.maxBlock, 4);
 	}
 }

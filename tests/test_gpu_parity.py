@@ -290,6 +290,29 @@ def test_runtime_shaped_kernel(na, O, name, tmp_path):
         assert float(np.abs(ys - outs[0][:, s, :].reshape(-1)).max()) <= WAVENET_TOL
 
 
+def test_split_launch_matches_fused(na, O, tmp_path):
+    """The TS kernel's split form (one launch per layer array, hand-over through a scratch buffer, head sum in registers)
+    computes the same path as the fused kernel."""
+    g = load_golden(golden_files("syn_a1_standard")[0])
+    mf = model_file_for(g, tmp_path)
+    S, n, calls = 20, 128, 9
+    x = np.random.default_rng(31).uniform(-1, 1, (calls, S, n)).astype(np.float32)
+    outs = []
+    for split in (1, 0):
+        prev = na.set_option("ts_split", split)
+        try:
+            m = _load(na, mf, streams=S)
+            y = np.empty_like(x)
+            for k in range(calls):
+                m.ProcessBatch(x[k], y[k], S, n)
+            outs.append(y)
+        finally:
+            na.set_option("ts_split", prev)
+    assert float(np.abs(outs[0] - outs[1]).max()) <= 2e-6
+    ys = O.PortModel.from_file(mf).process(np.ascontiguousarray(x[:, 3, :]).reshape(-1))
+    assert float(np.abs(ys - outs[0][:, 3, :].reshape(-1)).max()) <= WAVENET_TOL
+
+
 def test_full_size_config_properties(na, O, tmp_path):
     """BASELINE.json cfg 2 (A1 Standard, 4096 streams x 128 frames) at full size, through size-independent
     properties: identical inputs => bit-identical streams (independence + determinism), a tile of streams checked

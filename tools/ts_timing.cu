@@ -33,12 +33,15 @@ int main(int argc, char** argv)
 	if (alias) M.stateStride = 0;
 	cudaMalloc(&dHeads, (size_t)S * M.numRings * 4); cudaMemset(dHeads, 0, (size_t)S * M.numRings * 4);
 	cudaMalloc(&dIn, (size_t)S * n * 4); cudaMalloc(&dOut, (size_t)S * n * 4);
+	float* dScratch; cudaMalloc(&dScratch, (size_t)S * wavenet_ts_scratch_floats_per_stream() * 4);
+	const int split = argc > 3 ? atoi(argv[3]) : 1;
 	std::vector<float> hin((size_t)S * n);
 	for (auto& v : hin) v = 2.0f * rand() / RAND_MAX - 1.0f;
 	cudaMemcpy(dIn, hin.data(), hin.size() * 4, cudaMemcpyHostToDevice);
 	WnLaunch a;
 	a.weights = dW; a.state = dState; a.heads = dHeads; a.in = dIn; a.out = dOut;
 	a.inSS = n; a.inFS = 1; a.outSS = n; a.outFS = 1; a.S = S; a.n = n; a.numSMs = 148; a.useTma = true; a.stream = 0;
+	a.tsSplit = split; a.scratch = dScratch;
 	cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
 	for (int it = 0; it < 5; it++)
 	{
