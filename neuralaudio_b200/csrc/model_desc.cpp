@@ -642,8 +642,6 @@ namespace nab200
 		const float* w = desc.weights.data();
 		int layerIdx = 0, ringIdx = 0, ringOff = 0;
 		int prevCP = 1;
-		const float* prevHeadW = nullptr;   // unused; the carry uses THIS array's head conv
-		(void)prevHeadW;
 		for (int a = 0; a < M.numArrays; a++)
 		{
 			const WaveNetArrayDesc& A = desc.arrays[a];

@@ -30,7 +30,7 @@ namespace nab200
 		constexpr int kCur = 128;       // first row of the current frames
 		constexpr int kWbRows = 128;    // rows per plane of the second tap-window buffer
 		constexpr int kIssuers = 3;     // MMA-issuing threads (lane 0 of warps 0..2), one TMEM accumulator each
-		constexpr int kTmemCols = 128;  // D0[3] | D1[3] | Zhi | Zlo, 16 columns each
+		// TMEM: 128 columns = D0[3] | D1[3] | Zhi | Zlo, 16 columns each
 
 		__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 

@@ -34,7 +34,6 @@ namespace nab200
 		constexpr int kRows = 256;      // rows per XE plane: [0,128) history, [128,256) current frames
 		constexpr int kCur = 128;
 		constexpr int kWbRows = 128;    // rows per plane of the second window buffer
-		constexpr int kTmemCols = 128;
 		typedef unsigned long long u64;
 
 		// TMEM column maps.  Array 0 (16 channels) and array 1 (8 channels); array 1 lives in columns array 0 no longer needs.
@@ -285,7 +284,6 @@ namespace nab200
 		// tcgen05.commit (the only try_wait loops of the kernel, one warp, short waits) and the issuer then releases the
 		// stagers through another named barrier they block on in hardware.  (With every warp polling mbarriers a third of
 		// the SM's issue slots went to try_wait loops - ncu, round 1.)
-		constexpr int kStagerThreads = 128;
 		constexpr int kThreads = 160;
 		enum : int
 		{
@@ -394,9 +392,9 @@ namespace nab200
 			const uint4 g1 = lds128(la + 16), j0 = lds128(la + 32), j1 = lds128(la + 48);
 			const int Lp = (int)g1.y;
 			const int head = hd[g1.w];
-			// 16-byte units from the stream's state base: one 64-bit multiply-add per copy
-			const uint4* base = reinterpret_cast<const uint4*>(cx.state + (size_t)s * cx.M->stateStride);
-			const int ring16 = (int)g1.z >> 2;
+			// byte pointer to this layer's ring; one 64-bit add per further channel group
+			const char* ring = reinterpret_cast<const char*>(cx.state + (size_t)s * cx.M->stateStride + (int)g1.z);
+			const size_t step = (size_t)Lp * 16;
 			const uint32_t dstRow = cx.xe + (uint32_t)u * 16u;
 			{
 				const int cnt = (int)j0.x < 0 ? cx.n : (int)j0.x;
@@ -404,12 +402,13 @@ namespace nab200
 				{
 					int idx = head - (int)j0.y + u;
 					if (idx < 0) idx += Lp;
-					idx += ring16;
+					const char* src = ring + (size_t)idx * 16;
+					uint32_t dst = dstRow + j0.z;
 #pragma unroll
-					for (int g = 0; g < CG; g++)
+					for (int g = 0; g < CG; g++, src += step, dst += j0.w)
 					{
-						if (MODE == 0) cp_async16(dstRow + j0.z + (uint32_t)g * j0.w, base + (idx + g * Lp));
-						else l2_prefetch(base + (idx + g * Lp));
+						if (MODE == 0) cp_async16(dst, src);
+						else l2_prefetch(src);
 					}
 				}
 			}
@@ -419,12 +418,13 @@ namespace nab200
 				{
 					int idx = head - (int)j1.y + u;
 					if (idx < 0) idx += Lp;
-					idx += ring16;
+					const char* src = ring + (size_t)idx * 16;
+					uint32_t dst = dstRow + j1.z;
 #pragma unroll
-					for (int g = 0; g < CG; g++)
+					for (int g = 0; g < CG; g++, src += step, dst += j1.w)
 					{
-						if (MODE == 0) cp_async16(dstRow + j1.z + (uint32_t)g * j1.w, base + (idx + g * Lp));
-						else l2_prefetch(base + (idx + g * Lp));
+						if (MODE == 0) cp_async16(dst, src);
+						else l2_prefetch(src);
 					}
 				}
 			}
@@ -537,10 +537,10 @@ namespace nab200
 						// (head + t) mod Lp without a division: head + first is hdb's "head after the call" when n > Lp
 						int idx = (cx.n > Lp ? hd[36 + g1.w] : hd[g1.w]) + (tid - first);
 						if (idx >= Lp) idx -= Lp;
-						idx += (int)g1.z >> 2;
-						uint4* base = reinterpret_cast<uint4*>(st);
+						char* dst = reinterpret_cast<char*>(st + (int)g1.z) + (size_t)idx * 16;
+						const size_t step = (size_t)Lp * 16;
 #pragma unroll
-						for (int q = 0; q < CG; q++) base[idx + q * Lp] = make_uint4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
+						for (int q = 0; q < CG; q++, dst += step) *reinterpret_cast<uint4*>(dst) = make_uint4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
 					}
 				}
 
