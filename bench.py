@@ -114,7 +114,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -266,7 +266,6 @@ def run_b200(args, rank, local_rank, world):
     e1.record(stream)
     e1.synchronize()
     barrier()
-    clocks = sampler.stop()
     dev_ms = e0.elapsed_time(e1)
     launches_per_step = 1 if args.workload.startswith("lstm") else -(-frames // (256 if args.workload in ("a2_full", "a1_nano") else 128))
     if args.workload == "a1_standard" and os.environ.get("NAB200_USE_TC", "2") == "2" and os.environ.get("NAB200_TS_SPLIT", "0") != "0":
@@ -304,6 +303,7 @@ def run_b200(args, rank, local_rank, world):
     checksum += float(yh[(args.steps - 1) % 3][0, 0])
     e2e_s = time.perf_counter() - t0
     barrier()
+    clocks = sampler.stop()   # sampled every 20 ms from the start of the device-timed loop to the end of the end-to-end loops
 
     times = torch.tensor([dev_ms, e2e_s * 1e3, e2e_blocking_s * 1e3], dtype=torch.float64, device=dev)
     if dist is not None:
