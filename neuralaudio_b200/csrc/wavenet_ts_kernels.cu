@@ -212,6 +212,34 @@ namespace nab200
 			return d;
 		}
 
+		// Where the low part of the 3xTF32 split is computed.  true: ON THE TENSOR CORE - the stagers store the raw fp32 value
+		// twice, as the high operand and as the initial content of the low operand's columns, and the issuer runs one K = 8,
+		// N = 8 MMA per 8 channels with B = -I that accumulates into the low columns: lo = x + trunc(x) * (-1) = x - trunc(x),
+		// exact (the tensor core truncates its A operand to tf32 by itself; one product per output, same exponent as x).  That
+		// removes every split instruction from the CUDA cores (they were 41 % of the stagers' arithmetic instructions).
+		// false: on the CUDA cores (one LOP3 per value + one packed FFMA2 per pair, split_lo2 below).
+		// MEASURED (tools/tc_split_probe.cu, B200): the primitive is exact, but an MMA that reads as its A operand the columns the
+		// previous MMA accumulated into does NOT wait for that write (wrong results unless ~3 independent MMAs sit in between),
+		// so it needs a commit + wait per operand - and even without that wait the kernel was no faster (209.5 us): the
+		// stagers' arithmetic is not what bounds it.  Off by default; NAB_TCSPLIT is a bit mask of operand classes.
+#ifndef NAB_TCSPLIT
+#define NAB_TCSPLIT 0
+#endif
+		constexpr bool kSplitOnTensorCore = (NAB_TCSPLIT & 1) != 0;   // delayed taps
+		constexpr bool kSplitT2L = (NAB_TCSPLIT & 2) != 0;            // undelayed tap (residual accumulator)
+		constexpr bool kSplitZ = (NAB_TCSPLIT & 4) != 0;              // activated output
+		constexpr bool kSplitEntry = (NAB_TCSPLIT & 8) != 0;          // array transition / entry operands
+
+		// How many hand-offs a layer makes.  1: one per MMA phase (conv operands complete -> conv; activated output complete ->
+		// 1x1).  0: operands are handed over piecewise (low part of the undelayed tap, tap 0, tap 1; z per K-step) so that the
+		// issuer overlaps MMA issue with staging.  Measured: 221 us with one hand-off per phase vs 208 us piecewise, although
+		// issuing only a quarter of the MMAs, or taking the split arithmetic off the stagers, leaves the time unchanged
+		// (tools/ts_timing.cu ablations): what counts is how much issue time lands behind the last hand-off of a phase.
+#ifndef NAB_TS_FEW_HANDOFFS
+#define NAB_TS_FEW_HANDOFFS 0
+#endif
+		constexpr bool kFewHandoffs = NAB_TS_FEW_HANDOFFS != 0;
+
 		// Low parts of the 3xTF32 split for two values.  The tensor core truncates its fp32 inputs to tf32, so the high part is
 		// the raw value and lo = x - trunc(x).  lo is itself truncated to tf32 by the hardware, which would bias it toward
 		// zero; computing it as fma(trunc(x), -(1 - 2^-23), x) = lo + 2^-23 trunc(x) adds the mean truncation loss back
@@ -313,6 +341,7 @@ namespace nab200
 			// mbarriers: barD / barX tcgen05.commit of the conv / 1x1 MMAs (waited by the issuer only), barW0 (+8) weight buffers
 			uint32_t barW0, barD, barX;
 			uint32_t tmem;     // TMEM base (column 0, lane 0)
+			u64 negI;          // B operand -I (8 x 8, tf32) in shared memory: turns "x" columns into x - trunc(x)
 			float* state;
 			int n, tid, warp, lane, S, gstride;
 			bool el;           // this lane is its warp's elected lane
@@ -458,8 +487,16 @@ namespace nab200
 				const uint4 x = lds128(rowAddr + (uint32_t)q * planeStride);
 				v[4 * q + 0] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
 			}
+			if (kSplitOnTensorCore)
+			{
 #pragma unroll
-			for (int c = 0; c < C; c += 2) split_lo2(v[c], v[c + 1], v[C + c], v[C + c + 1]);
+				for (int c = 0; c < C; c++) v[C + c] = v[c];   // low columns start as x; the issuer's -I MMA turns them into x - trunc(x)
+			}
+			else
+			{
+#pragma unroll
+				for (int c = 0; c < C; c += 2) split_lo2(v[c], v[c + 1], v[C + c], v[C + c + 1]);
+			}
 			tmem_st<2 * C>(taddr, v);
 		}
 
@@ -500,13 +537,15 @@ namespace nab200
 #pragma unroll
 					for (int q = 0; q < CG; q++) sts128(cur + (uint32_t)q * (kRows * 16), x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
 				}
+				if (kSplitT2L) tmem_st<C>(lanebase + TC::T2L, x);
+				else
 				{
 					uint32_t xl[C];
 #pragma unroll
 					for (int c = 0; c < C; c += 2) split_lo2(x[c], x[c + 1], xl[c], xl[c + 1]);
 					tmem_st<C>(lanebase + TC::T2L, xl);
 				}
-				stager_arrive(kBarT2);
+				if (!kFewHandoffs) stager_arrive(kBarT2);
 				TS_STAMP(2);
 				// my copies of this layer's history window(s) have landed; where a tap mixes history and current frames the rows
 				// other threads copied / produced must be visible too (named barrier among the stagers)
@@ -516,7 +555,7 @@ namespace nab200
 				TS_STAMP(4);
 				const uint32_t row = cx.xe + (uint32_t)tid * 16u;
 				stage_tap<C>(row + g0.x, g0.y, lanebase + TC::T0);
-				stager_arrive(kBarT0);
+				if (!kFewHandoffs) stager_arrive(kBarT0);
 				TS_STAMP(5);
 				stage_tap<C>(row + g0.z, g0.w, lanebase + TC::T1);
 				stager_arrive(kBarT1);
@@ -579,16 +618,33 @@ namespace nab200
 							for (int c = 0; c < 8; c++) headSum[c] += __uint_as_float(z[c]);
 							if (li + 1 == numLayers) break;   // the last layer has no 1x1 (WaveNet.h:486): nothing to hand over
 						}
+						if (kSplitZ)
+						{
+							tmem_st<8>(lanebase + TC::T0 + 8u * h, z);
+							tmem_st<8>(lanebase + TC::T0 + C + 8u * h, z);
+						}
+						else
+						{
 #pragma unroll
-						for (int c = 0; c < 8; c += 2) split_lo2(z[c], z[c + 1], zl[c], zl[c + 1]);
-						tmem_st<8>(lanebase + TC::T0 + 8u * h, z);
-						tmem_st<8>(lanebase + TC::T0 + C + 8u * h, zl);
-						if (h + 1 < C / 8) stager_arrive(kBarZ0);
+							for (int c = 0; c < 8; c += 2) split_lo2(z[c], z[c + 1], zl[c], zl[c + 1]);
+							tmem_st<8>(lanebase + TC::T0 + 8u * h, z);
+							tmem_st<8>(lanebase + TC::T0 + C + 8u * h, zl);
+						}
+						if (!kFewHandoffs && h + 1 < C / 8) stager_arrive(kBarZ0);
 					}
 				}
 				if (!(kHeadInRegs && li + 1 == numLayers)) stager_arrive(kBarZ);
 				TS_STAMP(8);
 			}
+		}
+
+		// issuer (elected lane): low columns L (initialised with x by the stagers) -= trunc(high columns H), 8 channels per MMA
+		template <int KS, bool ON>
+		__device__ __forceinline__ void split_on_tc(const Ctx& cx, uint32_t H, uint32_t L)
+		{
+			if (!ON) return;
+#pragma unroll
+			for (int ks = 0; ks < KS; ks++) mma_ts<1>(cx.tmem + L + 8u * ks, cx.tmem + H + 8u * ks, cx.negI, idesc_of(8));
 		}
 
 		// ---- issuer warp: one layer array of the CTA's stream --------------------------------------------------------
@@ -616,7 +672,8 @@ namespace nab200
 
 				// ---- dilated conv + mix-in + bias (WaveNet.h:250-289,471-476), operands as the stagers deliver them ----
 				TS_STAMP(0);
-				issuer_sync(kBarT2);
+				if (!kFewHandoffs) issuer_sync(kBarT2);
+				else issuer_sync(kBarT1);
 				TS_STAMP(1);
 				if (cx.el)
 				{
@@ -634,15 +691,17 @@ namespace nab200
 						}
 						mma_ts<1>(tm + TC::D, tm + kConst, desc_at(wb16 + g4.y, C), idC);
 					}
+					split_on_tc<KS, kSplitT2L>(cx, TC::XR, TC::T2L);
 #pragma unroll
 					for (int ks = 0; ks < KS; ks++) mma_ts<1>(tm + TC::D, tm + TC::T2L + 8u * ks, dHi + (u64)((2 * CG + 2 * ks) * C), idC);
 				}
 				__syncwarp();
 				TS_STAMP(2);
-				issuer_sync(kBarT0);
+				if (!kFewHandoffs) issuer_sync(kBarT0);
 				TS_STAMP(3);
 				if (cx.el)
 				{
+					split_on_tc<KS, kSplitOnTensorCore>(cx, TC::T0, TC::T0 + C);
 #pragma unroll
 					for (int ks = 0; ks < KS; ks++)
 					{
@@ -654,10 +713,11 @@ namespace nab200
 				}
 				__syncwarp();
 				TS_STAMP(4);
-				issuer_sync(kBarT1);
+				if (!kFewHandoffs) issuer_sync(kBarT1);
 				TS_STAMP(5);
 				if (cx.el)
 				{
+					split_on_tc<KS, kSplitOnTensorCore>(cx, TC::T1, TC::T1 + C);
 #pragma unroll
 					for (int ks = 0; ks < KS; ks++)
 					{
@@ -692,12 +752,14 @@ namespace nab200
 #pragma unroll
 				for (int ks = 0; ks < KS; ks++)
 				{
-					issuer_sync(ks + 1 < KS ? kBarZ0 : kBarZ);
+					if (!kFewHandoffs) issuer_sync(ks + 1 < KS ? kBarZ0 : kBarZ);
+					else if (ks == 0) issuer_sync(kBarZ);
 					if (ks == 0) TS_STAMP(8);
 					if (cx.el)
 					{
 						const u64 boff = (u64)(2 * ks * N1P);
 						if (ks == 0) mma_ts<1>(tm + TC::XR, tm + kConst, desc_at(wb16 + oneC16, N1P), idN1);
+						split_on_tc<1, kSplitZ>(cx, TC::T0 + 8u * ks, TC::T0 + C + 8u * ks);
 						mma_ts<1>(tm + TC::XR, tm + TC::T0 + 8u * ks, oHi + boff, idN1);
 						mma_ts<1>(tm + TC::XR, tm + TC::T0 + C + 8u * ks, oHi + boff, idN1);
 						mma_ts<1>(tm + TC::XR, tm + TC::T0 + 8u * ks, oLo + boff, idN1);
@@ -766,6 +828,8 @@ namespace nab200
 			cx.hdb = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(Ls) + kTableBytes);
 			unsigned long long* bars = reinterpret_cast<unsigned long long*>(cx.hdb + 2 * kHdbHalf);
 			uint32_t* tmemSlot = reinterpret_cast<uint32_t*>(bars + kNumBars);
+			float* negI = reinterpret_cast<float*>(tmemSlot + 4);   // [2 k groups][8 n][4]: element (k, n) = -1 if k == n
+			cx.negI = desc_at(smem_u32(negI) >> 4, 8);
 			cx.barW0 = smem_u32(&bars[0]);
 			cx.barD = smem_u32(&bars[2]);
 			cx.barX = smem_u32(&bars[3]);
@@ -812,6 +876,12 @@ namespace nab200
 				T.cpCnt1 = !pure0 ? 0 : (pure1 ? -1 : D1); T.cpD1 = D1; T.cpOff1 = T.tap1Off; T.cpStride1 = T.tap1Stride;
 				T.pad[0] = T.pad[1] = T.pad[2] = 0;
 				Ls[tid] = T;
+			}
+			if (threadIdx.x < 64)
+			{
+				const int kg = threadIdx.x >> 5, nn = (threadIdx.x >> 2) & 7, i = threadIdx.x & 3;
+				negI[threadIdx.x] = (kg * 4 + i == nn) ? -1.0f : 0.0f;
+				asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
 			}
 			if (tid == 0)
 			{
@@ -886,6 +956,8 @@ namespace nab200
 						{
 							const uint32_t wb16 = (cx.wbuf + (cx.wq & 1u) * cx.wbufStride) >> 4;
 							const u64 dHi = desc_at(wb16 + re1, 8), dLo = desc_at(wb16 + re1Lo, 8);
+							split_on_tc<2, kSplitEntry>(cx, Cols<0>::XR, Cols<0>::T2L);
+							split_on_tc<1, kSplitEntry>(cx, Cols<0>::HD, kHdLo);
 							mma_ts<0>(tm + Cols<1>::XR, tm + Cols<0>::XR, dHi, idesc_of(8));
 							mma_ts<1>(tm + Cols<1>::XR, tm + Cols<0>::T2L, dHi, idesc_of(8));
 							mma_ts<1>(tm + Cols<1>::XR, tm + Cols<0>::XR, dLo, idesc_of(8));
@@ -914,6 +986,7 @@ namespace nab200
 							const uint32_t wb16 = (cx.wbuf + (cx.wq & 1u) * cx.wbufStride) >> 4;
 							const u64 dHi = desc_at(wb16 + re1, 8), dLo = desc_at(wb16 + re1Lo, 8);
 							constexpr uint32_t XH = Cols<2>::T0, XL = Cols<2>::T0 + 16;
+							split_on_tc<2, kSplitEntry>(cx, XH, XL);
 							mma_ts<0>(tm + Cols<2>::XR, tm + XH, dHi, idesc_of(8));
 							mma_ts<1>(tm + Cols<2>::XR, tm + XL, dHi, idesc_of(8));
 							mma_ts<1>(tm + Cols<2>::XR, tm + XH, dLo, idesc_of(8));
@@ -993,8 +1066,16 @@ namespace nab200
 							const uint4 a = sc[q * kCur];
 							v[4 * q + 0] = a.x; v[4 * q + 1] = a.y; v[4 * q + 2] = a.z; v[4 * q + 3] = a.w;
 						}
+						if (kSplitEntry)
+						{
 #pragma unroll
-						for (int c = 0; c < 16; c += 2) split_lo2(v[c], v[c + 1], v[16 + c], v[16 + c + 1]);
+							for (int c = 0; c < 16; c++) v[16 + c] = v[c];
+						}
+						else
+						{
+#pragma unroll
+							for (int c = 0; c < 16; c += 2) split_lo2(v[c], v[c + 1], v[16 + c], v[16 + c + 1]);
+						}
 						tmem_st<32>(lanebase + Cols<2>::T0, v);
 						const uint4 h0 = sc[4 * kCur], h1 = sc[5 * kCur];
 						headSum[0] = __uint_as_float(h0.x); headSum[1] = __uint_as_float(h0.y); headSum[2] = __uint_as_float(h0.z); headSum[3] = __uint_as_float(h0.w);
@@ -1011,12 +1092,20 @@ namespace nab200
 							uint32_t x[16], xl[16];
 							tmem_ld<16>(lanebase + Cols<0>::XR, x);
 #pragma unroll
-							for (int c = 0; c < 16; c += 2) split_lo2(x[c], x[c + 1], xl[c], xl[c + 1]);
+							for (int c = 0; c < 16; c += 2)
+							{
+								if (kSplitEntry) { xl[c] = x[c]; xl[c + 1] = x[c + 1]; }
+								else split_lo2(x[c], x[c + 1], xl[c], xl[c + 1]);
+							}
 							tmem_st<16>(lanebase + Cols<0>::T2L, xl);
 							uint32_t h[8], hl[8];
 							tmem_ld<8>(lanebase + Cols<0>::HD, h);
 #pragma unroll
-							for (int c = 0; c < 8; c += 2) split_lo2(h[c], h[c + 1], hl[c], hl[c + 1]);
+							for (int c = 0; c < 8; c += 2)
+							{
+								if (kSplitEntry) { hl[c] = h[c]; hl[c + 1] = h[c + 1]; }
+								else split_lo2(h[c], h[c + 1], hl[c], hl[c + 1]);
+							}
 							tmem_st<8>(lanebase + kHdLo, hl);
 						}
 						stager_arrive(kBarE);
@@ -1079,7 +1168,7 @@ namespace nab200
 	static cudaError_t ts_launch_mode(const WnModelDev& M, const WnLaunch& a, int wbufFloats, int ctasPerSM)
 	{
 		auto kfn = ts::wavenet_ts_kernel<MODE>;
-		const size_t smem = ts::smem_fixed_bytes(MODE == 2 ? 2 : 4) + (size_t)2 * wbufFloats * 4 + ts::kTableBytes + 2 * ts::kHdbHalf * 4 + ts::kNumBars * 8 + 16;
+		const size_t smem = ts::smem_fixed_bytes(MODE == 2 ? 2 : 4) + (size_t)2 * wbufFloats * 4 + ts::kTableBytes + 2 * ts::kHdbHalf * 4 + ts::kNumBars * 8 + 16 + 256;
 		cudaError_t err = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 		if (err != cudaSuccess) return err;
 		int grid = a.numSMs * ctasPerSM;
