@@ -106,7 +106,15 @@ NA_EXTERN int NA_GetDeviceBlob(NeuralModel* model, void** devicePtr, size_t* byt
 /* test / tooling hooks */
 NA_EXTERN int NA_CopyStreamState(NeuralModel* model, size_t stream, float* hostOut, size_t capacityFloats);   /* returns floats written */
 NA_EXTERN int NA_DescribeModelFile(const wchar_t* modelPath, int externalSampleRate, char* out, int capacity);   /* host only: parse + pack, no GPU touched; JSON text */
-NA_EXTERN int NA_SetOption(const char* name, int value);   /* "use_tma" (1), "wavenet_ctas_per_sm"... returns previous value or -1 */
+/* Tuning / test knobs, process-wide, read when a model is loaded; returns the previous value or -1 for an unknown name.
+ *   "use_tc":  2 (default) tcgen05 WaveNet kernel with TMEM operands where the architecture fits (A1 Standard / Lite),
+ *              1 tcgen05 kernel with shared-memory operands, 0 CUDA-core kernels only, -1 the run-time-shaped kernel even
+ *              for architectures that have a specialised one (cross-checks);
+ *   "ts_split": 1 = run the TMEM-operand kernel as one launch per layer array (default 0, fused);
+ *   "use_tma": 0 = plain loads instead of TMA in the CUDA-core WaveNet kernel (debugging aid);
+ *   "max_grid_ctas": cap on the SM count used for grid sizing (0 = all).
+ * The same knobs can be preset through NAB200_USE_TC / NAB200_TS_SPLIT / NAB200_USE_TMA / NAB200_MAX_GRID_CTAS. */
+NA_EXTERN int NA_SetOption(const char* name, int value);
 
 #ifdef __cplusplus
 }
