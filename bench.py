@@ -106,6 +106,8 @@ class ClockSampler:
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    # nvidia-smi needs ~1 s before its first sample, so it is started before the warm-up; every line is stamped with the host
+    # clock on arrival and only the lines that arrived inside [mark_begin, mark_end] (the timed loops) are used
 
     def __init__(self, device_index):
         self.device_index = device_index
@@ -114,7 +116,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "20"],
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", os.environ.get("NAB200_BENCH_SMI_MS", "50")],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -123,7 +125,13 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
+
+    def mark_begin(self):
+        self.t_begin = time.time()
+
+    def mark_end(self):
+        self.t_end = time.time()
 
     def stop(self):
         if not self.proc:
@@ -135,7 +143,10 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, smax, reasons = [], [], set()
-        for line in self.lines:
+        t0, t1 = getattr(self, "t_begin", 0.0), getattr(self, "t_end", float("inf"))
+        for stamp, line in self.lines:
+            if stamp < t0 or stamp > t1 + 0.03:
+                continue
             parts = [p.strip() for p in line.split(",")]
             if len(parts) < 9 or parts[0] != str(self.device_index):
                 continue
@@ -252,12 +263,19 @@ def run_b200(args, rank, local_rank, world):
         torch.cuda.synchronize(dev)
 
     # ---- device-resident hot path -------------------------------------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for i in range(max(args.warmup, 3)):
         model.ProcessBatch(xs[i % nbuf], ys[i % nbuf], streams, frames)
     model.Synchronize()
-    sampler = ClockSampler(local_rank)
+    # keep the GPU under the same load (untimed) until nvidia-smi delivers its first sample, at most 2 s
+    t_wait = time.time()
+    while sampler.proc is not None and not sampler.lines and time.time() - t_wait < 2.0:
+        for i in range(20):
+            model.ProcessBatch(xs[i % nbuf], ys[i % nbuf], streams, frames)
+        model.Synchronize()
     barrier()
-    sampler.start()
+    sampler.mark_begin()
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)
     e0.record(stream)
@@ -303,7 +321,8 @@ def run_b200(args, rank, local_rank, world):
     checksum += float(yh[(args.steps - 1) % 3][0, 0])
     e2e_s = time.perf_counter() - t0
     barrier()
-    clocks = sampler.stop()   # sampled every 20 ms from the start of the device-timed loop to the end of the end-to-end loops
+    sampler.mark_end()
+    clocks = sampler.stop()   # sampled every 20 ms; only samples from the start of the device-timed loop to the end of the end-to-end loops count
 
     times = torch.tensor([dev_ms, e2e_s * 1e3, e2e_blocking_s * 1e3], dtype=torch.float64, device=dev)
     if dist is not None:
