@@ -238,7 +238,8 @@ namespace nab200
 #ifndef NAB_TS_FEW_HANDOFFS
 #define NAB_TS_FEW_HANDOFFS 0
 #endif
-		constexpr bool kFewHandoffs = NAB_TS_FEW_HANDOFFS != 0;
+		constexpr bool kFewHandoffs = NAB_TS_FEW_HANDOFFS == 1;
+		constexpr bool kMergeT2 = NAB_TS_FEW_HANDOFFS == 2;   // the undelayed tap's low part rides on tap 0's hand-off
 
 		// Low parts of the 3xTF32 split for two values.  The tensor core truncates its fp32 inputs to tf32, so the high part is
 		// the raw value and lo = x - trunc(x).  lo is itself truncated to tf32 by the hardware, which would bias it toward
@@ -545,7 +546,7 @@ namespace nab200
 					for (int c = 0; c < C; c += 2) split_lo2(x[c], x[c + 1], xl[c], xl[c + 1]);
 					tmem_st<C>(lanebase + TC::T2L, xl);
 				}
-				if (!kFewHandoffs) stager_arrive(kBarT2);
+				if (!kFewHandoffs && !kMergeT2) stager_arrive(kBarT2);
 				TS_STAMP(2);
 				// my copies of this layer's history window(s) have landed; where a tap mixes history and current frames the rows
 				// other threads copied / produced must be visible too (named barrier among the stagers)
@@ -672,8 +673,9 @@ namespace nab200
 
 				// ---- dilated conv + mix-in + bias (WaveNet.h:250-289,471-476), operands as the stagers deliver them ----
 				TS_STAMP(0);
-				if (!kFewHandoffs) issuer_sync(kBarT2);
-				else issuer_sync(kBarT1);
+				if (kFewHandoffs) issuer_sync(kBarT1);
+				else if (kMergeT2) issuer_sync(kBarT0);
+				else issuer_sync(kBarT2);
 				TS_STAMP(1);
 				if (cx.el)
 				{
@@ -697,7 +699,7 @@ namespace nab200
 				}
 				__syncwarp();
 				TS_STAMP(2);
-				if (!kFewHandoffs) issuer_sync(kBarT0);
+				if (!kFewHandoffs && !kMergeT2) issuer_sync(kBarT0);
 				TS_STAMP(3);
 				if (cx.el)
 				{
