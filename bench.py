@@ -223,6 +223,8 @@ def run_b200(args, rank, local_rank, world):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     _fixture, _syn, streams, frames, quality = WORKLOADS[args.workload]
     if args.streams:
         streams = args.streams
@@ -263,17 +265,13 @@ def run_b200(args, rank, local_rank, world):
         torch.cuda.synchronize(dev)
 
     # ---- device-resident hot path -------------------------------------------------------------------------------
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    # (the clock sampler was started before the model was loaded: nvidia-smi needs ~1 s before its first sample)
+    t_wait = time.time()
+    while sampler.proc is not None and not sampler.lines and time.time() - t_wait < 2.0:
+        time.sleep(0.05)
     for i in range(max(args.warmup, 3)):
         model.ProcessBatch(xs[i % nbuf], ys[i % nbuf], streams, frames)
     model.Synchronize()
-    # keep the GPU under the same load (untimed) until nvidia-smi delivers its first sample, at most 2 s
-    t_wait = time.time()
-    while sampler.proc is not None and not sampler.lines and time.time() - t_wait < 2.0:
-        for i in range(20):
-            model.ProcessBatch(xs[i % nbuf], ys[i % nbuf], streams, frames)
-        model.Synchronize()
     barrier()
     sampler.mark_begin()
     e0 = torch.cuda.Event(enable_timing=True)

@@ -32,7 +32,8 @@ class EModelLoadMode:   # reference NeuralModel.h:20-25
 
 
 def library_path():
-    return os.path.join(_HERE, _LIB_NAME)
+    # NAB200_LIBNAME: load another build of the library from the package directory (A/B timing of kernel variants)
+    return os.path.join(_HERE, os.environ.get("NAB200_LIBNAME", _LIB_NAME))
 
 
 def build_library(force=False):
