@@ -313,6 +313,28 @@ def test_split_launch_matches_fused(na, O, tmp_path):
     assert float(np.abs(ys - outs[0][:, 3, :].reshape(-1)).max()) <= WAVENET_TOL
 
 
+@pytest.mark.parametrize("kind", ["zero", "huge", "tiny"])
+def test_lstm_activation_edge_ranges(na, O, kind, tmp_path):
+    """The LSTM kernel computes its gate activations in packed pairs with a hand-scheduled IEEE quotient that is valid
+    for ordinary arguments and hands zero / denormal / huge arguments to the scalar IEEE division: drive each range
+    (all-zero weights: gates exactly 0; weights x 1e7: saturated gates; weights x 1e-30: gates near the denormals)."""
+    import json
+    g = load_golden(golden_files("syn_lstm_1x16")[0])
+    w = np.asarray(g["weights"], dtype=np.float32).copy()
+    scale = {"zero": 0.0, "huge": 1e7, "tiny": 1e-30}[kind]
+    H = 16
+    w[:4 * H * (1 + H) + 4 * H] *= np.float32(scale)   # gate matrices and biases only: initial state and head stay as they are
+    d = dict(g["model"]); d["weights"] = [float(v) for v in w]
+    mf = os.path.join(str(tmp_path), "edge_%s.nam" % kind)
+    with open(mf, "w") as f:
+        json.dump(d, f)
+    x = np.random.default_rng(5).uniform(-0.5, 0.5, 1024).astype(np.float32)
+    y = _blocks(_load(na, mf), x, 128)
+    yo = O.PortModel.from_file(mf).process(x)
+    assert np.isfinite(yo).all() and np.isfinite(y).all()
+    assert float(np.abs(y - yo).max()) <= LSTM_TOL
+
+
 def test_full_size_config_properties(na, O, tmp_path):
     """BASELINE.json cfg 2 (A1 Standard, 4096 streams x 128 frames) at full size, through size-independent
     properties: identical inputs => bit-identical streams (independence + determinism), a tile of streams checked
