@@ -33,6 +33,9 @@
 #define DEFAULT_INPUT_DBU 12
 #endif
 
+// the shared library is built with hidden visibility; the two public classes are its C++ exports
+#define NEURALAUDIO_B200_API __attribute__((visibility("default")))
+
 namespace NeuralAudio
 {
 inline namespace b200
@@ -60,7 +63,7 @@ inline namespace b200
 		FrameMajor = 1     // element (stream s, frame f) at buffer[f * numStreams + s]
 	};
 
-	class NeuralModel
+	class NEURALAUDIO_B200_API NeuralModel
 	{
 	public:
 		virtual ~NeuralModel() {}
@@ -136,7 +139,7 @@ inline namespace b200
 		std::vector<std::pair<std::string, std::string>> metadata;
 	};
 
-	class NeuralModelLoader
+	class NEURALAUDIO_B200_API NeuralModelLoader
 	{
 	public:
 		// nullptr when the file does not exist or the model cannot be placed on the GPU; throws std::runtime_error

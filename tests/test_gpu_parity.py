@@ -335,6 +335,47 @@ def test_lstm_activation_edge_ranges(na, O, kind, tmp_path):
     assert float(np.abs(y - yo).max()) <= LSTM_TOL
 
 
+# known answers of the reference's Internal path (x[i] = sin(i * 0.01), 4096 samples in 128-sample
+# calls on a freshly loaded model): out[0], out[1000], out[4095], sum(out)
+KNOWN_ANSWERS = {
+    ("BossWN-nano.nam", 1.0): (0.000353399199, -0.252702147, -0.283021569, 21.8273232),
+    ("BossWN-feather.nam", 1.0): (-0.00016338109, -0.2728616, -0.295489967, 28.6872998),
+    ("BossWN-standard.nam", 1.0): (-0.00067000452, -0.317638844, -0.349413633, 39.1764422),
+    ("BossWN-a2.nam", 1.0): (0.000276284292, -0.257261902, -0.284163564, 30.4085193),
+    ("BossWN-a2.nam", 0.0): (0.000122590631, -0.236403778, -0.282012135, 14.3841253),
+    ("BossLSTM-1x16.nam", 1.0): (-0.0270614624, -0.253457189, -0.171944439, -219.212568),
+    ("BossLSTM-2x8.nam", 1.0): (0.00714398921, -0.170382544, -0.184256151, -172.00273),
+}
+
+
+@pytest.mark.parametrize("fixture,quality", sorted(KNOWN_ANSWERS), ids=lambda v: str(v))
+def test_cpp_model_test_known_answers(fixture, quality):
+    """The C++ surface end to end: tools/model_test (ModelTest.cpp's protocol against our header, plain g++) loads the
+    reference's own fixture, runs the known-answer input through Process(), a batch through ProcessBatch(), and its
+    batch-vs-single RMS (ComputeError protocol, ModelTest.cpp:81-118) is zero: every stream slot is the same machine."""
+    import re
+    import subprocess
+    import __graft_entry__ as ge
+    mf = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "models", fixture)
+    if not os.path.exists(mf):
+        pytest.skip("fixture model not staged")
+    exe = ge.build_model_test()
+    r = subprocess.run([exe, "--kat", "-s", "48", "-q", str(quality), mf], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    m = re.search(r"KAT out\[0\]=(\S+) out\[1000\]=(\S+) out\[4095\]=(\S+) sum=(\S+)", r.stdout)
+    assert m, r.stdout
+    got = [float(v) for v in m.groups()]
+    want = KNOWN_ANSWERS[(fixture, quality)]
+    tol = LSTM_TOL if "LSTM" in fixture else WAVENET_TOL
+    for a, b in zip(got[:3], want[:3]):
+        assert abs(a - b) <= tol, (got, want)
+    assert abs(got[3] - want[3]) <= 4096 * tol
+    assert re.search(r"Internal: \S+ \(\S+xRT\)", r.stdout)
+    assert re.search(r"Batch 48 streams: \S+ \(\S+xRT, \S+ Msamples/s\)", r.stdout)
+    rms = float(re.search(r"Batch vs single RMS err: (\S+)", r.stdout).group(1))
+    assert rms <= 1e-6, r.stdout
+
+
 def test_full_size_config_properties(na, O, tmp_path):
     """BASELINE.json cfg 2 (A1 Standard, 4096 streams x 128 frames) at full size, through size-independent
     properties: identical inputs => bit-identical streams (independence + determinism), a tile of streams checked

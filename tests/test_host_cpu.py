@@ -36,11 +36,16 @@ def test_library_exports_every_declared_symbol(na):
     assert set(L._na_signatures) == set(declared)
 
 
-def test_only_c_abi_symbols_are_exported(na):
+def test_only_the_public_surface_is_exported(na):
+    """Exports = the C ABI of include/NeuralAudioCApi.h plus the three out-of-line NeuralModelLoader::CreateFrom* methods of
+    include/NeuralAudio/NeuralModel.h (the C++ surface a ModelTest-style caller links against); nothing else leaks."""
     import subprocess
-    out = subprocess.check_output(["nm", "-D", "--defined-only", na.library_path()], text=True)
-    syms = [l.split()[-1] for l in out.splitlines() if " T " in l]
-    assert sorted(syms) == sorted(_declared_symbols())
+    out = subprocess.check_output(["nm", "-D", "-C", "--defined-only", na.library_path()], text=True)
+    syms = [l.split(" T ", 1)[1].strip() for l in out.splitlines() if " T " in l]
+    c_syms = [s for s in syms if "::" not in s]
+    cpp_syms = sorted(s.split("(")[0] for s in syms if "::" in s)
+    assert sorted(c_syms) == sorted(_declared_symbols())
+    assert cpp_syms == ["NeuralAudio::b200::NeuralModelLoader::" + m for m in ("CreateFromFile", "CreateFromJsonText", "CreateFromStream")]
 
 
 def test_loader_handles_work_without_gpu(na):
@@ -172,3 +177,20 @@ def test_tmem_operand_packing_reconstructs_weights(na, tmp_path):
         assert ts["max_block"] * 4 * 2 <= 48 * 1024      # two weight buffers per CTA, 4 CTAs per SM
     g = load_golden(golden_files("syn_a1_nano")[0])
     assert na.describe_model_file(model_file_for(g, tmp_path))["kernel"] == "cuda_cores"
+
+
+def test_cpp_consumer_builds_links_and_fails_loudly_without_gpu(tmp_path):
+    """A C++ caller of the reference (ModelTest.cpp:11-57 style) recompiles against include/NeuralAudio/NeuralModel.h and
+    links the shared library: the loader's out-of-line methods are exported.  Without a CUDA device loading returns nullptr
+    (no CPU fallback), which the tool reports the way the reference's ModelTest does."""
+    import subprocess
+    import __graft_entry__ as ge
+    exe = ge.build_model_test()
+    r = subprocess.run([exe, str(tmp_path / "missing.nam")], capture_output=True, text=True, timeout=120)
+    assert "Model file does not exist" in r.stdout and r.returncode == 1
+    import torch
+    if not torch.cuda.is_available():
+        g = load_golden(golden_files("syn_a1_nano")[0])
+        mf = model_file_for(g, tmp_path)
+        r = subprocess.run([exe, mf], capture_output=True, text=True, timeout=120)
+        assert "Unable to load model from" in r.stdout and r.returncode == 1
