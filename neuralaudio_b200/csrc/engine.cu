@@ -519,6 +519,8 @@ namespace nab200
 		a.in = nullptr; a.out = nullptr;
 		a.n = 2048;
 		a.zeroInput = true;
+		a.generic = GetOptions().useTc < 0;
+		a.numSMs = numSMs;
 		a.stream = stream;
 		a.state = dBlob + weightFloats;
 		a.S = 1;
@@ -542,6 +544,8 @@ namespace nab200
 		a.S = (int)S;
 		a.n = (int)n;
 		a.zeroInput = false;
+		a.generic = GetOptions().useTc < 0;
+		a.numSMs = numSMs;
 		a.stream = stream;
 		return CudaOk(lstm_launch(packed.dev, a), "lstm_fwd_kernel launch");
 	}

@@ -257,8 +257,9 @@ namespace nab200
 		d.numLayers = config.at("num_layers").as_int();
 		d.hiddenSize = config.at("hidden_size").as_int();
 		if (config.value_int("input_size", 1) != 1) throw std::runtime_error("unsupported model: LSTM input_size != 1");
-		if (d.numLayers < 1 || d.numLayers > 2) throw std::runtime_error("unsupported model: LSTM num_layers must be 1 or 2");
-		if (d.hiddenSize < 1 || d.hiddenSize > 32) throw std::runtime_error("unsupported model: LSTM hidden_size must be 1..32");
+		// LSTMDynamic.h takes any size; the run-time-shaped kernel's bounds are kMaxLstmLayers / kMaxLstmLanes
+		if (d.numLayers < 1 || d.numLayers > kMaxLstmLayers) throw std::runtime_error("unsupported model: LSTM num_layers must be 1..8");
+		if (d.hiddenSize < 1 || d.hiddenSize > kMaxLstmLanes) throw std::runtime_error("unsupported model: LSTM hidden_size must be 1..256");
 		const std::vector<float> w = FloatList(modelJson.at("weights"));
 		const int H = d.hiddenSize;
 		size_t expect = (size_t)H + 1;
@@ -313,8 +314,8 @@ namespace nab200
 		d.numLayers = (int)numLayers - 1;
 		const Json& shape = layers.at(0).at("shape");
 		d.hiddenSize = shape.at(shape.size() - 1).as_int();
-		if (d.numLayers > 2) throw std::runtime_error("unsupported model: keras LSTM with more than 2 layers");
-		if (d.hiddenSize < 1 || d.hiddenSize > 32) throw std::runtime_error("unsupported model: LSTM hidden_size must be 1..32");
+		if (d.numLayers > kMaxLstmLayers) throw std::runtime_error("unsupported model: keras LSTM with more than 8 layers");
+		if (d.hiddenSize < 1 || d.hiddenSize > kMaxLstmLanes) throw std::runtime_error("unsupported model: LSTM hidden_size must be 1..256");
 		const int H = d.hiddenSize;
 		for (int l = 0; l < d.numLayers; l++)
 			if (layers.at(l).at("type").as_string() != "lstm")
@@ -816,7 +817,8 @@ namespace nab200
 		memset(&M, 0, sizeof(M));
 		const int H = desc.hiddenSize;
 		int G = 4;
-		while (G < H) G *= 2;
+		while (G < H && G < 32) G *= 2;
+		if (H > 32) G = (H + 3) & ~3;
 		M.L = desc.numLayers; M.H = H; M.G = G;
 		M.stateStride = M.L * 2 * G;
 		P.initState.assign(M.stateStride, 0.0f);

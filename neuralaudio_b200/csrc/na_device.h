@@ -82,11 +82,14 @@ namespace nab200
 	// LSTM: lane == hidden unit, G = pow2 >= H lanes per stream, weights zero-padded to G.
 	// Packed per layer l (I = 1 for l == 0 else G):  W[4][I + G][G] (gate, column, unit) | b[4][G]
 	// then headW[G], headB.  State per stream: [layer][2][G] (h then c).
+	// G = pow2 >= H for H <= 32 (compile-time-shaped kernels, L <= 2), else H rounded up to 4 (run-time-shaped kernel).
+	constexpr int kMaxLstmLayers = 8;
+	constexpr int kMaxLstmLanes = 256;
 	struct LstmModelDev
 	{
 		int L, H, G;
-		int wOff[2];       // float offset of layer l's W
-		int bOff[2];
+		int wOff[kMaxLstmLayers];       // float offset of layer l's W
+		int bOff[kMaxLstmLayers];
 		int headOff;       // headW[G] then headB
 		int stateStride;   // floats per stream = L * 2 * G
 	};

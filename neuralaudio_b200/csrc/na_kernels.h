@@ -50,6 +50,8 @@ namespace nab200
 		int S;
 		int n;
 		bool zeroInput;         // ignore `in`, feed zeros (prewarm)
+		bool generic;           // force the run-time-shaped kernel (use_tc = -1), which otherwise serves L > 2 or H > 32
+		int numSMs;
 		cudaStream_t stream;
 	};
 

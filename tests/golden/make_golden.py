@@ -128,6 +128,21 @@ def dynamic_cases():
     return cases
 
 
+def dynamic_lstm_cases():
+    """LSTM sizes outside the reference's static list (NeuralModel.cpp:25-38): its dynamic path (LSTMDynamic.h)."""
+    rng = np.random.default_rng(20261019)
+    cases = {}
+    for name, (L, H) in {"dyn_lstm_3x18": (3, 18), "dyn_lstm_1x40": (1, 40), "dyn_lstm_4x6": (4, 6), "dyn_lstm_2x32": (2, 32)}.items():
+        n = H + 1
+        for l in range(L):
+            i = 1 if l == 0 else H
+            n += 4 * H * (i + H) + 4 * H + 2 * H
+        w = rng.uniform(-1.0, 1.0, n).astype(np.float32) * np.float32(2.5 / np.sqrt(H))
+        cases[name] = {"version": "0.5.2", "architecture": "LSTM", "config": {"input_size": 1, "hidden_size": H, "num_layers": L},
+                       "weights": w, "sample_rate": 48000, "metadata": {"loudness": -15.0}}
+    return cases
+
+
 def nam_text(case):
     d = dict(case)
     d["weights"] = [float(x) for x in np.asarray(case["weights"], dtype=np.float32)]
@@ -151,7 +166,7 @@ def main():
     tmpdir = os.path.join(HERE, "_tmp")
     os.makedirs(tmpdir, exist_ok=True)
     made = []
-    fixtures = [] if "--dynamic-only" in sys.argv else [("BossWN-nano.nam", 1.0), ("BossWN-feather.nam", 1.0), ("BossWN-standard.nam", 1.0), ("BossWN-a2.nam", 1.0),
+    fixtures = [] if ("--dynamic-only" in sys.argv or "--dynamic-lstm-only" in sys.argv) else [("BossWN-nano.nam", 1.0), ("BossWN-feather.nam", 1.0), ("BossWN-standard.nam", 1.0), ("BossWN-a2.nam", 1.0),
                 ("BossWN-a2.nam", 0.0), ("BossLSTM-1x16.nam", 1.0), ("BossLSTM-2x8.nam", 1.0),
                 ("tw40_blues_deluxe_deerinkstudios.json", 1.0), ("namcore_wavenet.nam", 1.0), ("namcore_lstm.nam", 1.0),
                 ("namcore_wavenet_a1_standard.nam", 1.0)]
@@ -168,17 +183,20 @@ def main():
         np.savez_compressed(out, x=x, y=y, dc=dc, fixture=name, quality=np.float32(q), info=json.dumps(info))
         made.append(out)
     only_dynamic = "--dynamic-only" in sys.argv   # adds the run-time-shaped cases without touching the earlier vectors
-    if only_dynamic:
+    only_dyn_lstm = "--dynamic-lstm-only" in sys.argv
+    if only_dynamic or only_dyn_lstm:
         made = []
-    allcases = list(synthetic_cases().items()) + list(dynamic_cases().items())
+    allcases = list(synthetic_cases().items()) + list(dynamic_cases().items()) + list(dynamic_lstm_cases().items())
     for j, (name, case) in enumerate(allcases):
         if only_dynamic and not name.startswith("dyn_"):
+            continue
+        if only_dyn_lstm and not name.startswith("dyn_lstm"):
             continue
         path = os.path.join(tmpdir, name + ".nam")
         with open(path, "w") as f:
             f.write(nam_text(case))
         rng = np.random.default_rng(777 + j)
-        amp = 0.5 if name.startswith("lstm") else 1.0
+        amp = 0.5 if "lstm" in name else 1.0
         x = (rng.uniform(-1.0, 1.0, N) * amp).astype(np.float32)
         y, dc, info = run_ref(path, x)
         meta = {k: v for k, v in case.items() if k != "weights"}

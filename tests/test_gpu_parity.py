@@ -313,6 +313,41 @@ def test_split_launch_matches_fused(na, O, tmp_path):
     assert float(np.abs(ys - outs[0][:, 3, :].reshape(-1)).max()) <= WAVENET_TOL
 
 
+@pytest.mark.parametrize("name,streams", [("syn_lstm_1x16", 37), ("syn_lstm_2x12", 10), ("syn_dyn_lstm_3x18", 23), ("syn_dyn_lstm_1x40", 7),
+                                          ("syn_dyn_lstm_2x32", 9)])
+def test_runtime_shaped_lstm_kernel(na, O, name, streams, tmp_path):
+    """The run-time-shaped LSTM kernel (the reference's dynamic path, LSTMDynamic.h): sizes outside the compile-time-shaped
+    list run on it by themselves; use_tc = -1 forces it for the others.  Ragged stream counts (not a multiple of the streams
+    one block carries), two layouts, every stream against its own oracle instance."""
+    g = load_golden(golden_files(name)[0])
+    mf = model_file_for(g, tmp_path)
+    calls, n = 5, 96
+    x = (np.random.default_rng(41).uniform(-1, 1, (calls, streams, n)) * 0.5).astype(np.float32)
+    prev = na.set_option("use_tc", -1)
+    try:
+        m = _load(na, mf, streams=streams)
+        y = np.empty_like(x)
+        for k in range(calls):
+            m.ProcessBatch(x[k], y[k], streams, n)
+        m2 = _load(na, mf, streams=streams)
+        yt = np.empty((calls, n, streams), dtype=np.float32)
+        for k in range(calls):
+            m2.ProcessBatch(np.ascontiguousarray(x[k].T), yt[k], streams, n, na.FRAME_MAJOR)
+    finally:
+        na.set_option("use_tc", prev)
+    assert np.array_equal(y, yt.transpose(0, 2, 1))
+    for s in sorted({0, streams // 2, streams - 1}):
+        ys = O.PortModel.from_file(mf).process(np.ascontiguousarray(x[:, s, :]).reshape(-1))
+        assert float(np.abs(ys - y[:, s, :].reshape(-1)).max()) <= LSTM_TOL
+    if "dyn" not in name:
+        # same shapes on the compile-time-shaped kernel
+        m3 = _load(na, mf, streams=streams)
+        y3 = np.empty_like(x)
+        for k in range(calls):
+            m3.ProcessBatch(x[k], y3[k], streams, n)
+        assert float(np.abs(y3 - y).max()) <= LSTM_TOL
+
+
 @pytest.mark.parametrize("kind", ["zero", "huge", "tiny"])
 def test_lstm_activation_edge_ranges(na, O, kind, tmp_path):
     """The LSTM kernel computes its gate activations in packed pairs with a hand-scheduled IEEE quotient that is valid
