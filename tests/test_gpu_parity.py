@@ -444,6 +444,37 @@ def test_full_size_config_properties(na, O, tmp_path):
     assert torch.equal(torch.flip(yr, dims=[1]), yd)
 
 
+@pytest.mark.parametrize("name", ["syn_a1_standard", "syn_a2_full", "syn_lstm_1x16", "syn_dyn_7x3", "syn_dyn_lstm_3x18"])
+def test_empty_partial_and_long_calls(na, O, name, tmp_path):
+    """Ragged use of the batch API: an empty call changes nothing; a call on the first k of S slots advances only those;
+    one very long call (many internal passes) equals the same audio in 128-frame calls."""
+    g = load_golden(golden_files(name)[0])
+    mf = model_file_for(g, tmp_path)
+    tol = tol_for(g)
+    S, n = 12, 128
+    amp = 0.5 if is_lstm_case(g) else 1.0
+    x = (np.random.default_rng(77).uniform(-1, 1, (3, S, n)) * amp).astype(np.float32)
+    m = _load(na, mf, streams=S)
+    y = np.empty_like(x)
+    m.ProcessBatch(x[0], y[0], S, n)
+    m.ProcessBatch(np.empty((S, 0), dtype=np.float32), np.empty((S, 0), dtype=np.float32), S, 0)       # empty call
+    m.Process(np.empty(0, dtype=np.float32))
+    k = 5
+    m.ProcessBatch(np.ascontiguousarray(x[1][:k]), y[1][:k], k, n)                                     # first k slots only
+    m.ProcessBatch(x[2], y[2], S, n)
+    ref = O.PortModel.from_file(mf)
+    r0 = ref.process(np.concatenate([x[0][0], x[1][0], x[2][0]]))       # slot 0 saw all three calls
+    assert float(np.abs(np.concatenate([y[0][0], y[1][0], y[2][0]]) - r0).max()) <= tol
+    r9 = O.PortModel.from_file(mf).process(np.concatenate([x[0][9], x[2][9]]))   # slot 9 skipped the middle call
+    assert float(np.abs(np.concatenate([y[0][9], y[2][9]]) - r9).max()) <= tol
+    # one long call
+    xl = (np.random.default_rng(78).uniform(-1, 1, 20000) * amp).astype(np.float32)
+    a = _load(na, mf).Process(xl.copy())
+    b = _blocks(_load(na, mf), xl, 128)
+    assert np.array_equal(a, b)
+    assert float(np.abs(a - O.PortModel.from_file(mf).process(xl)).max()) <= tol
+
+
 def test_errors_are_loud(na, tmp_path):
     g = load_golden(golden_files("syn_a1_nano")[0])
     mf = model_file_for(g, tmp_path)
