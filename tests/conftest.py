@@ -44,6 +44,11 @@ def load_golden(path):
     return g
 
 
+def external_sample_rate_of(g):
+    """48 kHz unless the vector was made with the host running faster (OversampleNAMConfig, NeuralModel.cpp:92-130)."""
+    return int(g["external_sample_rate"]) if "external_sample_rate" in g else 48000
+
+
 def is_lstm_case(g):
     name = g["name"].lower()
     return "lstm" in name or "tw40" in name

@@ -149,11 +149,11 @@ def nam_text(case):
     return json.dumps(d)
 
 
-def run_ref(path, x, quality=1.0):
-    m = O.RefModel(path, quality=quality)
+def run_ref(path, x, quality=1.0, external_sample_rate=48000):
+    m = O.RefModel(path, quality=quality, external_sample_rate=external_sample_rate)
     y = m.process_blocks(x, BLOCK)
     m.close()
-    m = O.RefModel(path, quality=quality)
+    m = O.RefModel(path, quality=quality, external_sample_rate=external_sample_rate)
     dc = m.process_blocks(np.zeros(512, dtype=np.float32), BLOCK)
     info = dict(static=m.is_static(), rf=m.receptive_field(), sample_rate=m.sample_rate(), in_adj=m.input_adjust(),
                 out_adj=m.output_adjust(), has_quality=m.has_quality())
@@ -161,10 +161,43 @@ def run_ref(path, x, quality=1.0):
     return y, dc, info
 
 
+def oversampled_vectors(tmpdir):
+    """The host runs at 96 kHz: OversampleNAMConfig (NeuralModel.cpp:92-130) doubles every dilation and the reference leaves
+    its static architectures for the dynamic path.  Same synthetic weights as the 48 kHz cases, `external_sample_rate` stored."""
+    made = []
+    cases = synthetic_cases()
+    for j, name in enumerate(["a1_standard", "a1_nano"]):   # (A2 at 96 kHz: the reference throws json out_of_range "head_bias", it has no dynamic A2)
+        case = cases[name]
+        path = os.path.join(tmpdir, name + ".nam")
+        with open(path, "w") as f:
+            f.write(nam_text(case))
+        rng = np.random.default_rng(999 + j)
+        x = rng.uniform(-1.0, 1.0, N).astype(np.float32)
+        try:
+            y, dc, info = run_ref(path, x, external_sample_rate=96000)
+        except Exception as e:   # the reference has no Internal path for this combination
+            print("reference refuses", name, "at 96 kHz:", e)
+            os.remove(path)
+            continue
+        meta = {k: v for k, v in case.items() if k != "weights"}
+        out = os.path.join(HERE, "syn_%s_sr96000.npz" % name)
+        np.savez_compressed(out, x=x, y=y, dc=dc, weights=np.asarray(case["weights"], dtype=np.float32), model=json.dumps(meta),
+                            info=json.dumps(info), external_sample_rate=np.int32(96000))
+        made.append(out)
+        os.remove(path)
+    return made
+
+
 def main():
     O.build()
     tmpdir = os.path.join(HERE, "_tmp")
     os.makedirs(tmpdir, exist_ok=True)
+    if "--oversampled-only" in sys.argv:
+        for m in oversampled_vectors(tmpdir):
+            z = np.load(m)
+            print("%-48s |y|max=%.4f std=%.4f dc=%.6g info=%s" % (os.path.basename(m), np.abs(z["y"]).max(), z["y"].std(), z["dc"][-1], str(z["info"])))
+        os.rmdir(tmpdir)
+        return
     made = []
     fixtures = [] if ("--dynamic-only" in sys.argv or "--dynamic-lstm-only" in sys.argv) else [("BossWN-nano.nam", 1.0), ("BossWN-feather.nam", 1.0), ("BossWN-standard.nam", 1.0), ("BossWN-a2.nam", 1.0),
                 ("BossWN-a2.nam", 0.0), ("BossLSTM-1x16.nam", 1.0), ("BossLSTM-2x8.nam", 1.0),

@@ -8,7 +8,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import WAVENET_TOL, LSTM_TOL, golden_files, golden_id, load_golden, model_file_for, tol_for, is_lstm_case
+from conftest import WAVENET_TOL, LSTM_TOL, golden_files, golden_id, load_golden, model_file_for, tol_for, is_lstm_case, external_sample_rate_of
 
 pytestmark = pytest.mark.gpu
 
@@ -19,8 +19,9 @@ def O():
     return oracle
 
 
-def _load(na, mf, quality=1.0, streams=1, prewarm=True):
+def _load(na, mf, quality=1.0, streams=1, prewarm=True, sample_rate=48000):
     ld = na.NeuralModelLoader()
+    ld.SetExternalSampleRate(sample_rate)
     ld.SetDefaultQualityScaleFactor(quality)
     ld.SetDefaultNumStreams(streams)
     return ld.CreateFromFile(mf, prewarm)
@@ -41,7 +42,8 @@ def test_single_stream_process_matches_reference_golden(na, path, tmp_path):
     if mf is None:
         pytest.skip("fixture model not staged")
     q = float(g.get("quality", 1.0))
-    m = _load(na, mf, q)
+    sr = external_sample_rate_of(g)
+    m = _load(na, mf, q, sample_rate=sr)
     y = _blocks(m, g["x"], 128)
     err = float(np.abs(y - g["y"]).max())
     assert err <= tol_for(g), "max-abs vs reference %.3g" % err
@@ -55,7 +57,7 @@ def test_single_stream_process_matches_reference_golden(na, path, tmp_path):
     assert abs(m.GetRecommendedOutputDBAdjustment() - info["out_adj"]) < 1e-4
     assert m.HasQualityScaling() == info["has_quality"]
     # zero input after load: the prewarmed steady state
-    m2 = _load(na, mf, q)
+    m2 = _load(na, mf, q, sample_rate=sr)
     dc = _blocks(m2, np.zeros(512, dtype=np.float32), 128)
     assert float(np.abs(dc - g["dc"]).max()) <= tol_for(g)
 
@@ -442,6 +444,24 @@ def test_full_size_config_properties(na, O, tmp_path):
         m2.ProcessBatch(xr[k], yr[k], S, n)
     m2.Synchronize()
     assert torch.equal(torch.flip(yr, dims=[1]), yd)
+
+
+@pytest.mark.parametrize("name,streams", [("syn_a1_standard_sr96000", 20), ("syn_a1_nano_sr96000", 33)])
+def test_oversampled_batch_matches_oracle(na, O, name, streams, tmp_path):
+    """Host at 96 kHz: every dilation doubles (OversampleNAMConfig, NeuralModel.cpp:92-130), the receptive field becomes 8184
+    and the rings twice as long; the batch kernels run the doubled dilations as run-time values."""
+    g = load_golden(golden_files(name)[0])
+    mf = model_file_for(g, tmp_path)
+    sr = external_sample_rate_of(g)
+    calls, n = 70, 128                     # 8960 frames > the 8184-frame receptive field
+    x = np.random.default_rng(97).uniform(-1, 1, (calls, streams, n)).astype(np.float32)
+    m = _load(na, mf, streams=streams, sample_rate=sr)
+    y = np.empty_like(x)
+    for k in range(calls):
+        m.ProcessBatch(x[k], y[k], streams, n)
+    for s in (0, streams - 1):
+        ys = O.PortModel.from_file(mf, external_sample_rate=sr).process(np.ascontiguousarray(x[:, s, :]).reshape(-1))
+        assert float(np.abs(ys - y[:, s, :].reshape(-1)).max()) <= WAVENET_TOL
 
 
 @pytest.mark.parametrize("name", ["syn_a1_standard", "syn_a2_full", "syn_lstm_1x16", "syn_dyn_7x3", "syn_dyn_lstm_3x18"])

@@ -7,7 +7,7 @@ import re
 import numpy as np
 import pytest
 
-from conftest import ROOT, golden_files, golden_id, load_golden, model_file_for
+from conftest import ROOT, golden_files, golden_id, load_golden, model_file_for, external_sample_rate_of
 
 
 def _declared_symbols():
@@ -65,7 +65,7 @@ def test_describe_matches_reference_dispatch(na, path, tmp_path):
     mf = model_file_for(g, tmp_path)
     if mf is None:
         pytest.skip("fixture model not staged")
-    d = na.describe_model_file(mf)
+    d = na.describe_model_file(mf, external_sample_rate_of(g))
     info = g["info"]
     if d["kind"] == "container":
         assert info["has_quality"]

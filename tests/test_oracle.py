@@ -7,7 +7,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import golden_files, golden_id, load_golden, model_file_for, tol_for, is_lstm_case
+from conftest import golden_files, golden_id, load_golden, model_file_for, tol_for, is_lstm_case, external_sample_rate_of
 from oracle import oracle as O
 
 
@@ -18,11 +18,12 @@ def test_port_reproduces_golden(path, tmp_path):
     if mf is None:
         pytest.skip("fixture model not staged (oracle/_ref/models)")
     q = float(g.get("quality", 1.0))
-    m = O.PortModel.from_file(mf, quality=q)
+    sr = external_sample_rate_of(g)
+    m = O.PortModel.from_file(mf, quality=q, external_sample_rate=sr)
     y = m.process(g["x"])
     err = float(np.abs(y - g["y"]).max())
     assert err <= tol_for(g), "port vs golden max-abs %.3g" % err
-    m2 = O.PortModel.from_file(mf, quality=q)
+    m2 = O.PortModel.from_file(mf, quality=q, external_sample_rate=sr)
     dc = m2.process(np.zeros(512, dtype=np.float32))
     assert float(np.abs(dc - g["dc"]).max()) <= tol_for(g)
     if not is_lstm_case(g):
