@@ -121,29 +121,31 @@ namespace nab200
 		return true;
 	}
 
-	static bool IsDevicePointer(const void* p)
+	// one query per pointer: pageable host memory (unknown to the driver), page-locked host memory, or device / managed memory
+	enum MemKind { kPageable = 0, kPinned = 1, kDevice = 2 };
+	static MemKind Classify(const void* p, void** devAlias = nullptr)
 	{
 		cudaPointerAttributes attr;
 		cudaError_t err = cudaPointerGetAttributes(&attr, p);
 		if (err != cudaSuccess)
 		{
 			cudaGetLastError();
-			return false;
+			return kPageable;
 		}
-		return attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged;
+		if (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged) return kDevice;
+		if (attr.type == cudaMemoryTypeHost)
+		{
+			if (devAlias) *devAlias = attr.devicePointer;
+			return kPinned;
+		}
+		return kPageable;
 	}
+	static bool IsDevicePointer(const void* p) { return Classify(p) == kDevice; }
+	static bool IsPinnedHost(const void* p) { return Classify(p) == kPinned; }
 
-	static bool IsPinnedHost(const void* p)
-	{
-		cudaPointerAttributes attr;
-		cudaError_t err = cudaPointerGetAttributes(&attr, p);
-		if (err != cudaSuccess)
-		{
-			cudaGetLastError();
-			return false;
-		}
-		return attr.type == cudaMemoryTypeHost;
-	}
+	// host calls up to this size skip the staging copies: the kernel reads the page-locked input and writes the page-locked
+	// output through their device aliases (unified addressing), which removes two DMA operations from a latency-bound call
+	constexpr size_t kZeroCopyFloats = 16384;
 
 	bool StreamEngine::Process(const float* in, float* out, size_t S, size_t n, int layout)
 	{
@@ -161,25 +163,40 @@ namespace nab200
 		if (!CudaOk(cudaSetDevice(device), "cudaSetDevice")) return false;
 		const long long SS = layout == 0 ? (long long)n : 1;
 		const long long FS = layout == 0 ? 1 : (long long)S;
-		const bool inDev = IsDevicePointer(in), outDev = IsDevicePointer(out);
+		void* inAlias = nullptr;
+		void* outAlias = nullptr;
+		const MemKind inKind = Classify(in, &inAlias), outKind = Classify(out, &outAlias);
+		const bool inDev = inKind == kDevice, outDev = outKind == kDevice;
 		if (inDev && outDev) return ProcessDevice(in, out, SS, FS, SS, FS, S, n);
 		if (inDev != outDev)
 		{
 			SetLastError("ProcessBatch: input and output must both be host or both be device memory");
 			return false;
 		}
-		// host path: H2D -> kernels -> D2H, all on the model's stream, then wait (the reference's Process is synchronous)
+		// host path; the call returns with `out` complete (the reference's Process is synchronous)
 		const size_t total = S * n;
 		if (!EnsureStaging(total)) return false;
+		const bool inPinned = inKind == kPinned && inAlias != nullptr, outPinned = outKind == kPinned && outAlias != nullptr;
+		if (total <= kZeroCopyFloats)
+		{
+			// small call: one kernel pass over page-locked memory, no staging DMA
+			const float* src = inPinned ? static_cast<const float*>(inAlias) : pinnedIn;
+			float* dst = outPinned ? static_cast<float*>(outAlias) : pinnedOut;
+			if (!inPinned) memcpy(pinnedIn, in, total * 4);
+			if (!ProcessDevice(src, dst, SS, FS, SS, FS, S, n)) return false;
+			if (!CudaOk(cudaStreamSynchronize(stream), "cudaStreamSynchronize")) return false;
+			if (!outPinned) memcpy(out, pinnedOut, total * 4);
+			return true;
+		}
+		// H2D -> kernels -> D2H, all on the model's stream, then wait
 		const float* hsrc = in;
-		if (!IsPinnedHost(in))
+		if (!inPinned)
 		{
 			memcpy(pinnedIn, in, total * 4);
 			hsrc = pinnedIn;
 		}
 		if (!CudaOk(cudaMemcpyAsync(devIn, hsrc, total * 4, cudaMemcpyHostToDevice, stream), "cudaMemcpyAsync(H2D)")) return false;
 		if (!ProcessDevice(devIn, devOut, SS, FS, SS, FS, S, n)) return false;
-		const bool outPinned = IsPinnedHost(out);
 		float* hdst = outPinned ? out : pinnedOut;
 		if (!CudaOk(cudaMemcpyAsync(hdst, devOut, total * 4, cudaMemcpyDeviceToHost, stream), "cudaMemcpyAsync(D2H)")) return false;
 		if (!CudaOk(cudaStreamSynchronize(stream), "cudaStreamSynchronize")) return false;
