@@ -92,8 +92,10 @@ def main():
             shutil.copy(os.path.join(OUT, f), os.path.join(PROF, tag + "_" + f))
     if os.path.exists(os.path.join(OUT, "launches.csv")):
         shutil.copy(os.path.join(OUT, "launches.csv"), os.path.join(PROF, tag + "_launches_a1_standard.csv"))
-    if os.path.exists(os.path.join(OUT, "pytest_gpu.log")):
-        shutil.copy(os.path.join(OUT, "pytest_gpu.log"), os.path.join(PROF, tag + "_pytest_gpu.log"))
+    for f, dst in (("pytest_gpu.log", "_pytest_gpu.log"), ("parity.txt", "_parity.txt"), ("latency.txt", "_single_stream_latency.txt"),
+                   ("model_test.txt", "_model_test.txt")):
+        if os.path.exists(os.path.join(OUT, f)):
+            shutil.copy(os.path.join(OUT, f), os.path.join(PROF, tag + dst))
     print(json.dumps({k: v["launches"][0] for k, v in summary.items()}, indent=1)[:3000])
 
 
