@@ -319,7 +319,8 @@ namespace nab200
 		const WnModelDev& M = packed.dev;
 		const int C0 = M.arrays[0].C, C1 = M.numArrays > 1 ? M.arrays[1].C : 0;
 		bool ok = M.tc == 2 ? wavenet_ts_variant_supported(C0, C1, M.arrays[0].act)
-			: M.tc ? wavenet_tc_variant_supported(C0, C1, M.arrays[0].act) : wavenet_variant_supported(C0, C1, M.arrays[0].act);
+			: M.tc ? wavenet_tc_variant_supported(C0, C1, M.arrays[0].act)
+			: (wavenet_variant_supported(C0, C1, M.arrays[0].act) && wavenet_window_jobs(M) <= wavenet_max_window_jobs());
 		if (M.tc == 0 && (!ok || GetOptions().useTc < 0) && wavenet_generic_supported(M))
 		{
 			// no compile-time-shaped kernel (or the generic one was asked for): the run-time-shaped kernel

@@ -39,6 +39,8 @@ namespace nab200
 	cudaError_t int_fill_launch(int* p, int v, long long total, cudaStream_t stream);
 	int wavenet_max_frames_per_pass(int C0);
 	bool wavenet_variant_supported(int C0, int C1, int act);
+	int wavenet_window_jobs(const WnModelDev& M);     // window jobs per stream pass of the CUDA-core kernel ...
+	int wavenet_max_window_jobs();                    // ... and how many its table holds
 
 	struct LstmLaunch
 	{

@@ -138,49 +138,60 @@ namespace nab200
 		int winOff0, winStep; // float offset of window buffer 0 inside sm, and distance to buffer 1
 		int stride;           // channel stride (floats) of xcur / win
 		int n, lane, half, barId;
-		int pl, pt;           // producer cursor (layer, job-in-layer); pl == numLayers -> exhausted
+		const int4* jobs;     // the call's window jobs in consumption order (shared memory, built once per CTA by build_jobs)
+		int numJobs;
+		int pj, cj;           // producer / consumer cursor into jobs for the current stream
 		uint32_t issued, consumed, phase;
 
 		// a layer whose whole history fits one window buffer stages it once and shares it between all taps;
 		// otherwise each tap gets its own window of min((K-1-k)*d, n) frames
-		static __device__ __forceinline__ bool is_whole(int hist) { return hist <= 32 * RT; }
+		static __device__ __host__ __forceinline__ bool is_whole(int hist) { return hist <= 32 * RT; }
 
-		__device__ __forceinline__ int jobs_in_layer(int l) const
+		// One entry per window a stream pass consumes: {ring offset, ring length, distance D back from the ring head,
+		// ring index | channels << 8 | frames << 16}.  Conv windows of layer l come first (one if the whole history fits a
+		// buffer, else one per delayed tap, oldest tap first), then the head-conv window of an array's last layer.
+		static __device__ int build_jobs(const WnModelDev& M, int n, int4* table, int cap)
 		{
-			const WnLayer& L = M->layers[l];
-			const int hist = (L.K - 1) * L.d;
-			int nj = hist == 0 ? 0 : (is_whole(hist) ? 1 : (L.K - 1));
-			if ((L.flags & kLastInArray) && M->arrays[L.array].Kh > 1) nj++;
+			int nj = 0;
+			for (int l = 0; l < M.numLayers; l++)
+			{
+				const WnLayer& L = M.layers[l];
+				const WnArray& A = M.arrays[L.array];
+				const int hist = (L.K - 1) * L.d;
+				if (hist > 0)
+				{
+					if (is_whole(hist))
+					{
+						if (nj < cap) table[nj] = make_int4(L.ringOff, L.Lp, hist, L.ringIdx | (A.C << 8) | (hist << 16));
+						nj++;
+					}
+					else
+						for (int t = 0; t < L.K - 1; t++)
+						{
+							const int D = (L.K - 1 - t) * L.d;
+							const int count = D < n ? D : n;
+							if (nj < cap) table[nj] = make_int4(L.ringOff, L.Lp, D, L.ringIdx | (A.C << 8) | (count << 16));
+							nj++;
+						}
+				}
+				if ((L.flags & kLastInArray) && A.Kh > 1)
+				{
+					if (nj < cap) table[nj] = make_int4(A.headRingOff, A.headLp, A.Kh - 1, A.headRingIdx | (A.C << 8) | ((A.Kh - 1) << 16));
+					nj++;
+				}
+			}
 			return nj;
 		}
 
-		// (l, t) -> window geometry.  t < convJobs: conv window; t == convJobs: head-conv window.
-		__device__ __forceinline__ JobParams params(int l, int t) const
+		__device__ __forceinline__ JobParams params(int j) const
 		{
-			const WnLayer& L = M->layers[l];
-			const WnArray& A = M->arrays[L.array];
-			const int hist = (L.K - 1) * L.d;
-			const int convJobs = hist == 0 ? 0 : (is_whole(hist) ? 1 : (L.K - 1));
+			const int4 e = jobs[j];
 			JobParams p;
-			int D, count, head;
-			if (t < convJobs)
-			{
-				p.ring = st + L.ringOff;
-				p.Lp = L.Lp;
-				head = hd[L.ringIdx];
-				if (is_whole(hist)) { D = hist; count = hist; }
-				else { D = (L.K - 1 - t) * L.d; count = D < n ? D : n; }
-			}
-			else
-			{
-				p.ring = st + A.headRingOff;
-				p.Lp = A.headLp;
-				head = hd[A.headRingIdx];
-				D = A.Kh - 1;
-				count = D;
-			}
-			p.C = A.C;
-			int idx0 = head - D;
+			p.ring = st + e.x;
+			p.Lp = e.y;
+			p.C = (e.w >> 8) & 255;
+			const int count = (int)((unsigned)e.w >> 16);
+			int idx0 = hd[e.w & 255] - e.z;
 			if (idx0 < 0) idx0 += p.Lp;
 			p.shift = idx0 & 3;
 			p.a0 = idx0 & ~3;
@@ -190,18 +201,17 @@ namespace nab200
 
 		__device__ __forceinline__ void start()
 		{
-			pl = 0; pt = 0;
-			while (pl < M->numLayers && jobs_in_layer(pl) == 0) pl++;
+			pj = 0; cj = 0;
 			issue_next();
 		}
 
 		// issue the producer cursor's job (if any) into the next buffer and advance the cursor
 		__device__ __forceinline__ void issue_next()
 		{
-			if (pl >= M->numLayers) return;
+			if (pj >= numJobs) return;
 			if (TMA)
 			{
-				const JobParams p = params(pl, pt);
+				const JobParams p = params(pj);
 				const int buf = issued & 1;
 				const int seg1 = min(p.len, p.Lp - p.a0);
 				const int seg2 = p.len - seg1;
@@ -218,8 +228,7 @@ namespace nab200
 				}
 			}
 			issued++;
-			pt++;
-			while (pl < M->numLayers && pt >= jobs_in_layer(pl)) { pl++; pt = 0; }
+			pj++;
 		}
 
 		// wait for job (l, t) -- which must be the next one in order -- then prefetch the one after it.
@@ -227,7 +236,9 @@ namespace nab200
 		__device__ __forceinline__ int acquire(int l, int t)
 		{
 			const int buf = consumed & 1;
-			const JobParams p = params(l, t);
+			const JobParams p = params(cj);
+			cj++;
+			(void)l; (void)t;
 			team_sync<WPS>(barId);   // every lane of the team is done with the buffer the NEXT issue will overwrite
 			if (TMA)
 			{
@@ -638,6 +649,7 @@ namespace nab200
 
 	constexpr int kWnStreamsPerCta = 4;   // two CTAs per SM: each has its own weight pipeline, so the CTAs drift out of phase
 	constexpr int kWnCtasPerSm = 2;
+	constexpr int kMaxWinJobs = 160;   // window jobs per stream pass (A1: 26, A2: 48); models that need more take the run-time-shaped kernel
 
 	template <int C0, int C1, int RT>
 	struct WnSmem
@@ -696,9 +708,17 @@ namespace nab200
 		pipe.issued = 0;
 		pipe.consumed = 0;
 		pipe.phase = 0;
-		pipe.pl = M.numLayers;
-		pipe.pt = 0;
 		pipe.st = state;
+		{
+			// the window job table of this call, shared by every stream the CTA processes
+			int4* table = reinterpret_cast<int4*>(smem_raw + (size_t)2 * M.maxBlock * 4 + (size_t)kWnStreamsPerCta * SM::kStreamBytes);
+			int* count = reinterpret_cast<int*>(table + kMaxWinJobs);
+			if (tid == 0) *count = WindowPipe<RT, WPS, TMA>::build_jobs(M, n, table, kMaxWinJobs);
+			pipe.jobs = table;
+			pipe.numJobs = 0;
+			pipe.pj = 0;
+			pipe.cj = 0;
+		}
 
 		if (TMA)
 		{
@@ -711,6 +731,7 @@ namespace nab200
 			asm volatile("fence.proxy.async;" ::: "memory");
 		}
 		__syncthreads();
+		pipe.numJobs = *reinterpret_cast<const int*>(pipe.jobs + kMaxWinJobs);
 
 		issue_weight_block(cx, 0, 0);
 
@@ -905,7 +926,7 @@ namespace nab200
 	static cudaError_t launch_variant(const WnModelDev& M, const WnLaunch& a)
 	{
 		using SM = WnSmem<C0, C1, RT>;
-		const size_t smem = (size_t)2 * M.maxBlock * 4 + (size_t)kWnStreamsPerCta * SM::kStreamBytes;
+		const size_t smem = (size_t)2 * M.maxBlock * 4 + (size_t)kWnStreamsPerCta * SM::kStreamBytes + (size_t)kMaxWinJobs * 16 + 16;
 		const int numGroups = (a.S + kWnStreamsPerCta - 1) / kWnStreamsPerCta;
 		const int maxCtas = a.numSMs * kWnCtasPerSm;
 		int grid = numGroups < maxCtas ? numGroups : maxCtas;
@@ -943,6 +964,22 @@ namespace nab200
 		return C0 <= 8 ? 256 : 128;
 	}
 
+	// worst case over the launch variants (one frame row per stream: only histories of <= 32 frames share a window)
+	int wavenet_window_jobs(const WnModelDev& M)
+	{
+		int nj = 0;
+		for (int l = 0; l < M.numLayers; l++)
+		{
+			const WnLayer& L = M.layers[l];
+			const int hist = (L.K - 1) * L.d;
+			if (hist > 0) nj += hist <= 32 ? 1 : L.K - 1;
+			if ((L.flags & kLastInArray) && M.arrays[L.array].Kh > 1) nj++;
+		}
+		return nj;
+	}
+
+	int wavenet_max_window_jobs() { return kMaxWinJobs; }
+
 	bool wavenet_variant_supported(int C0, int C1, int act)
 	{
 		if (act == 0) return (C0 == 16 && C1 == 8) || (C0 == 12 && C1 == 8) || (C0 == 8 && C1 == 4) || (C0 == 4 && C1 == 2);
@@ -951,6 +988,7 @@ namespace nab200
 
 	cudaError_t wavenet_launch(const WnModelDev& M, const WnLaunch& a)
 	{
+		if (wavenet_window_jobs(M) > kMaxWinJobs) return cudaErrorNotSupported;
 		const int C0 = M.arrays[0].C;
 		const int C1 = M.numArrays > 1 ? M.arrays[1].C : 0;
 		const int act = M.arrays[0].act;
