@@ -486,6 +486,7 @@ namespace nab200
 				float* __restrict__ ring = pipe.st + L.ringOff;
 				const int Lp = L.Lp;
 				const int hd = pipe.hd[L.ringIdx];
+				const int hdEnd = pipe.hd[kMaxRings + L.ringIdx] - n;   // frame f lands n - f columns before the head after the call
 				const int first = n > Lp ? n - Lp : 0;
 				if (((hd | n) & 3) == 0)
 				{
@@ -496,7 +497,8 @@ namespace nab200
 						const int f0 = 4 * (lane + 32 * rr);
 						if (f0 < n && f0 >= first && f0 < 32 * RT)
 						{
-							const int idx = (hd + f0) % Lp;
+							int idx = hdEnd + f0;
+							if (idx < 0) idx += Lp;
 #pragma unroll
 							for (int c = half; c < C; c += WPS)
 							{
@@ -514,7 +516,8 @@ namespace nab200
 						const int f = fr[r];
 						if (f < n && f >= first)
 						{
-							const int idx = (hd + f) % Lp;
+							int idx = hdEnd + f;
+							if (idx < 0) idx += Lp;
 #pragma unroll
 							for (int c = 0; c < C; c++) ring[(size_t)c * Lp + idx] = sm[c * STR + f];
 						}
@@ -624,7 +627,7 @@ namespace nab200
 					// head history write-back
 					float* __restrict__ ring = pipe.st + A.headRingOff;
 					const int Lp = A.headLp;
-					const int hd = pipe.hd[A.headRingIdx];
+					const int hdEnd = pipe.hd[kMaxRings + A.headRingIdx] - n;
 					const int first = n > Lp ? n - Lp : 0;
 #pragma unroll
 					for (int r = 0; r < RW; r++)
@@ -632,7 +635,8 @@ namespace nab200
 						const int f = fr[r];
 						if (f < n && f >= first)
 						{
-							const int idx = (hd + f) % Lp;
+							int idx = hdEnd + f;
+							if (idx < 0) idx += Lp;
 #pragma unroll
 							for (int c = 0; c < C2; c++)
 							{
@@ -657,7 +661,7 @@ namespace nab200
 		static constexpr int CM = C0 > C1 ? C0 : C1;
 		static constexpr int STR = 32 * RT + 4;
 		static constexpr int kArenaFloats = 3 * CM * STR;
-		static constexpr int kStreamBytes = ((kArenaFloats * 4 + kMaxRings * 4 + 16 + 15) / 16) * 16;
+		static constexpr int kStreamBytes = ((kArenaFloats * 4 + 2 * kMaxRings * 4 + 16 + 15) / 16) * 16;   // arena | ring heads now | after the call | 2 mbarriers
 	};
 
 	// C1 == 0: single-array model (A2).  ACT: 0 tanh, 1 LeakyReLU.  RT frame rows per stream, WPS warps per stream.
@@ -691,7 +695,7 @@ namespace nab200
 		unsigned char* wbase = smem_raw + (size_t)2 * M.maxBlock * 4 + (size_t)team * SM::kStreamBytes;
 		float* sm = reinterpret_cast<float*>(wbase);
 		int* hd = reinterpret_cast<int*>(wbase + SM::kArenaFloats * 4);
-		unsigned long long* bars = reinterpret_cast<unsigned long long*>(wbase + SM::kArenaFloats * 4 + kMaxRings * 4);
+		unsigned long long* bars = reinterpret_cast<unsigned long long*>(wbase + SM::kArenaFloats * 4 + 2 * kMaxRings * 4);
 
 		WindowPipe<RT, WPS, TMA> pipe;
 		pipe.M = &M;
@@ -748,7 +752,16 @@ namespace nab200
 				pipe.st = state + (size_t)s * M.stateStride;
 				team_sync<WPS>(pipe.barId);   // previous stream's last readers of hd are done
 				if (half == 0)
-					for (int i = lane; i < M.numRings; i += 32) hd[i] = heads[(size_t)s * M.numRings + i];
+					for (int i = lane; i < M.numRings; i += 32)
+					{
+						// ring head now, and after this call's n frames (the write-back addresses count back from the latter)
+						const int h0 = heads[(size_t)s * M.numRings + i];
+						const int Lp = M.ringLp[i];
+						int h1 = h0 + (n % Lp);
+						if (h1 >= Lp) h1 -= Lp;
+						hd[i] = h0;
+						hd[kMaxRings + i] = h1;
+					}
 				team_sync<WPS>(pipe.barId);
 #pragma unroll
 				for (int r = 0; r < RW; r++)
@@ -799,13 +812,7 @@ namespace nab200
 				}
 				// advance every ring head by n frames
 				if (half == 0)
-					for (int i = lane; i < M.numRings; i += 32)
-					{
-						const int Lp = M.ringLp[i];
-						int h = hd[i] + (n % Lp);
-						if (h >= Lp) h -= Lp;
-						heads[(size_t)s * M.numRings + i] = h;
-					}
+					for (int i = lane; i < M.numRings; i += 32) heads[(size_t)s * M.numRings + i] = hd[kMaxRings + i];
 			}
 		}
 		cp_async_wait_all();
