@@ -190,7 +190,7 @@ def run_reference(args, rank, world):
         T = host_threads()
         ipt = args.ref_instances_per_thread
         if not O.ref_available():
-            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libna_ref.so not built and /root/reference absent"}))
+            emit({"impl": "reference", "unavailable": "oracle/_ref/libna_ref.so not built and /root/reference absent"})
             return
         secs = O.ref_bench_steps(path, frames, T, ipt, args.warmup, args.steps, quality=quality)
         units = T * ipt * frames * args.steps
@@ -207,7 +207,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def run_b200(args, rank, local_rank, world):
@@ -368,7 +368,7 @@ def run_b200(args, rank, local_rank, world):
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(path, frames, quality, args.cpu_seconds)
-        print(json.dumps(line))
+        emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -399,7 +399,23 @@ def cpu_baseline(path, frames, quality, seconds):
             "one_thread_value": one, "thread_scaling": total / one if one > 0 else None, "isa": os.path.basename(O.ref_lib_path())}
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The one JSON line of the contract, on the process's real stdout."""
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    # stdout carries exactly one JSON line: anything a library writes to file descriptor 1 (NCCL prints its version banner
+    # there when NCCL_DEBUG is set on the box) is sent to stderr instead
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
