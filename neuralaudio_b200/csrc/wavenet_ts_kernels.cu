@@ -238,6 +238,13 @@ namespace nab200
 #ifndef NAB_TS_FEW_HANDOFFS
 #define NAB_TS_FEW_HANDOFFS 0
 #endif
+#ifndef NAB_TS_EARLY_PREFETCH
+#define NAB_TS_EARLY_PREFETCH 1
+#endif
+		// 1: the next layer's history windows are requested as soon as every stager has staged this layer's taps (one
+		// stagers-only barrier), i.e. before the wait for the conv accumulator instead of after it: ~400 more cycles of lead
+		// for the HBM reads and the issue cost of the copies moves into the stagers' idle time.
+		constexpr bool kEarlyPrefetch = NAB_TS_EARLY_PREFETCH != 0;
 		constexpr bool kFewHandoffs = NAB_TS_FEW_HANDOFFS == 1;
 		constexpr bool kMergeT2 = NAB_TS_FEW_HANDOFFS == 2;   // the undelayed tap's low part rides on tap 0's hand-off
 
@@ -561,6 +568,12 @@ namespace nab200
 				stage_tap<C>(row + g0.z, g0.w, lanebase + TC::T1);
 				stager_arrive(kBarT1);
 				TS_STAMP(6);
+				if (kEarlyPrefetch)
+				{
+					// every stager is done reading the shared-memory windows of this layer
+					asm volatile("bar.sync 1, 128;" ::: "memory");   // kBarMix, kStagerThreads
+					prefetch_layer<0>(cx, l + 1, s);
+				}
 				// history write-back (AdvanceFrames, WaveNet.h:59-65): frame t becomes ring column (head + t) mod Lp.  Off the
 				// critical path (the issuer is busy with the conv now) and after the window wait: the copies that read this ring
 				// must not race with the rows being replaced (a row is replaced by the thread that copied it or, behind the
@@ -603,7 +616,7 @@ namespace nab200
 					// copy the next layer's (or the next stream's first layer's) history while the accumulator load is in flight.
 					// (Tried: an L2 hint two layers ahead plus this copy after the hand-off below - no gain, the kernel is bound
 					// by issue slots under contention, not by this latency; tools/ts_timing.cu.)
-					prefetch_layer<0>(cx, l + 1, s);
+					if (!kEarlyPrefetch) prefetch_layer<0>(cx, l + 1, s);
 					wait_ld();
 					// z is the 1x1's A operand [hi | lo]; it is delivered in K-steps of 8 channels so that the issuer starts on the
 					// first while the second is still being activated
