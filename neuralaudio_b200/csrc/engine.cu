@@ -22,6 +22,7 @@ namespace nab200
 			env("NAB200_TS_SPLIT", v.tsSplit);
 			env("NAB200_USE_TMA", v.useTma);
 			env("NAB200_MAX_GRID_CTAS", v.maxGridCtas);
+			env("NAB200_LSTM_KERNEL", v.lstmKernel);
 			return v;
 		}();
 		return o;
@@ -36,6 +37,7 @@ namespace nab200
 		else if (strcmp(name, "ts_issuers") == 0) { prev = o.tsIssuers; o.tsIssuers = value; }
 		else if (strcmp(name, "ts_split") == 0) { prev = o.tsSplit; o.tsSplit = value; }
 		else if (strcmp(name, "max_grid_ctas") == 0) { prev = o.maxGridCtas; o.maxGridCtas = value; }
+		else if (strcmp(name, "lstm_kernel") == 0) { prev = o.lstmKernel; o.lstmKernel = value; }
 		return prev;
 	}
 
@@ -538,6 +540,7 @@ namespace nab200
 		a.n = 2048;
 		a.zeroInput = true;
 		a.generic = GetOptions().useTc < 0;
+		a.kernel = GetOptions().lstmKernel;
 		a.numSMs = numSMs;
 		a.stream = stream;
 		a.state = dBlob + weightFloats;
@@ -563,6 +566,7 @@ namespace nab200
 		a.n = (int)n;
 		a.zeroInput = false;
 		a.generic = GetOptions().useTc < 0;
+		a.kernel = GetOptions().lstmKernel;
 		a.numSMs = numSMs;
 		a.stream = stream;
 		return CudaOk(lstm_launch(packed.dev, a), "lstm_fwd_kernel launch");

@@ -23,6 +23,7 @@ namespace nab200
 		int tsSplit = 0;        // TS kernel: 1 = one launch per layer array, the 8-channel one with 6 CTAs per SM (measured 5 % slower
 		                        // than the fused kernel: 144 + 90 us vs 208 us; kept as an option, its head sum is exact fp32)
 		int maxGridCtas = 0;    // 0: one CTA per SM
+		int lstmKernel = 0;     // LSTM kernel: 0 automatic, 1 gate rows in registers, 2 lane = stream (matrices in shared memory), 3 run-time-shaped
 	};
 	Options& GetOptions();
 	int SetOption(const char* name, int value);

@@ -52,7 +52,8 @@ namespace nab200
 		int S;
 		int n;
 		bool zeroInput;         // ignore `in`, feed zeros (prewarm)
-		bool generic;           // force the run-time-shaped kernel (use_tc = -1), which otherwise serves L > 2 or H > 32
+		bool generic;           // force the run-time-shaped kernel (use_tc = -1)
+		int kernel;             // 0 automatic, 1 gate rows in registers, 2 lane = stream with shared-memory matrices, 3 run-time-shaped
 		int numSMs;
 		cudaStream_t stream;
 	};

@@ -350,6 +350,41 @@ def test_runtime_shaped_lstm_kernel(na, O, name, streams, tmp_path):
         assert float(np.abs(y3 - y).max()) <= LSTM_TOL
 
 
+@pytest.mark.parametrize("name,streams", [("syn_lstm_1x16", 70), ("syn_lstm_1x24", 65), ("syn_lstm_2x12", 37), ("syn_lstm_2x8", 129),
+                                          ("syn_dyn_lstm_3x18", 23), ("syn_dyn_lstm_1x40", 7), ("syn_dyn_lstm_2x32", 64), ("syn_dyn_lstm_4x6", 3)])
+def test_lane_per_stream_lstm_kernel(na, O, name, streams, tmp_path):
+    """The lane = stream LSTM kernel (gate matrices once per CTA in shared memory; the default past the register cliff: 1x24,
+    2x12, 2x16, run-time sizes up to 64 units) forced for every shape: ragged stream counts around its 64-stream CTAs, both
+    layouts, odd call sizes, every probed stream against its own oracle instance; and against the gate-rows-in-registers kernel."""
+    g = load_golden(golden_files(name)[0])
+    mf = model_file_for(g, tmp_path)
+    sizes = [96, 1, 37, 128, 70]
+    rng = np.random.default_rng(43)
+    xs = [(rng.uniform(-1, 1, (streams, n)) * 0.5).astype(np.float32) for n in sizes]
+    outs = {}
+    for kern in (2, 1):
+        prev = na.set_option("lstm_kernel", kern)
+        try:
+            m = _load(na, mf, streams=streams)
+            m2 = _load(na, mf, streams=streams)
+            ys, yts = [], []
+            for x in xs:
+                y = np.empty_like(x)
+                m.ProcessBatch(x, y, streams, x.shape[1])
+                ys.append(y)
+                yt = np.empty((x.shape[1], streams), dtype=np.float32)
+                m2.ProcessBatch(np.ascontiguousarray(x.T), yt, streams, x.shape[1], na.FRAME_MAJOR)
+                yts.append(yt.T)
+        finally:
+            na.set_option("lstm_kernel", prev)
+        outs[kern] = np.concatenate(ys, axis=1)
+        assert np.array_equal(outs[kern], np.concatenate(yts, axis=1))
+    for s in sorted({0, streams // 2, streams - 1}):
+        ref = O.PortModel.from_file(mf).process(np.concatenate([x[s] for x in xs]))
+        assert float(np.abs(ref - outs[2][s]).max()) <= LSTM_TOL
+    assert float(np.abs(outs[1] - outs[2]).max()) <= LSTM_TOL   # (kernel 1 falls back to the automatic choice where it has no variant)
+
+
 @pytest.mark.parametrize("kind", ["zero", "huge", "tiny"])
 def test_lstm_activation_edge_ranges(na, O, kind, tmp_path):
     """The LSTM kernel computes its gate activations in packed pairs with a hand-scheduled IEEE quotient that is valid
