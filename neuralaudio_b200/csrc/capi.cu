@@ -439,7 +439,8 @@ int NA_DescribeModelFile(const wchar_t* modelPath, int externalSampleRate, char*
 					nab200::LstmDesc d = nab200::ParseNamLstm(mj);
 					nab200::PackedLstm p = nab200::PackLstm(d);
 					os << "{\"kind\":\"lstm\",\"static\":" << (d.isStatic ? "true" : "false") << ",\"layers\":" << d.numLayers << ",\"hidden\":" << d.hiddenSize
-					   << ",\"lanes\":" << p.dev.G << ",\"packed_floats\":" << p.weights.size() << ",\"state_floats\":" << p.dev.stateStride << "}";
+					   << ",\"lanes\":" << p.dev.G << ",\"packed_floats\":" << p.weights.size() << ",\"state_floats\":" << p.dev.stateStride
+					   << ",\"kernel\":\"" << nab200::lstm_kernel_name(p.dev) << "\"}";
 					return;
 				}
 				throw std::runtime_error("unsupported model: architecture '" + arch + "'");
@@ -447,7 +448,8 @@ int NA_DescribeModelFile(const wchar_t* modelPath, int externalSampleRate, char*
 			nab200::LstmDesc d = nab200::ParseKerasLstm(mj);
 			nab200::PackedLstm p = nab200::PackLstm(d);
 			os << "{\"kind\":\"lstm\",\"static\":" << (d.isStatic ? "true" : "false") << ",\"layers\":" << d.numLayers << ",\"hidden\":" << d.hiddenSize
-			   << ",\"lanes\":" << p.dev.G << ",\"packed_floats\":" << p.weights.size() << ",\"state_floats\":" << p.dev.stateStride << "}";
+			   << ",\"lanes\":" << p.dev.G << ",\"packed_floats\":" << p.weights.size() << ",\"state_floats\":" << p.dev.stateStride
+					   << ",\"kernel\":\"" << nab200::lstm_kernel_name(p.dev) << "\"}";
 		};
 		if (ext == ".nam" && j.at("architecture").as_string() == "SlimmableContainer")
 		{

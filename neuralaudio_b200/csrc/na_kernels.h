@@ -60,4 +60,5 @@ namespace nab200
 
 	cudaError_t lstm_launch(const LstmModelDev& M, const LstmLaunch& a);
 	bool lstm_variant_supported(int L, int G);
+	const char* lstm_kernel_name(const LstmModelDev& M);   // the kernel the automatic choice runs for this shape
 }

@@ -194,3 +194,15 @@ def test_cpp_consumer_builds_links_and_fails_loudly_without_gpu(tmp_path):
         mf = model_file_for(g, tmp_path)
         r = subprocess.run([exe, mf], capture_output=True, text=True, timeout=120)
         assert "Unable to load model from" in r.stdout and r.returncode == 1
+
+
+def test_lstm_kernel_choice_by_shape(na, tmp_path):
+    """Host logic of the LSTM dispatch: gate rows in registers where they fit (up to 16 units in one layer, 8 in two), the
+    lane-per-stream kernel with shared-memory matrices past that register cliff and for run-time sizes."""
+    want = {"syn_lstm_1x16": "lstm_gate_rows_in_registers", "syn_lstm_2x8": "lstm_gate_rows_in_registers",
+            "syn_lstm_1x24": "lstm_lane_per_stream", "syn_lstm_2x12": "lstm_lane_per_stream",
+            "syn_dyn_lstm_3x18": "lstm_lane_per_stream", "syn_dyn_lstm_1x40": "lstm_lane_per_stream", "syn_dyn_lstm_4x6": "lstm_lane_per_stream"}
+    for name, kernel in want.items():
+        g = load_golden(golden_files(name)[0])
+        d = na.describe_model_file(model_file_for(g, tmp_path))
+        assert d["kernel"] == kernel, (name, d["kernel"])
