@@ -663,7 +663,10 @@ namespace nab200
 	constexpr int kWnStreamsPerCta = 4;   // two CTAs per SM: each has its own weight pipeline, so the CTAs drift out of phase
 	constexpr int kWnCtasPerSm = 2;
 	// resident CTAs per SM the kernel is compiled for: the narrow shapes (<= 4 channels in the first array) have registers to spare
-	template <int C0> constexpr int wn_ctas_per_sm() { return C0 <= 4 ? NAB_WN_SMALL_CTAS : kWnCtasPerSm; }
+#ifndef NAB_WN_MID_CTAS
+#define NAB_WN_MID_CTAS 3
+#endif
+	template <int C0, int RT> constexpr int wn_ctas_per_sm() { return C0 <= 4 ? NAB_WN_SMALL_CTAS : (C0 <= 8 && RT <= 4) ? NAB_WN_MID_CTAS : kWnCtasPerSm; }
 	constexpr int kMaxWinJobs = 160;   // window jobs per stream pass (A1: 26, A2: 48); models that need more take the run-time-shaped kernel
 
 	template <int C0, int C1, int RT>
@@ -677,7 +680,7 @@ namespace nab200
 
 	// C1 == 0: single-array model (A2).  ACT: 0 tanh, 1 LeakyReLU.  RT frame rows per stream, WPS warps per stream.
 	template <int C0, int C1, int RT, int WPS, int ACT, bool TMA>
-	__global__ void __launch_bounds__(kWnStreamsPerCta * WPS * 32, (WPS == 2 ? wn_ctas_per_sm<C0>() : 1))
+	__global__ void __launch_bounds__(kWnStreamsPerCta * WPS * 32, (WPS == 2 ? wn_ctas_per_sm<C0, RT>() : 1))
 		wavenet_fwd_kernel(const __grid_constant__ WnModelDev M, const float* __restrict__ Wg, float* __restrict__ state,
 			int* __restrict__ heads, const float* in, float* out, long long inSS, long long inFS, long long outSS, long long outFS,
 			int S, int n)
@@ -946,7 +949,7 @@ namespace nab200
 		using SM = WnSmem<C0, C1, RT>;
 		const size_t smem = (size_t)2 * M.maxBlock * 4 + (size_t)kWnStreamsPerCta * SM::kStreamBytes + (size_t)kMaxWinJobs * 16 + 16;
 		const int numGroups = (a.S + kWnStreamsPerCta - 1) / kWnStreamsPerCta;
-		const int maxCtas = a.numSMs * wn_ctas_per_sm<C0>();
+		const int maxCtas = a.numSMs * wn_ctas_per_sm<C0, RT>();
 		int grid = numGroups < maxCtas ? numGroups : maxCtas;
 		if (grid < 1) grid = 1;
 		const int threads = kWnStreamsPerCta * WPS * 32;
