@@ -132,7 +132,9 @@ def dynamic_lstm_cases():
     """LSTM sizes outside the reference's static list (NeuralModel.cpp:25-38): its dynamic path (LSTMDynamic.h)."""
     rng = np.random.default_rng(20261019)
     cases = {}
-    for name, (L, H) in {"dyn_lstm_3x18": (3, 18), "dyn_lstm_1x40": (1, 40), "dyn_lstm_4x6": (4, 6), "dyn_lstm_2x32": (2, 32)}.items():
+    # (lstm_1x8 / lstm_2x16 are static shapes of the reference, added with this batch so that every static LSTM size has a vector)
+    for name, (L, H) in {"dyn_lstm_3x18": (3, 18), "dyn_lstm_1x40": (1, 40), "dyn_lstm_4x6": (4, 6), "dyn_lstm_2x32": (2, 32),
+                         "lstm_1x8": (1, 8), "lstm_2x16": (2, 16)}.items():
         n = H + 1
         for l in range(L):
             i = 1 if l == 0 else H
@@ -199,7 +201,7 @@ def main():
         os.rmdir(tmpdir)
         return
     made = []
-    fixtures = [] if ("--dynamic-only" in sys.argv or "--dynamic-lstm-only" in sys.argv) else [("BossWN-nano.nam", 1.0), ("BossWN-feather.nam", 1.0), ("BossWN-standard.nam", 1.0), ("BossWN-a2.nam", 1.0),
+    fixtures = [] if ("--dynamic-only" in sys.argv or "--dynamic-lstm-only" in sys.argv or "--extra-lstm-only" in sys.argv) else [("BossWN-nano.nam", 1.0), ("BossWN-feather.nam", 1.0), ("BossWN-standard.nam", 1.0), ("BossWN-a2.nam", 1.0),
                 ("BossWN-a2.nam", 0.0), ("BossLSTM-1x16.nam", 1.0), ("BossLSTM-2x8.nam", 1.0),
                 ("tw40_blues_deluxe_deerinkstudios.json", 1.0), ("namcore_wavenet.nam", 1.0), ("namcore_lstm.nam", 1.0),
                 ("namcore_wavenet_a1_standard.nam", 1.0)]
@@ -217,13 +219,17 @@ def main():
         made.append(out)
     only_dynamic = "--dynamic-only" in sys.argv   # adds the run-time-shaped cases without touching the earlier vectors
     only_dyn_lstm = "--dynamic-lstm-only" in sys.argv
-    if only_dynamic or only_dyn_lstm:
+    only_extra = "--extra-lstm-only" in sys.argv     # the two static LSTM sizes added last (lstm_1x8, lstm_2x16)
+    extra_only = ("lstm_1x8", "lstm_2x16")
+    if only_dynamic or only_dyn_lstm or only_extra:
         made = []
     allcases = list(synthetic_cases().items()) + list(dynamic_cases().items()) + list(dynamic_lstm_cases().items())
     for j, (name, case) in enumerate(allcases):
         if only_dynamic and not name.startswith("dyn_"):
             continue
         if only_dyn_lstm and not name.startswith("dyn_lstm"):
+            continue
+        if only_extra and name not in extra_only:
             continue
         path = os.path.join(tmpdir, name + ".nam")
         with open(path, "w") as f:
