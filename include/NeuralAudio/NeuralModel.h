@@ -65,40 +65,91 @@ inline namespace b200
 
 	class NEURALAUDIO_B200_API NeuralModel
 	{
+	protected:
+		// levels and identity the loader fills in from the model file (reference NeuralModel.h:138-145)
+		std::vector<std::pair<std::string, std::string>> metadata;
+		std::string modelVersion = "";
+		float sampleRate = 48000;
+		float modelLoudnessDB = -18;
+		float modelOutputLevelDBu = 12;
+		float modelInputLevelDBu = 12;
+		float audioInputLevelDBu = (float)DEFAULT_INPUT_DBU;
+
 	public:
 		virtual ~NeuralModel() {}
 
-		virtual EModelLoadMode GetLoadMode() { return EModelLoadMode::Internal; }
-		virtual bool HasQualityScaling() { return false; }
-		virtual float GetQualityScaleFactor() { return 1.0f; }
-		virtual bool IsQualityChangeRealtimeSafe(float) { return true; }
-		virtual void SetQualityScaleFactor(float) {}
-		virtual bool IsStatic() { return false; }
-		virtual void SetMaxAudioBufferSize(const int) {}
-		virtual void SetAudioInputLevelDBu(float audioDBu) { audioInputLevelDBu = audioDBu; }
-		virtual float GetAudioInputLevelDBu() { return audioInputLevelDBu; }
-		virtual float GetRecommendedInputDBAdjustment() { return audioInputLevelDBu - modelInputLevelDBu; }
-		virtual float GetRecommendedOutputDBAdjustment() { return -18 - modelLoudnessDB; }
-		virtual float GetSampleRate() { return sampleRate; }
-		virtual int GetReceptiveFieldSize() { return -1; }   // -1: no fixed receptive field (LSTM)
-		virtual std::string GetModelVersion() { return modelVersion; }
-		virtual std::string GetMetadata(const std::string& fieldName)
-		{
-			for (const auto& kv : metadata)
-				if (kv.first == fieldName) return kv.second;
-			return "";
-		}
-
+		// ---- the hot path (reference NeuralModel.h:127, 134) ---------------------------------------------------
 		// One mono stream (stream slot 0), host OR device pointers, in == out allowed.  Synchronous: `output` is
-		// complete on return, like the reference (NeuralModel.h:127).
+		// complete on return, like the reference.
 		virtual void Process(float* input, float* output, size_t numSamples)
 		{
 			(void)input; (void)output; (void)numSamples;
 		}
-
 		// WaveNet: full state reset to "silence forever"; LSTM: 2048 more zero samples (reference semantics).
 		// Applies to every stream slot.
 		virtual void Prewarm() {}
+
+		// ---- what kind of model this is (reference NeuralModel.h:40, 67-72, 97-122) --------------------------------
+		virtual EModelLoadMode GetLoadMode()
+		{
+			return EModelLoadMode::Internal;
+		}
+		virtual bool IsStatic()
+		{
+			return false;
+		}
+		virtual int GetReceptiveFieldSize()
+		{
+			return -1;   // no fixed receptive field (LSTM, run-time-shaped WaveNet)
+		}
+		virtual float GetSampleRate()
+		{
+			return sampleRate;
+		}
+		virtual std::string GetModelVersion()
+		{
+			return modelVersion;
+		}
+		virtual std::string GetMetadata(const std::string& fieldName)
+		{
+			for (const auto& entry : metadata)
+				if (entry.first == fieldName) return entry.second;
+			return std::string();
+		}
+		virtual void SetMaxAudioBufferSize(const int) {}   // batch kernels take any call size; kept for source compatibility
+
+		// ---- quality scaling of slimmable containers (reference NeuralModel.h:45-65) ---------------------------
+		virtual bool HasQualityScaling()
+		{
+			return false;
+		}
+		virtual float GetQualityScaleFactor()
+		{
+			return 1.0f;
+		}
+		virtual void SetQualityScaleFactor(float) {}
+		virtual bool IsQualityChangeRealtimeSafe(float)
+		{
+			return true;
+		}
+
+		// ---- level calibration (reference NeuralModel.h:77-95) ------------------------------------------------
+		virtual float GetAudioInputLevelDBu()
+		{
+			return audioInputLevelDBu;
+		}
+		virtual void SetAudioInputLevelDBu(float audioDBu)
+		{
+			audioInputLevelDBu = audioDBu;
+		}
+		virtual float GetRecommendedInputDBAdjustment()
+		{
+			return audioInputLevelDBu - modelInputLevelDBu;
+		}
+		virtual float GetRecommendedOutputDBAdjustment()
+		{
+			return -18 - modelLoudnessDB;
+		}
 
 		// ---- additive batch API (no counterpart in the reference) -------------------------------------------
 		// Allocate and prewarm `numStreams` independent stream slots (default 1).  Returns false on failure
@@ -128,15 +179,6 @@ inline namespace b200
 		virtual int GetDevice() { return -1; }
 		virtual size_t GetStateBytesPerStream() { return 0; }
 		virtual std::string GetLastError() { return ""; }
-
-	protected:
-		float audioInputLevelDBu = (float)DEFAULT_INPUT_DBU;
-		float modelInputLevelDBu = 12;
-		float modelOutputLevelDBu = 12;
-		float modelLoudnessDB = -18;
-		float sampleRate = 48000;
-		std::string modelVersion = "";
-		std::vector<std::pair<std::string, std::string>> metadata;
 	};
 
 	class NEURALAUDIO_B200_API NeuralModelLoader
