@@ -1003,7 +1003,9 @@ namespace nab200
 
 	bool wavenet_variant_supported(int C0, int C1, int act)
 	{
-		if (act == 0) return (C0 == 16 && C1 == 8) || (C0 == 12 && C1 == 8) || (C0 == 8 && C1 == 4) || (C0 == 4 && C1 == 2);
+		// tanh: the official A1 pairs, plus equal-width pairs and single arrays for run-time-shaped stacks whose padded widths match
+		if (act == 0) return (C0 == 16 && C1 == 8) || (C0 == 12 && C1 == 8) || (C0 == 8 && C1 == 4) || (C0 == 4 && C1 == 2)
+			|| (C0 == 16 && C1 == 16) || (C0 == 8 && C1 == 8) || (C0 == 16 && C1 == 0) || (C0 == 8 && C1 == 0) || (C0 == 4 && C1 == 0);
 		return (C0 == 8 && C1 == 0) || (C0 == 4 && C1 == 0);
 	}
 
@@ -1019,6 +1021,11 @@ namespace nab200
 			if (C0 == 12 && C1 == 8) return launch_by_frames<12, 8, 0>(M, a);
 			if (C0 == 8 && C1 == 4) return launch_by_frames<8, 4, 0>(M, a);
 			if (C0 == 4 && C1 == 2) return launch_by_frames<4, 2, 0>(M, a);
+			if (C0 == 16 && C1 == 16) return launch_by_frames<16, 16, 0>(M, a);
+			if (C0 == 8 && C1 == 8) return launch_by_frames<8, 8, 0>(M, a);
+			if (C0 == 16 && C1 == 0) return launch_by_frames<16, 0, 0>(M, a);
+			if (C0 == 8 && C1 == 0) return launch_by_frames<8, 0, 0>(M, a);
+			if (C0 == 4 && C1 == 0) return launch_by_frames<4, 0, 0>(M, a);
 		}
 		else
 		{
