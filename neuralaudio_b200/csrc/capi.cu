@@ -1,5 +1,6 @@
 // extern "C" boundary: the reference's 15 exports (NeuralAudioCAPI/NeuralAudioCApi.cpp:14-97) plus the additive
 // batched entry points declared in include/NeuralAudioCApi.h.  No exception crosses this boundary.
+#include <cuda_fp16.h>
 #include <cmath>
 #include <cstring>
 #include <cstring>
@@ -155,6 +156,7 @@ float GetSampleRate(NeuralModel* model)
 void Process(NeuralModel* model, float* input, float* output, size_t numSamples)
 {
 	if (!impl(model)) return;
+	if (!nab200::LastError().empty()) nab200::SetLastError("");   // an earlier, already handled failure on this thread must not taint this call
 	try
 	{
 		model->model->Process(input, output, numSamples);
@@ -389,11 +391,12 @@ int NA_DescribeModelFile(const wchar_t* modelPath, int externalSampleRate, char*
 					os << "]";
 					// which kernel a load would pick, and the TMEM-operand packing checked against the file's weights:
 					// every conv tap matrix must reconstruct as hi + lo, with hi exactly representable in tf32
-					const bool ts = nab200::GetOptions().useTc >= 2 && nab200::WaveNetTsSupported(d);
-					const bool tc = !ts && nab200::GetOptions().useTc >= 1 && nab200::WaveNetTcSupported(d);
+					const bool hk = nab200::GetOptions().useTc >= 3 && nab200::WaveNetHSupported(d);
+					const bool ts = !hk && nab200::GetOptions().useTc >= 2 && nab200::WaveNetTsSupported(d);
+					const bool tc = !hk && !ts && nab200::GetOptions().useTc >= 1 && nab200::WaveNetTcSupported(d);
 					const int pc0 = p.dev.arrays[0].C, pc1 = p.dev.numArrays > 1 ? p.dev.arrays[1].C : 0;
 					const bool shaped = nab200::GetOptions().useTc >= 0 && nab200::wavenet_variant_supported(pc0, pc1, p.dev.arrays[0].act);
-					os << ",\"kernel\":\"" << (ts ? "tcgen05_tmem_operands" : tc ? "tcgen05_smem_operands" : shaped ? "cuda_cores" : nab200::wavenet_generic_supported(p.dev) ? "cuda_cores_runtime_shaped" : "none") << "\"";
+					os << ",\"kernel\":\"" << (hk ? "tcgen05_fp16_pairs" : ts ? "tcgen05_tmem_operands" : tc ? "tcgen05_smem_operands" : shaped ? "cuda_cores" : nab200::wavenet_generic_supported(p.dev) ? "cuda_cores_runtime_shaped" : "none") << "\"";
 					if (nab200::WaveNetTsSupported(d))
 					{
 						nab200::PackedWaveNet q = nab200::PackWaveNetTs(d);
@@ -430,6 +433,45 @@ int NA_DescribeModelFile(const wchar_t* modelPath, int externalSampleRate, char*
 						}
 						os << ",\"ts\":{\"packed_floats\":" << q.weights.size() << ",\"state_floats\":" << q.dev.stateStride << ",\"max_block\":" << q.dev.maxBlock
 						   << ",\"num_rings\":" << q.dev.numRings << ",\"conv_split_max_error\":" << worst << ",\"conv_hi_not_tf32\":" << badHi << "}";
+					}
+					if (nab200::WaveNetHSupported(d))
+					{
+						// fp16-pair packing checked against the file's weights: every conv tap matrix must reconstruct as W1 + W2
+						nab200::PackedWaveNet q = nab200::PackWaveNetH(d);
+						const nab200::HLayer* tab = reinterpret_cast<const nab200::HLayer*>(q.weights.data() + q.dev.tableOff);
+						double worst = 0.0, worstRel = 0.0;
+						const float* w = d.weights.data();
+						int layer = 0;
+						for (size_t a = 0; a < d.arrays.size(); a++)
+						{
+							const auto& A = d.arrays[a];
+							const int C = A.channels, CP = q.dev.arrays[a].C;
+							w += (size_t)C * A.inputSize;
+							for (size_t l = 0; l < A.dilations.size(); l++, layer++)
+							{
+								const nab200::WnLayer& L = q.dev.layers[layer];
+								const __half* blk = reinterpret_cast<const __half*>(q.weights.data() + L.wOff);
+								const int K = A.kernelSizes[l];
+								const size_t opHalves = (size_t)2 * CP * 8, tapHalves = (size_t)tab[layer].tapStride16 * 8;
+								const float* src = w;
+								for (int i = 0; i < C; i++)
+									for (int jn = 0; jn < C; jn++)
+										for (int k = 0; k < K; k++)
+										{
+											const size_t at = (size_t)k * tapHalves + ((size_t)(jn / 8) * CP + i) * 8 + (jn % 8);
+											const double v = (double)__half2float(blk[at]) + (double)__half2float(blk[at + opHalves]);
+											const double e = fabs(v - (double)*src);
+											if (e > worst) worst = e;
+											if (fabs((double)*src) > 1e-3 && e / fabs((double)*src) > worstRel) worstRel = e / fabs((double)*src);
+											src++;
+										}
+								w += (size_t)C * C * K + C + C + (size_t)C * C + C;
+							}
+							w += (size_t)A.headSize * C + (A.headBias ? A.headSize : 0);
+						}
+						os << ",\"h\":{\"packed_floats\":" << q.weights.size() << ",\"state_floats\":" << q.dev.stateStride << ",\"max_block_bytes\":" << q.dev.maxBlockBytes
+						   << ",\"num_rings\":" << q.dev.numRings << ",\"win_rows\":" << q.dev.winRows << ",\"table_bytes\":" << (size_t)q.dev.numLayers * sizeof(nab200::HLayer)
+						   << ",\"conv_split_max_error\":" << worst << ",\"conv_split_max_rel_error\":" << worstRel << "}";
 					}
 					os << "}";
 					return;

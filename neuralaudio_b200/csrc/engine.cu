@@ -20,6 +20,7 @@ namespace nab200
 			env("NAB200_USE_TC", v.useTc);
 			env("NAB200_TS_ISSUERS", v.tsIssuers);
 			env("NAB200_TS_SPLIT", v.tsSplit);
+			env("NAB200_H_CTAS", v.hCtas);
 			env("NAB200_USE_TMA", v.useTma);
 			env("NAB200_MAX_GRID_CTAS", v.maxGridCtas);
 			env("NAB200_LSTM_KERNEL", v.lstmKernel);
@@ -36,6 +37,7 @@ namespace nab200
 		else if (strcmp(name, "use_tc") == 0) { prev = o.useTc; o.useTc = value; }
 		else if (strcmp(name, "ts_issuers") == 0) { prev = o.tsIssuers; o.tsIssuers = value; }
 		else if (strcmp(name, "ts_split") == 0) { prev = o.tsSplit; o.tsSplit = value; }
+		else if (strcmp(name, "h_ctas") == 0) { prev = o.hCtas; o.hCtas = value; }
 		else if (strcmp(name, "max_grid_ctas") == 0) { prev = o.maxGridCtas; o.maxGridCtas = value; }
 		else if (strcmp(name, "lstm_kernel") == 0) { prev = o.lstmKernel; o.lstmKernel = value; }
 		return prev;
@@ -50,14 +52,34 @@ namespace nab200
 		return false;
 	}
 
+	// Every entry point works on its own device and leaves the caller's current device as it found it (a host such as
+	// PyTorch, or models on several GPUs driven from one thread, must not be redirected by a NeuralAudio call).
+	namespace
+	{
+		struct DeviceGuard
+		{
+			int prev = -1;
+			bool ok = true;
+			explicit DeviceGuard(int dev)
+			{
+				if (dev < 0) return;
+				if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); prev = -1; }
+				if (prev == dev) { prev = -1; return; }
+				ok = CudaOk(cudaSetDevice(dev), "cudaSetDevice");
+			}
+			~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+		};
+	}
+
 	// ---- StreamEngine -------------------------------------------------------------------------------------
 	StreamEngine::StreamEngine(int dev) : device(dev) {}
 
 	StreamEngine::~StreamEngine()
 	{
-		if (device >= 0) cudaSetDevice(device);
+		DeviceGuard guard(device);
 		if (pinnedIn) cudaFreeHost(pinnedIn);
 		if (pinnedOut) cudaFreeHost(pinnedOut);
+		if (hErr) cudaFreeHost(hErr);
 		if (devIn) cudaFree(devIn);
 		if (devOut) cudaFree(devOut);
 		for (int i = 0; i < 2; i++)
@@ -92,7 +114,8 @@ namespace nab200
 			SetLastError("requested CUDA device index out of range");
 			return false;
 		}
-		if (!CudaOk(cudaSetDevice(device), "cudaSetDevice")) return false;
+		DeviceGuard guard(device);
+		if (!guard.ok) return false;
 		cudaDeviceProp prop;
 		if (!CudaOk(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties")) return false;
 		if (prop.major < 10)
@@ -102,6 +125,19 @@ namespace nab200
 		}
 		numSMs = prop.multiProcessorCount;
 		if (!CudaOk(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking), "cudaStreamCreate")) return false;
+		if (!CudaOk(cudaHostAlloc(&hErr, sizeof(int), cudaHostAllocMapped), "cudaHostAlloc(error word)")) return false;
+		*hErr = 0;
+		if (!CudaOk(cudaHostGetDevicePointer(&dErr, hErr, 0), "cudaHostGetDevicePointer")) return false;
+		return true;
+	}
+
+	bool StreamEngine::CheckDeviceError()
+	{
+		if (hErr && *static_cast<volatile int*>(hErr) != 0)
+		{
+			SetLastError("device-side error: a tensor-core or bulk-copy completion was lost inside a kernel (results are invalid)");
+			return false;
+		}
 		return true;
 	}
 
@@ -162,7 +198,8 @@ namespace nab200
 			SetLastError("ProcessBatch: null buffer");
 			return false;
 		}
-		if (!CudaOk(cudaSetDevice(device), "cudaSetDevice")) return false;
+		DeviceGuard guard(device);
+		if (!guard.ok) return false;
 		const long long SS = layout == 0 ? (long long)n : 1;
 		const long long FS = layout == 0 ? 1 : (long long)S;
 		void* inAlias = nullptr;
@@ -188,7 +225,7 @@ namespace nab200
 			if (!ProcessDevice(src, dst, SS, FS, SS, FS, S, n)) return false;
 			if (!CudaOk(cudaStreamSynchronize(stream), "cudaStreamSynchronize")) return false;
 			if (!outPinned) memcpy(out, pinnedOut, total * 4);
-			return true;
+			return CheckDeviceError();
 		}
 		// H2D -> kernels -> D2H, all on the model's stream, then wait
 		const float* hsrc = in;
@@ -203,7 +240,7 @@ namespace nab200
 		if (!CudaOk(cudaMemcpyAsync(hdst, devOut, total * 4, cudaMemcpyDeviceToHost, stream), "cudaMemcpyAsync(D2H)")) return false;
 		if (!CudaOk(cudaStreamSynchronize(stream), "cudaStreamSynchronize")) return false;
 		if (!outPinned) memcpy(out, pinnedOut, total * 4);
-		return true;
+		return CheckDeviceError();
 	}
 
 	bool StreamEngine::EnsurePipeline(size_t floats)
@@ -243,7 +280,8 @@ namespace nab200
 		if (S == 0 || n == 0) return true;
 		if (S > numStreams) { SetLastError("ProcessBatchAsync: numStreams exceeds the allocated stream slots (call SetNumStreams first)"); return false; }
 		if (in == nullptr || out == nullptr) { SetLastError("ProcessBatchAsync: null buffer"); return false; }
-		if (!CudaOk(cudaSetDevice(device), "cudaSetDevice")) return false;
+		DeviceGuard guard(device);
+		if (!guard.ok) return false;
 		const bool inDev = IsDevicePointer(in), outDev = IsDevicePointer(out);
 		if (inDev || outDev) return Process(in, out, S, n, layout);   // device pointers are already asynchronous
 		if (!IsPinnedHost(in) || !IsPinnedHost(out))
@@ -280,7 +318,8 @@ namespace nab200
 	{
 		if (lag < 0) lag = 0;
 		if (asyncSeq == 0 || !h2dStream) return true;
-		if (!CudaOk(cudaSetDevice(device), "cudaSetDevice")) return false;
+		DeviceGuard guard(device);
+		if (!guard.ok) return false;
 		// calls complete in order; wait for call number (asyncSeq - lag), 1-based
 		if (asyncSeq <= (unsigned long long)lag) return true;
 		const unsigned long long target = asyncSeq - (unsigned long long)lag;
@@ -294,14 +333,14 @@ namespace nab200
 		const int slot = (int)((target - 1) & 1ull);
 		if (!CudaOk(cudaEventSynchronize(evDone[slot]), "cudaEventSynchronize")) return false;
 		asyncWaited = target;
-		return true;
+		return CheckDeviceError();
 	}
 
 	bool StreamEngine::Synchronize()
 	{
 		if (!stream) return true;
 		if (!WaitBatches(0)) return false;
-		return CudaOk(cudaStreamSynchronize(stream), "cudaStreamSynchronize");
+		return CudaOk(cudaStreamSynchronize(stream), "cudaStreamSynchronize") && CheckDeviceError();
 	}
 
 	// ---- WaveNetEngine ------------------------------------------------------------------------------------
@@ -309,7 +348,7 @@ namespace nab200
 
 	WaveNetEngine::~WaveNetEngine()
 	{
-		if (device >= 0) cudaSetDevice(device);
+		DeviceGuard guard(device);
 		if (dBlob) cudaFree(dBlob);
 		if (dState) cudaFree(dState);
 		if (dHeads) cudaFree(dHeads);
@@ -318,11 +357,17 @@ namespace nab200
 
 	bool WaveNetEngine::Upload()
 	{
+		DeviceGuard guard(device);
+		if (!guard.ok) return false;
 		const WnModelDev& M = packed.dev;
 		const int C0 = M.arrays[0].C, C1 = M.numArrays > 1 ? M.arrays[1].C : 0;
-		bool ok = M.tc == 2 ? wavenet_ts_variant_supported(C0, C1, M.arrays[0].act)
+		bool ok = M.tc == 3 ? wavenet_h_variant_supported(C0, C1, M.arrays[0].act)
+			: M.tc == 2 ? wavenet_ts_variant_supported(C0, C1, M.arrays[0].act)
 			: M.tc ? wavenet_tc_variant_supported(C0, C1, M.arrays[0].act)
 			: (wavenet_variant_supported(C0, C1, M.arrays[0].act) && wavenet_window_jobs(M) <= wavenet_max_window_jobs());
+		// the compile-time-shaped CUDA-core kernel double-buffers a layer's weight block in shared memory beside its windows:
+		// a block that cannot fit (very large kernel sizes) is a load-time refusal / generic-kernel case, not a launch failure
+		if (M.tc == 0 && ok && (size_t)2 * M.maxBlock * 4 > (size_t)96 * 1024) ok = false;
 		if (M.tc == 0 && (!ok || GetOptions().useTc < 0) && wavenet_generic_supported(M))
 		{
 			// no compile-time-shaped kernel (or the generic one was asked for): the run-time-shaped kernel
@@ -347,7 +392,8 @@ namespace nab200
 
 	bool WaveNetEngine::SetNumStreams(size_t S)
 	{
-		if (!CudaOk(cudaSetDevice(device), "cudaSetDevice")) return false;
+		DeviceGuard guard(device);
+		if (!guard.ok) return false;
 		if (!CudaOk(cudaStreamSynchronize(stream), "cudaStreamSynchronize")) return false;
 		if (S != numStreams)
 		{
@@ -369,18 +415,20 @@ namespace nab200
 	bool WaveNetEngine::ResetStreams()
 	{
 		if (numStreams == 0) return true;
-		if (!CudaOk(cudaSetDevice(device), "cudaSetDevice")) return false;
+		DeviceGuard guard(device);
+		if (!guard.ok) return false;
 		if (!CudaOk(state_fill_launch(dState, dBlob + weightFloats, packed.dev.stateStride, (long long)numStreams, stream), "state_fill")) return false;
 		return CudaOk(int_fill_launch(dHeads, 0, (long long)numStreams * packed.dev.numRings, stream), "int_fill");
 	}
 
 	bool WaveNetEngine::Prewarm()
 	{
-		if (!CudaOk(cudaSetDevice(device), "cudaSetDevice")) return false;
+		DeviceGuard guard(device);
+		if (!guard.ok) return false;
 		// steady state under silence (WaveNetModelT::Prewarm, WaveNet.h:746-766), computed analytically in fp32
-		if (packed.dev.tc == 2)
+		if (packed.dev.tc >= 2)
 		{
-			// the TMEM-operand packing keeps biases / mix-in inside tensor-core operands; its template is produced by the
+			// the TMEM-operand packings keep biases / mix-in inside tensor-core operands; its template is produced by the
 			// settle pass below alone, starting from silence-in, zero-state (a finite receptive field forgets the start)
 			if (!CudaOk(cudaMemsetAsync(dBlob + weightFloats, 0, (size_t)packed.dev.stateStride * 4, stream), "cudaMemset(template)")) return false;
 		}
@@ -400,7 +448,7 @@ namespace nab200
 			float* io = nullptr;
 			float* handover = nullptr;
 			if (M.tc == 2 && !CudaOk(cudaMalloc(&handover, wavenet_ts_scratch_floats_per_stream() * 4), "cudaMalloc(prewarm scratch)")) return false;
-			if (!CudaOk(cudaMalloc(&scratch, (size_t)M.stateStride * 4), "cudaMalloc(prewarm scratch)")) return false;
+			if (!CudaOk(cudaMalloc(&scratch, (size_t)M.stateStride * 4), "cudaMalloc(prewarm scratch)")) { if (handover) cudaFree(handover); return false; }
 			bool ok = CudaOk(cudaMalloc(&scratchHeads, (size_t)M.numRings * 4), "cudaMalloc(prewarm scratch)") &&
 				CudaOk(cudaMalloc(&io, (size_t)frames * 2 * 4), "cudaMalloc(prewarm scratch)");
 			ok = ok && CudaOk(cudaMemcpyAsync(scratch, dBlob + weightFloats, (size_t)M.stateStride * 4, cudaMemcpyDeviceToDevice, stream), "cudaMemcpy");
@@ -415,7 +463,8 @@ namespace nab200
 				a.S = 1; a.n = frames; a.numSMs = numSMs; a.useTma = true; a.stream = stream;
 				a.tsIssuers = GetOptions().tsIssuers;
 				a.tsSplit = GetOptions().tsSplit; a.scratch = handover;
-				ok = CudaOk(M.tc == 2 ? wavenet_ts_launch(M, a) : wavenet_tc_launch(M, a), "wavenet tensor-core prewarm settle");
+				a.err = dErr;
+				ok = CudaOk(M.tc == 3 ? wavenet_h_launch(M, a) : M.tc == 2 ? wavenet_ts_launch(M, a) : wavenet_tc_launch(M, a), "wavenet tensor-core prewarm settle");
 			}
 			// under constant input every ring column holds the same value, so the settled rings are a valid template
 			// for ring head 0 whatever position the scratch heads ended at
@@ -452,7 +501,8 @@ namespace nab200
 			a.stream = stream;
 			a.tsIssuers = opt.tsIssuers;
 			a.tsSplit = opt.tsSplit; a.scratch = dScratch;
-			const cudaError_t lerr = packed.dev.tc == 2 ? wavenet_ts_launch(packed.dev, a) : packed.dev.tc ? wavenet_tc_launch(packed.dev, a)
+			a.ctasPerSM = opt.hCtas; a.err = dErr;
+			const cudaError_t lerr = packed.dev.tc == 3 ? wavenet_h_launch(packed.dev, a) : packed.dev.tc == 2 ? wavenet_ts_launch(packed.dev, a) : packed.dev.tc ? wavenet_tc_launch(packed.dev, a)
 				: useGeneric ? wavenet_generic_launch(packed.dev, a) : wavenet_launch(packed.dev, a);
 			if (!CudaOk(lerr, "wavenet kernel launch")) return false;
 			done += chunk;
@@ -465,7 +515,8 @@ namespace nab200
 		if (s >= numStreams) { SetLastError("CopyStreamState: stream out of range"); return false; }
 		const size_t nState = (size_t)packed.dev.stateStride, nHeads = (size_t)packed.dev.numRings;
 		if (capFloats < nState + nHeads) { SetLastError("CopyStreamState: buffer too small"); return false; }
-		if (!CudaOk(cudaSetDevice(device), "cudaSetDevice")) return false;
+		DeviceGuard guard(device);
+		if (!guard.ok) return false;
 		if (!CudaOk(cudaStreamSynchronize(stream), "cudaStreamSynchronize")) return false;
 		if (!CudaOk(cudaMemcpy(hostOut, dState + s * nState, nState * 4, cudaMemcpyDeviceToHost), "cudaMemcpy(state)")) return false;
 		if (!CudaOk(cudaMemcpy(hostOut + nState, dHeads + s * nHeads, nHeads * 4, cudaMemcpyDeviceToHost), "cudaMemcpy(heads)")) return false;
@@ -485,13 +536,15 @@ namespace nab200
 
 	LstmEngine::~LstmEngine()
 	{
-		if (device >= 0) cudaSetDevice(device);
+		DeviceGuard guard(device);
 		if (dBlob) cudaFree(dBlob);
 		if (dState) cudaFree(dState);
 	}
 
 	bool LstmEngine::Upload()
 	{
+		DeviceGuard guard(device);
+		if (!guard.ok) return false;
 		if (!lstm_variant_supported(packed.dev.L, packed.dev.G))
 		{
 			SetLastError("unsupported model: no sm_100a LSTM kernel for this (layers, hidden size); no CPU fallback");
@@ -509,7 +562,8 @@ namespace nab200
 
 	bool LstmEngine::SetNumStreams(size_t S)
 	{
-		if (!CudaOk(cudaSetDevice(device), "cudaSetDevice")) return false;
+		DeviceGuard guard(device);
+		if (!guard.ok) return false;
 		if (!CudaOk(cudaStreamSynchronize(stream), "cudaStreamSynchronize")) return false;
 		if (S != numStreams)
 		{
@@ -524,7 +578,8 @@ namespace nab200
 	bool LstmEngine::ResetStreams()
 	{
 		if (numStreams == 0) return true;
-		if (!CudaOk(cudaSetDevice(device), "cudaSetDevice")) return false;
+		DeviceGuard guard(device);
+		if (!guard.ok) return false;
 		return CudaOk(state_fill_launch(dState, dBlob + weightFloats, packed.dev.stateStride, (long long)numStreams, stream), "state_fill");
 	}
 
@@ -532,7 +587,8 @@ namespace nab200
 	{
 		// InternalLSTMModelT::Prewarm (InternalModel.h:368-371): 2048 zero samples from the CURRENT state, for every slot
 		// and for the template (so slots created later start where a freshly prewarmed model would)
-		if (!CudaOk(cudaSetDevice(device), "cudaSetDevice")) return false;
+		DeviceGuard guard(device);
+		if (!guard.ok) return false;
 		LstmLaunch a;
 		memset(&a, 0, sizeof(a));
 		a.weights = dBlob;
@@ -577,7 +633,8 @@ namespace nab200
 		if (s >= numStreams) { SetLastError("CopyStreamState: stream out of range"); return false; }
 		const size_t nState = (size_t)packed.dev.stateStride;
 		if (capFloats < nState) { SetLastError("CopyStreamState: buffer too small"); return false; }
-		if (!CudaOk(cudaSetDevice(device), "cudaSetDevice")) return false;
+		DeviceGuard guard(device);
+		if (!guard.ok) return false;
 		if (!CudaOk(cudaStreamSynchronize(stream), "cudaStreamSynchronize")) return false;
 		if (!CudaOk(cudaMemcpy(hostOut, dState + s * nState, nState * 4, cudaMemcpyDeviceToHost), "cudaMemcpy(state)")) return false;
 		*written = nState;

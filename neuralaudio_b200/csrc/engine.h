@@ -16,13 +16,14 @@ namespace nab200
 	struct Options
 	{
 		int useTma = 1;         // stage history windows with cp.async.bulk + mbarrier (0: plain loads, debugging aid)
-		int useTc = 2;          // WaveNet kernel choice where the architecture fits: 2 tcgen05 with TMEM operands (default),
-		                        // 1 tcgen05 with shared-memory operands (round-1 kernel), 0 CUDA-core kernel,
+		int useTc = 3;          // WaveNet kernel choice where the architecture fits: 3 tcgen05 with fp16-pair TMEM operands (default),
+		                        // 2 tcgen05 3xTF32 with TMEM operands, 1 tcgen05 with shared-memory operands (round-1 kernel), 0 CUDA-core kernel,
 		                        // -1 the run-time-shaped kernel even for shapes that have a specialised one (tests)
 		int tsIssuers = 4;      // (unused since the TS kernel has a dedicated issuer warp)
 		int tsSplit = 0;        // TS kernel: 1 = one launch per layer array, the 8-channel one with 6 CTAs per SM (measured 5 % slower
 		                        // than the fused kernel: 144 + 90 us vs 208 us; kept as an option, its head sum is exact fp32)
 		int maxGridCtas = 0;    // 0: one CTA per SM
+		int hCtas = 0;          // fp16-pair kernel: streams in flight per SM (0: the kernel's default, 5)
 		int lstmKernel = 0;     // LSTM kernel: 0 automatic, 1 gate rows in registers, 2 lane = stream (matrices in shared memory), 3 run-time-shaped
 	};
 	Options& GetOptions();
@@ -64,6 +65,11 @@ namespace nab200
 		virtual bool ProcessDevice(const float* in, float* out, long long inSS, long long inFS, long long outSS, long long outFS,
 			size_t numStreams, size_t numFrames) = 0;
 		bool EnsureStaging(size_t floats);
+		// sticky device error word (page-locked, mapped): a kernel that loses an MMA / copy completion sets it instead of
+		// hanging; every host-side synchronisation point checks it
+		bool CheckDeviceError();
+		int* hErr = nullptr;
+		int* dErr = nullptr;
 
 		int device = -1;
 		int numSMs = 148;

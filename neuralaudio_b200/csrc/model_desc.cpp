@@ -1,6 +1,8 @@
 #include "model_desc.h"
 #include <cmath>
 #include <sstream>
+#include <cstring>
+#include <cuda_fp16.h>
 
 namespace nab200
 {
@@ -95,17 +97,28 @@ namespace nab200
 		if (!lc.contains("kernel_sizes") || !SameSequence(lc.at("kernel_sizes"), kA2KernelSizes)) return false;
 		if (!lc.contains("dilations") || !SameSequence(lc.at("dilations"), kA2Dilations)) return false;
 		if (!lc.contains("activation")) return false;
-		for (const Json& act : lc.at("activation").arr)
+		// The reference walks these with nlohmann's range-for, which visits an array's elements, an object's VALUES, a scalar
+		// once and null never (NeuralModel.cpp:246-283): a single string / dict activation therefore fails the "type" test and
+		// the file goes to NAM Core - here: it is refused, never loaded with the wrong activation.
+		auto elements = [](const Json& v)
 		{
-			if (!act.contains("type") || !act.at("type").is_string() || act.at("type").as_string() != "LeakyReLU") return false;
-			if (std::fabs((float)act.value_double("negative_slope", 0.01) - 0.01f) > 1e-5f) return false;
+			std::vector<const Json*> e;
+			if (v.is_array()) for (const Json& x : v.arr) e.push_back(&x);
+			else if (v.is_object()) for (const auto& kv : v.obj) e.push_back(&kv.second);
+			else if (!v.is_null()) e.push_back(&v);
+			return e;
+		};
+		for (const Json* act : elements(lc.at("activation")))
+		{
+			if (!act->contains("type") || !act->at("type").is_string() || act->at("type").as_string() != "LeakyReLU") return false;
+			if (std::fabs((float)act->value_double("negative_slope", 0.01) - 0.01f) > 1e-5f) return false;
 		}
 		if (lc.contains("secondary_activation"))
-			for (const Json& a : lc.at("secondary_activation").arr)
-				if (!a.is_null()) return false;
+			for (const Json* a : elements(lc.at("secondary_activation")))
+				if (!a->is_null()) return false;
 		if (lc.contains("gating_mode"))
-			for (const Json& g : lc.at("gating_mode").arr)
-				if (!g.is_null() && !(g.is_string() && g.as_string() == "none")) return false;
+			for (const Json* g : elements(lc.at("gating_mode")))
+				if (!g->is_null() && !(g->is_string() && g->as_string() == "none")) return false;
 		if (!lc.contains("head")) return false;
 		const Json& head = lc.at("head");
 		if (head.value_int("out_channels", 1) != 1) return false;
@@ -223,6 +236,26 @@ namespace nab200
 			totalLayers += A.dilations.size();
 		}
 		if (totalLayers > (size_t)kMaxLayers) throw std::runtime_error("unsupported model: more than 32 WaveNet layers");
+		// Per-stream history = sum over layers of channels x (K - 1) x dilation frames (WaveNet.h:30-83), laid out with int
+		// offsets by the packers.  Sum it in 64 bits after oversampling has scaled the dilations, and refuse what would wrap
+		// or is absurd for one audio stream (a corrupt or hostile file must not reach the kernels with undersized state).
+		{
+			constexpr long long kMaxStateFloats = 16ll << 20;   // 64 MiB of history per stream (A1 Standard: 0.19 MiB)
+			constexpr int kMaxKernelSize = 64;                  // largest official kernel: 16 (A2 head), 15 (A2 layers)
+			long long stateFloats = 0;
+			for (const auto& A : d.arrays)
+			{
+				if (A.headKernel < 1 || A.headKernel > kMaxKernelSize) throw std::runtime_error("unsupported model: head kernel size out of range");
+				for (size_t l = 0; l < A.dilations.size(); l++)
+				{
+					if (A.kernelSizes[l] > kMaxKernelSize) throw std::runtime_error("unsupported model: conv kernel size out of range");
+					const long long frames = (long long)(A.kernelSizes[l] - 1) * (long long)A.dilations[l];
+					if (frames > kMaxStateFloats) throw std::runtime_error("unsupported model: dilation out of range");
+					stateFloats += 32ll * (frames + 4);             // channels are padded to at most 32, rings to 4 frames
+					if (stateFloats > kMaxStateFloats) throw std::runtime_error("unsupported model: receptive field too large (history per stream exceeds 64 MiB)");
+				}
+			}
+		}
 
 		d.weights = FloatList(modelJson.at("weights"));
 		const size_t expect = ExpectedWaveNetWeights(d);
@@ -807,6 +840,237 @@ namespace nab200
 		M.numLayers = layerIdx;
 		M.numRings = ringIdx;
 		M.stateStride = Align4(ringOff);
+		return P;
+	}
+
+
+	// ---- fp16-pair packing (wavenet_h_kernels.cu, na_device.h "tc == 3") --------------------------------------------
+	namespace
+	{
+		// w ~ h[0] + h[1] + h[2], each rounded to nearest fp16 of what is left (the remainders are exact in fp32)
+		void SplitH3(float v, uint16_t (&h)[3])
+		{
+			float r = v;
+			for (int i = 0; i < 3; i++)
+			{
+				const __half q = __float2half_rn(r);
+				memcpy(&h[i], &q, 2);
+				r -= __half2float(q);
+			}
+		}
+
+		// B operand [k group of 8][n][8 halves] at 16-byte unit `base16` of a block of halves; N rows per k group
+		struct HBlock
+		{
+			std::vector<uint16_t> h;
+			uint32_t Alloc(uint32_t units16) { const uint32_t at = (uint32_t)(h.size() / 8); h.resize(h.size() + (size_t)units16 * 8, 0); return at; }
+			void Put(uint32_t base16, int N, int k, int n, uint16_t v) { h[(size_t)base16 * 8 + ((size_t)(k / 8) * N + n) * 8 + (k % 8)] = v; }
+		};
+	}
+
+	bool WaveNetHSupported(const WaveNetDesc& desc)
+	{
+		// same architecture family as the TMEM-operand 3xTF32 kernel: two arrays of (9..16, <= 8) channels, tanh, kernel size 3,
+		// 1x1 heads, head of array 0 feeding array 1; every layer's history must fit the window plan below
+		if (!WaveNetTsSupported(desc)) return false;
+		constexpr int R = 384;
+		for (const auto& A : desc.arrays)
+			for (size_t l = 0; l < A.dilations.size(); l++)
+			{
+				const long long K = A.kernelSizes[l], d = A.dilations[l], Lp = (K - 1) * d;
+				if (Lp + 128 <= R) continue;                       // one contiguous window
+				if (d < 128 || (K - 1) * 128 > R || K - 1 > kHMaxJobs) return false;   // else every tap needs its own 128-row window
+			}
+		return true;
+	}
+
+	PackedWaveNet PackWaveNetH(const WaveNetDesc& desc)
+	{
+		PackedWaveNet P;
+		WnModelDev& M = P.dev;
+		memset(&M, 0, sizeof(M));
+		M.tc = 3;
+		M.numArrays = (int)desc.arrays.size();
+		constexpr int R = 384;   // rows per plane of the shared-memory window buffer
+		M.winRows = R;
+		const float* w = desc.weights.data();
+		int layerIdx = 0, ringIdx = 0, ringOff = 0;
+		std::vector<HLayer> table;
+		uint16_t h3[3];
+		for (int a = 0; a < M.numArrays; a++)
+		{
+			const WaveNetArrayDesc& A = desc.arrays[a];
+			WnArray& DA = M.arrays[a];
+			const int C = A.channels, CP = TcPad(C), HN = 8, N1 = CP + HN;
+			const int last = a + 1 == M.numArrays;
+			const int inC = A.inputSize;
+			const int H = A.headSize;
+			const int nL = (int)A.dilations.size();
+			DA.C = CP; DA.inC = a == 0 ? 1 : TcPad(inC); DA.H = 8; DA.Kh = 1; DA.act = A.activation;
+			DA.firstLayer = layerIdx; DA.numLayers = nL; DA.realC = C; DA.realH = H;
+			const float* wRe = w; w += (size_t)C * inC;
+			std::vector<const float*> wLayer(nL);
+			for (int l = 0; l < nL; l++)
+			{
+				wLayer[l] = w;
+				w += (size_t)C * C * A.kernelSizes[l] + C + C + (size_t)C * C + C;
+			}
+			const float* wHead = w; w += (size_t)H * C + (A.headBias ? H : 0);   // file [H][C] then bias
+			// element (input channel j, output n) of a CP-channel contraction: C == 16: W1 at k = j of operand 1, W2 at k = j of
+			// operand 2; C == 8: [W1 ; W1] (k = j and k = 8 + j) and [W2 ; 0]
+			auto putPair = [&](HBlock& B, uint32_t op1, uint32_t op2, int N, int j, int n, float v)
+			{
+				SplitH3(v, h3);
+				B.Put(op1, N, j, n, h3[0]);
+				if (CP == 8) B.Put(op1, N, 8 + j, n, h3[0]);
+				B.Put(op2, N, j, n, h3[1]);
+			};
+			for (int l = 0; l < nL; l++)
+			{
+				WnLayer& L = M.layers[layerIdx];
+				HLayer T;
+				memset(&T, 0, sizeof(T));
+				const int K = A.kernelSizes[l], d = A.dilations[l];
+				L.K = K; L.d = d; L.array = a;
+				L.Lp = (K - 1) * d;
+				L.ringOff = ringOff; L.ringIdx = ringIdx;
+				M.ringLp[ringIdx] = L.Lp;
+				ringOff += CP * L.Lp; ringIdx++;
+				L.flags = 0;
+				if (l == 0) L.flags |= kFirstInArray;
+				if (l == nL - 1) L.flags |= kLastInArray;
+				const bool needOut = !(last && M.numArrays > 1 && l == nL - 1);
+				if (needOut) L.flags |= kNeedOutput;
+
+				HBlock B;
+				const uint32_t opN = 2u * CP;                       // units of one conv operand [2][CP][8]
+				const uint32_t taps16 = B.Alloc((uint32_t)K * 2u * opN);
+				const uint32_t convC16 = B.Alloc(opN);
+				const uint32_t one116 = B.Alloc(2u * N1), one216 = B.Alloc(2u * N1), oneC16 = B.Alloc(2u * N1);
+				uint32_t ent16 = 0;
+				if (l == 0) ent16 = B.Alloc(a == 0 ? 2u * 24u : 6u * 32u);
+				const float* src = wLayer[l];
+				// conv file order [out][in][k] (WaveNet.h:99-105); tap k = K - 1 is the undelayed one
+				for (int i = 0; i < C; i++)
+					for (int j = 0; j < C; j++)
+						for (int k = 0; k < K; k++) putPair(B, taps16 + (uint32_t)k * 2u * opN, taps16 + (uint32_t)k * 2u * opN + opN, CP, j, i, *src++);
+				// constant-operand rows against [c1, c2, c1, 1, 1, 1]: mix1, mix1, mix2, b1, b2, b3
+				const float* convB = src; src += C;
+				const float* mix = src; src += C;
+				for (int i = 0; i < C; i++)
+				{
+					SplitH3(mix[i], h3);
+					B.Put(convC16, CP, 0, i, h3[0]); B.Put(convC16, CP, 1, i, h3[0]); B.Put(convC16, CP, 2, i, h3[1]);
+					SplitH3(convB[i], h3);
+					B.Put(convC16, CP, 3, i, h3[0]); B.Put(convC16, CP, 4, i, h3[1]); B.Put(convC16, CP, 5, i, h3[2]);
+				}
+				// 1x1 file [out][in] (zero when the layer has no output) | head conv of this array, file [H][C], as columns CP..
+				for (int i = 0; i < C; i++)
+					for (int j = 0; j < C; j++)
+					{
+						const float v = *src++;
+						if (needOut) putPair(B, one116, one216, N1, j, i, v);
+					}
+				for (int h = 0; h < H; h++)
+					for (int j = 0; j < C; j++) putPair(B, one116, one216, N1, j, CP + h, wHead[h * C + j]);
+				for (int i = 0; i < C; i++)
+				{
+					SplitH3(*src++, h3);
+					if (!needOut) continue;
+					B.Put(oneC16, N1, 3, i, h3[0]); B.Put(oneC16, N1, 4, i, h3[1]); B.Put(oneC16, N1, 5, i, h3[2]);
+				}
+				if (l == 0)
+				{
+					if (a == 0)
+					{
+						// entry operand [2][24][8]: columns 0..15 rechannel 1 -> C (WaveNet.h:637), columns 16..23 head bias
+						for (int i = 0; i < C; i++)
+						{
+							SplitH3(wRe[i], h3);
+							B.Put(ent16, 24, 0, i, h3[0]); B.Put(ent16, 24, 1, i, h3[0]); B.Put(ent16, 24, 2, i, h3[1]);
+						}
+						if (A.headBias)
+							for (int h = 0; h < H && h < 8; h++)
+							{
+								SplitH3(wHead[(size_t)H * C + h], h3);
+								B.Put(ent16, 24, 3, 16 + h, h3[0]); B.Put(ent16, 24, 4, 16 + h, h3[1]); B.Put(ent16, 24, 5, 16 + h, h3[2]);
+							}
+					}
+					else
+					{
+						// transition operands, six [2][16][8] blocks (N = 16: columns 0..7 residual stream of this array, 8..15 its head sum):
+						//   0: [Re1 | 0]  1: [Re2 | 0]   (K = 16 channels of the previous array's output; used with its h1, h2 / h1)
+						//   2: [0 | Wc1 ; Wc1]  3: [0 | Wc2 ; 0]   (head conv of this array applied to the previous head output, WaveNet.h:785-788)
+						//   4: [0 | head bias rows]
+						for (int i = 0; i < C; i++)
+							for (int j = 0; j < inC; j++)
+							{
+								SplitH3(wRe[i * inC + j], h3);
+								B.Put(ent16, 16, j, i, h3[0]);
+								B.Put(ent16 + 32, 16, j, i, h3[1]);
+							}
+						const int Hprev = desc.arrays[a - 1].headSize;
+						for (int h = 0; h < H; h++)
+							for (int j = 0; j < Hprev && j < C && j < 8; j++)
+							{
+								SplitH3(wHead[h * C + j], h3);
+								B.Put(ent16 + 64, 16, j, 8 + h, h3[0]); B.Put(ent16 + 64, 16, 8 + j, 8 + h, h3[0]);
+								B.Put(ent16 + 96, 16, j, 8 + h, h3[1]);
+							}
+						if (A.headBias)
+							for (int h = 0; h < H; h++)
+							{
+								SplitH3(wHead[(size_t)H * C + h], h3);
+								B.Put(ent16 + 128, 16, 3, 8 + h, h3[0]); B.Put(ent16 + 128, 16, 4, 8 + h, h3[1]); B.Put(ent16 + 128, 16, 5, 8 + h, h3[2]);
+							}
+					}
+				}
+				L.wSize = (int)(B.h.size() / 2);
+				L.wOff = (int)P.weights.size();
+				P.weights.resize(P.weights.size() + L.wSize, 0.0f);
+				memcpy(P.weights.data() + L.wOff, B.h.data(), B.h.size() * 2);
+				if (L.wSize > M.maxBlock) M.maxBlock = L.wSize;
+
+				// window plan
+				T.numTaps = K - 1; T.Lp = L.Lp; T.ringOff = L.ringOff; T.ringIdx = L.ringIdx; T.K = K; T.C = CP;
+				T.wOff = (uint32_t)L.wOff; T.wBytes = (uint32_t)L.wSize * 4u; T.groupTaps = 2;
+				T.convC16 = convC16; T.one116 = one116; T.one216 = one216; T.oneC16 = oneC16;
+				T.tapStride16 = 2u * opN; T.N1 = (uint32_t)N1; T.ent16 = ent16; T.flags = (uint32_t)L.flags;
+				if (L.Lp + 128 <= R)
+				{
+					// one contiguous window: rows [0, Lp) = the ring in time order, rows [Lp, Lp + 128) = this call's frames
+					T.curOff = (uint32_t)L.Lp * 16u;
+					for (int j = 0; j < K - 1; j++)
+					{
+						const int D = (K - 1 - j) * d;
+						T.tapOff[j] = (uint32_t)(L.Lp - D) * 16u;
+						if (D < 128) T.mixed = 1;
+					}
+					T.numJobs = 1;
+					T.job[0].cnt = L.Lp; T.job[0].back = L.Lp; T.job[0].off = 0;
+				}
+				else
+				{
+					// every delayed tap is pure history (delay >= 128): its own 128-row window
+					T.numJobs = K - 1;
+					for (int j = 0; j < K - 1; j++)
+					{
+						T.tapOff[j] = (uint32_t)j * 128u * 16u;
+						T.job[j].cnt = -1; T.job[j].back = (K - 1 - j) * d; T.job[j].off = T.tapOff[j];
+					}
+				}
+				table.push_back(T);
+				layerIdx++;
+			}
+		}
+		M.headScale = *w;
+		M.numLayers = layerIdx;
+		M.numRings = ringIdx;
+		M.stateStride = Align4(ringOff);
+		M.maxBlockBytes = M.maxBlock * 4;
+		M.tableOff = (int)P.weights.size();
+		P.weights.resize(P.weights.size() + table.size() * sizeof(HLayer) / 4, 0.0f);
+		memcpy(P.weights.data() + M.tableOff, table.data(), table.size() * sizeof(HLayer));
 		return P;
 	}
 

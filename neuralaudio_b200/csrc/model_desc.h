@@ -74,6 +74,9 @@ namespace nab200
 	// TMEM-operand (tcgen05 "TS") packing: conv taps, 1x1, mix-in, biases, rechannel and head all as tensor-core B operands
 	bool WaveNetTsSupported(const WaveNetDesc& desc);
 	PackedWaveNet PackWaveNetTs(const WaveNetDesc& desc);
+	// fp16-pair tcgen05 packing (wavenet_h_kernels.cu): (h1, h2) operand pairs, rings hold the packed pairs
+	bool WaveNetHSupported(const WaveNetDesc& desc);
+	PackedWaveNet PackWaveNetH(const WaveNetDesc& desc);
 	PackedLstm PackLstm(const LstmDesc& desc);
 
 	int PadChannels(int c);   // 2, 4, 8, 12, 16, then multiples of 4 up to 32

@@ -72,12 +72,49 @@ namespace nab200
 		int stateStride;     // floats of ring state per stream (multiple of 4)
 		int maxBlock;        // largest weight block in floats
 		float headScale;
-		int tc;              // 1: tensor-core packing / ring layout
+		int tc;              // 0 CUDA-core packing, 1 / 2 tcgen05 3xTF32 packings, 3 tcgen05 fp16-pair packing (HLayer table)
 		int pad0;
 		WnArray arrays[kMaxArrays];
 		WnLayer layers[kMaxLayers];
 		int ringLp[kMaxRings];
+		// tc == 3 only: float offset of the HLayer table inside the packed weights, rows per plane of the shared-memory
+		// window buffer, largest weight block in bytes
+		int tableOff, winRows, maxBlockBytes, pad1;
 	};
+
+	// fp16-pair packing (WnModelDev::tc == 3), used by wavenet_h_kernels.cu.
+	//   Every A operand of every contraction is a pair of fp16 values per element, x ~ h1 + h2 with h1 = rn_f16(x) and
+	//   h2 = rn_f16(x - h1); every weight likewise W ~ W1 + W2 (+ W3 for biases); D += h1 W1 + h2 W1 + h1 W2 on
+	//   tcgen05.mma kind::f16 (K = 16) with fp32 accumulation - the same 22 significant bits as the 3xTF32 split at half the
+	//   TMEM columns, half the MMAs and no split arithmetic when a stored value is reused (tools/tsh_numerics.py).
+	//   Ring row of one frame = C words: [h1 of channel pairs (C/2 words) | h2 of channel pairs (C/2 words)], stored as
+	//   planes [C/4][Lp][4 words] exactly as the operand is staged to TMEM.
+	//   Weight block of a layer (16-byte units, fp16): per tap k = 0..K-1 (k = K-1 undelayed):
+	//       C == 16: W1[2][16][8] | W2[2][16][8]          (B operand [k group][n][8 halves], k = input channel)
+	//       C ==  8: Wa = [W1 ; W1][2][8][8] | Wb = [W2 ; 0]   (k group 0 pairs with the h1 halves, group 1 with the h2 halves)
+	//     then convC[2][C][8] (rows: mix1, mix1, mix2, b1, b2, b3 against the constant operand [c1, c2, c1, 1, 1, 1, 0...]),
+	//     one1 / one2 / oneC with N1 = C + HN columns (1x1 | head conv), and on the first layer of an array the entry /
+	//     transition operands (see PackWaveNetH).
+	constexpr int kHMaxTaps = 16;   // delayed taps per layer (K - 1 <= 14 for the official shapes)
+	constexpr int kHMaxJobs = 6;    // history-window copy jobs per layer
+	struct HJob
+	{
+		int cnt;         // rows to copy (-1: the call's frame count)
+		int back;        // row r comes from ring row (head - back + r) mod Lp
+		uint32_t off;    // byte offset of window row 0 inside a plane
+		int pad;
+	};
+	struct HLayer
+	{
+		int numTaps, mixed, Lp, ringOff;                       // group 0
+		int ringIdx, numJobs, K, C;                            // group 1
+		uint32_t curOff, wOff, wBytes; int groupTaps;          // group 2: current-row offset (bytes), block offset (floats), block bytes, taps per hand-off
+		uint32_t convC16, one116, one216, oneC16;              // group 3: offsets inside the block, 16-byte units
+		uint32_t tapStride16, N1, ent16, flags;                // group 4
+		uint32_t tapOff[kHMaxTaps];                            // byte offset (inside a plane) of frame 0's row of delayed tap j
+		HJob job[kHMaxJobs];
+	};
+	static_assert(sizeof(HLayer) % 16 == 0, "HLayer is read with 16-byte shared-memory loads");
 
 	// LSTM: lane == hidden unit, G = pow2 >= H lanes per stream, weights zero-padded to G.
 	// Packed per layer l (I = 1 for l == 0 else G):  W[4][I + G][G] (gate, column, unit) | b[4][G]

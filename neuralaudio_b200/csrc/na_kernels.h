@@ -20,6 +20,8 @@ namespace nab200
 		int tsIssuers = 4;      // (unused since the TS kernel has a dedicated issuer warp)
 		int tsSplit = 0;        // TS kernel: one launch per layer array (needs `scratch`)
 		float* scratch = nullptr;   // TS split launch: [S][wavenet_ts_scratch_floats_per_stream()] floats
+		int ctasPerSM = 0;      // H kernel: streams in flight per SM (0: default)
+		int* err = nullptr;     // H kernel: sticky device error word (a lost MMA / copy completion sets it)
 		cudaStream_t stream;
 	};
 
@@ -31,6 +33,9 @@ namespace nab200
 	cudaError_t wavenet_ts_launch(const WnModelDev& M, const WnLaunch& a);
 	bool wavenet_ts_variant_supported(int C0, int C1, int act);
 	size_t wavenet_ts_scratch_floats_per_stream();
+	// tcgen05 path with fp16-pair TMEM operands (WnModelDev::tc == 3 packing), n <= 128
+	cudaError_t wavenet_h_launch(const WnModelDev& M, const WnLaunch& a);
+	bool wavenet_h_variant_supported(int C0, int C1, int act);
 	// run-time-shaped fallback (CUDA-core packing, any channel count up to 32, 1x1 heads), n <= 128
 	cudaError_t wavenet_generic_launch(const WnModelDev& M, const WnLaunch& a);
 	bool wavenet_generic_supported(const WnModelDev& M);

@@ -276,10 +276,11 @@ inline namespace b200
 		// only the static adapters override GetReceptiveFieldSize (InternalModel.h:99-102); dynamic models report -1
 		model->receptiveField = desc.isStatic ? desc.receptiveField : -1;
 		const int tcOpt = nab200::GetOptions().useTc;
-		const bool useTs = tcOpt >= 2 && nab200::WaveNetTsSupported(desc);
-		const bool useTc = !useTs && tcOpt >= 1 && nab200::WaveNetTcSupported(desc);
+		const bool useH = tcOpt >= 3 && nab200::WaveNetHSupported(desc);
+		const bool useTs = !useH && tcOpt >= 2 && nab200::WaveNetTsSupported(desc);
+		const bool useTc = !useH && !useTs && tcOpt >= 1 && nab200::WaveNetTcSupported(desc);
 		auto* engine = new nab200::WaveNetEngine(loader->GetDevice(),
-			useTs ? nab200::PackWaveNetTs(desc) : useTc ? nab200::PackWaveNetTc(desc) : nab200::PackWaveNet(desc));
+			useH ? nab200::PackWaveNetH(desc) : useTs ? nab200::PackWaveNetTs(desc) : useTc ? nab200::PackWaveNetTc(desc) : nab200::PackWaveNet(desc));
 		model->engine = engine;
 		if (!engine->Init() || !engine->Upload()) { delete model; return nullptr; }
 		return model;

@@ -1,0 +1,632 @@
+// Batched WaveNet Process() on the Blackwell tensor cores with fp16-PAIR operands in TMEM ("H" kernel), sm_100a.
+// Same contract as the other WaveNet kernels: one call advances S independent streams by n <= 128 frames
+// (reference path WaveNetModelT::Process, WaveNet.h:768-799; layer WaveNetLayerT::Process :462-494; conv :139-290).
+//
+// What changed against the 3xTF32 kernel (wavenet_ts_kernels.cu) and why (round-1 profile: per-stream dependency chain
+// binds, 4 streams per SM capped by 128 TMEM columns each, tensor pipe 53 % busy with 26 MMAs per 16-channel layer):
+//   * every A operand is a pair of fp16 values per element, x ~ h1 + h2 (h1 = rn_f16(x), h2 = rn_f16(x - h1)), every
+//     weight W ~ W1 + W2 on the host; D += h1 W1 + h2 W1 + h1 W2 with kind::f16 MMAs (K = 16 per instruction) and fp32
+//     accumulation: the same 22 significant bits as 3xTF32 (tools/tsh_numerics.py: 3.9e-7 vs 3.6e-7 max-abs on the
+//     reference's own A1 Standard vector), but 16 TMEM columns per 16-channel operand instead of 32, 14 MMAs per
+//     16-channel layer instead of 26, and a stored (h1, h2) row is reused as is:
+//   * the history rings and the shared-memory windows hold the packed pairs (4 bytes per value, as before), so staging a
+//     delayed tap is LDS.128 -> tcgen05.st with no arithmetic; the split is computed once per produced value;
+//   * 96 TMEM columns per stream (three 32-column allocations) -> 5 streams in flight per SM instead of 4;
+//   * the residual stream stays an fp32 TMEM accumulator for the whole array (x += W1x1 z + b is the 1x1 MMA itself,
+//     WaveNet.h:486-491), the head sum accumulates as extra N columns of the 1x1 (WaveNet.h:482,658-660), mix-in,
+//     biases and the 1 -> C rechannel ride on a constant operand [c1, c2, c1, 1, 1, 1, 0...] (WaveNet.h:476,637).
+// Roles: warps 0..3 ("stagers", thread t <-> frame t <-> TMEM lane t) build operands and run the activation; warp 4
+// (the "issuer") issues every tcgen05.mma and the weight TMA.  Hand-offs: stagers -> issuer by named barriers the stagers
+// only arrive on; MMA completion -> the issuer's mbarrier (tcgen05.commit), which then releases the stagers through
+// another named barrier.  One issuing thread, fixed order: results do not depend on timing or on how a buffer is cut
+// into calls.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include "na_device.h"
+#include "na_kernels.h"
+#include "tcgen05_ptx.h"
+
+namespace nab200
+{
+	namespace hk
+	{
+		using namespace ptx;
+
+		constexpr int kCur = 128;        // frames per pass = TMEM lanes
+		constexpr int kStagers = 128;
+		constexpr int kThreads = 160;
+		constexpr int kHdbHalf = 72;     // ints per stream in hdb: heads[36] | heads after the call[36]
+		constexpr uint32_t kTabTaps = (uint32_t)offsetof(HLayer, tapOff);
+		constexpr uint32_t kTabJobs = (uint32_t)offsetof(HLayer, job);
+
+		enum : int
+		{
+			kBarMix = 1,      // stagers only
+			kBarE = 2,        // stagers -> issuer: entry / transition operands staged
+			kBarT2 = 3,       // stagers -> issuer: undelayed tap staged
+			kBarTaps = 4,     // stagers -> issuer: a group of delayed taps staged
+			kBarZ = 5,        // stagers -> issuer: activated output staged
+			kBarDReady = 6,   // issuer -> stagers: conv accumulator complete
+			kBarXReady = 7,   // issuer -> stagers: residual / head accumulators complete
+			kBarGReady = 8    // issuer -> stagers: the previous tap group's MMAs have read their operands
+		};
+
+		struct Ctx
+		{
+			const WnModelDev* M;
+			const float* Wg;
+			float* state;
+			uint32_t win, planeStride;    // window buffer: [planes][winRows][16 bytes]
+			uint32_t wbuf, wbufStride;    // two weight buffers
+			uint32_t tab;                 // HLayer table
+			int* hdb;                     // [2][kHdbHalf] ring heads of the current / next stream
+			uint32_t barW0, barD, barX;
+			uint32_t r0, r1, r2;          // TMEM: three 32-column regions
+			int n, tid, warp, S, gstride, numLayers;
+			bool el;
+			uint32_t wq, dq, xq;          // issuer: weight-block counter, barD / barX phase counters
+			int cur;
+			int* err;
+		};
+
+		// TMEM column maps.  CONST (8 columns) is always r2 + 24.
+		//   ROLE 0: first array, 16 channels, 8 head columns:  taps r0 + 16 j | T2 r1 | D r1 + 16 | XR r2 | HD r2 + 16
+		//   ROLE 1: second array, 8 channels, 8 head columns:  taps r0 + 8 j | T2 r0 + 16 | D r0 + 24 | XR r1 | HD r1 + 8
+		//           (the transition stages the first array's output pairs at r1 + 16 and its head output pairs at r0)
+		// The activated output z aliases tap 0.
+		template <int ROLE> struct Map;
+		template <> struct Map<0>
+		{
+			static constexpr int C = 16, HN = 8, N1 = 24;
+			static __device__ __forceinline__ uint32_t tap(const Ctx& cx, int j) { return cx.r0 + 16u * (uint32_t)j; }
+			static __device__ __forceinline__ uint32_t t2(const Ctx& cx) { return cx.r1; }
+			static __device__ __forceinline__ uint32_t d(const Ctx& cx) { return cx.r1 + 16u; }
+			static __device__ __forceinline__ uint32_t xr(const Ctx& cx) { return cx.r2; }
+			static __device__ __forceinline__ uint32_t hd(const Ctx& cx) { return cx.r2 + 16u; }
+		};
+		template <> struct Map<1>
+		{
+			static constexpr int C = 8, HN = 8, N1 = 16;
+			static __device__ __forceinline__ uint32_t tap(const Ctx& cx, int j) { return cx.r0 + 8u * (uint32_t)j; }
+			static __device__ __forceinline__ uint32_t t2(const Ctx& cx) { return cx.r0 + 16u; }
+			static __device__ __forceinline__ uint32_t d(const Ctx& cx) { return cx.r0 + 24u; }
+			static __device__ __forceinline__ uint32_t xr(const Ctx& cx) { return cx.r1; }
+			static __device__ __forceinline__ uint32_t hd(const Ctx& cx) { return cx.r1 + 8u; }
+		};
+		__device__ __forceinline__ uint32_t konst(const Ctx& cx) { return cx.r2 + 24u; }
+
+		// ---- hand-offs -------------------------------------------------------------------------------------------
+		template <int ID> __device__ __forceinline__ void stager_arrive()
+		{
+			wait_st();
+			fence_before();
+			nbar_arrive<ID, kThreads>();
+		}
+		template <int ID> __device__ __forceinline__ void stager_wait()
+		{
+			nbar_sync<ID, kThreads>();
+			fence_after();
+		}
+		template <int ID> __device__ __forceinline__ void issuer_sync()
+		{
+			nbar_sync<ID, kThreads>();
+			fence_after();
+		}
+		__device__ __forceinline__ void issuer_wait(Ctx& cx, uint32_t bar, uint32_t parity)
+		{
+			if (!mbar_wait(bar, parity) && cx.el) *reinterpret_cast<volatile int*>(cx.err) = 1;   // lost completion: flag it, keep going so the launch ends
+		}
+		template <int ID> __device__ __forceinline__ void issuer_release(Ctx& cx, uint32_t bar, uint32_t parity)
+		{
+			issuer_wait(cx, bar, parity);
+			nbar_arrive<ID, kThreads>();
+		}
+
+		// one lane: bulk copy of layer b's weight block into buffer (slot & 1)
+		__device__ __forceinline__ void issue_weights(const Ctx& cx, int b, uint32_t slot)
+		{
+			const uint4 g2 = lds128(cx.tab + (uint32_t)b * (uint32_t)sizeof(HLayer) + 32);
+			const uint32_t bar = cx.barW0 + 8u * (slot & 1u);
+			mbar_expect_tx(bar, g2.z);
+			bulk_g2s(cx.wbuf + (slot & 1u) * cx.wbufStride, cx.Wg + g2.y, g2.z, bar);
+		}
+
+		// Every stager thread: my rows of the history window(s) of layer l of stream s, HBM ring -> shared memory, with
+		// cp.async (16 bytes per plane and row; consecutive threads <-> consecutive rows, so a warp moves contiguous 512-byte
+		// runs); one cp.async group per layer.
+		template <int CG>
+		__device__ __forceinline__ void prefetch_windows(const Ctx& cx, int l, int s, const int* hd)
+		{
+			const uint32_t la = cx.tab + (uint32_t)l * (uint32_t)sizeof(HLayer);
+			const uint4 g0 = lds128(la), g1 = lds128(la + 16);
+			const int Lp = (int)g0.z, numJobs = (int)g1.y;
+			const int head = hd[g1.x];
+			const char* ring = reinterpret_cast<const char*>(cx.state + (size_t)s * cx.M->stateStride + (int)g0.w);
+			const size_t step = (size_t)Lp * 16;
+			for (int jb = 0; jb < numJobs; jb++)
+			{
+				const uint4 jj = lds128(la + kTabJobs + 16u * (uint32_t)jb);
+				const int cnt = (int)jj.x < 0 ? cx.n : (int)jj.x;
+				for (int r = cx.tid; r < cnt; r += kStagers)
+				{
+					int idx = head - (int)jj.y + r;
+					if (idx < 0) idx += Lp;
+					const char* src = ring + (size_t)idx * 16;
+					uint32_t dst = cx.win + jj.z + (uint32_t)r * 16u;
+#pragma unroll
+					for (int g = 0; g < CG; g++, src += step, dst += cx.planeStride) cp_async16(dst, src);
+				}
+			}
+			cp_async_commit();
+		}
+
+		// history of layer l counted from the first layer of stream s (l may run past the last layer: next stream)
+		__device__ __forceinline__ void prefetch_layer(const Ctx& cx, int l, int s, int a1First)
+		{
+			const int* hd = cx.hdb + cx.cur * kHdbHalf;
+			if (l >= cx.numLayers)
+			{
+				l = 0;
+				s += cx.gstride;
+				hd = cx.hdb + (cx.cur ^ 1) * kHdbHalf;
+				if (s >= cx.S) { cp_async_commit(); return; }
+			}
+			if (l < a1First) prefetch_windows<4>(cx, l, s, hd);
+			else prefetch_windows<2>(cx, l, s, hd);
+		}
+
+		// C fp32 values -> C words [h1 of channel pairs | h2 of channel pairs]
+		template <int C>
+		__device__ __forceinline__ void pack_pairs(const uint32_t (&x)[C], uint32_t (&p)[C])
+		{
+#pragma unroll
+			for (int c = 0; c < C / 2; c++) split_h2(x[2 * c], x[2 * c + 1], p[c], p[C / 2 + c]);
+		}
+
+		// FastMath<T>::Tanh (Activation.h:83-91) for two values.  With a = |x|: tanh ~ x * P(a) / Q(a),
+		// P = c0 + c0 a + c1 a^2 + c2 a^3 and Q = c3 + c3 a + c3 c4 a^2 + a^3 + c4 a^4 are the reference's numerator and
+		// denominator expanded (|x + c4 x a| = a (1 + c4 a)), evaluated by Horner; Q >= 2.445, one MUFU.RCP each.
+		__device__ __forceinline__ void fast_tanh2(uint32_t x0, uint32_t x1, uint32_t& y0, uint32_t& y1)
+		{
+			const float c0 = 2.45550750702956f, c1 = 0.893229853513558f, c2 = 0.821226666969744f;
+			const float c3 = 2.44506634652299f, c4 = 0.814642734961073f;
+			const u64 a = pack2(x0 & 0x7FFFFFFFu, x1 & 0x7FFFFFFFu);
+			u64 p = fma2(pack2f(c2, c2), a, pack2f(c1, c1));
+			p = fma2(p, a, pack2f(c0, c0));
+			p = fma2(p, a, pack2f(c0, c0));
+			u64 q = fma2(pack2f(c4, c4), a, pack2f(1.0f, 1.0f));
+			q = fma2(q, a, pack2f(c3 * c4, c3 * c4));
+			q = fma2(q, a, pack2f(c3, c3));
+			q = fma2(q, a, pack2f(c3, c3));
+			uint32_t q0, q1;
+			unpack2(q, q0, q1);
+			float r0, r1;
+			asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(__uint_as_float(q0)));
+			asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(__uint_as_float(q1)));
+			unpack2(mul2(mul2(pack2(x0, x1), p), pack2f(r0, r1)), y0, y1);
+		}
+
+		// ---- stager warps: one layer array of the CTA's stream ------------------------------------------------------
+		template <int ROLE>
+		__device__ __forceinline__ void stage_array(Ctx& cx, const int firstLayer, const int numLayers, const int s, const int a1First)
+		{
+			typedef Map<ROLE> MP;
+			constexpr int C = MP::C, CG = C / 4;
+			const int tid = cx.tid;
+			const uint32_t lane = (uint32_t)(cx.warp * 32) << 16;
+			const int* hd = cx.hdb + cx.cur * kHdbHalf;
+			float* const st = cx.state + (size_t)s * cx.M->stateStride;
+			const uint32_t myRow = cx.win + (uint32_t)tid * 16u;
+
+			for (int li = 0; li < numLayers; li++)
+			{
+				const int l = firstLayer + li;
+				const uint32_t la = cx.tab + (uint32_t)l * (uint32_t)sizeof(HLayer);
+				const uint4 g0 = lds128(la), g1 = lds128(la + 16), g2 = lds128(la + 32);
+				const int numTaps = (int)g0.x, groupTaps = (int)g2.w;
+				const bool mixed = g0.y != 0;
+
+				// ---- the residual stream after the previous layer -> packed pairs: undelayed tap, current rows, ring ----
+				stager_wait<kBarXReady>();
+				uint32_t p[C];
+				{
+					uint32_t x[C];
+					tmem_ld<C>(lane + MP::xr(cx), x);
+					pack_pairs<C>(x, p);
+				}
+				tmem_st<C>(lane + MP::t2(cx), p);
+				if (mixed)
+				{
+					const uint32_t cur = myRow + g2.x;
+#pragma unroll
+					for (int q = 0; q < CG; q++) sts128(cur + (uint32_t)q * cx.planeStride, p[4 * q], p[4 * q + 1], p[4 * q + 2], p[4 * q + 3]);
+				}
+				stager_arrive<kBarT2>();
+				// my copies of this layer's history have landed; where a tap mixes history and current frames the rows other
+				// threads copied / produced must be visible too
+				cp_async_wait_all();
+				if (mixed) nbar_sync<kBarMix, kStagers>();
+				// ---- delayed taps: my row of each, shared memory -> TMEM, no arithmetic ----
+#pragma unroll 1
+				for (int j0 = 0; j0 < numTaps; j0 += groupTaps)
+				{
+					if (j0 > 0) stager_wait<kBarGReady>();
+					const int jn = (j0 + groupTaps < numTaps) ? j0 + groupTaps : numTaps;
+#pragma unroll 1
+					for (int j = j0; j < jn; j++)
+					{
+						const uint32_t row = myRow + lds32(la + kTabTaps + 4u * (uint32_t)j);
+						uint32_t v[C];
+#pragma unroll
+						for (int q = 0; q < CG; q++)
+						{
+							const uint4 t = lds128(row + (uint32_t)q * cx.planeStride);
+							v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+						}
+						tmem_st<C>(lane + MP::tap(cx, j - j0), v);
+					}
+					stager_arrive<kBarTaps>();
+				}
+				// every stager is done with this layer's windows: request the next layer's (or the next stream's first layer's)
+				nbar_sync<kBarMix, kStagers>();
+				prefetch_layer(cx, l + 1, s, a1First);
+				// history write-back (AdvanceFrames, WaveNet.h:59-65): frame t becomes ring row (head + t) mod Lp
+				{
+					const int Lp = (int)g0.z;
+					const int first = cx.n > Lp ? cx.n - Lp : 0;
+					if (tid < cx.n && tid >= first)
+					{
+						int idx = (cx.n > Lp ? hd[36 + g1.x] : hd[g1.x]) + (tid - first);
+						if (idx >= Lp) idx -= Lp;
+						char* dst = reinterpret_cast<char*>(st + (int)g0.w) + (size_t)idx * 16;
+						const size_t step = (size_t)Lp * 16;
+#pragma unroll
+						for (int q = 0; q < CG; q++, dst += step) *reinterpret_cast<uint4*>(dst) = make_uint4(p[4 * q], p[4 * q + 1], p[4 * q + 2], p[4 * q + 3]);
+					}
+				}
+
+				// ---- activation (WaveNet.h:477-480); z -> packed pairs -> TMEM as the A operand of the 1x1 ----
+				stager_wait<kBarDReady>();
+				{
+					uint32_t dv[C], z[C];
+					tmem_ld<C>(lane + MP::d(cx), dv);
+#pragma unroll
+					for (int c = 0; c < C; c += 2) fast_tanh2(dv[c], dv[c + 1], z[c], z[c + 1]);
+					pack_pairs<C>(z, dv);
+					tmem_st<C>(lane + MP::tap(cx, 0), dv);
+				}
+				stager_arrive<kBarZ>();
+			}
+		}
+
+		// conv-type product into accumulator `acc`: A at TMEM `a` (C == 16: h1 at a, h2 at a + 8; C == 8: [h1 | h2] at a),
+		// weights at 16-byte unit `b16` (C == 16: W1 | W2, 2 N units each; C == 8: [W1; W1] | [W2; 0])
+		template <int C, uint32_t ACC0>
+		__device__ __forceinline__ void mma_pairs(uint32_t acc, uint32_t a, uint32_t b16, int N)
+		{
+			const uint32_t id = idesc_f16(N);
+			if constexpr (C == 16)
+			{
+				mma_f16_ts<ACC0>(acc, a, desc_at(b16, (uint32_t)N), id);
+				mma_f16_ts<1>(acc, a + 8u, desc_at(b16, (uint32_t)N), id);
+				mma_f16_ts<1>(acc, a, desc_at(b16 + 2u * (uint32_t)N, (uint32_t)N), id);
+			}
+			else
+			{
+				mma_f16_ts<ACC0>(acc, a, desc_at(b16, (uint32_t)N), id);
+				mma_f16_ts<1>(acc, a, desc_at(b16 + 2u * (uint32_t)N, (uint32_t)N), id);
+			}
+		}
+
+		// ---- issuer warp: one layer array of the CTA's stream --------------------------------------------------------
+		template <int ROLE>
+		__device__ __forceinline__ void issue_array(Ctx& cx, const int firstLayer, const int numLayers)
+		{
+			typedef Map<ROLE> MP;
+			constexpr int C = MP::C, N1 = MP::N1;
+			for (int li = 0; li < numLayers; li++)
+			{
+				const int l = firstLayer + li;
+				const uint32_t la = cx.tab + (uint32_t)l * (uint32_t)sizeof(HLayer);
+				const int numTaps = (int)lds32(la);
+				const uint4 g2 = lds128(la + 32), g3 = lds128(la + 48), g4 = lds128(la + 64);
+				const int groupTaps = (int)g2.w;
+				const uint32_t tapStride16 = g4.x;
+				// this layer's weight block (the first layer of an array was awaited by the entry / transition code)
+				if (li > 0) issuer_wait(cx, cx.barW0 + 8u * (cx.wq & 1u), (cx.wq >> 1) & 1u);
+				// the other buffer held the previous layer's block, whose MMAs are complete: request the next block
+				if (cx.el) issue_weights(cx, (l + 1 < cx.numLayers) ? l + 1 : 0, cx.wq + 1);
+				__syncwarp();
+				const uint32_t wb16 = (cx.wbuf + (cx.wq & 1u) * cx.wbufStride) >> 4;
+
+				// ---- dilated conv + mix-in + bias (WaveNet.h:250-289,471-476): undelayed tap, constant operand, delayed taps ----
+				issuer_sync<kBarT2>();
+				if (cx.el)
+				{
+					mma_pairs<C, 0>(MP::d(cx), MP::t2(cx), wb16 + (uint32_t)numTaps * tapStride16, C);   // overwrites the accumulator
+					mma_f16_ts<1>(MP::d(cx), konst(cx), desc_at(wb16 + g3.x, C), idesc_f16(C));
+				}
+				__syncwarp();
+				for (int j0 = 0; j0 < numTaps; j0 += groupTaps)
+				{
+					const int jn = (j0 + groupTaps < numTaps) ? j0 + groupTaps : numTaps;
+					issuer_sync<kBarTaps>();
+					if (cx.el)
+					{
+						for (int j = j0; j < jn; j++) mma_pairs<C, 1>(MP::d(cx), MP::tap(cx, j - j0), wb16 + (uint32_t)j * tapStride16, C);
+						mma_commit(cx.barD);
+					}
+					__syncwarp();
+					if (jn < numTaps) issuer_release<kBarGReady>(cx, cx.barD, cx.dq & 1u);
+					else issuer_release<kBarDReady>(cx, cx.barD, cx.dq & 1u);
+					cx.dq++;
+				}
+
+				// ---- 1x1 + bias + residual, head sum (WaveNet.h:482-491): XR | HD += [z] [W1x1 | Whead] ----
+				issuer_sync<kBarZ>();
+				if (cx.el)
+				{
+					mma_f16_ts<1>(MP::xr(cx), konst(cx), desc_at(wb16 + g3.w, N1), idesc_f16(N1));
+					if constexpr (C == 16)
+					{
+						mma_f16_ts<1>(MP::xr(cx), MP::tap(cx, 0), desc_at(wb16 + g3.y, N1), idesc_f16(N1));
+						mma_f16_ts<1>(MP::xr(cx), MP::tap(cx, 0) + 8u, desc_at(wb16 + g3.y, N1), idesc_f16(N1));
+						mma_f16_ts<1>(MP::xr(cx), MP::tap(cx, 0), desc_at(wb16 + g3.z, N1), idesc_f16(N1));
+					}
+					else
+					{
+						mma_f16_ts<1>(MP::xr(cx), MP::tap(cx, 0), desc_at(wb16 + g3.y, N1), idesc_f16(N1));
+						mma_f16_ts<1>(MP::xr(cx), MP::tap(cx, 0), desc_at(wb16 + g3.z, N1), idesc_f16(N1));
+					}
+					mma_commit(cx.barX);
+				}
+				__syncwarp();
+				issuer_release<kBarXReady>(cx, cx.barX, cx.xq & 1u);
+				cx.xq++;
+				cx.wq++;
+			}
+		}
+
+		constexpr int kNumBars = 4;
+
+		__global__ void __maxnreg__(64)
+			wavenet_h_kernel(const __grid_constant__ WnModelDev M, const float* __restrict__ Wg, float* __restrict__ state, int* __restrict__ heads,
+				const float* in, float* out, long long inSS, long long inFS, long long outSS, long long outFS, int S, int n, int* __restrict__ err)
+		{
+			extern __shared__ __align__(128) unsigned char smem[];
+			Ctx cx;
+			cx.M = &M;
+			cx.Wg = Wg;
+			cx.state = state;
+			cx.err = err;
+			cx.win = smem_u32(smem);
+			cx.planeStride = (uint32_t)M.winRows * 16u;
+			const uint32_t winBytes = (uint32_t)(M.arrays[0].C / 4) * cx.planeStride;
+			cx.wbuf = cx.win + winBytes;
+			cx.wbufStride = (uint32_t)M.maxBlockBytes;
+			unsigned char* tabPtr = smem + winBytes + 2u * (uint32_t)M.maxBlockBytes;
+			cx.tab = smem_u32(tabPtr);
+			cx.hdb = reinterpret_cast<int*>(tabPtr + (size_t)M.numLayers * sizeof(HLayer));
+			unsigned long long* bars = reinterpret_cast<unsigned long long*>(cx.hdb + 2 * kHdbHalf);
+			uint32_t* tmemSlot = reinterpret_cast<uint32_t*>(bars + kNumBars);
+			cx.barW0 = smem_u32(&bars[0]);
+			cx.barD = smem_u32(&bars[2]);
+			cx.barX = smem_u32(&bars[3]);
+			cx.n = n;
+			cx.tid = threadIdx.x;
+			cx.warp = threadIdx.x >> 5;
+			cx.S = S;
+			cx.gstride = gridDim.x;
+			cx.numLayers = M.numLayers;
+			cx.wq = 0; cx.dq = 0; cx.xq = 0; cx.cur = 0;
+			cx.el = elect_one();
+			const int tid = threadIdx.x, warp = cx.warp;
+			const bool stager = warp < 4;
+			const int first0 = M.arrays[0].firstLayer, num0 = M.arrays[0].numLayers;
+			const int first1 = M.arrays[1].firstLayer, num1 = M.arrays[1].numLayers;
+
+			// per-layer plan: built on the host (PackWaveNetH), copied to shared memory
+			{
+				const uint4* src = reinterpret_cast<const uint4*>(Wg + M.tableOff);
+				uint4* dst = reinterpret_cast<uint4*>(tabPtr);
+				const int n16 = M.numLayers * (int)(sizeof(HLayer) / 16);
+				for (int i = tid; i < n16; i += kThreads) dst[i] = __ldg(src + i);
+			}
+			if (tid == 0)
+			{
+				mbar_init(cx.barW0, 1);
+				mbar_init(cx.barW0 + 8u, 1);
+				mbar_init(cx.barD, 1);
+				mbar_init(cx.barX, 1);
+				asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+			}
+			if (warp == 4)
+			{
+				// three allocations of the same size cannot fragment: 5 CTAs x 96 columns fit the SM's 512
+				tmem_alloc<32>(smem_u32(tmemSlot));
+				tmem_alloc<32>(smem_u32(tmemSlot + 1));
+				tmem_alloc<32>(smem_u32(tmemSlot + 2));
+				tmem_relinquish();
+			}
+			const int s0 = blockIdx.x;
+			if (tid < M.numRings && s0 < S)
+			{
+				const int Lp = M.ringLp[tid];
+				const int h = heads[(size_t)s0 * M.numRings + tid];
+				int hn = h + (n % Lp);
+				if (hn >= Lp) hn -= Lp;
+				cx.hdb[tid] = h;
+				cx.hdb[36 + tid] = hn;
+			}
+			fence_before();
+			__syncthreads();
+			fence_after();
+			cx.r0 = tmemSlot[0]; cx.r1 = tmemSlot[1]; cx.r2 = tmemSlot[2];
+
+			if (!stager)
+			{
+				// =================================== issuer warp ===================================
+				const uint32_t ent0 = lds128(cx.tab + (uint32_t)first0 * (uint32_t)sizeof(HLayer) + 64).z;
+				const uint32_t ent1 = lds128(cx.tab + (uint32_t)first1 * (uint32_t)sizeof(HLayer) + 64).z;
+				if (cx.el) issue_weights(cx, 0, 0);
+				for (int s = s0; s < S; s += gridDim.x)
+				{
+					// ---- entry: [XR | HD] = constant operand x [rechannel 1 -> C0 | head bias] (WaveNet.h:637) ----
+					issuer_wait(cx, cx.barW0 + 8u * (cx.wq & 1u), (cx.wq >> 1) & 1u);
+					issuer_sync<kBarE>();
+					if (cx.el)
+					{
+						const uint32_t wb16 = (cx.wbuf + (cx.wq & 1u) * cx.wbufStride) >> 4;
+						mma_f16_ts<0>(Map<0>::xr(cx), konst(cx), desc_at(wb16 + ent0, 24), idesc_f16(24));
+						mma_commit(cx.barX);
+					}
+					__syncwarp();
+					issuer_release<kBarXReady>(cx, cx.barX, cx.xq & 1u);
+					cx.xq++;
+					issue_array<0>(cx, first0, num0);
+
+					// ---- array transition (WaveNet.h:785-789): [XR1 | HD1] = rechannel C0 -> C1 of the array output | head carry ----
+					issuer_wait(cx, cx.barW0 + 8u * (cx.wq & 1u), (cx.wq >> 1) & 1u);
+					issuer_sync<kBarE>();
+					if (cx.el)
+					{
+						const uint32_t wb16 = (cx.wbuf + (cx.wq & 1u) * cx.wbufStride) >> 4;
+						const uint32_t acc = Map<1>::xr(cx), e = wb16 + ent1, id = idesc_f16(16);
+						mma_f16_ts<0>(acc, cx.r1 + 16u, desc_at(e, 16), id);          // [Re1 | 0] x h1 of the array output
+						mma_f16_ts<1>(acc, cx.r1 + 24u, desc_at(e, 16), id);          // ... x h2
+						mma_f16_ts<1>(acc, cx.r1 + 16u, desc_at(e + 32u, 16), id);    // [Re2 | 0] x h1
+						mma_f16_ts<1>(acc, cx.r0, desc_at(e + 64u, 16), id);          // [0 | Wc1 ; Wc1] x [h1 | h2] of the head output
+						mma_f16_ts<1>(acc, cx.r0, desc_at(e + 96u, 16), id);          // [0 | Wc2 ; 0]
+						mma_f16_ts<1>(acc, konst(cx), desc_at(e + 128u, 16), id);     // [0 | head bias]
+						mma_commit(cx.barX);
+					}
+					__syncwarp();
+					issuer_release<kBarXReady>(cx, cx.barX, cx.xq & 1u);
+					cx.xq++;
+					issue_array<1>(cx, first1, num1);
+					cx.cur ^= 1;
+				}
+				// drain the weight prefetch that ran ahead of the last layer
+				issuer_wait(cx, cx.barW0 + 8u * (cx.wq & 1u), (cx.wq >> 1) & 1u);
+			}
+			else
+			{
+				// =================================== stager warps ===================================
+				const uint32_t lane = (uint32_t)(warp * 32) << 16;
+				float cond = 0.0f;
+				if (tid < n && s0 < S) cond = in[(long long)s0 * inSS + (long long)tid * inFS];
+				if (s0 < S) prefetch_windows<4>(cx, 0, s0, cx.hdb);
+				for (int s = s0; s < S; s += gridDim.x)
+				{
+					const int sn = s + gridDim.x;
+					int* hdNext = cx.hdb + (cx.cur ^ 1) * kHdbHalf;
+					float condNext = 0.0f;
+					if (sn < S)
+					{
+						if (tid < M.numRings)
+						{
+							const int Lp = M.ringLp[tid];
+							const int h = heads[(size_t)sn * M.numRings + tid];
+							int hn = h + (n % Lp);
+							if (hn >= Lp) hn -= Lp;
+							hdNext[tid] = h;
+							hdNext[36 + tid] = hn;
+						}
+						if (tid < n) condNext = in[(long long)sn * inSS + (long long)tid * inFS];
+					}
+					// ---- entry: constant operand, 16 halves [c1, c2, c1, 1, 1, 1, 0 ...] ----
+					{
+						uint32_t c12, dummy;
+						split_h2(__float_as_uint(cond), 0u, c12, dummy);   // c12 low half = c1; dummy low half = c2
+						uint32_t cv[8];
+						cv[0] = (c12 & 0xFFFFu) | (dummy << 16);           // k = 0: c1, k = 1: c2
+						cv[1] = (c12 & 0xFFFFu) | 0x3C000000u;             // k = 2: c1, k = 3: 1
+						cv[2] = 0x3C003C00u;                               // k = 4, 5: 1
+						cv[3] = 0u; cv[4] = 0u; cv[5] = 0u; cv[6] = 0u; cv[7] = 0u;
+						tmem_st<8>(lane + konst(cx), cv);
+					}
+					stager_arrive<kBarE>();
+					stage_array<0>(cx, first0, num0, s, first1);
+
+					// ---- array transition: the array output and its head output as packed pairs ----
+					stager_wait<kBarXReady>();
+					{
+						uint32_t x[16], p[16];
+						tmem_ld<16>(lane + Map<0>::xr(cx), x);
+						pack_pairs<16>(x, p);
+						tmem_st<16>(lane + cx.r1 + 16u, p);
+						uint32_t h[8], hp[8];
+						tmem_ld<8>(lane + Map<0>::hd(cx), h);
+						pack_pairs<8>(h, hp);
+						tmem_st<8>(lane + cx.r0, hp);
+					}
+					stager_arrive<kBarE>();
+					stage_array<1>(cx, first1, num1, s, first1);
+
+					// ---- output (WaveNet.h:793-798) ----
+					stager_wait<kBarXReady>();
+					{
+						uint32_t h[8];
+						tmem_ld<8>(lane + Map<1>::hd(cx), h);
+						if (tid < n) out[(long long)s * outSS + (long long)tid * outFS] = M.headScale * __uint_as_float(h[0]);
+					}
+					if (tid < M.numRings) heads[(size_t)s * M.numRings + tid] = cx.hdb[cx.cur * kHdbHalf + 36 + tid];
+					cx.cur ^= 1;
+					cond = condNext;
+					// a thread's TMEM reads above complete before its own stores of the next stream's entry; hdb slots are
+					// rewritten two streams later, after many hand-offs
+				}
+			}
+
+			fence_before();
+			__syncthreads();
+			if (warp == 4)
+			{
+				tmem_dealloc<32>(cx.r0);
+				tmem_dealloc<32>(cx.r1);
+				tmem_dealloc<32>(cx.r2);
+			}
+		}
+	}
+
+	bool wavenet_h_variant_supported(int C0, int C1, int act)
+	{
+		return C0 == 16 && C1 == 8 && act == 0;
+	}
+
+	size_t wavenet_h_smem_bytes(const WnModelDev& M)
+	{
+		return (size_t)(M.arrays[0].C / 4) * M.winRows * 16 + (size_t)2 * M.maxBlockBytes + (size_t)M.numLayers * sizeof(HLayer) +
+			2 * hk::kHdbHalf * 4 + hk::kNumBars * 8 + 16;
+	}
+
+	cudaError_t wavenet_h_launch(const WnModelDev& M, const WnLaunch& a)
+	{
+		if (M.tc != 3 || !wavenet_h_variant_supported(M.arrays[0].C, M.numArrays > 1 ? M.arrays[1].C : 0, M.arrays[0].act)) return cudaErrorNotSupported;
+		if (a.n > hk::kCur || a.n < 1) return cudaErrorInvalidValue;
+		if (!a.err) return cudaErrorInvalidValue;
+		auto kfn = hk::wavenet_h_kernel;
+		const size_t smem = wavenet_h_smem_bytes(M);
+		cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		if (e != cudaSuccess) return e;
+		// five CTAs of ~43 KB need the SM's full 228 KB as shared memory: ask for the maximum carve-out (the default heuristic
+		// keeps more L1 and fits only four - ncu launch__occupancy_limit_shared_mem)
+		e = cudaFuncSetAttribute(kfn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+		if (e != cudaSuccess) return e;
+		if (getenv("NAB200_H_DEBUG"))
+		{
+			int occ = 0;
+			cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kfn, hk::kThreads, smem);
+			fprintf(stderr, "wavenet_h_kernel: %zu bytes of shared memory per CTA, %d CTAs per SM fit\n", smem, occ);
+		}
+		int ctasPerSM = a.ctasPerSM > 0 ? a.ctasPerSM : 5;
+		int grid = a.numSMs * ctasPerSM;
+		if (grid > a.S) grid = a.S;
+		if (grid < 1) grid = 1;
+		kfn<<<grid, hk::kThreads, smem, a.stream>>>(M, a.weights, a.state, a.heads, a.in, a.out, a.inSS, a.inFS, a.outSS, a.outFS, a.S, a.n, a.err);
+		return cudaGetLastError();
+	}
+}

@@ -164,7 +164,7 @@ def test_tmem_operand_packing_reconstructs_weights(na, tmp_path):
         g = load_golden(golden_files(name)[0])
         mf = model_file_for(g, tmp_path)
         d = na.describe_model_file(mf)
-        assert d["kernel"] == "tcgen05_tmem_operands"
+        assert d["kernel"] == "tcgen05_fp16_pairs"     # the default; use_tc = 2 selects the 3xTF32 kernel described by d["ts"]
         ts = d["ts"]
         assert ts["num_rings"] == d["num_rings"] == d["num_layers"]
         pad = [a["padded"] for a in d["arrays"]]
@@ -173,6 +173,13 @@ def test_tmem_operand_packing_reconstructs_weights(na, tmp_path):
         if state_floats:
             assert ts["state_floats"] == state_floats and pad[0] >= 16
         assert ts["conv_hi_not_tf32"] == 0
+        # fp16-pair packing: same state size (the rings hold the packed (h1, h2) pairs, 4 bytes per value), every conv tap
+        # reconstructs as W1 + W2 to half an fp16 subnormal step (2^-25) or 2^-22 relative, whichever is larger
+        h = d["h"]
+        assert h["state_floats"] == ts["state_floats"] and h["num_rings"] == ts["num_rings"]
+        assert h["conv_split_max_error"] <= 2.0 ** -22 * max(1.0, float(np.abs(g["weights"]).max()))
+        # five streams per SM: shared memory per CTA must stay below (228 KB - 5 KB) / 5
+        assert h["win_rows"] * 64 + 2 * h["max_block_bytes"] + h["table_bytes"] + 1024 < (228 * 1024 - 5 * 1024) // 5
         assert ts["conv_split_max_error"] <= 1e-7
         assert ts["max_block"] * 4 * 2 <= 48 * 1024      # two weight buffers per CTA, 4 CTAs per SM
     g = load_golden(golden_files("syn_a1_nano")[0])
