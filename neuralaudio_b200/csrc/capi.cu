@@ -450,15 +450,24 @@ int NA_DescribeModelFile(const wchar_t* modelPath, int externalSampleRate, char*
 							for (size_t l = 0; l < A.dilations.size(); l++, layer++)
 							{
 								const nab200::WnLayer& L = q.dev.layers[layer];
-								const __half* blk = reinterpret_cast<const __half*>(q.weights.data() + L.wOff);
+								const nab200::HLayer& T = tab[layer];
 								const int K = A.kernelSizes[l];
-								const size_t opHalves = (size_t)2 * CP * 8, tapHalves = (size_t)tab[layer].tapStride16 * 8;
+								const size_t opHalves = (size_t)2 * CP * 8;
+								// where tap k's [W1 | W2] sits: the undelayed tap and group 0 in sub-block 0, later groups in their own sub-blocks
+								auto tapAt = [&](int k) -> const __half*
+								{
+									if (k == K - 1) return reinterpret_cast<const __half*>(q.weights.data() + T.gOff[0]) + (size_t)T.und16 * 8;
+									const int g = k / T.groupTaps;
+									return reinterpret_cast<const __half*>(q.weights.data() + T.gOff[g]) + ((size_t)(g == 0 ? T.tap0Base16 : 0) + (size_t)(k - g * T.groupTaps) * T.tapStride16) * 8;
+								};
+								(void)L;
 								const float* src = w;
 								for (int i = 0; i < C; i++)
 									for (int jn = 0; jn < C; jn++)
 										for (int k = 0; k < K; k++)
 										{
-											const size_t at = (size_t)k * tapHalves + ((size_t)(jn / 8) * CP + i) * 8 + (jn % 8);
+											const __half* blk = tapAt(k);
+											const size_t at = ((size_t)(jn / 8) * CP + i) * 8 + (jn % 8);
 											const double v = (double)__half2float(blk[at]) + (double)__half2float(blk[at + opHalves]);
 											const double e = fabs(v - (double)*src);
 											if (e > worst) worst = e;
@@ -467,7 +476,7 @@ int NA_DescribeModelFile(const wchar_t* modelPath, int externalSampleRate, char*
 										}
 								w += (size_t)C * C * K + C + C + (size_t)C * C + C;
 							}
-							w += (size_t)A.headSize * C + (A.headBias ? A.headSize : 0);
+							w += (size_t)A.headSize * C * A.headKernel + (A.headBias ? A.headSize : 0);
 						}
 						os << ",\"h\":{\"packed_floats\":" << q.weights.size() << ",\"state_floats\":" << q.dev.stateStride << ",\"max_block_bytes\":" << q.dev.maxBlockBytes
 						   << ",\"num_rings\":" << q.dev.numRings << ",\"win_rows\":" << q.dev.winRows << ",\"table_bytes\":" << (size_t)q.dev.numLayers * sizeof(nab200::HLayer)

@@ -868,20 +868,32 @@ namespace nab200
 		};
 	}
 
+	// A2-style single array: 8 padded channels, LeakyReLU, 16-tap head conv with one output (InternalModel.h:12-20, NeuralModel.cpp:188-317)
+	static bool IsHSingleArray(const WaveNetDesc& desc)
+	{
+		if (desc.arrays.size() != 1) return false;
+		const WaveNetArrayDesc& A = desc.arrays[0];
+		return A.channels > 4 && A.channels <= 8 && A.inputSize == 1 && A.headSize == 1 && A.headKernel == 16 && A.activation == 1 && !A.dilations.empty();
+	}
+
 	bool WaveNetHSupported(const WaveNetDesc& desc)
 	{
-		// same architecture family as the TMEM-operand 3xTF32 kernel: two arrays of (9..16, <= 8) channels, tanh, kernel size 3,
-		// 1x1 heads, head of array 0 feeding array 1; every layer's history must fit the window plan below
-		if (!WaveNetTsSupported(desc)) return false;
-		constexpr int R = 384;
+		// two arrays of (9..16, <= 8) channels, tanh, kernel size 3, 1x1 heads, head of array 0 feeding array 1 (A1 Standard / Lite
+		// and stacks of that family) - or the A2 single array; every layer's history must fit the window plan below
+		const bool single = IsHSingleArray(desc);
+		if (!single && !WaveNetTsSupported(desc)) return false;
+		const int R = single ? 640 : 384;
+		size_t layers = 0;
 		for (const auto& A : desc.arrays)
-			for (size_t l = 0; l < A.dilations.size(); l++)
+			for (size_t l = 0; l < A.dilations.size(); l++, layers++)
 			{
 				const long long K = A.kernelSizes[l], d = A.dilations[l], Lp = (K - 1) * d;
+				if (K < 2 || K - 1 > kHMaxTaps) return false;
+				if (single && l == 0 && Lp + 128 > 144) return false;   // the head-conv scratch sits behind the first layer's window
 				if (Lp + 128 <= R) continue;                       // one contiguous window
 				if (d < 128 || (K - 1) * 128 > R || K - 1 > kHMaxJobs) return false;   // else every tap needs its own 128-row window
 			}
-		return true;
+		return layers <= (size_t)kMaxLayers;
 	}
 
 	PackedWaveNet PackWaveNetH(const WaveNetDesc& desc)
@@ -891,7 +903,8 @@ namespace nab200
 		memset(&M, 0, sizeof(M));
 		M.tc = 3;
 		M.numArrays = (int)desc.arrays.size();
-		constexpr int R = 384;   // rows per plane of the shared-memory window buffer
+		const bool single = IsHSingleArray(desc);
+		const int R = single ? 640 : 384;   // rows per plane of the shared-memory window buffer
 		M.winRows = R;
 		const float* w = desc.weights.data();
 		int layerIdx = 0, ringIdx = 0, ringOff = 0;
@@ -901,12 +914,12 @@ namespace nab200
 		{
 			const WaveNetArrayDesc& A = desc.arrays[a];
 			WnArray& DA = M.arrays[a];
-			const int C = A.channels, CP = TcPad(C), HN = 8, N1 = CP + HN;
+			const int C = A.channels, CP = TcPad(C), Kh = A.headKernel, HN = single ? 16 : 8, N1 = CP + HN;
 			const int last = a + 1 == M.numArrays;
 			const int inC = A.inputSize;
 			const int H = A.headSize;
 			const int nL = (int)A.dilations.size();
-			DA.C = CP; DA.inC = a == 0 ? 1 : TcPad(inC); DA.H = 8; DA.Kh = 1; DA.act = A.activation;
+			DA.C = CP; DA.inC = a == 0 ? 1 : TcPad(inC); DA.H = 8; DA.Kh = Kh; DA.act = A.activation;
 			DA.firstLayer = layerIdx; DA.numLayers = nL; DA.realC = C; DA.realH = H;
 			const float* wRe = w; w += (size_t)C * inC;
 			std::vector<const float*> wLayer(nL);
@@ -915,7 +928,7 @@ namespace nab200
 				wLayer[l] = w;
 				w += (size_t)C * C * A.kernelSizes[l] + C + C + (size_t)C * C + C;
 			}
-			const float* wHead = w; w += (size_t)H * C + (A.headBias ? H : 0);   // file [H][C] then bias
+			const float* wHead = w; w += (size_t)H * C * Kh + (A.headBias ? H : 0);   // file [H][C][Kh] then bias
 			// element (input channel j, output n) of a CP-channel contraction: C == 16: W1 at k = j of operand 1, W2 at k = j of
 			// operand 2; C == 8: [W1 ; W1] (k = j and k = 8 + j) and [W2 ; 0]
 			auto putPair = [&](HBlock& B, uint32_t op1, uint32_t op2, int N, int j, int n, float v)
@@ -944,16 +957,28 @@ namespace nab200
 
 				HBlock B;
 				const uint32_t opN = 2u * CP;                       // units of one conv operand [2][CP][8]
-				const uint32_t taps16 = B.Alloc((uint32_t)K * 2u * opN);
-				const uint32_t convC16 = B.Alloc(opN);
-				const uint32_t one116 = B.Alloc(2u * N1), one216 = B.Alloc(2u * N1), oneC16 = B.Alloc(2u * N1);
+				const int groupTaps = single ? 6 : 2;
+				const int numGroups = (K - 1 + groupTaps - 1) / groupTaps;
+				// sub-block 0: [entry (first layer of an array)] [undelayed tap] [convC] [taps of group 0]; sub-block g: [taps of group g];
+				// the last sub-block ends with [one1] [one2] [oneC]
+				uint32_t gStart[4] = { 0, 0, 0, 0 };
 				uint32_t ent16 = 0;
 				if (l == 0) ent16 = B.Alloc(a == 0 ? 2u * 24u : 6u * 32u);
+				const uint32_t und16 = B.Alloc(2u * opN);
+				const uint32_t convC16 = B.Alloc(opN);
+				std::vector<uint32_t> tap16(K, und16);          // absolute unit offset of tap k's [W1 | W2]
+				for (int g = 0; g < numGroups; g++)
+				{
+					if (g > 0) gStart[g] = (uint32_t)(B.h.size() / 8);
+					for (int j = g * groupTaps; j < (g + 1) * groupTaps && j < K - 1; j++) tap16[j] = B.Alloc(2u * opN);
+				}
+				const uint32_t one116 = B.Alloc(2u * N1), one216 = B.Alloc(2u * N1), oneC16 = B.Alloc(2u * N1);
+				gStart[numGroups] = (uint32_t)(B.h.size() / 8);
 				const float* src = wLayer[l];
 				// conv file order [out][in][k] (WaveNet.h:99-105); tap k = K - 1 is the undelayed one
 				for (int i = 0; i < C; i++)
 					for (int j = 0; j < C; j++)
-						for (int k = 0; k < K; k++) putPair(B, taps16 + (uint32_t)k * 2u * opN, taps16 + (uint32_t)k * 2u * opN + opN, CP, j, i, *src++);
+						for (int k = 0; k < K; k++) putPair(B, tap16[k], tap16[k] + opN, CP, j, i, *src++);
 				// constant-operand rows against [c1, c2, c1, 1, 1, 1]: mix1, mix1, mix2, b1, b2, b3
 				const float* convB = src; src += C;
 				const float* mix = src; src += C;
@@ -971,8 +996,16 @@ namespace nab200
 						const float v = *src++;
 						if (needOut) putPair(B, one116, one216, N1, j, i, v);
 					}
-				for (int h = 0; h < H; h++)
-					for (int j = 0; j < C; j++) putPair(B, one116, one216, N1, j, CP + h, wHead[h * C + j]);
+				if (single)
+				{
+					// one head column per head-conv tap k: G_k = Wh[.][k] . z, summed over layers on the tensor core; the kernel's
+					// output stage adds the taps with their frame shifts (WaveNet.h:658-660)
+					for (int j = 0; j < C; j++)
+						for (int k = 0; k < Kh; k++) putPair(B, one116, one216, N1, j, CP + k, wHead[(size_t)j * Kh + k]);
+				}
+				else
+					for (int h = 0; h < H; h++)
+						for (int j = 0; j < C; j++) putPair(B, one116, one216, N1, j, CP + h, wHead[h * C + j]);
 				for (int i = 0; i < C; i++)
 				{
 					SplitH3(*src++, h3);
@@ -989,7 +1022,14 @@ namespace nab200
 							SplitH3(wRe[i], h3);
 							B.Put(ent16, 24, 0, i, h3[0]); B.Put(ent16, 24, 1, i, h3[0]); B.Put(ent16, 24, 2, i, h3[1]);
 						}
-						if (A.headBias)
+						if (A.headBias && single)
+						{
+							// the head bias rides in the newest tap's column (added once per output frame)
+							SplitH3(wHead[(size_t)C * Kh], h3);
+							const int col = CP + Kh - 1;
+							B.Put(ent16, 24, 3, col, h3[0]); B.Put(ent16, 24, 4, col, h3[1]); B.Put(ent16, 24, 5, col, h3[2]);
+						}
+						else if (A.headBias)
 							for (int h = 0; h < H && h < 8; h++)
 							{
 								SplitH3(wHead[(size_t)H * C + h], h3);
@@ -1029,12 +1069,19 @@ namespace nab200
 				L.wOff = (int)P.weights.size();
 				P.weights.resize(P.weights.size() + L.wSize, 0.0f);
 				memcpy(P.weights.data() + L.wOff, B.h.data(), B.h.size() * 2);
-				if (L.wSize > M.maxBlock) M.maxBlock = L.wSize;
 
 				// window plan
 				T.numTaps = K - 1; T.Lp = L.Lp; T.ringOff = L.ringOff; T.ringIdx = L.ringIdx; T.K = K; T.C = CP;
-				T.wOff = (uint32_t)L.wOff; T.wBytes = (uint32_t)L.wSize * 4u; T.groupTaps = 2;
-				T.convC16 = convC16; T.one116 = one116; T.one216 = one216; T.oneC16 = oneC16;
+				T.groupTaps = groupTaps; T.numGroups = numGroups;
+				for (int g = 0; g < numGroups; g++)
+				{
+					T.gOff[g] = (uint32_t)L.wOff + gStart[g] * 4u;
+					T.gBytes[g] = (gStart[g + 1] - gStart[g]) * 16u;
+					if ((int)T.gBytes[g] > M.maxBlockBytes) M.maxBlockBytes = (int)T.gBytes[g];
+				}
+				const uint32_t lastStart = gStart[numGroups - 1];
+				T.und16 = und16; T.convC16 = convC16; T.tap0Base16 = tap16[0];
+				T.one116 = one116 - lastStart; T.one216 = one216 - lastStart; T.oneC16 = oneC16 - lastStart;
 				T.tapStride16 = 2u * opN; T.N1 = (uint32_t)N1; T.ent16 = ent16; T.flags = (uint32_t)L.flags;
 				if (L.Lp + 128 <= R)
 				{
@@ -1066,8 +1113,15 @@ namespace nab200
 		M.headScale = *w;
 		M.numLayers = layerIdx;
 		M.numRings = ringIdx;
+		if (single)
+		{
+			// head-conv history: per head tap the last 15 frames of its per-frame product, [16 taps][16 frames] floats
+			M.arrays[0].headLp = 16;
+			M.arrays[0].headRingOff = Align4(ringOff);
+			ringOff = M.arrays[0].headRingOff + 16 * 16;
+		}
 		M.stateStride = Align4(ringOff);
-		M.maxBlockBytes = M.maxBlock * 4;
+		M.maxBlock = M.maxBlockBytes / 4;
 		M.tableOff = (int)P.weights.size();
 		P.weights.resize(P.weights.size() + table.size() * sizeof(HLayer) / 4, 0.0f);
 		memcpy(P.weights.data() + M.tableOff, table.data(), table.size() * sizeof(HLayer));

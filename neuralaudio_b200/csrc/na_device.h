@@ -94,7 +94,9 @@ namespace nab200
 	//       C ==  8: Wa = [W1 ; W1][2][8][8] | Wb = [W2 ; 0]   (k group 0 pairs with the h1 halves, group 1 with the h2 halves)
 	//     then convC[2][C][8] (rows: mix1, mix1, mix2, b1, b2, b3 against the constant operand [c1, c2, c1, 1, 1, 1, 0...]),
 	//     one1 / one2 / oneC with N1 = C + HN columns (1x1 | head conv), and on the first layer of an array the entry /
-	//     transition operands (see PackWaveNetH).
+	//     transition operands (see PackWaveNetH).  A layer with more delayed taps than one hand-off carries (K = 15) is cut
+	//     into sub-blocks, one per tap group, staged one after the other through the same two shared-memory buffers:
+	//     [entry | undelayed tap | convC | taps of group 0] [taps of group 1] ... [taps of the last group | one1 | one2 | oneC].
 	constexpr int kHMaxTaps = 16;   // delayed taps per layer (K - 1 <= 14 for the official shapes)
 	constexpr int kHMaxJobs = 6;    // history-window copy jobs per layer
 	struct HJob
@@ -108,9 +110,11 @@ namespace nab200
 	{
 		int numTaps, mixed, Lp, ringOff;                       // group 0
 		int ringIdx, numJobs, K, C;                            // group 1
-		uint32_t curOff, wOff, wBytes; int groupTaps;          // group 2: current-row offset (bytes), block offset (floats), block bytes, taps per hand-off
-		uint32_t convC16, one116, one216, oneC16;              // group 3: offsets inside the block, 16-byte units
-		uint32_t tapStride16, N1, ent16, flags;                // group 4
+		uint32_t curOff; int numGroups, pad0, groupTaps;       // group 2: current-row offset (bytes), weight sub-blocks, taps per hand-off
+		uint32_t convC16, one116, one216, oneC16;              // group 3: 16-byte-unit offsets: convC inside sub-block 0, 1x1 parts inside the last one
+		uint32_t tapStride16, N1, ent16, flags;                // group 4: ent16 inside sub-block 0
+		uint32_t gOff[3]; uint32_t und16;                      // group 5: float offset of each weight sub-block; undelayed tap inside sub-block 0
+		uint32_t gBytes[3]; uint32_t tap0Base16;               // group 6: bytes of each sub-block; first delayed tap of group 0 inside sub-block 0
 		uint32_t tapOff[kHMaxTaps];                            // byte offset (inside a plane) of frame 0's row of delayed tap j
 		HJob job[kHMaxJobs];
 	};

@@ -96,6 +96,17 @@ namespace nab200
 			static __device__ __forceinline__ uint32_t xr(const Ctx& cx) { return cx.r1; }
 			static __device__ __forceinline__ uint32_t hd(const Ctx& cx) { return cx.r1 + 8u; }
 		};
+		//   ROLE 2: single array (A2), 8 channels, 16 head columns (one per head-conv tap, see the output stage):
+		//           taps r0 + 8 j (j < 4), r1 + 8 (j - 4) (j = 4, 5) | T2 r1 + 16 | D r1 + 24 | XR r2 | HD r2 + 8
+		template <> struct Map<2>
+		{
+			static constexpr int C = 8, HN = 16, N1 = 24;
+			static __device__ __forceinline__ uint32_t tap(const Ctx& cx, int j) { return j < 4 ? cx.r0 + 8u * (uint32_t)j : cx.r1 + 8u * (uint32_t)(j - 4); }
+			static __device__ __forceinline__ uint32_t t2(const Ctx& cx) { return cx.r1 + 16u; }
+			static __device__ __forceinline__ uint32_t d(const Ctx& cx) { return cx.r1 + 24u; }
+			static __device__ __forceinline__ uint32_t xr(const Ctx& cx) { return cx.r2; }
+			static __device__ __forceinline__ uint32_t hd(const Ctx& cx) { return cx.r2 + 8u; }
+		};
 		__device__ __forceinline__ uint32_t konst(const Ctx& cx) { return cx.r2 + 24u; }
 
 		// ---- hand-offs -------------------------------------------------------------------------------------------
@@ -125,13 +136,14 @@ namespace nab200
 			nbar_arrive<ID, kThreads>();
 		}
 
-		// one lane: bulk copy of layer b's weight block into buffer (slot & 1)
-		__device__ __forceinline__ void issue_weights(const Ctx& cx, int b, uint32_t slot)
+		// one lane: bulk copy of sub-block g of layer b's weights into buffer (slot & 1)
+		__device__ __forceinline__ void issue_weights(const Ctx& cx, int b, int g, uint32_t slot)
 		{
-			const uint4 g2 = lds128(cx.tab + (uint32_t)b * (uint32_t)sizeof(HLayer) + 32);
+			const uint32_t la = cx.tab + (uint32_t)b * (uint32_t)sizeof(HLayer);
+			const uint32_t off = lds32(la + 80u + 4u * (uint32_t)g), bytes = lds32(la + 96u + 4u * (uint32_t)g);
 			const uint32_t bar = cx.barW0 + 8u * (slot & 1u);
-			mbar_expect_tx(bar, g2.z);
-			bulk_g2s(cx.wbuf + (slot & 1u) * cx.wbufStride, cx.Wg + g2.y, g2.z, bar);
+			mbar_expect_tx(bar, bytes);
+			bulk_g2s(cx.wbuf + (slot & 1u) * cx.wbufStride, cx.Wg + off, bytes, bar);
 		}
 
 		// Every stager thread: my rows of the history window(s) of layer l of stream s, HBM ring -> shared memory, with
@@ -174,7 +186,7 @@ namespace nab200
 				hd = cx.hdb + (cx.cur ^ 1) * kHdbHalf;
 				if (s >= cx.S) { cp_async_commit(); return; }
 			}
-			if (l < a1First) prefetch_windows<4>(cx, l, s, hd);
+			if (l < a1First) prefetch_windows<4>(cx, l, s, hd);   // a1First = 0 for a single 8-channel array
 			else prefetch_windows<2>(cx, l, s, hd);
 		}
 
@@ -207,6 +219,15 @@ namespace nab200
 			asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(__uint_as_float(q0)));
 			asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(__uint_as_float(q1)));
 			unpack2(mul2(mul2(pack2(x0, x1), p), pack2f(r0, r1)), y0, y1);
+		}
+
+		// LeakyReLU(0.01) (Activation.h:110-118) for two values: max(x, 0.01 x)
+		__device__ __forceinline__ void leaky2(uint32_t x0, uint32_t x1, uint32_t& y0, uint32_t& y1)
+		{
+			uint32_t s0, s1;
+			unpack2(mul2(pack2(x0, x1), pack2f(0.01f, 0.01f)), s0, s1);
+			y0 = __float_as_uint(fmaxf(__uint_as_float(x0), __uint_as_float(s0)));
+			y1 = __float_as_uint(fmaxf(__uint_as_float(x1), __uint_as_float(s1)));
 		}
 
 		// ---- stager warps: one layer array of the CTA's stream ------------------------------------------------------
@@ -294,7 +315,11 @@ namespace nab200
 					uint32_t dv[C], z[C];
 					tmem_ld<C>(lane + MP::d(cx), dv);
 #pragma unroll
-					for (int c = 0; c < C; c += 2) fast_tanh2(dv[c], dv[c + 1], z[c], z[c + 1]);
+					for (int c = 0; c < C; c += 2)
+					{
+						if constexpr (ROLE == 2) leaky2(dv[c], dv[c + 1], z[c], z[c + 1]);
+						else fast_tanh2(dv[c], dv[c + 1], z[c], z[c + 1]);
+					}
 					pack_pairs<C>(z, dv);
 					tmem_st<C>(lane + MP::tap(cx, 0), dv);
 				}
@@ -333,36 +358,50 @@ namespace nab200
 				const uint32_t la = cx.tab + (uint32_t)l * (uint32_t)sizeof(HLayer);
 				const int numTaps = (int)lds32(la);
 				const uint4 g2 = lds128(la + 32), g3 = lds128(la + 48), g4 = lds128(la + 64);
-				const int groupTaps = (int)g2.w;
+				const int numGroups = (int)g2.y, groupTaps = (int)g2.w;
 				const uint32_t tapStride16 = g4.x;
-				// this layer's weight block (the first layer of an array was awaited by the entry / transition code)
-				if (li > 0) issuer_wait(cx, cx.barW0 + 8u * (cx.wq & 1u), (cx.wq >> 1) & 1u);
-				// the other buffer held the previous layer's block, whose MMAs are complete: request the next block
-				if (cx.el) issue_weights(cx, (l + 1 < cx.numLayers) ? l + 1 : 0, cx.wq + 1);
-				__syncwarp();
-				const uint32_t wb16 = (cx.wbuf + (cx.wq & 1u) * cx.wbufStride) >> 4;
+				const uint32_t und16 = lds32(la + 92u), tap0Base16 = lds32(la + 108u);
+				uint32_t wb16 = 0;
 
 				// ---- dilated conv + mix-in + bias (WaveNet.h:250-289,471-476): undelayed tap, constant operand, delayed taps ----
-				issuer_sync<kBarT2>();
-				if (cx.el)
+				// one weight sub-block per tap group, through the two buffers in turn
+#pragma unroll 1
+				for (int g = 0; g < numGroups; g++)
 				{
-					mma_pairs<C, 0>(MP::d(cx), MP::t2(cx), wb16 + (uint32_t)numTaps * tapStride16, C);   // overwrites the accumulator
-					mma_f16_ts<1>(MP::d(cx), konst(cx), desc_at(wb16 + g3.x, C), idesc_f16(C));
-				}
-				__syncwarp();
-				for (int j0 = 0; j0 < numTaps; j0 += groupTaps)
-				{
+					// this sub-block (the first one of an array was awaited by the entry / transition code)
+					if (li > 0 || g > 0) issuer_wait(cx, cx.barW0 + 8u * (cx.wq & 1u), (cx.wq >> 1) & 1u);
+					// the other buffer held the previous sub-block, whose MMAs are complete: request the next one
+					if (cx.el)
+					{
+						if (g + 1 < numGroups) issue_weights(cx, l, g + 1, cx.wq + 1);
+						else issue_weights(cx, (l + 1 < cx.numLayers) ? l + 1 : 0, 0, cx.wq + 1);
+					}
+					__syncwarp();
+					wb16 = (cx.wbuf + (cx.wq & 1u) * cx.wbufStride) >> 4;
+					if (g == 0)
+					{
+						issuer_sync<kBarT2>();
+						if (cx.el)
+						{
+							mma_pairs<C, 0>(MP::d(cx), MP::t2(cx), wb16 + und16, C);   // overwrites the accumulator
+							mma_f16_ts<1>(MP::d(cx), konst(cx), desc_at(wb16 + g3.x, C), idesc_f16(C));
+						}
+						__syncwarp();
+					}
+					const int j0 = g * groupTaps;
 					const int jn = (j0 + groupTaps < numTaps) ? j0 + groupTaps : numTaps;
+					const uint32_t tb16 = wb16 + (g == 0 ? tap0Base16 : 0u);
 					issuer_sync<kBarTaps>();
 					if (cx.el)
 					{
-						for (int j = j0; j < jn; j++) mma_pairs<C, 1>(MP::d(cx), MP::tap(cx, j - j0), wb16 + (uint32_t)j * tapStride16, C);
+						for (int j = j0; j < jn; j++) mma_pairs<C, 1>(MP::d(cx), MP::tap(cx, j - j0), tb16 + (uint32_t)(j - j0) * tapStride16, C);
 						mma_commit(cx.barD);
 					}
 					__syncwarp();
 					if (jn < numTaps) issuer_release<kBarGReady>(cx, cx.barD, cx.dq & 1u);
 					else issuer_release<kBarDReady>(cx, cx.barD, cx.dq & 1u);
 					cx.dq++;
+					if (g + 1 < numGroups) cx.wq++;
 				}
 
 				// ---- 1x1 + bias + residual, head sum (WaveNet.h:482-491): XR | HD += [z] [W1x1 | Whead] ----
@@ -391,7 +430,14 @@ namespace nab200
 		}
 
 		constexpr int kNumBars = 4;
+		constexpr int kHeadTaps = 16;                           // A2 head conv kernel size (WaveNet.h:658-660, InternalModel.h:12-20)
+		constexpr int kHeadHistFloats = kHeadTaps * 16;         // per stream: [tap][16 frames] of per-tap head products (15 used)
+		constexpr int kHeadRows = kCur + kHeadTaps - 1;         // scratch rows per tap plane: 15 history + 128 current
+		constexpr uint32_t kHeadScratchOff = 640u * 16u + 2304u;   // inside the window buffer, clear of the first layer's windows (PackWaveNetH checks)
 
+		// ARCH 0: two arrays, (16, 8) channels, tanh, 1x1 heads (A1 Standard / Lite).  ARCH 1: one 8-channel array, LeakyReLU,
+		// 16-tap head conv (A2, WaveNet.h:632-661 with the InternalModel.h:12-20 shapes).
+		template <int ARCH>
 		__global__ void __maxnreg__(64)
 			wavenet_h_kernel(const __grid_constant__ WnModelDev M, const float* __restrict__ Wg, float* __restrict__ state, int* __restrict__ heads,
 				const float* in, float* out, long long inSS, long long inFS, long long outSS, long long outFS, int S, int n, int* __restrict__ err)
@@ -412,6 +458,7 @@ namespace nab200
 			cx.hdb = reinterpret_cast<int*>(tabPtr + (size_t)M.numLayers * sizeof(HLayer));
 			unsigned long long* bars = reinterpret_cast<unsigned long long*>(cx.hdb + 2 * kHdbHalf);
 			uint32_t* tmemSlot = reinterpret_cast<uint32_t*>(bars + kNumBars);
+			float* headHist = reinterpret_cast<float*>(tmemSlot + 4);   // ARCH 1: this stream's head history [tap][16]
 			cx.barW0 = smem_u32(&bars[0]);
 			cx.barD = smem_u32(&bars[2]);
 			cx.barX = smem_u32(&bars[3]);
@@ -426,7 +473,7 @@ namespace nab200
 			const int tid = threadIdx.x, warp = cx.warp;
 			const bool stager = warp < 4;
 			const int first0 = M.arrays[0].firstLayer, num0 = M.arrays[0].numLayers;
-			const int first1 = M.arrays[1].firstLayer, num1 = M.arrays[1].numLayers;
+			const int first1 = ARCH == 0 ? M.arrays[1].firstLayer : 0, num1 = ARCH == 0 ? M.arrays[1].numLayers : 0;
 
 			// per-layer plan: built on the host (PackWaveNetH), copied to shared memory
 			{
@@ -470,8 +517,8 @@ namespace nab200
 			{
 				// =================================== issuer warp ===================================
 				const uint32_t ent0 = lds128(cx.tab + (uint32_t)first0 * (uint32_t)sizeof(HLayer) + 64).z;
-				const uint32_t ent1 = lds128(cx.tab + (uint32_t)first1 * (uint32_t)sizeof(HLayer) + 64).z;
-				if (cx.el) issue_weights(cx, 0, 0);
+				const uint32_t ent1 = ARCH == 0 ? lds128(cx.tab + (uint32_t)first1 * (uint32_t)sizeof(HLayer) + 64).z : 0u;
+				if (cx.el) issue_weights(cx, 0, 0, 0);
 				for (int s = s0; s < S; s += gridDim.x)
 				{
 					// ---- entry: [XR | HD] = constant operand x [rechannel 1 -> C0 | head bias] (WaveNet.h:637) ----
@@ -480,33 +527,37 @@ namespace nab200
 					if (cx.el)
 					{
 						const uint32_t wb16 = (cx.wbuf + (cx.wq & 1u) * cx.wbufStride) >> 4;
-						mma_f16_ts<0>(Map<0>::xr(cx), konst(cx), desc_at(wb16 + ent0, 24), idesc_f16(24));
+						mma_f16_ts<0>(Map<ARCH == 0 ? 0 : 2>::xr(cx), konst(cx), desc_at(wb16 + ent0, 24), idesc_f16(24));
 						mma_commit(cx.barX);
 					}
 					__syncwarp();
 					issuer_release<kBarXReady>(cx, cx.barX, cx.xq & 1u);
 					cx.xq++;
-					issue_array<0>(cx, first0, num0);
-
-					// ---- array transition (WaveNet.h:785-789): [XR1 | HD1] = rechannel C0 -> C1 of the array output | head carry ----
-					issuer_wait(cx, cx.barW0 + 8u * (cx.wq & 1u), (cx.wq >> 1) & 1u);
-					issuer_sync<kBarE>();
-					if (cx.el)
+					if constexpr (ARCH == 0)
 					{
-						const uint32_t wb16 = (cx.wbuf + (cx.wq & 1u) * cx.wbufStride) >> 4;
-						const uint32_t acc = Map<1>::xr(cx), e = wb16 + ent1, id = idesc_f16(16);
-						mma_f16_ts<0>(acc, cx.r1 + 16u, desc_at(e, 16), id);          // [Re1 | 0] x h1 of the array output
-						mma_f16_ts<1>(acc, cx.r1 + 24u, desc_at(e, 16), id);          // ... x h2
-						mma_f16_ts<1>(acc, cx.r1 + 16u, desc_at(e + 32u, 16), id);    // [Re2 | 0] x h1
-						mma_f16_ts<1>(acc, cx.r0, desc_at(e + 64u, 16), id);          // [0 | Wc1 ; Wc1] x [h1 | h2] of the head output
-						mma_f16_ts<1>(acc, cx.r0, desc_at(e + 96u, 16), id);          // [0 | Wc2 ; 0]
-						mma_f16_ts<1>(acc, konst(cx), desc_at(e + 128u, 16), id);     // [0 | head bias]
-						mma_commit(cx.barX);
+						issue_array<0>(cx, first0, num0);
+
+						// ---- array transition (WaveNet.h:785-789): [XR1 | HD1] = rechannel C0 -> C1 of the array output | head carry ----
+						issuer_wait(cx, cx.barW0 + 8u * (cx.wq & 1u), (cx.wq >> 1) & 1u);
+						issuer_sync<kBarE>();
+						if (cx.el)
+						{
+							const uint32_t wb16 = (cx.wbuf + (cx.wq & 1u) * cx.wbufStride) >> 4;
+							const uint32_t acc = Map<1>::xr(cx), e = wb16 + ent1, id = idesc_f16(16);
+							mma_f16_ts<0>(acc, cx.r1 + 16u, desc_at(e, 16), id);          // [Re1 | 0] x h1 of the array output
+							mma_f16_ts<1>(acc, cx.r1 + 24u, desc_at(e, 16), id);          // ... x h2
+							mma_f16_ts<1>(acc, cx.r1 + 16u, desc_at(e + 32u, 16), id);    // [Re2 | 0] x h1
+							mma_f16_ts<1>(acc, cx.r0, desc_at(e + 64u, 16), id);          // [0 | Wc1 ; Wc1] x [h1 | h2] of the head output
+							mma_f16_ts<1>(acc, cx.r0, desc_at(e + 96u, 16), id);          // [0 | Wc2 ; 0]
+							mma_f16_ts<1>(acc, konst(cx), desc_at(e + 128u, 16), id);     // [0 | head bias]
+							mma_commit(cx.barX);
+						}
+						__syncwarp();
+						issuer_release<kBarXReady>(cx, cx.barX, cx.xq & 1u);
+						cx.xq++;
+						issue_array<1>(cx, first1, num1);
 					}
-					__syncwarp();
-					issuer_release<kBarXReady>(cx, cx.barX, cx.xq & 1u);
-					cx.xq++;
-					issue_array<1>(cx, first1, num1);
+					else issue_array<2>(cx, first0, num0);
 					cx.cur ^= 1;
 				}
 				// drain the weight prefetch that ran ahead of the last layer
@@ -516,9 +567,10 @@ namespace nab200
 			{
 				// =================================== stager warps ===================================
 				const uint32_t lane = (uint32_t)(warp * 32) << 16;
+				constexpr int CG0 = ARCH == 0 ? 4 : 2;
 				float cond = 0.0f;
 				if (tid < n && s0 < S) cond = in[(long long)s0 * inSS + (long long)tid * inFS];
-				if (s0 < S) prefetch_windows<4>(cx, 0, s0, cx.hdb);
+				if (s0 < S) prefetch_windows<CG0>(cx, 0, s0, cx.hdb);
 				for (int s = s0; s < S; s += gridDim.x)
 				{
 					const int sn = s + gridDim.x;
@@ -537,6 +589,13 @@ namespace nab200
 						}
 						if (tid < n) condNext = in[(long long)sn * inSS + (long long)tid * inFS];
 					}
+					float* const hist = state + (size_t)s * M.stateStride + M.arrays[0].headRingOff;
+					if constexpr (ARCH == 1)
+					{
+						// this stream's head history -> shared memory, off the chain (its own cp.async group, awaited in the first layer)
+						if (tid < kHeadHistFloats / 4) cp_async16(smem_u32(headHist) + (uint32_t)tid * 16u, hist + tid * 4);
+						cp_async_commit();
+					}
 					// ---- entry: constant operand, 16 halves [c1, c2, c1, 1, 1, 1, 0 ...] ----
 					{
 						uint32_t c12, dummy;
@@ -549,29 +608,68 @@ namespace nab200
 						tmem_st<8>(lane + konst(cx), cv);
 					}
 					stager_arrive<kBarE>();
-					stage_array<0>(cx, first0, num0, s, first1);
-
-					// ---- array transition: the array output and its head output as packed pairs ----
-					stager_wait<kBarXReady>();
+					if constexpr (ARCH == 0)
 					{
-						uint32_t x[16], p[16];
-						tmem_ld<16>(lane + Map<0>::xr(cx), x);
-						pack_pairs<16>(x, p);
-						tmem_st<16>(lane + cx.r1 + 16u, p);
-						uint32_t h[8], hp[8];
-						tmem_ld<8>(lane + Map<0>::hd(cx), h);
-						pack_pairs<8>(h, hp);
-						tmem_st<8>(lane + cx.r0, hp);
+						stage_array<0>(cx, first0, num0, s, first1);
+
+						// ---- array transition: the array output and its head output as packed pairs ----
+						stager_wait<kBarXReady>();
+						{
+							uint32_t x[16], p[16];
+							tmem_ld<16>(lane + Map<0>::xr(cx), x);
+							pack_pairs<16>(x, p);
+							tmem_st<16>(lane + cx.r1 + 16u, p);
+							uint32_t h[8], hp[8];
+							tmem_ld<8>(lane + Map<0>::hd(cx), h);
+							pack_pairs<8>(h, hp);
+							tmem_st<8>(lane + cx.r0, hp);
+						}
+						stager_arrive<kBarE>();
+						stage_array<1>(cx, first1, num1, s, first1);
+
+						// ---- output (WaveNet.h:793-798) ----
+						stager_wait<kBarXReady>();
+						{
+							uint32_t h[8];
+							tmem_ld<8>(lane + Map<1>::hd(cx), h);
+							if (tid < n) out[(long long)s * outSS + (long long)tid * outFS] = M.headScale * __uint_as_float(h[0]);
+						}
 					}
-					stager_arrive<kBarE>();
-					stage_array<1>(cx, first1, num1, s, first1);
-
-					// ---- output (WaveNet.h:793-798) ----
-					stager_wait<kBarXReady>();
+					else
 					{
-						uint32_t h[8];
-						tmem_ld<8>(lane + Map<1>::hd(cx), h);
-						if (tid < n) out[(long long)s * outSS + (long long)tid * outFS] = M.headScale * __uint_as_float(h[0]);
+						stage_array<2>(cx, first0, num0, s, 0);
+
+						// ---- output: 16-tap head conv of the summed head (WaveNet.h:658-660, 793-798) ----
+						// HD column k holds G_k[t] = Wh_k . headsum[t] (+ the head bias in column 15); out[t] = sum_k G_k[t - 15 + k].
+						// The shift across frames goes through shared memory, one conflict-free plane per tap: rows 0..14 = the last 15
+						// frames of the previous call (per-stream state), rows 15.. = this call; two halves of 8 taps share the scratch.
+						stager_wait<kBarXReady>();
+						uint32_t g[16];
+						tmem_ld<16>(lane + Map<2>::hd(cx), g);
+						float acc = 0.0f;
+						const uint32_t sc = cx.win + kHeadScratchOff;
+#pragma unroll
+						for (int half = 0; half < 2; half++)
+						{
+							nbar_sync<kBarMix, kStagers>();
+#pragma unroll
+							for (int kk = 0; kk < 8; kk++)
+							{
+								const uint32_t plane = sc + (uint32_t)(kk * kHeadRows) * 4u;
+								asm volatile("st.shared.b32 [%0], %1;" ::"r"(plane + (uint32_t)(15 + tid) * 4u), "r"(g[8 * half + kk]) : "memory");
+								if (tid < 15) asm volatile("st.shared.b32 [%0], %1;" ::"r"(plane + (uint32_t)tid * 4u), "r"(__float_as_uint(headHist[(8 * half + kk) * 16 + tid])) : "memory");
+							}
+							nbar_sync<kBarMix, kStagers>();
+#pragma unroll
+							for (int kk = 0; kk < 8; kk++)
+							{
+								const uint32_t plane = sc + (uint32_t)(kk * kHeadRows) * 4u;
+								acc += __uint_as_float(lds32(plane + (uint32_t)(tid + 8 * half + kk) * 4u));
+								// the last 15 frames of [history | this call] become the next call's history
+								if (tid < 15) hist[(8 * half + kk) * 16 + tid] = __uint_as_float(lds32(plane + (uint32_t)(n + tid) * 4u));
+							}
+						}
+						if (tid < n) out[(long long)s * outSS + (long long)tid * outFS] = M.headScale * acc;
 					}
 					if (tid < M.numRings) heads[(size_t)s * M.numRings + tid] = cx.hdb[cx.cur * kHdbHalf + 36 + tid];
 					cx.cur ^= 1;
@@ -594,21 +692,19 @@ namespace nab200
 
 	bool wavenet_h_variant_supported(int C0, int C1, int act)
 	{
-		return C0 == 16 && C1 == 8 && act == 0;
+		return (C0 == 16 && C1 == 8 && act == 0) || (C0 == 8 && C1 == 0 && act == 1);
 	}
 
 	size_t wavenet_h_smem_bytes(const WnModelDev& M)
 	{
 		return (size_t)(M.arrays[0].C / 4) * M.winRows * 16 + (size_t)2 * M.maxBlockBytes + (size_t)M.numLayers * sizeof(HLayer) +
-			2 * hk::kHdbHalf * 4 + hk::kNumBars * 8 + 16;
+			2 * hk::kHdbHalf * 4 + hk::kNumBars * 8 + 16 + hk::kHeadHistFloats * 4;
 	}
 
-	cudaError_t wavenet_h_launch(const WnModelDev& M, const WnLaunch& a)
+	template <int ARCH>
+	static cudaError_t h_launch_arch(const WnModelDev& M, const WnLaunch& a)
 	{
-		if (M.tc != 3 || !wavenet_h_variant_supported(M.arrays[0].C, M.numArrays > 1 ? M.arrays[1].C : 0, M.arrays[0].act)) return cudaErrorNotSupported;
-		if (a.n > hk::kCur || a.n < 1) return cudaErrorInvalidValue;
-		if (!a.err) return cudaErrorInvalidValue;
-		auto kfn = hk::wavenet_h_kernel;
+		auto kfn = hk::wavenet_h_kernel<ARCH>;
 		const size_t smem = wavenet_h_smem_bytes(M);
 		cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 		if (e != cudaSuccess) return e;
@@ -616,17 +712,24 @@ namespace nab200
 		// keeps more L1 and fits only four - ncu launch__occupancy_limit_shared_mem)
 		e = cudaFuncSetAttribute(kfn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 		if (e != cudaSuccess) return e;
-		if (getenv("NAB200_H_DEBUG"))
-		{
-			int occ = 0;
-			cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kfn, hk::kThreads, smem);
-			fprintf(stderr, "wavenet_h_kernel: %zu bytes of shared memory per CTA, %d CTAs per SM fit\n", smem, occ);
-		}
-		int ctasPerSM = a.ctasPerSM > 0 ? a.ctasPerSM : 5;
+		// streams in flight per SM: 5 by TMEM (96 columns each) and registers (64 x 6 allocated warps), fewer when a model's
+		// weight blocks make the CTA's shared memory larger than a fifth of the SM's
+		int fit = (int)((size_t)(228 * 1024) / (smem + 1024));
+		if (fit > 5) fit = 5;
+		if (fit < 1) fit = 1;
+		int ctasPerSM = a.ctasPerSM > 0 ? a.ctasPerSM : fit;
 		int grid = a.numSMs * ctasPerSM;
 		if (grid > a.S) grid = a.S;
 		if (grid < 1) grid = 1;
 		kfn<<<grid, hk::kThreads, smem, a.stream>>>(M, a.weights, a.state, a.heads, a.in, a.out, a.inSS, a.inFS, a.outSS, a.outFS, a.S, a.n, a.err);
 		return cudaGetLastError();
+	}
+
+	cudaError_t wavenet_h_launch(const WnModelDev& M, const WnLaunch& a)
+	{
+		if (M.tc != 3 || !wavenet_h_variant_supported(M.arrays[0].C, M.numArrays > 1 ? M.arrays[1].C : 0, M.arrays[0].act)) return cudaErrorNotSupported;
+		if (a.n > hk::kCur || a.n < 1) return cudaErrorInvalidValue;
+		if (!a.err) return cudaErrorInvalidValue;
+		return M.numArrays > 1 ? h_launch_arch<0>(M, a) : h_launch_arch<1>(M, a);
 	}
 }

@@ -38,6 +38,7 @@ def batch(name, streams, frames, calls):
 
 
 def timing(name, tc, ctas, S=4096, n=128, steps=50):
+    if "a2_" in name: n = 256
     import torch
     na.set_option("use_tc", tc); na.set_option("h_ctas", ctas)
     g = load_golden(golden_files(name)[0])
@@ -68,6 +69,15 @@ if __name__ == "__main__":
         single("ref_BossWN_standard"); single("syn_a1_standard.", 37); single("syn_a1_lite", 64); single("syn_a1_standard_sr96000", 128)
         single("ref_namcore_wavenet_a1_standard", 1 + 127)
         batch("ref_BossWN_standard", 900, 128, 40)
+    if what in ("all", "parity", "a2"):
+        na.set_option("use_tc", 3)
+        single("syn_a2_full", 256); single("ref_BossWN_a2.", 128); single("ref_BossWN_a2_q0", 100); single("syn_a2_lite", 7)
+        batch("syn_a2_full", 700, 256, 12)
+    if what in ("all", "a2"):
+        for tc, ctas in ((0, 0), (3, 0), (3, 3)):
+            timing("syn_a2_full", tc, ctas)
+        for tc, ctas in ((0, 0), (3, 0)):
+            timing("syn_a2_lite", tc, ctas)
     if what == "timing1":
         timing("syn_a1_standard.", 3, int(os.environ.get("NAB200_H_CTAS", "0")), steps=8)
     if what in ("all", "timing"):
