@@ -178,7 +178,17 @@ inline namespace b200
 		virtual void* GetCudaStream() { return nullptr; }
 		virtual int GetDevice() { return -1; }
 		virtual size_t GetStateBytesPerStream() { return 0; }
+		// how many of the library's own GPU kernels this model has launched so far (a measurement aid: bench.py reports it)
+		virtual unsigned long long GetKernelLaunchCount() { return 0; }
 		virtual std::string GetLastError() { return ""; }
+
+		// ---- multi-GPU load (no counterpart in the reference: it has one stream per object and no GPUs) -----------------
+		// One process per GPU: every rank builds the model (only the root needs doPrewarm = true), then all ranks call this
+		// with their NCCL communicator (an ncclComm_t passed as void*) and the library does ONE ncclBroadcast per resident
+		// engine of [packed weights | prewarmed state template] from `root`, and refills this rank's stream slots from it.
+		// Returns the bytes broadcast, -1 on failure.  After it, every rank starts every stream from the root's state and the
+		// stream batch shards with no further collective: rank r owns its own contiguous block of stream slots.
+		virtual long long BroadcastModel(void* ncclComm, int root) { (void)ncclComm; (void)root; return -1; }
 	};
 
 	class NEURALAUDIO_B200_API NeuralModelLoader
@@ -188,6 +198,11 @@ inline namespace b200
 		// for malformed files (wrong weight count, bad JSON), like the reference (WaveNet.h:704-709).
 		NeuralModel* CreateFromFile(const std::filesystem::path& modelPath, bool doPrewarm = true);
 		NeuralModel* CreateFromStream(std::basic_istream<char>& stream, const std::filesystem::path& extension, bool doPrewarm = true);
+		// One process, several GPUs: the model is built on every listed CUDA device, prewarmed on the first, and ONE grouped
+		// ncclBroadcast carries [packed weights | prewarmed state template] to the others.  The returned model owns the stream
+		// batch as contiguous shards: ProcessBatch(host buffers, S streams) sends block r of S / numDevices streams to device r
+		// (page-locked buffers: the shards run concurrently; no per-step collective).  SetDefaultNumStreams is the TOTAL.
+		NeuralModel* CreateShardedFromFile(const std::filesystem::path& modelPath, const int* cudaDevices, int numDevices, bool doPrewarm = true);
 		NeuralModel* CreateFromJsonText(const std::string& jsonText, const std::filesystem::path& extension, bool doPrewarm = true);
 #ifdef NEURALAUDIO_B200_HAVE_NLOHMANN
 		NeuralModel* CreateFromJson(nlohmann::json& modelJson, const std::filesystem::path& extension, bool doPrewarm = true)

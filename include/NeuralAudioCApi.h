@@ -84,6 +84,8 @@ NA_EXTERN int NA_GetMetadata(NeuralModel* model, const char* key, char* out, int
 NA_EXTERN int NA_SetNumStreams(NeuralModel* model, size_t numStreams);     /* (re)allocates and prewarms all slots */
 NA_EXTERN size_t NA_GetNumStreams(NeuralModel* model);
 NA_EXTERN size_t NA_GetStateBytesPerStream(NeuralModel* model);
+/* GPU kernels launched by this model so far (all sub-models of a container); a measurement aid */
+NA_EXTERN unsigned long long NA_GetKernelLaunchCount(NeuralModel* model);
 NA_EXTERN int NA_GetDevice(NeuralModel* model);
 
 /* Advance slots [0, numStreams) by numFrames.  layout 0: buffer[s * numFrames + f]; layout 1: buffer[f * numStreams + s].
@@ -102,6 +104,28 @@ NA_EXTERN void* NA_GetCudaStream(NeuralModel* model);    /* the cudaStream_t Pro
  * by the prewarmed one-stream state template) is broadcast in place -- one NCCL broadcast -- and each rank refills its
  * stream slots from it with NA_Prewarm.  The blob is one contiguous device allocation. */
 NA_EXTERN int NA_GetDeviceBlob(NeuralModel* model, void** devicePtr, size_t* bytes);
+
+/* ---- multi-GPU load inside the library (NCCL is loaded with dlopen; nothing here is needed on one GPU) ----------------------
+ * One process per GPU (torchrun / MPI style):
+ *   root:       NA_NcclGetUniqueId(id)  -> ship the 128 bytes to the other ranks by any means
+ *   every rank: comm = NA_NcclCommInitRank(nranks, rank, id, cudaDevice);
+ *               model = NA_CreateModelFromFileEx(loader, path, doPrewarm = (rank == root));
+ *               NA_BroadcastModel(model, comm, root);      ONE ncclBroadcast per resident engine of [packed weights | prewarmed
+ *                                                          state template]; this rank's stream slots are refilled from it
+ *   then each rank advances its own contiguous block of streams with NA_ProcessBatch: no per-step collective.
+ * NA_BroadcastModelOnComm takes a caller-owned ncclComm_t (as void*) instead.  Both return the bytes broadcast, -1 on failure. */
+NA_EXTERN int NA_NcclGetUniqueId(void* out128);
+NA_EXTERN void* NA_NcclCommInitRank(int numRanks, int rank, const void* id128, int cudaDevice);
+NA_EXTERN int NA_NcclCommCount(void* comm);
+NA_EXTERN void NA_NcclCommDestroy(void* comm);
+NA_EXTERN long long NA_BroadcastModel(NeuralModel* model, void* comm, int root);
+NA_EXTERN long long NA_BroadcastModelOnComm(NeuralModel* model, void* ncclComm, int root);
+/* One process, several GPUs: the model on every listed device, ONE grouped ncclBroadcast from the first, the stream batch cut
+ * into contiguous shards; NA_ProcessBatch(host buffers, S streams) fans block r out to device r.  NA_SetDefaultNumStreams
+ * gives the TOTAL.  NA_GetNumShards / NA_GetBroadcastBytes describe the result (1 / 0 for an ordinary model). */
+NA_EXTERN NeuralModel* NA_CreateModelSharded(NeuralModelLoader* loader, const wchar_t* modelPath, const int* cudaDevices, int numDevices, int doPrewarm);
+NA_EXTERN int NA_GetNumShards(NeuralModel* model);
+NA_EXTERN long long NA_GetBroadcastBytes(NeuralModel* model);
 
 /* test / tooling hooks */
 NA_EXTERN int NA_CopyStreamState(NeuralModel* model, size_t stream, float* hostOut, size_t capacityFloats);   /* returns floats written */

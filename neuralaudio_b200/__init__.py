@@ -99,6 +99,7 @@ def load_library():
         "NA_SetNumStreams": (ci, [vp, sz]),
         "NA_GetNumStreams": (sz, [vp]),
         "NA_GetStateBytesPerStream": (sz, [vp]),
+        "NA_GetKernelLaunchCount": (ctypes.c_ulonglong, [vp]),
         "NA_GetDevice": (ci, [vp]),
         "NA_ProcessBatch": (ci, [vp, vp, vp, sz, sz, ci]),
         "NA_ProcessBatchAsync": (ci, [vp, vp, vp, sz, sz, ci]),
@@ -109,6 +110,16 @@ def load_library():
         "NA_CopyStreamState": (ci, [vp, sz, _f32p, sz]),
         "NA_DescribeModelFile": (ci, [ctypes.c_wchar_p, ci, ctypes.c_char_p, ci]),
         "NA_SetOption": (ci, [ctypes.c_char_p, ci]),
+        # multi-GPU load inside the library (NCCL through dlopen)
+        "NA_NcclGetUniqueId": (ci, [ctypes.c_char_p]),
+        "NA_NcclCommInitRank": (vp, [ci, ci, ctypes.c_char_p, ci]),
+        "NA_NcclCommCount": (ci, [vp]),
+        "NA_NcclCommDestroy": (None, [vp]),
+        "NA_BroadcastModel": (ctypes.c_longlong, [vp, vp, ci]),
+        "NA_BroadcastModelOnComm": (ctypes.c_longlong, [vp, vp, ci]),
+        "NA_CreateModelSharded": (vp, [vp, ctypes.c_wchar_p, ctypes.POINTER(ci), ci, ci]),
+        "NA_GetNumShards": (ci, [vp]),
+        "NA_GetBroadcastBytes": (ctypes.c_longlong, [vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)   # AttributeError here == a declared symbol is missing from the build
@@ -126,6 +137,40 @@ def _last_error(L):
 
 def device_count():
     return load_library().NA_GetDeviceCount()
+
+
+def nccl_get_unique_id():
+    """128 bytes from ncclGetUniqueId (root rank); ship them to the other ranks by any means, then NcclComm(...) everywhere."""
+    L = load_library()
+    buf = ctypes.create_string_buffer(128)
+    if L.NA_NcclGetUniqueId(buf) != 0:
+        raise NeuralAudioError(_last_error(L) or "NCCL unavailable")
+    return buf.raw
+
+
+class NcclComm:
+    """One rank's NCCL communicator owned by the library (ncclCommInitRank), for NeuralModel.BroadcastModel."""
+
+    def __init__(self, nranks, rank, unique_id, device):
+        self._L = load_library()
+        if len(unique_id) != 128:
+            raise ValueError("unique_id must be the 128 bytes of nccl_get_unique_id()")
+        self._h = self._L.NA_NcclCommInitRank(int(nranks), int(rank), bytes(unique_id), int(device))
+        if not self._h:
+            raise NeuralAudioError(_last_error(self._L) or "ncclCommInitRank failed")
+        self.nranks = self._L.NA_NcclCommCount(self._h)
+        self.rank = int(rank)
+
+    def close(self):
+        if self._h:
+            self._L.NA_NcclCommDestroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def set_option(name, value):
@@ -205,6 +250,15 @@ class NeuralModelLoader:
 
     def CreateFromFile(self, path, doPrewarm=True):
         h = self._L.NA_CreateModelFromFileEx(self._h, os.path.abspath(path), 1 if doPrewarm else 0)
+        if not h:
+            raise NeuralAudioError(_last_error(self._L) or "model could not be loaded")
+        return NeuralModel(self._L, h)
+
+    def CreateShardedFromFile(self, path, devices, doPrewarm=True):
+        """One process, several GPUs: the model on every listed device, one grouped ncclBroadcast of [weights | prewarmed state]
+        from the first, the stream batch (SetDefaultNumStreams = the total) cut into contiguous shards."""
+        arr = (ctypes.c_int * len(devices))(*[int(d) for d in devices])
+        h = self._L.NA_CreateModelSharded(self._h, os.path.abspath(path), arr, len(devices), 1 if doPrewarm else 0)
         if not h:
             raise NeuralAudioError(_last_error(self._L) or "model could not be loaded")
         return NeuralModel(self._L, h)
@@ -302,6 +356,22 @@ class NeuralModel:
 
     def GetNumStreams(self):
         return self._L.NA_GetNumStreams(self._h)
+
+    def BroadcastModel(self, comm, root=0):
+        """ONE ncclBroadcast per resident engine of [packed weights | prewarmed state template] from `root`; returns the bytes."""
+        n = self._L.NA_BroadcastModel(self._h, comm._h, int(root))
+        if n < 0:
+            raise NeuralAudioError(_last_error(self._L) or "BroadcastModel failed")
+        return int(n)
+
+    def GetNumShards(self):
+        return int(self._L.NA_GetNumShards(self._h))
+
+    def GetBroadcastBytes(self):
+        return int(self._L.NA_GetBroadcastBytes(self._h))
+
+    def GetKernelLaunchCount(self):
+        return int(self._L.NA_GetKernelLaunchCount(self._h))
 
     def GetStateBytesPerStream(self):
         return self._L.NA_GetStateBytesPerStream(self._h)

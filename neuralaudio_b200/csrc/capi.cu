@@ -231,6 +231,93 @@ NeuralModel* NA_CreateModelFromFileEx(NeuralModelLoader* loader, const wchar_t* 
 	return guarded_create([&]() { return loader->loader->CreateFromFile(std::filesystem::path(modelPath), doPrewarm != 0); });
 }
 
+NeuralModel* NA_CreateModelSharded(NeuralModelLoader* loader, const wchar_t* modelPath, const int* cudaDevices, int numDevices, int doPrewarm)
+{
+	if (!loader || !modelPath || !cudaDevices || numDevices < 1) { nab200::SetLastError("null argument"); return nullptr; }
+	nab200::SetLastError("");
+	return guarded_create([&]() { return loader->loader->CreateShardedFromFile(std::filesystem::path(modelPath), cudaDevices, numDevices, doPrewarm != 0); });
+}
+
+int NA_GetNumShards(NeuralModel* model)
+{
+	auto* s = impl(model) ? dynamic_cast<NeuralAudio::B200ShardedModel*>(model->model) : nullptr;
+	return s ? s->NumShards() : (impl(model) ? 1 : 0);
+}
+
+long long NA_GetBroadcastBytes(NeuralModel* model)
+{
+	auto* s = impl(model) ? dynamic_cast<NeuralAudio::B200ShardedModel*>(model->model) : nullptr;
+	return s ? (long long)s->BroadcastBytes() : 0;
+}
+
+int NA_NcclGetUniqueId(void* out128)
+{
+	if (!out128) { nab200::SetLastError("null argument"); return -1; }
+	const nab200::NcclApi* nccl = nab200::GetNccl();
+	if (!nccl) return -1;
+	nab200::NcclUniqueId id;
+	if (!nab200::NcclOk(nccl->GetUniqueId(&id), "ncclGetUniqueId")) return -1;
+	memcpy(out128, id.internal, sizeof(id.internal));
+	return 0;
+}
+
+void* NA_NcclCommInitRank(int numRanks, int rank, const void* id128, int cudaDevice)
+{
+	if (!id128 || numRanks < 1 || rank < 0 || rank >= numRanks) { nab200::SetLastError("bad argument"); return nullptr; }
+	const nab200::NcclApi* nccl = nab200::GetNccl();
+	if (!nccl) return nullptr;
+	int prev = -1;
+	cudaGetDevice(&prev);
+	if (cudaDevice >= 0 && !nab200::CudaOk(cudaSetDevice(cudaDevice), "cudaSetDevice")) return nullptr;
+	nab200::NcclUniqueId id;
+	memcpy(id.internal, id128, sizeof(id.internal));
+	auto* c = new nab200::NcclComm;
+	c->device = cudaDevice; c->nranks = numRanks; c->rank = rank;
+	const bool ok = nab200::NcclOk(nccl->CommInitRank(&c->comm, numRanks, id, rank), "ncclCommInitRank");
+	if (prev >= 0 && prev != cudaDevice) cudaSetDevice(prev);
+	if (!ok) { delete c; return nullptr; }
+	return c;
+}
+
+int NA_NcclCommCount(void* comm)
+{
+	auto* c = static_cast<nab200::NcclComm*>(comm);
+	const nab200::NcclApi* nccl = c ? nab200::GetNccl() : nullptr;
+	int n = 0;
+	if (!nccl || !nab200::NcclOk(nccl->CommCount(c->comm, &n), "ncclCommCount")) return -1;
+	return n;
+}
+
+void NA_NcclCommDestroy(void* comm)
+{
+	auto* c = static_cast<nab200::NcclComm*>(comm);
+	if (!c) return;
+	const nab200::NcclApi* nccl = nab200::GetNccl();
+	if (nccl && c->comm) nccl->CommDestroy(c->comm);
+	delete c;
+}
+
+long long NA_BroadcastModelOnComm(NeuralModel* model, void* ncclComm, int root)
+{
+	if (!impl(model)) { nab200::SetLastError("null model"); return -1; }
+	try
+	{
+		return model->model->BroadcastModel(ncclComm, root);
+	}
+	catch (...)
+	{
+		nab200::SetLastError("exception in BroadcastModel");
+		return -1;
+	}
+}
+
+long long NA_BroadcastModel(NeuralModel* model, void* comm, int root)
+{
+	auto* c = static_cast<nab200::NcclComm*>(comm);
+	if (!c) { nab200::SetLastError("null communicator"); return -1; }
+	return NA_BroadcastModelOnComm(model, c->comm, root);
+}
+
 void NA_Prewarm(NeuralModel* model)
 {
 	if (impl(model)) model->model->Prewarm();
@@ -280,6 +367,11 @@ int NA_SetNumStreams(NeuralModel* model, size_t numStreams)
 size_t NA_GetNumStreams(NeuralModel* model)
 {
 	return impl(model) ? model->model->GetNumStreams() : 0;
+}
+
+unsigned long long NA_GetKernelLaunchCount(NeuralModel* model)
+{
+	return impl(model) ? model->model->GetKernelLaunchCount() : 0;
 }
 
 size_t NA_GetStateBytesPerStream(NeuralModel* model)

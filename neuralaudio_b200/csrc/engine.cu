@@ -336,6 +336,22 @@ namespace nab200
 		return CheckDeviceError();
 	}
 
+	bool StreamEngine::BroadcastBlob(NcclCommRaw comm, int root, size_t* bytesOut, bool sync)
+	{
+		const NcclApi* nccl = GetNccl();
+		if (!nccl) return false;
+		DeviceGuard guard(device);
+		if (!guard.ok) return false;
+		void* blob = nullptr;
+		size_t bytes = 0;
+		if (!GetBlob(&blob, &bytes) || !blob) { SetLastError("BroadcastModel: the model has no device blob"); return false; }
+		if (!NcclOk(nccl->Broadcast(blob, blob, bytes, kNcclUint8, root, comm, stream), "ncclBroadcast")) return false;
+		if (bytesOut) *bytesOut = bytes;
+		if (!sync) return true;
+		if (!CudaOk(cudaStreamSynchronize(stream), "cudaStreamSynchronize(broadcast)")) return false;
+		return ResetStreams();
+	}
+
 	bool StreamEngine::Synchronize()
 	{
 		if (!stream) return true;
@@ -505,6 +521,7 @@ namespace nab200
 			const cudaError_t lerr = packed.dev.tc == 3 ? wavenet_h_launch(packed.dev, a) : packed.dev.tc == 2 ? wavenet_ts_launch(packed.dev, a) : packed.dev.tc ? wavenet_tc_launch(packed.dev, a)
 				: useGeneric ? wavenet_generic_launch(packed.dev, a) : wavenet_launch(packed.dev, a);
 			if (!CudaOk(lerr, "wavenet kernel launch")) return false;
+			kernelLaunches += (packed.dev.tc == 2 && opt.tsSplit && dScratch) ? 2 : 1;
 			done += chunk;
 		}
 		return true;
@@ -625,7 +642,9 @@ namespace nab200
 		a.kernel = GetOptions().lstmKernel;
 		a.numSMs = numSMs;
 		a.stream = stream;
-		return CudaOk(lstm_launch(packed.dev, a), "lstm_fwd_kernel launch");
+		if (!CudaOk(lstm_launch(packed.dev, a), "lstm_fwd_kernel launch")) return false;
+		kernelLaunches++;
+		return true;
 	}
 
 	bool LstmEngine::CopyStreamState(size_t s, float* hostOut, size_t capFloats, size_t* written)

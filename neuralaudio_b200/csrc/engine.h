@@ -7,6 +7,7 @@
 #include <string>
 #include "model_desc.h"
 #include "na_kernels.h"
+#include "nccl_api.h"
 
 namespace nab200
 {
@@ -45,6 +46,10 @@ namespace nab200
 		virtual size_t StateBytesPerStream() const = 0;
 		virtual bool CopyStreamState(size_t stream, float* hostOut, size_t capFloats, size_t* written) = 0;
 		virtual bool GetBlob(void** devPtr, size_t* bytes) = 0;
+		// Multi-GPU load: ONE ncclBroadcast of this engine's [packed weights | prewarmed state template] from rank `root` of
+		// `comm` into every other rank's blob (in place), then every slot of this engine is refilled from the received template.
+		// The collective is queued on the engine's own stream; `sync` = false leaves the wait to the caller (grouped calls).
+		bool BroadcastBlob(NcclCommRaw comm, int root, size_t* bytesOut, bool sync = true);
 
 		// host or device pointers; layout 0 = [stream][frame], 1 = [frame][stream]
 		bool Process(const float* in, float* out, size_t numStreams, size_t numFrames, int layout);
@@ -57,6 +62,7 @@ namespace nab200
 		bool Synchronize();
 
 		size_t NumStreams() const { return numStreams; }
+		unsigned long long KernelLaunches() const { return kernelLaunches; }
 		int Device() const { return device; }
 		cudaStream_t Stream() const { return stream; }
 
@@ -71,6 +77,7 @@ namespace nab200
 		int* hErr = nullptr;
 		int* dErr = nullptr;
 
+		unsigned long long kernelLaunches = 0;   // kernels of this library launched on behalf of this engine
 		int device = -1;
 		int numSMs = 148;
 		cudaStream_t stream = nullptr;

@@ -103,6 +103,7 @@ inline namespace b200
 	void* B200EngineModel::GetCudaStream() { return engine ? (void*)engine->Stream() : nullptr; }
 	int B200EngineModel::GetDevice() { return engine ? engine->Device() : -1; }
 	size_t B200EngineModel::GetStateBytesPerStream() { return engine ? engine->StateBytesPerStream() : 0; }
+	unsigned long long B200EngineModel::GetKernelLaunchCount() { return engine ? engine->KernelLaunches() : 0; }
 
 	bool B200EngineModel::ResetStreams()
 	{
@@ -119,6 +120,28 @@ inline namespace b200
 	}
 
 	bool B200EngineModel::GetBlob(void** p, size_t* bytes) { return engine ? engine->GetBlob(p, bytes) : false; }
+	bool B200EngineModel::BroadcastQueue(nab200::NcclCommRaw comm, int root, size_t* bytes)
+	{
+		size_t b = 0;
+		if (!engine || !engine->BroadcastBlob(comm, root, &b, false)) { lastError = nab200::LastError(); return false; }
+		if (bytes) *bytes += b;
+		return true;
+	}
+	bool B200EngineModel::BroadcastFinish()
+	{
+		if (!engine || !engine->Synchronize() || !engine->ResetStreams() || !engine->Synchronize()) { lastError = nab200::LastError(); return false; }
+		SetHadInitialPrewarm();   // the received template IS the root's prewarmed state
+		return true;
+	}
+
+	long long B200ModelImpl::BroadcastModel(void* ncclComm, int root)
+	{
+		if (!ncclComm) { nab200::SetLastError("BroadcastModel: null communicator"); return -1; }
+		size_t bytes = 0;
+		if (!BroadcastQueue(static_cast<nab200::NcclCommRaw>(ncclComm), root, &bytes)) return -1;
+		if (!BroadcastFinish()) return -1;
+		return (long long)bytes;
+	}
 
 	// ---- A2 slimmable container (CompositeModel / ScalableCompositeModel, CompositeModel.h:10-214) --------------
 	B200CompositeModel::~B200CompositeModel()
@@ -241,6 +264,12 @@ inline namespace b200
 
 	void* B200CompositeModel::GetCudaStream() { auto* m = Current(); return m ? m->GetCudaStream() : nullptr; }
 	int B200CompositeModel::GetDevice() { auto* m = Current(); return m ? m->GetDevice() : -1; }
+	unsigned long long B200CompositeModel::GetKernelLaunchCount()
+	{
+		unsigned long long n = 0;
+		for (auto* m : models) n += m->GetKernelLaunchCount();
+		return n;
+	}
 	size_t B200CompositeModel::GetStateBytesPerStream() { auto* m = Current(); return m ? m->GetStateBytesPerStream() : 0; }
 	std::string B200CompositeModel::GetLastError() { auto* m = Current(); return m ? m->GetLastError() : lastError; }
 
@@ -261,6 +290,115 @@ inline namespace b200
 	{
 		auto* m = Current();
 		return m ? m->GetBlob(p, bytes) : false;
+	}
+	bool B200CompositeModel::BroadcastQueue(nab200::NcclCommRaw comm, int root, size_t* bytes)
+	{
+		// every resident sub-model (quality level) travels: one ncclBroadcast each, queued back to back
+		for (auto* m : models) if (!m->BroadcastQueue(comm, root, bytes)) return false;
+		return true;
+	}
+	bool B200CompositeModel::BroadcastFinish()
+	{
+		bool ok = true;
+		for (auto* m : models) ok = m->BroadcastFinish() && ok;
+		return ok;
+	}
+
+	// ---- sharded model: one host process, several GPUs ------------------------------------------------------------
+	B200ShardedModel::~B200ShardedModel()
+	{
+		for (auto* m : shards) delete m;
+		const nab200::NcclApi* nccl = comms.empty() ? nullptr : nab200::GetNccl();
+		if (nccl) for (auto c : comms) if (c) nccl->CommDestroy(c);
+	}
+
+	bool B200ShardedModel::SetNumStreams(size_t numStreams)
+	{
+		const size_t n = shards.size();
+		for (size_t r = 0; r < n; r++)
+		{
+			const size_t cnt = ShardBegin(numStreams, n, r + 1) - ShardBegin(numStreams, n, r);
+			if (!shards[r]->SetNumStreams(cnt > 0 ? cnt : 1)) { lastError = shards[r]->GetLastError(); return false; }
+		}
+		totalStreams = numStreams;
+		return true;
+	}
+
+	size_t B200ShardedModel::GetNumStreams() { return totalStreams; }
+
+	bool B200ShardedModel::ProcessBatchAsync(const float* input, float* output, size_t numStreams, size_t numFrames, EBatchLayout layout)
+	{
+		if (layout != StreamMajor)
+		{
+			nab200::SetLastError("sharded ProcessBatch: only the [stream][frame] layout shards into contiguous blocks");
+			return false;
+		}
+		if (numStreams > totalStreams) { nab200::SetLastError("ProcessBatch: numStreams exceeds the allocated stream slots (call SetNumStreams first)"); return false; }
+		const size_t n = shards.size();
+		// shard r advances ITS slots [0, count_r) with block r of the batch; the blocks are cut on the allocated total so that a
+		// stream always lands on the same device
+		for (size_t r = 0; r < n; r++)
+		{
+			const size_t b = ShardBegin(totalStreams, n, r), e = ShardBegin(totalStreams, n, r + 1);
+			if (b >= numStreams) break;
+			const size_t cnt = (e < numStreams ? e : numStreams) - b;
+			if (!shards[r]->ProcessBatchAsync(input + b * numFrames, output + b * numFrames, cnt, numFrames, layout)) { lastError = shards[r]->GetLastError(); return false; }
+		}
+		return true;
+	}
+
+	bool B200ShardedModel::ProcessBatch(const float* input, float* output, size_t numStreams, size_t numFrames, EBatchLayout layout)
+	{
+		// every shard is queued before any is awaited, so the devices run concurrently
+		if (!ProcessBatchAsync(input, output, numStreams, numFrames, layout)) return false;
+		return WaitBatches(0) && Synchronize();
+	}
+
+	bool B200ShardedModel::WaitBatches(int lag)
+	{
+		bool ok = true;
+		for (auto* m : shards) ok = m->WaitBatches(lag) && ok;
+		return ok;
+	}
+
+	bool B200ShardedModel::Synchronize()
+	{
+		bool ok = true;
+		for (auto* m : shards) ok = m->Synchronize() && ok;
+		return ok;
+	}
+
+	unsigned long long B200ShardedModel::GetKernelLaunchCount()
+	{
+		unsigned long long c = 0;
+		for (auto* m : shards) c += m->GetKernelLaunchCount();
+		return c;
+	}
+
+	std::string B200ShardedModel::GetLastError()
+	{
+		if (!lastError.empty()) return lastError;
+		for (auto* m : shards) { std::string e = m->GetLastError(); if (!e.empty()) return e; }
+		return "";
+	}
+
+	bool B200ShardedModel::ResetStreams()
+	{
+		bool ok = true;
+		for (auto* m : shards) ok = m->ResetStreams() && ok;
+		return ok;
+	}
+
+	bool B200ShardedModel::CopyStreamState(size_t stream, float* hostOut, size_t cap, size_t* written)
+	{
+		const size_t n = shards.size();
+		for (size_t r = 0; r < n; r++)
+		{
+			const size_t b = ShardBegin(totalStreams, n, r), e = ShardBegin(totalStreams, n, r + 1);
+			if (stream >= b && stream < e) return shards[r]->CopyStreamState(stream - b, hostOut, cap, written);
+		}
+		nab200::SetLastError("CopyStreamState: stream out of range");
+		return false;
 	}
 
 	// ---- loader (NeuralModelLoader::CreateFrom*, NeuralModel.cpp:319-581, Internal branch only) ------------------
@@ -364,6 +502,65 @@ inline namespace b200
 		if (!model->SetNumStreams(slots)) { delete model; return nullptr; }
 		if (doPrewarm) model->Prewarm();
 		if (!model->Synchronize()) { delete model; return nullptr; }
+		return model;
+	}
+
+	NeuralModel* NeuralModelLoader::CreateShardedFromFile(const std::filesystem::path& modelPath, const int* cudaDevices, int numDevices, bool doPrewarm)
+	{
+		if (!cudaDevices || numDevices < 1) { nab200::SetLastError("CreateShardedFromFile: no devices"); return nullptr; }
+		if (!std::filesystem::exists(modelPath)) { nab200::SetLastError("model file not found: " + modelPath.string()); return nullptr; }
+		std::ifstream jsonStream(modelPath, std::ifstream::binary);
+		std::stringstream text;
+		text << jsonStream.rdbuf();
+		const size_t total = defaultNumStreams > 0 ? defaultNumStreams : (size_t)numDevices;
+		const int savedDevice = device;
+		const size_t savedStreams = defaultNumStreams;
+		auto* model = new B200ShardedModel;
+		model->SetModelLoader(this);
+		auto restore = [&]() { device = savedDevice; defaultNumStreams = savedStreams; };
+		try
+		{
+			// the host parses and packs per device (cheap, deterministic); only device 0 computes the prewarmed state, which then
+			// travels with the weights in ONE grouped ncclBroadcast
+			for (int r = 0; r < numDevices; r++)
+			{
+				device = cudaDevices[r];
+				defaultNumStreams = B200ShardedModel::ShardBegin(total, (size_t)numDevices, (size_t)r + 1) - B200ShardedModel::ShardBegin(total, (size_t)numDevices, (size_t)r);
+				if (defaultNumStreams == 0) defaultNumStreams = 1;
+				NeuralModel* m = CreateFromJsonText(text.str(), modelPath.extension(), doPrewarm && r == 0);
+				if (!m) { restore(); delete model; return nullptr; }
+				model->shards.push_back(static_cast<B200ModelImpl*>(m));
+				model->devices.push_back(cudaDevices[r]);
+			}
+			restore();
+			model->CopyIdentityFrom(*model->shards[0]);
+			model->totalStreams = total;
+			if (numDevices > 1)
+			{
+				const nab200::NcclApi* nccl = nab200::GetNccl();
+				if (!nccl) { delete model; return nullptr; }
+				model->comms.assign((size_t)numDevices, nullptr);
+				if (!nab200::NcclOk(nccl->CommInitAll(model->comms.data(), numDevices, cudaDevices), "ncclCommInitAll")) { model->comms.clear(); delete model; return nullptr; }
+				bool ok = nab200::NcclOk(nccl->GroupStart(), "ncclGroupStart");
+				size_t bytes = 0;
+				for (int r = 0; ok && r < numDevices; r++)
+				{
+					size_t b = 0;
+					ok = model->shards[(size_t)r]->BroadcastQueue(model->comms[(size_t)r], 0, &b);
+					if (r == 0) bytes = b;
+				}
+				ok = nab200::NcclOk(nccl->GroupEnd(), "ncclGroupEnd") && ok;
+				for (int r = 0; ok && r < numDevices; r++) ok = model->shards[(size_t)r]->BroadcastFinish();
+				if (!ok) { delete model; return nullptr; }
+				model->broadcastBytes = bytes;
+			}
+		}
+		catch (...)
+		{
+			restore();
+			delete model;
+			throw;
+		}
 		return model;
 	}
 

@@ -70,6 +70,8 @@ namespace nab200
 			uint32_t wq, dq, xq;          // issuer: weight-block counter, barD / barX phase counters
 			int cur;
 			int* err;
+			char* sbase;                  // stagers: this stream's state
+			bool hasNext;                 // stagers: the CTA has another stream after this one
 		};
 
 		// TMEM column maps.  CONST (8 columns) is always r2 + 24.
@@ -150,44 +152,45 @@ namespace nab200
 		// cp.async (16 bytes per plane and row; consecutive threads <-> consecutive rows, so a warp moves contiguous 512-byte
 		// runs); one cp.async group per layer.
 		template <int CG>
-		__device__ __forceinline__ void prefetch_windows(const Ctx& cx, int l, int s, const int* hd)
+		__device__ __forceinline__ void prefetch_windows(const Ctx& cx, int l, const char* sbase, const int* hd)
 		{
 			const uint32_t la = cx.tab + (uint32_t)l * (uint32_t)sizeof(HLayer);
 			const uint4 g0 = lds128(la), g1 = lds128(la + 16);
 			const int Lp = (int)g0.z, numJobs = (int)g1.y;
 			const int head = hd[g1.x];
-			const char* ring = reinterpret_cast<const char*>(cx.state + (size_t)s * cx.M->stateStride + (int)g0.w);
-			const size_t step = (size_t)Lp * 16;
+			const char* ring = sbase + (size_t)g0.w * 4;
+#pragma unroll 1
 			for (int jb = 0; jb < numJobs; jb++)
 			{
 				const uint4 jj = lds128(la + kTabJobs + 16u * (uint32_t)jb);
 				const int cnt = (int)jj.x < 0 ? cx.n : (int)jj.x;
-				for (int r = cx.tid; r < cnt; r += kStagers)
+				int idx = head - (int)jj.y + cx.tid;                       // in [-Lp, Lp): one conditional wrap
+				uint32_t dst = cx.win + jj.z + (uint32_t)cx.tid * 16u;
+#pragma unroll 1
+				for (int r = cx.tid; r < cnt; r += kStagers, idx += kStagers, dst += kStagers * 16u)
 				{
-					int idx = head - (int)jj.y + r;
-					if (idx < 0) idx += Lp;
-					const char* src = ring + (size_t)idx * 16;
-					uint32_t dst = cx.win + jj.z + (uint32_t)r * 16u;
+					const int i2 = idx < 0 ? idx + Lp : idx;
 #pragma unroll
-					for (int g = 0; g < CG; g++, src += step, dst += cx.planeStride) cp_async16(dst, src);
+					for (int g = 0; g < CG; g++) cp_async16(dst + (uint32_t)g * cx.planeStride, ring + (size_t)(uint32_t)(i2 + g * Lp) * 16);
 				}
 			}
 			cp_async_commit();
 		}
 
-		// history of layer l counted from the first layer of stream s (l may run past the last layer: next stream)
-		__device__ __forceinline__ void prefetch_layer(const Ctx& cx, int l, int s, int a1First)
+		// history of layer l counted from the first layer of this stream (l may run past the last layer: next stream)
+		__device__ __forceinline__ void prefetch_layer(const Ctx& cx, int l, int a1First)
 		{
 			const int* hd = cx.hdb + cx.cur * kHdbHalf;
+			const char* sbase = cx.sbase;
 			if (l >= cx.numLayers)
 			{
 				l = 0;
-				s += cx.gstride;
 				hd = cx.hdb + (cx.cur ^ 1) * kHdbHalf;
-				if (s >= cx.S) { cp_async_commit(); return; }
+				if (!cx.hasNext) { cp_async_commit(); return; }
+				sbase = cx.sbase + (size_t)cx.gstride * ((size_t)cx.M->stateStride * 4);
 			}
-			if (l < a1First) prefetch_windows<4>(cx, l, s, hd);   // a1First = 0 for a single 8-channel array
-			else prefetch_windows<2>(cx, l, s, hd);
+			if (l < a1First) prefetch_windows<4>(cx, l, sbase, hd);   // a1First = 0 for a single 8-channel array
+			else prefetch_windows<2>(cx, l, sbase, hd);
 		}
 
 		// C fp32 values -> C words [h1 of channel pairs | h2 of channel pairs]
@@ -232,14 +235,14 @@ namespace nab200
 
 		// ---- stager warps: one layer array of the CTA's stream ------------------------------------------------------
 		template <int ROLE>
-		__device__ __forceinline__ void stage_array(Ctx& cx, const int firstLayer, const int numLayers, const int s, const int a1First)
+		__device__ __forceinline__ void stage_array(Ctx& cx, const int firstLayer, const int numLayers, const int a1First)
 		{
 			typedef Map<ROLE> MP;
 			constexpr int C = MP::C, CG = C / 4;
+			constexpr int NT = ROLE == 2 ? 5 : 2;   // the delayed-tap count with an unrolled path (K = 6 / K = 3)
 			const int tid = cx.tid;
 			const uint32_t lane = (uint32_t)(cx.warp * 32) << 16;
 			const int* hd = cx.hdb + cx.cur * kHdbHalf;
-			float* const st = cx.state + (size_t)s * cx.M->stateStride;
 			const uint32_t myRow = cx.win + (uint32_t)tid * 16u;
 
 			for (int li = 0; li < numLayers; li++)
@@ -271,29 +274,58 @@ namespace nab200
 				cp_async_wait_all();
 				if (mixed) nbar_sync<kBarMix, kStagers>();
 				// ---- delayed taps: my row of each, shared memory -> TMEM, no arithmetic ----
-#pragma unroll 1
-				for (int j0 = 0; j0 < numTaps; j0 += groupTaps)
+				if (numTaps == NT)
 				{
-					if (j0 > 0) stager_wait<kBarGReady>();
-					const int jn = (j0 + groupTaps < numTaps) ? j0 + groupTaps : numTaps;
-#pragma unroll 1
-					for (int j = j0; j < jn; j++)
+					uint32_t off[8];
 					{
-						const uint32_t row = myRow + lds32(la + kTabTaps + 4u * (uint32_t)j);
+						const uint4 o0 = lds128(la + kTabTaps);
+						off[0] = o0.x; off[1] = o0.y; off[2] = o0.z; off[3] = o0.w;
+						if (NT > 4)
+						{
+							const uint4 o1 = lds128(la + kTabTaps + 16);
+							off[4] = o1.x; off[5] = o1.y; off[6] = o1.z; off[7] = o1.w;
+						}
+					}
+#pragma unroll
+					for (int j = 0; j < NT; j++)
+					{
 						uint32_t v[C];
 #pragma unroll
 						for (int q = 0; q < CG; q++)
 						{
-							const uint4 t = lds128(row + (uint32_t)q * cx.planeStride);
+							const uint4 t = lds128(myRow + off[j] + (uint32_t)q * cx.planeStride);
 							v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
 						}
-						tmem_st<C>(lane + MP::tap(cx, j - j0), v);
+						tmem_st<C>(lane + MP::tap(cx, j), v);
 					}
 					stager_arrive<kBarTaps>();
 				}
+				else
+				{
+#pragma unroll 1
+					for (int j0 = 0; j0 < numTaps; j0 += groupTaps)
+					{
+						if (j0 > 0) stager_wait<kBarGReady>();
+						const int jn = (j0 + groupTaps < numTaps) ? j0 + groupTaps : numTaps;
+#pragma unroll 1
+						for (int j = j0; j < jn; j++)
+						{
+							const uint32_t row = myRow + lds32(la + kTabTaps + 4u * (uint32_t)j);
+							uint32_t v[C];
+#pragma unroll
+							for (int q = 0; q < CG; q++)
+							{
+								const uint4 t = lds128(row + (uint32_t)q * cx.planeStride);
+								v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+							}
+							tmem_st<C>(lane + MP::tap(cx, j - j0), v);
+						}
+						stager_arrive<kBarTaps>();
+					}
+				}
 				// every stager is done with this layer's windows: request the next layer's (or the next stream's first layer's)
 				nbar_sync<kBarMix, kStagers>();
-				prefetch_layer(cx, l + 1, s, a1First);
+				prefetch_layer(cx, l + 1, a1First);
 				// history write-back (AdvanceFrames, WaveNet.h:59-65): frame t becomes ring row (head + t) mod Lp
 				{
 					const int Lp = (int)g0.z;
@@ -302,10 +334,10 @@ namespace nab200
 					{
 						int idx = (cx.n > Lp ? hd[36 + g1.x] : hd[g1.x]) + (tid - first);
 						if (idx >= Lp) idx -= Lp;
-						char* dst = reinterpret_cast<char*>(st + (int)g0.w) + (size_t)idx * 16;
-						const size_t step = (size_t)Lp * 16;
+						char* const ring = cx.sbase + (size_t)g0.w * 4;
 #pragma unroll
-						for (int q = 0; q < CG; q++, dst += step) *reinterpret_cast<uint4*>(dst) = make_uint4(p[4 * q], p[4 * q + 1], p[4 * q + 2], p[4 * q + 3]);
+						for (int q = 0; q < CG; q++)
+							*reinterpret_cast<uint4*>(ring + (size_t)(uint32_t)(idx + q * Lp) * 16) = make_uint4(p[4 * q], p[4 * q + 1], p[4 * q + 2], p[4 * q + 3]);
 					}
 				}
 
@@ -352,6 +384,8 @@ namespace nab200
 		{
 			typedef Map<ROLE> MP;
 			constexpr int C = MP::C, N1 = MP::N1;
+			constexpr int NT = ROLE == 2 ? 5 : 2;   // the delayed-tap count with an unrolled path (K = 6 / K = 3)
+#pragma unroll 1
 			for (int li = 0; li < numLayers; li++)
 			{
 				const int l = firstLayer + li;
@@ -364,6 +398,34 @@ namespace nab200
 				uint32_t wb16 = 0;
 
 				// ---- dilated conv + mix-in + bias (WaveNet.h:250-289,471-476): undelayed tap, constant operand, delayed taps ----
+				if (numGroups == 1 && numTaps == NT)
+				{
+					// the common shape (K = 3 / K = 6): one weight block, every product's descriptor known before the hand-offs
+					if (li > 0) issuer_wait(cx, cx.barW0 + 8u * (cx.wq & 1u), (cx.wq >> 1) & 1u);
+					if (cx.el) issue_weights(cx, (l + 1 < cx.numLayers) ? l + 1 : 0, 0, cx.wq + 1);
+					__syncwarp();
+					wb16 = (cx.wbuf + (cx.wq & 1u) * cx.wbufStride) >> 4;
+					const uint32_t tb16 = wb16 + tap0Base16;
+					issuer_sync<kBarT2>();
+					if (cx.el)
+					{
+						mma_pairs<C, 0>(MP::d(cx), MP::t2(cx), wb16 + und16, C);   // overwrites the accumulator
+						mma_f16_ts<1>(MP::d(cx), konst(cx), desc_at(wb16 + g3.x, C), idesc_f16(C));
+					}
+					__syncwarp();
+					issuer_sync<kBarTaps>();
+					if (cx.el)
+					{
+#pragma unroll
+						for (int j = 0; j < NT; j++) mma_pairs<C, 1>(MP::d(cx), MP::tap(cx, j), tb16 + (uint32_t)(j * 4 * C), C);
+						mma_commit(cx.barD);
+					}
+					__syncwarp();
+					issuer_release<kBarDReady>(cx, cx.barD, cx.dq & 1u);
+					cx.dq++;
+				}
+				else
+				{
 				// one weight sub-block per tap group, through the two buffers in turn
 #pragma unroll 1
 				for (int g = 0; g < numGroups; g++)
@@ -394,6 +456,7 @@ namespace nab200
 					issuer_sync<kBarTaps>();
 					if (cx.el)
 					{
+#pragma unroll 1
 						for (int j = j0; j < jn; j++) mma_pairs<C, 1>(MP::d(cx), MP::tap(cx, j - j0), tb16 + (uint32_t)(j - j0) * tapStride16, C);
 						mma_commit(cx.barD);
 					}
@@ -402,6 +465,7 @@ namespace nab200
 					else issuer_release<kBarDReady>(cx, cx.barD, cx.dq & 1u);
 					cx.dq++;
 					if (g + 1 < numGroups) cx.wq++;
+				}
 				}
 
 				// ---- 1x1 + bias + residual, head sum (WaveNet.h:482-491): XR | HD += [z] [W1x1 | Whead] ----
@@ -570,10 +634,14 @@ namespace nab200
 				constexpr int CG0 = ARCH == 0 ? 4 : 2;
 				float cond = 0.0f;
 				if (tid < n && s0 < S) cond = in[(long long)s0 * inSS + (long long)tid * inFS];
-				if (s0 < S) prefetch_windows<CG0>(cx, 0, s0, cx.hdb);
+				const size_t strideBytes = (size_t)M.stateStride * 4;
+				cx.sbase = reinterpret_cast<char*>(state) + (size_t)s0 * strideBytes;
+				cx.hasNext = false;
+				if (s0 < S) prefetch_windows<CG0>(cx, 0, cx.sbase, cx.hdb);
 				for (int s = s0; s < S; s += gridDim.x)
 				{
 					const int sn = s + gridDim.x;
+					cx.hasNext = sn < S;
 					int* hdNext = cx.hdb + (cx.cur ^ 1) * kHdbHalf;
 					float condNext = 0.0f;
 					if (sn < S)
@@ -589,7 +657,7 @@ namespace nab200
 						}
 						if (tid < n) condNext = in[(long long)sn * inSS + (long long)tid * inFS];
 					}
-					float* const hist = state + (size_t)s * M.stateStride + M.arrays[0].headRingOff;
+					float* const hist = reinterpret_cast<float*>(cx.sbase) + M.arrays[0].headRingOff;
 					if constexpr (ARCH == 1)
 					{
 						// this stream's head history -> shared memory, off the chain (its own cp.async group, awaited in the first layer)
@@ -610,7 +678,7 @@ namespace nab200
 					stager_arrive<kBarE>();
 					if constexpr (ARCH == 0)
 					{
-						stage_array<0>(cx, first0, num0, s, first1);
+						stage_array<0>(cx, first0, num0, first1);
 
 						// ---- array transition: the array output and its head output as packed pairs ----
 						stager_wait<kBarXReady>();
@@ -625,7 +693,7 @@ namespace nab200
 							tmem_st<8>(lane + cx.r0, hp);
 						}
 						stager_arrive<kBarE>();
-						stage_array<1>(cx, first1, num1, s, first1);
+						stage_array<1>(cx, first1, num1, first1);
 
 						// ---- output (WaveNet.h:793-798) ----
 						stager_wait<kBarXReady>();
@@ -637,7 +705,7 @@ namespace nab200
 					}
 					else
 					{
-						stage_array<2>(cx, first0, num0, s, 0);
+						stage_array<2>(cx, first0, num0, 0);
 
 						// ---- output: 16-tap head conv of the summed head (WaveNet.h:658-660, 793-798) ----
 						// HD column k holds G_k[t] = Wh_k . headsum[t] (+ the head bias in column 15); out[t] = sum_k G_k[t - 15 + k].
@@ -674,6 +742,7 @@ namespace nab200
 					if (tid < M.numRings) heads[(size_t)s * M.numRings + tid] = cx.hdb[cx.cur * kHdbHalf + 36 + tid];
 					cx.cur ^= 1;
 					cond = condNext;
+					cx.sbase += (size_t)gridDim.x * strideBytes;
 					// a thread's TMEM reads above complete before its own stores of the next stream's entry; hdb slots are
 					// rewritten two streams later, after many hand-offs
 				}

@@ -248,7 +248,7 @@ def test_tensor_core_and_cuda_core_kernels_agree(na, O, name, tmp_path):
     S, n, calls = 12, 128, 10
     x = np.random.default_rng(17).uniform(-1, 1, (calls, S, n)).astype(np.float32)
     outs = []
-    for tc in (2, 1, 0):   # TMEM-operand tcgen05 kernel (default), shared-memory-operand tcgen05 kernel, CUDA-core kernel
+    for tc in (2, 1, 0, 3):   # 3xTF32 TMEM-operand tcgen05 kernel, shared-memory-operand tcgen05 kernel, CUDA-core kernel, fp16-pair tcgen05 kernel (default)
         prev = na.set_option("use_tc", tc)
         try:
             m = _load(na, mf, streams=S)
@@ -260,6 +260,7 @@ def test_tensor_core_and_cuda_core_kernels_agree(na, O, name, tmp_path):
             na.set_option("use_tc", prev)
     assert float(np.abs(outs[0] - outs[2]).max()) <= 4e-6
     assert float(np.abs(outs[1] - outs[2]).max()) <= 2e-6
+    assert float(np.abs(outs[3] - outs[2]).max()) <= 4e-6
     for s in (0, S - 1):
         ys = O.PortModel.from_file(mf).process(np.ascontiguousarray(x[:, s, :]).reshape(-1))
         for y in outs:
@@ -300,16 +301,20 @@ def test_split_launch_matches_fused(na, O, tmp_path):
     S, n, calls = 20, 128, 9
     x = np.random.default_rng(31).uniform(-1, 1, (calls, S, n)).astype(np.float32)
     outs = []
-    for split in (1, 0):
-        prev = na.set_option("ts_split", split)
-        try:
-            m = _load(na, mf, streams=S)
-            y = np.empty_like(x)
-            for k in range(calls):
-                m.ProcessBatch(x[k], y[k], S, n)
-            outs.append(y)
-        finally:
-            na.set_option("ts_split", prev)
+    prev_tc = na.set_option("use_tc", 2)       # the 3xTF32 kernel (the default is the fp16-pair kernel, which has no split form)
+    try:
+        for split in (1, 0):
+            prev = na.set_option("ts_split", split)
+            try:
+                m = _load(na, mf, streams=S)
+                y = np.empty_like(x)
+                for k in range(calls):
+                    m.ProcessBatch(x[k], y[k], S, n)
+                outs.append(y)
+            finally:
+                na.set_option("ts_split", prev)
+    finally:
+        na.set_option("use_tc", prev_tc)
     assert float(np.abs(outs[0] - outs[1]).max()) <= 2e-6
     ys = O.PortModel.from_file(mf).process(np.ascontiguousarray(x[:, 3, :]).reshape(-1))
     assert float(np.abs(ys - outs[0][:, 3, :].reshape(-1)).max()) <= WAVENET_TOL

@@ -37,7 +37,7 @@ def test_library_exports_every_declared_symbol(na):
 
 
 def test_only_the_public_surface_is_exported(na):
-    """Exports = the C ABI of include/NeuralAudioCApi.h plus the three out-of-line NeuralModelLoader::CreateFrom* methods of
+    """Exports = the C ABI of include/NeuralAudioCApi.h plus the four out-of-line NeuralModelLoader::Create* methods of
     include/NeuralAudio/NeuralModel.h (the C++ surface a ModelTest-style caller links against); nothing else leaks."""
     import subprocess
     out = subprocess.check_output(["nm", "-D", "-C", "--defined-only", na.library_path()], text=True)
@@ -45,7 +45,7 @@ def test_only_the_public_surface_is_exported(na):
     c_syms = [s for s in syms if "::" not in s]
     cpp_syms = sorted(s.split("(")[0] for s in syms if "::" in s)
     assert sorted(c_syms) == sorted(_declared_symbols())
-    assert cpp_syms == ["NeuralAudio::b200::NeuralModelLoader::" + m for m in ("CreateFromFile", "CreateFromJsonText", "CreateFromStream")]
+    assert cpp_syms == ["NeuralAudio::b200::NeuralModelLoader::" + m for m in ("CreateFromFile", "CreateFromJsonText", "CreateFromStream", "CreateShardedFromFile")]
 
 
 def test_loader_handles_work_without_gpu(na):

@@ -1,6 +1,8 @@
 #!/bin/bash
-# parity + timing of the fp16-pair kernel, then one full ncu capture of it (5 streams per SM)
+# instruction profile of one stream pass (a prewarm launch runs one stream) and a full-batch capture of the fp16-pair kernel
+# usage: tools/gpu_prof_h.sh [a1|a2]
 mkdir -p gpurun_out
-NAB200_H_DEBUG=1 timeout 300 python tools/h_check.py parity 2>&1 | grep -v "^wavenet_h_kernel" | tail -3; NAB200_H_DEBUG=1 python tools/h_check.py timing1 2>&1 | tail -2
-timeout 300 python tools/h_check.py timing 2>&1 | tail -6
-NAB200_H_CTAS=${1:-5} timeout 600 ncu --set full --clock-control none --import-source on -k regex:wavenet_h -s 60 -c 1 -f -o gpurun_out/prof_h python tools/h_check.py timing1 > gpurun_out/ncu_h.out 2>&1; tail -2 gpurun_out/ncu_h.out
+W=${1:-a1}
+T=timing1; [ "$W" = a2 ] && T=timing_a2
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:wavenet_h -s 10 -c 1 -f -o gpurun_out/prof_${W}_one python tools/h_check.py $T > gpurun_out/ncu_${W}.out 2>&1; tail -1 gpurun_out/ncu_${W}.out
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:wavenet_h -s 80 -c 1 -f -o gpurun_out/prof_${W} python tools/h_check.py $T > gpurun_out/ncu_${W}b.out 2>&1; tail -1 gpurun_out/ncu_${W}b.out

@@ -78,6 +78,8 @@ if __name__ == "__main__":
             timing("syn_a2_full", tc, ctas)
         for tc, ctas in ((0, 0), (3, 0)):
             timing("syn_a2_lite", tc, ctas)
+    if what == "timing_a2":
+        timing("syn_a2_full", 3, 0, steps=8)
     if what == "timing1":
         timing("syn_a1_standard.", 3, int(os.environ.get("NAB200_H_CTAS", "0")), steps=8)
     if what in ("all", "timing"):
