@@ -90,6 +90,11 @@ namespace nab200
 			if (evKernel[i]) cudaEventDestroy(evKernel[i]);
 			if (evDone[i]) cudaEventDestroy(evDone[i]);
 		}
+		for (int i = 0; i < kMaxSlices; i++)
+		{
+			if (evSliceIn[i]) cudaEventDestroy(evSliceIn[i]);
+			if (evSliceK[i]) cudaEventDestroy(evSliceK[i]);
+		}
 		if (h2dStream) cudaStreamDestroy(h2dStream);
 		if (d2hStream) cudaStreamDestroy(d2hStream);
 		if (stream) cudaStreamDestroy(stream);
@@ -227,6 +232,25 @@ namespace nab200
 			if (!outPinned) memcpy(out, pinnedOut, total * 4);
 			return CheckDeviceError();
 		}
+		// Large call: the batch is cut into slices of streams and the slices are pipelined over three CUDA streams (copy-in |
+		// kernels | copy-out), so the blocking drop-in call overlaps its own transfers with its own kernels.  The slice count
+		// keeps the number of kernel waves of the whole batch (a slice that does not fill a wave would waste the rest of it).
+		if (layout == 0 && S >= 64)
+		{
+			const size_t G = WaveStreams();
+			const size_t baseWaves = (S + G - 1) / G;
+			int best = 1;
+			double bestCost = 1e30;
+			for (int c = 1; c <= kMaxSlices; c++)
+			{
+				const size_t per = (S + (size_t)c - 1) / (size_t)c;
+				const double waves = (double)c * (double)((per + G - 1) / G);
+				// transfers not hidden behind kernels: the first slice's copy-in and the last one's copy-out (~0.4 of a wave-set)
+				const double cost = waves + 0.4 * (double)baseWaves / c + 0.03 * c;
+				if (cost < bestCost - 1e-9) { bestCost = cost; best = c; }
+			}
+			if (best > 1) return ProcessHostSliced(in, out, S, n, inPinned, outPinned, best);
+		}
 		// H2D -> kernels -> D2H, all on the model's stream, then wait
 		const float* hsrc = in;
 		if (!inPinned)
@@ -240,6 +264,46 @@ namespace nab200
 		if (!CudaOk(cudaMemcpyAsync(hdst, devOut, total * 4, cudaMemcpyDeviceToHost, stream), "cudaMemcpyAsync(D2H)")) return false;
 		if (!CudaOk(cudaStreamSynchronize(stream), "cudaStreamSynchronize")) return false;
 		if (!outPinned) memcpy(out, pinnedOut, total * 4);
+		return CheckDeviceError();
+	}
+
+	bool StreamEngine::ProcessHostSliced(const float* in, float* out, size_t S, size_t n, bool inPinned, bool outPinned, int slices)
+	{
+		if (!EnsurePipeline(0)) return false;
+		if (!WaitBatches(0)) return false;   // queued async calls use the same copy streams: keep the order simple
+		if (!evSliceIn[0])
+			for (int i = 0; i < kMaxSlices; i++)
+			{
+				if (!CudaOk(cudaEventCreateWithFlags(&evSliceIn[i], cudaEventDisableTiming), "cudaEventCreate")) return false;
+				if (!CudaOk(cudaEventCreateWithFlags(&evSliceK[i], cudaEventDisableTiming), "cudaEventCreate")) return false;
+			}
+		// the copy streams must not run ahead of work already queued on the model's stream (device-pointer calls)
+		if (!CudaOk(cudaEventRecord(evSliceK[0], stream), "cudaEventRecord")) return false;
+		if (!CudaOk(cudaStreamWaitEvent(d2hStream, evSliceK[0], 0), "cudaStreamWaitEvent")) return false;
+		const size_t per = (S + (size_t)slices - 1) / (size_t)slices;
+		int used = 0;
+		for (size_t b = 0; b < S; b += per, used++)
+		{
+			const size_t cnt = (S - b) < per ? (S - b) : per;
+			const size_t off = b * n, floats = cnt * n;
+			const float* hsrc = in + off;
+			if (!inPinned)
+			{
+				memcpy(pinnedIn + off, in + off, floats * 4);   // overlaps the transfers and kernels of the slices already queued
+				hsrc = pinnedIn + off;
+			}
+			if (!CudaOk(cudaMemcpyAsync(devIn + off, hsrc, floats * 4, cudaMemcpyHostToDevice, h2dStream), "cudaMemcpyAsync(H2D)")) return false;
+			if (!CudaOk(cudaEventRecord(evSliceIn[used], h2dStream), "cudaEventRecord")) return false;
+			if (!CudaOk(cudaStreamWaitEvent(stream, evSliceIn[used], 0), "cudaStreamWaitEvent")) return false;
+			if (!ProcessDevice(devIn + off, devOut + off, (long long)n, 1, (long long)n, 1, cnt, n, b)) return false;
+			if (!CudaOk(cudaEventRecord(evSliceK[used], stream), "cudaEventRecord")) return false;
+			if (!CudaOk(cudaStreamWaitEvent(d2hStream, evSliceK[used], 0), "cudaStreamWaitEvent")) return false;
+			float* hdst = outPinned ? out + off : pinnedOut + off;
+			if (!CudaOk(cudaMemcpyAsync(hdst, devOut + off, floats * 4, cudaMemcpyDeviceToHost, d2hStream), "cudaMemcpyAsync(D2H)")) return false;
+		}
+		if (!CudaOk(cudaStreamSynchronize(d2hStream), "cudaStreamSynchronize")) return false;
+		// later device-pointer calls on the model's stream may reuse the staging buffers only after these copies (already done)
+		if (!outPinned) memcpy(out, pinnedOut, S * n * 4);
 		return CheckDeviceError();
 	}
 
@@ -495,7 +559,13 @@ namespace nab200
 		return ResetStreams();
 	}
 
-	bool WaveNetEngine::ProcessDevice(const float* in, float* out, long long inSS, long long inFS, long long outSS, long long outFS, size_t S, size_t n)
+	size_t WaveNetEngine::WaveStreams() const
+	{
+		const int tc = packed.dev.tc;
+		return (size_t)numSMs * (tc == 3 ? 5 : tc ? 4 : 6);
+	}
+
+	bool WaveNetEngine::ProcessDevice(const float* in, float* out, long long inSS, long long inFS, long long outSS, long long outFS, size_t S, size_t n, size_t slotOffset)
 	{
 		const int maxPass = (packed.dev.tc || useGeneric) ? 128 : wavenet_max_frames_per_pass(packed.dev.arrays[0].C);
 		const Options& opt = GetOptions();
@@ -505,8 +575,8 @@ namespace nab200
 			const size_t chunk = (n - done) < (size_t)maxPass ? (n - done) : (size_t)maxPass;
 			WnLaunch a;
 			a.weights = dBlob;
-			a.state = dState;
-			a.heads = dHeads;
+			a.state = dState + slotOffset * (size_t)packed.dev.stateStride;
+			a.heads = dHeads + slotOffset * (size_t)packed.dev.numRings;
 			a.in = in + (long long)done * inFS;
 			a.out = out + (long long)done * outFS;
 			a.inSS = inSS; a.inFS = inFS; a.outSS = outSS; a.outFS = outFS;
@@ -516,7 +586,7 @@ namespace nab200
 			a.useTma = opt.useTma != 0;
 			a.stream = stream;
 			a.tsIssuers = opt.tsIssuers;
-			a.tsSplit = opt.tsSplit; a.scratch = dScratch;
+			a.tsSplit = opt.tsSplit; a.scratch = dScratch ? dScratch + slotOffset * wavenet_ts_scratch_floats_per_stream() : nullptr;
 			a.ctasPerSM = opt.hCtas; a.err = dErr;
 			const cudaError_t lerr = packed.dev.tc == 3 ? wavenet_h_launch(packed.dev, a) : packed.dev.tc == 2 ? wavenet_ts_launch(packed.dev, a) : packed.dev.tc ? wavenet_tc_launch(packed.dev, a)
 				: useGeneric ? wavenet_generic_launch(packed.dev, a) : wavenet_launch(packed.dev, a);
@@ -628,11 +698,11 @@ namespace nab200
 		return true;
 	}
 
-	bool LstmEngine::ProcessDevice(const float* in, float* out, long long inSS, long long inFS, long long outSS, long long outFS, size_t S, size_t n)
+	bool LstmEngine::ProcessDevice(const float* in, float* out, long long inSS, long long inFS, long long outSS, long long outFS, size_t S, size_t n, size_t slotOffset)
 	{
 		LstmLaunch a;
 		a.weights = dBlob;
-		a.state = dState;
+		a.state = dState + slotOffset * (size_t)packed.dev.stateStride;
 		a.in = in; a.out = out;
 		a.inSS = inSS; a.inFS = inFS; a.outSS = outSS; a.outFS = outFS;
 		a.S = (int)S;

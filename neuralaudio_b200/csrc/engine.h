@@ -68,8 +68,15 @@ namespace nab200
 
 	protected:
 		// device pointers, element (s, f) at p[s*SS + f*FS]
+		// advances stream slots [slotOffset, slotOffset + numStreams)
 		virtual bool ProcessDevice(const float* in, float* out, long long inSS, long long inFS, long long outSS, long long outFS,
-			size_t numStreams, size_t numFrames) = 0;
+			size_t numStreams, size_t numFrames, size_t slotOffset = 0) = 0;
+		// streams one launch keeps in flight at a time (a slice of the batch smaller than this runs as one wave)
+		virtual size_t WaveStreams() const { return (size_t)numSMs * 4; }
+		// blocking host call as a pipeline over slices of the batch (H2D | kernels | D2H on three streams)
+		bool ProcessHostSliced(const float* in, float* out, size_t S, size_t n, bool inPinned, bool outPinned, int slices);
+		static constexpr int kMaxSlices = 8;
+		cudaEvent_t evSliceIn[kMaxSlices] = {}, evSliceK[kMaxSlices] = {};
 		bool EnsureStaging(size_t floats);
 		// sticky device error word (page-locked, mapped): a kernel that loses an MMA / copy completion sets it instead of
 		// hanging; every host-side synchronisation point checks it
@@ -114,7 +121,8 @@ namespace nab200
 
 	protected:
 		bool ProcessDevice(const float* in, float* out, long long inSS, long long inFS, long long outSS, long long outFS, size_t numStreams,
-			size_t numFrames) override;
+			size_t numFrames, size_t slotOffset) override;
+		size_t WaveStreams() const override;
 
 	private:
 		PackedWaveNet packed;
@@ -141,7 +149,8 @@ namespace nab200
 
 	protected:
 		bool ProcessDevice(const float* in, float* out, long long inSS, long long inFS, long long outSS, long long outFS, size_t numStreams,
-			size_t numFrames) override;
+			size_t numFrames, size_t slotOffset) override;
+		size_t WaveStreams() const override { return (size_t)numSMs * 32; }
 
 	private:
 		PackedLstm packed;

@@ -170,3 +170,30 @@ def test_sharded_model_equals_single_device(na, name, S, tmp_path):
     sharded.ProcessBatch(x[0][:part].contiguous().pin_memory(), ys[0][:part], part, n)
     single.ProcessBatch(x[0][:part].contiguous().pin_memory(), y1[0][:part], part, n)
     assert torch.equal(ys[0][:part], y1[0][:part])
+
+
+@pytest.mark.parametrize("name,S,n", [("syn_a1_standard.", 4096, 128), ("syn_lstm_1x16", 8192, 128), ("syn_a1_nano.", 1500, 64)])
+def test_blocking_host_call_is_sliced_and_exact(na, name, S, n, tmp_path):
+    """The drop-in blocking NA_ProcessBatch with HOST pointers pipelines slices of the batch (copy-in | kernels | copy-out):
+    pinned and pageable buffers must give bit-identical results to the device-pointer path, call after call."""
+    import torch
+    g = load_golden(golden_files(name)[0])
+    mf = model_file_for(g, tmp_path)
+    calls = 3
+    x = torch.from_numpy(np.random.default_rng(41).uniform(-0.6, 0.6, (calls, S, n)).astype(np.float32))
+    ref = _load(na, mf, streams=S)
+    xd = x.cuda()
+    yd = torch.empty_like(xd)
+    for k in range(calls):
+        ref.ProcessBatch(xd[k], yd[k], S, n)
+    ref.Synchronize()
+    want = yd.cpu()
+    pinned = _load(na, mf, streams=S)
+    xp, yp = x.pin_memory(), torch.empty_like(x).pin_memory()
+    pageable = _load(na, mf, streams=S)
+    xq, yq = x.numpy().copy(), np.empty((calls, S, n), dtype=np.float32)
+    for k in range(calls):
+        pinned.ProcessBatch(xp[k], yp[k], S, n)
+        pageable.ProcessBatch(xq[k], yq[k], S, n)
+    assert torch.equal(yp, want)
+    assert np.array_equal(yq, want.numpy())
