@@ -246,7 +246,7 @@ namespace nab200
 				const size_t per = (S + (size_t)c - 1) / (size_t)c;
 				const double waves = (double)c * (double)((per + G - 1) / G);
 				// transfers not hidden behind kernels: the first slice's copy-in and the last one's copy-out (~0.4 of a wave-set)
-				const double cost = waves + 0.4 * (double)baseWaves / c + 0.03 * c;
+				const double cost = waves + 0.4 * (double)baseWaves / c + 0.15 * c;   // + host-side issue cost per slice
 				if (cost < bestCost - 1e-9) { bestCost = cost; best = c; }
 			}
 			if (best > 1) return ProcessHostSliced(in, out, S, n, inPinned, outPinned, best);

@@ -5,6 +5,26 @@
 
 namespace nab200
 {
+	// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) costs microseconds per call: do it once per (kernel, device, size) instead of
+	// once per launch.  `slot` is a per-kernel static the caller provides: [device] -> largest size already granted.
+	struct SmemGrant { int granted[16] = { 0 }; };
+	template <typename K>
+	inline cudaError_t EnsureDynamicSmem(K kfn, SmemGrant& slot, size_t bytes, bool maxCarveout = false)
+	{
+		int dev = 0;
+		cudaGetDevice(&dev);
+		if (dev >= 0 && dev < 16 && slot.granted[dev] >= (int)bytes && bytes > 0) return cudaSuccess;
+		cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+		if (e != cudaSuccess) return e;
+		if (maxCarveout)
+		{
+			e = cudaFuncSetAttribute(kfn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+			if (e != cudaSuccess) return e;
+		}
+		if (dev >= 0 && dev < 16) slot.granted[dev] = (int)bytes;
+		return cudaSuccess;
+	}
+
 	struct WnLaunch
 	{
 		const float* weights;   // packed weight blocks (device)

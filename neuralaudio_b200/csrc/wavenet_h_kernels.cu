@@ -775,11 +775,10 @@ namespace nab200
 	{
 		auto kfn = hk::wavenet_h_kernel<ARCH>;
 		const size_t smem = wavenet_h_smem_bytes(M);
-		cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-		if (e != cudaSuccess) return e;
 		// five CTAs of ~43 KB need the SM's full 228 KB as shared memory: ask for the maximum carve-out (the default heuristic
 		// keeps more L1 and fits only four - ncu launch__occupancy_limit_shared_mem)
-		e = cudaFuncSetAttribute(kfn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+		static SmemGrant grant;
+		cudaError_t e = EnsureDynamicSmem(kfn, grant, smem, true);
 		if (e != cudaSuccess) return e;
 		// streams in flight per SM: 5 by TMEM (96 columns each) and registers (64 x 6 allocated warps), fewer when a model's
 		// weight blocks make the CTA's shared memory larger than a fifth of the SM's

@@ -957,14 +957,16 @@ namespace nab200
 		if (a.useTma)
 		{
 			auto kfn = wavenet_fwd_kernel<C0, C1, RT, WPS, ACT, true>;
-			err = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+			static SmemGrant grant1;
+			err = EnsureDynamicSmem(kfn, grant1, smem);
 			if (err != cudaSuccess) return err;
 			kfn<<<grid, threads, smem, a.stream>>>(M, a.weights, a.state, a.heads, a.in, a.out, a.inSS, a.inFS, a.outSS, a.outFS, a.S, a.n);
 		}
 		else
 		{
 			auto kfn = wavenet_fwd_kernel<C0, C1, RT, WPS, ACT, false>;
-			err = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+			static SmemGrant grant2;
+			err = EnsureDynamicSmem(kfn, grant2, smem);
 			if (err != cudaSuccess) return err;
 			kfn<<<grid, threads, smem, a.stream>>>(M, a.weights, a.state, a.heads, a.in, a.out, a.inSS, a.inFS, a.outSS, a.outFS, a.S, a.n);
 		}

@@ -687,7 +687,8 @@ namespace nab200
 		if (a.n > tc::kCur) return cudaErrorInvalidValue;
 		auto kfn = tc::wavenet_tc_kernel<16, 8, 0>;
 		const size_t smem = tc::smem_floats_fixed<16>() * 4 + (size_t)2 * M.maxBlock * 4 + tc::kTableBytes + 72 * 4 + 4 * 8 + 16;
-		cudaError_t err = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		static SmemGrant grant1;
+		cudaError_t err = EnsureDynamicSmem(kfn, grant1, smem);
 		if (err != cudaSuccess) return err;
 		int grid = a.numSMs * 3;
 		if (grid > a.S) grid = a.S;

@@ -1212,7 +1212,8 @@ namespace nab200
 	{
 		auto kfn = ts::wavenet_ts_kernel<MODE>;
 		const size_t smem = ts::smem_fixed_bytes(MODE == 2 ? 2 : 4) + (size_t)2 * wbufFloats * 4 + ts::kTableBytes + 2 * ts::kHdbHalf * 4 + ts::kNumBars * 8 + 16 + 256;
-		cudaError_t err = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		static SmemGrant grant1;
+		cudaError_t err = EnsureDynamicSmem(kfn, grant1, smem);
 		if (err != cudaSuccess) return err;
 		int grid = a.numSMs * ctasPerSM;
 		if (grid > a.S) grid = a.S;
