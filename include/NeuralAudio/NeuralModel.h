@@ -245,6 +245,10 @@ inline namespace b200
 		void SetDefaultNumStreams(size_t numStreams) { defaultNumStreams = numStreams; }
 		size_t GetDefaultNumStreams() { return defaultNumStreams; }
 		int GetExternalSampleRate() { return externalSampleRate; }
+		// tuning knob for the models THIS loader builds (names as NA_SetOption); the process-wide defaults stay untouched, so
+		// loaders on different threads can use different knobs without racing
+		void SetOption(const std::string& name, int value) { optionOverrides.emplace_back(name, value); }
+		const std::vector<std::pair<std::string, int>>& GetOptionOverrides() const { return optionOverrides; }
 
 	protected:
 		EModelLoadMode lstmLoadMode = EModelLoadMode::Internal;
@@ -256,6 +260,7 @@ inline namespace b200
 		int externalSampleRate = 48000;
 		int device = -1;
 		size_t defaultNumStreams = 1;
+		std::vector<std::pair<std::string, int>> optionOverrides;
 	};
 }
 }

@@ -139,6 +139,8 @@ NA_EXTERN int NA_DescribeModelFile(const wchar_t* modelPath, int externalSampleR
  *   "max_grid_ctas": cap on the SM count used for grid sizing (0 = all).
  * The same knobs can be preset through NAB200_USE_TC / NAB200_TS_SPLIT / NAB200_USE_TMA / NAB200_MAX_GRID_CTAS. */
 NA_EXTERN int NA_SetOption(const char* name, int value);
+/* the same knobs for the models ONE loader builds (copied into each model at load; nothing is read from globals at run time) */
+NA_EXTERN void NA_SetLoaderOption(NeuralModelLoader* loader, const char* name, int value);
 
 #ifdef __cplusplus
 }

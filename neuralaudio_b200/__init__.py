@@ -110,6 +110,7 @@ def load_library():
         "NA_CopyStreamState": (ci, [vp, sz, _f32p, sz]),
         "NA_DescribeModelFile": (ci, [ctypes.c_wchar_p, ci, ctypes.c_char_p, ci]),
         "NA_SetOption": (ci, [ctypes.c_char_p, ci]),
+        "NA_SetLoaderOption": (None, [vp, ctypes.c_char_p, ci]),
         # multi-GPU load inside the library (NCCL through dlopen)
         "NA_NcclGetUniqueId": (ci, [ctypes.c_char_p]),
         "NA_NcclCommInitRank": (vp, [ci, ci, ctypes.c_char_p, ci]),
@@ -139,8 +140,28 @@ def device_count():
     return load_library().NA_GetDeviceCount()
 
 
+def _prefer_bundled_nccl():
+    """The library reaches NCCL with dlopen("libnccl.so.2").  In a Python process that also imports PyTorch, the copy that
+    gets loaded FIRST wins for everybody (same soname), and PyTorch needs the one bundled with it (nvidia/nccl/lib): point
+    the library at that copy unless the user chose one (NAB200_NCCL_LIB)."""
+    if os.environ.get("NAB200_NCCL_LIB"):
+        return
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        if spec and spec.submodule_search_locations:
+            for base in spec.submodule_search_locations:
+                cand = os.path.join(base, "lib", "libnccl.so.2")
+                if os.path.exists(cand):
+                    os.environ["NAB200_NCCL_LIB"] = cand
+                    return
+    except Exception:
+        pass
+
+
 def nccl_get_unique_id():
     """128 bytes from ncclGetUniqueId (root rank); ship them to the other ranks by any means, then NcclComm(...) everywhere."""
+    _prefer_bundled_nccl()
     L = load_library()
     buf = ctypes.create_string_buffer(128)
     if L.NA_NcclGetUniqueId(buf) != 0:
@@ -152,6 +173,7 @@ class NcclComm:
     """One rank's NCCL communicator owned by the library (ncclCommInitRank), for NeuralModel.BroadcastModel."""
 
     def __init__(self, nranks, rank, unique_id, device):
+        _prefer_bundled_nccl()
         self._L = load_library()
         if len(unique_id) != 128:
             raise ValueError("unique_id must be the 128 bytes of nccl_get_unique_id()")
@@ -242,6 +264,10 @@ class NeuralModelLoader:
     def SetCompositeModelLoadMode(self, mode):
         self._L.NA_SetCompositeModelLoadMode(self._h, int(mode))
 
+    def SetOption(self, name, value):
+        """Tuning knob for the models this loader builds (the process-wide set_option defaults stay untouched)."""
+        self._L.NA_SetLoaderOption(self._h, name.encode(), int(value))
+
     def SetDevice(self, device):
         self._L.NA_SetLoaderDevice(self._h, int(device))
 
@@ -257,6 +283,7 @@ class NeuralModelLoader:
     def CreateShardedFromFile(self, path, devices, doPrewarm=True):
         """One process, several GPUs: the model on every listed device, one grouped ncclBroadcast of [weights | prewarmed state]
         from the first, the stream batch (SetDefaultNumStreams = the total) cut into contiguous shards."""
+        _prefer_bundled_nccl()
         arr = (ctypes.c_int * len(devices))(*[int(d) for d in devices])
         h = self._L.NA_CreateModelSharded(self._h, os.path.abspath(path), arr, len(devices), 1 if doPrewarm else 0)
         if not h:

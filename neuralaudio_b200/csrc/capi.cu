@@ -485,10 +485,9 @@ int NA_DescribeModelFile(const wchar_t* modelPath, int externalSampleRate, char*
 					// every conv tap matrix must reconstruct as hi + lo, with hi exactly representable in tf32
 					const bool hk = nab200::GetOptions().useTc >= 3 && nab200::WaveNetHSupported(d);
 					const bool ts = !hk && nab200::GetOptions().useTc >= 2 && nab200::WaveNetTsSupported(d);
-					const bool tc = !hk && !ts && nab200::GetOptions().useTc >= 1 && nab200::WaveNetTcSupported(d);
 					const int pc0 = p.dev.arrays[0].C, pc1 = p.dev.numArrays > 1 ? p.dev.arrays[1].C : 0;
 					const bool shaped = nab200::GetOptions().useTc >= 0 && nab200::wavenet_variant_supported(pc0, pc1, p.dev.arrays[0].act);
-					os << ",\"kernel\":\"" << (hk ? "tcgen05_fp16_pairs" : ts ? "tcgen05_tmem_operands" : tc ? "tcgen05_smem_operands" : shaped ? "cuda_cores" : nab200::wavenet_generic_supported(p.dev) ? "cuda_cores_runtime_shaped" : "none") << "\"";
+					os << ",\"kernel\":\"" << (hk ? "tcgen05_fp16_pairs" : ts ? "tcgen05_tmem_operands" : shaped ? "cuda_cores" : nab200::wavenet_generic_supported(p.dev) ? "cuda_cores_runtime_shaped" : "none") << "\"";
 					if (nab200::WaveNetTsSupported(d))
 					{
 						nab200::PackedWaveNet q = nab200::PackWaveNetTs(d);
@@ -620,6 +619,11 @@ int NA_DescribeModelFile(const wchar_t* modelPath, int externalSampleRate, char*
 		nab200::SetLastError("unknown error");
 	}
 	return -1;
+}
+
+void NA_SetLoaderOption(NeuralModelLoader* loader, const char* name, int value)
+{
+	if (loader && loader->loader && name) loader->loader->SetOption(name, value);
 }
 
 int NA_SetOption(const char* name, int value)

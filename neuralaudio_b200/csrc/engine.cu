@@ -14,11 +14,10 @@ namespace nab200
 	{
 		static Options o = []
 		{
-			// tuning knobs can also come from the environment (NAB200_USE_TC, NAB200_TS_ISSUERS, NAB200_USE_TMA, NAB200_MAX_GRID_CTAS)
+			// tuning knobs can also come from the environment (NAB200_USE_TC, NAB200_USE_TMA, NAB200_MAX_GRID_CTAS)
 			Options v;
 			auto env = [](const char* name, int& dst) { const char* e = getenv(name); if (e && *e) dst = atoi(e); };
 			env("NAB200_USE_TC", v.useTc);
-			env("NAB200_TS_ISSUERS", v.tsIssuers);
 			env("NAB200_TS_SPLIT", v.tsSplit);
 			env("NAB200_H_CTAS", v.hCtas);
 			env("NAB200_USE_TMA", v.useTma);
@@ -29,13 +28,13 @@ namespace nab200
 		return o;
 	}
 
-	int SetOption(const char* name, int value)
+	int SetOption(const char* name, int value) { return ApplyOption(GetOptions(), name, value); }
+
+	int ApplyOption(Options& o, const char* name, int value)
 	{
-		Options& o = GetOptions();
 		int prev = -1;
 		if (strcmp(name, "use_tma") == 0) { prev = o.useTma; o.useTma = value; }
 		else if (strcmp(name, "use_tc") == 0) { prev = o.useTc; o.useTc = value; }
-		else if (strcmp(name, "ts_issuers") == 0) { prev = o.tsIssuers; o.tsIssuers = value; }
 		else if (strcmp(name, "ts_split") == 0) { prev = o.tsSplit; o.tsSplit = value; }
 		else if (strcmp(name, "h_ctas") == 0) { prev = o.hCtas; o.hCtas = value; }
 		else if (strcmp(name, "max_grid_ctas") == 0) { prev = o.maxGridCtas; o.maxGridCtas = value; }
@@ -72,7 +71,7 @@ namespace nab200
 	}
 
 	// ---- StreamEngine -------------------------------------------------------------------------------------
-	StreamEngine::StreamEngine(int dev) : device(dev) {}
+	StreamEngine::StreamEngine(int dev) : opt(GetOptions()), device(dev) {}
 
 	StreamEngine::~StreamEngine()
 	{
@@ -443,12 +442,11 @@ namespace nab200
 		const int C0 = M.arrays[0].C, C1 = M.numArrays > 1 ? M.arrays[1].C : 0;
 		bool ok = M.tc == 3 ? wavenet_h_variant_supported(C0, C1, M.arrays[0].act)
 			: M.tc == 2 ? wavenet_ts_variant_supported(C0, C1, M.arrays[0].act)
-			: M.tc ? wavenet_tc_variant_supported(C0, C1, M.arrays[0].act)
 			: (wavenet_variant_supported(C0, C1, M.arrays[0].act) && wavenet_window_jobs(M) <= wavenet_max_window_jobs());
 		// the compile-time-shaped CUDA-core kernel double-buffers a layer's weight block in shared memory beside its windows:
 		// a block that cannot fit (very large kernel sizes) is a load-time refusal / generic-kernel case, not a launch failure
 		if (M.tc == 0 && ok && (size_t)2 * M.maxBlock * 4 > (size_t)96 * 1024) ok = false;
-		if (M.tc == 0 && (!ok || GetOptions().useTc < 0) && wavenet_generic_supported(M))
+		if (M.tc == 0 && (!ok || opt.useTc < 0) && wavenet_generic_supported(M))
 		{
 			// no compile-time-shaped kernel (or the generic one was asked for): the run-time-shaped kernel
 			useGeneric = true;
@@ -541,10 +539,9 @@ namespace nab200
 				a.in = io; a.out = io + frames;
 				a.inSS = frames; a.inFS = 1; a.outSS = frames; a.outFS = 1;
 				a.S = 1; a.n = frames; a.numSMs = numSMs; a.useTma = true; a.stream = stream;
-				a.tsIssuers = GetOptions().tsIssuers;
-				a.tsSplit = GetOptions().tsSplit; a.scratch = handover;
+				a.tsSplit = opt.tsSplit; a.scratch = handover;
 				a.err = dErr;
-				ok = CudaOk(M.tc == 3 ? wavenet_h_launch(M, a) : M.tc == 2 ? wavenet_ts_launch(M, a) : wavenet_tc_launch(M, a), "wavenet tensor-core prewarm settle");
+				ok = CudaOk(M.tc == 3 ? wavenet_h_launch(M, a) : wavenet_ts_launch(M, a), "wavenet tensor-core prewarm settle");
 			}
 			// under constant input every ring column holds the same value, so the settled rings are a valid template
 			// for ring head 0 whatever position the scratch heads ended at
@@ -568,7 +565,6 @@ namespace nab200
 	bool WaveNetEngine::ProcessDevice(const float* in, float* out, long long inSS, long long inFS, long long outSS, long long outFS, size_t S, size_t n, size_t slotOffset)
 	{
 		const int maxPass = (packed.dev.tc || useGeneric) ? 128 : wavenet_max_frames_per_pass(packed.dev.arrays[0].C);
-		const Options& opt = GetOptions();
 		size_t done = 0;
 		while (done < n)
 		{
@@ -585,10 +581,9 @@ namespace nab200
 			a.numSMs = (opt.maxGridCtas > 0) ? opt.maxGridCtas : numSMs;
 			a.useTma = opt.useTma != 0;
 			a.stream = stream;
-			a.tsIssuers = opt.tsIssuers;
 			a.tsSplit = opt.tsSplit; a.scratch = dScratch ? dScratch + slotOffset * wavenet_ts_scratch_floats_per_stream() : nullptr;
 			a.ctasPerSM = opt.hCtas; a.err = dErr;
-			const cudaError_t lerr = packed.dev.tc == 3 ? wavenet_h_launch(packed.dev, a) : packed.dev.tc == 2 ? wavenet_ts_launch(packed.dev, a) : packed.dev.tc ? wavenet_tc_launch(packed.dev, a)
+			const cudaError_t lerr = packed.dev.tc == 3 ? wavenet_h_launch(packed.dev, a) : packed.dev.tc == 2 ? wavenet_ts_launch(packed.dev, a)
 				: useGeneric ? wavenet_generic_launch(packed.dev, a) : wavenet_launch(packed.dev, a);
 			if (!CudaOk(lerr, "wavenet kernel launch")) return false;
 			kernelLaunches += (packed.dev.tc == 2 && opt.tsSplit && dScratch) ? 2 : 1;
@@ -682,8 +677,8 @@ namespace nab200
 		a.in = nullptr; a.out = nullptr;
 		a.n = 2048;
 		a.zeroInput = true;
-		a.generic = GetOptions().useTc < 0;
-		a.kernel = GetOptions().lstmKernel;
+		a.generic = opt.useTc < 0;
+		a.kernel = opt.lstmKernel;
 		a.numSMs = numSMs;
 		a.stream = stream;
 		a.state = dBlob + weightFloats;
@@ -708,8 +703,8 @@ namespace nab200
 		a.S = (int)S;
 		a.n = (int)n;
 		a.zeroInput = false;
-		a.generic = GetOptions().useTc < 0;
-		a.kernel = GetOptions().lstmKernel;
+		a.generic = opt.useTc < 0;
+		a.kernel = opt.lstmKernel;
 		a.numSMs = numSMs;
 		a.stream = stream;
 		if (!CudaOk(lstm_launch(packed.dev, a), "lstm_fwd_kernel launch")) return false;

@@ -18,9 +18,8 @@ namespace nab200
 	{
 		int useTma = 1;         // stage history windows with cp.async.bulk + mbarrier (0: plain loads, debugging aid)
 		int useTc = 3;          // WaveNet kernel choice where the architecture fits: 3 tcgen05 with fp16-pair TMEM operands (default),
-		                        // 2 tcgen05 3xTF32 with TMEM operands, 1 tcgen05 with shared-memory operands (round-1 kernel), 0 CUDA-core kernel,
+		                        // 2 tcgen05 3xTF32 with TMEM operands, 0 (or 1) CUDA-core kernel,
 		                        // -1 the run-time-shaped kernel even for shapes that have a specialised one (tests)
-		int tsIssuers = 4;      // (unused since the TS kernel has a dedicated issuer warp)
 		int tsSplit = 0;        // TS kernel: 1 = one launch per layer array, the 8-channel one with 6 CTAs per SM (measured 5 % slower
 		                        // than the fused kernel: 144 + 90 us vs 208 us; kept as an option, its head sum is exact fp32)
 		int maxGridCtas = 0;    // 0: one CTA per SM
@@ -28,7 +27,8 @@ namespace nab200
 		int lstmKernel = 0;     // LSTM kernel: 0 automatic, 1 gate rows in registers, 2 lane = stream (matrices in shared memory), 3 run-time-shaped
 	};
 	Options& GetOptions();
-	int SetOption(const char* name, int value);
+	int SetOption(const char* name, int value);                       // the process-wide defaults (what a new loader starts from)
+	int ApplyOption(Options& o, const char* name, int value);          // one knob of one Options value; returns the previous value, -1 if unknown
 
 	bool CudaOk(cudaError_t err, const char* what);
 
@@ -36,6 +36,9 @@ namespace nab200
 	{
 	public:
 		StreamEngine(int device);
+		// tuning knobs are copied when the engine is built (from the loader that builds it): later changes of the process-wide
+		// defaults, or loaders with other knobs on other threads, cannot race with this engine's launches
+		Options opt;
 		virtual ~StreamEngine();
 
 		bool Init();   // picks the device, creates the stream; false (with LastError) when there is no usable GPU

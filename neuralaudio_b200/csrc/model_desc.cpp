@@ -513,128 +513,6 @@ namespace nab200
 		return x;
 	}
 
-	bool WaveNetTcSupported(const WaveNetDesc& desc)
-	{
-		// what wavenet_tc_kernels.cu instantiates: tanh A1-style stacks of (16, 8) channels after padding, 1x1 heads,
-		// every layer either "whole window" ((K-1)*d <= 128) or K == 3 with d >= 128 (two pure-history tap windows)
-		if (desc.arrays.size() != 2) return false;
-		if (TcPad(desc.arrays[0].channels) != 16 || TcPad(desc.arrays[1].channels) != 8) return false;
-		if (desc.arrays[0].channels <= 8) return false;
-		for (const auto& A : desc.arrays)
-		{
-			if (A.activation != 0 || A.headKernel != 1) return false;
-			for (size_t l = 0; l < A.dilations.size(); l++)
-			{
-				const int K = A.kernelSizes[l], d = A.dilations[l], hist = (K - 1) * d;
-				if (hist < 1) return false;
-				if (hist <= 128) continue;
-				if (K == 3 && d >= 128) continue;
-				return false;
-			}
-		}
-		return true;
-	}
-
-	PackedWaveNet PackWaveNetTc(const WaveNetDesc& desc)
-	{
-		PackedWaveNet P;
-		WnModelDev& M = P.dev;
-		memset(&M, 0, sizeof(M));
-		M.tc = 1;
-		M.numArrays = (int)desc.arrays.size();
-		const float* w = desc.weights.data();
-		int layerIdx = 0, ringIdx = 0, ringOff = 0;
-		for (int a = 0; a < M.numArrays; a++)
-		{
-			const WaveNetArrayDesc& A = desc.arrays[a];
-			WnArray& DA = M.arrays[a];
-			const int C = A.channels, CP = TcPad(C), KC = CP / 4;
-			const int last = a + 1 == M.numArrays;
-			const int inC = A.inputSize, inCP = a == 0 ? 1 : TcPad(inC);
-			const int H = A.headSize, HP = last ? 1 : TcPad(H);
-			const int nL = (int)A.dilations.size();
-			DA.C = CP; DA.inC = inCP; DA.H = HP; DA.Kh = 1; DA.act = A.activation;
-			DA.firstLayer = layerIdx; DA.numLayers = nL; DA.realC = C; DA.realH = H;
-			const float* wRe = w; w += (size_t)C * inC;
-			std::vector<const float*> wLayer(nL);
-			for (int l = 0; l < nL; l++)
-			{
-				wLayer[l] = w;
-				w += (size_t)C * C * A.kernelSizes[l] + C + C + (size_t)C * C + C;
-			}
-			const float* wHead = w; w += (size_t)H * C + (A.headBias ? H : 0);
-			for (int l = 0; l < nL; l++)
-			{
-				WnLayer& L = M.layers[layerIdx];
-				const int K = A.kernelSizes[l], d = A.dilations[l];
-				L.K = K; L.d = d; L.array = a;
-				L.Lp = (K - 1) * d;
-				L.ringOff = ringOff; L.ringIdx = ringIdx;
-				M.ringLp[ringIdx] = L.Lp;
-				ringOff += CP * L.Lp; ringIdx++;
-				L.flags = 0;
-				if (l == 0) L.flags |= kFirstInArray;
-				if (l == nL - 1) L.flags |= kLastInArray;
-				if (!(last && M.numArrays > 1 && l == nL - 1)) L.flags |= kNeedOutput;
-				int off = 0;
-				const int oConvHi = off; off += K * KC * CP * 4;
-				L.oConvLo = off; off += K * KC * CP * 4;
-				L.oOneW = off; off += KC * CP * 4;
-				L.oOneLo = off; off += KC * CP * 4;
-				L.oConvB = off; off += CP;
-				L.oMix = off; off += CP;
-				L.oOneB = off; off += CP;
-				L.oRe = off; if (l == 0) off += Align4(inCP * CP);
-				L.oHeadW = off; if (l == nL - 1) off += Align4(CP * HP);
-				L.oHeadB = off; if (l == nL - 1) off += Align4(HP);
-				L.wSize = Align4(off);
-				L.wOff = (int)P.weights.size();
-				P.weights.resize(P.weights.size() + L.wSize, 0.0f);
-				float* blk = P.weights.data() + L.wOff;
-				if (L.wSize > M.maxBlock) M.maxBlock = L.wSize;
-				const float* src = wLayer[l];
-				// conv file order [out][in][k] (WaveNet.h:99-105) -> [k][in/4][out][in%4], split hi/lo
-				for (int i = 0; i < C; i++)
-					for (int j = 0; j < C; j++)
-						for (int k = 0; k < K; k++)
-						{
-							const float v = *src++, hi = RoundTf32(v);
-							const int at = ((k * KC + j / 4) * CP + i) * 4 + (j % 4);
-							blk[oConvHi + at] = hi;
-							blk[L.oConvLo + at] = v - hi;
-						}
-				for (int i = 0; i < C; i++) blk[L.oConvB + i] = *src++;
-				for (int i = 0; i < C; i++) blk[L.oMix + i] = *src++;
-				for (int i = 0; i < C; i++)
-					for (int j = 0; j < C; j++)
-					{
-						const float v = *src++, hi = RoundTf32(v);
-						const int at = ((j / 4) * CP + i) * 4 + (j % 4);
-						blk[L.oOneW + at] = hi;
-						blk[L.oOneLo + at] = v - hi;
-					}
-				for (int i = 0; i < C; i++) blk[L.oOneB + i] = *src++;
-				if (l == 0)
-					for (int i = 0; i < C; i++)
-						for (int j = 0; j < inC; j++) blk[L.oRe + j * CP + i] = wRe[i * inC + j];
-				if (l == nL - 1)
-				{
-					const float* hs = wHead;
-					for (int i = 0; i < H; i++)
-						for (int j = 0; j < C; j++) blk[L.oHeadW + j * HP + i] = *hs++;
-					if (A.headBias)
-						for (int i = 0; i < H; i++) blk[L.oHeadB + i] = *hs++;
-				}
-				layerIdx++;
-			}
-		}
-		M.headScale = *w;
-		M.numLayers = layerIdx;
-		M.numRings = ringIdx;
-		M.stateStride = Align4(ringOff);
-		return P;
-	}
-
 	// ---- TMEM-operand packing (wavenet_ts_kernels.cu) --------------------------------------------------------------
 	bool WaveNetTsSupported(const WaveNetDesc& desc)
 	{

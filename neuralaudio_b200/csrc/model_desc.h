@@ -68,9 +68,6 @@ namespace nab200
 	};
 
 	PackedWaveNet PackWaveNet(const WaveNetDesc& desc);
-	// tensor-core (tcgen05) packing; TcSupported tells whether the architecture fits that kernel
-	bool WaveNetTcSupported(const WaveNetDesc& desc);
-	PackedWaveNet PackWaveNetTc(const WaveNetDesc& desc);
 	// TMEM-operand (tcgen05 "TS") packing: conv taps, 1x1, mix-in, biases, rechannel and head all as tensor-core B operands
 	bool WaveNetTsSupported(const WaveNetDesc& desc);
 	PackedWaveNet PackWaveNetTs(const WaveNetDesc& desc);

@@ -50,13 +50,10 @@ namespace nab200
 		int realC, realH;
 	};
 
-	// Tensor-core packing (WnModelDev::tc == 1), used by wavenet_tc_kernels.cu:
-	//   rings are [C/4][Lp][4] (channel-group major, a frame's 4 channels contiguous) so a window lands in shared memory
-	//   directly in the tcgen05 K-major operand layout and a tap shift is a 16-byte row offset;
-	//   block = convHi[K][C/4][C][4] | convLo | oneHi[C/4][C][4] | oneLo | convB[C] | mix[C] | oneB[C] | re[inC][C] | headW[C][H] | headB[H]
-	//   where X[kc][n][i] = W[out n][in 4*kc+i], hi = tf32-rounded weight, lo = weight - hi.
+	// Tensor-core ring layout (tc >= 2): [C/4][Lp][4] (channel-group major, a frame's 4 channels - or packed pairs - contiguous),
+	// so a window lands in shared memory as conflict-free 16-byte rows and a tap shift is a row offset.
 	//
-	// TMEM-operand packing (WnModelDev::tc == 2), used by wavenet_ts_kernels.cu.  Rings as for tc == 1.  Every matrix is a
+	// TMEM-operand packing (WnModelDev::tc == 2), used by wavenet_ts_kernels.cu.  Every matrix is a
 	// tcgen05 B operand [k/4][n][4] (K-major, no swizzle), split hi = tf32-rounded / lo = w - hi.  N1 = C + 8 (1x1 | head).
 	//   block = convHi[K][C/4][C][4] | convLo (oConvLo) | convC[2][C][4] (oConvB) | oneHi[C/4][N1][4] (oOneW) | oneLo (oOneLo)
 	//           | oneC[2][N1][4] (oOneB) | first layer of an array only (oRe): array 0: reC[2][C][4] | hdC[2][8][4]
@@ -72,7 +69,7 @@ namespace nab200
 		int stateStride;     // floats of ring state per stream (multiple of 4)
 		int maxBlock;        // largest weight block in floats
 		float headScale;
-		int tc;              // 0 CUDA-core packing, 1 / 2 tcgen05 3xTF32 packings, 3 tcgen05 fp16-pair packing (HLayer table)
+		int tc;              // 0 CUDA-core packing, 2 tcgen05 3xTF32 packing (TMEM operands), 3 tcgen05 fp16-pair packing (HLayer table)
 		int pad0;
 		WnArray arrays[kMaxArrays];
 		WnLayer layers[kMaxLayers];

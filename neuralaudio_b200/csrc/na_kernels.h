@@ -37,7 +37,6 @@ namespace nab200
 		int n;                  // frames this pass (<= wavenet_max_frames_per_pass)
 		int numSMs;
 		bool useTma;
-		int tsIssuers = 4;      // (unused since the TS kernel has a dedicated issuer warp)
 		int tsSplit = 0;        // TS kernel: one launch per layer array (needs `scratch`)
 		float* scratch = nullptr;   // TS split launch: [S][wavenet_ts_scratch_floats_per_stream()] floats
 		int ctasPerSM = 0;      // H kernel: streams in flight per SM (0: default)
@@ -46,9 +45,6 @@ namespace nab200
 	};
 
 	cudaError_t wavenet_launch(const WnModelDev& M, const WnLaunch& a);
-	// tcgen05 path (WnModelDev::tc == 1 packing), n <= 128
-	cudaError_t wavenet_tc_launch(const WnModelDev& M, const WnLaunch& a);
-	bool wavenet_tc_variant_supported(int C0, int C1, int act);
 	// tcgen05 path with TMEM A operands (WnModelDev::tc == 2 packing), n <= 128
 	cudaError_t wavenet_ts_launch(const WnModelDev& M, const WnLaunch& a);
 	bool wavenet_ts_variant_supported(int C0, int C1, int act);

@@ -404,6 +404,14 @@ inline namespace b200
 	// ---- loader (NeuralModelLoader::CreateFrom*, NeuralModel.cpp:319-581, Internal branch only) ------------------
 	static B200ModelImpl* CreateImplFromJson(NeuralModelLoader* loader, Json& modelJson, const std::string& extension, bool isSubmodel);
 
+	// process-wide defaults, then this loader's own knobs
+	static nab200::Options LoaderOptions(NeuralModelLoader* loader)
+	{
+		nab200::Options o = nab200::GetOptions();
+		if (loader) for (const auto& kv : loader->GetOptionOverrides()) nab200::ApplyOption(o, kv.first.c_str(), kv.second);
+		return o;
+	}
+
 	static B200EngineModel* MakeWaveNet(NeuralModelLoader* loader, const Json& modelJson)
 	{
 		nab200::WaveNetDesc desc = nab200::ParseNamWaveNet(modelJson);   // throws on malformed / unsupported
@@ -413,12 +421,13 @@ inline namespace b200
 		model->isStatic = desc.isStatic;
 		// only the static adapters override GetReceptiveFieldSize (InternalModel.h:99-102); dynamic models report -1
 		model->receptiveField = desc.isStatic ? desc.receptiveField : -1;
-		const int tcOpt = nab200::GetOptions().useTc;
+		const nab200::Options opts = LoaderOptions(loader);
+		const int tcOpt = opts.useTc;
 		const bool useH = tcOpt >= 3 && nab200::WaveNetHSupported(desc);
 		const bool useTs = !useH && tcOpt >= 2 && nab200::WaveNetTsSupported(desc);
-		const bool useTc = !useH && !useTs && tcOpt >= 1 && nab200::WaveNetTcSupported(desc);
 		auto* engine = new nab200::WaveNetEngine(loader->GetDevice(),
-			useH ? nab200::PackWaveNetH(desc) : useTs ? nab200::PackWaveNetTs(desc) : useTc ? nab200::PackWaveNetTc(desc) : nab200::PackWaveNet(desc));
+			useH ? nab200::PackWaveNetH(desc) : useTs ? nab200::PackWaveNetTs(desc) : nab200::PackWaveNet(desc));
+		engine->opt = opts;
 		model->engine = engine;
 		if (!engine->Init() || !engine->Upload()) { delete model; return nullptr; }
 		return model;
@@ -441,6 +450,7 @@ inline namespace b200
 		model->isStatic = desc.isStatic;
 		model->receptiveField = -1;
 		auto* engine = new nab200::LstmEngine(loader->GetDevice(), nab200::PackLstm(desc));
+		engine->opt = LoaderOptions(loader);
 		model->engine = engine;
 		if (!engine->Init() || !engine->Upload()) { delete model; return nullptr; }
 		return model;

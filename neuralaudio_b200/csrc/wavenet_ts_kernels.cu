@@ -74,18 +74,29 @@ namespace nab200
 
 		// try_wait blocks in hardware for a bounded time before it reports failure, so the loop rarely iterates.  (Passing
 		// an explicit suspend-time hint made ptxas emit TRYWAIT + NANOSLEEP.SYNCS + PHASECHK per iteration and the waiting
-		// warps then spent a third of the SM's issue slots spinning - ncu, round 1.)
-		__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+		// warps then spent a third of the SM's issue slots spinning - ncu, round 1.)  The loop gives up after 2^22 failed tries
+		// (seconds): a faulted bulk copy or a lost commit then surfaces as the engine's sticky error word instead of a hung device.
+		__device__ __forceinline__ bool mbar_wait_bounded(uint32_t bar, uint32_t parity)
 		{
+			uint32_t done;
 			asm volatile(
 				"{\n"
 				".reg .pred P1;\n"
-				"LAB_WAIT:\n"
-				"mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-				"@P1 bra DONE;\n"
-				"bra LAB_WAIT;\n"
-				"DONE:\n"
-				"}" ::"r"(bar), "r"(parity) : "memory");
+				".reg .u32 it;\n"
+				"mov.u32 it, 0;\n"
+				"WAIT_%=:\n"
+				"mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+				"@P1 bra DONE_%=;\n"
+				"add.u32 it, it, 1;\n"
+				"setp.lt.u32 P1, it, 4194304;\n"
+				"@P1 bra WAIT_%=;\n"
+				"mov.u32 %0, 0;\n"
+				"bra END_%=;\n"
+				"DONE_%=:\n"
+				"mov.u32 %0, 1;\n"
+				"END_%=:\n"
+				"}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+			return done != 0;
 		}
 
 		__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar)
@@ -367,6 +378,7 @@ namespace nab200
 			int cur;           // which hdb half belongs to the current stream
 			int lBegin, lEnd;  // layers this kernel runs (the fused kernel: all; the split kernels: one array each)
 			int a1First;       // first layer of array 1
+			int* err;          // sticky device error word (mapped host memory)
 #ifdef NAB_TS_TIMING
 			bool stampOn; int stampCta, stampStream;
 #endif
@@ -388,10 +400,15 @@ namespace nab200
 			fence_after();
 		}
 
-		// issuer: the MMAs committed to `bar` are complete -> release the stagers blocked on named barrier `id`
-		__device__ __forceinline__ void issuer_release(uint32_t bar, uint32_t parity, int id)
+		__device__ __forceinline__ void mbar_wait(const Ctx& cx, uint32_t bar, uint32_t parity)
 		{
-			mbar_wait(bar, parity);
+			if (!mbar_wait_bounded(bar, parity) && cx.el && cx.err) *reinterpret_cast<volatile int*>(cx.err) = 1;
+		}
+
+		// issuer: the MMAs committed to `bar` are complete -> release the stagers blocked on named barrier `id`
+		__device__ __forceinline__ void issuer_release(const Ctx& cx, uint32_t bar, uint32_t parity, int id)
+		{
+			mbar_wait(cx, bar, parity);
 			nbar_arrive(id);
 		}
 
@@ -773,7 +790,7 @@ namespace nab200
 				}
 				__syncwarp();
 				TS_STAMP(6);
-				issuer_release(cx.barD, cx.dq & 1u, kBarDReady);
+				issuer_release(cx, cx.barD, cx.dq & 1u, kBarDReady);
 				cx.dq++;
 				// the stagers saw the previous layer complete long ago: the other weight buffer is free for the next block
 				if (cx.el) issue_weights(cx, (l + 1 < cx.lEnd) ? l + 1 : cx.lBegin, cx.wq + 1);
@@ -781,7 +798,7 @@ namespace nab200
 				TS_STAMP(7);
 				// the next layer's weights are needed right behind the 1x1 (below); they were requested a whole layer ago
 				const bool more = li + 1 < numLayers;
-				if (more) mbar_wait(cx.barW0 + 8u * ((cx.wq + 1) & 1u), ((cx.wq + 1) >> 1) & 1u);
+				if (more) mbar_wait(cx, cx.barW0 + 8u * ((cx.wq + 1) & 1u), ((cx.wq + 1) >> 1) & 1u);
 
 				if (ARRAY == 2 && !more)
 				{
@@ -811,7 +828,7 @@ namespace nab200
 					__syncwarp();
 				}
 				TS_STAMP(9);
-				issuer_release(cx.barX, cx.xq & 1u, kBarXReady);
+				issuer_release(cx, cx.barX, cx.xq & 1u, kBarXReady);
 				cx.xq++;
 				if (more && cx.el)
 				{
@@ -854,7 +871,7 @@ namespace nab200
 		__global__ void __launch_bounds__(kThreads, MODE == 2 ? 6 : 4)
 			wavenet_ts_kernel(const __grid_constant__ WnModelDev M, const float* __restrict__ Wg, float* __restrict__ state, int* __restrict__ heads,
 				const float* in, float* out, long long inSS, long long inFS, long long outSS, long long outFS, int S, int n,
-				float* __restrict__ scratch, int wbufFloats)
+				float* __restrict__ scratch, int wbufFloats, int* __restrict__ err)
 		{
 			constexpr int kPlanes = MODE == 2 ? 2 : 4;
 			constexpr uint32_t kTmem = MODE == 2 ? 64 : 128;
@@ -883,6 +900,8 @@ namespace nab200
 			cx.S = S;
 			cx.gstride = gridDim.x;
 			cx.state = state;
+			cx.err = err;
+			cx.err = err;
 			cx.wq = 0; cx.dq = 0; cx.xq = 0; cx.cur = 0;
 			cx.el = elect_one();
 			const int tid = threadIdx.x;
@@ -976,7 +995,7 @@ namespace nab200
 					if constexpr (MODE != 2)
 					{
 						// ---- entry: rechannel 1 -> C0 and head bias from the constant operand ----
-						mbar_wait(cx.barW0 + 8u * (cx.wq & 1u), (cx.wq >> 1) & 1u);
+						mbar_wait(cx, cx.barW0 + 8u * (cx.wq & 1u), (cx.wq >> 1) & 1u);
 						issuer_sync(kBarE);
 						if (cx.el)
 						{
@@ -986,14 +1005,14 @@ namespace nab200
 							mma_commit(cx.barX);
 						}
 						__syncwarp();
-						issuer_release(cx.barX, cx.xq & 1u, kBarXReady);
+						issuer_release(cx, cx.barX, cx.xq & 1u, kBarXReady);
 						cx.xq++;
 						issue_array<0>(cx, first0, num0);
 					}
 					if constexpr (MODE == 0)
 					{
 						// ---- array transition (WaveNet.h:785-789): rechannel C0 -> C1 of the array output, head carry ----
-						mbar_wait(cx.barW0 + 8u * (cx.wq & 1u), (cx.wq >> 1) & 1u);
+						mbar_wait(cx, cx.barW0 + 8u * (cx.wq & 1u), (cx.wq >> 1) & 1u);
 						issuer_sync(kBarE);
 						if (cx.el)
 						{
@@ -1015,14 +1034,14 @@ namespace nab200
 							mma_commit(cx.barX);
 						}
 						__syncwarp();
-						issuer_release(cx.barX, cx.xq & 1u, kBarXReady);
+						issuer_release(cx, cx.barX, cx.xq & 1u, kBarXReady);
 						cx.xq++;
 						issue_array<1>(cx, first1, num1);
 					}
 					if constexpr (MODE == 2)
 					{
 						// ---- entry: rechannel C0 -> C1 of array 0's output, staged [hi 16 | lo 16] at the tap columns ----
-						mbar_wait(cx.barW0 + 8u * (cx.wq & 1u), (cx.wq >> 1) & 1u);
+						mbar_wait(cx, cx.barW0 + 8u * (cx.wq & 1u), (cx.wq >> 1) & 1u);
 						issuer_sync(kBarE);
 						if (cx.el)
 						{
@@ -1039,14 +1058,14 @@ namespace nab200
 							mma_commit(cx.barX);
 						}
 						__syncwarp();
-						issuer_release(cx.barX, cx.xq & 1u, kBarXReady);
+						issuer_release(cx, cx.barX, cx.xq & 1u, kBarXReady);
 						cx.xq++;
 						issue_array<2>(cx, first1, num1);
 					}
 					cx.cur ^= 1;
 				}
 				// drain the weight prefetch that ran ahead of the last layer
-				mbar_wait(cx.barW0 + 8u * (cx.wq & 1u), (cx.wq >> 1) & 1u);
+				mbar_wait(cx, cx.barW0 + 8u * (cx.wq & 1u), (cx.wq >> 1) & 1u);
 			}
 			else
 			{
@@ -1219,7 +1238,7 @@ namespace nab200
 		if (grid > a.S) grid = a.S;
 		if (grid < 1) grid = 1;
 		kfn<<<grid, ts::kThreads, smem, a.stream>>>(M, a.weights, a.state, a.heads, a.in, a.out, a.inSS, a.inFS, a.outSS, a.outFS, a.S, a.n,
-			a.scratch, wbufFloats);
+			a.scratch, wbufFloats, a.err);
 		return cudaGetLastError();
 	}
 

@@ -248,7 +248,7 @@ def test_tensor_core_and_cuda_core_kernels_agree(na, O, name, tmp_path):
     S, n, calls = 12, 128, 10
     x = np.random.default_rng(17).uniform(-1, 1, (calls, S, n)).astype(np.float32)
     outs = []
-    for tc in (2, 1, 0, 3):   # 3xTF32 TMEM-operand tcgen05 kernel, shared-memory-operand tcgen05 kernel, CUDA-core kernel, fp16-pair tcgen05 kernel (default)
+    for tc in (2, 0, 3):   # 3xTF32 TMEM-operand tcgen05 kernel, CUDA-core kernel, fp16-pair tcgen05 kernel (default)
         prev = na.set_option("use_tc", tc)
         try:
             m = _load(na, mf, streams=S)
@@ -258,9 +258,8 @@ def test_tensor_core_and_cuda_core_kernels_agree(na, O, name, tmp_path):
             outs.append(y)
         finally:
             na.set_option("use_tc", prev)
-    assert float(np.abs(outs[0] - outs[2]).max()) <= 4e-6
-    assert float(np.abs(outs[1] - outs[2]).max()) <= 2e-6
-    assert float(np.abs(outs[3] - outs[2]).max()) <= 4e-6
+    assert float(np.abs(outs[0] - outs[1]).max()) <= 4e-6
+    assert float(np.abs(outs[2] - outs[1]).max()) <= 4e-6
     for s in (0, S - 1):
         ys = O.PortModel.from_file(mf).process(np.ascontiguousarray(x[:, s, :]).reshape(-1))
         for y in outs:
