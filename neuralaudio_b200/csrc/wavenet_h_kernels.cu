@@ -63,16 +63,32 @@ namespace nab200
 			uint32_t wbuf, wbufStride;    // two weight buffers
 			uint32_t tab;                 // HLayer table
 			int* hdb;                     // [2][kHdbHalf] ring heads of the current / next stream
-			uint32_t barW0, barD, barX;
+			uint32_t barW0, barD, barX, barWin;   // barWin: this layer's history windows have landed (TMA bulk copies)
 			uint32_t r0, r1, r2;          // TMEM: three 32-column regions
 			int n, tid, warp, S, gstride, numLayers;
 			bool el;
 			uint32_t wq, dq, xq;          // issuer: weight-block counter, barD / barX phase counters
+			uint32_t winq;                // stagers: window phase counter (one per layer)
 			int cur;
 			int* err;
 			char* sbase;                  // stagers: this stream's state
 			bool hasNext;                 // stagers: the CTA has another stream after this one
+#ifdef NAB_H_TIMING
+			bool stampOn; int stampCta, stampStream;
+#endif
 		};
+
+#ifdef NAB_H_TIMING
+		// tools/h_timing.cu: cycle stamps of one thread per warp of a few CTAs, [cta][warp][stream][layer][stamp]
+		__device__ long long g_stamps[4][5][4][32][12];
+#define H_STAMP(i) do { if (cx.stampOn) g_stamps[cx.stampCta][cx.warp][cx.stampStream][l][i] = clock64(); } while (0)
+#define H_STAMP_SELECT(s, s0) do { const int k_ = ((s) - (s0)) / (int)gridDim.x; \
+		const int c_ = blockIdx.x == 0 ? 0 : blockIdx.x == 1 ? 1 : blockIdx.x == 300 ? 2 : blockIdx.x == gridDim.x - 1 ? 3 : -1; \
+		cx.stampOn = (threadIdx.x & 31) == 0 && c_ >= 0 && k_ >= 1 && k_ < 5; cx.stampCta = c_ < 0 ? 0 : c_; cx.stampStream = k_ - 1; } while (0)
+#else
+#define H_STAMP(i) do { } while (0)
+#define H_STAMP_SELECT(s, s0) do { } while (0)
+#endif
 
 		// TMEM column maps.  CONST (8 columns) is always r2 + 24.
 		//   ROLE 0: first array, 16 channels, 8 head columns:  taps r0 + 16 j | T2 r1 | D r1 + 16 | XR r2 | HD r2 + 16
@@ -148,49 +164,60 @@ namespace nab200
 			bulk_g2s(cx.wbuf + (slot & 1u) * cx.wbufStride, cx.Wg + off, bytes, bar);
 		}
 
-		// Every stager thread: my rows of the history window(s) of layer l of stream s, HBM ring -> shared memory, with
-		// cp.async (16 bytes per plane and row; consecutive threads <-> consecutive rows, so a warp moves contiguous 512-byte
-		// runs); one cp.async group per layer.
-		template <int CG>
-		__device__ __forceinline__ void prefetch_windows(const Ctx& cx, int l, const char* sbase, const int* hd)
+		// Stager warps (all 128 threads call it): the history window(s) of layer l of the stream whose state starts at `sbase`,
+		// HBM ring -> shared memory, as TMA bulk copies.  A window job is rows r in [0, cnt) <- ring rows (head - back + r) mod Lp:
+		// at most two contiguous runs per 16-byte plane, i.e. numJobs x planes x 2 copies per layer (<= 20), dealt to lanes 0..4 of
+		// the four warps; every copy completes on barWin (4 arrivals, one per warp, + the bytes).
+		// (Round 2 profile: per-thread cp.async copies cost ~105 issued instructions per warp and layer - 8 LDGSTS, their 64-bit
+		// address arithmetic and 24 predicated-off fillers - in an issue-bound kernel; this costs ~30.)
+		__device__ __forceinline__ void request_windows(const Ctx& cx, int l, const char* sbase, const int* hd)
 		{
+#ifdef NAB_H_NO_WINDOWS   // timing experiment only (tools/h_timing.cu): results are wrong
+			if ((cx.tid & 31) == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(cx.barWin) : "memory");
+			return;
+#endif
 			const uint32_t la = cx.tab + (uint32_t)l * (uint32_t)sizeof(HLayer);
 			const uint4 g0 = lds128(la), g1 = lds128(la + 16);
-			const int Lp = (int)g0.z, numJobs = (int)g1.y;
-			const int head = hd[g1.x];
-			const char* ring = sbase + (size_t)g0.w * 4;
-#pragma unroll 1
-			for (int jb = 0; jb < numJobs; jb++)
+			const int Lp = (int)g0.z, numJobs = (int)g1.y, CG = (int)g1.w >> 2;
+			const int lane = cx.tid & 31;
+			const int c = lane * 4 + cx.warp;
+			if (lane < 8 && c < numJobs * CG * 2)
 			{
+				const int head = hd[g1.x];
+				const int jb = c / (2 * CG), rem = c - jb * 2 * CG, g = rem >> 1, run = rem & 1;
 				const uint4 jj = lds128(la + kTabJobs + 16u * (uint32_t)jb);
 				const int cnt = (int)jj.x < 0 ? cx.n : (int)jj.x;
-				int idx = head - (int)jj.y + cx.tid;                       // in [-Lp, Lp): one conditional wrap
-				uint32_t dst = cx.win + jj.z + (uint32_t)cx.tid * 16u;
-#pragma unroll 1
-				for (int r = cx.tid; r < cnt; r += kStagers, idx += kStagers, dst += kStagers * 16u)
+				int start = head - (int)jj.y;
+				if (start < 0) start += Lp;
+				const int run1 = cnt < Lp - start ? cnt : Lp - start;
+				const int rows = run == 0 ? run1 : cnt - run1;
+				const int srcRow = run == 0 ? start : 0, dstRow = run == 0 ? 0 : run1;
+				if (rows > 0)
 				{
-					const int i2 = idx < 0 ? idx + Lp : idx;
-#pragma unroll
-					for (int g = 0; g < CG; g++) cp_async16(dst + (uint32_t)g * cx.planeStride, ring + (size_t)(uint32_t)(i2 + g * Lp) * 16);
+					const uint32_t bytes = (uint32_t)rows * 16u;
+					asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(cx.barWin), "r"(bytes) : "memory");
+					bulk_g2s(cx.win + jj.z + (uint32_t)g * cx.planeStride + (uint32_t)dstRow * 16u,
+						sbase + (size_t)g0.w * 4 + (size_t)(uint32_t)(g * Lp + srcRow) * 16, bytes, cx.barWin);
 				}
 			}
-			cp_async_commit();
+			__syncwarp();
+			if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(cx.barWin) : "memory");
 		}
 
-		// history of layer l counted from the first layer of this stream (l may run past the last layer: next stream)
-		__device__ __forceinline__ void prefetch_layer(const Ctx& cx, int l, int a1First)
+		// windows of the layer after l (the next layer of this stream, or the first layer of the CTA's next stream)
+		__device__ __forceinline__ void request_next_windows(const Ctx& cx, int l)
 		{
+			int nl = l + 1;
 			const int* hd = cx.hdb + cx.cur * kHdbHalf;
-			const char* sbase = cx.sbase;
-			if (l >= cx.numLayers)
+			const char* sb = cx.sbase;
+			if (nl >= cx.numLayers)
 			{
-				l = 0;
+				if (!cx.hasNext) return;
+				nl = 0;
 				hd = cx.hdb + (cx.cur ^ 1) * kHdbHalf;
-				if (!cx.hasNext) { cp_async_commit(); return; }
-				sbase = cx.sbase + (size_t)cx.gstride * ((size_t)cx.M->stateStride * 4);
+				sb = cx.sbase + (size_t)cx.gstride * ((size_t)cx.M->stateStride * 4);
 			}
-			if (l < a1First) prefetch_windows<4>(cx, l, sbase, hd);   // a1First = 0 for a single 8-channel array
-			else prefetch_windows<2>(cx, l, sbase, hd);
+			request_windows(cx, nl, sb, hd);
 		}
 
 		// C fp32 values -> C words [h1 of channel pairs | h2 of channel pairs]
@@ -254,7 +281,9 @@ namespace nab200
 				const bool mixed = g0.y != 0;
 
 				// ---- the residual stream after the previous layer -> packed pairs: undelayed tap, current rows, ring ----
+				H_STAMP(0);
 				stager_wait<kBarXReady>();
+				H_STAMP(1);
 				uint32_t p[C];
 				{
 					uint32_t x[C];
@@ -269,10 +298,14 @@ namespace nab200
 					for (int q = 0; q < CG; q++) sts128(cur + (uint32_t)q * cx.planeStride, p[4 * q], p[4 * q + 1], p[4 * q + 2], p[4 * q + 3]);
 				}
 				stager_arrive<kBarT2>();
-				// my copies of this layer's history have landed; where a tap mixes history and current frames the rows other
-				// threads copied / produced must be visible too
-				cp_async_wait_all();
+				H_STAMP(2);
+				// this layer's history windows have landed (the issuer's bulk copies); where a tap mixes history and current frames the
+				// rows the other stagers produced must be visible too
+				if (!mbar_wait(cx.barWin, cx.winq & 1u) && cx.tid == 0) *reinterpret_cast<volatile int*>(cx.err) = 1;
+				cx.winq++;
+				H_STAMP(3);
 				if (mixed) nbar_sync<kBarMix, kStagers>();
+				H_STAMP(4);
 				// ---- delayed taps: my row of each, shared memory -> TMEM, no arithmetic ----
 				if (numTaps == NT)
 				{
@@ -323,14 +356,21 @@ namespace nab200
 						stager_arrive<kBarTaps>();
 					}
 				}
+				H_STAMP(5);
 				// every stager is done with this layer's windows: request the next layer's (or the next stream's first layer's)
 				nbar_sync<kBarMix, kStagers>();
-				prefetch_layer(cx, l + 1, a1First);
+				H_STAMP(9);
+				request_next_windows(cx, l);
+				H_STAMP(10);
 				// history write-back (AdvanceFrames, WaveNet.h:59-65): frame t becomes ring row (head + t) mod Lp
 				{
 					const int Lp = (int)g0.z;
 					const int first = cx.n > Lp ? cx.n - Lp : 0;
+#ifdef NAB_H_NO_RINGWRITE   // timing experiment only
+					if (false)
+#else
 					if (tid < cx.n && tid >= first)
+#endif
 					{
 						int idx = (cx.n > Lp ? hd[36 + g1.x] : hd[g1.x]) + (tid - first);
 						if (idx >= Lp) idx -= Lp;
@@ -342,7 +382,9 @@ namespace nab200
 				}
 
 				// ---- activation (WaveNet.h:477-480); z -> packed pairs -> TMEM as the A operand of the 1x1 ----
+				H_STAMP(6);
 				stager_wait<kBarDReady>();
+				H_STAMP(7);
 				{
 					uint32_t dv[C], z[C];
 					tmem_ld<C>(lane + MP::d(cx), dv);
@@ -356,6 +398,7 @@ namespace nab200
 					tmem_st<C>(lane + MP::tap(cx, 0), dv);
 				}
 				stager_arrive<kBarZ>();
+				H_STAMP(8);
 			}
 		}
 
@@ -401,19 +444,24 @@ namespace nab200
 				if (numGroups == 1 && numTaps == NT)
 				{
 					// the common shape (K = 3 / K = 6): one weight block, every product's descriptor known before the hand-offs
+					H_STAMP(0);
 					if (li > 0) issuer_wait(cx, cx.barW0 + 8u * (cx.wq & 1u), (cx.wq >> 1) & 1u);
 					if (cx.el) issue_weights(cx, (l + 1 < cx.numLayers) ? l + 1 : 0, 0, cx.wq + 1);
 					__syncwarp();
 					wb16 = (cx.wbuf + (cx.wq & 1u) * cx.wbufStride) >> 4;
 					const uint32_t tb16 = wb16 + tap0Base16;
+					H_STAMP(1);
 					issuer_sync<kBarT2>();
+					H_STAMP(2);
 					if (cx.el)
 					{
 						mma_pairs<C, 0>(MP::d(cx), MP::t2(cx), wb16 + und16, C);   // overwrites the accumulator
 						mma_f16_ts<1>(MP::d(cx), konst(cx), desc_at(wb16 + g3.x, C), idesc_f16(C));
 					}
 					__syncwarp();
+					H_STAMP(3);
 					issuer_sync<kBarTaps>();
+					H_STAMP(4);
 					if (cx.el)
 					{
 #pragma unroll
@@ -421,7 +469,9 @@ namespace nab200
 						mma_commit(cx.barD);
 					}
 					__syncwarp();
+					H_STAMP(5);
 					issuer_release<kBarDReady>(cx, cx.barD, cx.dq & 1u);
+					H_STAMP(6);
 					cx.dq++;
 				}
 				else
@@ -470,6 +520,7 @@ namespace nab200
 
 				// ---- 1x1 + bias + residual, head sum (WaveNet.h:482-491): XR | HD += [z] [W1x1 | Whead] ----
 				issuer_sync<kBarZ>();
+				H_STAMP(7);
 				if (cx.el)
 				{
 					mma_f16_ts<1>(MP::xr(cx), konst(cx), desc_at(wb16 + g3.w, N1), idesc_f16(N1));
@@ -487,13 +538,15 @@ namespace nab200
 					mma_commit(cx.barX);
 				}
 				__syncwarp();
+				H_STAMP(8);
 				issuer_release<kBarXReady>(cx, cx.barX, cx.xq & 1u);
+				H_STAMP(9);
 				cx.xq++;
 				cx.wq++;
 			}
 		}
 
-		constexpr int kNumBars = 4;
+		constexpr int kNumBars = 6;   // W0, W1, D, X, Win (+ one slot of padding: what follows is read with 16-byte copies)
 		constexpr int kHeadTaps = 16;                           // A2 head conv kernel size (WaveNet.h:658-660, InternalModel.h:12-20)
 		constexpr int kHeadHistFloats = kHeadTaps * 16;         // per stream: [tap][16 frames] of per-tap head products (15 used)
 		constexpr int kHeadRows = kCur + kHeadTaps - 1;         // scratch rows per tap plane: 15 history + 128 current
@@ -526,13 +579,14 @@ namespace nab200
 			cx.barW0 = smem_u32(&bars[0]);
 			cx.barD = smem_u32(&bars[2]);
 			cx.barX = smem_u32(&bars[3]);
+			cx.barWin = smem_u32(&bars[4]);
 			cx.n = n;
 			cx.tid = threadIdx.x;
 			cx.warp = threadIdx.x >> 5;
 			cx.S = S;
 			cx.gstride = gridDim.x;
 			cx.numLayers = M.numLayers;
-			cx.wq = 0; cx.dq = 0; cx.xq = 0; cx.cur = 0;
+			cx.wq = 0; cx.dq = 0; cx.xq = 0; cx.winq = 0; cx.cur = 0;
 			cx.el = elect_one();
 			const int tid = threadIdx.x, warp = cx.warp;
 			const bool stager = warp < 4;
@@ -552,6 +606,7 @@ namespace nab200
 				mbar_init(cx.barW0 + 8u, 1);
 				mbar_init(cx.barD, 1);
 				mbar_init(cx.barX, 1);
+				mbar_init(cx.barWin, 4);
 				asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 			}
 			if (warp == 4)
@@ -585,6 +640,7 @@ namespace nab200
 				if (cx.el) issue_weights(cx, 0, 0, 0);
 				for (int s = s0; s < S; s += gridDim.x)
 				{
+					H_STAMP_SELECT(s, s0);
 					// ---- entry: [XR | HD] = constant operand x [rechannel 1 -> C0 | head bias] (WaveNet.h:637) ----
 					issuer_wait(cx, cx.barW0 + 8u * (cx.wq & 1u), (cx.wq >> 1) & 1u);
 					issuer_sync<kBarE>();
@@ -631,16 +687,16 @@ namespace nab200
 			{
 				// =================================== stager warps ===================================
 				const uint32_t lane = (uint32_t)(warp * 32) << 16;
-				constexpr int CG0 = ARCH == 0 ? 4 : 2;
 				float cond = 0.0f;
 				if (tid < n && s0 < S) cond = in[(long long)s0 * inSS + (long long)tid * inFS];
 				const size_t strideBytes = (size_t)M.stateStride * 4;
 				cx.sbase = reinterpret_cast<char*>(state) + (size_t)s0 * strideBytes;
 				cx.hasNext = false;
-				if (s0 < S) prefetch_windows<CG0>(cx, 0, cx.sbase, cx.hdb);
+				if (s0 < S) request_windows(cx, 0, cx.sbase, cx.hdb);
 				for (int s = s0; s < S; s += gridDim.x)
 				{
 					const int sn = s + gridDim.x;
+					H_STAMP_SELECT(s, s0);
 					cx.hasNext = sn < S;
 					int* hdNext = cx.hdb + (cx.cur ^ 1) * kHdbHalf;
 					float condNext = 0.0f;
@@ -660,7 +716,7 @@ namespace nab200
 					float* const hist = reinterpret_cast<float*>(cx.sbase) + M.arrays[0].headRingOff;
 					if constexpr (ARCH == 1)
 					{
-						// this stream's head history -> shared memory, off the chain (its own cp.async group, awaited in the first layer)
+						// this stream's head history -> shared memory, off the chain (its own cp.async group, awaited before the output stage)
 						if (tid < kHeadHistFloats / 4) cp_async16(smem_u32(headHist) + (uint32_t)tid * 16u, hist + tid * 4);
 						cp_async_commit();
 					}
@@ -712,6 +768,7 @@ namespace nab200
 						// The shift across frames goes through shared memory, one conflict-free plane per tap: rows 0..14 = the last 15
 						// frames of the previous call (per-stream state), rows 15.. = this call; two halves of 8 taps share the scratch.
 						stager_wait<kBarXReady>();
+						cp_async_wait_all();   // the head history requested at the start of this stream
 						uint32_t g[16];
 						tmem_ld<16>(lane + Map<2>::hd(cx), g);
 						float acc = 0.0f;

@@ -1,0 +1,105 @@
+// Phase-level timing of the fp16-pair WaveNet kernel: builds an A1-Standard-shaped (or, with argv[2] = 1, A2-Full-shaped) model
+// with random weights, runs the kernel with cycle stamps compiled in (NAB_H_TIMING) and prints where one CTA's warps spend a
+// layer.  Not a correctness test.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -DNAB_H_TIMING -Iinclude -Ineuralaudio_b200/csrc \
+//        -o tools/h_timing tools/h_timing.cu neuralaudio_b200/csrc/model_desc.cpp -x cu
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include "../neuralaudio_b200/csrc/wavenet_h_kernels.cu"
+#include "../neuralaudio_b200/csrc/model_desc.h"
+using namespace nab200;
+
+int main(int argc, char** argv)
+{
+	const int S = argc > 1 ? atoi(argv[1]) : 4096, n = 128;
+	const bool a2 = argc > 2 && atoi(argv[2]) == 1;
+	const int ctas = argc > 3 ? atoi(argv[3]) : 0;
+	WaveNetDesc desc;
+	if (!a2)
+		for (int a = 0; a < 2; a++)
+		{
+			WaveNetArrayDesc A;
+			A.inputSize = a == 0 ? 1 : 16; A.channels = a == 0 ? 16 : 8; A.headSize = a == 0 ? 8 : 1; A.headKernel = 1; A.headBias = a == 1; A.activation = 0;
+			for (int d = 1; d <= 512; d *= 2) { A.dilations.push_back(d); A.kernelSizes.push_back(3); }
+			desc.arrays.push_back(A);
+		}
+	else
+	{
+		WaveNetArrayDesc A;
+		A.inputSize = 1; A.channels = 8; A.headSize = 1; A.headKernel = 16; A.headBias = true; A.activation = 1;
+		const int ks[23] = { 6, 6, 6, 6, 6, 6, 6, 6, 6, 6, 6, 6, 6, 6, 15, 15, 6, 6, 6, 6, 6, 6, 6 };
+		const int ds[23] = { 1, 3, 7, 17, 41, 101, 239, 1, 3, 7, 17, 41, 101, 239, 1, 13, 1, 3, 7, 17, 41, 101, 239 };
+		for (int i = 0; i < 23; i++) { A.kernelSizes.push_back(ks[i]); A.dilations.push_back(ds[i]); }
+		desc.arrays.push_back(A);
+	}
+	size_t nw = 1;
+	for (auto& A : desc.arrays)
+	{
+		nw += (size_t)A.channels * A.inputSize + (size_t)A.headSize * A.channels * A.headKernel + (A.headBias ? A.headSize : 0);
+		for (size_t l = 0; l < A.dilations.size(); l++) nw += (size_t)A.channels * A.channels * A.kernelSizes[l] + 2 * A.channels + (size_t)A.channels * A.channels + A.channels;
+	}
+	srand(1);
+	for (size_t i = 0; i < nw; i++) desc.weights.push_back(0.2f * ((float)rand() / RAND_MAX - 0.5f));
+	if (!WaveNetHSupported(desc)) { printf("shape not supported by the fp16-pair kernel\n"); return 1; }
+	PackedWaveNet P = PackWaveNetH(desc);
+	WnModelDev M = P.dev;
+	float *dW, *dState, *dIn, *dOut; int* dHeads; int* dErr;
+	cudaMalloc(&dW, P.weights.size() * 4); cudaMemcpy(dW, P.weights.data(), P.weights.size() * 4, cudaMemcpyHostToDevice);
+	cudaMalloc(&dState, (size_t)S * M.stateStride * 4); cudaMemset(dState, 0, (size_t)S * M.stateStride * 4);
+	cudaMalloc(&dHeads, (size_t)S * M.numRings * 4); cudaMemset(dHeads, 0, (size_t)S * M.numRings * 4);
+	cudaMalloc(&dIn, (size_t)S * n * 4); cudaMalloc(&dOut, (size_t)S * n * 4);
+	cudaMalloc(&dErr, 4); cudaMemset(dErr, 0, 4);
+	std::vector<float> hin((size_t)S * n);
+	for (auto& v : hin) v = 2.0f * rand() / RAND_MAX - 1.0f;
+	cudaMemcpy(dIn, hin.data(), hin.size() * 4, cudaMemcpyHostToDevice);
+	WnLaunch a;
+	a.weights = dW; a.state = dState; a.heads = dHeads; a.in = dIn; a.out = dOut;
+	a.inSS = n; a.inFS = 1; a.outSS = n; a.outFS = 1; a.S = S; a.n = n; a.numSMs = 148; a.useTma = true; a.stream = 0;
+	a.err = dErr; a.ctasPerSM = ctas;
+	cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+	for (int it = 0; it < 5; it++)
+	{
+		cudaEventRecord(e0);
+		cudaError_t err = wavenet_h_launch(M, a);
+		cudaEventRecord(e1);
+		cudaError_t e2 = cudaDeviceSynchronize();
+		if (err != cudaSuccess || e2 != cudaSuccess) { printf("error %s %s\n", cudaGetErrorString(err), cudaGetErrorString(e2)); return 1; }
+		float ms; cudaEventElapsedTime(&ms, e0, e1);
+		printf("S=%d launch %d: %.1f us (stamps compiled in)\n", S, it, ms * 1000);
+	}
+	static long long st[4][5][4][32][12];
+	cudaMemcpyFromSymbol(st, hk::g_stamps, sizeof(st));
+	const int NL = M.numLayers;
+	const char* stagerNames[8] = { "wait XR (1x1 done)", "ldXR+pack+stT2+arrive", "cp.async wait_group", "bar(mixed)", "taps LDS->STTM+arrive", "bar+prefetch+ring STG", "wait D (conv done)", "act+pack+stZ+arrive" };
+	const char* issuerNames[9] = { "wait W + issue next W", "wait T2", "T2+const MMAs", "wait taps", "tap MMAs+commit", "wait barD+release", "wait Z", "1x1 MMAs+commit", "wait barX+release" };
+	for (int c = 0; c < 4; c++)
+		for (int w : {0, 3, 4})
+		{
+			const int np = w == 4 ? 9 : 8;
+			printf("CTA slot %d warp %d (%s; mean cycles over 4 streams), per layer then mean:\n", c, w, w == 4 ? "issuer" : "stager");
+			for (int p = 0; p < np; p++)
+			{
+				printf("  %-24s", w == 4 ? issuerNames[p] : stagerNames[p]);
+				double tot = 0;
+				for (int l = 0; l < NL; l++)
+				{
+					double m = 0;
+					for (int k = 0; k < 4; k++) m += (double)(st[c][w][k][l][p + 1] - st[c][w][k][l][p]);
+					m /= 4; tot += m;
+					printf(" %5.0f", m);
+				}
+				printf("  | %6.0f\n", tot / NL);
+			}
+			if (w != 4)
+			{
+				double b = 0, r = 0, g = 0;
+				for (int l = 0; l < NL; l++) for (int k = 0; k < 4; k++) { b += (double)(st[c][w][k][l][9] - st[c][w][k][l][5]); r += (double)(st[c][w][k][l][10] - st[c][w][k][l][9]); g += (double)(st[c][w][k][l][6] - st[c][w][k][l][10]); }
+				printf("  split of 'bar+prefetch+ring STG': barrier %.0f | window requests %.0f | ring STG %.0f\n", b / (4 * NL), r / (4 * NL), g / (4 * NL));
+			}
+			double whole = 0;
+			for (int k = 0; k < 4; k++) whole += (double)(st[c][w][k][NL - 1][np] - st[c][w][k][0][0]);
+			printf("  stream total (layers only): %.0f cycles\n", whole / 4);
+		}
+	return 0;
+}
