@@ -760,15 +760,15 @@ namespace nab200
 		// and stacks of that family) - or the A2 single array; every layer's history must fit the window plan below
 		const bool single = IsHSingleArray(desc);
 		if (!single && !WaveNetTsSupported(desc)) return false;
-		const int R = single ? 640 : 384;
+		const int R = single ? 1024 : 512;
 		size_t layers = 0;
 		for (const auto& A : desc.arrays)
 			for (size_t l = 0; l < A.dilations.size(); l++, layers++)
 			{
 				const long long K = A.kernelSizes[l], d = A.dilations[l], Lp = (K - 1) * d;
 				if (K < 2 || K - 1 > kHMaxTaps) return false;
-				if (single && l == 0 && Lp + 128 > 144) return false;   // the head-conv scratch sits behind the first layer's window
-				if (Lp + 128 <= R) continue;                       // one contiguous window
+				if (single && l == 0 && Lp + 128 > R - 320) return false;   // the head-conv scratch sits at the top of the window buffer
+				if (Lp + 128 <= 640 && Lp + 128 <= R) continue;    // one contiguous window
 				if (d < 128 || (K - 1) * 128 > R || K - 1 > kHMaxJobs) return false;   // else every tap needs its own 128-row window
 			}
 		return layers <= (size_t)kMaxLayers;
@@ -782,7 +782,7 @@ namespace nab200
 		M.tc = 3;
 		M.numArrays = (int)desc.arrays.size();
 		const bool single = IsHSingleArray(desc);
-		const int R = single ? 640 : 384;   // rows per plane of the shared-memory window buffer
+		const int R = single ? 1024 : 512;   // rows per plane of the shared-memory window buffer
 		M.winRows = R;
 		const float* w = desc.weights.data();
 		int layerIdx = 0, ringIdx = 0, ringOff = 0;
@@ -961,9 +961,11 @@ namespace nab200
 				T.und16 = und16; T.convC16 = convC16; T.tap0Base16 = tap16[0];
 				T.one116 = one116 - lastStart; T.one216 = one216 - lastStart; T.oneC16 = oneC16 - lastStart;
 				T.tapStride16 = 2u * opN; T.N1 = (uint32_t)N1; T.ent16 = ent16; T.flags = (uint32_t)L.flags;
-				if (L.Lp + 128 <= R)
+				int regionRows;
+				if (L.Lp + 128 <= 640 && L.Lp + 128 <= R)
 				{
-					// one contiguous window: rows [0, Lp) = the ring in time order, rows [Lp, Lp + 128) = this call's frames
+					// one contiguous window: rows [0, Lp) = the ring in time order, rows [Lp, Lp + 128) = this call's frames (only where
+					// a tap reads them); offsets are relative to the region, its base is added below
 					T.curOff = (uint32_t)L.Lp * 16u;
 					for (int j = 0; j < K - 1; j++)
 					{
@@ -973,6 +975,7 @@ namespace nab200
 					}
 					T.numJobs = 1;
 					T.job[0].cnt = L.Lp; T.job[0].back = L.Lp; T.job[0].off = 0;
+					regionRows = L.Lp + (T.mixed ? 128 : 0);
 				}
 				else
 				{
@@ -983,9 +986,43 @@ namespace nab200
 						T.tapOff[j] = (uint32_t)j * 128u * 16u;
 						T.job[j].cnt = -1; T.job[j].back = (K - 1 - j) * d; T.job[j].off = T.tapOff[j];
 					}
+					regionRows = (K - 1) * 128;
 				}
+				T.pad0 = regionRows;
 				table.push_back(T);
 				layerIdx++;
+			}
+		}
+		// Window regions: layer L's rows go where layer L - 1's are not (below them, else right above them), so that its windows
+		// can be requested while layer L - 1 still reads its own; where neither fits the request is late (after that conv).
+		// The first layer of the next stream follows the last layer of this one (persistent CTAs).
+		{
+			const int NL = (int)table.size();
+			std::vector<int> base(NL, 0);
+			for (int i = 1; i < NL; i++)
+			{
+				const int rows = table[i].pad0, pb = base[i - 1], pr = table[i - 1].pad0;
+				uint32_t late = 0;
+				if (rows <= pb) base[i] = 0;                       // below the previous layer's rows
+				else if (pb + pr + rows <= R) base[i] = pb + pr;   // right above them
+				else { base[i] = 0; late = kHLate; }
+				table[i].flags = (table[i].flags & ~kHLate) | late;
+			}
+			// layer 0 (base 0) of the CTA's next stream against the last layer of this one
+			{
+				const int pb = base[NL - 1], pr = table[NL - 1].pad0, rows = table[0].pad0;
+				const bool overlap = NL > 1 ? (rows > pb) : true;
+				(void)pr;
+				table[0].flags = (table[0].flags & ~kHLate) | (overlap ? kHLate : 0u);
+			}
+			for (int i = 0; i < NL; i++)
+			{
+				HLayer& T = table[i];
+				const uint32_t off = (uint32_t)base[i] * 16u;
+				T.curOff += off;
+				for (int j = 0; j < T.numTaps; j++) T.tapOff[j] += off;
+				for (int j = 0; j < T.numJobs; j++) T.job[j].off += off;
+				T.pad0 = base[i];
 			}
 		}
 		M.headScale = *w;

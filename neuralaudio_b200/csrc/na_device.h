@@ -86,6 +86,10 @@ namespace nab200
 	//   TMEM columns, half the MMAs and no split arithmetic when a stored value is reused (tools/tsh_numerics.py).
 	//   Ring row of one frame = C words: [h1 of channel pairs (C/2 words) | h2 of channel pairs (C/2 words)], stored as
 	//   planes [C/4][Lp][4 words] exactly as the operand is staged to TMEM.
+	//   Shared-memory window buffer: [planes][winRows][16 bytes].  Each layer owns a row region [base, base + rows) of it
+	//   (history rows, then - where a tap reads this call's frames - the 128 current rows); consecutive layers get disjoint
+	//   regions where both fit, so a layer's windows are requested (TMA bulk copies) a whole layer ahead; where they cannot
+	//   (kHLate) the request waits for the previous layer's conv.
 	//   Weight block of a layer (16-byte units, fp16): per tap k = 0..K-1 (k = K-1 undelayed):
 	//       C == 16: W1[2][16][8] | W2[2][16][8]          (B operand [k group][n][8 halves], k = input channel)
 	//       C ==  8: Wa = [W1 ; W1][2][8][8] | Wb = [W2 ; 0]   (k group 0 pairs with the h1 halves, group 1 with the h2 halves)
@@ -94,6 +98,7 @@ namespace nab200
 	//     transition operands (see PackWaveNetH).  A layer with more delayed taps than one hand-off carries (K = 15) is cut
 	//     into sub-blocks, one per tap group, staged one after the other through the same two shared-memory buffers:
 	//     [entry | undelayed tap | convC | taps of group 0] [taps of group 1] ... [taps of the last group | one1 | one2 | oneC].
+	constexpr uint32_t kHLate = 1u << 8;   // HLayer::flags: this layer's window region overlaps the previous layer's (request it after that conv)
 	constexpr int kHMaxTaps = 16;   // delayed taps per layer (K - 1 <= 14 for the official shapes)
 	constexpr int kHMaxJobs = 6;    // history-window copy jobs per layer
 	struct HJob

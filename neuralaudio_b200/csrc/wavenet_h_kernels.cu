@@ -9,8 +9,10 @@
 //     accumulation: the same 22 significant bits as 3xTF32 (tools/tsh_numerics.py: 3.9e-7 vs 3.6e-7 max-abs on the
 //     reference's own A1 Standard vector), but 16 TMEM columns per 16-channel operand instead of 32, 14 MMAs per
 //     16-channel layer instead of 26, and a stored (h1, h2) row is reused as is:
-//   * the history rings and the shared-memory windows hold the packed pairs (4 bytes per value, as before), so staging a
-//     delayed tap is LDS.128 -> tcgen05.st with no arithmetic; the split is computed once per produced value;
+//   * the history rings and the shared-memory windows hold the packed pairs (4 bytes per value, as before) in the operand's own
+//     layout, so a delayed tap needs no thread at all: the issuer copies its 128 rows shared memory -> TMEM with tcgen05.cp
+//     (a tap shift is a row offset of the copy's descriptor) right in front of the MMAs that read them, in the same in-order
+//     pipe (tools/cp_probe.cu); the split is computed once per produced value;
 //   * 96 TMEM columns per stream (three 32-column allocations) -> 5 streams in flight per SM instead of 4;
 //   * the residual stream stays an fp32 TMEM accumulator for the whole array (x += W1x1 z + b is the 1x1 MMA itself,
 //     WaveNet.h:486-491), the head sum accumulates as extra N columns of the 1x1 (WaveNet.h:482,658-660), mix-in,
@@ -47,11 +49,9 @@ namespace nab200
 			kBarMix = 1,      // stagers only
 			kBarE = 2,        // stagers -> issuer: entry / transition operands staged
 			kBarT2 = 3,       // stagers -> issuer: undelayed tap staged
-			kBarTaps = 4,     // stagers -> issuer: a group of delayed taps staged
 			kBarZ = 5,        // stagers -> issuer: activated output staged
 			kBarDReady = 6,   // issuer -> stagers: conv accumulator complete
-			kBarXReady = 7,   // issuer -> stagers: residual / head accumulators complete
-			kBarGReady = 8    // issuer -> stagers: the previous tap group's MMAs have read their operands
+			kBarXReady = 7    // issuer -> stagers: residual / head accumulators complete
 		};
 
 		struct Ctx
@@ -63,16 +63,18 @@ namespace nab200
 			uint32_t wbuf, wbufStride;    // two weight buffers
 			uint32_t tab;                 // HLayer table
 			int* hdb;                     // [2][kHdbHalf] ring heads of the current / next stream
-			uint32_t barW0, barD, barX, barWin;   // barWin: this layer's history windows have landed (TMA bulk copies)
+			uint32_t barW0, barD, barX, barWin0;  // barWin0 (+8): history windows landed (TMA bulk copies), alternating by layer parity
 			uint32_t r0, r1, r2;          // TMEM: three 32-column regions
 			int n, tid, warp, S, gstride, numLayers;
 			bool el;
 			uint32_t wq, dq, xq;          // issuer: weight-block counter, barD / barX phase counters
-			uint32_t winq;                // stagers: window phase counter (one per layer)
+			uint32_t winq;                // window request counter (stagers) / wait counter (issuer), one per layer
+			uint32_t wwq;                 // stagers: window wait counter
 			int cur;
 			int* err;
 			char* sbase;                  // stagers: this stream's state
 			bool hasNext;                 // stagers: the CTA has another stream after this one
+			bool preWaited;               // stagers: this layer's windows were awaited at the end of the previous layer; issuer: first layer of the CTA
 #ifdef NAB_H_TIMING
 			bool stampOn; int stampCta, stampStream;
 #endif
@@ -170,54 +172,72 @@ namespace nab200
 		// the four warps; every copy completes on barWin (4 arrivals, one per warp, + the bytes).
 		// (Round 2 profile: per-thread cp.async copies cost ~105 issued instructions per warp and layer - 8 LDGSTS, their 64-bit
 		// address arithmetic and 24 predicated-off fillers - in an issue-bound kernel; this costs ~30.)
-		__device__ __forceinline__ void request_windows(const Ctx& cx, int l, const char* sbase, const int* hd)
+		__device__ __forceinline__ void request_windows(Ctx& cx, int l, const char* sbase, const int* hd)
 		{
+			const uint32_t bar = cx.barWin0 + 8u * (cx.winq & 1u);
+			cx.winq++;
 #ifdef NAB_H_NO_WINDOWS   // timing experiment only (tools/h_timing.cu): results are wrong
-			if ((cx.tid & 31) == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(cx.barWin) : "memory");
+			if ((cx.tid & 31) == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 			return;
 #endif
 			const uint32_t la = cx.tab + (uint32_t)l * (uint32_t)sizeof(HLayer);
-			const uint4 g0 = lds128(la), g1 = lds128(la + 16);
-			const int Lp = (int)g0.z, numJobs = (int)g1.y, CG = (int)g1.w >> 2;
 			const int lane = cx.tid & 31;
-			const int c = lane * 4 + cx.warp;
-			if (lane < 8 && c < numJobs * CG * 2)
+			if (lane < 8)
 			{
-				const int head = hd[g1.x];
-				const int jb = c / (2 * CG), rem = c - jb * 2 * CG, g = rem >> 1, run = rem & 1;
-				const uint4 jj = lds128(la + kTabJobs + 16u * (uint32_t)jb);
-				const int cnt = (int)jj.x < 0 ? cx.n : (int)jj.x;
-				int start = head - (int)jj.y;
-				if (start < 0) start += Lp;
-				const int run1 = cnt < Lp - start ? cnt : Lp - start;
-				const int rows = run == 0 ? run1 : cnt - run1;
-				const int srcRow = run == 0 ? start : 0, dstRow = run == 0 ? 0 : run1;
-				if (rows > 0)
+				// copy c = (job, plane, run) without a division: planes per row = 4 (16 channels) or 2 (8 channels)
+				const uint4 g1 = lds128(la + 16);
+				const int sh = ((int)g1.w >> 4) + 2;          // log2(2 * planes)
+				const int c = lane * 4 + cx.warp;
+				if (c < ((int)g1.y << sh))
 				{
-					const uint32_t bytes = (uint32_t)rows * 16u;
-					asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(cx.barWin), "r"(bytes) : "memory");
-					bulk_g2s(cx.win + jj.z + (uint32_t)g * cx.planeStride + (uint32_t)dstRow * 16u,
-						sbase + (size_t)g0.w * 4 + (size_t)(uint32_t)(g * Lp + srcRow) * 16, bytes, cx.barWin);
+					const uint4 g0 = lds128(la);
+					const int Lp = (int)g0.z;
+					const int jb = c >> sh, g = (c >> 1) & ((1 << (sh - 1)) - 1), run = c & 1;
+					const uint4 jj = lds128(la + kTabJobs + 16u * (uint32_t)jb);
+					const int cnt = (int)jj.x < 0 ? cx.n : (int)jj.x;
+					int start = hd[g1.x] - (int)jj.y;
+					if (start < 0) start += Lp;
+					const int run1 = min(cnt, Lp - start);
+					const int rows = run == 0 ? run1 : cnt - run1;
+					if (rows > 0)
+					{
+						const int srcRow = run == 0 ? start : 0, dstRow = run == 0 ? 0 : run1;
+						const uint32_t bytes = (uint32_t)rows * 16u;
+						asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+						bulk_g2s(cx.win + jj.z + (uint32_t)g * cx.planeStride + (uint32_t)dstRow * 16u,
+							sbase + (size_t)(uint32_t)((int)g0.w * 4 + (g * Lp + srcRow) * 16), bytes, bar);
+					}
 				}
 			}
 			__syncwarp();
-			if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(cx.barWin) : "memory");
+			if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 		}
 
-		// windows of the layer after l (the next layer of this stream, or the first layer of the CTA's next stream)
-		__device__ __forceinline__ void request_next_windows(const Ctx& cx, int l)
+		// Windows of the layer after l (the next layer of this stream, or the first layer of the CTA's next stream).  Its region
+		// of the window buffer may overlap layer l's (HLayer::flags kHLate, decided by PackWaveNetH): then the request must wait
+		// until layer l's conv has read its windows (`afterConv`), else it goes out as early as layer l's own hand-off.
+		__device__ __forceinline__ bool request_next_windows(Ctx& cx, int l, bool afterConv)
 		{
 			int nl = l + 1;
 			const int* hd = cx.hdb + cx.cur * kHdbHalf;
 			const char* sb = cx.sbase;
 			if (nl >= cx.numLayers)
 			{
-				if (!cx.hasNext) return;
+				if (!cx.hasNext) return false;
 				nl = 0;
 				hd = cx.hdb + (cx.cur ^ 1) * kHdbHalf;
 				sb = cx.sbase + (size_t)cx.gstride * ((size_t)cx.M->stateStride * 4);
 			}
-			request_windows(cx, nl, sb, hd);
+			const bool late = (lds32(cx.tab + (uint32_t)nl * (uint32_t)sizeof(HLayer) + 76u) & kHLate) != 0;
+			if (late == afterConv) request_windows(cx, nl, sb, hd);
+			return !late;   // an early layer's windows have a whole layer to land: the stagers wait for them off the chain
+		}
+
+		// stagers: the windows counted by wwq have landed
+		__device__ __forceinline__ void wait_windows(Ctx& cx)
+		{
+			if (!mbar_wait(cx.barWin0 + 8u * (cx.wwq & 1u), (cx.wwq >> 1) & 1u) && cx.tid == 0) *reinterpret_cast<volatile int*>(cx.err) = 1;
+			cx.wwq++;
 		}
 
 		// C fp32 values -> C words [h1 of channel pairs | h2 of channel pairs]
@@ -266,7 +286,6 @@ namespace nab200
 		{
 			typedef Map<ROLE> MP;
 			constexpr int C = MP::C, CG = C / 4;
-			constexpr int NT = ROLE == 2 ? 5 : 2;   // the delayed-tap count with an unrolled path (K = 6 / K = 3)
 			const int tid = cx.tid;
 			const uint32_t lane = (uint32_t)(cx.warp * 32) << 16;
 			const int* hd = cx.hdb + cx.cur * kHdbHalf;
@@ -277,7 +296,6 @@ namespace nab200
 				const int l = firstLayer + li;
 				const uint32_t la = cx.tab + (uint32_t)l * (uint32_t)sizeof(HLayer);
 				const uint4 g0 = lds128(la), g1 = lds128(la + 16), g2 = lds128(la + 32);
-				const int numTaps = (int)g0.x, groupTaps = (int)g2.w;
 				const bool mixed = g0.y != 0;
 
 				// ---- the residual stream after the previous layer -> packed pairs: undelayed tap, current rows, ring ----
@@ -296,73 +314,17 @@ namespace nab200
 					const uint32_t cur = myRow + g2.x;
 #pragma unroll
 					for (int q = 0; q < CG; q++) sts128(cur + (uint32_t)q * cx.planeStride, p[4 * q], p[4 * q + 1], p[4 * q + 2], p[4 * q + 3]);
+					asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy rows -> visible to the issuer's tcgen05.cp
 				}
 				stager_arrive<kBarT2>();
 				H_STAMP(2);
-				// this layer's history windows have landed (the issuer's bulk copies); where a tap mixes history and current frames the
-				// rows the other stagers produced must be visible too
-				if (!mbar_wait(cx.barWin, cx.winq & 1u) && cx.tid == 0) *reinterpret_cast<volatile int*>(cx.err) = 1;
-				cx.winq++;
+				// the delayed taps need no thread: the issuer copies them shared memory -> TMEM (tcgen05.cp) in front of their MMAs.
+				// What the stagers do in the conv's shadow: request the next layer's history windows, write this layer's ring rows.
+				request_next_windows(cx, l, false);
 				H_STAMP(3);
-				if (mixed) nbar_sync<kBarMix, kStagers>();
-				H_STAMP(4);
-				// ---- delayed taps: my row of each, shared memory -> TMEM, no arithmetic ----
-				if (numTaps == NT)
-				{
-					uint32_t off[8];
-					{
-						const uint4 o0 = lds128(la + kTabTaps);
-						off[0] = o0.x; off[1] = o0.y; off[2] = o0.z; off[3] = o0.w;
-						if (NT > 4)
-						{
-							const uint4 o1 = lds128(la + kTabTaps + 16);
-							off[4] = o1.x; off[5] = o1.y; off[6] = o1.z; off[7] = o1.w;
-						}
-					}
-#pragma unroll
-					for (int j = 0; j < NT; j++)
-					{
-						uint32_t v[C];
-#pragma unroll
-						for (int q = 0; q < CG; q++)
-						{
-							const uint4 t = lds128(myRow + off[j] + (uint32_t)q * cx.planeStride);
-							v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
-						}
-						tmem_st<C>(lane + MP::tap(cx, j), v);
-					}
-					stager_arrive<kBarTaps>();
-				}
-				else
-				{
-#pragma unroll 1
-					for (int j0 = 0; j0 < numTaps; j0 += groupTaps)
-					{
-						if (j0 > 0) stager_wait<kBarGReady>();
-						const int jn = (j0 + groupTaps < numTaps) ? j0 + groupTaps : numTaps;
-#pragma unroll 1
-						for (int j = j0; j < jn; j++)
-						{
-							const uint32_t row = myRow + lds32(la + kTabTaps + 4u * (uint32_t)j);
-							uint32_t v[C];
-#pragma unroll
-							for (int q = 0; q < CG; q++)
-							{
-								const uint4 t = lds128(row + (uint32_t)q * cx.planeStride);
-								v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
-							}
-							tmem_st<C>(lane + MP::tap(cx, j - j0), v);
-						}
-						stager_arrive<kBarTaps>();
-					}
-				}
-				H_STAMP(5);
-				// every stager is done with this layer's windows: request the next layer's (or the next stream's first layer's)
-				nbar_sync<kBarMix, kStagers>();
-				H_STAMP(9);
-				request_next_windows(cx, l);
-				H_STAMP(10);
-				// history write-back (AdvanceFrames, WaveNet.h:59-65): frame t becomes ring row (head + t) mod Lp
+				// history write-back (AdvanceFrames, WaveNet.h:59-65): frame t becomes ring row (head + t) mod Lp.  The rows replaced
+				// are the oldest ones, which this layer's own window copy reads: it must have landed (requested a layer ago).
+				if (!cx.preWaited) wait_windows(cx);
 				{
 					const int Lp = (int)g0.z;
 					const int first = cx.n > Lp ? cx.n - Lp : 0;
@@ -398,8 +360,26 @@ namespace nab200
 					tmem_st<C>(lane + MP::tap(cx, 0), dv);
 				}
 				stager_arrive<kBarZ>();
+				// in the shadow of the 1x1: the late request (only where the next layer's windows overlap this layer's), or - for an
+				// early layer, requested a whole layer ago - the wait for its windows, so that the next hand-off implies them and
+				// the issuer does not have to poll for them on the chain
+				cx.preWaited = request_next_windows(cx, l, true);
+				if (cx.preWaited)
+				{
+					wait_windows(cx);
+					asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+				}
 				H_STAMP(8);
 			}
+		}
+
+		// 128 rows of a shared-memory window (plane layout, 16 bytes per row and plane) -> a tap's TMEM columns
+		template <int C>
+		__device__ __forceinline__ void tap_copy(uint32_t tmemCol, uint32_t row16, uint32_t lbo16)
+		{
+			asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(tmemCol), "l"(desc_at(row16, lbo16)) : "memory");
+			if constexpr (C == 16)
+				asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(tmemCol + 8u), "l"(desc_at(row16 + 2u * lbo16, lbo16)) : "memory");
 		}
 
 		// conv-type product into accumulator `acc`: A at TMEM `a` (C == 16: h1 at a, h2 at a + 8; C == 8: [h1 | h2] at a),
@@ -439,84 +419,101 @@ namespace nab200
 				const uint32_t tapStride16 = g4.x;
 				const uint32_t und16 = lds32(la + 92u), tap0Base16 = lds32(la + 108u);
 				uint32_t wb16 = 0;
+				H_STAMP(0);
 
 				// ---- dilated conv + mix-in + bias (WaveNet.h:250-289,471-476): undelayed tap, constant operand, delayed taps ----
-				if (numGroups == 1 && numTaps == NT)
+				// A delayed tap is 128 rows of the shared-memory window starting at its own row offset: tcgen05.cp moves them to the
+				// tap's TMEM columns (two planes = 8 columns per copy) and the MMAs behind it in the same pipe read them.
+				// Everything the products need is computed BEFORE the hand-offs; the next weight block is requested AFTER the conv has
+				// been committed (round 2 timing: a bulk-copy request costs the issuing warp hundreds of cycles under contention).
+				const uint32_t win16 = cx.win >> 4, lbo16 = cx.planeStride >> 4;
+				const bool fast = numGroups == 1 && numTaps == NT;
+				uint32_t row16[NT];
 				{
-					// the common shape (K = 3 / K = 6): one weight block, every product's descriptor known before the hand-offs
-					H_STAMP(0);
-					if (li > 0) issuer_wait(cx, cx.barW0 + 8u * (cx.wq & 1u), (cx.wq >> 1) & 1u);
-					if (cx.el) issue_weights(cx, (l + 1 < cx.numLayers) ? l + 1 : 0, 0, cx.wq + 1);
-					__syncwarp();
-					wb16 = (cx.wbuf + (cx.wq & 1u) * cx.wbufStride) >> 4;
-					const uint32_t tb16 = wb16 + tap0Base16;
-					H_STAMP(1);
-					issuer_sync<kBarT2>();
-					H_STAMP(2);
+					const uint4 o0 = lds128(la + kTabTaps);
+					row16[0] = win16 + (o0.x >> 4);
+					if (NT > 1) row16[1] = win16 + (o0.y >> 4);
+					if (NT > 2) { row16[2] = win16 + (o0.z >> 4); row16[3] = win16 + (o0.w >> 4); }
+					if (NT > 4) row16[4] = win16 + (lds32(la + kTabTaps + 16u) >> 4);
+				}
+				// this layer's first weight block (the first one of an array was awaited by the entry / transition code)
+				if (li > 0) issuer_wait(cx, cx.barW0 + 8u * (cx.wq & 1u), (cx.wq >> 1) & 1u);
+				wb16 = (cx.wbuf + (cx.wq & 1u) * cx.wbufStride) >> 4;
+				H_STAMP(1);
+				issuer_sync<kBarT2>();
+				H_STAMP(2);
+				if (cx.el)
+				{
+					mma_pairs<C, 0>(MP::d(cx), MP::t2(cx), wb16 + und16, C);   // overwrites the accumulator
+					mma_f16_ts<1>(MP::d(cx), konst(cx), desc_at(wb16 + g3.x, C), idesc_f16(C));
+				}
+				__syncwarp();
+				H_STAMP(3);
+				// this layer's history windows: implied by the hand-off above where the stagers awaited them a layer ago (early layers);
+				// polled here only for a late layer and for the first layer this CTA runs
+				if ((g4.w & kHLate) != 0 || cx.preWaited) issuer_wait(cx, cx.barWin0 + 8u * (cx.winq & 1u), (cx.winq >> 1) & 1u);
+				cx.preWaited = false;
+				cx.winq++;
+				H_STAMP(4);
+				if (fast)
+				{
 					if (cx.el)
 					{
-						mma_pairs<C, 0>(MP::d(cx), MP::t2(cx), wb16 + und16, C);   // overwrites the accumulator
-						mma_f16_ts<1>(MP::d(cx), konst(cx), desc_at(wb16 + g3.x, C), idesc_f16(C));
-					}
-					__syncwarp();
-					H_STAMP(3);
-					issuer_sync<kBarTaps>();
-					H_STAMP(4);
-					if (cx.el)
-					{
+						const uint32_t tb16 = wb16 + tap0Base16;
 #pragma unroll
-						for (int j = 0; j < NT; j++) mma_pairs<C, 1>(MP::d(cx), MP::tap(cx, j), tb16 + (uint32_t)(j * 4 * C), C);
+						for (int j = 0; j < NT; j++)
+						{
+							tap_copy<C>(MP::tap(cx, j), row16[j], lbo16);
+							mma_pairs<C, 1>(MP::d(cx), MP::tap(cx, j), tb16 + (uint32_t)(j * 4 * C), C);
+						}
 						mma_commit(cx.barD);
+						// the other buffer held the previous layer's block, whose MMAs are complete
+						issue_weights(cx, (l + 1 < cx.numLayers) ? l + 1 : 0, 0, cx.wq + 1);
 					}
 					__syncwarp();
 					H_STAMP(5);
 					issuer_release<kBarDReady>(cx, cx.barD, cx.dq & 1u);
-					H_STAMP(6);
 					cx.dq++;
 				}
 				else
 				{
-				// one weight sub-block per tap group, through the two buffers in turn
 #pragma unroll 1
-				for (int g = 0; g < numGroups; g++)
-				{
-					// this sub-block (the first one of an array was awaited by the entry / transition code)
-					if (li > 0 || g > 0) issuer_wait(cx, cx.barW0 + 8u * (cx.wq & 1u), (cx.wq >> 1) & 1u);
-					// the other buffer held the previous sub-block, whose MMAs are complete: request the next one
-					if (cx.el)
+					for (int g = 0; g < numGroups; g++)
 					{
-						if (g + 1 < numGroups) issue_weights(cx, l, g + 1, cx.wq + 1);
-						else issue_weights(cx, (l + 1 < cx.numLayers) ? l + 1 : 0, 0, cx.wq + 1);
-					}
-					__syncwarp();
-					wb16 = (cx.wbuf + (cx.wq & 1u) * cx.wbufStride) >> 4;
-					if (g == 0)
-					{
-						issuer_sync<kBarT2>();
+						if (g > 0)
+						{
+							issuer_wait(cx, cx.barW0 + 8u * (cx.wq & 1u), (cx.wq >> 1) & 1u);
+							wb16 = (cx.wbuf + (cx.wq & 1u) * cx.wbufStride) >> 4;
+						}
+						const int j0 = g * groupTaps;
+						const int jn = (j0 + groupTaps < numTaps) ? j0 + groupTaps : numTaps;
+						const uint32_t tb16 = wb16 + (g == 0 ? tap0Base16 : 0u);
 						if (cx.el)
 						{
-							mma_pairs<C, 0>(MP::d(cx), MP::t2(cx), wb16 + und16, C);   // overwrites the accumulator
-							mma_f16_ts<1>(MP::d(cx), konst(cx), desc_at(wb16 + g3.x, C), idesc_f16(C));
+#pragma unroll 1
+							for (int j = j0; j < jn; j++)
+							{
+								const uint32_t r16 = win16 + (lds32(la + kTabTaps + 4u * (uint32_t)j) >> 4);
+								tap_copy<C>(MP::tap(cx, j - j0), r16, lbo16);
+								mma_pairs<C, 1>(MP::d(cx), MP::tap(cx, j - j0), tb16 + (uint32_t)(j - j0) * tapStride16, C);
+							}
+							mma_commit(cx.barD);
+							// the other buffer held the previous sub-block (or the previous layer's last block): complete
+							if (g + 1 < numGroups) issue_weights(cx, l, g + 1, cx.wq + 1);
+							else issue_weights(cx, (l + 1 < cx.numLayers) ? l + 1 : 0, 0, cx.wq + 1);
 						}
 						__syncwarp();
+						if (jn < numTaps)
+						{
+							// more tap groups: this sub-block's buffer and the tap columns are reused by the group after next / the next group
+							issuer_wait(cx, cx.barD, cx.dq & 1u);
+							cx.wq++;
+						}
+						else issuer_release<kBarDReady>(cx, cx.barD, cx.dq & 1u);
+						cx.dq++;
 					}
-					const int j0 = g * groupTaps;
-					const int jn = (j0 + groupTaps < numTaps) ? j0 + groupTaps : numTaps;
-					const uint32_t tb16 = wb16 + (g == 0 ? tap0Base16 : 0u);
-					issuer_sync<kBarTaps>();
-					if (cx.el)
-					{
-#pragma unroll 1
-						for (int j = j0; j < jn; j++) mma_pairs<C, 1>(MP::d(cx), MP::tap(cx, j - j0), tb16 + (uint32_t)(j - j0) * tapStride16, C);
-						mma_commit(cx.barD);
-					}
-					__syncwarp();
-					if (jn < numTaps) issuer_release<kBarGReady>(cx, cx.barD, cx.dq & 1u);
-					else issuer_release<kBarDReady>(cx, cx.barD, cx.dq & 1u);
-					cx.dq++;
-					if (g + 1 < numGroups) cx.wq++;
 				}
-				}
+				H_STAMP(6);
 
 				// ---- 1x1 + bias + residual, head sum (WaveNet.h:482-491): XR | HD += [z] [W1x1 | Whead] ----
 				issuer_sync<kBarZ>();
@@ -546,11 +543,11 @@ namespace nab200
 			}
 		}
 
-		constexpr int kNumBars = 6;   // W0, W1, D, X, Win (+ one slot of padding: what follows is read with 16-byte copies)
+		constexpr int kNumBars = 6;   // W0, W1, D, X, Win0, Win1 (what follows is read with 16-byte copies: keep the count even)
 		constexpr int kHeadTaps = 16;                           // A2 head conv kernel size (WaveNet.h:658-660, InternalModel.h:12-20)
 		constexpr int kHeadHistFloats = kHeadTaps * 16;         // per stream: [tap][16 frames] of per-tap head products (15 used)
 		constexpr int kHeadRows = kCur + kHeadTaps - 1;         // scratch rows per tap plane: 15 history + 128 current
-		constexpr uint32_t kHeadScratchOff = 640u * 16u + 2304u;   // inside the window buffer, clear of the first layer's windows (PackWaveNetH checks)
+		constexpr uint32_t kHeadScratchBytes = 8u * (uint32_t)(kCur + kHeadTaps - 1) * 4u + 32u;   // at the top of the window buffer, clear of the first layer's region (PackWaveNetH checks)
 
 		// ARCH 0: two arrays, (16, 8) channels, tanh, 1x1 heads (A1 Standard / Lite).  ARCH 1: one 8-channel array, LeakyReLU,
 		// 16-tap head conv (A2, WaveNet.h:632-661 with the InternalModel.h:12-20 shapes).
@@ -579,14 +576,14 @@ namespace nab200
 			cx.barW0 = smem_u32(&bars[0]);
 			cx.barD = smem_u32(&bars[2]);
 			cx.barX = smem_u32(&bars[3]);
-			cx.barWin = smem_u32(&bars[4]);
+			cx.barWin0 = smem_u32(&bars[4]);
 			cx.n = n;
 			cx.tid = threadIdx.x;
 			cx.warp = threadIdx.x >> 5;
 			cx.S = S;
 			cx.gstride = gridDim.x;
 			cx.numLayers = M.numLayers;
-			cx.wq = 0; cx.dq = 0; cx.xq = 0; cx.winq = 0; cx.cur = 0;
+			cx.wq = 0; cx.dq = 0; cx.xq = 0; cx.winq = 0; cx.wwq = 0; cx.cur = 0;
 			cx.el = elect_one();
 			const int tid = threadIdx.x, warp = cx.warp;
 			const bool stager = warp < 4;
@@ -606,7 +603,8 @@ namespace nab200
 				mbar_init(cx.barW0 + 8u, 1);
 				mbar_init(cx.barD, 1);
 				mbar_init(cx.barX, 1);
-				mbar_init(cx.barWin, 4);
+				mbar_init(cx.barWin0, 4);
+				mbar_init(cx.barWin0 + 8u, 4);
 				asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 			}
 			if (warp == 4)
@@ -638,6 +636,7 @@ namespace nab200
 				const uint32_t ent0 = lds128(cx.tab + (uint32_t)first0 * (uint32_t)sizeof(HLayer) + 64).z;
 				const uint32_t ent1 = ARCH == 0 ? lds128(cx.tab + (uint32_t)first1 * (uint32_t)sizeof(HLayer) + 64).z : 0u;
 				if (cx.el) issue_weights(cx, 0, 0, 0);
+				cx.preWaited = true;   // (issuer: the first layer's windows must be polled for)
 				for (int s = s0; s < S; s += gridDim.x)
 				{
 					H_STAMP_SELECT(s, s0);
@@ -692,6 +691,7 @@ namespace nab200
 				const size_t strideBytes = (size_t)M.stateStride * 4;
 				cx.sbase = reinterpret_cast<char*>(state) + (size_t)s0 * strideBytes;
 				cx.hasNext = false;
+				cx.preWaited = false;
 				if (s0 < S) request_windows(cx, 0, cx.sbase, cx.hdb);
 				for (int s = s0; s < S; s += gridDim.x)
 				{
@@ -772,7 +772,7 @@ namespace nab200
 						uint32_t g[16];
 						tmem_ld<16>(lane + Map<2>::hd(cx), g);
 						float acc = 0.0f;
-						const uint32_t sc = cx.win + kHeadScratchOff;
+						const uint32_t sc = (cx.win + 2u * cx.planeStride - kHeadScratchBytes) & ~15u;
 #pragma unroll
 						for (int half = 0; half < 2; half++)
 						{
