@@ -999,21 +999,14 @@ namespace nab200
 		{
 			const int NL = (int)table.size();
 			std::vector<int> base(NL, 0);
-			for (int i = 1; i < NL; i++)
+			// even layers sit at the bottom of the buffer, odd layers at the top: two consecutive layers overlap only when their
+			// rows do not fit side by side
+			for (int i = 0; i < NL; i++) base[i] = (i & 1) ? R - table[i].pad0 : 0;
+			for (int i = 0; i < NL; i++)
 			{
-				const int rows = table[i].pad0, pb = base[i - 1], pr = table[i - 1].pad0;
-				uint32_t late = 0;
-				if (rows <= pb) base[i] = 0;                       // below the previous layer's rows
-				else if (pb + pr + rows <= R) base[i] = pb + pr;   // right above them
-				else { base[i] = 0; late = kHLate; }
-				table[i].flags = (table[i].flags & ~kHLate) | late;
-			}
-			// layer 0 (base 0) of the CTA's next stream against the last layer of this one
-			{
-				const int pb = base[NL - 1], pr = table[NL - 1].pad0, rows = table[0].pad0;
-				const bool overlap = NL > 1 ? (rows > pb) : true;
-				(void)pr;
-				table[0].flags = (table[0].flags & ~kHLate) | (overlap ? kHLate : 0u);
+				const int prev = (i + NL - 1) % NL;
+				const bool overlap = NL > 1 ? (base[i] < base[prev] + table[prev].pad0 && base[prev] < base[i] + table[i].pad0) : true;
+				table[i].flags = (table[i].flags & ~kHLate) | (overlap ? kHLate : 0u);
 			}
 			for (int i = 0; i < NL; i++)
 			{
@@ -1022,7 +1015,8 @@ namespace nab200
 				T.curOff += off;
 				for (int j = 0; j < T.numTaps; j++) T.tapOff[j] += off;
 				for (int j = 0; j < T.numJobs; j++) T.job[j].off += off;
-				T.pad0 = base[i];
+				// what the stagers need to know at layer i: is the NEXT layer's request late (after this layer's conv) or early
+				T.pad0 = (int)(table[(i + 1) % NL].flags & kHLate);
 			}
 		}
 		M.headScale = *w;

@@ -112,7 +112,7 @@ namespace nab200
 	{
 		int numTaps, mixed, Lp, ringOff;                       // group 0
 		int ringIdx, numJobs, K, C;                            // group 1
-		uint32_t curOff; int numGroups, pad0, groupTaps;       // group 2: current-row offset (bytes), weight sub-blocks, taps per hand-off
+		uint32_t curOff; int numGroups, pad0, groupTaps;       // group 2: current-row offset (bytes), weight sub-blocks, (pad0: kHLate of the NEXT layer), taps per hand-off
 		uint32_t convC16, one116, one216, oneC16;              // group 3: 16-byte-unit offsets: convC inside sub-block 0, 1x1 parts inside the last one
 		uint32_t tapStride16, N1, ent16, flags;                // group 4: ent16 inside sub-block 0
 		uint32_t gOff[3]; uint32_t und16;                      // group 5: float offset of each weight sub-block; undelayed tap inside sub-block 0

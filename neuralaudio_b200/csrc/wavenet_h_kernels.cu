@@ -63,18 +63,15 @@ namespace nab200
 			uint32_t wbuf, wbufStride;    // two weight buffers
 			uint32_t tab;                 // HLayer table
 			int* hdb;                     // [2][kHdbHalf] ring heads of the current / next stream
-			uint32_t barW0, barD, barX, barWin0;  // barWin0 (+8): history windows landed (TMA bulk copies), alternating by layer parity
+			uint32_t barW0, barD, barX;
 			uint32_t r0, r1, r2;          // TMEM: three 32-column regions
 			int n, tid, warp, S, gstride, numLayers;
 			bool el;
 			uint32_t wq, dq, xq;          // issuer: weight-block counter, barD / barX phase counters
-			uint32_t winq;                // window request counter (stagers) / wait counter (issuer), one per layer
-			uint32_t wwq;                 // stagers: window wait counter
 			int cur;
 			int* err;
 			char* sbase;                  // stagers: this stream's state
 			bool hasNext;                 // stagers: the CTA has another stream after this one
-			bool preWaited;               // stagers: this layer's windows were awaited at the end of the previous layer; issuer: first layer of the CTA
 #ifdef NAB_H_TIMING
 			bool stampOn; int stampCta, stampStream;
 #endif
@@ -167,77 +164,64 @@ namespace nab200
 		}
 
 		// Stager warps (all 128 threads call it): the history window(s) of layer l of the stream whose state starts at `sbase`,
-		// HBM ring -> shared memory, as TMA bulk copies.  A window job is rows r in [0, cnt) <- ring rows (head - back + r) mod Lp:
-		// at most two contiguous runs per 16-byte plane, i.e. numJobs x planes x 2 copies per layer (<= 20), dealt to lanes 0..4 of
-		// the four warps; every copy completes on barWin (4 arrivals, one per warp, + the bytes).
-		// (Round 2 profile: per-thread cp.async copies cost ~105 issued instructions per warp and layer - 8 LDGSTS, their 64-bit
-		// address arithmetic and 24 predicated-off fillers - in an issue-bound kernel; this costs ~30.)
-		__device__ __forceinline__ void request_windows(Ctx& cx, int l, const char* sbase, const int* hd)
+		// HBM ring -> shared memory with cp.async: a window job is rows r in [0, cnt) <- ring rows (head - back + r) mod Lp, thread t
+		// copies rows t, t + 128, ... (16 bytes per plane and row; a warp moves contiguous 512-byte runs).  One cp.async group
+		// per request; the thread that issued a copy waits for it (cp.async.wait_group) before its next hand-off.
+		// (Measured, round 2: the same windows as TMA bulk copies - 8 to 16 small requests per layer and CTA - took ~2000 cycles
+		// to land under load against ~1200 for these; their request cost was no lower either.)
+		template <int CG>
+		__device__ __forceinline__ void request_windows_cg(const Ctx& cx, uint32_t la, const char* sbase, const int* hd)
 		{
-			const uint32_t bar = cx.barWin0 + 8u * (cx.winq & 1u);
-			cx.winq++;
+			const uint4 g0 = lds128(la), g1 = lds128(la + 16);
+			const int Lp = (int)g0.z, numJobs = (int)g1.y;
+			const int head = hd[g1.x];
+			const uint32_t ringB = g0.w * 4u, stepB = (uint32_t)Lp * 16u;
+#pragma unroll 1
+			for (int jb = 0; jb < numJobs; jb++)
+			{
+				const uint4 jj = lds128(la + kTabJobs + 16u * (uint32_t)jb);
+				const int cnt = (int)jj.x < 0 ? cx.n : (int)jj.x;
+				int idx = head - (int)jj.y + cx.tid;                       // in [-Lp, Lp): one conditional wrap
+				if (idx < 0) idx += Lp;
+				uint32_t dst = cx.win + jj.z + (uint32_t)cx.tid * 16u;
+#pragma unroll 1
+				for (int r = cx.tid; r < cnt; r += kStagers, dst += kStagers * 16u)
+				{
+					const uint32_t so = ringB + (uint32_t)idx * 16u;
+#pragma unroll
+					for (int g = 0; g < CG; g++) cp_async16(dst + (uint32_t)g * cx.planeStride, sbase + (so + (uint32_t)g * stepB));
+					idx += kStagers;
+					if (idx >= Lp) idx -= Lp;
+				}
+			}
+		}
+		__device__ __forceinline__ void request_windows(const Ctx& cx, int l, const char* sbase, const int* hd)
+		{
 #ifdef NAB_H_NO_WINDOWS   // timing experiment only (tools/h_timing.cu): results are wrong
-			if ((cx.tid & 31) == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 			return;
 #endif
 			const uint32_t la = cx.tab + (uint32_t)l * (uint32_t)sizeof(HLayer);
-			const int lane = cx.tid & 31;
-			if (lane < 8)
-			{
-				// copy c = (job, plane, run) without a division: planes per row = 4 (16 channels) or 2 (8 channels)
-				const uint4 g1 = lds128(la + 16);
-				const int sh = ((int)g1.w >> 4) + 2;          // log2(2 * planes)
-				const int c = lane * 4 + cx.warp;
-				if (c < ((int)g1.y << sh))
-				{
-					const uint4 g0 = lds128(la);
-					const int Lp = (int)g0.z;
-					const int jb = c >> sh, g = (c >> 1) & ((1 << (sh - 1)) - 1), run = c & 1;
-					const uint4 jj = lds128(la + kTabJobs + 16u * (uint32_t)jb);
-					const int cnt = (int)jj.x < 0 ? cx.n : (int)jj.x;
-					int start = hd[g1.x] - (int)jj.y;
-					if (start < 0) start += Lp;
-					const int run1 = min(cnt, Lp - start);
-					const int rows = run == 0 ? run1 : cnt - run1;
-					if (rows > 0)
-					{
-						const int srcRow = run == 0 ? start : 0, dstRow = run == 0 ? 0 : run1;
-						const uint32_t bytes = (uint32_t)rows * 16u;
-						asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-						bulk_g2s(cx.win + jj.z + (uint32_t)g * cx.planeStride + (uint32_t)dstRow * 16u,
-							sbase + (size_t)(uint32_t)((int)g0.w * 4 + (g * Lp + srcRow) * 16), bytes, bar);
-					}
-				}
-			}
-			__syncwarp();
-			if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+			if (lds32(la + 28u) == 16u) request_windows_cg<4>(cx, la, sbase, hd);
+			else request_windows_cg<2>(cx, la, sbase, hd);
+			cp_async_commit();
 		}
 
 		// Windows of the layer after l (the next layer of this stream, or the first layer of the CTA's next stream).  Its region
 		// of the window buffer may overlap layer l's (HLayer::flags kHLate, decided by PackWaveNetH): then the request must wait
 		// until layer l's conv has read its windows (`afterConv`), else it goes out as early as layer l's own hand-off.
-		__device__ __forceinline__ bool request_next_windows(Ctx& cx, int l, bool afterConv)
+		__device__ __forceinline__ void request_next_windows(const Ctx& cx, int l)
 		{
 			int nl = l + 1;
 			const int* hd = cx.hdb + cx.cur * kHdbHalf;
 			const char* sb = cx.sbase;
 			if (nl >= cx.numLayers)
 			{
-				if (!cx.hasNext) return false;
+				if (!cx.hasNext) return;
 				nl = 0;
 				hd = cx.hdb + (cx.cur ^ 1) * kHdbHalf;
 				sb = cx.sbase + (size_t)cx.gstride * ((size_t)cx.M->stateStride * 4);
 			}
-			const bool late = (lds32(cx.tab + (uint32_t)nl * (uint32_t)sizeof(HLayer) + 76u) & kHLate) != 0;
-			if (late == afterConv) request_windows(cx, nl, sb, hd);
-			return !late;   // an early layer's windows have a whole layer to land: the stagers wait for them off the chain
-		}
-
-		// stagers: the windows counted by wwq have landed
-		__device__ __forceinline__ void wait_windows(Ctx& cx)
-		{
-			if (!mbar_wait(cx.barWin0 + 8u * (cx.wwq & 1u), (cx.wwq >> 1) & 1u) && cx.tid == 0) *reinterpret_cast<volatile int*>(cx.err) = 1;
-			cx.wwq++;
+			request_windows(cx, nl, sb, hd);
 		}
 
 		// C fp32 values -> C words [h1 of channel pairs | h2 of channel pairs]
@@ -314,17 +298,22 @@ namespace nab200
 					const uint32_t cur = myRow + g2.x;
 #pragma unroll
 					for (int q = 0; q < CG; q++) sts128(cur + (uint32_t)q * cx.planeStride, p[4 * q], p[4 * q + 1], p[4 * q + 2], p[4 * q + 3]);
-					asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy rows -> visible to the issuer's tcgen05.cp
 				}
+				// my copies of this layer's history windows (requested a layer ago; after the previous conv where the regions overlap)
+				// have landed; they and the current rows become visible to the issuer's tcgen05.cp (async proxy) with the hand-off
+				cp_async_wait_all();
+				asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 				stager_arrive<kBarT2>();
 				H_STAMP(2);
 				// the delayed taps need no thread: the issuer copies them shared memory -> TMEM (tcgen05.cp) in front of their MMAs.
 				// What the stagers do in the conv's shadow: request the next layer's history windows, write this layer's ring rows.
-				request_next_windows(cx, l, false);
+				const bool nextLate = g2.z != 0;   // the next layer's window region overlaps this layer's (PackWaveNetH)
+				if (!nextLate) request_next_windows(cx, l);
 				H_STAMP(3);
 				// history write-back (AdvanceFrames, WaveNet.h:59-65): frame t becomes ring row (head + t) mod Lp.  The rows replaced
-				// are the oldest ones, which this layer's own window copy reads: it must have landed (requested a layer ago).
-				if (!cx.preWaited) wait_windows(cx);
+				// are the oldest ones, which this layer's own window copies read - possibly another thread's: every stager has
+				// waited for its copies before the hand-off above, so a stagers-only barrier (in the conv's shadow) orders them.
+				nbar_sync<kBarMix, kStagers>();
 				{
 					const int Lp = (int)g0.z;
 					const int first = cx.n > Lp ? cx.n - Lp : 0;
@@ -349,7 +338,11 @@ namespace nab200
 				H_STAMP(7);
 				{
 					uint32_t dv[C], z[C];
-					tmem_ld<C>(lane + MP::d(cx), dv);
+					tmem_ld_nowait<C>(lane + MP::d(cx), dv);
+					// where the next layer's windows overlap this layer's they could not be requested earlier: do it now that the conv
+					// has read them, in front of the activation (their HBM latency is longer than the rest of the layer)
+					if (nextLate) request_next_windows(cx, l);
+					wait_ld();
 #pragma unroll
 					for (int c = 0; c < C; c += 2)
 					{
@@ -360,15 +353,6 @@ namespace nab200
 					tmem_st<C>(lane + MP::tap(cx, 0), dv);
 				}
 				stager_arrive<kBarZ>();
-				// in the shadow of the 1x1: the late request (only where the next layer's windows overlap this layer's), or - for an
-				// early layer, requested a whole layer ago - the wait for its windows, so that the next hand-off implies them and
-				// the issuer does not have to poll for them on the chain
-				cx.preWaited = request_next_windows(cx, l, true);
-				if (cx.preWaited)
-				{
-					wait_windows(cx);
-					asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-				}
 				H_STAMP(8);
 			}
 		}
@@ -449,11 +433,7 @@ namespace nab200
 				}
 				__syncwarp();
 				H_STAMP(3);
-				// this layer's history windows: implied by the hand-off above where the stagers awaited them a layer ago (early layers);
-				// polled here only for a late layer and for the first layer this CTA runs
-				if ((g4.w & kHLate) != 0 || cx.preWaited) issuer_wait(cx, cx.barWin0 + 8u * (cx.winq & 1u), (cx.winq >> 1) & 1u);
-				cx.preWaited = false;
-				cx.winq++;
+				// (this layer's history windows are implied by the hand-off above: every stager waited for its copies before it)
 				H_STAMP(4);
 				if (fast)
 				{
@@ -467,13 +447,15 @@ namespace nab200
 							mma_pairs<C, 1>(MP::d(cx), MP::tap(cx, j), tb16 + (uint32_t)(j * 4 * C), C);
 						}
 						mma_commit(cx.barD);
-						// the other buffer held the previous layer's block, whose MMAs are complete
-						issue_weights(cx, (l + 1 < cx.numLayers) ? l + 1 : 0, 0, cx.wq + 1);
 					}
 					__syncwarp();
 					H_STAMP(5);
 					issuer_release<kBarDReady>(cx, cx.barD, cx.dq & 1u);
 					cx.dq++;
+					// idle until the activated output arrives: request the next layer's weight block (the other buffer held the
+					// previous layer's block, complete long ago; a bulk-copy request costs the issuing warp hundreds of cycles)
+					if (cx.el) issue_weights(cx, (l + 1 < cx.numLayers) ? l + 1 : 0, 0, cx.wq + 1);
+					__syncwarp();
 				}
 				else
 				{
@@ -543,7 +525,7 @@ namespace nab200
 			}
 		}
 
-		constexpr int kNumBars = 6;   // W0, W1, D, X, Win0, Win1 (what follows is read with 16-byte copies: keep the count even)
+		constexpr int kNumBars = 4;   // W0, W1, D, X (what follows is read with 16-byte copies: keep the count even)
 		constexpr int kHeadTaps = 16;                           // A2 head conv kernel size (WaveNet.h:658-660, InternalModel.h:12-20)
 		constexpr int kHeadHistFloats = kHeadTaps * 16;         // per stream: [tap][16 frames] of per-tap head products (15 used)
 		constexpr int kHeadRows = kCur + kHeadTaps - 1;         // scratch rows per tap plane: 15 history + 128 current
@@ -576,14 +558,13 @@ namespace nab200
 			cx.barW0 = smem_u32(&bars[0]);
 			cx.barD = smem_u32(&bars[2]);
 			cx.barX = smem_u32(&bars[3]);
-			cx.barWin0 = smem_u32(&bars[4]);
 			cx.n = n;
 			cx.tid = threadIdx.x;
 			cx.warp = threadIdx.x >> 5;
 			cx.S = S;
 			cx.gstride = gridDim.x;
 			cx.numLayers = M.numLayers;
-			cx.wq = 0; cx.dq = 0; cx.xq = 0; cx.winq = 0; cx.wwq = 0; cx.cur = 0;
+			cx.wq = 0; cx.dq = 0; cx.xq = 0; cx.cur = 0;
 			cx.el = elect_one();
 			const int tid = threadIdx.x, warp = cx.warp;
 			const bool stager = warp < 4;
@@ -603,8 +584,6 @@ namespace nab200
 				mbar_init(cx.barW0 + 8u, 1);
 				mbar_init(cx.barD, 1);
 				mbar_init(cx.barX, 1);
-				mbar_init(cx.barWin0, 4);
-				mbar_init(cx.barWin0 + 8u, 4);
 				asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 			}
 			if (warp == 4)
@@ -636,7 +615,6 @@ namespace nab200
 				const uint32_t ent0 = lds128(cx.tab + (uint32_t)first0 * (uint32_t)sizeof(HLayer) + 64).z;
 				const uint32_t ent1 = ARCH == 0 ? lds128(cx.tab + (uint32_t)first1 * (uint32_t)sizeof(HLayer) + 64).z : 0u;
 				if (cx.el) issue_weights(cx, 0, 0, 0);
-				cx.preWaited = true;   // (issuer: the first layer's windows must be polled for)
 				for (int s = s0; s < S; s += gridDim.x)
 				{
 					H_STAMP_SELECT(s, s0);
@@ -691,7 +669,6 @@ namespace nab200
 				const size_t strideBytes = (size_t)M.stateStride * 4;
 				cx.sbase = reinterpret_cast<char*>(state) + (size_t)s0 * strideBytes;
 				cx.hasNext = false;
-				cx.preWaited = false;
 				if (s0 < S) request_windows(cx, 0, cx.sbase, cx.hdb);
 				for (int s = s0; s < S; s += gridDim.x)
 				{
