@@ -767,7 +767,13 @@ namespace nab200
 			{
 				const long long K = A.kernelSizes[l], d = A.dilations[l], Lp = (K - 1) * d;
 				if (K < 2 || K - 1 > kHMaxTaps) return false;
-				if (single && l == 0 && Lp + 128 > R - 320) return false;   // the head-conv scratch sits at the top of the window buffer
+				// the head-conv scratch (288 rows) sits between the first layer's region (bottom) and the second layer's (top)
+				if (single && l == 0 && Lp + 128 + 288 > R) return false;
+				if (single && l == 1 && A.dilations.size() > 1)
+				{
+					const long long L0 = (long long)(A.kernelSizes[0] - 1) * A.dilations[0];
+					if (L0 + 128 + 288 + Lp + 128 > R) return false;
+				}
 				if (Lp + 128 <= 640 && Lp + 128 <= R) continue;    // one contiguous window
 				if (d < 128 || (K - 1) * 128 > R || K - 1 > kHMaxJobs) return false;   // else every tap needs its own 128-row window
 			}
@@ -782,7 +788,10 @@ namespace nab200
 		M.tc = 3;
 		M.numArrays = (int)desc.arrays.size();
 		const bool single = IsHSingleArray(desc);
-		const int R = single ? 1024 : 512;   // rows per plane of the shared-memory window buffer
+		int R = single ? 1024 : 512;   // rows per plane of the shared-memory window buffer
+#ifdef NAB_H_TOOLS
+		if (getenv("NAB_H_FAKE_R")) R = atoi(getenv("NAB_H_FAKE_R"));   // timing experiments only (tools/h_timing.cu): results are wrong
+#endif
 		M.winRows = R;
 		const float* w = desc.weights.data();
 		int layerIdx = 0, ringIdx = 0, ringOff = 0;
@@ -989,6 +998,20 @@ namespace nab200
 					regionRows = (K - 1) * 128;
 				}
 				T.pad0 = regionRows;
+				T.iUnd16 = T.und16; T.iTap0Base16 = T.tap0Base16; T.iTapStride16 = T.tapStride16;
+				T.iNumTaps = T.numTaps; T.iNumGroups = T.numGroups; T.iGroupTaps = T.groupTaps;
+				{
+					uint32_t fixedBytes = 0, perFrame = 0;
+					for (int j = 0; j < T.numJobs; j++)
+					{
+						if (T.job[j].cnt < 0) perFrame += (uint32_t)CP * 4u;
+						else fixedBytes += (uint32_t)T.job[j].cnt * (uint32_t)CP * 4u;
+					}
+					T.winBytes = fixedBytes | (perFrame << 20);
+				}
+				if (numGroups == 1)
+					for (int j = 0; j < K - 1; j++)
+						if ((K - 1 - j) * d >= 128) T.histMask |= 1u << j;
 				table.push_back(T);
 				layerIdx++;
 			}
@@ -1002,11 +1025,17 @@ namespace nab200
 			// even layers sit at the bottom of the buffer, odd layers at the top: two consecutive layers overlap only when their
 			// rows do not fit side by side
 			for (int i = 0; i < NL; i++) base[i] = (i & 1) ? R - table[i].pad0 : 0;
+			// A2 head-conv scratch of the output stage (288 rows of plane 0): above the first layer's region and below the second
+			// layer's - the two regions the fetcher may be filling for the CTA's next stream while the output stage runs
+			M.headScratchRow = table[0].pad0;
 			for (int i = 0; i < NL; i++)
 			{
 				const int prev = (i + NL - 1) % NL;
 				const bool overlap = NL > 1 ? (base[i] < base[prev] + table[prev].pad0 && base[prev] < base[i] + table[i].pad0) : true;
 				table[i].flags = (table[i].flags & ~kHLate) | (overlap ? kHLate : 0u);
+#ifdef NAB_H_TOOLS
+				if (getenv("NAB_H_FAKE_R")) table[i].flags &= ~kHLate;
+#endif
 			}
 			for (int i = 0; i < NL; i++)
 			{

@@ -76,7 +76,8 @@ namespace nab200
 		int ringLp[kMaxRings];
 		// tc == 3 only: float offset of the HLayer table inside the packed weights, rows per plane of the shared-memory
 		// window buffer, largest weight block in bytes
-		int tableOff, winRows, maxBlockBytes, pad1;
+		int tableOff, winRows, maxBlockBytes;
+		int headScratchRow;   // A2 head-conv scratch: first 16-byte row of it inside plane 0 of the window buffer
 	};
 
 	// fp16-pair packing (WnModelDev::tc == 3), used by wavenet_h_kernels.cu.
@@ -85,7 +86,8 @@ namespace nab200
 	//   tcgen05.mma kind::f16 (K = 16) with fp32 accumulation - the same 22 significant bits as the 3xTF32 split at half the
 	//   TMEM columns, half the MMAs and no split arithmetic when a stored value is reused (tools/tsh_numerics.py).
 	//   Ring row of one frame = C words: [h1 of channel pairs (C/2 words) | h2 of channel pairs (C/2 words)], stored as
-	//   planes [C/4][Lp][4 words] exactly as the operand is staged to TMEM.
+	//   planes [C/4][Lp][4 words] in HBM and in shared memory: the operand's own core-matrix layout, and a window is one or
+	//   two contiguous runs per plane (bulk copies).
 	//   Shared-memory window buffer: [planes][winRows][16 bytes].  Each layer owns a row region [base, base + rows) of it
 	//   (history rows, then - where a tap reads this call's frames - the 128 current rows); consecutive layers get disjoint
 	//   regions where both fit, so a layer's windows are requested (TMA bulk copies) a whole layer ahead; where they cannot
@@ -117,6 +119,8 @@ namespace nab200
 		uint32_t tapStride16, N1, ent16, flags;                // group 4: ent16 inside sub-block 0
 		uint32_t gOff[3]; uint32_t und16;                      // group 5: float offset of each weight sub-block; undelayed tap inside sub-block 0
 		uint32_t gBytes[3]; uint32_t tap0Base16;               // group 6: bytes of each sub-block; first delayed tap of group 0 inside sub-block 0
+		uint32_t histMask, iUnd16, iTap0Base16, iTapStride16;  // group 7 (issuer): bit j of histMask: delayed tap j reads only history (delay >= 128 frames) and is issued ahead of the hand-off; copies of und16 / tap0Base16 / tapStride16
+		int iNumTaps, iNumGroups, iGroupTaps; uint32_t winBytes;   // group 8 (issuer): copies of numTaps / numGroups / groupTaps; (fetcher) bytes of the layer's window copies: fixed part | per-frame part << 20
 		uint32_t tapOff[kHMaxTaps];                            // byte offset (inside a plane) of frame 0's row of delayed tap j
 		HJob job[kHMaxJobs];
 	};

@@ -22,6 +22,10 @@ namespace nab200
 		{
 			asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 		}
+		__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+		{
+			asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+		}
 		// One try_wait blocks in hardware for a bounded time; the loop gives up after `kSpinLimit` failed tries (seconds of
 		// wall time) so that a faulted copy or a lost commit surfaces as a sticky error flag instead of hanging the device.
 		constexpr uint32_t kSpinLimit = 1u << 22;
@@ -52,9 +56,19 @@ namespace nab200
 			asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
 				"r"(bytes), "r"(bar) : "memory");
 		}
+		// bring `bytes` (multiple of 16, 16-byte aligned) of global memory into L2 without a destination
+		__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes)
+		{
+			asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+		}
 		__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src)
 		{
 			asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+		}
+		// arrival on `bar` once all of this thread's earlier cp.async copies have landed (counted in the barrier's initial count)
+		__device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar)
+		{
+			asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 		}
 		__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 		__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
@@ -102,6 +116,17 @@ namespace nab200
 				"setp.ne.b32 p, %4, 0;\n\t"
 				"tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
 				"}\n" ::"r"(tmemD), "r"(tmemA), "l"(db), "r"(idesc), "n"(ACC) : "memory");
+		}
+		// D[tmem] (+)= A[smem] * B[smem]: A in the same no-swizzle K-major core-matrix layout ([k group][row][16 bytes])
+		template <uint32_t ACC>
+		__device__ __forceinline__ void mma_f16_ss(uint32_t tmemD, u64 da, u64 db, uint32_t idesc)
+		{
+			asm volatile(
+				"{\n\t"
+				".reg .pred p;\n\t"
+				"setp.ne.b32 p, %4, 0;\n\t"
+				"tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+				"}\n" ::"r"(tmemD), "l"(da), "l"(db), "r"(idesc), "n"(ACC) : "memory");
 		}
 		__device__ __forceinline__ void mma_commit(uint32_t bar)
 		{

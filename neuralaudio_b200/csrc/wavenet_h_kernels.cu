@@ -1,27 +1,32 @@
-// Batched WaveNet Process() on the Blackwell tensor cores with fp16-PAIR operands in TMEM ("H" kernel), sm_100a.
+// Batched WaveNet Process() on the Blackwell tensor cores with fp16-PAIR operands ("H" kernel), sm_100a.
 // Same contract as the other WaveNet kernels: one call advances S independent streams by n <= 128 frames
 // (reference path WaveNetModelT::Process, WaveNet.h:768-799; layer WaveNetLayerT::Process :462-494; conv :139-290).
 //
-// What changed against the 3xTF32 kernel (wavenet_ts_kernels.cu) and why (round-1 profile: per-stream dependency chain
-// binds, 4 streams per SM capped by 128 TMEM columns each, tensor pipe 53 % busy with 26 MMAs per 16-channel layer):
-//   * every A operand is a pair of fp16 values per element, x ~ h1 + h2 (h1 = rn_f16(x), h2 = rn_f16(x - h1)), every
-//     weight W ~ W1 + W2 on the host; D += h1 W1 + h2 W1 + h1 W2 with kind::f16 MMAs (K = 16 per instruction) and fp32
-//     accumulation: the same 22 significant bits as 3xTF32 (tools/tsh_numerics.py: 3.9e-7 vs 3.6e-7 max-abs on the
-//     reference's own A1 Standard vector), but 16 TMEM columns per 16-channel operand instead of 32, 14 MMAs per
-//     16-channel layer instead of 26, and a stored (h1, h2) row is reused as is:
-//   * the history rings and the shared-memory windows hold the packed pairs (4 bytes per value, as before) in the operand's own
-//     layout, so a delayed tap needs no thread at all: the issuer copies its 128 rows shared memory -> TMEM with tcgen05.cp
-//     (a tap shift is a row offset of the copy's descriptor) right in front of the MMAs that read them, in the same in-order
-//     pipe (tools/cp_probe.cu); the split is computed once per produced value;
-//   * 96 TMEM columns per stream (three 32-column allocations) -> 5 streams in flight per SM instead of 4;
-//   * the residual stream stays an fp32 TMEM accumulator for the whole array (x += W1x1 z + b is the 1x1 MMA itself,
-//     WaveNet.h:486-491), the head sum accumulates as extra N columns of the 1x1 (WaveNet.h:482,658-660), mix-in,
-//     biases and the 1 -> C rechannel ride on a constant operand [c1, c2, c1, 1, 1, 1, 0...] (WaveNet.h:476,637).
-// Roles: warps 0..3 ("stagers", thread t <-> frame t <-> TMEM lane t) build operands and run the activation; warp 4
-// (the "issuer") issues every tcgen05.mma and the weight TMA.  Hand-offs: stagers -> issuer by named barriers the stagers
-// only arrive on; MMA completion -> the issuer's mbarrier (tcgen05.commit), which then releases the stagers through
-// another named barrier.  One issuing thread, fixed order: results do not depend on timing or on how a buffer is cut
-// into calls.
+// Arithmetic: every A operand is a pair of fp16 values per element, x ~ h1 + h2 (h1 = rn_f16(x), h2 = rn_f16(x - h1)), every
+// weight W ~ W1 + W2 on the host; D += h1 W1 + h2 W1 + h1 W2 with kind::f16 MMAs (K = 16 per instruction) and fp32
+// accumulation: the same 22 significant bits as 3xTF32 (tools/tsh_numerics.py).  The residual stream stays an fp32 TMEM
+// accumulator for the whole array (x += W1x1 z + b is the 1x1 MMA itself, WaveNet.h:486-491), the head sum accumulates as
+// extra N columns of the 1x1 (WaveNet.h:482,658-660), mix-in, biases and the 1 -> C rechannel ride on a constant operand
+// [c1, c2, c1, 1, 1, 1, 0...] (WaveNet.h:476,637).
+//
+// Data movement: the history rings hold the packed pairs as planes [C/4][Lp][16 bytes] in HBM; a layer's history window
+// lands in shared memory in the same, the operand's own core-matrix layout (planes [C/4][rows][16 bytes]), so a delayed tap needs no
+// thread at all: its MMAs read their A operand straight from the window (a tap shift is a row offset of the descriptor).
+// Only the undelayed tap and the activated output are staged to TMEM by threads.  64 TMEM columns per stream.
+//
+// Roles (round-2 timing, tools/h_timing.cu: the stager warps' own instruction stream was the per-layer dependency chain,
+// a third of it window requests):
+//   warps 0..3 "stagers": thread t <-> frame t <-> TMEM lane t: residual stream -> packed pairs (undelayed tap, current
+//              rows, ring write-back), activation -> packed pairs;
+//   warp 4 "issuer": every tcgen05.mma and the weight TMA.  The products that do not depend on the layer's input (constant
+//              operand, taps that read only history) are issued while the stagers still pack;
+//   warp 5 "fetcher": all history windows: L2 prefetch two layers ahead, then HBM/L2 ring -> shared memory with bulk copies
+//              (TMA; one lane per contiguous run of rows) one layer ahead, completing by bytes on an mbarrier the issuer (and
+//              the stagers' ring write-back) wait on.
+// Hand-offs: stagers -> issuer by named barriers the stagers only arrive on; MMA completion -> the issuer's mbarrier
+// (tcgen05.commit), which then releases the stagers through another named barrier; conv completion also frees the window
+// region for the fetcher (second commit).  One issuing thread, fixed order: results do not depend on timing or on how a
+// buffer is cut into calls.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stddef.h>
@@ -39,10 +44,14 @@ namespace nab200
 
 		constexpr int kCur = 128;        // frames per pass = TMEM lanes
 		constexpr int kStagers = 128;
-		constexpr int kThreads = 160;
+		constexpr int kSync = 160;       // stagers + issuer: the threads of the hand-off barriers
+		constexpr int kThreads = 192;    // + the fetcher warp
+		constexpr int kWeightThread = 96; // the stager thread that requests weight blocks (warp 3, lane 0)
 		constexpr int kHdbHalf = 72;     // ints per stream in hdb: heads[36] | heads after the call[36]
 		constexpr uint32_t kTabTaps = (uint32_t)offsetof(HLayer, tapOff);
 		constexpr uint32_t kTabJobs = (uint32_t)offsetof(HLayer, job);
+		constexpr uint32_t kTabHist = (uint32_t)offsetof(HLayer, histMask);
+		constexpr uint32_t kTabFlags = (uint32_t)offsetof(HLayer, flags);
 
 		enum : int
 		{
@@ -64,14 +73,17 @@ namespace nab200
 			uint32_t tab;                 // HLayer table
 			int* hdb;                     // [2][kHdbHalf] ring heads of the current / next stream
 			uint32_t barW0, barD, barX;
-			uint32_t r0, r1, r2;          // TMEM: three 32-column regions
+			uint32_t barL0;               // [2] fetcher -> issuer / stagers: history windows and first weight block of an even / odd layer have landed
+			uint32_t barFree0;            // [2] conv of an even / odd layer complete: its window region may be overwritten
+			uint32_t r0;                  // TMEM: 64 columns
 			int n, tid, warp, S, gstride, numLayers;
 			bool el;
-			uint32_t wq, dq, xq;          // issuer: weight-block counter, barD / barX phase counters
+			uint32_t wq, dq, xq, sq, sqr; // weight-block counter; issuer: barD / barX phase counters, sub-blocks awaited / requested (barW phases)
+			bool hasNext;                 // the CTA has another stream after this one
+			uint32_t lq;                  // layers done by this thread since the kernel started (over all its streams): barWin / barFree phases
 			int cur;
 			int* err;
 			char* sbase;                  // stagers: this stream's state
-			bool hasNext;                 // stagers: the CTA has another stream after this one
 #ifdef NAB_H_TIMING
 			bool stampOn; int stampCta, stampStream;
 #endif
@@ -79,7 +91,7 @@ namespace nab200
 
 #ifdef NAB_H_TIMING
 		// tools/h_timing.cu: cycle stamps of one thread per warp of a few CTAs, [cta][warp][stream][layer][stamp]
-		__device__ long long g_stamps[4][5][4][32][12];
+		__device__ long long g_stamps[4][6][4][32][12];
 #define H_STAMP(i) do { if (cx.stampOn) g_stamps[cx.stampCta][cx.warp][cx.stampStream][l][i] = clock64(); } while (0)
 #define H_STAMP_SELECT(s, s0) do { const int k_ = ((s) - (s0)) / (int)gridDim.x; \
 		const int c_ = blockIdx.x == 0 ? 0 : blockIdx.x == 1 ? 1 : blockIdx.x == 300 ? 2 : blockIdx.x == gridDim.x - 1 ? 3 : -1; \
@@ -89,58 +101,57 @@ namespace nab200
 #define H_STAMP_SELECT(s, s0) do { } while (0)
 #endif
 
-		// TMEM column maps.  CONST (8 columns) is always r2 + 24.
-		//   ROLE 0: first array, 16 channels, 8 head columns:  taps r0 + 16 j | T2 r1 | D r1 + 16 | XR r2 | HD r2 + 16
-		//   ROLE 1: second array, 8 channels, 8 head columns:  taps r0 + 8 j | T2 r0 + 16 | D r0 + 24 | XR r1 | HD r1 + 8
-		//           (the transition stages the first array's output pairs at r1 + 16 and its head output pairs at r0)
-		// The activated output z aliases tap 0.
+		// TMEM column maps (64 columns per stream; CONST, 8 columns, is always r0 + 56).  The activated output z reuses the
+		// undelayed tap's columns (the conv has read them by the time the activation runs).
+		//   ROLE 0: first array, 16 channels, 8 head columns:  T2 / z r0 | D r0 + 16 | XR r0 + 32 | HD r0 + 48
+		//   ROLE 1: second array, 8 channels, 8 head columns:  T2 / z r0 | D r0 + 8  | XR r0 + 32 | HD r0 + 40
+		//           (the transition stages the first array's output pairs at r0 and its head output pairs at r0 + 16)
+		//   ROLE 2: single array (A2), 8 channels, 16 head columns (one per head-conv tap, see the output stage):
+		//                                                      T2 / z r0 | D r0 + 8  | XR r0 + 16 | HD r0 + 24
 		template <int ROLE> struct Map;
 		template <> struct Map<0>
 		{
 			static constexpr int C = 16, HN = 8, N1 = 24;
-			static __device__ __forceinline__ uint32_t tap(const Ctx& cx, int j) { return cx.r0 + 16u * (uint32_t)j; }
-			static __device__ __forceinline__ uint32_t t2(const Ctx& cx) { return cx.r1; }
-			static __device__ __forceinline__ uint32_t d(const Ctx& cx) { return cx.r1 + 16u; }
-			static __device__ __forceinline__ uint32_t xr(const Ctx& cx) { return cx.r2; }
-			static __device__ __forceinline__ uint32_t hd(const Ctx& cx) { return cx.r2 + 16u; }
+			static __device__ __forceinline__ uint32_t t2(const Ctx& cx) { return cx.r0; }
+			static __device__ __forceinline__ uint32_t d(const Ctx& cx) { return cx.r0 + 16u; }
+			static __device__ __forceinline__ uint32_t xr(const Ctx& cx) { return cx.r0 + 32u; }
+			static __device__ __forceinline__ uint32_t hd(const Ctx& cx) { return cx.r0 + 48u; }
 		};
 		template <> struct Map<1>
 		{
 			static constexpr int C = 8, HN = 8, N1 = 16;
-			static __device__ __forceinline__ uint32_t tap(const Ctx& cx, int j) { return cx.r0 + 8u * (uint32_t)j; }
-			static __device__ __forceinline__ uint32_t t2(const Ctx& cx) { return cx.r0 + 16u; }
-			static __device__ __forceinline__ uint32_t d(const Ctx& cx) { return cx.r0 + 24u; }
-			static __device__ __forceinline__ uint32_t xr(const Ctx& cx) { return cx.r1; }
-			static __device__ __forceinline__ uint32_t hd(const Ctx& cx) { return cx.r1 + 8u; }
+			static __device__ __forceinline__ uint32_t t2(const Ctx& cx) { return cx.r0; }
+			static __device__ __forceinline__ uint32_t d(const Ctx& cx) { return cx.r0 + 8u; }
+			static __device__ __forceinline__ uint32_t xr(const Ctx& cx) { return cx.r0 + 32u; }
+			static __device__ __forceinline__ uint32_t hd(const Ctx& cx) { return cx.r0 + 40u; }
 		};
-		//   ROLE 2: single array (A2), 8 channels, 16 head columns (one per head-conv tap, see the output stage):
-		//           taps r0 + 8 j (j < 4), r1 + 8 (j - 4) (j = 4, 5) | T2 r1 + 16 | D r1 + 24 | XR r2 | HD r2 + 8
 		template <> struct Map<2>
 		{
 			static constexpr int C = 8, HN = 16, N1 = 24;
-			static __device__ __forceinline__ uint32_t tap(const Ctx& cx, int j) { return j < 4 ? cx.r0 + 8u * (uint32_t)j : cx.r1 + 8u * (uint32_t)(j - 4); }
-			static __device__ __forceinline__ uint32_t t2(const Ctx& cx) { return cx.r1 + 16u; }
-			static __device__ __forceinline__ uint32_t d(const Ctx& cx) { return cx.r1 + 24u; }
-			static __device__ __forceinline__ uint32_t xr(const Ctx& cx) { return cx.r2; }
-			static __device__ __forceinline__ uint32_t hd(const Ctx& cx) { return cx.r2 + 8u; }
+			static __device__ __forceinline__ uint32_t t2(const Ctx& cx) { return cx.r0; }
+			static __device__ __forceinline__ uint32_t d(const Ctx& cx) { return cx.r0 + 8u; }
+			static __device__ __forceinline__ uint32_t xr(const Ctx& cx) { return cx.r0 + 16u; }
+			static __device__ __forceinline__ uint32_t hd(const Ctx& cx) { return cx.r0 + 24u; }
 		};
-		__device__ __forceinline__ uint32_t konst(const Ctx& cx) { return cx.r2 + 24u; }
+		__device__ __forceinline__ uint32_t konst(const Ctx& cx) { return cx.r0 + 56u; }
 
 		// ---- hand-offs -------------------------------------------------------------------------------------------
 		template <int ID> __device__ __forceinline__ void stager_arrive()
 		{
 			wait_st();
 			fence_before();
-			nbar_arrive<ID, kThreads>();
+			nbar_arrive<ID, kSync>();
 		}
+		// (Measured, round 2: stagers waiting on the commit mbarriers themselves - no relay through the issuer - made the whole
+		// SM slower: 16 polling warps per SM; a named barrier parks a warp for free.)
 		template <int ID> __device__ __forceinline__ void stager_wait()
 		{
-			nbar_sync<ID, kThreads>();
+			nbar_sync<ID, kSync>();
 			fence_after();
 		}
 		template <int ID> __device__ __forceinline__ void issuer_sync()
 		{
-			nbar_sync<ID, kThreads>();
+			nbar_sync<ID, kSync>();
 			fence_after();
 		}
 		__device__ __forceinline__ void issuer_wait(Ctx& cx, uint32_t bar, uint32_t parity)
@@ -150,78 +161,138 @@ namespace nab200
 		template <int ID> __device__ __forceinline__ void issuer_release(Ctx& cx, uint32_t bar, uint32_t parity)
 		{
 			issuer_wait(cx, bar, parity);
-			nbar_arrive<ID, kThreads>();
+			nbar_arrive<ID, kSync>();
 		}
 
 		// one lane: bulk copy of sub-block g of layer b's weights into buffer (slot & 1)
-		__device__ __forceinline__ void issue_weights(const Ctx& cx, int b, int g, uint32_t slot)
+		__device__ __forceinline__ void request_weights(const Ctx& cx, int b, int g, uint32_t slot, uint32_t bar)
 		{
 			const uint32_t la = cx.tab + (uint32_t)b * (uint32_t)sizeof(HLayer);
 			const uint32_t off = lds32(la + 80u + 4u * (uint32_t)g), bytes = lds32(la + 96u + 4u * (uint32_t)g);
-			const uint32_t bar = cx.barW0 + 8u * (slot & 1u);
 			mbar_expect_tx(bar, bytes);
 			bulk_g2s(cx.wbuf + (slot & 1u) * cx.wbufStride, cx.Wg + off, bytes, bar);
 		}
 
-		// Stager warps (all 128 threads call it): the history window(s) of layer l of the stream whose state starts at `sbase`,
-		// HBM ring -> shared memory with cp.async: a window job is rows r in [0, cnt) <- ring rows (head - back + r) mod Lp, thread t
-		// copies rows t, t + 128, ... (16 bytes per plane and row; a warp moves contiguous 512-byte runs).  One cp.async group
-		// per request; the thread that issued a copy waits for it (cp.async.wait_group) before its next hand-off.
-		// (Measured, round 2: the same windows as TMA bulk copies - 8 to 16 small requests per layer and CTA - took ~2000 cycles
-		// to land under load against ~1200 for these; their request cost was no lower either.)
-		template <int CG>
-		__device__ __forceinline__ void request_windows_cg(const Ctx& cx, uint32_t la, const char* sbase, const int* hd)
+		// ---- fetcher warp ----------------------------------------------------------------------------------------------
+		// History windows of every layer of every stream of this CTA, in the order the issuer consumes them.  A window job is
+		// rows r in [0, cnt) <- ring rows (head - back + r) mod Lp; lane i copies rows i, i + 32, ... (one ring row = CG x 16
+		// contiguous bytes -> one 16-byte row in each of CG planes).  Layer g's region of the window buffer is free once the conv
+		// of layer g - 2 has completed (consecutive layers own disjoint regions) or, where the two regions overlap (kHLate,
+		// PackWaveNetH), the conv of layer g - 1.
+		// One layer's window jobs as bulk copies (TMA): a job is rows r in [0, cnt) <- ring rows (head - back + r) mod Lp of every
+		// plane, i.e. one or two contiguous runs of 16-byte rows per plane; item = (job, plane, run), one lane per item.
+		// PREFETCH: the same runs as L2 prefetches (no destination).
+		template <bool PREFETCH, int CG>
+		__device__ __forceinline__ void window_items(const Ctx& cx, uint32_t la, const char* ring, int head, int Lp, int numJobs, uint32_t bar, int lane)
 		{
-			const uint4 g0 = lds128(la), g1 = lds128(la + 16);
-			const int Lp = (int)g0.z, numJobs = (int)g1.y;
-			const int head = hd[g1.x];
-			const uint32_t ringB = g0.w * 4u, stepB = (uint32_t)Lp * 16u;
+			const int items = numJobs * CG * 2;
 #pragma unroll 1
-			for (int jb = 0; jb < numJobs; jb++)
+			for (int it = lane; it < items; it += 32)
 			{
+				const int run = it & 1, q = (it >> 1) & (CG - 1), jb = it / (2 * CG);
 				const uint4 jj = lds128(la + kTabJobs + 16u * (uint32_t)jb);
 				const int cnt = (int)jj.x < 0 ? cx.n : (int)jj.x;
-				int idx = head - (int)jj.y + cx.tid;                       // in [-Lp, Lp): one conditional wrap
-				if (idx < 0) idx += Lp;
-				uint32_t dst = cx.win + jj.z + (uint32_t)cx.tid * 16u;
-#pragma unroll 1
-				for (int r = cx.tid; r < cnt; r += kStagers, dst += kStagers * 16u)
+				int idx0 = head - (int)jj.y;                          // in [-Lp, Lp)
+				if (idx0 < 0) idx0 += Lp;
+				const int run0 = (idx0 + cnt <= Lp) ? cnt : Lp - idx0;
+				const int first = run ? 0 : idx0, rows = run ? cnt - run0 : run0, dstRow = run ? run0 : 0;
+				if (rows > 0)
 				{
-					const uint32_t so = ringB + (uint32_t)idx * 16u;
-#pragma unroll
-					for (int g = 0; g < CG; g++) cp_async16(dst + (uint32_t)g * cx.planeStride, sbase + (so + (uint32_t)g * stepB));
-					idx += kStagers;
-					if (idx >= Lp) idx -= Lp;
+					const char* src = ring + (size_t)(uint32_t)(q * Lp + first) * 16;
+					if (PREFETCH) bulk_prefetch_l2(src, (uint32_t)rows * 16u);
+					else bulk_g2s(cx.win + jj.z + (uint32_t)q * cx.planeStride + (uint32_t)dstRow * 16u, src, (uint32_t)rows * 16u, bar);
 				}
 			}
 		}
-		__device__ __forceinline__ void request_windows(const Ctx& cx, int l, const char* sbase, const int* hd)
+
+		// L2 prefetch of layer li's history windows of the stream whose state starts at `sbase`
+		__device__ __forceinline__ void prefetch_windows(const Ctx& cx, int li, const char* sbase, int hA, int hB, int lane)
 		{
-#ifdef NAB_H_NO_WINDOWS   // timing experiment only (tools/h_timing.cu): results are wrong
-			return;
-#endif
-			const uint32_t la = cx.tab + (uint32_t)l * (uint32_t)sizeof(HLayer);
-			if (lds32(la + 28u) == 16u) request_windows_cg<4>(cx, la, sbase, hd);
-			else request_windows_cg<2>(cx, la, sbase, hd);
-			cp_async_commit();
+			const uint32_t la = cx.tab + (uint32_t)li * (uint32_t)sizeof(HLayer);
+			const uint4 g0 = lds128(la), g1 = lds128(la + 16);
+			const int ringIdx = (int)g1.x;
+			const int head = __shfl_sync(0xffffffffu, ringIdx < 32 ? hA : hB, ringIdx & 31);
+			if (g1.w == 16u) window_items<true, 4>(cx, la, sbase + (size_t)g0.w * 4, head, (int)g0.z, (int)g1.y, 0u, lane);
+			else window_items<true, 2>(cx, la, sbase + (size_t)g0.w * 4, head, (int)g0.z, (int)g1.y, 0u, lane);
 		}
 
-		// Windows of the layer after l (the next layer of this stream, or the first layer of the CTA's next stream).  Its region
-		// of the window buffer may overlap layer l's (HLayer::flags kHLate, decided by PackWaveNetH): then the request must wait
-		// until layer l's conv has read its windows (`afterConv`), else it goes out as early as layer l's own hand-off.
-		__device__ __forceinline__ void request_next_windows(const Ctx& cx, int l)
+		__device__ __forceinline__ void fetch_loop(Ctx& cx, const int* __restrict__ heads, int s0)
 		{
-			int nl = l + 1;
-			const int* hd = cx.hdb + cx.cur * kHdbHalf;
-			const char* sb = cx.sbase;
-			if (nl >= cx.numLayers)
+#ifdef NAB_H_TIMING
+			int l = 0;
+#endif
+#ifdef NAB_H_L2_PREFETCH
+			constexpr int kAhead = 2;   // layers between a window's L2 prefetch and its copy to shared memory
+#else
+			constexpr int kAhead = 0;   // no L2 prefetch (round-2 timing: each bulk request costs the issuing warp ~100 cycles; the copies land in time without)
+#endif
+			const int lane = cx.tid & 31;
+			const int numRings = cx.M->numRings;
+			const size_t strideBytes = (size_t)cx.M->stateStride * 4;
+			uint32_t gl = 0;
+			// ring heads of a stream: lane i holds rings i and 32 + i
+			int hA = 0, hB = 0;
+			if (s0 < cx.S)
 			{
-				if (!cx.hasNext) return;
-				nl = 0;
-				hd = cx.hdb + (cx.cur ^ 1) * kHdbHalf;
-				sb = cx.sbase + (size_t)cx.gstride * ((size_t)cx.M->stateStride * 4);
+				hA = lane < numRings ? heads[(size_t)s0 * numRings + lane] : 0;
+				hB = lane + 32 < numRings ? heads[(size_t)s0 * numRings + 32 + lane] : 0;
+#ifndef NAB_H_NO_WINDOWS
+				for (int li = 0; li < kAhead && li < cx.numLayers; li++)
+					prefetch_windows(cx, li, reinterpret_cast<const char*>(cx.state) + (size_t)s0 * strideBytes, hA, hB, lane);
+#endif
 			}
-			request_windows(cx, nl, sb, hd);
+			for (int s = s0; s < cx.S; s += cx.gstride)
+			{
+				H_STAMP_SELECT(s, s0);
+				const int sn = s + cx.gstride;
+				int hAn = 0, hBn = 0;
+				if (sn < cx.S)
+				{
+					hAn = lane < numRings ? heads[(size_t)sn * numRings + lane] : 0;
+					hBn = lane + 32 < numRings ? heads[(size_t)sn * numRings + 32 + lane] : 0;
+				}
+				const char* sbase = reinterpret_cast<const char*>(cx.state) + (size_t)s * strideBytes;
+#pragma unroll 1
+				for (int li = 0; li < cx.numLayers; li++, gl++)
+				{
+#ifdef NAB_H_TIMING
+					l = li;
+#endif
+					const uint32_t la = cx.tab + (uint32_t)li * (uint32_t)sizeof(HLayer);
+					const uint4 g0 = lds128(la), g1 = lds128(la + 16);
+					const uint32_t flags = lds32(la + kTabFlags);
+					const int ringIdx = (int)g1.x;
+					const int head = __shfl_sync(0xffffffffu, ringIdx < 32 ? hA : hB, ringIdx & 31);
+					H_STAMP(0);
+#ifndef NAB_H_NO_WINDOWS   // timing experiment only (tools/h_timing.cu): results are wrong
+					// HBM latency is paid here, kAhead layers before the rows are needed, with no shared memory held for it
+					if (kAhead > 0)
+					{
+						if (li + kAhead < cx.numLayers) prefetch_windows(cx, li + kAhead, sbase, hA, hB, lane);
+						else if (sn < cx.S) prefetch_windows(cx, li + kAhead - cx.numLayers, sbase + (size_t)cx.gstride * strideBytes, hAn, hBn, lane);
+					}
+#endif
+					const int c = (int)gl - ((flags & kHLate) ? 1 : 2);
+					if (c >= 0 && !mbar_wait(cx.barFree0 + 8u * ((uint32_t)c & 1u), ((uint32_t)c >> 1) & 1u) && lane == 0) *reinterpret_cast<volatile int*>(cx.err) = 1;
+					H_STAMP(1);
+					const uint32_t bar = cx.barL0 + 8u * (gl & 1u);
+#ifndef NAB_H_NO_WINDOWS
+					// the copies complete on the barrier by bytes; lane 0's arrival carries the total (known from the plan)
+					if (lane == 0)
+					{
+						const uint32_t wbytes = lds32(la + kTabHist + 28u);
+						mbar_expect_tx(bar, (wbytes & 0xFFFFFu) + (wbytes >> 20) * (uint32_t)cx.n);
+					}
+					if (g1.w == 16u) window_items<false, 4>(cx, la, sbase + (size_t)g0.w * 4, head, (int)g0.z, (int)g1.y, bar, lane);
+					else window_items<false, 2>(cx, la, sbase + (size_t)g0.w * 4, head, (int)g0.z, (int)g1.y, bar, lane);
+#else
+					if (lane == 0) mbar_arrive(bar);
+#endif
+					H_STAMP(2);
+					H_STAMP(3);
+				}
+				hA = hAn; hB = hBn;
+			}
 		}
 
 		// C fp32 values -> C words [h1 of channel pairs | h2 of channel pairs]
@@ -266,7 +337,7 @@ namespace nab200
 
 		// ---- stager warps: one layer array of the CTA's stream ------------------------------------------------------
 		template <int ROLE>
-		__device__ __forceinline__ void stage_array(Ctx& cx, const int firstLayer, const int numLayers, const int a1First)
+		__device__ __forceinline__ void stage_array(Ctx& cx, const int firstLayer, const int numLayers)
 		{
 			typedef Map<ROLE> MP;
 			constexpr int C = MP::C, CG = C / 4;
@@ -279,7 +350,7 @@ namespace nab200
 			{
 				const int l = firstLayer + li;
 				const uint32_t la = cx.tab + (uint32_t)l * (uint32_t)sizeof(HLayer);
-				const uint4 g0 = lds128(la), g1 = lds128(la + 16), g2 = lds128(la + 32);
+				const uint4 g0 = lds128(la), g1 = lds128(la + 16);
 				const bool mixed = g0.y != 0;
 
 				// ---- the residual stream after the previous layer -> packed pairs: undelayed tap, current rows, ring ----
@@ -295,25 +366,32 @@ namespace nab200
 				tmem_st<C>(lane + MP::t2(cx), p);
 				if (mixed)
 				{
-					const uint32_t cur = myRow + g2.x;
+					// a delayed tap shorter than the call reads this call's frames: they follow the history rows in the window
+					const uint32_t cur = myRow + lds32(la + 32u);
 #pragma unroll
 					for (int q = 0; q < CG; q++) sts128(cur + (uint32_t)q * cx.planeStride, p[4 * q], p[4 * q + 1], p[4 * q + 2], p[4 * q + 3]);
+					asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy rows -> the tensor core's async-proxy reads
 				}
-				// my copies of this layer's history windows (requested a layer ago; after the previous conv where the regions overlap)
-				// have landed; they and the current rows become visible to the issuer's tcgen05.cp (async proxy) with the hand-off
-				cp_async_wait_all();
-				asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 				stager_arrive<kBarT2>();
 				H_STAMP(2);
-				// the delayed taps need no thread: the issuer copies them shared memory -> TMEM (tcgen05.cp) in front of their MMAs.
-				// What the stagers do in the conv's shadow: request the next layer's history windows, write this layer's ring rows.
-				const bool nextLate = g2.z != 0;   // the next layer's window region overlaps this layer's (PackWaveNetH)
-				if (!nextLate) request_next_windows(cx, l);
+				// ---- the next layer's first weight block, a layer ahead (one thread): the buffer it goes to held the previous layer's
+				// block, whose last readers - that layer's 1x1 products - completed before this layer began.  (A layer with tap
+				// groups streams its sub-blocks and the block after them from the issuer.)
+				{
+					const int ng = (int)lds32(la + 36u);
+					if (ng == 1 && tid == kWeightThread)
+					{
+						const int nl = l + 1 < cx.numLayers ? l + 1 : (cx.hasNext ? 0 : -1);
+						if (nl >= 0) request_weights(cx, nl, 0, cx.wq + 1, cx.barL0 + 8u * ((cx.lq + 1u) & 1u));
+					}
+					cx.wq += (uint32_t)ng;
+				}
+				// ---- history write-back (AdvanceFrames, WaveNet.h:59-65) in the conv's shadow: frame t becomes ring row (head + t) mod Lp.
+				// The rows replaced are the oldest ones, which this layer's own window copies read: wait until the fetcher has
+				// published them (long done as a rule: the issuer needed them before the conv).
+				if (!mbar_wait(cx.barL0 + 8u * (cx.lq & 1u), (cx.lq >> 1) & 1u) && tid == 0) *reinterpret_cast<volatile int*>(cx.err) = 1;
+				cx.lq++;
 				H_STAMP(3);
-				// history write-back (AdvanceFrames, WaveNet.h:59-65): frame t becomes ring row (head + t) mod Lp.  The rows replaced
-				// are the oldest ones, which this layer's own window copies read - possibly another thread's: every stager has
-				// waited for its copies before the hand-off above, so a stagers-only barrier (in the conv's shadow) orders them.
-				nbar_sync<kBarMix, kStagers>();
 				{
 					const int Lp = (int)g0.z;
 					const int first = cx.n > Lp ? cx.n - Lp : 0;
@@ -338,11 +416,7 @@ namespace nab200
 				H_STAMP(7);
 				{
 					uint32_t dv[C], z[C];
-					tmem_ld_nowait<C>(lane + MP::d(cx), dv);
-					// where the next layer's windows overlap this layer's they could not be requested earlier: do it now that the conv
-					// has read them, in front of the activation (their HBM latency is longer than the rest of the layer)
-					if (nextLate) request_next_windows(cx, l);
-					wait_ld();
+					tmem_ld<C>(lane + MP::d(cx), dv);
 #pragma unroll
 					for (int c = 0; c < C; c += 2)
 					{
@@ -350,186 +424,253 @@ namespace nab200
 						else fast_tanh2(dv[c], dv[c + 1], z[c], z[c + 1]);
 					}
 					pack_pairs<C>(z, dv);
-					tmem_st<C>(lane + MP::tap(cx, 0), dv);
+					tmem_st<C>(lane + MP::t2(cx), dv);
 				}
 				stager_arrive<kBarZ>();
 				H_STAMP(8);
 			}
 		}
 
-		// 128 rows of a shared-memory window (plane layout, 16 bytes per row and plane) -> a tap's TMEM columns
-		template <int C>
-		__device__ __forceinline__ void tap_copy(uint32_t tmemCol, uint32_t row16, uint32_t lbo16)
-		{
-			asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(tmemCol), "l"(desc_at(row16, lbo16)) : "memory");
-			if constexpr (C == 16)
-				asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(tmemCol + 8u), "l"(desc_at(row16 + 2u * lbo16, lbo16)) : "memory");
-		}
+		// Descriptor low words (address and leading-dimension offset in 16-byte units); the high word is a constant.
+		__device__ __forceinline__ uint32_t desc_lo(uint32_t addr16, uint32_t lbo16) { return addr16 | (lbo16 << 16); }
+		__device__ __forceinline__ u64 desc_of(uint32_t lo) { return ((u64)kDescHi << 32) | lo; }
 
 		// conv-type product into accumulator `acc`: A at TMEM `a` (C == 16: h1 at a, h2 at a + 8; C == 8: [h1 | h2] at a),
-		// weights at 16-byte unit `b16` (C == 16: W1 | W2, 2 N units each; C == 8: [W1; W1] | [W2; 0])
-		template <int C, uint32_t ACC0>
-		__device__ __forceinline__ void mma_pairs(uint32_t acc, uint32_t a, uint32_t b16, int N)
+		// weights b0 | b1 (C == 16: W1 | W2; C == 8: [W1; W1] | [W2; 0]): D += h1 W1 + h2 W1 + h1 W2
+		template <int C>
+		__device__ __forceinline__ void mma_pairs(uint32_t acc, uint32_t a, uint32_t b0, uint32_t b1, uint32_t id)
 		{
-			const uint32_t id = idesc_f16(N);
 			if constexpr (C == 16)
 			{
-				mma_f16_ts<ACC0>(acc, a, desc_at(b16, (uint32_t)N), id);
-				mma_f16_ts<1>(acc, a + 8u, desc_at(b16, (uint32_t)N), id);
-				mma_f16_ts<1>(acc, a, desc_at(b16 + 2u * (uint32_t)N, (uint32_t)N), id);
+				mma_f16_ts<1>(acc, a, desc_of(b0), id);
+				mma_f16_ts<1>(acc, a + 8u, desc_of(b0), id);
+				mma_f16_ts<1>(acc, a, desc_of(b1), id);
 			}
 			else
 			{
-				mma_f16_ts<ACC0>(acc, a, desc_at(b16, (uint32_t)N), id);
-				mma_f16_ts<1>(acc, a, desc_at(b16 + 2u * (uint32_t)N, (uint32_t)N), id);
+				mma_f16_ts<1>(acc, a, desc_of(b0), id);
+				mma_f16_ts<1>(acc, a, desc_of(b1), id);
+			}
+		}
+
+		// the same product with the A operand read from the shared-memory window: 128 rows, planes a0 (h1; C == 8: [h1 | h2])
+		// and a1 (h2) as descriptors (a delayed tap is a row offset into the layer's window)
+		template <int C>
+		__device__ __forceinline__ void mma_pairs_ss(uint32_t acc, uint32_t a0, uint32_t a1, uint32_t b0, uint32_t b1, uint32_t id)
+		{
+			if constexpr (C == 16)
+			{
+				mma_f16_ss<1>(acc, desc_of(a0), desc_of(b0), id);
+				mma_f16_ss<1>(acc, desc_of(a1), desc_of(b0), id);
+				mma_f16_ss<1>(acc, desc_of(a0), desc_of(b1), id);
+			}
+			else
+			{
+				mma_f16_ss<1>(acc, desc_of(a0), desc_of(b0), id);
+				mma_f16_ss<1>(acc, desc_of(a0), desc_of(b1), id);
 			}
 		}
 
 		// ---- issuer warp: one layer array of the CTA's stream --------------------------------------------------------
+		// What the issuer knows about a layer before its hand-offs: the plan out of the table and every operand descriptor.
+		template <int NT>
+		struct LayerPlan
+		{
+			uint32_t la, wb16, histMask;
+			bool fast;
+			uint32_t convC, und, one[3];   // B descriptors: constant operand of the conv, undelayed tap (W1; W2 follows 2 C units on), 1x1 (constant operand, W1, W2)
+			uint32_t tapA[NT], tapB[NT];   // delayed taps (unrolled path): window rows (h1 plane; h2 two planes on), weights (W1; W2 2 C units on)
+		};
+
+		// No waiting (runs while the issuer would idle: the stagers' activation): layer l's plan; `block` = number of its first weight block.
+		template <int C, int N1, int NT>
+		__device__ __forceinline__ void plan_layer(const Ctx& cx, int l, uint32_t block, LayerPlan<NT>& P)
+		{
+			const uint32_t la = cx.tab + (uint32_t)l * (uint32_t)sizeof(HLayer);
+			const uint4 g3 = lds128(la + 48), g7 = lds128(la + kTabHist), g8 = lds128(la + kTabHist + 16u), o0 = lds128(la + kTabTaps);
+			const uint32_t o4 = NT > 4 ? lds32(la + kTabTaps + 16u) : 0u;
+			P.la = la;
+			P.histMask = g7.x;
+			P.fast = (int)g8.y == 1 && (int)g8.x == NT;
+			const uint32_t wb16 = (cx.wbuf + (block & 1u) * cx.wbufStride) >> 4;
+			P.wb16 = wb16;
+			P.convC = desc_lo(wb16 + g3.x, C);
+			P.und = desc_lo(wb16 + g7.y, C);
+			P.one[0] = desc_lo(wb16 + g3.w, N1); P.one[1] = desc_lo(wb16 + g3.y, N1); P.one[2] = desc_lo(wb16 + g3.z, N1);
+			const uint32_t win16 = cx.win >> 4, lbo16 = cx.planeStride >> 4, tb16 = wb16 + g7.z;
+			const uint32_t off[5] = { o0.x, o0.y, o0.z, o0.w, o4 };
+#pragma unroll
+			for (int j = 0; j < NT; j++)
+			{
+				P.tapA[j] = desc_lo(win16 + (off[j] >> 4), lbo16);
+				P.tapB[j] = desc_lo(tb16 + (uint32_t)(j * 4 * C), C);
+			}
+		}
+
+		// What does not depend on the layer's input, issued while the stagers pack it: the constant-operand product (mix-in +
+		// conv bias, WaveNet.h:471-476; it overwrites the accumulator) and the delayed taps that read only history.  The
+		// layer's first weight block and its history windows must have landed (wait_layer).
+		template <int ROLE, int NT>
+		__device__ __forceinline__ void early_products(Ctx& cx, const LayerPlan<NT>& P)
+		{
+			typedef Map<ROLE> MP;
+			constexpr int C = MP::C;
+			if (cx.el)
+			{
+				const uint32_t id = idesc_f16(C);
+				mma_f16_ts<0>(MP::d(cx), konst(cx), desc_of(P.convC), id);
+				if (P.fast)
+				{
+#pragma unroll
+					for (int j = 0; j < NT; j++)
+						if ((P.histMask >> j) & 1u) mma_pairs_ss<C>(MP::d(cx), P.tapA[j], P.tapA[j] + 2u * (cx.planeStride >> 4), P.tapB[j], P.tapB[j] + 2u * C, id);
+				}
+			}
+			__syncwarp();
+		}
+		__device__ __forceinline__ void wait_layer(Ctx& cx, uint32_t lq)
+		{
+			issuer_wait(cx, cx.barL0 + 8u * (lq & 1u), (lq >> 1) & 1u);   // the fetcher's bulk copies: windows + first weight block
+		}
+
 		template <int ROLE>
 		__device__ __forceinline__ void issue_array(Ctx& cx, const int firstLayer, const int numLayers)
 		{
 			typedef Map<ROLE> MP;
 			constexpr int C = MP::C, N1 = MP::N1;
 			constexpr int NT = ROLE == 2 ? 5 : 2;   // the delayed-tap count with an unrolled path (K = 6 / K = 3)
+			const uint32_t idC = idesc_f16(C), idN1 = idesc_f16(N1);
+			LayerPlan<NT> P, Q;
+			plan_layer<C, N1, NT>(cx, firstLayer, cx.wq, P);
+			wait_layer(cx, cx.lq);
+			early_products<ROLE, NT>(cx, P);
 #pragma unroll 1
 			for (int li = 0; li < numLayers; li++)
 			{
 				const int l = firstLayer + li;
-				const uint32_t la = cx.tab + (uint32_t)l * (uint32_t)sizeof(HLayer);
-				const int numTaps = (int)lds32(la);
-				const uint4 g2 = lds128(la + 32), g3 = lds128(la + 48), g4 = lds128(la + 64);
-				const int numGroups = (int)g2.y, groupTaps = (int)g2.w;
-				const uint32_t tapStride16 = g4.x;
-				const uint32_t und16 = lds32(la + 92u), tap0Base16 = lds32(la + 108u);
-				uint32_t wb16 = 0;
-				H_STAMP(0);
-
-				// ---- dilated conv + mix-in + bias (WaveNet.h:250-289,471-476): undelayed tap, constant operand, delayed taps ----
-				// A delayed tap is 128 rows of the shared-memory window starting at its own row offset: tcgen05.cp moves them to the
-				// tap's TMEM columns (two planes = 8 columns per copy) and the MMAs behind it in the same pipe read them.
-				// Everything the products need is computed BEFORE the hand-offs; the next weight block is requested AFTER the conv has
-				// been committed (round 2 timing: a bulk-copy request costs the issuing warp hundreds of cycles under contention).
-				const uint32_t win16 = cx.win >> 4, lbo16 = cx.planeStride >> 4;
-				const bool fast = numGroups == 1 && numTaps == NT;
-				uint32_t row16[NT];
-				{
-					const uint4 o0 = lds128(la + kTabTaps);
-					row16[0] = win16 + (o0.x >> 4);
-					if (NT > 1) row16[1] = win16 + (o0.y >> 4);
-					if (NT > 2) { row16[2] = win16 + (o0.z >> 4); row16[3] = win16 + (o0.w >> 4); }
-					if (NT > 4) row16[4] = win16 + (lds32(la + kTabTaps + 16u) >> 4);
-				}
-				// this layer's first weight block (the first one of an array was awaited by the entry / transition code)
-				if (li > 0) issuer_wait(cx, cx.barW0 + 8u * (cx.wq & 1u), (cx.wq >> 1) & 1u);
-				wb16 = (cx.wbuf + (cx.wq & 1u) * cx.wbufStride) >> 4;
-				H_STAMP(1);
-				issuer_sync<kBarT2>();
+				const bool hasNext = li + 1 < numLayers;
+				uint32_t wb16 = P.wb16;
 				H_STAMP(2);
-				if (cx.el)
-				{
-					mma_pairs<C, 0>(MP::d(cx), MP::t2(cx), wb16 + und16, C);   // overwrites the accumulator
-					mma_f16_ts<1>(MP::d(cx), konst(cx), desc_at(wb16 + g3.x, C), idesc_f16(C));
-				}
-				__syncwarp();
+
+				// ---- dilated conv (WaveNet.h:250-289): the undelayed tap and the delayed taps that read this call's frames ----
+				// A delayed tap is 128 rows of the shared-memory window starting at its own row offset: the MMAs read them in place.
+				issuer_sync<kBarT2>();
 				H_STAMP(3);
-				// (this layer's history windows are implied by the hand-off above: every stager waited for its copies before it)
-				H_STAMP(4);
-				if (fast)
+				if (P.fast)
 				{
 					if (cx.el)
 					{
-						const uint32_t tb16 = wb16 + tap0Base16;
+						mma_pairs<C>(MP::d(cx), MP::t2(cx), P.und, P.und + 2u * C, idC);
 #pragma unroll
 						for (int j = 0; j < NT; j++)
-						{
-							tap_copy<C>(MP::tap(cx, j), row16[j], lbo16);
-							mma_pairs<C, 1>(MP::d(cx), MP::tap(cx, j), tb16 + (uint32_t)(j * 4 * C), C);
-						}
+							if (!((P.histMask >> j) & 1u)) mma_pairs_ss<C>(MP::d(cx), P.tapA[j], P.tapA[j] + 2u * (cx.planeStride >> 4), P.tapB[j], P.tapB[j] + 2u * C, idC);
 						mma_commit(cx.barD);
+						mma_commit(cx.barFree0 + 8u * (cx.lq & 1u));
 					}
 					__syncwarp();
 					H_STAMP(5);
 					issuer_release<kBarDReady>(cx, cx.barD, cx.dq & 1u);
 					cx.dq++;
-					// idle until the activated output arrives: request the next layer's weight block (the other buffer held the
-					// previous layer's block, complete long ago; a bulk-copy request costs the issuing warp hundreds of cycles)
-					if (cx.el) issue_weights(cx, (l + 1 < cx.numLayers) ? l + 1 : 0, 0, cx.wq + 1);
-					__syncwarp();
 				}
 				else
 				{
+					// more delayed taps than one weight block carries (K = 15): tap groups, their sub-blocks streamed through the buffers
+					const uint32_t win16 = cx.win >> 4, lbo16 = cx.planeStride >> 4;
+					const uint4 g3 = lds128(P.la + 48), g7 = lds128(P.la + kTabHist), g8 = lds128(P.la + kTabHist + 16u);
+					const int numTaps = (int)g8.x, numGroups = (int)g8.y, groupTaps = (int)g8.z;
+					if (cx.el) mma_pairs<C>(MP::d(cx), MP::t2(cx), P.und, P.und + 2u * C, idC);
 #pragma unroll 1
 					for (int g = 0; g < numGroups; g++)
 					{
 						if (g > 0)
 						{
-							issuer_wait(cx, cx.barW0 + 8u * (cx.wq & 1u), (cx.wq >> 1) & 1u);
+							issuer_wait(cx, cx.barW0 + 8u * (cx.sq & 1u), (cx.sq >> 1) & 1u);
+							cx.sq++;
 							wb16 = (cx.wbuf + (cx.wq & 1u) * cx.wbufStride) >> 4;
 						}
 						const int j0 = g * groupTaps;
 						const int jn = (j0 + groupTaps < numTaps) ? j0 + groupTaps : numTaps;
-						const uint32_t tb16 = wb16 + (g == 0 ? tap0Base16 : 0u);
+						const uint32_t tb16 = wb16 + (g == 0 ? g7.z : 0u);
 						if (cx.el)
 						{
 #pragma unroll 1
 							for (int j = j0; j < jn; j++)
 							{
-								const uint32_t r16 = win16 + (lds32(la + kTabTaps + 4u * (uint32_t)j) >> 4);
-								tap_copy<C>(MP::tap(cx, j - j0), r16, lbo16);
-								mma_pairs<C, 1>(MP::d(cx), MP::tap(cx, j - j0), tb16 + (uint32_t)(j - j0) * tapStride16, C);
+								const uint32_t r16 = win16 + (lds32(P.la + kTabTaps + 4u * (uint32_t)j) >> 4);
+								const uint32_t b16 = tb16 + (uint32_t)(j - j0) * g7.w;
+								mma_pairs_ss<C>(MP::d(cx), desc_lo(r16, lbo16), desc_lo(r16 + 2u * lbo16, lbo16), desc_lo(b16, C), desc_lo(b16 + 2u * C, C), idC);
 							}
 							mma_commit(cx.barD);
-							// the other buffer held the previous sub-block (or the previous layer's last block): complete
-							if (g + 1 < numGroups) issue_weights(cx, l, g + 1, cx.wq + 1);
-							else issue_weights(cx, (l + 1 < cx.numLayers) ? l + 1 : 0, 0, cx.wq + 1);
+							if (jn >= numTaps) mma_commit(cx.barFree0 + 8u * (cx.lq & 1u));
+							// weight requests of a layer with tap groups: the next sub-block, or - behind the last group - the next layer's first
+							// block; the buffer they go to held the sub-block before this one (or the previous layer's last block): all read
+							if (g + 1 < numGroups) { request_weights(cx, l, g + 1, cx.wq + 1, cx.barW0 + 8u * (cx.sqr & 1u)); cx.sqr++; }
+							else
+							{
+								const int nl = l + 1 < cx.numLayers ? l + 1 : (cx.hasNext ? 0 : -1);
+								if (nl >= 0) request_weights(cx, nl, 0, cx.wq + 1, cx.barL0 + 8u * ((cx.lq + 1u) & 1u));
+							}
 						}
 						__syncwarp();
 						if (jn < numTaps)
 						{
-							// more tap groups: this sub-block's buffer and the tap columns are reused by the group after next / the next group
+							// more tap groups: this sub-block's buffer is reused by the group after next
 							issuer_wait(cx, cx.barD, cx.dq & 1u);
 							cx.wq++;
 						}
 						else issuer_release<kBarDReady>(cx, cx.barD, cx.dq & 1u);
 						cx.dq++;
 					}
+					// the 1x1 operands sit in the layer's last sub-block
+					P.one[0] = desc_lo(wb16 + g3.w, N1); P.one[1] = desc_lo(wb16 + g3.y, N1); P.one[2] = desc_lo(wb16 + g3.z, N1);
 				}
+				cx.lq++;
 				H_STAMP(6);
+				// idle while the stagers run the activation: the next layer's plan, and its windows / weights (landed long ago as a rule)
+				if (hasNext)
+				{
+					plan_layer<C, N1, NT>(cx, l + 1, cx.wq + 1, Q);
+					wait_layer(cx, cx.lq);
+				}
 
 				// ---- 1x1 + bias + residual, head sum (WaveNet.h:482-491): XR | HD += [z] [W1x1 | Whead] ----
 				issuer_sync<kBarZ>();
 				H_STAMP(7);
 				if (cx.el)
 				{
-					mma_f16_ts<1>(MP::xr(cx), konst(cx), desc_at(wb16 + g3.w, N1), idesc_f16(N1));
+					mma_f16_ts<1>(MP::xr(cx), konst(cx), desc_of(P.one[0]), idN1);
 					if constexpr (C == 16)
 					{
-						mma_f16_ts<1>(MP::xr(cx), MP::tap(cx, 0), desc_at(wb16 + g3.y, N1), idesc_f16(N1));
-						mma_f16_ts<1>(MP::xr(cx), MP::tap(cx, 0) + 8u, desc_at(wb16 + g3.y, N1), idesc_f16(N1));
-						mma_f16_ts<1>(MP::xr(cx), MP::tap(cx, 0), desc_at(wb16 + g3.z, N1), idesc_f16(N1));
+						mma_f16_ts<1>(MP::xr(cx), MP::t2(cx), desc_of(P.one[1]), idN1);
+						mma_f16_ts<1>(MP::xr(cx), MP::t2(cx) + 8u, desc_of(P.one[1]), idN1);
+						mma_f16_ts<1>(MP::xr(cx), MP::t2(cx), desc_of(P.one[2]), idN1);
 					}
 					else
 					{
-						mma_f16_ts<1>(MP::xr(cx), MP::tap(cx, 0), desc_at(wb16 + g3.y, N1), idesc_f16(N1));
-						mma_f16_ts<1>(MP::xr(cx), MP::tap(cx, 0), desc_at(wb16 + g3.z, N1), idesc_f16(N1));
+						mma_f16_ts<1>(MP::xr(cx), MP::t2(cx), desc_of(P.one[1]), idN1);
+						mma_f16_ts<1>(MP::xr(cx), MP::t2(cx), desc_of(P.one[2]), idN1);
 					}
 					mma_commit(cx.barX);
 				}
 				__syncwarp();
 				H_STAMP(8);
+				// behind the 1x1, in the shadow of its completion: the next layer's input-independent products (the conv accumulator
+				// is free: the stagers have read it); the tensor pipe runs them while the stagers pack
+				// release the stagers first (they pack the next layer's input), then - while they pack - the next layer's
+				// input-independent products (the conv accumulator is free: the stagers have read it)
 				issuer_release<kBarXReady>(cx, cx.barX, cx.xq & 1u);
 				H_STAMP(9);
 				cx.xq++;
 				cx.wq++;
+				if (hasNext) early_products<ROLE, NT>(cx, Q);
+				P = Q;
 			}
 		}
 
-		constexpr int kNumBars = 4;   // W0, W1, D, X (what follows is read with 16-byte copies: keep the count even)
+		constexpr int kNumBars = 8;   // W0, W1, D, X, L0, L1, Free0, Free1 (what follows is read with 16-byte copies: keep the count even)
 		constexpr int kHeadTaps = 16;                           // A2 head conv kernel size (WaveNet.h:658-660, InternalModel.h:12-20)
 		constexpr int kHeadHistFloats = kHeadTaps * 16;         // per stream: [tap][16 frames] of per-tap head products (15 used)
-		constexpr int kHeadRows = kCur + kHeadTaps - 1;         // scratch rows per tap plane: 15 history + 128 current
-		constexpr uint32_t kHeadScratchBytes = 8u * (uint32_t)(kCur + kHeadTaps - 1) * 4u + 32u;   // at the top of the window buffer, clear of the first layer's region (PackWaveNetH checks)
+		constexpr int kHeadRows = kCur + kHeadTaps - 1;         // scratch words per tap plane: 15 history + 128 current (8 planes = 288 16-byte rows of the window buffer, PackWaveNetH: headScratchRow)
 
 		// ARCH 0: two arrays, (16, 8) channels, tanh, 1x1 heads (A1 Standard / Lite).  ARCH 1: one 8-channel array, LeakyReLU,
 		// 16-tap head conv (A2, WaveNet.h:632-661 with the InternalModel.h:12-20 shapes).
@@ -558,16 +699,17 @@ namespace nab200
 			cx.barW0 = smem_u32(&bars[0]);
 			cx.barD = smem_u32(&bars[2]);
 			cx.barX = smem_u32(&bars[3]);
+			cx.barL0 = smem_u32(&bars[4]);
+			cx.barFree0 = smem_u32(&bars[6]);
 			cx.n = n;
 			cx.tid = threadIdx.x;
 			cx.warp = threadIdx.x >> 5;
 			cx.S = S;
 			cx.gstride = gridDim.x;
 			cx.numLayers = M.numLayers;
-			cx.wq = 0; cx.dq = 0; cx.xq = 0; cx.cur = 0;
+			cx.wq = 0; cx.dq = 0; cx.xq = 0; cx.sq = 0; cx.sqr = 0; cx.lq = 0; cx.cur = 0; cx.hasNext = false;
 			cx.el = elect_one();
 			const int tid = threadIdx.x, warp = cx.warp;
-			const bool stager = warp < 4;
 			const int first0 = M.arrays[0].firstLayer, num0 = M.arrays[0].numLayers;
 			const int first1 = ARCH == 0 ? M.arrays[1].firstLayer : 0, num1 = ARCH == 0 ? M.arrays[1].numLayers : 0;
 
@@ -580,18 +722,14 @@ namespace nab200
 			}
 			if (tid == 0)
 			{
-				mbar_init(cx.barW0, 1);
-				mbar_init(cx.barW0 + 8u, 1);
-				mbar_init(cx.barD, 1);
-				mbar_init(cx.barX, 1);
+#pragma unroll
+				for (int b = 0; b < kNumBars; b++) mbar_init(cx.barW0 + 8u * (uint32_t)b, (b == 4 || b == 5) ? 2 : 1);   // a layer's barrier: its windows + its first weight block
 				asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 			}
 			if (warp == 4)
 			{
-				// three allocations of the same size cannot fragment: 5 CTAs x 96 columns fit the SM's 512
-				tmem_alloc<32>(smem_u32(tmemSlot));
-				tmem_alloc<32>(smem_u32(tmemSlot + 1));
-				tmem_alloc<32>(smem_u32(tmemSlot + 2));
+				// one power-of-two allocation per CTA cannot fragment: up to 8 CTAs x 64 columns fit the SM's 512
+				tmem_alloc<64>(smem_u32(tmemSlot));
 				tmem_relinquish();
 			}
 			const int s0 = blockIdx.x;
@@ -607,19 +745,24 @@ namespace nab200
 			fence_before();
 			__syncthreads();
 			fence_after();
-			cx.r0 = tmemSlot[0]; cx.r1 = tmemSlot[1]; cx.r2 = tmemSlot[2];
+			cx.r0 = tmemSlot[0];
 
-			if (!stager)
+			if (warp == 5)
+			{
+				// =================================== fetcher warp ===================================
+				fetch_loop(cx, heads, s0);
+			}
+			else if (warp == 4)
 			{
 				// =================================== issuer warp ===================================
 				const uint32_t ent0 = lds128(cx.tab + (uint32_t)first0 * (uint32_t)sizeof(HLayer) + 64).z;
 				const uint32_t ent1 = ARCH == 0 ? lds128(cx.tab + (uint32_t)first1 * (uint32_t)sizeof(HLayer) + 64).z : 0u;
-				if (cx.el) issue_weights(cx, 0, 0, 0);
 				for (int s = s0; s < S; s += gridDim.x)
 				{
 					H_STAMP_SELECT(s, s0);
+					cx.hasNext = s + (int)gridDim.x < S;
 					// ---- entry: [XR | HD] = constant operand x [rechannel 1 -> C0 | head bias] (WaveNet.h:637) ----
-					issuer_wait(cx, cx.barW0 + 8u * (cx.wq & 1u), (cx.wq >> 1) & 1u);
+					issuer_wait(cx, cx.barL0 + 8u * (cx.lq & 1u), (cx.lq >> 1) & 1u);   // the first layer's block carries the entry operand
 					issuer_sync<kBarE>();
 					if (cx.el)
 					{
@@ -635,21 +778,22 @@ namespace nab200
 						issue_array<0>(cx, first0, num0);
 
 						// ---- array transition (WaveNet.h:785-789): [XR1 | HD1] = rechannel C0 -> C1 of the array output | head carry ----
-						issuer_wait(cx, cx.barW0 + 8u * (cx.wq & 1u), (cx.wq >> 1) & 1u);
+						issuer_wait(cx, cx.barL0 + 8u * (cx.lq & 1u), (cx.lq >> 1) & 1u);   // the second array's first block carries the transition operands
 						issuer_sync<kBarE>();
 						if (cx.el)
 						{
 							const uint32_t wb16 = (cx.wbuf + (cx.wq & 1u) * cx.wbufStride) >> 4;
 							const uint32_t acc = Map<1>::xr(cx), e = wb16 + ent1, id = idesc_f16(16);
-							mma_f16_ts<0>(acc, cx.r1 + 16u, desc_at(e, 16), id);          // [Re1 | 0] x h1 of the array output
-							mma_f16_ts<1>(acc, cx.r1 + 24u, desc_at(e, 16), id);          // ... x h2
-							mma_f16_ts<1>(acc, cx.r1 + 16u, desc_at(e + 32u, 16), id);    // [Re2 | 0] x h1
-							mma_f16_ts<1>(acc, cx.r0, desc_at(e + 64u, 16), id);          // [0 | Wc1 ; Wc1] x [h1 | h2] of the head output
-							mma_f16_ts<1>(acc, cx.r0, desc_at(e + 96u, 16), id);          // [0 | Wc2 ; 0]
+							mma_f16_ts<0>(acc, cx.r0, desc_at(e, 16), id);                // [Re1 | 0] x h1 of the array output
+							mma_f16_ts<1>(acc, cx.r0 + 8u, desc_at(e, 16), id);           // ... x h2
+							mma_f16_ts<1>(acc, cx.r0, desc_at(e + 32u, 16), id);          // [Re2 | 0] x h1
+							mma_f16_ts<1>(acc, cx.r0 + 16u, desc_at(e + 64u, 16), id);    // [0 | Wc1 ; Wc1] x [h1 | h2] of the head output
+							mma_f16_ts<1>(acc, cx.r0 + 16u, desc_at(e + 96u, 16), id);    // [0 | Wc2 ; 0]
 							mma_f16_ts<1>(acc, konst(cx), desc_at(e + 128u, 16), id);     // [0 | head bias]
 							mma_commit(cx.barX);
 						}
 						__syncwarp();
+						// (the second array's conv accumulator reuses columns the transition products read: they have completed)
 						issuer_release<kBarXReady>(cx, cx.barX, cx.xq & 1u);
 						cx.xq++;
 						issue_array<1>(cx, first1, num1);
@@ -657,8 +801,6 @@ namespace nab200
 					else issue_array<2>(cx, first0, num0);
 					cx.cur ^= 1;
 				}
-				// drain the weight prefetch that ran ahead of the last layer
-				issuer_wait(cx, cx.barW0 + 8u * (cx.wq & 1u), (cx.wq >> 1) & 1u);
 			}
 			else
 			{
@@ -668,8 +810,7 @@ namespace nab200
 				if (tid < n && s0 < S) cond = in[(long long)s0 * inSS + (long long)tid * inFS];
 				const size_t strideBytes = (size_t)M.stateStride * 4;
 				cx.sbase = reinterpret_cast<char*>(state) + (size_t)s0 * strideBytes;
-				cx.hasNext = false;
-				if (s0 < S) request_windows(cx, 0, cx.sbase, cx.hdb);
+				if (tid == kWeightThread && s0 < S) request_weights(cx, 0, 0, 0, cx.barL0);
 				for (int s = s0; s < S; s += gridDim.x)
 				{
 					const int sn = s + gridDim.x;
@@ -711,22 +852,22 @@ namespace nab200
 					stager_arrive<kBarE>();
 					if constexpr (ARCH == 0)
 					{
-						stage_array<0>(cx, first0, num0, first1);
+						stage_array<0>(cx, first0, num0);
 
 						// ---- array transition: the array output and its head output as packed pairs ----
 						stager_wait<kBarXReady>();
 						{
 							uint32_t x[16], p[16];
-							tmem_ld<16>(lane + Map<0>::xr(cx), x);
-							pack_pairs<16>(x, p);
-							tmem_st<16>(lane + cx.r1 + 16u, p);
+							tmem_ld_nowait<16>(lane + Map<0>::xr(cx), x);
 							uint32_t h[8], hp[8];
 							tmem_ld<8>(lane + Map<0>::hd(cx), h);
+							pack_pairs<16>(x, p);
+							tmem_st<16>(lane + cx.r0, p);
 							pack_pairs<8>(h, hp);
-							tmem_st<8>(lane + cx.r0, hp);
+							tmem_st<8>(lane + cx.r0 + 16u, hp);
 						}
 						stager_arrive<kBarE>();
-						stage_array<1>(cx, first1, num1, first1);
+						stage_array<1>(cx, first1, num1);
 
 						// ---- output (WaveNet.h:793-798) ----
 						stager_wait<kBarXReady>();
@@ -738,7 +879,7 @@ namespace nab200
 					}
 					else
 					{
-						stage_array<2>(cx, first0, num0, 0);
+						stage_array<2>(cx, first0, num0);
 
 						// ---- output: 16-tap head conv of the summed head (WaveNet.h:658-660, 793-798) ----
 						// HD column k holds G_k[t] = Wh_k . headsum[t] (+ the head bias in column 15); out[t] = sum_k G_k[t - 15 + k].
@@ -749,7 +890,7 @@ namespace nab200
 						uint32_t g[16];
 						tmem_ld<16>(lane + Map<2>::hd(cx), g);
 						float acc = 0.0f;
-						const uint32_t sc = (cx.win + 2u * cx.planeStride - kHeadScratchBytes) & ~15u;
+						const uint32_t sc = cx.win + (uint32_t)M.headScratchRow * 16u;
 #pragma unroll
 						for (int half = 0; half < 2; half++)
 						{
@@ -784,12 +925,7 @@ namespace nab200
 
 			fence_before();
 			__syncthreads();
-			if (warp == 4)
-			{
-				tmem_dealloc<32>(cx.r0);
-				tmem_dealloc<32>(cx.r1);
-				tmem_dealloc<32>(cx.r2);
-			}
+			if (warp == 4) tmem_dealloc<64>(cx.r0);
 		}
 	}
 

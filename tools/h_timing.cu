@@ -9,6 +9,11 @@
 #include "../neuralaudio_b200/csrc/wavenet_h_kernels.cu"
 #include "../neuralaudio_b200/csrc/model_desc.h"
 using namespace nab200;
+#ifdef NAB_H_TIMING
+static const char* kStampNote = "(stamps compiled in)";
+#else
+static const char* kStampNote = "";
+#endif
 
 int main(int argc, char** argv)
 {
@@ -44,9 +49,11 @@ int main(int argc, char** argv)
 	if (!WaveNetHSupported(desc)) { printf("shape not supported by the fp16-pair kernel\n"); return 1; }
 	PackedWaveNet P = PackWaveNetH(desc);
 	WnModelDev M = P.dev;
+	const int realStride = M.stateStride;
+	if (getenv("NAB_H_ALIAS")) M.stateStride = 0;   // timing experiment: every stream uses the same (L2-resident) state; results are wrong
 	float *dW, *dState, *dIn, *dOut; int* dHeads; int* dErr;
 	cudaMalloc(&dW, P.weights.size() * 4); cudaMemcpy(dW, P.weights.data(), P.weights.size() * 4, cudaMemcpyHostToDevice);
-	cudaMalloc(&dState, (size_t)S * M.stateStride * 4); cudaMemset(dState, 0, (size_t)S * M.stateStride * 4);
+	cudaMalloc(&dState, (size_t)S * realStride * 4); cudaMemset(dState, 0, (size_t)S * realStride * 4);
 	cudaMalloc(&dHeads, (size_t)S * M.numRings * 4); cudaMemset(dHeads, 0, (size_t)S * M.numRings * 4);
 	cudaMalloc(&dIn, (size_t)S * n * 4); cudaMalloc(&dOut, (size_t)S * n * 4);
 	cudaMalloc(&dErr, 4); cudaMemset(dErr, 0, 4);
@@ -66,40 +73,60 @@ int main(int argc, char** argv)
 		cudaError_t e2 = cudaDeviceSynchronize();
 		if (err != cudaSuccess || e2 != cudaSuccess) { printf("error %s %s\n", cudaGetErrorString(err), cudaGetErrorString(e2)); return 1; }
 		float ms; cudaEventElapsedTime(&ms, e0, e1);
-		printf("S=%d launch %d: %.1f us (stamps compiled in)\n", S, it, ms * 1000);
+		printf("S=%d launch %d: %.1f us %s\n", S, it, ms * 1000, kStampNote);
 	}
-	static long long st[4][5][4][32][12];
+#ifndef NAB_H_TIMING
+	return 0;
+#else
+	static long long st[4][6][4][32][12];
 	cudaMemcpyFromSymbol(st, hk::g_stamps, sizeof(st));
 	const int NL = M.numLayers;
-	const char* stagerNames[8] = { "wait XR (1x1 done)", "ldXR+pack+stT2+arrive", "cp.async wait_group", "bar(mixed)", "taps LDS->STTM+arrive", "bar+prefetch+ring STG", "wait D (conv done)", "act+pack+stZ+arrive" };
-	const char* issuerNames[9] = { "wait W + issue next W", "wait T2", "T2+const MMAs", "wait taps", "tap MMAs+commit", "wait barD+release", "wait Z", "1x1 MMAs+commit", "wait barX+release" };
-	for (int c = 0; c < 4; c++)
-		for (int w : {0, 3, 4})
+	if (getenv("NAB_H_DUMP"))
+	{
+		// absolute event times of one stream of one CTA (cycles since the issuer began the stream's first layer)
+		const int c = 1, k = 1;
+		const long long t0 = st[c][4][k][0][2];
+		printf("layer | fetcher: start regionFree issued | issuer: top T2 committed DReady Z 1x1committed XReady | stager0: XReady' T2arrive winWait ringDone DReady' Zarrive\n");
+		for (int l = 0; l < NL; l++)
 		{
-			const int np = w == 4 ? 9 : 8;
-			printf("CTA slot %d warp %d (%s; mean cycles over 4 streams), per layer then mean:\n", c, w, w == 4 ? "issuer" : "stager");
+			printf("%2d |", l);
+			for (int i : {0, 1, 2}) printf(" %6lld", st[c][5][k][l][i] - t0);
+			printf(" |");
+			for (int i : {2, 3, 5, 6, 7, 8, 9}) printf(" %6lld", st[c][4][k][l][i] - t0);
+			printf(" |");
+			for (int i : {1, 2, 3, 6, 7, 8}) printf(" %6lld", st[c][0][k][l][i] - t0);
+			printf("\n");
+		}
+	}
+	struct Phase { const char* name; int from, to; };
+	const Phase stagerPhases[] = { { "wait XR (1x1 done)", 0, 1 }, { "ldXR+pack+stT2+(sts)+arrive", 1, 2 }, { "wait window (ring WAR)", 2, 3 },
+		{ "ring STG", 3, 6 }, { "wait D (conv done)", 6, 7 }, { "act+pack+stZ+arrive", 7, 8 } };
+	const Phase issuerPhases[] = { { "wait T2", 2, 3 }, { "T2 + mixed-tap MMAs+commit", 3, 5 }, { "wait barD + release", 5, 6 },
+		{ "plan next + wait its data + wait Z", 6, 7 }, { "1x1 MMAs+commit", 7, 8 }, { "wait barX + release", 8, 9 } };
+	const Phase fetcherPhases[] = { { "wait region free", 0, 1 }, { "issue copies", 1, 2 }, { "-", 2, 3 } };
+	for (int c = 0; c < 4; c++)
+		for (int w : {0, 3, 4, 5})
+		{
+			const Phase* ph = w == 5 ? fetcherPhases : w == 4 ? issuerPhases : stagerPhases;
+			const int np = w == 5 ? 3 : 6;
+			printf("CTA slot %d warp %d (%s; mean cycles over 4 streams), per layer then mean:\n", c, w, w == 5 ? "fetcher" : w == 4 ? "issuer" : "stager");
 			for (int p = 0; p < np; p++)
 			{
-				printf("  %-24s", w == 4 ? issuerNames[p] : stagerNames[p]);
+				printf("  %-30s", ph[p].name);
 				double tot = 0;
 				for (int l = 0; l < NL; l++)
 				{
 					double m = 0;
-					for (int k = 0; k < 4; k++) m += (double)(st[c][w][k][l][p + 1] - st[c][w][k][l][p]);
+					for (int k = 0; k < 4; k++) m += (double)(st[c][w][k][l][ph[p].to] - st[c][w][k][l][ph[p].from]);
 					m /= 4; tot += m;
 					printf(" %5.0f", m);
 				}
 				printf("  | %6.0f\n", tot / NL);
 			}
-			if (w != 4)
-			{
-				double b = 0, r = 0, g = 0;
-				for (int l = 0; l < NL; l++) for (int k = 0; k < 4; k++) { b += (double)(st[c][w][k][l][9] - st[c][w][k][l][5]); r += (double)(st[c][w][k][l][10] - st[c][w][k][l][9]); g += (double)(st[c][w][k][l][6] - st[c][w][k][l][10]); }
-				printf("  split of 'bar+prefetch+ring STG': barrier %.0f | window requests %.0f | ring STG %.0f\n", b / (4 * NL), r / (4 * NL), g / (4 * NL));
-			}
 			double whole = 0;
-			for (int k = 0; k < 4; k++) whole += (double)(st[c][w][k][NL - 1][np] - st[c][w][k][0][0]);
+			for (int k = 0; k < 4; k++) whole += (double)(st[c][w][k][NL - 1][ph[np - 1].to] - st[c][w][k][0][ph[0].from]);
 			printf("  stream total (layers only): %.0f cycles\n", whole / 4);
 		}
+#endif
 	return 0;
 }
