@@ -754,13 +754,18 @@ namespace nab200
 		return A.channels > 4 && A.channels <= 8 && A.inputSize == 1 && A.headSize == 1 && A.headKernel == 16 && A.activation == 1 && !A.dilations.empty();
 	}
 
+	// Rows per plane of the window buffer for the two-array (16, 8)-channel family: consecutive layers (up to 256 rows each) get
+	// disjoint regions, so every window is fetched a whole layer ahead.  (Measured: 384 rows = 24 KB lets five streams share an SM
+	// instead of four, but the largest layers' regions then overlap and their bulk copies start one conv later: 216 us against 201.)
+	static const int kHWinRowsTwoArrays = 512;
+
 	bool WaveNetHSupported(const WaveNetDesc& desc)
 	{
 		// two arrays of (9..16, <= 8) channels, tanh, kernel size 3, 1x1 heads, head of array 0 feeding array 1 (A1 Standard / Lite
 		// and stacks of that family) - or the A2 single array; every layer's history must fit the window plan below
 		const bool single = IsHSingleArray(desc);
 		if (!single && !WaveNetTsSupported(desc)) return false;
-		const int R = single ? 1024 : 512;
+		const int R = single ? 1024 : kHWinRowsTwoArrays;
 		size_t layers = 0;
 		for (const auto& A : desc.arrays)
 			for (size_t l = 0; l < A.dilations.size(); l++, layers++)
@@ -788,7 +793,7 @@ namespace nab200
 		M.tc = 3;
 		M.numArrays = (int)desc.arrays.size();
 		const bool single = IsHSingleArray(desc);
-		int R = single ? 1024 : 512;   // rows per plane of the shared-memory window buffer
+		int R = single ? 1024 : kHWinRowsTwoArrays;   // rows per plane of the shared-memory window buffer
 #ifdef NAB_H_TOOLS
 		if (getenv("NAB_H_FAKE_R")) R = atoi(getenv("NAB_H_FAKE_R"));   // timing experiments only (tools/h_timing.cu): results are wrong
 #endif
@@ -852,7 +857,7 @@ namespace nab200
 				uint32_t ent16 = 0;
 				if (l == 0) ent16 = B.Alloc(a == 0 ? 2u * 24u : 6u * 32u);
 				const uint32_t und16 = B.Alloc(2u * opN);
-				const uint32_t convC16 = B.Alloc(opN);
+				const uint32_t convC16 = B.Alloc(2u * opN);
 				std::vector<uint32_t> tap16(K, und16);          // absolute unit offset of tap k's [W1 | W2]
 				for (int g = 0; g < numGroups; g++)
 				{
@@ -865,16 +870,24 @@ namespace nab200
 				// conv file order [out][in][k] (WaveNet.h:99-105); tap k = K - 1 is the undelayed one
 				for (int i = 0; i < C; i++)
 					for (int j = 0; j < C; j++)
-						for (int k = 0; k < K; k++) putPair(B, tap16[k], tap16[k] + opN, CP, j, i, *src++);
+						for (int k = 0; k < K; k++)
+						{
+							// one operand per tap, 2 CP output columns: [W1 | W2] (C == 8: [W1 ; W1 | W2 ; 0]) - one product per A operand
+							// delivers the W1 and the W2 partial sums side by side; the activation adds the two halves
+							SplitH3(*src++, h3);
+							B.Put(tap16[k], 2 * CP, j, i, h3[0]);
+							if (CP == 8) B.Put(tap16[k], 2 * CP, 8 + j, i, h3[0]);
+							B.Put(tap16[k], 2 * CP, j, CP + i, h3[1]);
+						}
 				// constant-operand rows against [c1, c2, c1, 1, 1, 1]: mix1, mix1, mix2, b1, b2, b3
 				const float* convB = src; src += C;
 				const float* mix = src; src += C;
 				for (int i = 0; i < C; i++)
 				{
 					SplitH3(mix[i], h3);
-					B.Put(convC16, CP, 0, i, h3[0]); B.Put(convC16, CP, 1, i, h3[0]); B.Put(convC16, CP, 2, i, h3[1]);
+					B.Put(convC16, 2 * CP, 0, i, h3[0]); B.Put(convC16, 2 * CP, 1, i, h3[0]); B.Put(convC16, 2 * CP, 2, i, h3[1]);
 					SplitH3(convB[i], h3);
-					B.Put(convC16, CP, 3, i, h3[0]); B.Put(convC16, CP, 4, i, h3[1]); B.Put(convC16, CP, 5, i, h3[2]);
+					B.Put(convC16, 2 * CP, 3, i, h3[0]); B.Put(convC16, 2 * CP, 4, i, h3[1]); B.Put(convC16, 2 * CP, 5, i, h3[2]);
 				}
 				// 1x1 file [out][in] (zero when the layer has no output) | head conv of this array, file [H][C], as columns CP..
 				for (int i = 0; i < C; i++)

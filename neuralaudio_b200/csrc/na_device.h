@@ -92,10 +92,13 @@ namespace nab200
 	//   (history rows, then - where a tap reads this call's frames - the 128 current rows); consecutive layers get disjoint
 	//   regions where both fit, so a layer's windows are requested (TMA bulk copies) a whole layer ahead; where they cannot
 	//   (kHLate) the request waits for the previous layer's conv.
-	//   Weight block of a layer (16-byte units, fp16): per tap k = 0..K-1 (k = K-1 undelayed):
-	//       C == 16: W1[2][16][8] | W2[2][16][8]          (B operand [k group][n][8 halves], k = input channel)
-	//       C ==  8: Wa = [W1 ; W1][2][8][8] | Wb = [W2 ; 0]   (k group 0 pairs with the h1 halves, group 1 with the h2 halves)
-	//     then convC[2][C][8] (rows: mix1, mix1, mix2, b1, b2, b3 against the constant operand [c1, c2, c1, 1, 1, 1, 0...]),
+	//   Weight block of a layer (16-byte units, fp16): per tap k = 0..K-1 (k = K-1 undelayed) ONE B operand [k group][n][8 halves]
+	//   with 2 C output columns, k = input channel:
+	//       C == 16: columns 0..15 = W1, 16..31 = W2: the h1 operand takes all 32 (h1 W1 | h1 W2), the h2 operand the first 16
+	//       C ==  8: columns 0..7 = [W1 ; W1], 8..15 = [W2 ; 0] (k group 0 pairs with the h1 halves, group 1 with the h2 halves)
+	//     so the conv accumulator is 2 C columns wide and the activation adds its two halves (one shared-memory A read per
+	//     product instead of two);
+	//     then convC[2][2 C][8] (rows: mix1, mix1, mix2, b1, b2, b3 against the constant operand [c1, c2, c1, 1, 1, 1, 0...]; first C columns),
 	//     one1 / one2 / oneC with N1 = C + HN columns (1x1 | head conv), and on the first layer of an array the entry /
 	//     transition operands (see PackWaveNetH).  A layer with more delayed taps than one hand-off carries (K = 15) is cut
 	//     into sub-blocks, one per tap group, staged one after the other through the same two shared-memory buffers:

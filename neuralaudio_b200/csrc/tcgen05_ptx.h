@@ -51,6 +51,19 @@ namespace nab200
 				"}" : "=r"(done) : "r"(bar), "r"(parity), "n"(kSpinLimit) : "memory");
 			return done != 0;
 		}
+		// The same wait for a warp that is in no hurry (waits of a microsecond): it sleeps between tries instead of polling
+		// (round 2: the fetcher's waits looped ~30 times each, 7 % of the kernel's instructions).
+		__device__ __forceinline__ bool mbar_wait_relaxed(uint32_t bar, uint32_t parity)
+		{
+			for (uint32_t it = 0; it < kSpinLimit; it++)
+			{
+				uint32_t ok;
+				asm volatile("{\n.reg .pred P1;\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\nselp.u32 %0, 1, 0, P1;\n}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+				if (ok) return true;
+				__nanosleep(100);
+			}
+			return false;
+		}
 		__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar)
 		{
 			asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
@@ -200,6 +213,12 @@ namespace nab200
 		{
 			u64 d;
 			asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+			return d;
+		}
+		__device__ __forceinline__ u64 add2(u64 a, u64 b)
+		{
+			u64 d;
+			asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
 			return d;
 		}
 		__device__ __forceinline__ u64 mul2(u64 a, u64 b)

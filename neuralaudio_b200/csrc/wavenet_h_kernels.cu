@@ -75,7 +75,7 @@ namespace nab200
 			uint32_t barW0, barD, barX;
 			uint32_t barL0;               // [2] fetcher -> issuer / stagers: history windows and first weight block of an even / odd layer have landed
 			uint32_t barFree0;            // [2] conv of an even / odd layer complete: its window region may be overwritten
-			uint32_t r0;                  // TMEM: 64 columns
+			uint32_t r0, konst;           // TMEM: this stream's columns, the constant operand's
 			int n, tid, warp, S, gstride, numLayers;
 			bool el;
 			uint32_t wq, dq, xq, sq, sqr; // weight-block counter; issuer: barD / barX phase counters, sub-blocks awaited / requested (barW phases)
@@ -101,21 +101,23 @@ namespace nab200
 #define H_STAMP_SELECT(s, s0) do { } while (0)
 #endif
 
-		// TMEM column maps (64 columns per stream; CONST, 8 columns, is always r0 + 56).  The activated output z reuses the
-		// undelayed tap's columns (the conv has read them by the time the activation runs).
-		//   ROLE 0: first array, 16 channels, 8 head columns:  T2 / z r0 | D r0 + 16 | XR r0 + 32 | HD r0 + 48
-		//   ROLE 1: second array, 8 channels, 8 head columns:  T2 / z r0 | D r0 + 8  | XR r0 + 32 | HD r0 + 40
+		// TMEM column maps.  The conv accumulator D is 2 C columns wide: [h1 W1 + h2 W1 | h1 W2] partial sums, added by the
+		// activation.  The activated output z reuses the undelayed tap's columns (the conv has read them by the time the
+		// activation runs).  The constant operand (8 columns) sits at cx.konst.
+		//   ROLE 0: first array, 16 channels, 8 head columns:  T2 / z r0 | D r0 + 16 (32) | XR r0 + 48 | HD r0 + 64 | CONST r0 + 72
+		//   ROLE 1: second array, 8 channels, 8 head columns:  T2 / z r0 | D r0 + 8 (16)  | XR r0 + 32 | HD r0 + 40
 		//           (the transition stages the first array's output pairs at r0 and its head output pairs at r0 + 16)
 		//   ROLE 2: single array (A2), 8 channels, 16 head columns (one per head-conv tap, see the output stage):
-		//                                                      T2 / z r0 | D r0 + 8  | XR r0 + 16 | HD r0 + 24
+		//                                                      T2 / z r0 | D r0 + 8 (16)  | XR r0 + 24 | HD r0 + 32 | CONST r0 + 56
+		// ARCH 0 (roles 0 and 1) allocates 128 columns per stream, ARCH 1 (role 2) 64.
 		template <int ROLE> struct Map;
 		template <> struct Map<0>
 		{
 			static constexpr int C = 16, HN = 8, N1 = 24;
 			static __device__ __forceinline__ uint32_t t2(const Ctx& cx) { return cx.r0; }
 			static __device__ __forceinline__ uint32_t d(const Ctx& cx) { return cx.r0 + 16u; }
-			static __device__ __forceinline__ uint32_t xr(const Ctx& cx) { return cx.r0 + 32u; }
-			static __device__ __forceinline__ uint32_t hd(const Ctx& cx) { return cx.r0 + 48u; }
+			static __device__ __forceinline__ uint32_t xr(const Ctx& cx) { return cx.r0 + 48u; }
+			static __device__ __forceinline__ uint32_t hd(const Ctx& cx) { return cx.r0 + 64u; }
 		};
 		template <> struct Map<1>
 		{
@@ -130,10 +132,10 @@ namespace nab200
 			static constexpr int C = 8, HN = 16, N1 = 24;
 			static __device__ __forceinline__ uint32_t t2(const Ctx& cx) { return cx.r0; }
 			static __device__ __forceinline__ uint32_t d(const Ctx& cx) { return cx.r0 + 8u; }
-			static __device__ __forceinline__ uint32_t xr(const Ctx& cx) { return cx.r0 + 16u; }
-			static __device__ __forceinline__ uint32_t hd(const Ctx& cx) { return cx.r0 + 24u; }
+			static __device__ __forceinline__ uint32_t xr(const Ctx& cx) { return cx.r0 + 24u; }
+			static __device__ __forceinline__ uint32_t hd(const Ctx& cx) { return cx.r0 + 32u; }
 		};
-		__device__ __forceinline__ uint32_t konst(const Ctx& cx) { return cx.r0 + 56u; }
+		__device__ __forceinline__ uint32_t konst(const Ctx& cx) { return cx.konst; }
 
 		// ---- hand-offs -------------------------------------------------------------------------------------------
 		template <int ID> __device__ __forceinline__ void stager_arrive()
@@ -273,7 +275,7 @@ namespace nab200
 					}
 #endif
 					const int c = (int)gl - ((flags & kHLate) ? 1 : 2);
-					if (c >= 0 && !mbar_wait(cx.barFree0 + 8u * ((uint32_t)c & 1u), ((uint32_t)c >> 1) & 1u) && lane == 0) *reinterpret_cast<volatile int*>(cx.err) = 1;
+					if (c >= 0 && !mbar_wait_relaxed(cx.barFree0 + 8u * ((uint32_t)c & 1u), ((uint32_t)c >> 1) & 1u) && lane == 0) *reinterpret_cast<volatile int*>(cx.err) = 1;
 					H_STAMP(1);
 					const uint32_t bar = cx.barL0 + 8u * (gl & 1u);
 #ifndef NAB_H_NO_WINDOWS
@@ -387,9 +389,8 @@ namespace nab200
 					cx.wq += (uint32_t)ng;
 				}
 				// ---- history write-back (AdvanceFrames, WaveNet.h:59-65) in the conv's shadow: frame t becomes ring row (head + t) mod Lp.
-				// The rows replaced are the oldest ones, which this layer's own window copies read: wait until the fetcher has
-				// published them (long done as a rule: the issuer needed them before the conv).
-				if (!mbar_wait(cx.barL0 + 8u * (cx.lq & 1u), (cx.lq >> 1) & 1u) && tid == 0) *reinterpret_cast<volatile int*>(cx.err) = 1;
+				// The rows replaced are the oldest ones, which this layer's own window copies read.  Those copies have landed: the
+				// issuer saw them complete (wait_layer / the entry and transition waits) before it released the stagers into this layer.
 				cx.lq++;
 				H_STAMP(3);
 				{
@@ -415,13 +416,17 @@ namespace nab200
 				stager_wait<kBarDReady>();
 				H_STAMP(7);
 				{
-					uint32_t dv[C], z[C];
-					tmem_ld<C>(lane + MP::d(cx), dv);
+					// the conv accumulator's two halves (W1 and W2 partial sums) are added here
+					uint32_t dv[C], dw[C], z[C];
+					tmem_ld_nowait<C>(lane + MP::d(cx), dv);
+					tmem_ld<C>(lane + MP::d(cx) + (uint32_t)C, dw);
 #pragma unroll
 					for (int c = 0; c < C; c += 2)
 					{
-						if constexpr (ROLE == 2) leaky2(dv[c], dv[c + 1], z[c], z[c + 1]);
-						else fast_tanh2(dv[c], dv[c + 1], z[c], z[c + 1]);
+						uint32_t s0, s1;
+						unpack2(add2(pack2(dv[c], dv[c + 1]), pack2(dw[c], dw[c + 1])), s0, s1);
+						if constexpr (ROLE == 2) leaky2(s0, s1, z[c], z[c + 1]);
+						else fast_tanh2(s0, s1, z[c], z[c + 1]);
 					}
 					pack_pairs<C>(z, dv);
 					tmem_st<C>(lane + MP::t2(cx), dv);
@@ -435,40 +440,30 @@ namespace nab200
 		__device__ __forceinline__ uint32_t desc_lo(uint32_t addr16, uint32_t lbo16) { return addr16 | (lbo16 << 16); }
 		__device__ __forceinline__ u64 desc_of(uint32_t lo) { return ((u64)kDescHi << 32) | lo; }
 
-		// conv-type product into accumulator `acc`: A at TMEM `a` (C == 16: h1 at a, h2 at a + 8; C == 8: [h1 | h2] at a),
-		// weights b0 | b1 (C == 16: W1 | W2; C == 8: [W1; W1] | [W2; 0]): D += h1 W1 + h2 W1 + h1 W2
+		// conv-type product into the 2 C-column accumulator `acc`: A at TMEM `a` (C == 16: h1 at a, h2 at a + 8; C == 8: [h1 | h2]
+		// at a), B = the tap's operand [W1 | W2]: acc[0..C) += h1 W1 + h2 W1, acc[C..2C) += h1 W2
 		template <int C>
-		__device__ __forceinline__ void mma_pairs(uint32_t acc, uint32_t a, uint32_t b0, uint32_t b1, uint32_t id)
+		__device__ __forceinline__ void mma_pairs(uint32_t acc, uint32_t a, uint32_t b)
 		{
 			if constexpr (C == 16)
 			{
-				mma_f16_ts<1>(acc, a, desc_of(b0), id);
-				mma_f16_ts<1>(acc, a + 8u, desc_of(b0), id);
-				mma_f16_ts<1>(acc, a, desc_of(b1), id);
+				mma_f16_ts<1>(acc, a, desc_of(b), idesc_f16(32));
+				mma_f16_ts<1>(acc, a + 8u, desc_of(b), idesc_f16(16));
 			}
-			else
-			{
-				mma_f16_ts<1>(acc, a, desc_of(b0), id);
-				mma_f16_ts<1>(acc, a, desc_of(b1), id);
-			}
+			else mma_f16_ts<1>(acc, a, desc_of(b), idesc_f16(16));
 		}
 
 		// the same product with the A operand read from the shared-memory window: 128 rows, planes a0 (h1; C == 8: [h1 | h2])
-		// and a1 (h2) as descriptors (a delayed tap is a row offset into the layer's window)
+		// and a0 + lbo2 (h2) as descriptors (a delayed tap is a row offset into the layer's window)
 		template <int C>
-		__device__ __forceinline__ void mma_pairs_ss(uint32_t acc, uint32_t a0, uint32_t a1, uint32_t b0, uint32_t b1, uint32_t id)
+		__device__ __forceinline__ void mma_pairs_ss(uint32_t acc, uint32_t a0, uint32_t lbo2, uint32_t b)
 		{
 			if constexpr (C == 16)
 			{
-				mma_f16_ss<1>(acc, desc_of(a0), desc_of(b0), id);
-				mma_f16_ss<1>(acc, desc_of(a1), desc_of(b0), id);
-				mma_f16_ss<1>(acc, desc_of(a0), desc_of(b1), id);
+				mma_f16_ss<1>(acc, desc_of(a0), desc_of(b), idesc_f16(32));
+				mma_f16_ss<1>(acc, desc_of(a0 + lbo2), desc_of(b), idesc_f16(16));
 			}
-			else
-			{
-				mma_f16_ss<1>(acc, desc_of(a0), desc_of(b0), id);
-				mma_f16_ss<1>(acc, desc_of(a0), desc_of(b1), id);
-			}
+			else mma_f16_ss<1>(acc, desc_of(a0), desc_of(b), idesc_f16(16));
 		}
 
 		// ---- issuer warp: one layer array of the CTA's stream --------------------------------------------------------
@@ -478,8 +473,8 @@ namespace nab200
 		{
 			uint32_t la, wb16, histMask;
 			bool fast;
-			uint32_t convC, und, one[3];   // B descriptors: constant operand of the conv, undelayed tap (W1; W2 follows 2 C units on), 1x1 (constant operand, W1, W2)
-			uint32_t tapA[NT], tapB[NT];   // delayed taps (unrolled path): window rows (h1 plane; h2 two planes on), weights (W1; W2 2 C units on)
+			uint32_t convC, und, one[3];   // B descriptors: constant operand of the conv, undelayed tap, 1x1 (constant operand, W1, W2)
+			uint32_t tapA[NT], tapB[NT];   // delayed taps (unrolled path): window rows (h1 plane; h2 two planes on), weights
 		};
 
 		// No waiting (runs while the issuer would idle: the stagers' activation): layer l's plan; `block` = number of its first weight block.
@@ -494,8 +489,8 @@ namespace nab200
 			P.fast = (int)g8.y == 1 && (int)g8.x == NT;
 			const uint32_t wb16 = (cx.wbuf + (block & 1u) * cx.wbufStride) >> 4;
 			P.wb16 = wb16;
-			P.convC = desc_lo(wb16 + g3.x, C);
-			P.und = desc_lo(wb16 + g7.y, C);
+			P.convC = desc_lo(wb16 + g3.x, 2 * C);
+			P.und = desc_lo(wb16 + g7.y, 2 * C);
 			P.one[0] = desc_lo(wb16 + g3.w, N1); P.one[1] = desc_lo(wb16 + g3.y, N1); P.one[2] = desc_lo(wb16 + g3.z, N1);
 			const uint32_t win16 = cx.win >> 4, lbo16 = cx.planeStride >> 4, tb16 = wb16 + g7.z;
 			const uint32_t off[5] = { o0.x, o0.y, o0.z, o0.w, o4 };
@@ -503,7 +498,7 @@ namespace nab200
 			for (int j = 0; j < NT; j++)
 			{
 				P.tapA[j] = desc_lo(win16 + (off[j] >> 4), lbo16);
-				P.tapB[j] = desc_lo(tb16 + (uint32_t)(j * 4 * C), C);
+				P.tapB[j] = desc_lo(tb16 + (uint32_t)(j * 4 * C), 2 * C);
 			}
 		}
 
@@ -517,13 +512,12 @@ namespace nab200
 			constexpr int C = MP::C;
 			if (cx.el)
 			{
-				const uint32_t id = idesc_f16(C);
-				mma_f16_ts<0>(MP::d(cx), konst(cx), desc_of(P.convC), id);
+				mma_f16_ts<0>(MP::d(cx), konst(cx), desc_of(P.convC), idesc_f16(2 * C));
 				if (P.fast)
 				{
 #pragma unroll
 					for (int j = 0; j < NT; j++)
-						if ((P.histMask >> j) & 1u) mma_pairs_ss<C>(MP::d(cx), P.tapA[j], P.tapA[j] + 2u * (cx.planeStride >> 4), P.tapB[j], P.tapB[j] + 2u * C, id);
+						if ((P.histMask >> j) & 1u) mma_pairs_ss<C>(MP::d(cx), P.tapA[j], 2u * (cx.planeStride >> 4), P.tapB[j]);
 				}
 			}
 			__syncwarp();
@@ -539,7 +533,7 @@ namespace nab200
 			typedef Map<ROLE> MP;
 			constexpr int C = MP::C, N1 = MP::N1;
 			constexpr int NT = ROLE == 2 ? 5 : 2;   // the delayed-tap count with an unrolled path (K = 6 / K = 3)
-			const uint32_t idC = idesc_f16(C), idN1 = idesc_f16(N1);
+			const uint32_t idN1 = idesc_f16(N1);
 			LayerPlan<NT> P, Q;
 			plan_layer<C, N1, NT>(cx, firstLayer, cx.wq, P);
 			wait_layer(cx, cx.lq);
@@ -560,10 +554,10 @@ namespace nab200
 				{
 					if (cx.el)
 					{
-						mma_pairs<C>(MP::d(cx), MP::t2(cx), P.und, P.und + 2u * C, idC);
+						mma_pairs<C>(MP::d(cx), MP::t2(cx), P.und);
 #pragma unroll
 						for (int j = 0; j < NT; j++)
-							if (!((P.histMask >> j) & 1u)) mma_pairs_ss<C>(MP::d(cx), P.tapA[j], P.tapA[j] + 2u * (cx.planeStride >> 4), P.tapB[j], P.tapB[j] + 2u * C, idC);
+							if (!((P.histMask >> j) & 1u)) mma_pairs_ss<C>(MP::d(cx), P.tapA[j], 2u * (cx.planeStride >> 4), P.tapB[j]);
 						mma_commit(cx.barD);
 						mma_commit(cx.barFree0 + 8u * (cx.lq & 1u));
 					}
@@ -578,7 +572,7 @@ namespace nab200
 					const uint32_t win16 = cx.win >> 4, lbo16 = cx.planeStride >> 4;
 					const uint4 g3 = lds128(P.la + 48), g7 = lds128(P.la + kTabHist), g8 = lds128(P.la + kTabHist + 16u);
 					const int numTaps = (int)g8.x, numGroups = (int)g8.y, groupTaps = (int)g8.z;
-					if (cx.el) mma_pairs<C>(MP::d(cx), MP::t2(cx), P.und, P.und + 2u * C, idC);
+					if (cx.el) mma_pairs<C>(MP::d(cx), MP::t2(cx), P.und);
 #pragma unroll 1
 					for (int g = 0; g < numGroups; g++)
 					{
@@ -598,7 +592,7 @@ namespace nab200
 							{
 								const uint32_t r16 = win16 + (lds32(P.la + kTabTaps + 4u * (uint32_t)j) >> 4);
 								const uint32_t b16 = tb16 + (uint32_t)(j - j0) * g7.w;
-								mma_pairs_ss<C>(MP::d(cx), desc_lo(r16, lbo16), desc_lo(r16 + 2u * lbo16, lbo16), desc_lo(b16, C), desc_lo(b16 + 2u * C, C), idC);
+								mma_pairs_ss<C>(MP::d(cx), desc_lo(r16, lbo16), 2u * lbo16, desc_lo(b16, 2 * C));
 							}
 							mma_commit(cx.barD);
 							if (jn >= numTaps) mma_commit(cx.barFree0 + 8u * (cx.lq & 1u));
@@ -728,8 +722,8 @@ namespace nab200
 			}
 			if (warp == 4)
 			{
-				// one power-of-two allocation per CTA cannot fragment: up to 8 CTAs x 64 columns fit the SM's 512
-				tmem_alloc<64>(smem_u32(tmemSlot));
+				// one power-of-two allocation per CTA cannot fragment: 4 CTAs x 128 (8 x 64) columns fit the SM's 512
+				tmem_alloc<ARCH == 0 ? 128 : 64>(smem_u32(tmemSlot));
 				tmem_relinquish();
 			}
 			const int s0 = blockIdx.x;
@@ -746,6 +740,7 @@ namespace nab200
 			__syncthreads();
 			fence_after();
 			cx.r0 = tmemSlot[0];
+			cx.konst = cx.r0 + (ARCH == 0 ? 72u : 56u);
 
 			if (warp == 5)
 			{
@@ -925,7 +920,7 @@ namespace nab200
 
 			fence_before();
 			__syncthreads();
-			if (warp == 4) tmem_dealloc<64>(cx.r0);
+			if (warp == 4) tmem_dealloc<ARCH == 0 ? 128 : 64>(cx.r0);
 		}
 	}
 
@@ -937,7 +932,7 @@ namespace nab200
 	size_t wavenet_h_smem_bytes(const WnModelDev& M)
 	{
 		return (size_t)(M.arrays[0].C / 4) * M.winRows * 16 + (size_t)2 * M.maxBlockBytes + (size_t)M.numLayers * sizeof(HLayer) +
-			2 * hk::kHdbHalf * 4 + hk::kNumBars * 8 + 16 + hk::kHeadHistFloats * 4;
+			2 * hk::kHdbHalf * 4 + hk::kNumBars * 8 + 16 + (M.numArrays == 1 ? hk::kHeadHistFloats * 4 : 0);   // (the head history: A2 only)
 	}
 
 	template <int ARCH>
@@ -950,10 +945,11 @@ namespace nab200
 		static SmemGrant grant;
 		cudaError_t e = EnsureDynamicSmem(kfn, grant, smem, true);
 		if (e != cudaSuccess) return e;
-		// streams in flight per SM: 5 by TMEM (96 columns each) and registers (64 x 6 allocated warps), fewer when a model's
-		// weight blocks make the CTA's shared memory larger than a fifth of the SM's
+		// streams in flight per SM: 5 by registers (64 x 6 warps; TMEM, 64 columns each, would allow 8), fewer when a model's
+		// windows and weight blocks make the CTA's shared memory larger than a fifth of the SM's
 		int fit = (int)((size_t)(228 * 1024) / (smem + 1024));
 		if (fit > 5) fit = 5;
+		if (ARCH == 0 && fit > 4) fit = 4;   // 128 TMEM columns per stream
 		if (fit < 1) fit = 1;
 		int ctasPerSM = a.ctasPerSM > 0 ? a.ctasPerSM : fit;
 		int grid = a.numSMs * ctasPerSM;

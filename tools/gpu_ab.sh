@@ -1,9 +1,10 @@
 #!/bin/bash
-# A/B of timing binaries: tools/gpu_ab.sh bin1 bin2 ... ; each run for A1 (ctas 4, 5) and A2
+# same-box A/B of plain timing binaries: tools/gpu_ab.sh suffix1 suffix2 ... (h_bench<suffix>); A1 and A2 shapes, two rounds
 mkdir -p gpurun_out
-for b in "$@"; do
-  for c in 4 5; do
-    echo "== $b A1 ctas=$c"; timeout 120 ./tools/$b 4096 0 $c > gpurun_out/${b}_a1_c$c.txt 2>&1; sed -n 2,5p gpurun_out/${b}_a1_c$c.txt | tr '\n' ' '; echo
-  done
-  echo "== $b A2"; timeout 120 ./tools/$b 4096 1 0 > gpurun_out/${b}_a2.txt 2>&1; sed -n 2,5p gpurun_out/${b}_a2.txt | tr '\n' ' '; echo
+for round in 1 2; do
+for sfx in "$@"; do
+  [ "$sfx" = base ] && sfx=""
+  a1=$(timeout 120 ./tools/h_bench$sfx 4096 0 0 | tail -1); a2=$(timeout 120 ./tools/h_bench$sfx 4096 1 0 | tail -1)
+  echo "h_bench$sfx | A1 $a1 | A2 $a2"
+done
 done
