@@ -849,7 +849,10 @@ namespace nab200
 
 				HBlock B;
 				const uint32_t opN = 2u * CP;                       // units of one conv operand [2][CP][8]
-				const int groupTaps = single ? 6 : 2;
+				int groupTaps = single ? 7 : 2;   // A2: K = 6 (5 delayed taps) in one block, K = 15 in two of 7 taps, each no larger than a K = 6 layer's block
+#ifdef NAB_H_TOOLS
+				if (getenv("NAB_H_GROUPTAPS")) groupTaps = atoi(getenv("NAB_H_GROUPTAPS"));   // experiments (tools/h_timing.cu)
+#endif
 				const int numGroups = (K - 1 + groupTaps - 1) / groupTaps;
 				// sub-block 0: [entry (first layer of an array)] [undelayed tap] [convC] [taps of group 0]; sub-block g: [taps of group g];
 				// the last sub-block ends with [one1] [one2] [oneC]
@@ -1029,36 +1032,104 @@ namespace nab200
 				layerIdx++;
 			}
 		}
-		// Window regions: layer L's rows go where layer L - 1's are not (below them, else right above them), so that its windows
-		// can be requested while layer L - 1 still reads its own; where neither fits the request is late (after that conv).
+		// Window regions.  A layer's rows may be overwritten (by the fetcher, for a later layer) once the products that read them
+		// have completed: the taps that read only history go out ahead of the layer's hand-off ("early products"), so their rows
+		// die when the layer begins; the rows the other taps read (and the current rows) live until the layer's conv completes.
+		// Layer i's copies therefore wait for (kHDep*, HLayer::flags):
+		//   conv(i - 2)   its rows touch none of layer i - 1's (the default: even layers at the bottom of the buffer, odd ones at the top)
+		//   early(i - 1)  they touch rows of layer i - 1 that die early (a layer whose taps each have their own 128-row window is
+		//                 dealt slot by slot around the rows of layer i - 1 that live on)
+		//   conv(i - 1)   they touch rows of layer i - 1 that live until its conv: the request goes out a whole conv later
 		// The first layer of the next stream follows the last layer of this one (persistent CTAs).
 		{
+			struct Iv { int a, b; };
 			const int NL = (int)table.size();
+			auto touches = [](const std::vector<Iv>& x, const std::vector<Iv>& y)
+			{
+				for (const Iv& p : x) for (const Iv& q : y) if (p.a < q.b && q.a < p.b) return true;
+				return false;
+			};
+			std::vector<std::vector<Iv>> rows(NL), live(NL);   // absolute row intervals of layer i: all / alive until its conv
 			std::vector<int> base(NL, 0);
-			// even layers sit at the bottom of the buffer, odd layers at the top: two consecutive layers overlap only when their
-			// rows do not fit side by side
-			for (int i = 0; i < NL; i++) base[i] = (i & 1) ? R - table[i].pad0 : 0;
+			std::vector<uint32_t> dep(NL, kHDepConv2);
+			// a layer's early-dead / live split, relative to its region: rows below `liveFrom` are read by early products only
+			auto liveFromOf = [&](const HLayer& T) -> int
+			{
+				if (T.numGroups != 1) return 0;                      // tap groups: nothing is issued early
+				if (T.numJobs > 1 || T.job[0].cnt < 0) return T.pad0;   // every tap its own window, all of them history: nothing lives on
+				int from = T.pad0;
+				for (int j = 0; j < T.numTaps; j++)
+					if (!((T.histMask >> j) & 1u)) { const int r = (int)(T.tapOff[j] / 16u); if (r < from) from = r; }
+				return from;
+			};
+			for (int pass = 0; pass < 2; pass++)   // second pass: the first layer sees the last one placed (stream after stream)
+				for (int i = 0; i < NL; i++)
+				{
+					const HLayer& T = table[i];
+					const int prev = (i + NL - 1) % NL;
+					const bool slotted = T.numJobs > 1 || T.job[0].cnt < 0;   // every tap its own 128-row window
+					base[i] = (i & 1) ? R - T.pad0 : 0;
+					rows[i].assign(1, Iv{ base[i], base[i] + T.pad0 });
+					const int lf = liveFromOf(T);
+					live[i].clear();
+					if (lf < T.pad0) live[i].push_back(Iv{ base[i] + lf, base[i] + T.pad0 });
+					dep[i] = kHDepConv2;
+					if (NL == 1 || (pass == 0 && i == 0)) { if (NL == 1) dep[i] = kHDepConv1; continue; }
+					if (!touches(rows[i], rows[prev])) continue;
+					if (!touches(rows[i], live[prev])) { dep[i] = kHDepEarly1; continue; }
+					if (slotted && i != 0 && i != 1)   // (the first two layers keep their place: the A2 head scratch sits between them)
+					{
+						// 128-row slots clear of the previous layer's living rows, those clear of all its rows first
+						std::vector<int> slots;
+						for (int prefer = 0; prefer < 2; prefer++)
+							for (int k = 0; k + 128 <= R; k += 128)
+							{
+								const std::vector<Iv> sl(1, Iv{ k, k + 128 });
+								if (touches(sl, live[prev])) continue;
+								if ((prefer == 0) == touches(sl, rows[prev])) continue;
+								slots.push_back(k);
+							}
+						if ((int)slots.size() >= T.numJobs)
+						{
+							rows[i].clear();
+							bool early = false;
+							for (int j = 0; j < T.numJobs; j++)
+							{
+								rows[i].push_back(Iv{ slots[j], slots[j] + 128 });
+								if (touches(std::vector<Iv>(1, rows[i].back()), rows[prev])) early = true;
+							}
+							dep[i] = early ? kHDepEarly1 : kHDepConv2;
+							base[i] = -1;   // per-job offsets below
+							continue;
+						}
+					}
+					dep[i] = kHDepConv1;
+				}
 			// A2 head-conv scratch of the output stage (288 rows of plane 0): above the first layer's region and below the second
 			// layer's - the two regions the fetcher may be filling for the CTA's next stream while the output stage runs
 			M.headScratchRow = table[0].pad0;
 			for (int i = 0; i < NL; i++)
 			{
-				const int prev = (i + NL - 1) % NL;
-				const bool overlap = NL > 1 ? (base[i] < base[prev] + table[prev].pad0 && base[prev] < base[i] + table[i].pad0) : true;
-				table[i].flags = (table[i].flags & ~kHLate) | (overlap ? kHLate : 0u);
-#ifdef NAB_H_TOOLS
-				if (getenv("NAB_H_FAKE_R")) table[i].flags &= ~kHLate;
-#endif
-			}
-			for (int i = 0; i < NL; i++)
-			{
 				HLayer& T = table[i];
-				const uint32_t off = (uint32_t)base[i] * 16u;
-				T.curOff += off;
-				for (int j = 0; j < T.numTaps; j++) T.tapOff[j] += off;
-				for (int j = 0; j < T.numJobs; j++) T.job[j].off += off;
-				// what the stagers need to know at layer i: is the NEXT layer's request late (after this layer's conv) or early
-				T.pad0 = (int)(table[(i + 1) % NL].flags & kHLate);
+#ifdef NAB_H_TOOLS
+				if (getenv("NAB_H_FAKE_R")) dep[i] = kHDepConv2;
+				if (getenv("NAB_H_DEP_LATE") && dep[i] != kHDepConv2) dep[i] = kHDepConv1;
+#endif
+				T.flags = (T.flags & ~kHDepMask) | dep[i];
+				if (base[i] >= 0)
+				{
+					const uint32_t off = (uint32_t)base[i] * 16u;
+					T.curOff += off;
+					for (int j = 0; j < T.numTaps; j++) T.tapOff[j] += off;
+					for (int j = 0; j < T.numJobs; j++) T.job[j].off += off;
+				}
+				else
+					for (int j = 0; j < T.numJobs; j++)
+					{
+						T.tapOff[j] = (uint32_t)rows[i][j].a * 16u;
+						T.job[j].off = T.tapOff[j];
+					}
+				T.pad0 = 0;
 			}
 		}
 		M.headScale = *w;

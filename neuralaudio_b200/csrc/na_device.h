@@ -91,7 +91,7 @@ namespace nab200
 	//   Shared-memory window buffer: [planes][winRows][16 bytes].  Each layer owns a row region [base, base + rows) of it
 	//   (history rows, then - where a tap reads this call's frames - the 128 current rows); consecutive layers get disjoint
 	//   regions where both fit, so a layer's windows are requested (TMA bulk copies) a whole layer ahead; where they cannot
-	//   (kHLate) the request waits for the previous layer's conv.
+	//   the request waits for the previous layer's early products or its conv (kHDep*).
 	//   Weight block of a layer (16-byte units, fp16): per tap k = 0..K-1 (k = K-1 undelayed) ONE B operand [k group][n][8 halves]
 	//   with 2 C output columns, k = input channel:
 	//       C == 16: columns 0..15 = W1, 16..31 = W2: the h1 operand takes all 32 (h1 W1 | h1 W2), the h2 operand the first 16
@@ -103,7 +103,11 @@ namespace nab200
 	//     transition operands (see PackWaveNetH).  A layer with more delayed taps than one hand-off carries (K = 15) is cut
 	//     into sub-blocks, one per tap group, staged one after the other through the same two shared-memory buffers:
 	//     [entry | undelayed tap | convC | taps of group 0] [taps of group 1] ... [taps of the last group | one1 | one2 | oneC].
-	constexpr uint32_t kHLate = 1u << 8;   // HLayer::flags: this layer's window region overlaps the previous layer's (request it after that conv)
+	// HLayer::flags bits 8-9: what this layer's window copies wait for before they overwrite their rows (PackWaveNetH):
+	constexpr uint32_t kHDepConv2 = 0u << 8;    // the conv of the layer two back (the rows touch none of the previous layer's)
+	constexpr uint32_t kHDepEarly1 = 1u << 8;   // the previous layer's early products (they touch rows of it that only those read)
+	constexpr uint32_t kHDepConv1 = 2u << 8;    // the previous layer's conv (they touch rows of it that live until then)
+	constexpr uint32_t kHDepMask = 3u << 8;
 	constexpr int kHMaxTaps = 16;   // delayed taps per layer (K - 1 <= 14 for the official shapes)
 	constexpr int kHMaxJobs = 6;    // history-window copy jobs per layer
 	struct HJob

@@ -75,10 +75,12 @@ namespace nab200
 			uint32_t barW0, barD, barX;
 			uint32_t barL0;               // [2] fetcher -> issuer / stagers: history windows and first weight block of an even / odd layer have landed
 			uint32_t barFree0;            // [2] conv of an even / odd layer complete: its window region may be overwritten
+			uint32_t barG;                // issuer only: an intermediate tap group's products complete (a layer with tap groups)
+			uint32_t barEarly0;           // [2] early products of an even / odd layer complete: the rows only they read may be overwritten
 			uint32_t r0, konst;           // TMEM: this stream's columns, the constant operand's
 			int n, tid, warp, S, gstride, numLayers;
 			bool el;
-			uint32_t wq, dq, xq, sq, sqr; // weight-block counter; issuer: barD / barX phase counters, sub-blocks awaited / requested (barW phases)
+			uint32_t wq, dq, xq, gq, sq, sqr; // weight-block counter; issuer: barD / barX / barG phase counters, sub-blocks awaited / requested (barW phases)
 			bool hasNext;                 // the CTA has another stream after this one
 			uint32_t lq;                  // layers done by this thread since the kernel started (over all its streams): barWin / barFree phases
 			int cur;
@@ -151,6 +153,26 @@ namespace nab200
 			nbar_sync<ID, kSync>();
 			fence_after();
 		}
+#ifdef NAB_H_DIRECT_WAIT   // experiment: the stagers wait on the commit barriers themselves (the issuer still releases nobody)
+		__device__ __forceinline__ void stager_wait_x(Ctx& cx)
+		{
+			if (!mbar_wait(cx.barX, cx.xq & 1u) && cx.tid == 0) *reinterpret_cast<volatile int*>(cx.err) = 1;
+			cx.xq++;
+			fence_after();
+		}
+		__device__ __forceinline__ void stager_wait_d(Ctx& cx, int phases)
+		{
+			for (int i = 0; i < phases; i++) { if (!mbar_wait(cx.barD, cx.dq & 1u) && cx.tid == 0) *reinterpret_cast<volatile int*>(cx.err) = 1; cx.dq++; }
+			fence_after();
+		}
+#define STAGER_WAIT_X() stager_wait_x(cx)
+#define STAGER_WAIT_D(la) stager_wait_d(cx, (int)lds32((la) + 36u))
+#define ISSUER_RELEASE(ID, bar, parity) issuer_wait(cx, bar, parity)
+#else
+#define STAGER_WAIT_X() stager_wait<kBarXReady>()
+#define STAGER_WAIT_D(la) stager_wait<kBarDReady>()
+#define ISSUER_RELEASE(ID, bar, parity) issuer_release<ID>(cx, bar, parity)
+#endif
 		template <int ID> __device__ __forceinline__ void issuer_sync()
 		{
 			nbar_sync<ID, kSync>();
@@ -171,16 +193,17 @@ namespace nab200
 		{
 			const uint32_t la = cx.tab + (uint32_t)b * (uint32_t)sizeof(HLayer);
 			const uint32_t off = lds32(la + 80u + 4u * (uint32_t)g), bytes = lds32(la + 96u + 4u * (uint32_t)g);
+#ifdef NAB_H_DEBUG_PRINT
+			if (blockIdx.x == 0) printf("W tid %d layer %d g %d slot %u bar %d bytes %u\n", (int)threadIdx.x, b, g, slot, (int)((bar - cx.barW0) / 8), bytes);
+#endif
 			mbar_expect_tx(bar, bytes);
 			bulk_g2s(cx.wbuf + (slot & 1u) * cx.wbufStride, cx.Wg + off, bytes, bar);
 		}
 
 		// ---- fetcher warp ----------------------------------------------------------------------------------------------
-		// History windows of every layer of every stream of this CTA, in the order the issuer consumes them.  A window job is
-		// rows r in [0, cnt) <- ring rows (head - back + r) mod Lp; lane i copies rows i, i + 32, ... (one ring row = CG x 16
-		// contiguous bytes -> one 16-byte row in each of CG planes).  Layer g's region of the window buffer is free once the conv
-		// of layer g - 2 has completed (consecutive layers own disjoint regions) or, where the two regions overlap (kHLate,
-		// PackWaveNetH), the conv of layer g - 1.
+		// History windows of every layer of every stream of this CTA, in the order the issuer consumes them.  The rows layer g's
+		// copies overwrite belonged to earlier layers; PackWaveNetH laid the regions out and says what to wait for (kHDep*):
+		// the conv of layer g - 2, the early products of layer g - 1, or the conv of layer g - 1.
 		// One layer's window jobs as bulk copies (TMA): a job is rows r in [0, cnt) <- ring rows (head - back + r) mod Lp of every
 		// plane, i.e. one or two contiguous runs of 16-byte rows per plane; item = (job, plane, run), one lane per item.
 		// PREFETCH: the same runs as L2 prefetches (no destination).
@@ -274,8 +297,11 @@ namespace nab200
 						else if (sn < cx.S) prefetch_windows(cx, li + kAhead - cx.numLayers, sbase + (size_t)cx.gstride * strideBytes, hAn, hBn, lane);
 					}
 #endif
-					const int c = (int)gl - ((flags & kHLate) ? 1 : 2);
-					if (c >= 0 && !mbar_wait_relaxed(cx.barFree0 + 8u * ((uint32_t)c & 1u), ((uint32_t)c >> 1) & 1u) && lane == 0) *reinterpret_cast<volatile int*>(cx.err) = 1;
+					// the rows this layer's copies overwrite are free once ... (PackWaveNetH decides which)
+					const uint32_t dep = flags & kHDepMask;
+					const int c = (int)gl - (dep == kHDepConv2 ? 2 : 1);
+					const uint32_t depBar = (dep == kHDepEarly1 ? cx.barEarly0 : cx.barFree0) + 8u * ((uint32_t)c & 1u);
+					if (c >= 0 && !mbar_wait_relaxed(depBar, ((uint32_t)c >> 1) & 1u) && lane == 0) *reinterpret_cast<volatile int*>(cx.err) = 1;
 					H_STAMP(1);
 					const uint32_t bar = cx.barL0 + 8u * (gl & 1u);
 #ifndef NAB_H_NO_WINDOWS
@@ -283,6 +309,9 @@ namespace nab200
 					if (lane == 0)
 					{
 						const uint32_t wbytes = lds32(la + kTabHist + 28u);
+#ifdef NAB_H_DEBUG_PRINT
+						if (blockIdx.x == 0) printf("F gl %u bar %d bytes %u\n", gl, (int)((bar - cx.barW0) / 8), (wbytes & 0xFFFFFu) + (wbytes >> 20) * (uint32_t)cx.n);
+#endif
 						mbar_expect_tx(bar, (wbytes & 0xFFFFFu) + (wbytes >> 20) * (uint32_t)cx.n);
 					}
 					if (g1.w == 16u) window_items<false, 4>(cx, la, sbase + (size_t)g0.w * 4, head, (int)g0.z, (int)g1.y, bar, lane);
@@ -357,8 +386,17 @@ namespace nab200
 
 				// ---- the residual stream after the previous layer -> packed pairs: undelayed tap, current rows, ring ----
 				H_STAMP(0);
-				stager_wait<kBarXReady>();
+				STAGER_WAIT_X();
 				H_STAMP(1);
+				{
+					// a layer with tap groups: its second weight sub-block, now that the buffer it goes to is free (it held the
+					// previous layer's last block, whose readers completed with that layer's 1x1)
+					const int ng = (int)lds32(la + 36u);
+#ifndef NAB_H_SUB1_BY_ISSUER
+					if (ng > 1 && tid == kWeightThread) request_weights(cx, l, 1, cx.wq + 1, cx.barW0 + 8u * (cx.sqr & 1u));
+#endif
+					cx.sqr += (uint32_t)(ng - 1);
+				}
 				uint32_t p[C];
 				{
 					uint32_t x[C];
@@ -413,7 +451,7 @@ namespace nab200
 
 				// ---- activation (WaveNet.h:477-480); z -> packed pairs -> TMEM as the A operand of the 1x1 ----
 				H_STAMP(6);
-				stager_wait<kBarDReady>();
+				STAGER_WAIT_D(la);
 				H_STAMP(7);
 				{
 					// the conv accumulator's two halves (W1 and W2 partial sums) are added here
@@ -506,7 +544,7 @@ namespace nab200
 		// conv bias, WaveNet.h:471-476; it overwrites the accumulator) and the delayed taps that read only history.  The
 		// layer's first weight block and its history windows must have landed (wait_layer).
 		template <int ROLE, int NT>
-		__device__ __forceinline__ void early_products(Ctx& cx, const LayerPlan<NT>& P)
+		__device__ __forceinline__ void early_products(Ctx& cx, const LayerPlan<NT>& P, uint32_t lq)
 		{
 			typedef Map<ROLE> MP;
 			constexpr int C = MP::C;
@@ -519,6 +557,7 @@ namespace nab200
 					for (int j = 0; j < NT; j++)
 						if ((P.histMask >> j) & 1u) mma_pairs_ss<C>(MP::d(cx), P.tapA[j], 2u * (cx.planeStride >> 4), P.tapB[j]);
 				}
+				mma_commit(cx.barEarly0 + 8u * (lq & 1u));   // the window rows only these products read may be overwritten once they complete
 			}
 			__syncwarp();
 		}
@@ -537,7 +576,7 @@ namespace nab200
 			LayerPlan<NT> P, Q;
 			plan_layer<C, N1, NT>(cx, firstLayer, cx.wq, P);
 			wait_layer(cx, cx.lq);
-			early_products<ROLE, NT>(cx, P);
+			early_products<ROLE, NT>(cx, P, cx.lq);
 #pragma unroll 1
 			for (int li = 0; li < numLayers; li++)
 			{
@@ -563,16 +602,19 @@ namespace nab200
 					}
 					__syncwarp();
 					H_STAMP(5);
-					issuer_release<kBarDReady>(cx, cx.barD, cx.dq & 1u);
+					ISSUER_RELEASE(kBarDReady, cx.barD, cx.dq & 1u);
 					cx.dq++;
 				}
 				else
 				{
-					// more delayed taps than one weight block carries (K = 15): tap groups, their sub-blocks streamed through the buffers
+					// more delayed taps than one weight block carries (K = 15): tap groups, their sub-blocks streamed through the two
+					// buffers.  Sub-block 1 was requested by the stagers when the layer began; sub-block g + 2 goes where sub-block g
+					// sits, once group g's products have completed; the next layer's first block likewise, behind the last group.
 					const uint32_t win16 = cx.win >> 4, lbo16 = cx.planeStride >> 4;
 					const uint4 g3 = lds128(P.la + 48), g7 = lds128(P.la + kTabHist), g8 = lds128(P.la + kTabHist + 16u);
 					const int numTaps = (int)g8.x, numGroups = (int)g8.y, groupTaps = (int)g8.z;
 					if (cx.el) mma_pairs<C>(MP::d(cx), MP::t2(cx), P.und);
+					int waited = 0;   // commit phases of this layer's tap groups already consumed
 #pragma unroll 1
 					for (int g = 0; g < numGroups; g++)
 					{
@@ -594,27 +636,37 @@ namespace nab200
 								const uint32_t b16 = tb16 + (uint32_t)(j - j0) * g7.w;
 								mma_pairs_ss<C>(MP::d(cx), desc_lo(r16, lbo16), 2u * lbo16, desc_lo(b16, 2 * C));
 							}
-							mma_commit(cx.barD);
-							if (jn >= numTaps) mma_commit(cx.barFree0 + 8u * (cx.lq & 1u));
-							// weight requests of a layer with tap groups: the next sub-block, or - behind the last group - the next layer's first
-							// block; the buffer they go to held the sub-block before this one (or the previous layer's last block): all read
-							if (g + 1 < numGroups) { request_weights(cx, l, g + 1, cx.wq + 1, cx.barW0 + 8u * (cx.sqr & 1u)); cx.sqr++; }
-							else
-							{
-								const int nl = l + 1 < cx.numLayers ? l + 1 : (cx.hasNext ? 0 : -1);
-								if (nl >= 0) request_weights(cx, nl, 0, cx.wq + 1, cx.barL0 + 8u * ((cx.lq + 1u) & 1u));
-							}
+							// an intermediate group completes on its own barrier (one completion outstanding at a time: a parity wait
+							// cannot tell one completed phase from three), the last one on the conv's
+							if (jn < numTaps) mma_commit(cx.barG);
+							else { mma_commit(cx.barD); mma_commit(cx.barFree0 + 8u * (cx.lq & 1u)); }
 						}
 						__syncwarp();
 						if (jn < numTaps)
 						{
-							// more tap groups: this sub-block's buffer is reused by the group after next
-							issuer_wait(cx, cx.barD, cx.dq & 1u);
+#ifdef NAB_H_SUB1_BY_ISSUER   // experiment: sub-block 1 requested here instead of by the stagers at the layer's start
+							if (g == 0 && cx.el) request_weights(cx, l, 1, cx.wq + 1, cx.barW0 + 8u * (cx.sq & 1u));
+							__syncwarp();
+#endif
+							if (g + 2 < numGroups)
+							{
+								issuer_wait(cx, cx.barG, cx.gq & 1u);
+								cx.gq++; waited++;
+								if (cx.el) request_weights(cx, l, g + 2, cx.wq + 2, cx.barW0 + 8u * ((cx.sq + 1u) & 1u));
+								__syncwarp();
+							}
 							cx.wq++;
 						}
-						else issuer_release<kBarDReady>(cx, cx.barD, cx.dq & 1u);
-						cx.dq++;
 					}
+					for (; waited < numGroups - 1; waited++) { issuer_wait(cx, cx.barG, cx.gq & 1u); cx.gq++; }
+					if (cx.el && numGroups > 1)   // (behind a single group the stagers have asked already)
+					{
+						const int nl = l + 1 < cx.numLayers ? l + 1 : (cx.hasNext ? 0 : -1);
+						if (nl >= 0) request_weights(cx, nl, 0, cx.wq + 1, cx.barL0 + 8u * ((cx.lq + 1u) & 1u));
+					}
+					__syncwarp();
+					ISSUER_RELEASE(kBarDReady, cx.barD, cx.dq & 1u);
+					cx.dq++;
 					// the 1x1 operands sit in the layer's last sub-block
 					P.one[0] = desc_lo(wb16 + g3.w, N1); P.one[1] = desc_lo(wb16 + g3.y, N1); P.one[2] = desc_lo(wb16 + g3.z, N1);
 				}
@@ -652,16 +704,16 @@ namespace nab200
 				// is free: the stagers have read it); the tensor pipe runs them while the stagers pack
 				// release the stagers first (they pack the next layer's input), then - while they pack - the next layer's
 				// input-independent products (the conv accumulator is free: the stagers have read it)
-				issuer_release<kBarXReady>(cx, cx.barX, cx.xq & 1u);
+				ISSUER_RELEASE(kBarXReady, cx.barX, cx.xq & 1u);
 				H_STAMP(9);
 				cx.xq++;
 				cx.wq++;
-				if (hasNext) early_products<ROLE, NT>(cx, Q);
+				if (hasNext) early_products<ROLE, NT>(cx, Q, cx.lq);
 				P = Q;
 			}
 		}
 
-		constexpr int kNumBars = 8;   // W0, W1, D, X, L0, L1, Free0, Free1 (what follows is read with 16-byte copies: keep the count even)
+		constexpr int kNumBars = 12;   // W0, W1, D, X, L0, L1, Free0, Free1, Early0, Early1, G, (spare) (what follows is read with 16-byte copies: keep the count even)
 		constexpr int kHeadTaps = 16;                           // A2 head conv kernel size (WaveNet.h:658-660, InternalModel.h:12-20)
 		constexpr int kHeadHistFloats = kHeadTaps * 16;         // per stream: [tap][16 frames] of per-tap head products (15 used)
 		constexpr int kHeadRows = kCur + kHeadTaps - 1;         // scratch words per tap plane: 15 history + 128 current (8 planes = 288 16-byte rows of the window buffer, PackWaveNetH: headScratchRow)
@@ -695,13 +747,15 @@ namespace nab200
 			cx.barX = smem_u32(&bars[3]);
 			cx.barL0 = smem_u32(&bars[4]);
 			cx.barFree0 = smem_u32(&bars[6]);
+			cx.barEarly0 = smem_u32(&bars[8]);
+			cx.barG = smem_u32(&bars[10]);
 			cx.n = n;
 			cx.tid = threadIdx.x;
 			cx.warp = threadIdx.x >> 5;
 			cx.S = S;
 			cx.gstride = gridDim.x;
 			cx.numLayers = M.numLayers;
-			cx.wq = 0; cx.dq = 0; cx.xq = 0; cx.sq = 0; cx.sqr = 0; cx.lq = 0; cx.cur = 0; cx.hasNext = false;
+			cx.wq = 0; cx.dq = 0; cx.xq = 0; cx.gq = 0; cx.sq = 0; cx.sqr = 0; cx.lq = 0; cx.cur = 0; cx.hasNext = false;
 			cx.el = elect_one();
 			const int tid = threadIdx.x, warp = cx.warp;
 			const int first0 = M.arrays[0].firstLayer, num0 = M.arrays[0].numLayers;
@@ -766,7 +820,7 @@ namespace nab200
 						mma_commit(cx.barX);
 					}
 					__syncwarp();
-					issuer_release<kBarXReady>(cx, cx.barX, cx.xq & 1u);
+					ISSUER_RELEASE(kBarXReady, cx.barX, cx.xq & 1u);
 					cx.xq++;
 					if constexpr (ARCH == 0)
 					{
@@ -789,7 +843,7 @@ namespace nab200
 						}
 						__syncwarp();
 						// (the second array's conv accumulator reuses columns the transition products read: they have completed)
-						issuer_release<kBarXReady>(cx, cx.barX, cx.xq & 1u);
+						ISSUER_RELEASE(kBarXReady, cx.barX, cx.xq & 1u);
 						cx.xq++;
 						issue_array<1>(cx, first1, num1);
 					}
@@ -850,7 +904,7 @@ namespace nab200
 						stage_array<0>(cx, first0, num0);
 
 						// ---- array transition: the array output and its head output as packed pairs ----
-						stager_wait<kBarXReady>();
+						STAGER_WAIT_X();
 						{
 							uint32_t x[16], p[16];
 							tmem_ld_nowait<16>(lane + Map<0>::xr(cx), x);
@@ -865,7 +919,7 @@ namespace nab200
 						stage_array<1>(cx, first1, num1);
 
 						// ---- output (WaveNet.h:793-798) ----
-						stager_wait<kBarXReady>();
+						STAGER_WAIT_X();
 						{
 							uint32_t h[8];
 							tmem_ld<8>(lane + Map<1>::hd(cx), h);
@@ -880,7 +934,7 @@ namespace nab200
 						// HD column k holds G_k[t] = Wh_k . headsum[t] (+ the head bias in column 15); out[t] = sum_k G_k[t - 15 + k].
 						// The shift across frames goes through shared memory, one conflict-free plane per tap: rows 0..14 = the last 15
 						// frames of the previous call (per-stream state), rows 15.. = this call; two halves of 8 taps share the scratch.
-						stager_wait<kBarXReady>();
+						STAGER_WAIT_X();
 						cp_async_wait_all();   // the head history requested at the start of this stream
 						uint32_t g[16];
 						tmem_ld<16>(lane + Map<2>::hd(cx), g);

@@ -49,6 +49,25 @@ int main(int argc, char** argv)
 	if (!WaveNetHSupported(desc)) { printf("shape not supported by the fp16-pair kernel\n"); return 1; }
 	PackedWaveNet P = PackWaveNetH(desc);
 	WnModelDev M = P.dev;
+	if (getenv("NAB_H_PLAN"))
+	{
+		// the window plan (no GPU needed): per layer its tap rows, copy jobs and what its copies wait for
+		const HLayer* T = reinterpret_cast<const HLayer*>(P.weights.data() + M.tableOff);
+		printf("winRows %d maxBlockBytes %d headScratchRow %d smem %zu\n", M.winRows, M.maxBlockBytes, M.headScratchRow, wavenet_h_smem_bytes(M));
+		for (int l = 0; l < M.numLayers; l++)
+		{
+			const char* dep = (T[l].flags & kHDepMask) == kHDepConv2 ? "conv(l-2)" : (T[l].flags & kHDepMask) == kHDepEarly1 ? "early(l-1)" : "conv(l-1)";
+			printf("layer %2d K %2d d %3d Lp %4d groups %d mixed %d hist %02x dep %-10s cur %4u taps", l, T[l].K, M.layers[l].d, T[l].Lp, T[l].numGroups, T[l].mixed, T[l].histMask, dep, T[l].curOff / 16);
+			for (int j = 0; j < T[l].numTaps; j++) printf(" %u", T[l].tapOff[j] / 16);
+			printf(" | blocks");
+			for (int g = 0; g < T[l].numGroups; g++) printf(" %u+%u", T[l].gOff[g], T[l].gBytes[g]);
+			printf(" one %u %u %u und %u convC %u tap0 %u stride %u", T[l].one116, T[l].one216, T[l].oneC16, T[l].und16, T[l].convC16, T[l].tap0Base16, T[l].tapStride16);
+			printf(" | jobs");
+			for (int j = 0; j < T[l].numJobs; j++) printf(" (%d rows back %d at %u)", T[l].job[j].cnt, T[l].job[j].back, T[l].job[j].off / 16);
+			printf("\n");
+		}
+		return 0;
+	}
 	const int realStride = M.stateStride;
 	if (getenv("NAB_H_ALIAS")) M.stateStride = 0;   // timing experiment: every stream uses the same (L2-resident) state; results are wrong
 	float *dW, *dState, *dIn, *dOut; int* dHeads; int* dErr;
