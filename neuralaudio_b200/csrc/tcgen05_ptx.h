@@ -51,6 +51,13 @@ namespace nab200
 				"}" : "=r"(done) : "r"(bar), "r"(parity), "n"(kSpinLimit) : "memory");
 			return done != 0;
 		}
+		// non-blocking: has the phase with this parity completed?
+		__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity)
+		{
+			uint32_t ok;
+			asm volatile("{\n.reg .pred P1;\nmbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\nselp.u32 %0, 1, 0, P1;\n}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+			return ok != 0;
+		}
 		// The same wait for a warp that is in no hurry (waits of a microsecond): it sleeps between tries instead of polling
 		// (round 2: the fetcher's waits looped ~30 times each, 7 % of the kernel's instructions).
 		__device__ __forceinline__ bool mbar_wait_relaxed(uint32_t bar, uint32_t parity)

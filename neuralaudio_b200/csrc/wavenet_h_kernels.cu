@@ -196,6 +196,9 @@ namespace nab200
 #ifdef NAB_H_DEBUG_PRINT
 			if (blockIdx.x == 0) printf("W tid %d layer %d g %d slot %u bar %d bytes %u\n", (int)threadIdx.x, b, g, slot, (int)((bar - cx.barW0) / 8), bytes);
 #endif
+#ifdef NAB_H_NO_WEIGHTS   // timing experiment only (is the TMA path a bottleneck?): results are wrong
+			if (slot >= 2) { mbar_arrive(bar); return; }
+#endif
 			mbar_expect_tx(bar, bytes);
 			bulk_g2s(cx.wbuf + (slot & 1u) * cx.wbufStride, cx.Wg + off, bytes, bar);
 		}
@@ -563,7 +566,14 @@ namespace nab200
 		}
 		__device__ __forceinline__ void wait_layer(Ctx& cx, uint32_t lq)
 		{
-			issuer_wait(cx, cx.barL0 + 8u * (lq & 1u), (lq >> 1) & 1u);   // the fetcher's bulk copies: windows + first weight block
+			issuer_wait(cx, cx.barL0 + 8u * (lq & 1u), (lq >> 1) & 1u);   // the bulk copies of the layer's windows (fetcher) and first weight block
+		}
+		// the same, without waiting: have they landed?  (Where a layer's window rows become free only a layer ahead - the largest
+		// layers of A2 - the copies can still be in flight when the issuer would issue the early products: it then goes on, and
+		// issues them behind the hand-off, in front of the other taps, instead of stalling the stagers' release.)
+		__device__ __forceinline__ bool layer_landed(const Ctx& cx, uint32_t lq)
+		{
+			return __shfl_sync(0xffffffffu, mbar_test(cx.barL0 + 8u * (lq & 1u), (lq >> 1) & 1u) ? 1 : 0, 0) != 0;
 		}
 
 		template <int ROLE>
@@ -577,6 +587,7 @@ namespace nab200
 			plan_layer<C, N1, NT>(cx, firstLayer, cx.wq, P);
 			wait_layer(cx, cx.lq);
 			early_products<ROLE, NT>(cx, P, cx.lq);
+			bool deferred = false;   // this layer's early products are still to be issued (its copies had not landed in time)
 #pragma unroll 1
 			for (int li = 0; li < numLayers; li++)
 			{
@@ -589,6 +600,12 @@ namespace nab200
 				// A delayed tap is 128 rows of the shared-memory window starting at its own row offset: the MMAs read them in place.
 				issuer_sync<kBarT2>();
 				H_STAMP(3);
+				if (deferred)
+				{
+					wait_layer(cx, cx.lq);
+					early_products<ROLE, NT>(cx, P, cx.lq);
+					deferred = false;
+				}
 				if (P.fast)
 				{
 					if (cx.el)
@@ -673,11 +690,7 @@ namespace nab200
 				cx.lq++;
 				H_STAMP(6);
 				// idle while the stagers run the activation: the next layer's plan, and its windows / weights (landed long ago as a rule)
-				if (hasNext)
-				{
-					plan_layer<C, N1, NT>(cx, l + 1, cx.wq + 1, Q);
-					wait_layer(cx, cx.lq);
-				}
+				if (hasNext) plan_layer<C, N1, NT>(cx, l + 1, cx.wq + 1, Q);
 
 				// ---- 1x1 + bias + residual, head sum (WaveNet.h:482-491): XR | HD += [z] [W1x1 | Whead] ----
 				issuer_sync<kBarZ>();
@@ -708,7 +721,11 @@ namespace nab200
 				H_STAMP(9);
 				cx.xq++;
 				cx.wq++;
-				if (hasNext) early_products<ROLE, NT>(cx, Q, cx.lq);
+				if (hasNext)
+				{
+					if (layer_landed(cx, cx.lq)) early_products<ROLE, NT>(cx, Q, cx.lq);
+					else deferred = true;
+				}
 				P = Q;
 			}
 		}
