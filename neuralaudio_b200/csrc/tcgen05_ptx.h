@@ -177,8 +177,12 @@ namespace nab200
 		template <int N>
 		__device__ __forceinline__ void tmem_ld_nowait(uint32_t taddr, uint32_t (&r)[N])
 		{
-			static_assert(N == 8 || N == 16, "tmem_ld width");
-			if constexpr (N == 16)
+			static_assert(N == 2 || N == 4 || N == 8 || N == 16, "tmem_ld width");
+			if constexpr (N == 2)
+				asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(taddr));
+			else if constexpr (N == 4)
+				asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr));
+			else if constexpr (N == 16)
 				asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
 							 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
 							   "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
@@ -197,8 +201,12 @@ namespace nab200
 		template <int N>
 		__device__ __forceinline__ void tmem_st(uint32_t taddr, const uint32_t (&r)[N])
 		{
-			static_assert(N == 8 || N == 16, "tmem_st width");
-			if constexpr (N == 16)
+			static_assert(N == 2 || N == 4 || N == 8 || N == 16, "tmem_st width");
+			if constexpr (N == 2)
+				asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1,%2};" ::"r"(taddr), "r"(r[0]), "r"(r[1]) : "memory");
+			else if constexpr (N == 4)
+				asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]) : "memory");
+			else if constexpr (N == 16)
 				asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
 					"r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
 					"r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");

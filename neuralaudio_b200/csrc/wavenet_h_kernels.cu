@@ -43,9 +43,21 @@ namespace nab200
 		using namespace ptx;
 
 		constexpr int kCur = 128;        // frames per pass = TMEM lanes
-		constexpr int kStagers = 128;
-		constexpr int kSync = 160;       // stagers + issuer: the threads of the hand-off barriers
-		constexpr int kThreads = 192;    // + the fetcher warp
+		// HV = stager threads per frame: each takes C / HV of the frame's channels (thread t of half h <-> frame t % 128, TMEM lane
+		// t % 128, warp % 4 picks the lane quarter either way).
+		template <int HV> struct Th
+		{
+			static constexpr int kStagers = 128 * HV;          // stager threads
+			static constexpr int kSync = 128 * HV + 32;        // stagers + issuer: the threads of the hand-off barriers
+			static constexpr int kThreads = 128 * HV + 64;     // + the fetcher warp
+			static constexpr int kIssuerWarp = 4 * HV, kFetcherWarp = 4 * HV + 1;
+		};
+		// (Measured, round 2, A1 Standard: two halves 235 us against 203 us with one - the phases did not get shorter, the SM's
+		// issue slots are what the co-resident streams share, and ten warps per stream add hand-off instructions.  One it is.)
+#ifndef NAB_H_HV
+#define NAB_H_HV 1
+#endif
+		constexpr int kHvTwoArrays = NAB_H_HV;   // stager threads per frame for the A1 family (16 / 8 channels); A2 always one
 		constexpr int kWeightThread = 96; // the stager thread that requests weight blocks (warp 3, lane 0)
 		constexpr int kHdbHalf = 72;     // ints per stream in hdb: heads[36] | heads after the call[36]
 		constexpr uint32_t kTabTaps = (uint32_t)offsetof(HLayer, tapOff);
@@ -93,7 +105,7 @@ namespace nab200
 
 #ifdef NAB_H_TIMING
 		// tools/h_timing.cu: cycle stamps of one thread per warp of a few CTAs, [cta][warp][stream][layer][stamp]
-		__device__ long long g_stamps[4][6][4][32][12];
+		__device__ long long g_stamps[4][10][4][32][12];
 #define H_STAMP(i) do { if (cx.stampOn) g_stamps[cx.stampCta][cx.warp][cx.stampStream][l][i] = clock64(); } while (0)
 #define H_STAMP_SELECT(s, s0) do { const int k_ = ((s) - (s0)) / (int)gridDim.x; \
 		const int c_ = blockIdx.x == 0 ? 0 : blockIdx.x == 1 ? 1 : blockIdx.x == 300 ? 2 : blockIdx.x == gridDim.x - 1 ? 3 : -1; \
@@ -140,17 +152,17 @@ namespace nab200
 		__device__ __forceinline__ uint32_t konst(const Ctx& cx) { return cx.konst; }
 
 		// ---- hand-offs -------------------------------------------------------------------------------------------
-		template <int ID> __device__ __forceinline__ void stager_arrive()
+		template <int ID, int HV> __device__ __forceinline__ void stager_arrive()
 		{
 			wait_st();
 			fence_before();
-			nbar_arrive<ID, kSync>();
+			nbar_arrive<ID, Th<HV>::kSync>();
 		}
 		// (Measured, round 2: stagers waiting on the commit mbarriers themselves - no relay through the issuer - made the whole
 		// SM slower: 16 polling warps per SM; a named barrier parks a warp for free.)
-		template <int ID> __device__ __forceinline__ void stager_wait()
+		template <int ID, int HV> __device__ __forceinline__ void stager_wait()
 		{
-			nbar_sync<ID, kSync>();
+			nbar_sync<ID, Th<HV>::kSync>();
 			fence_after();
 		}
 #ifdef NAB_H_DIRECT_WAIT   // experiment: the stagers wait on the commit barriers themselves (the issuer still releases nobody)
@@ -169,23 +181,23 @@ namespace nab200
 #define STAGER_WAIT_D(la) stager_wait_d(cx, (int)lds32((la) + 36u))
 #define ISSUER_RELEASE(ID, bar, parity) issuer_wait(cx, bar, parity)
 #else
-#define STAGER_WAIT_X() stager_wait<kBarXReady>()
-#define STAGER_WAIT_D(la) stager_wait<kBarDReady>()
-#define ISSUER_RELEASE(ID, bar, parity) issuer_release<ID>(cx, bar, parity)
+#define STAGER_WAIT_X() stager_wait<kBarXReady, HV>()
+#define STAGER_WAIT_D(la) stager_wait<kBarDReady, HV>()
+#define ISSUER_RELEASE(ID, bar, parity) issuer_release<ID, HV>(cx, bar, parity)
 #endif
-		template <int ID> __device__ __forceinline__ void issuer_sync()
+		template <int ID, int HV> __device__ __forceinline__ void issuer_sync()
 		{
-			nbar_sync<ID, kSync>();
+			nbar_sync<ID, Th<HV>::kSync>();
 			fence_after();
 		}
 		__device__ __forceinline__ void issuer_wait(Ctx& cx, uint32_t bar, uint32_t parity)
 		{
 			if (!mbar_wait(bar, parity) && cx.el) *reinterpret_cast<volatile int*>(cx.err) = 1;   // lost completion: flag it, keep going so the launch ends
 		}
-		template <int ID> __device__ __forceinline__ void issuer_release(Ctx& cx, uint32_t bar, uint32_t parity)
+		template <int ID, int HV> __device__ __forceinline__ void issuer_release(Ctx& cx, uint32_t bar, uint32_t parity)
 		{
 			issuer_wait(cx, bar, parity);
-			nbar_arrive<ID, kSync>();
+			nbar_arrive<ID, Th<HV>::kSync>();
 		}
 
 		// one lane: bulk copy of sub-block g of layer b's weights into buffer (slot & 1)
@@ -329,12 +341,37 @@ namespace nab200
 			}
 		}
 
-		// C fp32 values -> C words [h1 of channel pairs | h2 of channel pairs]
-		template <int C>
-		__device__ __forceinline__ void pack_pairs(const uint32_t (&x)[C], uint32_t (&p)[C])
+		// A thread's share of a frame: CH consecutive channels -> CH / 2 words of h1 halves and CH / 2 words of h2 halves.  In the
+		// operand's row of C words, [h1 of channel pairs | h2 of channel pairs], they are words hv * CH / 2 .. and C / 2 + hv * CH / 2 ..
+		template <int CH>
+		__device__ __forceinline__ void pack_share(const uint32_t (&x)[CH], uint32_t (&h1)[CH / 2], uint32_t (&h2)[CH / 2])
 		{
 #pragma unroll
-			for (int c = 0; c < C / 2; c++) split_h2(x[2 * c], x[2 * c + 1], p[c], p[C / 2 + c]);
+			for (int c = 0; c < CH / 2; c++) split_h2(x[2 * c], x[2 * c + 1], h1[c], h2[c]);
+		}
+		// PW words of a frame's operand row, starting at word w0 (PW = 2, 4 or 8; w0 a multiple of PW), to the row's planes:
+		// word w sits in plane w / 4 at byte (w % 4) * 4 of the plane's 16-byte row.  `row` = address of the row in plane 0,
+		// `planeBytes` = distance between planes.
+		template <int PW>
+		__device__ __forceinline__ void sts_words(uint32_t row, uint32_t planeBytes, int w0, const uint32_t (&w)[PW])
+		{
+			if constexpr (PW == 2)
+				asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(row + (uint32_t)(w0 >> 2) * planeBytes + (uint32_t)(w0 & 3) * 4u), "r"(w[0]), "r"(w[1]) : "memory");
+			else
+			{
+#pragma unroll
+				for (int q = 0; q < PW / 4; q++) sts128(row + (uint32_t)((w0 >> 2) + q) * planeBytes, w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+			}
+		}
+		template <int PW>
+		__device__ __forceinline__ void stg_words(char* row, size_t planeBytes, int w0, const uint32_t (&w)[PW])
+		{
+			if constexpr (PW == 2) *reinterpret_cast<uint2*>(row + (size_t)(w0 >> 2) * planeBytes + (size_t)(w0 & 3) * 4) = make_uint2(w[0], w[1]);
+			else
+			{
+#pragma unroll
+				for (int q = 0; q < PW / 4; q++) *reinterpret_cast<uint4*>(row + (size_t)((w0 >> 2) + q) * planeBytes) = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+			}
 		}
 
 		// FastMath<T>::Tanh (Activation.h:83-91) for two values.  With a = |x|: tanh ~ x * P(a) / Q(a),
@@ -370,15 +407,17 @@ namespace nab200
 		}
 
 		// ---- stager warps: one layer array of the CTA's stream ------------------------------------------------------
-		template <int ROLE>
+		template <int ROLE, int HV>
 		__device__ __forceinline__ void stage_array(Ctx& cx, const int firstLayer, const int numLayers)
 		{
 			typedef Map<ROLE> MP;
-			constexpr int C = MP::C, CG = C / 4;
+			constexpr int C = MP::C, CH = C / HV, PW = CH / 2;   // channels, words of h1 (and of h2) per thread
 			const int tid = cx.tid;
-			const uint32_t lane = (uint32_t)(cx.warp * 32) << 16;
+			const int t = tid & 127, hv = tid >> 7;              // frame, channel half
+			const uint32_t lane = (uint32_t)((cx.warp & 3) * 32) << 16;
 			const int* hd = cx.hdb + cx.cur * kHdbHalf;
-			const uint32_t myRow = cx.win + (uint32_t)tid * 16u;
+			const uint32_t myRow = cx.win + (uint32_t)t * 16u;
+			const int w1 = hv * PW, w2 = C / 2 + hv * PW;        // this thread's words of the operand row: h1 part, h2 part
 
 			for (int li = 0; li < numLayers; li++)
 			{
@@ -400,22 +439,23 @@ namespace nab200
 #endif
 					cx.sqr += (uint32_t)(ng - 1);
 				}
-				uint32_t p[C];
+				uint32_t h1[PW], h2[PW];
 				{
-					uint32_t x[C];
-					tmem_ld<C>(lane + MP::xr(cx), x);
-					pack_pairs<C>(x, p);
+					uint32_t x[CH];
+					tmem_ld<CH>(lane + MP::xr(cx) + (uint32_t)(hv * CH), x);
+					pack_share<CH>(x, h1, h2);
 				}
-				tmem_st<C>(lane + MP::t2(cx), p);
+				tmem_st<PW>(lane + MP::t2(cx) + (uint32_t)w1, h1);
+				tmem_st<PW>(lane + MP::t2(cx) + (uint32_t)w2, h2);
 				if (mixed)
 				{
 					// a delayed tap shorter than the call reads this call's frames: they follow the history rows in the window
 					const uint32_t cur = myRow + lds32(la + 32u);
-#pragma unroll
-					for (int q = 0; q < CG; q++) sts128(cur + (uint32_t)q * cx.planeStride, p[4 * q], p[4 * q + 1], p[4 * q + 2], p[4 * q + 3]);
+					sts_words<PW>(cur, cx.planeStride, w1, h1);
+					sts_words<PW>(cur, cx.planeStride, w2, h2);
 					asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy rows -> the tensor core's async-proxy reads
 				}
-				stager_arrive<kBarT2>();
+				stager_arrive<kBarT2, HV>();
 				H_STAMP(2);
 				// ---- the next layer's first weight block, a layer ahead (one thread): the buffer it goes to held the previous layer's
 				// block, whose last readers - that layer's 1x1 products - completed before this layer began.  (A layer with tap
@@ -440,15 +480,14 @@ namespace nab200
 #ifdef NAB_H_NO_RINGWRITE   // timing experiment only
 					if (false)
 #else
-					if (tid < cx.n && tid >= first)
+					if (t < cx.n && t >= first)
 #endif
 					{
-						int idx = (cx.n > Lp ? hd[36 + g1.x] : hd[g1.x]) + (tid - first);
+						int idx = (cx.n > Lp ? hd[36 + g1.x] : hd[g1.x]) + (t - first);
 						if (idx >= Lp) idx -= Lp;
-						char* const ring = cx.sbase + (size_t)g0.w * 4;
-#pragma unroll
-						for (int q = 0; q < CG; q++)
-							*reinterpret_cast<uint4*>(ring + (size_t)(uint32_t)(idx + q * Lp) * 16) = make_uint4(p[4 * q], p[4 * q + 1], p[4 * q + 2], p[4 * q + 3]);
+						char* const row = cx.sbase + (size_t)g0.w * 4 + (size_t)(uint32_t)idx * 16;
+						stg_words<PW>(row, (size_t)(uint32_t)Lp * 16, w1, h1);
+						stg_words<PW>(row, (size_t)(uint32_t)Lp * 16, w2, h2);
 					}
 				}
 
@@ -458,21 +497,22 @@ namespace nab200
 				H_STAMP(7);
 				{
 					// the conv accumulator's two halves (W1 and W2 partial sums) are added here
-					uint32_t dv[C], dw[C], z[C];
-					tmem_ld_nowait<C>(lane + MP::d(cx), dv);
-					tmem_ld<C>(lane + MP::d(cx) + (uint32_t)C, dw);
+					uint32_t dv[CH], dw[CH], z[CH];
+					tmem_ld_nowait<CH>(lane + MP::d(cx) + (uint32_t)(hv * CH), dv);
+					tmem_ld<CH>(lane + MP::d(cx) + (uint32_t)(C + hv * CH), dw);
 #pragma unroll
-					for (int c = 0; c < C; c += 2)
+					for (int c = 0; c < CH; c += 2)
 					{
 						uint32_t s0, s1;
 						unpack2(add2(pack2(dv[c], dv[c + 1]), pack2(dw[c], dw[c + 1])), s0, s1);
 						if constexpr (ROLE == 2) leaky2(s0, s1, z[c], z[c + 1]);
 						else fast_tanh2(s0, s1, z[c], z[c + 1]);
 					}
-					pack_pairs<C>(z, dv);
-					tmem_st<C>(lane + MP::t2(cx), dv);
+					pack_share<CH>(z, h1, h2);
+					tmem_st<PW>(lane + MP::t2(cx) + (uint32_t)w1, h1);
+					tmem_st<PW>(lane + MP::t2(cx) + (uint32_t)w2, h2);
 				}
-				stager_arrive<kBarZ>();
+				stager_arrive<kBarZ, HV>();
 				H_STAMP(8);
 			}
 		}
@@ -576,7 +616,7 @@ namespace nab200
 			return __shfl_sync(0xffffffffu, mbar_test(cx.barL0 + 8u * (lq & 1u), (lq >> 1) & 1u) ? 1 : 0, 0) != 0;
 		}
 
-		template <int ROLE>
+		template <int ROLE, int HV>
 		__device__ __forceinline__ void issue_array(Ctx& cx, const int firstLayer, const int numLayers)
 		{
 			typedef Map<ROLE> MP;
@@ -598,7 +638,7 @@ namespace nab200
 
 				// ---- dilated conv (WaveNet.h:250-289): the undelayed tap and the delayed taps that read this call's frames ----
 				// A delayed tap is 128 rows of the shared-memory window starting at its own row offset: the MMAs read them in place.
-				issuer_sync<kBarT2>();
+				issuer_sync<kBarT2, HV>();
 				H_STAMP(3);
 				if (deferred)
 				{
@@ -693,7 +733,7 @@ namespace nab200
 				if (hasNext) plan_layer<C, N1, NT>(cx, l + 1, cx.wq + 1, Q);
 
 				// ---- 1x1 + bias + residual, head sum (WaveNet.h:482-491): XR | HD += [z] [W1x1 | Whead] ----
-				issuer_sync<kBarZ>();
+				issuer_sync<kBarZ, HV>();
 				H_STAMP(7);
 				if (cx.el)
 				{
@@ -737,8 +777,8 @@ namespace nab200
 
 		// ARCH 0: two arrays, (16, 8) channels, tanh, 1x1 heads (A1 Standard / Lite).  ARCH 1: one 8-channel array, LeakyReLU,
 		// 16-tap head conv (A2, WaveNet.h:632-661 with the InternalModel.h:12-20 shapes).
-		template <int ARCH>
-		__global__ void __maxnreg__(64)
+		template <int ARCH, int HV>
+		__global__ void __launch_bounds__(Th<HV>::kThreads, HV == 2 ? 4 : 5)
 			wavenet_h_kernel(const __grid_constant__ WnModelDev M, const float* __restrict__ Wg, float* __restrict__ state, int* __restrict__ heads,
 				const float* in, float* out, long long inSS, long long inFS, long long outSS, long long outFS, int S, int n, int* __restrict__ err)
 		{
@@ -783,7 +823,7 @@ namespace nab200
 				const uint4* src = reinterpret_cast<const uint4*>(Wg + M.tableOff);
 				uint4* dst = reinterpret_cast<uint4*>(tabPtr);
 				const int n16 = M.numLayers * (int)(sizeof(HLayer) / 16);
-				for (int i = tid; i < n16; i += kThreads) dst[i] = __ldg(src + i);
+				for (int i = tid; i < n16; i += Th<HV>::kThreads) dst[i] = __ldg(src + i);
 			}
 			if (tid == 0)
 			{
@@ -791,7 +831,7 @@ namespace nab200
 				for (int b = 0; b < kNumBars; b++) mbar_init(cx.barW0 + 8u * (uint32_t)b, (b == 4 || b == 5) ? 2 : 1);   // a layer's barrier: its windows + its first weight block
 				asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 			}
-			if (warp == 4)
+			if (warp == Th<HV>::kIssuerWarp)
 			{
 				// one power-of-two allocation per CTA cannot fragment: 4 CTAs x 128 (8 x 64) columns fit the SM's 512
 				tmem_alloc<ARCH == 0 ? 128 : 64>(smem_u32(tmemSlot));
@@ -813,12 +853,12 @@ namespace nab200
 			cx.r0 = tmemSlot[0];
 			cx.konst = cx.r0 + (ARCH == 0 ? 72u : 56u);
 
-			if (warp == 5)
+			if (warp == Th<HV>::kFetcherWarp)
 			{
 				// =================================== fetcher warp ===================================
 				fetch_loop(cx, heads, s0);
 			}
-			else if (warp == 4)
+			else if (warp == Th<HV>::kIssuerWarp)
 			{
 				// =================================== issuer warp ===================================
 				const uint32_t ent0 = lds128(cx.tab + (uint32_t)first0 * (uint32_t)sizeof(HLayer) + 64).z;
@@ -829,7 +869,7 @@ namespace nab200
 					cx.hasNext = s + (int)gridDim.x < S;
 					// ---- entry: [XR | HD] = constant operand x [rechannel 1 -> C0 | head bias] (WaveNet.h:637) ----
 					issuer_wait(cx, cx.barL0 + 8u * (cx.lq & 1u), (cx.lq >> 1) & 1u);   // the first layer's block carries the entry operand
-					issuer_sync<kBarE>();
+					issuer_sync<kBarE, HV>();
 					if (cx.el)
 					{
 						const uint32_t wb16 = (cx.wbuf + (cx.wq & 1u) * cx.wbufStride) >> 4;
@@ -841,11 +881,11 @@ namespace nab200
 					cx.xq++;
 					if constexpr (ARCH == 0)
 					{
-						issue_array<0>(cx, first0, num0);
+						issue_array<0, HV>(cx, first0, num0);
 
 						// ---- array transition (WaveNet.h:785-789): [XR1 | HD1] = rechannel C0 -> C1 of the array output | head carry ----
 						issuer_wait(cx, cx.barL0 + 8u * (cx.lq & 1u), (cx.lq >> 1) & 1u);   // the second array's first block carries the transition operands
-						issuer_sync<kBarE>();
+						issuer_sync<kBarE, HV>();
 						if (cx.el)
 						{
 							const uint32_t wb16 = (cx.wbuf + (cx.wq & 1u) * cx.wbufStride) >> 4;
@@ -862,18 +902,19 @@ namespace nab200
 						// (the second array's conv accumulator reuses columns the transition products read: they have completed)
 						ISSUER_RELEASE(kBarXReady, cx.barX, cx.xq & 1u);
 						cx.xq++;
-						issue_array<1>(cx, first1, num1);
+						issue_array<1, HV>(cx, first1, num1);
 					}
-					else issue_array<2>(cx, first0, num0);
+					else issue_array<2, HV>(cx, first0, num0);
 					cx.cur ^= 1;
 				}
 			}
 			else
 			{
 				// =================================== stager warps ===================================
-				const uint32_t lane = (uint32_t)(warp * 32) << 16;
+				const uint32_t lane = (uint32_t)((warp & 3) * 32) << 16;
+				const int t = tid & 127, hv = tid >> 7;   // frame, channel half (HV == 1: always 0)
 				float cond = 0.0f;
-				if (tid < n && s0 < S) cond = in[(long long)s0 * inSS + (long long)tid * inFS];
+				if (hv == 0 && t < n && s0 < S) cond = in[(long long)s0 * inSS + (long long)t * inFS];
 				const size_t strideBytes = (size_t)M.stateStride * 4;
 				cx.sbase = reinterpret_cast<char*>(state) + (size_t)s0 * strideBytes;
 				if (tid == kWeightThread && s0 < S) request_weights(cx, 0, 0, 0, cx.barL0);
@@ -895,7 +936,7 @@ namespace nab200
 							hdNext[tid] = h;
 							hdNext[36 + tid] = hn;
 						}
-						if (tid < n) condNext = in[(long long)sn * inSS + (long long)tid * inFS];
+						if (hv == 0 && t < n) condNext = in[(long long)sn * inSS + (long long)t * inFS];
 					}
 					float* const hist = reinterpret_cast<float*>(cx.sbase) + M.arrays[0].headRingOff;
 					if constexpr (ARCH == 1)
@@ -905,6 +946,7 @@ namespace nab200
 						cp_async_commit();
 					}
 					// ---- entry: constant operand, 16 halves [c1, c2, c1, 1, 1, 1, 0 ...] ----
+					if (hv == 0)
 					{
 						uint32_t c12, dummy;
 						split_h2(__float_as_uint(cond), 0u, c12, dummy);   // c12 low half = c1; dummy low half = c2
@@ -915,37 +957,41 @@ namespace nab200
 						cv[3] = 0u; cv[4] = 0u; cv[5] = 0u; cv[6] = 0u; cv[7] = 0u;
 						tmem_st<8>(lane + konst(cx), cv);
 					}
-					stager_arrive<kBarE>();
+					stager_arrive<kBarE, HV>();
 					if constexpr (ARCH == 0)
 					{
-						stage_array<0>(cx, first0, num0);
+						stage_array<0, HV>(cx, first0, num0);
 
 						// ---- array transition: the array output and its head output as packed pairs ----
 						STAGER_WAIT_X();
 						{
-							uint32_t x[16], p[16];
-							tmem_ld_nowait<16>(lane + Map<0>::xr(cx), x);
-							uint32_t h[8], hp[8];
-							tmem_ld<8>(lane + Map<0>::hd(cx), h);
-							pack_pairs<16>(x, p);
-							tmem_st<16>(lane + cx.r0, p);
-							pack_pairs<8>(h, hp);
-							tmem_st<8>(lane + cx.r0 + 16u, hp);
+							// each thread its share of the 16 output channels (operand row at r0) and of the 8 head values (row at r0 + 16)
+							constexpr int CX = 16 / HV, CHd = 8 / HV;
+							uint32_t x[CX], xh1[CX / 2], xh2[CX / 2];
+							tmem_ld_nowait<CX>(lane + Map<0>::xr(cx) + (uint32_t)(hv * CX), x);
+							uint32_t h[CHd], hh1[CHd / 2], hh2[CHd / 2];
+							tmem_ld<CHd>(lane + Map<0>::hd(cx) + (uint32_t)(hv * CHd), h);
+							pack_share<CX>(x, xh1, xh2);
+							tmem_st<CX / 2>(lane + cx.r0 + (uint32_t)(hv * (CX / 2)), xh1);
+							tmem_st<CX / 2>(lane + cx.r0 + 8u + (uint32_t)(hv * (CX / 2)), xh2);
+							pack_share<CHd>(h, hh1, hh2);
+							tmem_st<CHd / 2>(lane + cx.r0 + 16u + (uint32_t)(hv * (CHd / 2)), hh1);
+							tmem_st<CHd / 2>(lane + cx.r0 + 20u + (uint32_t)(hv * (CHd / 2)), hh2);
 						}
-						stager_arrive<kBarE>();
-						stage_array<1>(cx, first1, num1);
+						stager_arrive<kBarE, HV>();
+						stage_array<1, HV>(cx, first1, num1);
 
 						// ---- output (WaveNet.h:793-798) ----
 						STAGER_WAIT_X();
 						{
-							uint32_t h[8];
-							tmem_ld<8>(lane + Map<1>::hd(cx), h);
-							if (tid < n) out[(long long)s * outSS + (long long)tid * outFS] = M.headScale * __uint_as_float(h[0]);
+							uint32_t h[2];
+							tmem_ld<2>(lane + Map<1>::hd(cx), h);
+							if (hv == 0 && t < n) out[(long long)s * outSS + (long long)t * outFS] = M.headScale * __uint_as_float(h[0]);
 						}
 					}
 					else
 					{
-						stage_array<2>(cx, first0, num0);
+						stage_array<2, HV>(cx, first0, num0);
 
 						// ---- output: 16-tap head conv of the summed head (WaveNet.h:658-660, 793-798) ----
 						// HD column k holds G_k[t] = Wh_k . headsum[t] (+ the head bias in column 15); out[t] = sum_k G_k[t - 15 + k].
@@ -960,7 +1006,7 @@ namespace nab200
 #pragma unroll
 						for (int half = 0; half < 2; half++)
 						{
-							nbar_sync<kBarMix, kStagers>();
+							nbar_sync<kBarMix, Th<HV>::kStagers>();
 #pragma unroll
 							for (int kk = 0; kk < 8; kk++)
 							{
@@ -968,7 +1014,7 @@ namespace nab200
 								asm volatile("st.shared.b32 [%0], %1;" ::"r"(plane + (uint32_t)(15 + tid) * 4u), "r"(g[8 * half + kk]) : "memory");
 								if (tid < 15) asm volatile("st.shared.b32 [%0], %1;" ::"r"(plane + (uint32_t)tid * 4u), "r"(__float_as_uint(headHist[(8 * half + kk) * 16 + tid])) : "memory");
 							}
-							nbar_sync<kBarMix, kStagers>();
+							nbar_sync<kBarMix, Th<HV>::kStagers>();
 #pragma unroll
 							for (int kk = 0; kk < 8; kk++)
 							{
@@ -991,7 +1037,7 @@ namespace nab200
 
 			fence_before();
 			__syncthreads();
-			if (warp == 4) tmem_dealloc<ARCH == 0 ? 128 : 64>(cx.r0);
+			if (warp == Th<HV>::kIssuerWarp) tmem_dealloc<ARCH == 0 ? 128 : 64>(cx.r0);
 		}
 	}
 
@@ -1009,7 +1055,8 @@ namespace nab200
 	template <int ARCH>
 	static cudaError_t h_launch_arch(const WnModelDev& M, const WnLaunch& a)
 	{
-		auto kfn = hk::wavenet_h_kernel<ARCH>;
+		constexpr int HV = ARCH == 0 ? hk::kHvTwoArrays : 1;
+		auto kfn = hk::wavenet_h_kernel<ARCH, HV>;
 		const size_t smem = wavenet_h_smem_bytes(M);
 		// five CTAs of ~43 KB need the SM's full 228 KB as shared memory: ask for the maximum carve-out (the default heuristic
 		// keeps more L1 and fits only four - ncu launch__occupancy_limit_shared_mem)
@@ -1020,13 +1067,13 @@ namespace nab200
 		// windows and weight blocks make the CTA's shared memory larger than a fifth of the SM's
 		int fit = (int)((size_t)(228 * 1024) / (smem + 1024));
 		if (fit > 5) fit = 5;
-		if (ARCH == 0 && fit > 4) fit = 4;   // 128 TMEM columns per stream
+		if (ARCH == 0 && fit > 4) fit = 4;   // 128 TMEM columns per stream (and, with two threads per frame, 10 warps of 48 registers)
 		if (fit < 1) fit = 1;
 		int ctasPerSM = a.ctasPerSM > 0 ? a.ctasPerSM : fit;
 		int grid = a.numSMs * ctasPerSM;
 		if (grid > a.S) grid = a.S;
 		if (grid < 1) grid = 1;
-		kfn<<<grid, hk::kThreads, smem, a.stream>>>(M, a.weights, a.state, a.heads, a.in, a.out, a.inSS, a.inFS, a.outSS, a.outFS, a.S, a.n, a.err);
+		kfn<<<grid, hk::Th<HV>::kThreads, smem, a.stream>>>(M, a.weights, a.state, a.heads, a.in, a.out, a.inSS, a.inFS, a.outSS, a.outFS, a.S, a.n, a.err);
 		return cudaGetLastError();
 	}
 

@@ -97,21 +97,22 @@ int main(int argc, char** argv)
 #ifndef NAB_H_TIMING
 	return 0;
 #else
-	static long long st[4][6][4][32][12];
+	static long long st[4][10][4][32][12];
+	const int IW = a2 ? 4 : 4 * hk::kHvTwoArrays, FW = IW + 1;   // issuer / fetcher warp index
 	cudaMemcpyFromSymbol(st, hk::g_stamps, sizeof(st));
 	const int NL = M.numLayers;
 	if (getenv("NAB_H_DUMP"))
 	{
 		// absolute event times of one stream of one CTA (cycles since the issuer began the stream's first layer)
 		const int c = 1, k = 1;
-		const long long t0 = st[c][4][k][0][2];
+		const long long t0 = st[c][IW][k][0][2];
 		printf("layer | fetcher: start regionFree issued | issuer: top T2 committed DReady Z 1x1committed XReady | stager0: XReady' T2arrive winWait ringDone DReady' Zarrive\n");
 		for (int l = 0; l < NL; l++)
 		{
 			printf("%2d |", l);
-			for (int i : {0, 1, 2}) printf(" %6lld", st[c][5][k][l][i] - t0);
+			for (int i : {0, 1, 2}) printf(" %6lld", st[c][FW][k][l][i] - t0);
 			printf(" |");
-			for (int i : {2, 3, 5, 6, 7, 8, 9}) printf(" %6lld", st[c][4][k][l][i] - t0);
+			for (int i : {2, 3, 5, 6, 7, 8, 9}) printf(" %6lld", st[c][IW][k][l][i] - t0);
 			printf(" |");
 			for (int i : {1, 2, 3, 6, 7, 8}) printf(" %6lld", st[c][0][k][l][i] - t0);
 			printf("\n");
@@ -124,11 +125,11 @@ int main(int argc, char** argv)
 		{ "plan next + wait its data + wait Z", 6, 7 }, { "1x1 MMAs+commit", 7, 8 }, { "wait barX + release", 8, 9 } };
 	const Phase fetcherPhases[] = { { "wait region free", 0, 1 }, { "issue copies", 1, 2 }, { "-", 2, 3 } };
 	for (int c = 0; c < 4; c++)
-		for (int w : {0, 3, 4, 5})
+		for (int w : {0, 3, IW, FW})
 		{
-			const Phase* ph = w == 5 ? fetcherPhases : w == 4 ? issuerPhases : stagerPhases;
-			const int np = w == 5 ? 3 : 6;
-			printf("CTA slot %d warp %d (%s; mean cycles over 4 streams), per layer then mean:\n", c, w, w == 5 ? "fetcher" : w == 4 ? "issuer" : "stager");
+			const Phase* ph = w == FW ? fetcherPhases : w == IW ? issuerPhases : stagerPhases;
+			const int np = w == FW ? 3 : 6;
+			printf("CTA slot %d warp %d (%s; mean cycles over 4 streams), per layer then mean:\n", c, w, w == FW ? "fetcher" : w == IW ? "issuer" : "stager");
 			for (int p = 0; p < np; p++)
 			{
 				printf("  %-30s", ph[p].name);
