@@ -60,6 +60,10 @@ namespace nab200
 		}
 		// The same wait for a warp that is in no hurry (waits of a microsecond): it sleeps between tries instead of polling
 		// (round 2: the fetcher's waits looped ~30 times each, 7 % of the kernel's instructions).
+#ifndef NAB_RELAXED_SLEEP_NS
+#define NAB_RELAXED_SLEEP_NS 400
+#endif
+		constexpr uint32_t kRelaxedSleepNs = NAB_RELAXED_SLEEP_NS;
 		__device__ __forceinline__ bool mbar_wait_relaxed(uint32_t bar, uint32_t parity)
 		{
 			for (uint32_t it = 0; it < kSpinLimit; it++)
@@ -67,7 +71,7 @@ namespace nab200
 				uint32_t ok;
 				asm volatile("{\n.reg .pred P1;\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\nselp.u32 %0, 1, 0, P1;\n}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
 				if (ok) return true;
-				__nanosleep(100);
+				__nanosleep(kRelaxedSleepNs);
 			}
 			return false;
 		}

@@ -364,13 +364,14 @@ namespace nab200
 			}
 		}
 		template <int PW>
-		__device__ __forceinline__ void stg_words(char* row, size_t planeBytes, int w0, const uint32_t (&w)[PW])
+		__device__ __forceinline__ void stg_words(char* row, uint32_t planeBytes, int w0, const uint32_t (&w)[PW])
 		{
-			if constexpr (PW == 2) *reinterpret_cast<uint2*>(row + (size_t)(w0 >> 2) * planeBytes + (size_t)(w0 & 3) * 4) = make_uint2(w[0], w[1]);
+			// (32-bit offsets: one stream's state is far below 4 GB)
+			if constexpr (PW == 2) *reinterpret_cast<uint2*>(row + ((uint32_t)(w0 >> 2) * planeBytes + (uint32_t)(w0 & 3) * 4u)) = make_uint2(w[0], w[1]);
 			else
 			{
 #pragma unroll
-				for (int q = 0; q < PW / 4; q++) *reinterpret_cast<uint4*>(row + (size_t)((w0 >> 2) + q) * planeBytes) = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+				for (int q = 0; q < PW / 4; q++) *reinterpret_cast<uint4*>(row + (uint32_t)((w0 >> 2) + q) * planeBytes) = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
 			}
 		}
 
@@ -433,11 +434,14 @@ namespace nab200
 				{
 					// a layer with tap groups: its second weight sub-block, now that the buffer it goes to is free (it held the
 					// previous layer's last block, whose readers completed with that layer's 1x1)
-					const int ng = (int)lds32(la + 36u);
+					if (tid == kWeightThread)
+					{
+						const int ng = (int)lds32(la + 36u);
 #ifndef NAB_H_SUB1_BY_ISSUER
-					if (ng > 1 && tid == kWeightThread) request_weights(cx, l, 1, cx.wq + 1, cx.barW0 + 8u * (cx.sqr & 1u));
+						if (ng > 1) request_weights(cx, l, 1, cx.wq + 1, cx.barW0 + 8u * (cx.sqr & 1u));
 #endif
-					cx.sqr += (uint32_t)(ng - 1);
+						cx.sqr += (uint32_t)(ng - 1);
+					}
 				}
 				uint32_t h1[PW], h2[PW];
 				{
@@ -460,9 +464,10 @@ namespace nab200
 				// ---- the next layer's first weight block, a layer ahead (one thread): the buffer it goes to held the previous layer's
 				// block, whose last readers - that layer's 1x1 products - completed before this layer began.  (A layer with tap
 				// groups streams its sub-blocks and the block after them from the issuer.)
+				if (tid == kWeightThread)
 				{
 					const int ng = (int)lds32(la + 36u);
-					if (ng == 1 && tid == kWeightThread)
+					if (ng == 1)
 					{
 						const int nl = l + 1 < cx.numLayers ? l + 1 : (cx.hasNext ? 0 : -1);
 						if (nl >= 0) request_weights(cx, nl, 0, cx.wq + 1, cx.barL0 + 8u * ((cx.lq + 1u) & 1u));
@@ -475,19 +480,21 @@ namespace nab200
 				cx.lq++;
 				H_STAMP(3);
 				{
+					// frames first .. n - 1 are written (the last min(n, Lp) of the call); frame `first` goes to ring row hd[36 + ring]
+					// (prepared with the heads: the head itself, or the post-call head when the call is longer than the ring)
 					const int Lp = (int)g0.z;
-					const int first = cx.n > Lp ? cx.n - Lp : 0;
+					const int rel = t - (cx.n > Lp ? cx.n - Lp : 0);
 #ifdef NAB_H_NO_RINGWRITE   // timing experiment only
 					if (false)
 #else
-					if (t < cx.n && t >= first)
+					if (t < cx.n && rel >= 0)
 #endif
 					{
-						int idx = (cx.n > Lp ? hd[36 + g1.x] : hd[g1.x]) + (t - first);
+						int idx = hd[36 + g1.x] + rel;
 						if (idx >= Lp) idx -= Lp;
-						char* const row = cx.sbase + (size_t)g0.w * 4 + (size_t)(uint32_t)idx * 16;
-						stg_words<PW>(row, (size_t)(uint32_t)Lp * 16, w1, h1);
-						stg_words<PW>(row, (size_t)(uint32_t)Lp * 16, w2, h2);
+						char* const row = cx.sbase + ((uint32_t)g0.w * 4u + (uint32_t)idx * 16u);
+						stg_words<PW>(row, (uint32_t)Lp * 16u, w1, h1);
+						stg_words<PW>(row, (uint32_t)Lp * 16u, w2, h2);
 					}
 				}
 
@@ -845,7 +852,7 @@ namespace nab200
 				int hn = h + (n % Lp);
 				if (hn >= Lp) hn -= Lp;
 				cx.hdb[tid] = h;
-				cx.hdb[36 + tid] = hn;
+				cx.hdb[36 + tid] = n > Lp ? hn : h;   // ring row of the first frame the write-back stores (a call longer than the ring rewrites all of it, from the new head on)
 			}
 			fence_before();
 			__syncthreads();
@@ -934,7 +941,7 @@ namespace nab200
 							int hn = h + (n % Lp);
 							if (hn >= Lp) hn -= Lp;
 							hdNext[tid] = h;
-							hdNext[36 + tid] = hn;
+							hdNext[36 + tid] = n > Lp ? hn : h;
 						}
 						if (hv == 0 && t < n) condNext = in[(long long)sn * inSS + (long long)t * inFS];
 					}
@@ -1026,7 +1033,14 @@ namespace nab200
 						}
 						if (tid < n) out[(long long)s * outSS + (long long)tid * outFS] = M.headScale * acc;
 					}
-					if (tid < M.numRings) heads[(size_t)s * M.numRings + tid] = cx.hdb[cx.cur * kHdbHalf + 36 + tid];
+					if (tid < M.numRings)
+					{
+						// the ring heads after the call
+						const int Lp = M.ringLp[tid];
+						int hn = cx.hdb[cx.cur * kHdbHalf + tid] + (n % Lp);
+						if (hn >= Lp) hn -= Lp;
+						heads[(size_t)s * M.numRings + tid] = hn;
+					}
 					cx.cur ^= 1;
 					cond = condNext;
 					cx.sbase += (size_t)gridDim.x * strideBytes;
