@@ -543,8 +543,7 @@ int NA_DescribeModelFile(const wchar_t* modelPath, int externalSampleRate, char*
 								const nab200::WnLayer& L = q.dev.layers[layer];
 								const nab200::HLayer& T = tab[layer];
 								const int K = A.kernelSizes[l];
-								const size_t opHalves = (size_t)2 * CP * 8;
-								// where tap k's [W1 | W2] sits: the undelayed tap and group 0 in sub-block 0, later groups in their own sub-blocks
+								// where tap k's operand [k group][2 CP columns: W1 | W2][8 halves] sits: the undelayed tap and group 0 in sub-block 0, later groups in their own sub-blocks
 								auto tapAt = [&](int k) -> const __half*
 								{
 									if (k == K - 1) return reinterpret_cast<const __half*>(q.weights.data() + T.gOff[0]) + (size_t)T.und16 * 8;
@@ -558,8 +557,8 @@ int NA_DescribeModelFile(const wchar_t* modelPath, int externalSampleRate, char*
 										for (int k = 0; k < K; k++)
 										{
 											const __half* blk = tapAt(k);
-											const size_t at = ((size_t)(jn / 8) * CP + i) * 8 + (jn % 8);
-											const double v = (double)__half2float(blk[at]) + (double)__half2float(blk[at + opHalves]);
+											const size_t at = ((size_t)(jn / 8) * 2 * CP + i) * 8 + (jn % 8);
+											const double v = (double)__half2float(blk[at]) + (double)__half2float(blk[at + (size_t)CP * 8]);
 											const double e = fabs(v - (double)*src);
 											if (e > worst) worst = e;
 											if (fabs((double)*src) > 1e-3 && e / fabs((double)*src) > worstRel) worstRel = e / fabs((double)*src);

@@ -764,7 +764,23 @@ namespace nab200
 		// two arrays of (9..16, <= 8) channels, tanh, kernel size 3, 1x1 heads, head of array 0 feeding array 1 (A1 Standard / Lite
 		// and stacks of that family) - or the A2 single array; every layer's history must fit the window plan below
 		const bool single = IsHSingleArray(desc);
-		if (!single && !WaveNetTsSupported(desc)) return false;
+		if (!single)
+		{
+			// two arrays of (5..16, <= 8) channels (padded to 16 and 8: A1 Standard, Lite, Feather and stacks of that family; the
+			// 4-channel Nano stays on the CUDA-core kernel, faster at that width), tanh, kernel size 3, 1x1 heads, head of array 0
+			// feeding array 1
+			if (desc.arrays.size() != 2) return false;
+			const WaveNetArrayDesc& A0 = desc.arrays[0];
+			const WaveNetArrayDesc& A1 = desc.arrays[1];
+			if (A0.channels <= 4 || A0.channels > 16 || A1.channels < 1 || A1.channels > 8) return false;
+			if (A0.inputSize != 1 || A1.inputSize != A0.channels || A0.headSize != A1.channels || A1.headSize != 1) return false;
+			for (const auto& A : desc.arrays)
+			{
+				if (A.activation != 0 || A.headKernel != 1 || A.dilations.empty()) return false;
+				for (size_t l = 0; l < A.dilations.size(); l++)
+					if (A.kernelSizes[l] != 3 || A.dilations[l] < 1) return false;
+			}
+		}
 		const int R = single ? 1024 : kHWinRowsTwoArrays;
 		size_t layers = 0;
 		for (const auto& A : desc.arrays)
@@ -806,12 +822,12 @@ namespace nab200
 		{
 			const WaveNetArrayDesc& A = desc.arrays[a];
 			WnArray& DA = M.arrays[a];
-			const int C = A.channels, CP = TcPad(C), Kh = A.headKernel, HN = single ? 16 : 8, N1 = CP + HN;
+			const int C = A.channels, CP = single ? TcPad(C) : (a == 0 ? 16 : 8), Kh = A.headKernel, HN = single ? 16 : 8, N1 = CP + HN;
 			const int last = a + 1 == M.numArrays;
 			const int inC = A.inputSize;
 			const int H = A.headSize;
 			const int nL = (int)A.dilations.size();
-			DA.C = CP; DA.inC = a == 0 ? 1 : TcPad(inC); DA.H = 8; DA.Kh = Kh; DA.act = A.activation;
+			DA.C = CP; DA.inC = a == 0 ? 1 : 16; DA.H = 8; DA.Kh = Kh; DA.act = A.activation;
 			DA.firstLayer = layerIdx; DA.numLayers = nL; DA.realC = C; DA.realH = H;
 			const float* wRe = w; w += (size_t)C * inC;
 			std::vector<const float*> wLayer(nL);
