@@ -364,7 +364,8 @@ def measure(na, torch, dist, dev, rank, world, workload, path, streams, frames, 
             ent = json.load(open(tp)).get(workload, {})
             # a capture of another kernel is stale: report nothing rather than a wrong number
             if ent.get("kernel_choice") == kernel_name or kernel_name is None:
-                traffic = ent.get("dram_bytes_per_launch")
+                # a step of more than 128 frames is several launches of the tensor-core kernels (128 frames per pass)
+                traffic = ent.get("dram_bytes_per_step", ent.get("dram_bytes_per_launch"))
         except Exception:
             traffic = None
     total_units = world * streams * frames

@@ -131,13 +131,14 @@ NA_EXTERN long long NA_GetBroadcastBytes(NeuralModel* model);
 NA_EXTERN int NA_CopyStreamState(NeuralModel* model, size_t stream, float* hostOut, size_t capacityFloats);   /* returns floats written */
 NA_EXTERN int NA_DescribeModelFile(const wchar_t* modelPath, int externalSampleRate, char* out, int capacity);   /* host only: parse + pack, no GPU touched; JSON text */
 /* Tuning / test knobs, process-wide, read when a model is loaded; returns the previous value or -1 for an unknown name.
- *   "use_tc":  2 (default) tcgen05 WaveNet kernel with TMEM operands where the architecture fits (A1 Standard / Lite),
- *              1 tcgen05 kernel with shared-memory operands, 0 CUDA-core kernels only, -1 the run-time-shaped kernel even
- *              for architectures that have a specialised one (cross-checks);
- *   "ts_split": 1 = run the TMEM-operand kernel as one launch per layer array (default 0, fused);
+ *   "use_tc":  3 (default) tcgen05 WaveNet kernel with fp16-pair operands where the architecture fits (A1 Standard / Lite /
+ *              Feather, A2 Full), 2 the 3xTF32 tcgen05 kernel with TMEM operands (A1 Standard / Lite), 0 CUDA-core kernels
+ *              only, -1 the run-time-shaped kernel even for architectures that have a specialised one (cross-checks);
+ *   "h_ctas":  streams in flight per SM of the fp16-pair kernel (0 = its default);
+ *   "ts_split": 1 = run the 3xTF32 kernel as one launch per layer array (default 0, fused);
  *   "use_tma": 0 = plain loads instead of TMA in the CUDA-core WaveNet kernel (debugging aid);
  *   "max_grid_ctas": cap on the SM count used for grid sizing (0 = all).
- * The same knobs can be preset through NAB200_USE_TC / NAB200_TS_SPLIT / NAB200_USE_TMA / NAB200_MAX_GRID_CTAS. */
+ * The same knobs can be preset through NAB200_USE_TC / NAB200_H_CTAS / NAB200_TS_SPLIT / NAB200_USE_TMA / NAB200_MAX_GRID_CTAS. */
 NA_EXTERN int NA_SetOption(const char* name, int value);
 /* the same knobs for the models ONE loader builds (copied into each model at load; nothing is read from globals at run time) */
 NA_EXTERN void NA_SetLoaderOption(NeuralModelLoader* loader, const char* name, int value);

@@ -14,7 +14,7 @@ timeout 300 python bench.py --impl reference --steps 20 --warmup 3 > gpurun_out/
 # every launch with its device time (cold-cache, serialised: compare shares)
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file gpurun_out/launches.csv python bench.py --steps 4 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launches.out 2>&1
 # full capture of the dominant kernel: skip the S = 1 launches of the prewarm settle pass (receptive field / 128 + 2 of them)
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:wavenet_h -s 60 -c 1 -f -o gpurun_out/prof_wavenet python bench.py --steps 4 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full.out 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:wavenet_h -s 36 -c 1 -f -o gpurun_out/prof_wavenet python bench.py --steps 4 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full.out 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:lstm_fwd -s 20 -c 1 -f -o gpurun_out/prof_lstm python bench.py --workload lstm_1x16 --steps 4 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full_lstm.out 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:wavenet_h -s 120 -c 1 -f -o gpurun_out/prof_a2 python bench.py --workload a2_full --steps 4 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full_a2.out 2>&1
 ls -la gpurun_out

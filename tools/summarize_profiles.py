@@ -83,6 +83,12 @@ def main():
             rd = float(launches[0]["dram__bytes_read.sum"].split()[0]) * (1e6 if "Mbyte" in launches[0]["dram__bytes_read.sum"] else 1e9 if "Gbyte" in launches[0]["dram__bytes_read.sum"] else 1e3 if "Kbyte" in launches[0]["dram__bytes_read.sum"] else 1)
             wr = float(launches[0]["dram__bytes_write.sum"].split()[0]) * (1e6 if "Mbyte" in launches[0]["dram__bytes_write.sum"] else 1e9 if "Gbyte" in launches[0]["dram__bytes_write.sum"] else 1e3 if "Kbyte" in launches[0]["dram__bytes_write.sum"] else 1)
             traffic[workload] = {"dram_bytes_per_launch": rd + wr, "dram_read": rd, "dram_write": wr, "kernel": launches[0]["kernel"][:60], "from": tag}
+            if "wavenet_h_kernel<0>" in launches[0]["kernel"] or "wavenet_h_kernel<(int)0" in launches[0]["kernel"]:
+                traffic[workload]["kernel_choice"] = "tcgen05_fp16_pairs"
+            if workload == "a2_full":
+                # the bench's A2 step is 256 frames = two 128-frame launches of the tensor-core kernel
+                traffic[workload]["launches_per_step"] = 2
+                traffic[workload]["dram_bytes_per_step"] = 2 * (rd + wr)
         except Exception as e:
             print("traffic parse failed", e)
     json.dump(summary, open(os.path.join(PROF, tag + "_ncu_summary.json"), "w"), indent=1)
