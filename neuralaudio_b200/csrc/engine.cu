@@ -20,6 +20,7 @@ namespace nab200
 			env("NAB200_USE_TC", v.useTc);
 			env("NAB200_TS_SPLIT", v.tsSplit);
 			env("NAB200_H_CTAS", v.hCtas);
+			env("NAB200_USE_ONE", v.useOne);
 			env("NAB200_USE_TMA", v.useTma);
 			env("NAB200_MAX_GRID_CTAS", v.maxGridCtas);
 			env("NAB200_LSTM_KERNEL", v.lstmKernel);
@@ -37,6 +38,7 @@ namespace nab200
 		else if (strcmp(name, "use_tc") == 0) { prev = o.useTc; o.useTc = value; }
 		else if (strcmp(name, "ts_split") == 0) { prev = o.tsSplit; o.tsSplit = value; }
 		else if (strcmp(name, "h_ctas") == 0) { prev = o.hCtas; o.hCtas = value; }
+		else if (strcmp(name, "use_one") == 0) { prev = o.useOne; o.useOne = value; }
 		else if (strcmp(name, "max_grid_ctas") == 0) { prev = o.maxGridCtas; o.maxGridCtas = value; }
 		else if (strcmp(name, "lstm_kernel") == 0) { prev = o.lstmKernel; o.lstmKernel = value; }
 		return prev;
@@ -564,7 +566,9 @@ namespace nab200
 
 	bool WaveNetEngine::ProcessDevice(const float* in, float* out, long long inSS, long long inFS, long long outSS, long long outFS, size_t S, size_t n, size_t slotOffset)
 	{
-		const int maxPass = (packed.dev.tc || useGeneric) ? 128 : wavenet_max_frames_per_pass(packed.dev.arrays[0].C);
+		// a single stream of a small WaveNet: the one-CTA kernel (the reference's own use: one mono stream, one short buffer per call)
+		const bool one = S == 1 && opt.useOne != 0 && !useGeneric && wavenet_one_supported(packed.dev, weightFloats);
+		const int maxPass = (packed.dev.tc || useGeneric || one) ? 128 : wavenet_max_frames_per_pass(packed.dev.arrays[0].C);
 		size_t done = 0;
 		while (done < n)
 		{
@@ -584,7 +588,7 @@ namespace nab200
 			a.tsSplit = opt.tsSplit; a.scratch = dScratch ? dScratch + slotOffset * wavenet_ts_scratch_floats_per_stream() : nullptr;
 			a.ctasPerSM = opt.hCtas; a.err = dErr;
 			const cudaError_t lerr = packed.dev.tc == 3 ? wavenet_h_launch(packed.dev, a) : packed.dev.tc == 2 ? wavenet_ts_launch(packed.dev, a)
-				: useGeneric ? wavenet_generic_launch(packed.dev, a) : wavenet_launch(packed.dev, a);
+				: useGeneric ? wavenet_generic_launch(packed.dev, a) : one ? wavenet_one_launch(packed.dev, a, weightFloats) : wavenet_launch(packed.dev, a);
 			if (!CudaOk(lerr, "wavenet kernel launch")) return false;
 			kernelLaunches += (packed.dev.tc == 2 && opt.tsSplit && dScratch) ? 2 : 1;
 			done += chunk;

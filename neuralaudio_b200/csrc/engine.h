@@ -23,6 +23,7 @@ namespace nab200
 		int tsSplit = 0;        // TS kernel: 1 = one launch per layer array, the 8-channel one with 6 CTAs per SM (measured 5 % slower
 		                        // than the fused kernel: 144 + 90 us vs 208 us; kept as an option, its head sum is exact fp32)
 		int maxGridCtas = 0;    // 0: one CTA per SM
+		int useOne = 1;         // single-stream calls of small WaveNets on the one-CTA kernel (0: the batched kernels for every call)
 		int hCtas = 0;          // fp16-pair kernel: streams in flight per SM (0: the kernel's default, 5)
 		int lstmKernel = 0;     // LSTM kernel: 0 automatic, 1 gate rows in registers, 2 lane = stream (matrices in shared memory), 3 run-time-shaped
 	};

@@ -45,6 +45,9 @@ namespace nab200
 	};
 
 	cudaError_t wavenet_launch(const WnModelDev& M, const WnLaunch& a);
+	// single-stream path (one CTA owns the stream, whole ring state in shared memory): S == 1, n <= 128, small CUDA-core packings
+	bool wavenet_one_supported(const WnModelDev& M, size_t weightFloats);
+	cudaError_t wavenet_one_launch(const WnModelDev& M, const WnLaunch& a, size_t weightFloats);
 	// tcgen05 path with TMEM A operands (WnModelDev::tc == 2 packing), n <= 128
 	cudaError_t wavenet_ts_launch(const WnModelDev& M, const WnLaunch& a);
 	bool wavenet_ts_variant_supported(int C0, int C1, int act);

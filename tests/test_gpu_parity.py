@@ -212,6 +212,46 @@ def test_tma_and_plain_window_paths_are_bit_identical(na, tmp_path):
     assert np.array_equal(outs[0], outs[1])
 
 
+@pytest.mark.parametrize("name", ["syn_a1_nano.", "syn_a2_lite", "ref_BossWN_nano", "syn_dyn_single6_k2"])
+def test_single_stream_kernel_is_bit_identical_to_batched_kernel(na, name, tmp_path):
+    """A single-stream call of a small WaveNet runs on the one-CTA kernel (whole ring state in shared memory, wavenet_one_kernels.cu):
+    its results equal the batched kernel's bit for bit - for buffers of 1, 37 and 128 frames and for calls longer than one pass -
+    and a stream advanced partly by Process() and partly as slot 0 of ProcessBatch() stays consistent."""
+    files = golden_files(name)
+    if not files:
+        pytest.skip("no such vector")
+    g = load_golden(files[0])
+    mf = model_file_for(g, tmp_path)
+    if mf is None:
+        pytest.skip("fixture model not staged")
+    q = float(g.get("quality", 1.0))
+    x = np.random.default_rng(11).uniform(-1, 1, 128 * 7 + 37 + 1 + 300).astype(np.float32)
+    cuts = [0, 128, 256, 293, 294, 422, 722, 850, 978, 1106, x.size]
+    outs = {}
+    for one in (1, 0):
+        prev = na.set_option("use_one", one)
+        try:
+            m = _load(na, mf, q)
+            y = np.empty_like(x)
+            for a, b in zip(cuts[:-1], cuts[1:]):
+                y[a:b] = m.Process(np.ascontiguousarray(x[a:b]))
+            outs[one] = y
+        finally:
+            na.set_option("use_one", prev)
+    assert np.array_equal(outs[1], outs[0])
+    # mixed use: batch of 3 slots, slot 0 advanced alternately through Process() and ProcessBatch()
+    m = _load(na, mf, q, streams=3)
+    xb = np.random.default_rng(12).uniform(-1, 1, (4, 3, 128)).astype(np.float32)
+    ref = _load(na, mf, q, streams=3)
+    for c in range(4):
+        yb = np.empty_like(xb[c]); ref.ProcessBatch(xb[c], yb, 3, 128)
+        if c % 2 == 0:
+            y0 = m.Process(np.ascontiguousarray(xb[c, 0]))      # slot 0 only (slots 1, 2 of `m` fall behind: not compared)
+        else:
+            yy = np.empty_like(xb[c]); m.ProcessBatch(xb[c], yy, 3, 128); y0 = yy[0]
+        assert np.array_equal(y0, yb[0])
+
+
 @pytest.mark.parametrize("name", ["syn_a1_standard", "syn_lstm_1x16"])
 def test_pipelined_host_path_matches_blocking(na, name, tmp_path):
     """NA_ProcessBatchAsync (copy-in / kernels / copy-out of consecutive calls overlapped) is the same computation as the
