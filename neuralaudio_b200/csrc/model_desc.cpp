@@ -1124,6 +1124,36 @@ namespace nab200
 			// A2 head-conv scratch of the output stage (288 rows of plane 0): above the first layer's region and below the second
 			// layer's - the two regions the fetcher may be filling for the CTA's next stream while the output stage runs
 			M.headScratchRow = table[0].pad0;
+			// Which completions are anybody's dependency: only those are committed to the free / early barriers (two barriers
+			// each, used alternately), so that every committed phase is waited for - in commit order - and a wait names its
+			// completion by number.
+			std::vector<int> freeIdx(NL, -1), earlyIdx(NL, -1);
+			{
+				std::vector<char> wf(NL, 0), we(NL, 0);
+				for (int i = 0; i < NL; i++)
+				{
+#ifdef NAB_H_TOOLS
+					if (getenv("NAB_H_FAKE_R")) dep[i] = kHDepConv2;
+					if (getenv("NAB_H_DEP_LATE") && dep[i] != kHDepConv2) dep[i] = kHDepConv1;
+#endif
+					if (dep[i] == kHDepConv2) wf[(i - 2 + 2 * NL) % NL] = 1;
+					else if (dep[i] == kHDepConv1) wf[(i - 1 + NL) % NL] = 1;
+					else we[(i - 1 + NL) % NL] = 1;
+				}
+				int nf = 0, ne = 0;
+				for (int i = 0; i < NL; i++) { if (wf[i]) freeIdx[i] = nf++; if (we[i]) earlyIdx[i] = ne++; }
+				for (int i = 0; i < NL; i++)
+				{
+					HLayer& T = table[i];
+					T.numFree = nf; T.numEarly = ne;
+					T.commits = (wf[i] ? 1u : 0u) | (we[i] ? 2u : 0u);
+					const int back = dep[i] == kHDepConv2 ? 2 : 1;
+					const int tl = i - back;
+					const std::vector<int>& idx = dep[i] == kHDepEarly1 ? earlyIdx : freeIdx;
+					const int per = dep[i] == kHDepEarly1 ? ne : nf;
+					T.waitIdx = tl >= 0 ? idx[tl] : idx[(tl + 2 * NL) % NL] - per;
+				}
+			}
 			for (int i = 0; i < NL; i++)
 			{
 				HLayer& T = table[i];

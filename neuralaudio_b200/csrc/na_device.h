@@ -128,6 +128,7 @@ namespace nab200
 		uint32_t gBytes[3]; uint32_t tap0Base16;               // group 6: bytes of each sub-block; first delayed tap of group 0 inside sub-block 0
 		uint32_t histMask, iUnd16, iTap0Base16, iTapStride16;  // group 7 (issuer): bit j of histMask: delayed tap j reads only history (delay >= 128 frames) and is issued ahead of the hand-off; copies of und16 / tap0Base16 / tapStride16
 		int iNumTaps, iNumGroups, iGroupTaps; uint32_t winBytes;   // group 8 (issuer): copies of numTaps / numGroups / groupTaps; (fetcher) bytes of the layer's window copies: fixed part | per-frame part << 20
+		int waitIdx; uint32_t commits; int numFree, numEarly;  // group 9 (fetcher / issuer): which completion (number within the stream, negative: of the previous stream) this layer's copies wait for, of the kind flags & kHDepMask says; bit 0 / 1: this layer's conv / early products are somebody's dependency and commit to the free / early barriers; such commits per stream
 		uint32_t tapOff[kHMaxTaps];                            // byte offset (inside a plane) of frame 0's row of delayed tap j
 		HJob job[kHMaxJobs];
 	};

@@ -84,16 +84,13 @@ namespace nab200
 			uint32_t wbuf, wbufStride;    // two weight buffers
 			uint32_t tab;                 // HLayer table
 			int* hdb;                     // [2][kHdbHalf] ring heads of the current / next stream
-			uint32_t barW0, barD, barX;
-			uint32_t barL0;               // [2] fetcher -> issuer / stagers: history windows and first weight block of an even / odd layer have landed
-			uint32_t barFree0;            // [2] conv of an even / odd layer complete: its window region may be overwritten
-			uint32_t barG;                // issuer only: an intermediate tap group's products complete (a layer with tap groups)
-			uint32_t barEarly0;           // [2] early products of an even / odd layer complete: the rows only they read may be overwritten
+			uint32_t barW0;               // the mbarriers, 8 bytes apart: W0, W1, D, X, L0, L1, Free0, Free1, Early0, Early1, G
 			uint32_t r0, konst;           // TMEM: this stream's columns, the constant operand's
 			int n, tid, warp, S, gstride, numLayers;
 			bool el;
 			uint32_t wq, dq, xq, gq, sq, sqr; // weight-block counter; issuer: barD / barX / barG phase counters, sub-blocks awaited / requested (barW phases)
 			bool hasNext;                 // the CTA has another stream after this one
+			uint32_t fcq, ecq;            // issuer's elected lane: commits to the free / early barriers so far
 			uint32_t lq;                  // layers done by this thread since the kernel started (over all its streams): barWin / barFree phases
 			int cur;
 			int* err;
@@ -168,13 +165,13 @@ namespace nab200
 #ifdef NAB_H_DIRECT_WAIT   // experiment: the stagers wait on the commit barriers themselves (the issuer still releases nobody)
 		__device__ __forceinline__ void stager_wait_x(Ctx& cx)
 		{
-			if (!mbar_wait(cx.barX, cx.xq & 1u) && cx.tid == 0) *reinterpret_cast<volatile int*>(cx.err) = 1;
+			if (!mbar_wait((cx.barW0 + 24u), cx.xq & 1u) && cx.tid == 0) *reinterpret_cast<volatile int*>(cx.err) = 1;
 			cx.xq++;
 			fence_after();
 		}
 		__device__ __forceinline__ void stager_wait_d(Ctx& cx, int phases)
 		{
-			for (int i = 0; i < phases; i++) { if (!mbar_wait(cx.barD, cx.dq & 1u) && cx.tid == 0) *reinterpret_cast<volatile int*>(cx.err) = 1; cx.dq++; }
+			for (int i = 0; i < phases; i++) { if (!mbar_wait((cx.barW0 + 16u), cx.dq & 1u) && cx.tid == 0) *reinterpret_cast<volatile int*>(cx.err) = 1; cx.dq++; }
 			fence_after();
 		}
 #define STAGER_WAIT_X() stager_wait_x(cx)
@@ -270,6 +267,7 @@ namespace nab200
 			const int numRings = cx.M->numRings;
 			const size_t strideBytes = (size_t)cx.M->stateStride * 4;
 			uint32_t gl = 0;
+			int sk = 0;   // streams this CTA has finished
 			// ring heads of a stream: lane i holds rings i and 32 + i
 			int hA = 0, hB = 0;
 			if (s0 < cx.S)
@@ -312,13 +310,18 @@ namespace nab200
 						else if (sn < cx.S) prefetch_windows(cx, li + kAhead - cx.numLayers, sbase + (size_t)cx.gstride * strideBytes, hAn, hBn, lane);
 					}
 #endif
-					// the rows this layer's copies overwrite are free once ... (PackWaveNetH decides which)
-					const uint32_t dep = flags & kHDepMask;
-					const int c = (int)gl - (dep == kHDepConv2 ? 2 : 1);
-					const uint32_t depBar = (dep == kHDepEarly1 ? cx.barEarly0 : cx.barFree0) + 8u * ((uint32_t)c & 1u);
-					if (c >= 0 && !mbar_wait_relaxed(depBar, ((uint32_t)c >> 1) & 1u) && lane == 0) *reinterpret_cast<volatile int*>(cx.err) = 1;
+					// the rows this layer's copies overwrite are free once ... (PackWaveNetH decides which: the conv of the layer two
+					// back, the previous layer's early products or its conv - completion number `waitIdx` of that kind in this stream,
+					// negative for the previous stream's; the two barriers of a kind take the completions alternately)
+					{
+						const uint4 g9 = lds128(la + kTabHist + 32u);
+						const bool early = (flags & kHDepMask) == kHDepEarly1;
+						const int num = sk * (early ? (int)g9.w : (int)g9.z) + (int)g9.x;
+						if (num >= 0 && !mbar_wait_relaxed((early ? (cx.barW0 + 64u) : (cx.barW0 + 48u)) + 8u * ((uint32_t)num & 1u), ((uint32_t)num >> 1) & 1u) && lane == 0)
+							*reinterpret_cast<volatile int*>(cx.err) = 1;
+					}
 					H_STAMP(1);
-					const uint32_t bar = cx.barL0 + 8u * (gl & 1u);
+					const uint32_t bar = (cx.barW0 + 32u) + 8u * (gl & 1u);
 #ifndef NAB_H_NO_WINDOWS
 					// the copies complete on the barrier by bytes; lane 0's arrival carries the total (known from the plan)
 					if (lane == 0)
@@ -338,6 +341,7 @@ namespace nab200
 					H_STAMP(3);
 				}
 				hA = hAn; hB = hBn;
+				sk++;
 			}
 		}
 
@@ -470,7 +474,7 @@ namespace nab200
 					if (ng == 1)
 					{
 						const int nl = l + 1 < cx.numLayers ? l + 1 : (cx.hasNext ? 0 : -1);
-						if (nl >= 0) request_weights(cx, nl, 0, cx.wq + 1, cx.barL0 + 8u * ((cx.lq + 1u) & 1u));
+						if (nl >= 0) request_weights(cx, nl, 0, cx.wq + 1, (cx.barW0 + 32u) + 8u * ((cx.lq + 1u) & 1u));
 					}
 					cx.wq += (uint32_t)ng;
 				}
@@ -559,7 +563,7 @@ namespace nab200
 		template <int NT>
 		struct LayerPlan
 		{
-			uint32_t la, wb16, histMask;
+			uint32_t la, wb16, histMask, commits;
 			bool fast;
 			uint32_t convC, und, one[3];   // B descriptors: constant operand of the conv, undelayed tap, 1x1 (constant operand, W1, W2)
 			uint32_t tapA[NT], tapB[NT];   // delayed taps (unrolled path): window rows (h1 plane; h2 two planes on), weights
@@ -574,6 +578,7 @@ namespace nab200
 			const uint32_t o4 = NT > 4 ? lds32(la + kTabTaps + 16u) : 0u;
 			P.la = la;
 			P.histMask = g7.x;
+			P.commits = lds32(la + kTabHist + 36u);
 			P.fast = (int)g8.y == 1 && (int)g8.x == NT;
 			const uint32_t wb16 = (cx.wbuf + (block & 1u) * cx.wbufStride) >> 4;
 			P.wb16 = wb16;
@@ -607,20 +612,21 @@ namespace nab200
 					for (int j = 0; j < NT; j++)
 						if ((P.histMask >> j) & 1u) mma_pairs_ss<C>(MP::d(cx), P.tapA[j], 2u * (cx.planeStride >> 4), P.tapB[j]);
 				}
-				mma_commit(cx.barEarly0 + 8u * (lq & 1u));   // the window rows only these products read may be overwritten once they complete
+				// the window rows only these products read may be overwritten once they complete: committed where a later layer's copies go there
+				if (P.commits & 2u) { mma_commit((cx.barW0 + 64u) + 8u * (cx.ecq & 1u)); cx.ecq++; }
 			}
 			__syncwarp();
 		}
 		__device__ __forceinline__ void wait_layer(Ctx& cx, uint32_t lq)
 		{
-			issuer_wait(cx, cx.barL0 + 8u * (lq & 1u), (lq >> 1) & 1u);   // the bulk copies of the layer's windows (fetcher) and first weight block
+			issuer_wait(cx, (cx.barW0 + 32u) + 8u * (lq & 1u), (lq >> 1) & 1u);   // the bulk copies of the layer's windows (fetcher) and first weight block
 		}
 		// the same, without waiting: have they landed?  (Where a layer's window rows become free only a layer ahead - the largest
 		// layers of A2 - the copies can still be in flight when the issuer would issue the early products: it then goes on, and
 		// issues them behind the hand-off, in front of the other taps, instead of stalling the stagers' release.)
 		__device__ __forceinline__ bool layer_landed(const Ctx& cx, uint32_t lq)
 		{
-			return __shfl_sync(0xffffffffu, mbar_test(cx.barL0 + 8u * (lq & 1u), (lq >> 1) & 1u) ? 1 : 0, 0) != 0;
+			return __shfl_sync(0xffffffffu, mbar_test((cx.barW0 + 32u) + 8u * (lq & 1u), (lq >> 1) & 1u) ? 1 : 0, 0) != 0;
 		}
 
 		template <int ROLE, int HV>
@@ -630,7 +636,7 @@ namespace nab200
 			constexpr int C = MP::C, N1 = MP::N1;
 			constexpr int NT = ROLE == 2 ? 5 : 2;   // the delayed-tap count with an unrolled path (K = 6 / K = 3)
 			const uint32_t idN1 = idesc_f16(N1);
-			LayerPlan<NT> P, Q;
+			LayerPlan<NT> P;
 			plan_layer<C, N1, NT>(cx, firstLayer, cx.wq, P);
 			wait_layer(cx, cx.lq);
 			early_products<ROLE, NT>(cx, P, cx.lq);
@@ -661,12 +667,12 @@ namespace nab200
 #pragma unroll
 						for (int j = 0; j < NT; j++)
 							if (!((P.histMask >> j) & 1u)) mma_pairs_ss<C>(MP::d(cx), P.tapA[j], 2u * (cx.planeStride >> 4), P.tapB[j]);
-						mma_commit(cx.barD);
-						mma_commit(cx.barFree0 + 8u * (cx.lq & 1u));
+						mma_commit((cx.barW0 + 16u));
+						if (P.commits & 1u) { mma_commit((cx.barW0 + 48u) + 8u * (cx.fcq & 1u)); cx.fcq++; }
 					}
 					__syncwarp();
 					H_STAMP(5);
-					ISSUER_RELEASE(kBarDReady, cx.barD, cx.dq & 1u);
+					ISSUER_RELEASE(kBarDReady, (cx.barW0 + 16u), cx.dq & 1u);
 					cx.dq++;
 				}
 				else
@@ -702,8 +708,8 @@ namespace nab200
 							}
 							// an intermediate group completes on its own barrier (one completion outstanding at a time: a parity wait
 							// cannot tell one completed phase from three), the last one on the conv's
-							if (jn < numTaps) mma_commit(cx.barG);
-							else { mma_commit(cx.barD); mma_commit(cx.barFree0 + 8u * (cx.lq & 1u)); }
+							if (jn < numTaps) mma_commit((cx.barW0 + 80u));
+							else { mma_commit((cx.barW0 + 16u)); if (P.commits & 1u) { mma_commit((cx.barW0 + 48u) + 8u * (cx.fcq & 1u)); cx.fcq++; } }
 						}
 						__syncwarp();
 						if (jn < numTaps)
@@ -714,7 +720,7 @@ namespace nab200
 #endif
 							if (g + 2 < numGroups)
 							{
-								issuer_wait(cx, cx.barG, cx.gq & 1u);
+								issuer_wait(cx, (cx.barW0 + 80u), cx.gq & 1u);
 								cx.gq++; waited++;
 								if (cx.el) request_weights(cx, l, g + 2, cx.wq + 2, cx.barW0 + 8u * ((cx.sq + 1u) & 1u));
 								__syncwarp();
@@ -722,22 +728,20 @@ namespace nab200
 							cx.wq++;
 						}
 					}
-					for (; waited < numGroups - 1; waited++) { issuer_wait(cx, cx.barG, cx.gq & 1u); cx.gq++; }
+					for (; waited < numGroups - 1; waited++) { issuer_wait(cx, (cx.barW0 + 80u), cx.gq & 1u); cx.gq++; }
 					if (cx.el && numGroups > 1)   // (behind a single group the stagers have asked already)
 					{
 						const int nl = l + 1 < cx.numLayers ? l + 1 : (cx.hasNext ? 0 : -1);
-						if (nl >= 0) request_weights(cx, nl, 0, cx.wq + 1, cx.barL0 + 8u * ((cx.lq + 1u) & 1u));
+						if (nl >= 0) request_weights(cx, nl, 0, cx.wq + 1, (cx.barW0 + 32u) + 8u * ((cx.lq + 1u) & 1u));
 					}
 					__syncwarp();
-					ISSUER_RELEASE(kBarDReady, cx.barD, cx.dq & 1u);
+					ISSUER_RELEASE(kBarDReady, (cx.barW0 + 16u), cx.dq & 1u);
 					cx.dq++;
 					// the 1x1 operands sit in the layer's last sub-block
 					P.one[0] = desc_lo(wb16 + g3.w, N1); P.one[1] = desc_lo(wb16 + g3.y, N1); P.one[2] = desc_lo(wb16 + g3.z, N1);
 				}
 				cx.lq++;
 				H_STAMP(6);
-				// idle while the stagers run the activation: the next layer's plan, and its windows / weights (landed long ago as a rule)
-				if (hasNext) plan_layer<C, N1, NT>(cx, l + 1, cx.wq + 1, Q);
 
 				// ---- 1x1 + bias + residual, head sum (WaveNet.h:482-491): XR | HD += [z] [W1x1 | Whead] ----
 				issuer_sync<kBarZ, HV>();
@@ -756,24 +760,24 @@ namespace nab200
 						mma_f16_ts<1>(MP::xr(cx), MP::t2(cx), desc_of(P.one[1]), idN1);
 						mma_f16_ts<1>(MP::xr(cx), MP::t2(cx), desc_of(P.one[2]), idN1);
 					}
-					mma_commit(cx.barX);
+					mma_commit((cx.barW0 + 24u));
 				}
 				__syncwarp();
 				H_STAMP(8);
-				// behind the 1x1, in the shadow of its completion: the next layer's input-independent products (the conv accumulator
-				// is free: the stagers have read it); the tensor pipe runs them while the stagers pack
+				// in the shadow of the 1x1's completion: the next layer's plan (one plan at a time: two of them spill registers on
+				// the issuer's critical sections)
+				if (hasNext) plan_layer<C, N1, NT>(cx, l + 1, cx.wq + 1, P);
 				// release the stagers first (they pack the next layer's input), then - while they pack - the next layer's
 				// input-independent products (the conv accumulator is free: the stagers have read it)
-				ISSUER_RELEASE(kBarXReady, cx.barX, cx.xq & 1u);
+				ISSUER_RELEASE(kBarXReady, (cx.barW0 + 24u), cx.xq & 1u);
 				H_STAMP(9);
 				cx.xq++;
 				cx.wq++;
 				if (hasNext)
 				{
-					if (layer_landed(cx, cx.lq)) early_products<ROLE, NT>(cx, Q, cx.lq);
+					if (layer_landed(cx, cx.lq)) early_products<ROLE, NT>(cx, P, cx.lq);
 					else deferred = true;
 				}
-				P = Q;
 			}
 		}
 
@@ -807,19 +811,13 @@ namespace nab200
 			uint32_t* tmemSlot = reinterpret_cast<uint32_t*>(bars + kNumBars);
 			float* headHist = reinterpret_cast<float*>(tmemSlot + 4);   // ARCH 1: this stream's head history [tap][16]
 			cx.barW0 = smem_u32(&bars[0]);
-			cx.barD = smem_u32(&bars[2]);
-			cx.barX = smem_u32(&bars[3]);
-			cx.barL0 = smem_u32(&bars[4]);
-			cx.barFree0 = smem_u32(&bars[6]);
-			cx.barEarly0 = smem_u32(&bars[8]);
-			cx.barG = smem_u32(&bars[10]);
 			cx.n = n;
 			cx.tid = threadIdx.x;
 			cx.warp = threadIdx.x >> 5;
 			cx.S = S;
 			cx.gstride = gridDim.x;
 			cx.numLayers = M.numLayers;
-			cx.wq = 0; cx.dq = 0; cx.xq = 0; cx.gq = 0; cx.sq = 0; cx.sqr = 0; cx.lq = 0; cx.cur = 0; cx.hasNext = false;
+			cx.wq = 0; cx.dq = 0; cx.xq = 0; cx.gq = 0; cx.sq = 0; cx.sqr = 0; cx.lq = 0; cx.fcq = 0; cx.ecq = 0; cx.cur = 0; cx.hasNext = false;
 			cx.el = elect_one();
 			const int tid = threadIdx.x, warp = cx.warp;
 			const int first0 = M.arrays[0].firstLayer, num0 = M.arrays[0].numLayers;
@@ -875,23 +873,23 @@ namespace nab200
 					H_STAMP_SELECT(s, s0);
 					cx.hasNext = s + (int)gridDim.x < S;
 					// ---- entry: [XR | HD] = constant operand x [rechannel 1 -> C0 | head bias] (WaveNet.h:637) ----
-					issuer_wait(cx, cx.barL0 + 8u * (cx.lq & 1u), (cx.lq >> 1) & 1u);   // the first layer's block carries the entry operand
+					issuer_wait(cx, (cx.barW0 + 32u) + 8u * (cx.lq & 1u), (cx.lq >> 1) & 1u);   // the first layer's block carries the entry operand
 					issuer_sync<kBarE, HV>();
 					if (cx.el)
 					{
 						const uint32_t wb16 = (cx.wbuf + (cx.wq & 1u) * cx.wbufStride) >> 4;
 						mma_f16_ts<0>(Map<ARCH == 0 ? 0 : 2>::xr(cx), konst(cx), desc_at(wb16 + ent0, 24), idesc_f16(24));
-						mma_commit(cx.barX);
+						mma_commit((cx.barW0 + 24u));
 					}
 					__syncwarp();
-					ISSUER_RELEASE(kBarXReady, cx.barX, cx.xq & 1u);
+					ISSUER_RELEASE(kBarXReady, (cx.barW0 + 24u), cx.xq & 1u);
 					cx.xq++;
 					if constexpr (ARCH == 0)
 					{
 						issue_array<0, HV>(cx, first0, num0);
 
 						// ---- array transition (WaveNet.h:785-789): [XR1 | HD1] = rechannel C0 -> C1 of the array output | head carry ----
-						issuer_wait(cx, cx.barL0 + 8u * (cx.lq & 1u), (cx.lq >> 1) & 1u);   // the second array's first block carries the transition operands
+						issuer_wait(cx, (cx.barW0 + 32u) + 8u * (cx.lq & 1u), (cx.lq >> 1) & 1u);   // the second array's first block carries the transition operands
 						issuer_sync<kBarE, HV>();
 						if (cx.el)
 						{
@@ -903,11 +901,11 @@ namespace nab200
 							mma_f16_ts<1>(acc, cx.r0 + 16u, desc_at(e + 64u, 16), id);    // [0 | Wc1 ; Wc1] x [h1 | h2] of the head output
 							mma_f16_ts<1>(acc, cx.r0 + 16u, desc_at(e + 96u, 16), id);    // [0 | Wc2 ; 0]
 							mma_f16_ts<1>(acc, konst(cx), desc_at(e + 128u, 16), id);     // [0 | head bias]
-							mma_commit(cx.barX);
+							mma_commit((cx.barW0 + 24u));
 						}
 						__syncwarp();
 						// (the second array's conv accumulator reuses columns the transition products read: they have completed)
-						ISSUER_RELEASE(kBarXReady, cx.barX, cx.xq & 1u);
+						ISSUER_RELEASE(kBarXReady, (cx.barW0 + 24u), cx.xq & 1u);
 						cx.xq++;
 						issue_array<1, HV>(cx, first1, num1);
 					}
@@ -924,7 +922,7 @@ namespace nab200
 				if (hv == 0 && t < n && s0 < S) cond = in[(long long)s0 * inSS + (long long)t * inFS];
 				const size_t strideBytes = (size_t)M.stateStride * 4;
 				cx.sbase = reinterpret_cast<char*>(state) + (size_t)s0 * strideBytes;
-				if (tid == kWeightThread && s0 < S) request_weights(cx, 0, 0, 0, cx.barL0);
+				if (tid == kWeightThread && s0 < S) request_weights(cx, 0, 0, 0, (cx.barW0 + 32u));
 				for (int s = s0; s < S; s += gridDim.x)
 				{
 					const int sn = s + gridDim.x;
