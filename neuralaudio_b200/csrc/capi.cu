@@ -581,7 +581,7 @@ int NA_DescribeModelFile(const wchar_t* modelPath, int externalSampleRate, char*
 					nab200::PackedLstm p = nab200::PackLstm(d);
 					os << "{\"kind\":\"lstm\",\"static\":" << (d.isStatic ? "true" : "false") << ",\"layers\":" << d.numLayers << ",\"hidden\":" << d.hiddenSize
 					   << ",\"lanes\":" << p.dev.G << ",\"packed_floats\":" << p.weights.size() << ",\"state_floats\":" << p.dev.stateStride
-					   << ",\"kernel\":\"" << nab200::lstm_kernel_name(p.dev) << "\"}";
+					   << ",\"kernel\":\"" << nab200::lstm_kernel_name(p.dev, 8192) << "\",\"kernel_32768_streams\":\"" << nab200::lstm_kernel_name(p.dev, 32768) << "\"}";
 					return;
 				}
 				throw std::runtime_error("unsupported model: architecture '" + arch + "'");
@@ -590,7 +590,7 @@ int NA_DescribeModelFile(const wchar_t* modelPath, int externalSampleRate, char*
 			nab200::PackedLstm p = nab200::PackLstm(d);
 			os << "{\"kind\":\"lstm\",\"static\":" << (d.isStatic ? "true" : "false") << ",\"layers\":" << d.numLayers << ",\"hidden\":" << d.hiddenSize
 			   << ",\"lanes\":" << p.dev.G << ",\"packed_floats\":" << p.weights.size() << ",\"state_floats\":" << p.dev.stateStride
-					   << ",\"kernel\":\"" << nab200::lstm_kernel_name(p.dev) << "\"}";
+					   << ",\"kernel\":\"" << nab200::lstm_kernel_name(p.dev, 8192) << "\",\"kernel_32768_streams\":\"" << nab200::lstm_kernel_name(p.dev, 32768) << "\"}";
 		};
 		if (ext == ".nam" && j.at("architecture").as_string() == "SlimmableContainer")
 		{

@@ -24,6 +24,7 @@ namespace nab200
 			env("NAB200_USE_TMA", v.useTma);
 			env("NAB200_MAX_GRID_CTAS", v.maxGridCtas);
 			env("NAB200_LSTM_KERNEL", v.lstmKernel);
+			env("NAB200_LSTM_TC_ROWS", v.lstmTcRows);
 			return v;
 		}();
 		return o;
@@ -41,6 +42,7 @@ namespace nab200
 		else if (strcmp(name, "use_one") == 0) { prev = o.useOne; o.useOne = value; }
 		else if (strcmp(name, "max_grid_ctas") == 0) { prev = o.maxGridCtas; o.maxGridCtas = value; }
 		else if (strcmp(name, "lstm_kernel") == 0) { prev = o.lstmKernel; o.lstmKernel = value; }
+		else if (strcmp(name, "lstm_tc_rows") == 0) { prev = o.lstmTcRows; o.lstmTcRows = value; }
 		return prev;
 	}
 
@@ -683,7 +685,9 @@ namespace nab200
 		a.zeroInput = true;
 		a.generic = opt.useTc < 0;
 		a.kernel = opt.lstmKernel;
+		a.tcRows = opt.lstmTcRows;
 		a.numSMs = numSMs;
+		a.pickS = (int)numStreams;   // the template advances under the arithmetic its slots will run
 		a.stream = stream;
 		a.state = dBlob + weightFloats;
 		a.S = 1;
@@ -709,7 +713,9 @@ namespace nab200
 		a.zeroInput = false;
 		a.generic = opt.useTc < 0;
 		a.kernel = opt.lstmKernel;
+		a.tcRows = opt.lstmTcRows;
 		a.numSMs = numSMs;
+		a.pickS = (int)numStreams;
 		a.stream = stream;
 		if (!CudaOk(lstm_launch(packed.dev, a), "lstm_fwd_kernel launch")) return false;
 		kernelLaunches++;

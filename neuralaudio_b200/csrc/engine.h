@@ -25,7 +25,8 @@ namespace nab200
 		int maxGridCtas = 0;    // 0: one CTA per SM
 		int useOne = 1;         // single-stream calls of small WaveNets on the one-CTA kernel (0: the batched kernels for every call)
 		int hCtas = 0;          // fp16-pair kernel: streams in flight per SM (0: the kernel's default, 5)
-		int lstmKernel = 0;     // LSTM kernel: 0 automatic, 1 gate rows in registers, 2 lane = stream (matrices in shared memory), 3 run-time-shaped
+		int lstmKernel = 0;     // LSTM kernel: 0 automatic, 1 gate rows in registers, 2 lane = stream (matrices in shared memory), 3 run-time-shaped, 4 tensor cores
+		int lstmTcRows = 0;     // tensor-core LSTM kernel: streams per CTA, 64 or 128 (0: by batch size)
 	};
 	Options& GetOptions();
 	int SetOption(const char* name, int value);                       // the process-wide defaults (what a new loader starts from)

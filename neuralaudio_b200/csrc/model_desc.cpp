@@ -1239,6 +1239,13 @@ namespace nab200
 		P.weights.resize(P.weights.size() + G + 4, 0.0f);
 		for (int u = 0; u < H; u++) P.weights[M.headOff + u] = desc.headW[u];
 		P.weights[M.headOff + G] = desc.headB;
+		// the tensor-core kernel holds the gate matrices and h as fp16 pairs: finite and inside the fp16 range, or it is not offered
+		M.tcOk = 1;
+		for (int i = 0; i < M.headOff; i++)
+			if (!(std::fabs(P.weights[i]) < 32768.0f)) M.tcOk = 0;
+		for (int l = 0; l < M.L; l++)
+			for (int u = 0; u < G; u++)
+				if (!(std::fabs(P.initState[(2 * l) * G + u]) < 32768.0f)) M.tcOk = 0;
 		return P;
 	}
 }

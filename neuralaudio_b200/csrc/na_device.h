@@ -147,5 +147,6 @@ namespace nab200
 		int bOff[kMaxLstmLayers];
 		int headOff;       // headW[G] then headB
 		int stateStride;   // floats per stream = L * 2 * G
+		int tcOk;          // every gate weight, bias and initial h fits the fp16-pair operands of the tensor-core kernel (|v| < 2^15)
 	};
 }

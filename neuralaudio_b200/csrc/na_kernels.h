@@ -77,12 +77,17 @@ namespace nab200
 		int n;
 		bool zeroInput;         // ignore `in`, feed zeros (prewarm)
 		bool generic;           // force the run-time-shaped kernel (use_tc = -1)
-		int kernel;             // 0 automatic, 1 gate rows in registers, 2 lane = stream with shared-memory matrices, 3 run-time-shaped
+		int kernel;             // 0 automatic, 1 gate rows in registers, 2 lane = stream with shared-memory matrices, 3 run-time-shaped, 4 tensor cores (tcgen05)
 		int numSMs;
+		int tcRows;             // tensor-core kernel: streams per CTA, 64 or 128 (0: 64 while that is at most one CTA per SM)
+		int pickS;              // streams the automatic kernel choice is made for (the model's slot count; 0: S)
 		cudaStream_t stream;
 	};
 
 	cudaError_t lstm_launch(const LstmModelDev& M, const LstmLaunch& a);
 	bool lstm_variant_supported(int L, int G);
-	const char* lstm_kernel_name(const LstmModelDev& M);   // the kernel the automatic choice runs for this shape
+	const char* lstm_kernel_name(const LstmModelDev& M, int S);   // the kernel the automatic choice runs for this shape on a model of S stream slots
+	// tcgen05 path (lstm_tc_kernels.cu): gates as one small GEMM per step for 128 streams, fp16-pair operands; 1 or 2 layers, <= 32 units
+	bool lstm_tc_supported(const LstmModelDev& M);
+	cudaError_t lstm_tc_launch(const LstmModelDev& M, const LstmLaunch& a);
 }

@@ -205,12 +205,31 @@ def test_cpp_consumer_builds_links_and_fails_loudly_without_gpu(tmp_path):
 
 
 def test_lstm_kernel_choice_by_shape(na, tmp_path):
-    """Host logic of the LSTM dispatch: gate rows in registers where they fit (up to 16 units in one layer, 8 in two), the
-    lane-per-stream kernel with shared-memory matrices past that register cliff and for run-time sizes."""
-    want = {"syn_lstm_1x16": "lstm_gate_rows_in_registers", "syn_lstm_2x8": "lstm_gate_rows_in_registers",
-            "syn_lstm_1x24": "lstm_lane_per_stream", "syn_lstm_2x12": "lstm_lane_per_stream",
-            "syn_dyn_lstm_3x18": "lstm_lane_per_stream", "syn_dyn_lstm_1x40": "lstm_lane_per_stream", "syn_dyn_lstm_4x6": "lstm_lane_per_stream"}
-    for name, kernel in want.items():
+    """Host logic of the LSTM dispatch (reported for a model of 8192 stream slots, and of 32768): gate rows in registers where they
+    fit (up to 16 units in one layer, 8 in two) until the batch is large enough for the tensor-core kernel's fixed step chain to pay;
+    past that register cliff the tensor-core kernel (one or two layers, up to 32 units) from ~6000 streams, the lane-per-stream
+    kernel with shared-memory matrices for everything else (three or more layers, more than 32 units)."""
+    want = {"syn_lstm_1x16": ("lstm_gate_rows_in_registers", "lstm_tcgen05_gates"), "syn_lstm_2x8": ("lstm_gate_rows_in_registers", "lstm_tcgen05_gates"),
+            "syn_lstm_1x8": ("lstm_gate_rows_in_registers", "lstm_gate_rows_in_registers"),
+            "syn_lstm_1x24": ("lstm_tcgen05_gates", "lstm_tcgen05_gates"), "syn_lstm_2x12": ("lstm_tcgen05_gates", "lstm_tcgen05_gates"),
+            "syn_dyn_lstm_2x32": ("lstm_tcgen05_gates", "lstm_tcgen05_gates"),
+            "syn_dyn_lstm_3x18": ("lstm_lane_per_stream",) * 2, "syn_dyn_lstm_1x40": ("lstm_lane_per_stream",) * 2, "syn_dyn_lstm_4x6": ("lstm_lane_per_stream",) * 2}
+    for name, (kernel, kernel_large) in want.items():
         g = load_golden(golden_files(name)[0])
         d = na.describe_model_file(model_file_for(g, tmp_path))
         assert d["kernel"] == kernel, (name, d["kernel"])
+        assert d["kernel_32768_streams"] == kernel_large, (name, d["kernel_32768_streams"])
+
+
+def test_lstm_tensor_core_kernel_refuses_weights_outside_fp16_range(na, tmp_path):
+    """The tensor-core LSTM kernel holds the gate matrices as fp16 pairs: a model with a weight beyond the fp16 range keeps the
+    fp32 CUDA-core kernels at every batch size (PackLstm's tcOk)."""
+    import json
+    g = load_golden(golden_files("syn_lstm_1x24")[0])
+    w = np.asarray(g["weights"], dtype=np.float32).copy()
+    w[5] = 1.0e6
+    d = dict(g["model"]); d["weights"] = [float(v) for v in w]
+    mf = os.path.join(str(tmp_path), "huge_weight.nam")
+    with open(mf, "w") as f:
+        json.dump(d, f)
+    assert na.describe_model_file(mf)["kernel_32768_streams"] == "lstm_lane_per_stream"
