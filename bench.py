@@ -382,7 +382,7 @@ def measure(na, torch, dist, dev, rank, world, workload, path, streams, frames, 
                        "out and the host reads each result; consecutive steps are pipelined (two in flight)",
                 "blocking_value": total_units * steps / (e2e_blocking_ms * 1e-3),
                 "blocking_ms_per_step": e2e_blocking_ms / steps,
-                "blocking_api": "NA_ProcessBatch with pinned host pointers (the call returns with the output complete)"},
+                "blocking_api": "NA_ProcessBatch with pinned host pointers (the call returns with the output complete; the kernels read and write the page-locked buffers directly)"},
         "parity": parity,
         "gpu_launches": int(launches),
     }

@@ -24,7 +24,8 @@ namespace nab200
 			env("NAB200_USE_TMA", v.useTma);
 			env("NAB200_MAX_GRID_CTAS", v.maxGridCtas);
 			env("NAB200_LSTM_KERNEL", v.lstmKernel);
-			env("NAB200_LSTM_TC_ROWS", v.lstmTcRows);
+			env("NAB200_ASYNC_ZERO_COPY", v.asyncZeroCopy);
+			env("NAB200_ZERO_COPY_KFLOATS", v.zeroCopyKFloats);
 			return v;
 		}();
 		return o;
@@ -42,7 +43,8 @@ namespace nab200
 		else if (strcmp(name, "use_one") == 0) { prev = o.useOne; o.useOne = value; }
 		else if (strcmp(name, "max_grid_ctas") == 0) { prev = o.maxGridCtas; o.maxGridCtas = value; }
 		else if (strcmp(name, "lstm_kernel") == 0) { prev = o.lstmKernel; o.lstmKernel = value; }
-		else if (strcmp(name, "lstm_tc_rows") == 0) { prev = o.lstmTcRows; o.lstmTcRows = value; }
+		else if (strcmp(name, "async_zero_copy") == 0) { prev = o.asyncZeroCopy; o.asyncZeroCopy = value; }
+		else if (strcmp(name, "zero_copy_kfloats") == 0) { prev = o.zeroCopyKFloats; o.zeroCopyKFloats = value; }
 		return prev;
 	}
 
@@ -191,7 +193,6 @@ namespace nab200
 
 	// host calls up to this size skip the staging copies: the kernel reads the page-locked input and writes the page-locked
 	// output through their device aliases (unified addressing), which removes two DMA operations from a latency-bound call
-	constexpr size_t kZeroCopyFloats = 16384;
 
 	bool StreamEngine::Process(const float* in, float* out, size_t S, size_t n, int layout)
 	{
@@ -224,7 +225,7 @@ namespace nab200
 		const size_t total = S * n;
 		if (!EnsureStaging(total)) return false;
 		const bool inPinned = inKind == kPinned && inAlias != nullptr, outPinned = outKind == kPinned && outAlias != nullptr;
-		if (total <= kZeroCopyFloats)
+		if (total <= (size_t)opt.zeroCopyKFloats * 1024)
 		{
 			// small call: one kernel pass over page-locked memory, no staging DMA
 			const float* src = inPinned ? static_cast<const float*>(inAlias) : pinnedIn;
@@ -351,13 +352,16 @@ namespace nab200
 		if (!guard.ok) return false;
 		const bool inDev = IsDevicePointer(in), outDev = IsDevicePointer(out);
 		if (inDev || outDev) return Process(in, out, S, n, layout);   // device pointers are already asynchronous
-		if (!IsPinnedHost(in) || !IsPinnedHost(out))
+		void* inAlias = nullptr;
+		void* outAlias = nullptr;
+		if (Classify(in, &inAlias) != kPinned || Classify(out, &outAlias) != kPinned)
 		{
 			SetLastError("ProcessBatchAsync: host buffers must be page-locked (cudaHostAlloc / cudaHostRegister); use ProcessBatch for pageable memory");
 			return false;
 		}
 		const size_t total = S * n;
-		if (!EnsurePipeline(total)) return false;
+		const bool zeroCopy = opt.asyncZeroCopy != 0 && inAlias != nullptr && outAlias != nullptr;
+		if (!EnsurePipeline(zeroCopy ? 0 : total)) return false;
 		const int slot = (int)(asyncSeq & 1ull);
 		// the slot's previous user (two calls ago) must have finished its copy-out
 		if (asyncSeq >= 2 && asyncWaited + 2 <= asyncSeq)
@@ -367,6 +371,15 @@ namespace nab200
 		}
 		const long long SS = layout == 0 ? (long long)n : 1;
 		const long long FS = layout == 0 ? 1 : (long long)S;
+		if (zeroCopy)
+		{
+			// the kernels read the input and write the output over PCIe themselves: a sample crosses the bus once each way, inside the
+			// kernel that consumes / produces it, and consecutive calls simply queue on the model's stream
+			if (!ProcessDevice(static_cast<const float*>(inAlias), static_cast<float*>(outAlias), SS, FS, SS, FS, S, n)) return false;
+			if (!CudaOk(cudaEventRecord(evDone[slot], stream), "cudaEventRecord")) return false;
+			asyncSeq++;
+			return true;
+		}
 		if (!CudaOk(cudaMemcpyAsync(slotIn[slot], in, total * 4, cudaMemcpyHostToDevice, h2dStream), "cudaMemcpyAsync(H2D)")) return false;
 		if (!CudaOk(cudaEventRecord(evIn[slot], h2dStream), "cudaEventRecord")) return false;
 		if (!CudaOk(cudaStreamWaitEvent(stream, evIn[slot], 0), "cudaStreamWaitEvent")) return false;
@@ -685,7 +698,6 @@ namespace nab200
 		a.zeroInput = true;
 		a.generic = opt.useTc < 0;
 		a.kernel = opt.lstmKernel;
-		a.tcRows = opt.lstmTcRows;
 		a.numSMs = numSMs;
 		a.pickS = (int)numStreams;   // the template advances under the arithmetic its slots will run
 		a.stream = stream;
@@ -713,7 +725,6 @@ namespace nab200
 		a.zeroInput = false;
 		a.generic = opt.useTc < 0;
 		a.kernel = opt.lstmKernel;
-		a.tcRows = opt.lstmTcRows;
 		a.numSMs = numSMs;
 		a.pickS = (int)numStreams;
 		a.stream = stream;

@@ -25,8 +25,15 @@ namespace nab200
 		int maxGridCtas = 0;    // 0: one CTA per SM
 		int useOne = 1;         // single-stream calls of small WaveNets on the one-CTA kernel (0: the batched kernels for every call)
 		int hCtas = 0;          // fp16-pair kernel: streams in flight per SM (0: the kernel's default, 5)
+		// blocking host calls of up to this many thousand samples run on the caller's page-locked buffers directly: one launch whose
+		// kernels read the input and write the output over PCIe themselves (measured against the sliced copy-engine pipeline, blocking
+		// calls on page-locked buffers: A1 Standard 4096x128 311 -> 266 us, LSTM 8192x128 423 -> 207 us, A2 Full 754 -> 530 us)
+		int zeroCopyKFloats = 1 << 20;
+		// ProcessBatchAsync: 1 = the same zero-copy form; 0 = staged through device slots by the copy engines, overlapped with the
+		// kernels of the neighbouring calls (the default: the staged pipeline runs the kernels at their device-resident speed, which
+		// wins once calls are queued back to back: A1 Standard 2.65 vs 2.14 Gsamples/s; only A1 Nano gains from zero-copy, 3.5 vs 2.8)
+		int asyncZeroCopy = 0;
 		int lstmKernel = 0;     // LSTM kernel: 0 automatic, 1 gate rows in registers, 2 lane = stream (matrices in shared memory), 3 run-time-shaped, 4 tensor cores
-		int lstmTcRows = 0;     // tensor-core LSTM kernel: streams per CTA, 64 or 128 (0: by batch size)
 	};
 	Options& GetOptions();
 	int SetOption(const char* name, int value);                       // the process-wide defaults (what a new loader starts from)

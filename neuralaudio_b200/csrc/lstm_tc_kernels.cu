@@ -38,17 +38,17 @@ namespace nab200
 	constexpr uint32_t kTcGroupBytes = kTcM * 16;      // one k group (8 halves per row) of the A operand
 	constexpr float kTcInputClamp = 60000.0f;             // fp16 range of the input sample's pair (audio is |x| <= 1)
 
-	// Q = TMEM lane quarters in use: 4 (128 streams per CTA) or 2 (64 streams per CTA, for batches that would otherwise leave SMs
-	// without a CTA: the warps of quarters 2 and 3 cannot reach lanes 0..63, so they idle and one of them is the issuer)
-	template <int UPT, int NWG, int L, int Q>
+	// (A CTA of 64 streams -- TMEM lane quarters 0 and 1 only -- was measured for batches that leave SMs without a CTA: no gain.  A warp
+	// reaches only the lane quarter of its own scheduler, so half the SM's fp32 pipes would sit idle, and those pipes are the bound.)
+	template <int UPT, int NWG, int L>
 	struct TcCfg
 	{
 		static constexpr int Ut = UPT * NWG;              // hidden units, padded
 		static constexpr int N = 4 * Ut;                  // gate columns of one layer
-		static constexpr int kRows = 32 * Q;              // streams per CTA
-		static constexpr int kWorkers = 32 * Q * NWG;
-		static constexpr int kThreads = Q == 4 ? 128 * NWG + 32 : 128 * NWG;
-		static constexpr int kIssuerWarp = Q == 4 ? 4 * NWG : 2;
+		static constexpr int kRows = 128;                 // streams per CTA
+		static constexpr int kWorkers = 128 * NWG;
+		static constexpr int kThreads = kWorkers + 32;
+		static constexpr int kIssuerWarp = 4 * NWG;
 		static constexpr int kIssueBar = kWorkers + 32;     // threads on the workers -> issuer barrier
 		__host__ __device__ static constexpr int ks(int l) { return 1 + (l + 1) * Ut / 8; }      // K steps of layer l: [x, 1 | h_0 .. h_l]
 		static constexpr uint32_t kABytes = 2u * ks(L - 1) * kTcGroupBytes;
@@ -57,11 +57,14 @@ namespace nab200
 		static constexpr uint32_t kB0 = kABytes;
 		static constexpr uint32_t kB1 = kB0 + bBytes(0);
 		static constexpr uint32_t kTin = kB1 + (L == 2 ? bBytes(1) : 0u);     // [2][tile][128] floats
-		static constexpr uint32_t kTprod = kTin + 2u * kTcTile * kRows * 4u;   // [tile][NWG][128] floats
-		static constexpr uint32_t kBars = kTprod + (uint32_t)kTcTile * NWG * kRows * 4u;
+		// frame strides of the staged tiles, odd in banks: the tile is written stream-major by the steps and read frame-major by a
+		// [stream][frame] batch's coalesced copies (and the other way round), both conflict-free
+		static constexpr int kTinStride = kRows + 1, kTprodStride = NWG * kRows + 1;
+		static constexpr uint32_t kTprod = kTin + 2u * kTcTile * kTinStride * 4u;   // [tile][NWG][128] floats
+		static constexpr uint32_t kBars = ((kTprod + (uint32_t)kTcTile * kTprodStride * 4u + 15u) & ~15u);
 		static constexpr uint32_t kSmem = kBars + 64u;
 		static constexpr int kTmemCols = L * N <= 32 ? 32 : L * N <= 64 ? 64 : L * N <= 128 ? 128 : 256;
-		static_assert(Ut % 8 == 0 && L * N <= 256 && (L == 1 || L == 2) && (Q == 2 || Q == 4) && kThreads <= 1024, "shape");
+		static_assert(Ut % 8 == 0 && L * N <= 256 && (L == 1 || L == 2)  && kThreads <= 1024, "shape");
 	};
 
 	// weight of layer l that multiplies element e of K step ks, for gate q of unit u (zero where the layer has no such input)
@@ -84,10 +87,10 @@ namespace nab200
 		return __ldg(Wg + M.wOff[l] + (size_t)(q * colsP + col) * G + u);
 	}
 
-	template <int UPT, int NWG, int L, int Q>
+	template <int UPT, int NWG, int L>
 	__device__ __forceinline__ void tc_build_b(const LstmModelDev& M, const float* __restrict__ Wg, unsigned char* smem, int l, int tid)
 	{
-		using C = TcCfg<UPT, NWG, L, Q>;
+		using C = TcCfg<UPT, NWG, L>;
 		unsigned char* B = smem + (l == 0 ? C::kB0 : C::kB1);
 		const int Ks = C::ks(l);
 		for (int i = tid; i < Ks * C::N; i += C::kThreads)
@@ -98,7 +101,8 @@ namespace nab200
 #pragma unroll
 			for (int e = 0; e < 8; e++)
 			{
-				const float w = tc_weight(M, Wg, l, C::Ut, ks, e, q, u);
+				// the sigmoid gates (i, f, o) take their argument halved (Activation.h:93-96): folded into the weights, exact in binary
+				const float w = tc_weight(M, Wg, l, C::Ut, ks, e, q, u) * (q == 2 ? 1.0f : 0.5f);
 				const __half w1 = __float2half_rn(w);
 				const float d1 = w - __half2float(w1);
 				const __half w2 = __float2half_rn(d1);
@@ -165,11 +169,11 @@ namespace nab200
 			const float2 gf = make_float2(__uint_as_float(r[UPT + j]), __uint_as_float(r[UPT + j + 1]));
 			const float2 gg = make_float2(__uint_as_float(r[2 * UPT + j]), __uint_as_float(r[2 * UPT + j + 1]));
 			const float2 go = make_float2(__uint_as_float(r[3 * UPT + j]), __uint_as_float(r[3 * UPT + j + 1]));
-			// sigmoid(x) = 0.5 * (tanh(0.5 x) + 1) (Activation.h:93-96)
-			const float2 si = ffma2(NAB_TC_TANH2(fmul2(gi, half2)), half2, half2);
-			const float2 sf = ffma2(NAB_TC_TANH2(fmul2(gf, half2)), half2, half2);
+			// sigmoid(x) = 0.5 * (tanh(0.5 x) + 1) (Activation.h:93-96); the 0.5 x is already in the gate sums (tc_build_b)
+			const float2 si = ffma2(NAB_TC_TANH2(gi), half2, half2);
+			const float2 sf = ffma2(NAB_TC_TANH2(gf), half2, half2);
 			const float2 tg = NAB_TC_TANH2(gg);
-			const float2 so = ffma2(NAB_TC_TANH2(fmul2(go, half2)), half2, half2);
+			const float2 so = ffma2(NAB_TC_TANH2(go), half2, half2);
 			const float2 cn = ffma2(sf, make_float2(c[j], c[j + 1]), fmul2(si, tg));   // c first, then h (LSTM.h:94-99)
 			const float2 hn = fmul2(so, NAB_TC_TANH2(cn));
 			c[j] = cn.x; c[j + 1] = cn.y;
@@ -219,12 +223,12 @@ namespace nab200
 #define NAB_TC_STAMP(i) do { } while (0)
 #endif
 
-	template <int UPT, int NWG, int L, int Q>
-	__global__ void __launch_bounds__(TcCfg<UPT, NWG, L, Q>::kThreads, (Q == 4 && UPT <= 4 && TcCfg<UPT, NWG, L, Q>::kThreads <= 544) ? 2 : 1)
+	template <int UPT, int NWG, int L>
+	__global__ void __launch_bounds__(TcCfg<UPT, NWG, L>::kThreads, (UPT <= 4 && TcCfg<UPT, NWG, L>::kThreads <= 544) ? 2 : 1)
 		lstm_tc_kernel(const __grid_constant__ LstmModelDev M, const float* __restrict__ Wg, float* __restrict__ state, const float* in,
 			float* out, long long inSS, long long inFS, long long outSS, long long outFS, int S, int n, int zeroInput)
 	{
-		using C = TcCfg<UPT, NWG, L, Q>;
+		using C = TcCfg<UPT, NWG, L>;
 		extern __shared__ __align__(128) unsigned char smem[];
 		const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 		const uint32_t sA = smem_u32(smem);
@@ -235,16 +239,15 @@ namespace nab200
 		uint32_t* const tmemSlot = reinterpret_cast<uint32_t*>(smem + C::kBars + 16);
 		constexpr int kRows = C::kRows;
 		const long long base = (long long)blockIdx.x * kRows;
-		const bool worker = warp < 4 * NWG && (warp & 3) < Q;
+		const bool worker = warp < C::kIssuerWarp;
 		const int g = warp >> 2, row = ((warp & 3) << 5) | lane;    // workers: warpgroup, stream of the CTA (= TMEM lane)
-		const int wid = (g * Q + (warp & 3)) * 32 + lane;           // workers: dense index
 		const long long s = base + row;
 		const bool live = worker && s < S;
 		const int u0 = g * UPT;                                     // first hidden unit of this thread
 
 		// ---- set-up: B operands, barriers, TMEM, the streams' state into registers and into A ----
-		tc_build_b<UPT, NWG, L, Q>(M, Wg, smem, 0, tid);
-		if (L == 2) tc_build_b<UPT, NWG, L, Q>(M, Wg, smem, 1, tid);
+		tc_build_b<UPT, NWG, L>(M, Wg, smem, 0, tid);
+		if (L == 2) tc_build_b<UPT, NWG, L>(M, Wg, smem, 1, tid);
 		if (tid == 0)
 		{
 			mbar_init(bar0, 1);
@@ -284,7 +287,7 @@ namespace nab200
 				sts128(sA + kTcGroupBytes + (uint32_t)row * 16u, w2, 0u, 0u, 0u);
 			}
 			// tile 0 of the look-ahead inputs: tin[0][f][r] = x(1 + f)
-			for (int i = wid; i < kTcTile * kRows; i += C::kWorkers)
+			for (int i = tid; i < kTcTile * kRows; i += C::kWorkers)
 			{
 				int r, f;
 				if (inFS == 1 || zeroInput) { r = i / kTcTile; f = i % kTcTile; }
@@ -292,8 +295,8 @@ namespace nab200
 				const long long ss = base + r;
 				float v = 0.0f;
 				if (!zeroInput && ss < S && 1 + f < n) v = in[ss * inSS + (long long)(1 + f) * inFS];
-				tin[f * kRows + r] = v;
-				tin[kTcTile * kRows + f * kRows + r] = 0.0f;
+				tin[f * C::kTinStride + r] = v;
+				tin[kTcTile * C::kTinStride + f * C::kTinStride + r] = 0.0f;
 			}
 		}
 		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -331,7 +334,7 @@ namespace nab200
 				__syncwarp();
 			}
 		}
-		else if (worker)
+		else
 		{
 			// =================================== worker warps ===================================
 			const uint32_t tmLane = tm + ((uint32_t)((warp & 3) << 5) << 16) + (uint32_t)(g * 4 * UPT);
@@ -348,19 +351,19 @@ namespace nab200
 			for (int t0 = 0; t0 < n; t0 += kTcTile, tileIdx++)
 			{
 				const int tn = min(kTcTile, n - t0);
-				const float* tcur = tin + (tileIdx & 1) * (kTcTile * kRows);
+				const float* tcur = tin + (tileIdx & 1) * (kTcTile * C::kTinStride);
 				// the next tile's look-ahead inputs, x(t0 + tile + 1 + f), on their way while this tile runs
 				if (!zeroInput && t0 + kTcTile < n)
 				{
-					float* tnext = tin + ((tileIdx + 1) & 1) * (kTcTile * kRows);
-					for (int i = wid; i < kTcTile * kRows; i += C::kWorkers)
+					float* tnext = tin + ((tileIdx + 1) & 1) * (kTcTile * C::kTinStride);
+					for (int i = tid; i < kTcTile * kRows; i += C::kWorkers)
 					{
 						int r, f;
 						if (inFS == 1) { r = i / kTcTile; f = i % kTcTile; }
 						else { r = i % kRows; f = i / kRows; }
 						const long long ss = base + r;
 						const long long t = (long long)t0 + kTcTile + 1 + f;
-						float* dst = tnext + f * kRows + r;
+						float* dst = tnext + f * C::kTinStride + r;
 						if (ss < S && t < n)
 							asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(in + ss * inSS + t * inFS) : "memory");
 						else *dst = 0.0f;
@@ -382,7 +385,7 @@ namespace nab200
 					if (g == 0)
 					{
 						uint32_t w1, w2;
-						tc_input_words(tcur[f * kRows + row], w1, w2);
+						tc_input_words(tcur[f * C::kTinStride + row], w1, w2);
 						asm volatile("st.shared.b32 [%0], %1;" ::"r"(sA + (uint32_t)row * 16u), "r"(w1) : "memory");
 						asm volatile("st.shared.b32 [%0], %1;" ::"r"(sA + kTcGroupBytes + (uint32_t)row * 16u), "r"(w2) : "memory");
 					}
@@ -405,14 +408,14 @@ namespace nab200
 					float part = 0.0f;
 #pragma unroll
 					for (int j = 0; j < UPT; j++) part = fmaf(hw[j], h[L - 1][j], part);
-					tprod[(f * NWG + g) * kRows + row] = part;
+					tprod[f * C::kTprodStride + g * kRows + row] = part;
 				}
 				// ---- flush the tile's outputs ----
 				cp_async_wait_all();
 				nbar_sync<kTcBarWork, C::kWorkers>();
 				if (out != nullptr)
 				{
-					for (int i = wid; i < kTcTile * kRows; i += C::kWorkers)
+					for (int i = tid; i < kTcTile * kRows; i += C::kWorkers)
 					{
 						int rr, f;
 						if (outFS == 1) { rr = i / kTcTile; f = i % kTcTile; }
@@ -420,9 +423,9 @@ namespace nab200
 						const long long ss = base + rr;
 						if (ss < S && f < tn)
 						{
-							float acc = tprod[(f * NWG) * kRows + rr];
+							float acc = tprod[f * C::kTprodStride + rr];
 #pragma unroll
-							for (int k = 1; k < NWG; k++) acc += tprod[(f * NWG + k) * kRows + rr];
+							for (int k = 1; k < NWG; k++) acc += tprod[f * C::kTprodStride + k * kRows + rr];
 							out[ss * outSS + (long long)(t0 + f) * outFS] = acc + headB;
 						}
 					}
@@ -454,11 +457,11 @@ namespace nab200
 		if (warp == C::kIssuerWarp) tmem_dealloc<C::kTmemCols>(tm);
 	}
 
-	template <int UPT, int NWG, int L, int Q>
+	template <int UPT, int NWG, int L>
 	static cudaError_t lstm_tc_launch_variant(const LstmModelDev& M, const LstmLaunch& a)
 	{
-		using C = TcCfg<UPT, NWG, L, Q>;
-		auto kfn = lstm_tc_kernel<UPT, NWG, L, Q>;
+		using C = TcCfg<UPT, NWG, L>;
+		auto kfn = lstm_tc_kernel<UPT, NWG, L>;
 		static SmemGrant grant;
 		cudaError_t err = EnsureDynamicSmem(kfn, grant, C::kSmem);
 		if (err != cudaSuccess) return err;
@@ -478,21 +481,16 @@ namespace nab200
 		if (a.S == 0 || a.n == 0) return cudaSuccess;
 		if (!lstm_tc_supported(M)) return cudaErrorNotSupported;
 		const int Ut = (M.H + 7) & ~7;
-		// 64 streams per CTA while that still is at most one CTA per SM (the step is bound by one SM's issue slots), else 128
-		const int sms = a.numSMs > 0 ? a.numSMs : 148;
-		// (by the model's slot count, like the kernel choice itself: the two CTA sizes sum the head's partial products in different orders)
-		const int Sp = a.pickS > 0 ? a.pickS : a.S;
-		const bool half = a.tcRows == 64 || (a.tcRows != 128 && (Sp + 63) / 64 <= sms);
 		if (M.L == 1)
 		{
-			if (Ut == 8) return half ? lstm_tc_launch_variant<2, 4, 1, 2>(M, a) : lstm_tc_launch_variant<2, 4, 1, 4>(M, a);
-			if (Ut == 16) return half ? lstm_tc_launch_variant<2, 8, 1, 2>(M, a) : lstm_tc_launch_variant<4, 4, 1, 4>(M, a);
-			if (Ut == 24) return half ? lstm_tc_launch_variant<4, 6, 1, 2>(M, a) : lstm_tc_launch_variant<4, 6, 1, 4>(M, a);
-			return half ? lstm_tc_launch_variant<4, 8, 1, 2>(M, a) : lstm_tc_launch_variant<8, 4, 1, 4>(M, a);
+			if (Ut == 8) return lstm_tc_launch_variant<2, 4, 1>(M, a);
+			if (Ut == 16) return lstm_tc_launch_variant<4, 4, 1>(M, a);
+			if (Ut == 24) return lstm_tc_launch_variant<4, 6, 1>(M, a);
+			return lstm_tc_launch_variant<8, 4, 1>(M, a);
 		}
-		if (Ut == 8) return half ? lstm_tc_launch_variant<2, 4, 2, 2>(M, a) : lstm_tc_launch_variant<2, 4, 2, 4>(M, a);
-		if (Ut == 16) return half ? lstm_tc_launch_variant<2, 8, 2, 2>(M, a) : lstm_tc_launch_variant<4, 4, 2, 4>(M, a);
-		if (Ut == 24) return half ? lstm_tc_launch_variant<4, 6, 2, 2>(M, a) : lstm_tc_launch_variant<4, 6, 2, 4>(M, a);
-		return half ? lstm_tc_launch_variant<4, 8, 2, 2>(M, a) : lstm_tc_launch_variant<8, 4, 2, 4>(M, a);
+		if (Ut == 8) return lstm_tc_launch_variant<2, 4, 2>(M, a);
+		if (Ut == 16) return lstm_tc_launch_variant<4, 4, 2>(M, a);
+		if (Ut == 24) return lstm_tc_launch_variant<4, 6, 2>(M, a);
+		return lstm_tc_launch_variant<8, 4, 2>(M, a);
 	}
 }

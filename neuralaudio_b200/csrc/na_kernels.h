@@ -79,7 +79,6 @@ namespace nab200
 		bool generic;           // force the run-time-shaped kernel (use_tc = -1)
 		int kernel;             // 0 automatic, 1 gate rows in registers, 2 lane = stream with shared-memory matrices, 3 run-time-shaped, 4 tensor cores (tcgen05)
 		int numSMs;
-		int tcRows;             // tensor-core kernel: streams per CTA, 64 or 128 (0: 64 while that is at most one CTA per SM)
 		int pickS;              // streams the automatic kernel choice is made for (the model's slot count; 0: S)
 		cudaStream_t stream;
 	};

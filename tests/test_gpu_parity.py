@@ -432,8 +432,8 @@ def test_lane_per_stream_lstm_kernel(na, O, name, streams, tmp_path):
 @pytest.mark.parametrize("name,streams", [("syn_lstm_1x16", 70), ("syn_lstm_1x24", 65), ("syn_lstm_2x12", 37), ("syn_lstm_2x8", 129),
                                           ("syn_lstm_2x16", 200), ("syn_dyn_lstm_2x32", 64), ("syn_lstm_1x8", 3), ("ref_BossLSTM_1x16", 131)])
 def test_tensor_core_lstm_kernel(na, O, name, streams, tmp_path):
-    """The tcgen05 LSTM kernel (gates of 64 / 128 streams as one small GEMM per step and layer, fp16-pair operands; the default
-    for large batches) forced for every shape it covers: ragged stream counts around its 64- and 128-stream CTAs (both CTA sizes),
+    """The tcgen05 LSTM kernel (gates of 128 streams as one small GEMM per step and layer, fp16-pair operands; the default
+    for large batches) forced for every shape it covers: ragged stream counts around its 128-stream CTAs,
     both layouts, odd call sizes across its 16-frame tiles, probed streams against their own oracle instances, the whole batch
     against the fp32 CUDA-core kernels, and bit-identical results however the samples are cut into calls."""
     g = load_golden(golden_files(name)[0])
@@ -445,9 +445,8 @@ def test_tensor_core_lstm_kernel(na, O, name, streams, tmp_path):
     xs = [(rng.uniform(-1, 1, (streams, n)) * 0.5).astype(np.float32) for n in sizes]
     xall = np.concatenate(xs, axis=1)
     outs = {}
-    for kern, q in ((4, 64), (4, 128), (0, 0)):
+    for kern in (4, 0):
         prev = na.set_option("lstm_kernel", kern)
-        prev_rows = na.set_option("lstm_tc_rows", q)
         try:
             m = _load(na, mf, streams=streams)
             m2 = _load(na, mf, streams=streams)
@@ -468,15 +467,11 @@ def test_tensor_core_lstm_kernel(na, O, name, streams, tmp_path):
                 assert np.array_equal(y1, yall), "the cut of the call sequence changed the result"
         finally:
             na.set_option("lstm_kernel", prev)
-            na.set_option("lstm_tc_rows", prev_rows)
-        outs[(kern, q)] = y1
+        outs[kern] = y1
     for s in sorted({0, streams // 2, streams - 1}):
         ref = O.PortModel.from_file(mf).process(xall[s])
-        assert float(np.abs(ref - outs[(4, 64)][s]).max()) <= LSTM_TOL
-        assert float(np.abs(ref - outs[(4, 128)][s]).max()) <= LSTM_TOL
-    # (64- and 128-stream CTAs compute the same gates; they sum the head's partial products in different orders)
-    assert float(np.abs(outs[(4, 64)] - outs[(4, 128)]).max()) <= 2e-6
-    assert float(np.abs(outs[(4, 64)] - outs[(0, 0)]).max()) <= LSTM_TOL
+        assert float(np.abs(ref - outs[4][s]).max()) <= LSTM_TOL
+    assert float(np.abs(outs[4] - outs[0]).max()) <= LSTM_TOL
 
 
 @pytest.mark.parametrize("kind", ["zero", "huge", "tiny"])
