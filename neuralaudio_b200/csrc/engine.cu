@@ -463,6 +463,7 @@ namespace nab200
 		// the compile-time-shaped CUDA-core kernel double-buffers a layer's weight block in shared memory beside its windows:
 		// a block that cannot fit (very large kernel sizes) is a load-time refusal / generic-kernel case, not a launch failure
 		if (M.tc == 0 && ok && (size_t)2 * M.maxBlock * 4 > (size_t)96 * 1024) ok = false;
+		if (M.numArrays > 2) ok = false;   // the compile-time-shaped kernels know one or two layer arrays
 		if (M.tc == 0 && (!ok || opt.useTc < 0) && wavenet_generic_supported(M))
 		{
 			// no compile-time-shaped kernel (or the generic one was asked for): the run-time-shaped kernel

@@ -219,13 +219,13 @@ namespace nab200
 		}
 
 		// structural checks the kernels rely on
-		if (d.arrays.empty() || d.arrays.size() > (size_t)kMaxArrays) throw std::runtime_error("unsupported model: WaveNet must have 1 or 2 layer arrays");
+		if (d.arrays.empty() || d.arrays.size() > (size_t)kMaxArrays) throw std::runtime_error("unsupported model: WaveNet must have 1 to 4 layer arrays");
 		size_t totalLayers = 0;
 		for (size_t a = 0; a < d.arrays.size(); a++)
 		{
 			const auto& A = d.arrays[a];
 			if (A.dilations.empty()) throw std::runtime_error("unsupported model: empty layer array");
-			if (A.channels < 1 || A.channels > 32) throw std::runtime_error("unsupported model: WaveNet channels must be 1..32");
+			if (A.channels < 1 || A.channels > kMaxDynChannels) throw std::runtime_error("unsupported model: WaveNet channels must be 1..128");
 			if (a == 0 && A.inputSize != 1) throw std::runtime_error("unsupported model: first layer array input_size != 1");
 			if (a > 0 && A.inputSize != d.arrays[a - 1].channels) throw std::runtime_error("malformed model: layer array input_size does not match previous channels");
 			if (a + 1 < d.arrays.size() && A.headSize != d.arrays[a + 1].channels) throw std::runtime_error("malformed model: head_size does not match next array's channels");

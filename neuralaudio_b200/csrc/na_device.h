@@ -9,7 +9,8 @@
 namespace nab200
 {
 	constexpr int kMaxLayers = 32;   // layers over all arrays (A1 Standard 20, A1 Lite-pattern 20, A2 23)
-	constexpr int kMaxArrays = 2;
+	constexpr int kMaxArrays = 4;    // official shapes have 1 or 2; the run-time-shaped kernels take up to 4 (WaveNetDynamic.h takes any count)
+	constexpr int kMaxDynChannels = 128;   // widest layer array of a run-time-shaped stack
 	constexpr int kMaxRings = kMaxLayers + kMaxArrays;
 
 	enum : int

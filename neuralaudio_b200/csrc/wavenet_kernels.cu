@@ -833,14 +833,15 @@ namespace nab200
 	}
 
 	// ---- prewarm: steady state under silence (WaveNetModelT::Prewarm WaveNet.h:746-766, LayerArrayT::Prewarm :607-630)
-	// One warp computes the single zero-input frame; lane == output channel.  Fills a one-stream state TEMPLATE
+	// One block (32 threads, or 128 for run-time-shaped stacks wider than 32 channels) computes the single zero-input frame;
+	// thread == output channel.  Fills a one-stream state TEMPLATE
 	// (every ring column = the layer's steady-state input) that state_fill_kernel replicates to all stream slots.
 	__global__ void wavenet_prewarm_kernel(const __grid_constant__ WnModelDev M, const float* __restrict__ Wg, float* __restrict__ tmpl)
 	{
-		__shared__ float x[32], z[32], head[32], xin[32], hnext[32];
+		__shared__ float x[kMaxDynChannels], z[kMaxDynChannels], head[kMaxDynChannels], xin[kMaxDynChannels], hnext[kMaxDynChannels];
 		const int lane = threadIdx.x;
 		x[lane] = 0.0f; z[lane] = 0.0f; head[lane] = 0.0f; xin[lane] = 0.0f; hnext[lane] = 0.0f;
-		__syncwarp();
+		__syncthreads();
 		for (int a = 0; a < M.numArrays; a++)
 		{
 			const WnArray& A = M.arrays[a];
@@ -878,9 +879,9 @@ namespace nab200
 					float acc = 0.0f;
 					if (lane < C)
 						for (int ci = 0; ci < A.inC; ci++) acc = fmaf(wb[L.oRe + ci * C + lane], xin[ci], acc);
-					__syncwarp();
+					__syncthreads();
 					x[lane] = (lane < C) ? acc : 0.0f;
-					__syncwarp();
+					__syncthreads();
 				}
 				// history := this layer's input column everywhere (CopyBuffer, WaveNet.h:74-82)
 				if (lane < C)
@@ -895,7 +896,7 @@ namespace nab200
 					head[lane] += acc;
 				}
 				z[lane] = acc;
-				__syncwarp();
+				__syncthreads();
 				float o = 0.0f;
 				if (lane < C)
 				{
@@ -903,9 +904,9 @@ namespace nab200
 					for (int ci = 0; ci < C; ci++) o = fmaf(oneW(ci, lane), z[ci], o);
 					o += x[lane];
 				}
-				__syncwarp();
+				__syncthreads();
 				x[lane] = o;
-				__syncwarp();
+				__syncthreads();
 				if (L.flags & kLastInArray)
 				{
 					if (A.Kh > 1 && lane < C)
@@ -919,10 +920,10 @@ namespace nab200
 							for (int c = 0; c < C; c++) ho = fmaf(wb[L.oHeadW + (k * C + c) * A.H + lane], head[c], ho);
 					}
 					hnext[lane] = ho;
-					__syncwarp();
+					__syncthreads();
 					xin[lane] = x[lane];      // arrayOutputs -> next array's rechannel input
 					head[lane] = hnext[lane]; // headOutputs  -> next array's running head
-					__syncwarp();
+					__syncthreads();
 				}
 			}
 		}
@@ -1039,7 +1040,9 @@ namespace nab200
 
 	cudaError_t wavenet_prewarm_launch(const WnModelDev& M, const float* weights, float* tmpl, cudaStream_t stream)
 	{
-		wavenet_prewarm_kernel<<<1, 32, 0, stream>>>(M, weights, tmpl);
+		int width = 0;
+		for (int a = 0; a < M.numArrays; a++) width = max(width, max(M.arrays[a].C, max(M.arrays[a].H, M.arrays[a].inC)));
+		wavenet_prewarm_kernel<<<1, width > 32 ? kMaxDynChannels : 32, 0, stream>>>(M, weights, tmpl);
 		return cudaGetLastError();
 	}
 

@@ -369,7 +369,7 @@ namespace nab200
 	// shared memory, channel widths up to 8 (A1 Nano, A2 Lite and run-time-shaped stacks of those widths).
 	bool wavenet_one_supported(const WnModelDev& M, size_t weightFloats)
 	{
-		if (M.tc != 0) return false;
+		if (M.tc != 0 || M.numArrays > 2) return false;
 		const int C0 = M.arrays[0].C, C1 = M.numArrays > 1 ? M.arrays[1].C : 0, act = M.arrays[0].act;
 		const bool shape = act == 0 ? ((C0 == 8 && C1 == 4) || (C0 == 4 && C1 == 2) || (C0 == 8 && C1 == 8) || (C0 == 8 && C1 == 0) || (C0 == 4 && C1 == 0))
 			: ((C0 == 8 && C1 == 0) || (C0 == 4 && C1 == 0));

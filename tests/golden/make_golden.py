@@ -117,7 +117,13 @@ def dynamic_cases():
     shapes = {"dyn_20x10": [(20, 3, [1, 2, 4, 8, 16, 32, 64]), (10, 3, [128, 1, 2, 4, 8])],
               "dyn_single6_k2": [(6, 2, [1, 3, 9, 27])],
               "dyn_16x16_k5": [(16, 5, [1, 2, 4, 8]), (16, 5, [1, 2, 4, 8])],
-              "dyn_7x3": [(7, 3, [1, 2, 4, 8, 16]), (3, 3, [1, 2, 4])]}
+              "dyn_7x3": [(7, 3, [1, 2, 4, 8, 16]), (3, 3, [1, 2, 4])],
+              # beyond two layer arrays / 32 channels (WaveNetDynamic.h takes any count and width); appended so that the draws of
+              # the earlier cases stay what they were
+              "dyn_3arrays": [(8, 3, [1, 2, 4, 8, 16]), (6, 3, [1, 2, 4, 8]), (4, 2, [1, 3, 9])],
+              "dyn_4arrays": [(5, 2, [1, 2, 4]), (10, 3, [1, 2]), (3, 3, [1, 4, 16]), (2, 2, [1, 2])],
+              "dyn_48x24": [(48, 3, [1, 2, 4, 8, 16, 32]), (24, 3, [1, 2, 4, 8])],
+              "dyn_single40_k3": [(40, 3, [1, 2, 4, 8, 16, 32, 64, 128])]}
     cases = {}
     for name, arrays in shapes.items():
         cfg = dyn_config(arrays)
@@ -201,7 +207,7 @@ def main():
         os.rmdir(tmpdir)
         return
     made = []
-    fixtures = [] if ("--dynamic-only" in sys.argv or "--dynamic-lstm-only" in sys.argv or "--extra-lstm-only" in sys.argv) else [("BossWN-nano.nam", 1.0), ("BossWN-feather.nam", 1.0), ("BossWN-standard.nam", 1.0), ("BossWN-a2.nam", 1.0),
+    fixtures = [] if ("--wide-only" in sys.argv or "--dynamic-only" in sys.argv or "--dynamic-lstm-only" in sys.argv or "--extra-lstm-only" in sys.argv) else [("BossWN-nano.nam", 1.0), ("BossWN-feather.nam", 1.0), ("BossWN-standard.nam", 1.0), ("BossWN-a2.nam", 1.0),
                 ("BossWN-a2.nam", 0.0), ("BossLSTM-1x16.nam", 1.0), ("BossLSTM-2x8.nam", 1.0),
                 ("tw40_blues_deluxe_deerinkstudios.json", 1.0), ("namcore_wavenet.nam", 1.0), ("namcore_lstm.nam", 1.0),
                 ("namcore_wavenet_a1_standard.nam", 1.0)]
@@ -218,10 +224,12 @@ def main():
         np.savez_compressed(out, x=x, y=y, dc=dc, fixture=name, quality=np.float32(q), info=json.dumps(info))
         made.append(out)
     only_dynamic = "--dynamic-only" in sys.argv   # adds the run-time-shaped cases without touching the earlier vectors
+    only_wide = "--wide-only" in sys.argv         # the cases beyond two layer arrays / 32 channels, added last
+    wide_only = ("dyn_3arrays", "dyn_4arrays", "dyn_48x24", "dyn_single40_k3")
     only_dyn_lstm = "--dynamic-lstm-only" in sys.argv
     only_extra = "--extra-lstm-only" in sys.argv     # the two static LSTM sizes added last (lstm_1x8, lstm_2x16)
     extra_only = ("lstm_1x8", "lstm_2x16")
-    if only_dynamic or only_dyn_lstm or only_extra:
+    if only_dynamic or only_dyn_lstm or only_extra or only_wide:
         made = []
     allcases = list(synthetic_cases().items()) + list(dynamic_cases().items()) + list(dynamic_lstm_cases().items())
     for j, (name, case) in enumerate(allcases):
@@ -230,6 +238,8 @@ def main():
         if only_dyn_lstm and not name.startswith("dyn_lstm"):
             continue
         if only_extra and name not in extra_only:
+            continue
+        if only_wide and name not in wide_only:
             continue
         path = os.path.join(tmpdir, name + ".nam")
         with open(path, "w") as f:

@@ -306,11 +306,13 @@ def test_tensor_core_and_cuda_core_kernels_agree(na, O, name, tmp_path):
             assert float(np.abs(ys - y[:, s, :].reshape(-1)).max()) <= WAVENET_TOL
 
 
-@pytest.mark.parametrize("name", ["syn_a1_standard", "syn_a1_feather", "syn_a2_full", "syn_dyn_20x10", "syn_dyn_16x16_k5"])
+@pytest.mark.parametrize("name", ["syn_a1_standard", "syn_a1_feather", "syn_a2_full", "syn_dyn_20x10", "syn_dyn_16x16_k5",
+                                  "syn_dyn_3arrays", "syn_dyn_4arrays", "syn_dyn_48x24", "syn_dyn_single40_k3"])
 def test_runtime_shaped_kernel(na, O, name, tmp_path):
-    """The run-time-shaped kernel (the batched counterpart of the reference's dynamic path, WaveNetDynamic.h) against the
-    oracle per stream, for shapes that only it can run and - forced with use_tc = -1 - for official shapes, where it must
-    also agree with the specialised kernels."""
+    """The run-time-shaped kernels (the batched counterpart of the reference's dynamic path, WaveNetDynamic.h) against the
+    oracle per stream, for shapes that only they can run (three and four layer arrays; more than 32 channels: the
+    shared-memory form) and - forced with use_tc = -1 - for official shapes, where they must also agree with the
+    specialised kernels."""
     g = load_golden(golden_files(name)[0])
     mf = model_file_for(g, tmp_path)
     S, n, calls = 9, 100, 11     # ragged: 100-frame calls
