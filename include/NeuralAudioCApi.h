@@ -137,8 +137,15 @@ NA_EXTERN int NA_DescribeModelFile(const wchar_t* modelPath, int externalSampleR
  *   "h_ctas":  streams in flight per SM of the fp16-pair kernel (0 = its default);
  *   "ts_split": 1 = run the 3xTF32 kernel as one launch per layer array (default 0, fused);
  *   "use_tma": 0 = plain loads instead of TMA in the CUDA-core WaveNet kernel (debugging aid);
- *   "max_grid_ctas": cap on the SM count used for grid sizing (0 = all).
- * The same knobs can be preset through NAB200_USE_TC / NAB200_H_CTAS / NAB200_TS_SPLIT / NAB200_USE_TMA / NAB200_MAX_GRID_CTAS. */
+ *   "max_grid_ctas": cap on the SM count used for grid sizing (0 = all);
+ *   "use_one": 1 (default) single-stream calls of small WaveNets on the one-CTA kernel, 0 the batched kernels for every call;
+ *   "lstm_kernel": 0 (default) by shape and stream-slot count, 1 gate rows in registers, 2 lane = stream with shared-memory
+ *              matrices, 3 run-time-shaped, 4 tcgen05 gates (one or two layers, up to 32 units);
+ *   "zero_copy_kfloats": blocking host calls of up to this many thousand samples run on the caller's page-locked buffers
+ *              directly (default: every size; 0 = always staged through the copy engines);
+ *   "async_zero_copy": 1 = NA_ProcessBatchAsync runs zero-copy too (default 0: staged, overlapped with the neighbouring calls).
+ * The same knobs can be preset through NAB200_USE_TC / NAB200_H_CTAS / NAB200_TS_SPLIT / NAB200_USE_TMA / NAB200_MAX_GRID_CTAS /
+ * NAB200_USE_ONE / NAB200_LSTM_KERNEL / NAB200_ZERO_COPY_KFLOATS / NAB200_ASYNC_ZERO_COPY. */
 NA_EXTERN int NA_SetOption(const char* name, int value);
 /* the same knobs for the models ONE loader builds (copied into each model at load; nothing is read from globals at run time) */
 NA_EXTERN void NA_SetLoaderOption(NeuralModelLoader* loader, const char* name, int value);

@@ -486,7 +486,7 @@ int NA_DescribeModelFile(const wchar_t* modelPath, int externalSampleRate, char*
 					const bool hk = nab200::GetOptions().useTc >= 3 && nab200::WaveNetHSupported(d);
 					const bool ts = !hk && nab200::GetOptions().useTc >= 2 && nab200::WaveNetTsSupported(d);
 					const int pc0 = p.dev.arrays[0].C, pc1 = p.dev.numArrays > 1 ? p.dev.arrays[1].C : 0;
-					const bool shaped = nab200::GetOptions().useTc >= 0 && nab200::wavenet_variant_supported(pc0, pc1, p.dev.arrays[0].act);
+					const bool shaped = nab200::GetOptions().useTc >= 0 && p.dev.numArrays <= 2 && nab200::wavenet_variant_supported(pc0, pc1, p.dev.arrays[0].act);
 					os << ",\"kernel\":\"" << (hk ? "tcgen05_fp16_pairs" : ts ? "tcgen05_tmem_operands" : shaped ? "cuda_cores" : nab200::wavenet_generic_supported(p.dev) ? "cuda_cores_runtime_shaped" : "none") << "\"";
 					if (nab200::WaveNetTsSupported(d))
 					{

@@ -17,4 +17,9 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --c
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:wavenet_h -s 36 -c 1 -f -o gpurun_out/prof_wavenet python bench.py --steps 4 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full.out 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:lstm_fwd -s 20 -c 1 -f -o gpurun_out/prof_lstm python bench.py --workload lstm_1x16 --steps 4 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full_lstm.out 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:wavenet_h -s 120 -c 1 -f -o gpurun_out/prof_a2 python bench.py --workload a2_full --steps 4 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full_a2.out 2>&1
+# the tensor-core LSTM kernel: 2x16 at 8192 streams is its automatic choice (skip the 2048-step prewarm launch)
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:lstm_tc -s 1 -c 1 -f -o gpurun_out/prof_lstm_tc python tools/lstm_tc_check.py 8192 syn_lstm_2x16 > gpurun_out/ncu_full_lstm_tc.out 2>&1
+timeout 300 python tools/shape_table.py > gpurun_out/shape_table.txt 2>&1; tail -12 gpurun_out/shape_table.txt
+(timeout 200 python tools/lstm_tc_check.py 8192; timeout 200 python tools/lstm_tc_check.py 32768 syn_lstm_1x16 syn_lstm_1x24 syn_lstm_2x8 syn_lstm_2x12 syn_lstm_2x16 syn_dyn_lstm_2x32) > gpurun_out/lstm_tc_check.txt 2>&1; cat gpurun_out/lstm_tc_check.txt
+timeout 300 bash tools/gpu_blocking_ab.sh > gpurun_out/host_paths_ab.txt 2>&1; cat gpurun_out/host_paths_ab.txt
 ls -la gpurun_out

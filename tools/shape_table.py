@@ -16,21 +16,24 @@ import neuralaudio_b200 as na
 
 SHAPES = ["syn_a1_standard.", "syn_a1_lite", "syn_a1_feather", "syn_a1_nano.", "syn_a2_full", "syn_a2_lite", "syn_a1_standard_sr96000",
           "syn_dyn_20x10", "syn_dyn_16x16_k5", "syn_dyn_7x3", "syn_dyn_single6_k2",
-          "syn_lstm_1x16", "syn_lstm_1x24", "syn_lstm_2x8", "syn_lstm_2x12", "syn_dyn_lstm_2x32", "syn_dyn_lstm_3x18", "syn_dyn_lstm_1x40"]
+          "syn_dyn_3arrays", "syn_dyn_48x24",
+          "syn_lstm_1x16", "syn_lstm_1x24", "syn_lstm_2x8", "syn_lstm_2x12", "syn_lstm_2x16", "syn_dyn_lstm_2x32", "syn_dyn_lstm_3x18", "syn_dyn_lstm_1x40",
+          "syn_lstm_1x16@32768", "syn_lstm_1x24@32768", "syn_lstm_2x16@32768"]
 
 
 def main():
     with tempfile.TemporaryDirectory() as tmp:
         for name in SHAPES:
+            name, _, big = name.partition("@")
             g = C.load_golden(C.golden_files(name)[0])
             mf = C.model_file_for(g, tmp)
             sr = C.external_sample_rate_of(g)
             lstm = C.is_lstm_case(g)
-            S = 8192 if lstm else 4096
+            S = int(big) if big else 8192 if lstm else 4096
             n = 256 if "a2_" in name else 128
             d = na.describe_model_file(mf, sr)
-            kernel = d.get("kernel") or ("lstm" if lstm else "")
-            if "dyn_20x10" in name or "16x16" in name or "single6" in name or ("dyn_lstm" in name and "2x32" not in name):
+            kernel = (d.get("kernel_32768_streams") if big else d.get("kernel")) or ("lstm" if lstm else "")
+            if "dyn_20x10" in name or "16x16" in name or "single6" in name or "dyn_3arrays" in name or "dyn_48x24" in name or ("dyn_lstm" in name and "2x32" not in name):
                 S //= 8      # run-time-shaped kernels: correctness paths, a smaller batch keeps the table quick
             ld = na.NeuralModelLoader()
             ld.SetExternalSampleRate(sr)

@@ -71,7 +71,7 @@ def main():
     tp = os.path.join(PROF, "roofline_traffic.json")
     if os.path.exists(tp):
         traffic = json.load(open(tp))
-    for name, workload in (("prof_wavenet", "a1_standard"), ("prof_lstm", "lstm_1x16"), ("prof_a2", "a2_full")):
+    for name, workload in (("prof_wavenet", "a1_standard"), ("prof_lstm", "lstm_1x16"), ("prof_a2", "a2_full"), ("prof_lstm_tc", None)):
         rep = os.path.join(OUT, name + ".ncu-rep")
         if not os.path.exists(rep):
             continue
@@ -79,11 +79,13 @@ def main():
         if not launches:
             continue
         summary[name] = {"launches": launches, "sampling": stalls(rep)}
+        if workload is None:
+            continue
         try:
             rd = float(launches[0]["dram__bytes_read.sum"].split()[0]) * (1e6 if "Mbyte" in launches[0]["dram__bytes_read.sum"] else 1e9 if "Gbyte" in launches[0]["dram__bytes_read.sum"] else 1e3 if "Kbyte" in launches[0]["dram__bytes_read.sum"] else 1)
             wr = float(launches[0]["dram__bytes_write.sum"].split()[0]) * (1e6 if "Mbyte" in launches[0]["dram__bytes_write.sum"] else 1e9 if "Gbyte" in launches[0]["dram__bytes_write.sum"] else 1e3 if "Kbyte" in launches[0]["dram__bytes_write.sum"] else 1)
             traffic[workload] = {"dram_bytes_per_launch": rd + wr, "dram_read": rd, "dram_write": wr, "kernel": launches[0]["kernel"][:60], "from": tag}
-            if "wavenet_h_kernel<0>" in launches[0]["kernel"] or "wavenet_h_kernel<(int)0" in launches[0]["kernel"]:
+            if "wavenet_h_kernel<" in launches[0]["kernel"]:
                 traffic[workload]["kernel_choice"] = "tcgen05_fp16_pairs"
             if workload == "a2_full":
                 # the bench's A2 step is 256 frames = two 128-frame launches of the tensor-core kernel
@@ -99,7 +101,8 @@ def main():
     if os.path.exists(os.path.join(OUT, "launches.csv")):
         shutil.copy(os.path.join(OUT, "launches.csv"), os.path.join(PROF, tag + "_launches_a1_standard.csv"))
     for f, dst in (("pytest_gpu.log", "_pytest_gpu.log"), ("parity.txt", "_parity.txt"), ("latency.txt", "_single_stream_latency.txt"),
-                   ("model_test.txt", "_model_test.txt")):
+                   ("model_test.txt", "_model_test.txt"), ("shape_table.txt", "_shape_table.txt"), ("lstm_tc_check.txt", "_lstm_tc_check.txt"),
+                   ("host_paths_ab.txt", "_host_paths_ab.txt")):
         if os.path.exists(os.path.join(OUT, f)):
             shutil.copy(os.path.join(OUT, f), os.path.join(PROF, tag + dst))
     print(json.dumps({k: v["launches"][0] for k, v in summary.items()}, indent=1)[:3000])
