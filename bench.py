@@ -428,7 +428,40 @@ def single_stream_latency(na, torch, dev, workload, path, frames, quality, calls
     return out
 
 
+def pin_to_gpu_numa_node(local_rank):
+    """Multi-GPU runs: bind this rank's host threads (and with them its page-locked staging buffers, first touched here) to the
+    NUMA node its GPU hangs off, so eight ranks do not all stage through one socket.  Returns what was done, for the JSON line."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        idx = local_rank
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        if vis:
+            ent = [v.strip() for v in vis.split(",") if v.strip()]
+            if local_rank < len(ent) and ent[local_rank].isdigit():
+                idx = int(ent[local_rank])
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(idx)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        dom, rest = bus.lower().split(":", 1)
+        sysdev = "/sys/bus/pci/devices/%s:%s" % (dom[-4:], rest)
+        node = int(open(os.path.join(sysdev, "numa_node")).read().strip())
+        if node < 0:
+            return {"numa_node": node, "pinned": False}
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return {"numa_node": node, "pinned": False}
+        os.sched_setaffinity(0, cpus)
+        return {"numa_node": node, "pinned": True, "cpus": len(cpus)}
+    except Exception as e:   # no NVML / no sysfs: run unpinned
+        return {"pinned": False, "why": str(e)[:80]}
+
+
 def run_b200(args, rank, local_rank, world):
+    affinity = pin_to_gpu_numa_node(local_rank) if world > 1 else None
     import torch
     import neuralaudio_b200 as na
 
@@ -476,6 +509,7 @@ def run_b200(args, rank, local_rank, world):
             line["sustained"] = dict(head["sustained"], clocks=clocks.get("sustained"))
         if shard is not None:
             line["multi_gpu_load"] = shard
+            line["host_affinity"] = {"rank0": affinity, "note": "each rank binds its host threads to its GPU's NUMA node before CUDA starts"}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(path, frames, quality, args.cpu_seconds)
         if world == 1 and not args.no_extras and args.workload == "a1_standard":
