@@ -206,10 +206,10 @@ def test_cpp_consumer_builds_links_and_fails_loudly_without_gpu(tmp_path):
 
 def test_lstm_kernel_choice_by_shape(na, tmp_path):
     """Host logic of the LSTM dispatch (reported for a model of 8192 stream slots, and of 32768): gate rows in registers where they
-    fit (up to 16 units in one layer, 8 in two) until the batch is large enough for the tensor-core kernel's fixed step chain to pay;
-    past that register cliff the tensor-core kernel (one or two layers, up to 32 units) from ~6000 streams, the lane-per-stream
+    fit (up to 16 units in one layer, 8 in two; 1x16 moves to the tensor-core kernel once the batch is large enough for that kernel's
+    fixed step chain to pay, ~14000 streams); past that register cliff the tensor-core kernel (one or two layers, up to 32 units) from ~5000 streams, the lane-per-stream
     kernel with shared-memory matrices for everything else (three or more layers, more than 32 units)."""
-    want = {"syn_lstm_1x16": ("lstm_gate_rows_in_registers", "lstm_tcgen05_gates"), "syn_lstm_2x8": ("lstm_gate_rows_in_registers", "lstm_tcgen05_gates"),
+    want = {"syn_lstm_1x16": ("lstm_gate_rows_in_registers", "lstm_tcgen05_gates"), "syn_lstm_2x8": ("lstm_gate_rows_in_registers", "lstm_gate_rows_in_registers"),
             "syn_lstm_1x8": ("lstm_gate_rows_in_registers", "lstm_gate_rows_in_registers"),
             "syn_lstm_1x24": ("lstm_tcgen05_gates", "lstm_tcgen05_gates"), "syn_lstm_2x12": ("lstm_tcgen05_gates", "lstm_tcgen05_gates"),
             "syn_dyn_lstm_2x32": ("lstm_tcgen05_gates", "lstm_tcgen05_gates"),
