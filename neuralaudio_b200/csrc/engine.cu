@@ -464,6 +464,9 @@ namespace nab200
 		// a block that cannot fit (very large kernel sizes) is a load-time refusal / generic-kernel case, not a launch failure
 		if (M.tc == 0 && ok && (size_t)2 * M.maxBlock * 4 > (size_t)96 * 1024) ok = false;
 		if (M.numArrays > 2) ok = false;   // the compile-time-shaped kernels know one or two layer arrays
+		// a K > 1 head conv stages its whole history as one window: (Kh - 1) x head dilation frames must fit a window row (hosts up to 4x the model's rate)
+		for (int a = 0; a < M.numArrays; a++)
+			if (M.arrays[a].Kh > 1 && (M.arrays[a].Kh - 1) * M.arrays[a].Kd > 64) ok = false;
 		if (M.tc == 0 && (!ok || opt.useTc < 0) && wavenet_generic_supported(M))
 		{
 			// no compile-time-shaped kernel (or the generic one was asked for): the run-time-shaped kernel

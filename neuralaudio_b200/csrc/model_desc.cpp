@@ -78,7 +78,7 @@ namespace nab200
 		return j.contains(name) && !j.at(name).is_null();
 	}
 
-	bool NamIsA2Standard(const Json& modelJson)
+	bool NamIsA2Standard(const Json& modelJson, bool anyTiming)
 	{
 		if (!modelJson.contains("architecture") || !modelJson.at("architecture").is_string()) return false;
 		if (modelJson.at("architecture").as_string() != "WaveNet") return false;
@@ -94,8 +94,8 @@ namespace nab200
 		const int channels = lc.value_int("channels", 0);
 		if (channels != 3 && channels != 8) return false;
 		if (lc.value_int("bottleneck", channels) != channels) return false;
-		if (!lc.contains("kernel_sizes") || !SameSequence(lc.at("kernel_sizes"), kA2KernelSizes)) return false;
-		if (!lc.contains("dilations") || !SameSequence(lc.at("dilations"), kA2Dilations)) return false;
+		if (!lc.contains("kernel_sizes") || !lc.at("kernel_sizes").is_array() || !lc.contains("dilations") || !lc.at("dilations").is_array()) return false;
+		if (!anyTiming && (!SameSequence(lc.at("kernel_sizes"), kA2KernelSizes) || !SameSequence(lc.at("dilations"), kA2Dilations))) return false;
 		if (!lc.contains("activation")) return false;
 		// The reference walks these with nlohmann's range-for, which visits an array's elements, an object's VALUES, a scalar
 		// once and null never (NeuralModel.cpp:246-283): a single string / dict activation therefore fails the "type" test and
@@ -123,7 +123,7 @@ namespace nab200
 		const Json& head = lc.at("head");
 		if (head.value_int("out_channels", 1) != 1) return false;
 		if (head.value_int("kernel_size", 16) != 16) return false;
-		if (head.value_int("head_dilation", 1) != 1) return false;
+		if (!anyTiming && head.value_int("head_dilation", 1) != 1) return false;
 		if (!head.value_bool("bias", true)) return false;
 		if (!IsActive(lc, "layer1x1")) return false;
 		if (lc.contains("layer1x1") && lc.at("layer1x1").value_int("groups", 1) != 1) return false;
@@ -164,8 +164,11 @@ namespace nab200
 		const Json& config = modelJson.at("config");
 		const Json& layers = config.at("layers");
 
-		// NeuralModel.cpp:365-380: A2-generation files that are not the "standard" A2 need NAM Core in the reference
-		if (NamIsA2(version) && !NamIsA2Standard(modelJson))
+		// NeuralModel.cpp:365-380: A2-generation files that are not the "standard" A2 need NAM Core in the reference.  One family of
+		// them runs here: the standard A2 network with other delays -- what OversampleNAMConfig (NeuralModel.cpp:92-130) makes of an A2
+		// file when the host runs at a multiple of the model's rate (dilations and head dilation scaled); the same layers, the same
+		// weights, longer histories.  Everything else NAM-Core-only (gating, FiLM, head1x1, groups, slimmable slicing...) is refused.
+		if (NamIsA2(version) && !NamIsA2Standard(modelJson, true))
 			throw std::runtime_error("unsupported model: A2-generation WaveNet with non-standard features (the reference loads it with NAM Core; "
 									 "this build has no CPU fallback)");
 
@@ -173,16 +176,19 @@ namespace nab200
 		{
 			// NeuralModel.cpp:389-421: the static A2 types (3 or 8 channels, LeakyReLU, head K=16 with bias)
 			const Json& lc = layers.at(0);
-			if (!SameSequence(lc.at("dilations"), kA2Dilations))
-				throw std::runtime_error("unsupported model: A2 WaveNet with non-standard dilations (oversampled A2 is NAM-Core-only in the reference)");
 			const int ch = lc.at("channels").as_int();
 			if (ch != 3 && ch != 8) throw std::runtime_error("unsupported model: A2 WaveNet must have 3 or 8 channels");
 			WaveNetArrayDesc a;
 			a.inputSize = 1; a.channels = ch; a.headSize = 1; a.headKernel = 16; a.headBias = true; a.activation = 1;
-			a.kernelSizes = kA2KernelSizes;
-			a.dilations = kA2Dilations;
+			a.kernelSizes = IntList(lc.at("kernel_sizes"));
+			a.dilations = IntList(lc.at("dilations"));
+			if (a.kernelSizes.size() != a.dilations.size()) throw std::runtime_error("malformed model: kernel_sizes and dilations differ in length");
+			a.headDilation = lc.contains("head") ? lc.at("head").value_int("head_dilation", 1) : 1;
+			if (a.headDilation < 1 || a.headDilation > 64) throw std::runtime_error("unsupported model: head dilation out of range");
 			d.arrays.push_back(a);
-			d.isStatic = true;
+			// the reference's static A2 types are exactly the standard delays (NeuralModel.cpp:389-421); other delays: NAM Core there, dynamic semantics here
+			d.isStatic = a.headDilation == 1 && SameSequence(lc.at("kernel_sizes"), kA2KernelSizes) && SameSequence(lc.at("dilations"), kA2Dilations);
+			d.namCoreTiming = !d.isStatic;
 		}
 		else
 		{
@@ -251,7 +257,7 @@ namespace nab200
 					if (A.kernelSizes[l] > kMaxKernelSize) throw std::runtime_error("unsupported model: conv kernel size out of range");
 					const long long frames = (long long)(A.kernelSizes[l] - 1) * (long long)A.dilations[l];
 					if (frames > kMaxStateFloats) throw std::runtime_error("unsupported model: dilation out of range");
-					stateFloats += 32ll * (frames + 4);             // channels are padded to at most 32, rings to 4 frames
+					stateFloats += (long long)kMaxDynChannels * (frames + 4);   // channels are padded to at most 128, rings to 4 frames
 					if (stateFloats > kMaxStateFloats) throw std::runtime_error("unsupported model: receptive field too large (history per stream exceeds 64 MiB)");
 				}
 			}
@@ -270,7 +276,7 @@ namespace nab200
 		for (const auto& A : d.arrays)
 		{
 			for (size_t l = 0; l < A.dilations.size(); l++) d.receptiveField += (A.kernelSizes[l] - 1) * A.dilations[l];
-			d.receptiveField += (A.headKernel - 1);
+			d.receptiveField += (A.headKernel - 1) * A.headDilation;
 		}
 		return d;
 	}
@@ -415,7 +421,7 @@ namespace nab200
 			const int inC = A.inputSize, inCP = a == 0 ? 1 : PadChannels(inC);
 			const int H = A.headSize, HP = last ? 1 : PadChannels(H);
 			const int nL = (int)A.dilations.size();
-			DA.C = CP; DA.inC = inCP; DA.H = HP; DA.Kh = A.headKernel; DA.act = A.activation;
+			DA.C = CP; DA.inC = inCP; DA.H = HP; DA.Kh = A.headKernel; DA.Kd = A.headDilation; DA.act = A.activation;
 			DA.firstLayer = layerIdx; DA.numLayers = nL; DA.realC = C; DA.realH = H;
 
 			// file order (WaveNet.h:570-580): rechannel, layers..., head
@@ -486,7 +492,7 @@ namespace nab200
 			}
 			if (A.headKernel > 1)
 			{
-				DA.headLp = Align4(A.headKernel - 1);
+				DA.headLp = Align4((A.headKernel - 1) * A.headDilation);
 				DA.headRingOff = ringOff;
 				DA.headRingIdx = ringIdx;
 				M.ringLp[ringIdx] = DA.headLp;
@@ -563,7 +569,7 @@ namespace nab200
 			const int inC = A.inputSize, inCP = a == 0 ? 1 : prevCP;
 			const int H = A.headSize;
 			const int nL = (int)A.dilations.size();
-			DA.C = CP; DA.inC = inCP; DA.H = 8; DA.Kh = 1; DA.act = A.activation;
+			DA.C = CP; DA.inC = inCP; DA.H = 8; DA.Kh = 1; DA.Kd = 1; DA.act = A.activation;
 			DA.firstLayer = layerIdx; DA.numLayers = nL; DA.realC = C; DA.realH = H;
 			const float* wRe = w; w += (size_t)C * inC;
 			std::vector<const float*> wLayer(nL);
@@ -751,7 +757,7 @@ namespace nab200
 	{
 		if (desc.arrays.size() != 1) return false;
 		const WaveNetArrayDesc& A = desc.arrays[0];
-		return A.channels > 4 && A.channels <= 8 && A.inputSize == 1 && A.headSize == 1 && A.headKernel == 16 && A.activation == 1 && !A.dilations.empty();
+		return A.channels > 4 && A.channels <= 8 && A.inputSize == 1 && A.headSize == 1 && A.headKernel == 16 && A.headDilation == 1 && A.activation == 1 && !A.dilations.empty();
 	}
 
 	// Rows per plane of the window buffer for the two-array (16, 8)-channel family: consecutive layers (up to 256 rows each) get
@@ -827,7 +833,7 @@ namespace nab200
 			const int inC = A.inputSize;
 			const int H = A.headSize;
 			const int nL = (int)A.dilations.size();
-			DA.C = CP; DA.inC = a == 0 ? 1 : 16; DA.H = 8; DA.Kh = Kh; DA.act = A.activation;
+			DA.C = CP; DA.inC = a == 0 ? 1 : 16; DA.H = 8; DA.Kh = Kh; DA.Kd = 1; DA.act = A.activation;
 			DA.firstLayer = layerIdx; DA.numLayers = nL; DA.realC = C; DA.realH = H;
 			const float* wRe = w; w += (size_t)C * inC;
 			std::vector<const float*> wLayer(nL);

@@ -12,6 +12,7 @@ namespace nab200
 	struct WaveNetArrayDesc
 	{
 		int inputSize = 1, channels = 0, headSize = 1, headKernel = 1;
+		int headDilation = 1;   // 1; the oversampling factor for an A2 file on a faster host (OversampleNAMConfig, NeuralModel.cpp:122-127)
 		bool headBias = false;
 		int activation = 0;   // 0 tanh, 1 leaky relu
 		std::vector<int> kernelSizes, dilations;
@@ -22,6 +23,7 @@ namespace nab200
 		std::vector<WaveNetArrayDesc> arrays;
 		std::vector<float> weights;   // file order
 		bool isStatic = false;        // one of the reference's compile-time architectures
+		bool namCoreTiming = false;   // the standard A2 network with other delays: the reference runs it on NAM Core (NeuralModel.cpp:365-380)
 		int receptiveField = 0;
 	};
 
@@ -47,7 +49,8 @@ namespace nab200
 	// reference NeuralModel.cpp:159-168
 	bool NamIsA2(const std::string& version);
 	// reference NeuralModel.cpp:188-317
-	bool NamIsA2Standard(const Json& modelJson);
+	// anyTiming: the same predicate without the three checks that pin the delays (kernel sizes, dilations, head dilation)
+	bool NamIsA2Standard(const Json& modelJson, bool anyTiming = false);
 
 	// throw std::runtime_error with a clear message for anything outside the supported set
 	WaveNetDesc ParseNamWaveNet(const Json& modelJson);

@@ -45,6 +45,7 @@ namespace nab200
 		int inC;        // padded input channels of the rechannel (1 for the first array)
 		int H;          // padded head size (== next array's C; 1 for the last array)
 		int Kh;         // head conv kernel size (1 for A1, 16 for A2)
+		int Kd;         // head conv dilation (1; the oversampling factor for an A2 file on a faster host)
 		int act;        // 0 = FastMath tanh, 1 = LeakyReLU(0.01)
 		int firstLayer, numLayers;
 		int headLp, headRingOff, headRingIdx;   // head-conv history ring (Kh > 1 only)

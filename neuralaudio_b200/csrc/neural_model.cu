@@ -420,7 +420,9 @@ inline namespace b200
 		model->ReadNAMConfig(modelJson);
 		model->isStatic = desc.isStatic;
 		// only the static adapters override GetReceptiveFieldSize (InternalModel.h:99-102); dynamic models report -1
-		model->receptiveField = desc.isStatic ? desc.receptiveField : -1;
+		// (an A2 network with non-standard delays is a NAM Core model in the reference: NAMModel::GetReceptiveFieldSize = GetPrewarmSamples
+		// = 1 + the sum of the conv histories, deps/NeuralAmpModelerCore/NAM/wavenet/model.cpp:615-620)
+		model->receptiveField = desc.isStatic ? desc.receptiveField : desc.namCoreTiming ? desc.receptiveField + 1 : -1;
 		const nab200::Options opts = LoaderOptions(loader);
 		const int tcOpt = opts.useTc;
 		const bool useH = tcOpt >= 3 && nab200::WaveNetHSupported(desc);

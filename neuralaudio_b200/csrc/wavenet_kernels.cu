@@ -185,7 +185,7 @@ namespace nab200
 				}
 				if ((L.flags & kLastInArray) && A.Kh > 1)
 				{
-					if (nj < cap) table[nj] = make_int4(A.headRingOff, A.headLp, A.Kh - 1, A.headRingIdx | (A.C << 8) | ((A.Kh - 1) << 16));
+					if (nj < cap) table[nj] = make_int4(A.headRingOff, A.headLp, (A.Kh - 1) * A.Kd, A.headRingIdx | (A.C << 8) | (((A.Kh - 1) * A.Kd) << 16));
 					nj++;
 				}
 			}
@@ -611,11 +611,11 @@ namespace nab200
 							sm[(2 * c + 1) * STR + fr[r]] = head2[r][c].y;
 						}
 					const int convJobs = hist == 0 ? 0 : (whole ? 1 : (K - 1));
-					const int hwin = pipe.acquire(l, convJobs);   // whole head history: Kh-1 frames (also syncs the team)
-					const int Hh = Kh - 1;
+					const int hwin = pipe.acquire(l, convJobs);   // whole head history: (Kh - 1) * Kd frames (also syncs the team)
+					const int Hh = (Kh - 1) * A.Kd;
 					for (int k = 0; k < Kh; k++)
 					{
-						const int D = Hh - k;
+						const int D = Hh - k * A.Kd;
 						int src[RW];
 #pragma unroll
 						for (int r = 0; r < RW; r++) src[r] = (fr[r] >= D) ? (fr[r] - D) : (hwin + Hh - D + fr[r]);

@@ -238,12 +238,12 @@ namespace nab200
 #pragma unroll
 						for (int c = 0; c < C; c++) hc[c * kStr + t] = head[c];
 						__syncthreads();
-						const int Hh = Kh - 1, HLp = A.headLp;
+						const int Hh = (Kh - 1) * A.Kd, HLp = A.headLp;
 						const float* __restrict__ hring = cx.st + A.headRingOff;
 						const int hhd = cx.hd[A.headRingIdx];
 						for (int k = 0; k < Kh; k++)
 						{
-							const int D = Hh - k;
+							const int D = Hh - k * A.Kd;
 							int idx = hhd - D + t;
 							if (idx < 0) idx += HLp;
 							const bool fromCall = t >= D;

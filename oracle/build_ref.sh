@@ -43,6 +43,22 @@ else
   rm -f "$OUT"/obj_*.o
   echo "$NEW" > "$STAMP"
 fi
+# A third build WITH the reference's NAM Core back-end (BUILD_NAMCORE, NeuralAudio/CMakeLists.txt:14-17,145-171): what the reference itself
+# runs for the A2 files its Internal path refuses (NeuralModel.cpp:365-380), e.g. an A2 model on a host at 96 kHz.  Used only to
+# generate golden vectors for those cases (tests/golden/make_golden.py --a2-oversampled-only with NA_REF_NAMCORE=1).
+NAMC="$R/deps/NeuralAmpModelerCore"
+if [ -d "$NAMC/NAM" ] && { [ ! -f "$OUT/libna_ref_namcore.so" ] || [ "$(cat "$STAMP.namcore" 2>/dev/null)" != "$NEW" ]; }; then
+  pids=""; i=0
+  for s in $SRCS "$HERE/ref_extra.cpp" $NAMC/NAM/activations.cpp $NAMC/NAM/conv1d.cpp $NAMC/NAM/get_dsp.cpp $NAMC/NAM/ring_buffer.cpp $NAMC/NAM/lstm.cpp \
+           $NAMC/NAM/dsp.cpp $NAMC/NAM/container.cpp $NAMC/NAM/wavenet/slimmable.cpp $NAMC/NAM/wavenet/model.cpp $NAMC/NAM/wavenet/a2_fast.cpp; do
+    $CXX $FLAGS -DBUILD_NAMCORE -DNAM_SAMPLE_FLOAT -isystem $NAMC -march=x86-64-v3 -mtune=generic -c "$s" -o "$OUT/obj_nc_$i.o" &
+    pids="$pids $!"; i=$((i+1))
+  done
+  for p in $pids; do wait $p; done
+  $CXX -shared -o "$OUT/libna_ref_namcore.so" "$OUT"/obj_nc_*.o -Wl,--version-script="$HERE/ref_exports.map" -Wl,-Bsymbolic -lpthread
+  rm -f "$OUT"/obj_nc_*.o
+  echo "$NEW" > "$STAMP.namcore"
+fi
 # stage fixtures (read in place from the reference, never committed)
 cp -u "$R"/Utils/Models/*.nam "$R"/Utils/Models/*.json "$OUT/models/" 2>/dev/null || true
 for f in wavenet.nam wavenet_a1_standard.nam lstm.nam; do

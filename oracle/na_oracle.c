@@ -52,6 +52,8 @@ typedef struct
 	int activation;   /* 0 = Tanh, 1 = LeakyReLU(0.01) */
 	const int* kernel_sizes;
 	const int* dilations;
+	int head_dilation; /* 1; an A2 model on a faster host gets the oversampling factor (OversampleNAMConfig, NeuralModel.cpp:122-127: the reference's
+	                      Internal path then refuses the file and NAM Core runs it -- the port follows the same network with the dilated head) */
 } na_oracle_array_desc;
 
 /* One dilated conv's history: the last (K-1)*d input columns, frame-major like ChannelBuffer.h:116.
@@ -77,7 +79,7 @@ typedef struct
 
 typedef struct
 {
-	int in_size, C, H, Kh, head_bias, L, act;
+	int in_size, C, H, Kh, Kd, head_bias, L, act;
 	float* reW;     /* [C][in_size], no bias                                   WaveNet.h:521 */
 	layer_t* layers;
 	float* headW;   /* [k][H][C] */
@@ -178,7 +180,7 @@ void* na_oracle_wavenet_create(int n_arrays, const na_oracle_array_desc* desc, c
 	{
 		const na_oracle_array_desc* D = &desc[a];
 		array_t* A = &m->arrays[a];
-		A->in_size = D->input_size; A->C = D->channels; A->H = D->head_size; A->Kh = D->head_kernel;
+		A->in_size = D->input_size; A->C = D->channels; A->H = D->head_size; A->Kh = D->head_kernel; A->Kd = D->head_dilation > 0 ? D->head_dilation : 1;
 		A->head_bias = D->head_bias; A->L = D->num_layers; A->act = D->activation;
 		if (A->C > m->max_c) m->max_c = A->C;
 		if (A->H > m->max_c) m->max_c = A->H;
@@ -210,7 +212,7 @@ void* na_oracle_wavenet_create(int n_arrays, const na_oracle_array_desc* desc, c
 		for (int i = 0; i < A->H; i++) for (int j = 0; j < A->C; j++) for (int k = 0; k < A->Kh; k++)
 			A->headW[((size_t)k * A->H + i) * A->C + j] = *w++;
 		if (A->head_bias) for (int i = 0; i < A->H; i++) A->headB[i] = *w++;
-		hist_alloc(&A->headHist, A->C, A->Kh - 1);   /* head dilation 1 */
+		hist_alloc(&A->headHist, A->C, (A->Kh - 1) * A->Kd);
 		A->x = (float*)calloc((size_t)A->C, sizeof(float));
 		A->headOut = (float*)calloc((size_t)A->H, sizeof(float));
 	}
@@ -257,7 +259,7 @@ static void array_frame(array_t* A, const float* in, float cond, float* head, in
 	}
 	/* head conv over the summed head (:658-660) */
 	if (prewarm) hist_fill(&A->headHist, head);                               /* :627-628 */
-	conv_frame(C, A->H, A->Kh, 1, A->headW, A->head_bias ? A->headB : NULL, &A->headHist, head, A->headOut);
+	conv_frame(C, A->H, A->Kh, A->Kd, A->headW, A->head_bias ? A->headB : NULL, &A->headHist, head, A->headOut);
 	if (!prewarm) hist_push(&A->headHist, head);
 }
 

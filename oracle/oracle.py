@@ -37,7 +37,7 @@ def build(force=False):
 class _ArrayDesc(ctypes.Structure):
     _fields_ = [("input_size", ctypes.c_int), ("channels", ctypes.c_int), ("head_size", ctypes.c_int),
                 ("head_kernel", ctypes.c_int), ("head_bias", ctypes.c_int), ("num_layers", ctypes.c_int),
-                ("activation", ctypes.c_int), ("kernel_sizes", _c_int_p), ("dilations", _c_int_p)]
+                ("activation", ctypes.c_int), ("kernel_sizes", _c_int_p), ("dilations", _c_int_p), ("head_dilation", ctypes.c_int)]
 
 
 _port_lib = None
@@ -111,10 +111,13 @@ def wavenet_arrays_from_config(config, version):
     arrays = []
     if len(layers) == 1 and "kernel_sizes" in layers[0]:
         lc = layers[0]
-        if list(lc["dilations"]) != A2_DILATIONS or lc["channels"] not in (3, 8):
+        if lc["channels"] not in (3, 8) or len(lc["dilations"]) != len(lc["kernel_sizes"]):
             raise ValueError("A2 WaveNet outside the Internal static set (reference would use NAM Core)")
-        arrays.append(dict(input_size=1, channels=int(lc["channels"]), head_size=1, head_kernel=16, head_bias=1,
-                           kernel_sizes=list(A2_KERNEL_SIZES), dilations=list(A2_DILATIONS), activation=1))
+        # (standard dilations: the reference's static A2; any other list - e.g. doubled by OversampleNAMConfig together with the
+        # head dilation - is the same network with other delays: the reference runs it on NAM Core, the port follows its arithmetic)
+        arrays.append(dict(input_size=1, channels=int(lc["channels"]), head_size=1, head_kernel=int(lc["head"].get("kernel_size", 16)), head_bias=1,
+                           kernel_sizes=[int(k) for k in lc["kernel_sizes"]], dilations=[int(d) for d in lc["dilations"]], activation=1,
+                           head_dilation=int(lc["head"].get("head_dilation", 1))))
         return arrays
     for lc in layers:
         n = len(lc["dilations"])
@@ -165,7 +168,7 @@ class PortModel:
                 ds = (ctypes.c_int * len(a["dilations"]))(*a["dilations"])
                 self._keep += [ks, ds]
                 descs[i] = _ArrayDesc(a["input_size"], a["channels"], a["head_size"], a["head_kernel"], a["head_bias"],
-                                      len(a["dilations"]), a["activation"], ks, ds)
+                                      len(a["dilations"]), a["activation"], ks, ds, a.get("head_dilation", 1))
             h = self._L.na_oracle_wavenet_create(len(arrays), descs, w.ctypes.data_as(_c_float_p), int(w.size))
             if not h:
                 raise RuntimeError("Wrong number of weights")   # WaveNet.h:704-709
@@ -267,6 +270,10 @@ def _cpu_has_avx512():
 
 
 def ref_lib_path():
+    # NA_REF_NAMCORE=1: the build that carries the reference's NAM Core back-end (golden vectors of the files its Internal path refuses)
+    nc = os.path.join(REF_DIR, "libna_ref_namcore.so")
+    if os.environ.get("NA_REF_NAMCORE", "") == "1" and os.path.exists(nc):
+        return nc
     v4 = os.path.join(REF_DIR, "libna_ref_v4.so")
     if _cpu_has_avx512() and os.path.exists(v4) and os.environ.get("NA_REF_ISA", "") != "v3":
         return v4

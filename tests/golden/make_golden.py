@@ -65,6 +65,44 @@ def a2_config(c):
             "head": None, "head_scale": 1.0, "in_channels": 1}
 
 
+def a2_config_namcore(c):
+    """The same A2 architecture with every key NAM Core's own parser reads (the fixture's layout, BossWN-a2.nam): needed where the
+    reference hands the file to NAM Core (an A2 model on a host at 96 kHz: OversampleNAMConfig, NeuralModel.cpp:92-130,365-380)."""
+    cfg = a2_config(c)
+    lc = cfg["layers"][0]
+    lc["head1x1"] = {"active": False, "out_channels": 1, "groups": 1}
+    for k in ("conv_pre_film", "conv_post_film", "input_mixin_pre_film", "input_mixin_post_film", "activation_pre_film",
+              "activation_post_film", "layer1x1_post_film", "head1x1_post_film"):
+        lc[k] = {"active": False, "shift": True, "groups": 1}
+    del cfg["in_channels"]
+    return cfg
+
+
+def a2_oversampled_vectors(tmpdir):
+    """A2 models on a host at 96 kHz.  The reference doubles the dilations and the head dilation, its Internal path refuses the
+    result and NAM Core runs it; run with NA_REF_NAMCORE=1 so that oracle/_ref/libna_ref_namcore.so (the reference built WITH
+    its NAM Core back-end) produces the vectors."""
+    made = []
+    rng = np.random.default_rng(20261020)
+    for j, (name, c) in enumerate([("a2_full", 8), ("a2_lite", 3)]):
+        cfg = a2_config_namcore(c)
+        w = synth_wavenet_weights(rng, a2_num_weights(c), 1.0 / np.sqrt(6 * c), 1.0)
+        case = {"version": "0.7.0", "architecture": "WaveNet", "config": cfg, "weights": w, "sample_rate": 48000,
+                "metadata": {"loudness": -12.0, "name": "syn-" + name + "-96k"}}
+        path = os.path.join(tmpdir, name + "_nc.nam")
+        with open(path, "w") as f:
+            f.write(nam_text(case))
+        x = np.random.default_rng(555 + j).uniform(-1.0, 1.0, N).astype(np.float32)
+        y, dc, info = run_ref(path, x, external_sample_rate=96000)
+        meta = {k: v for k, v in case.items() if k != "weights"}
+        out = os.path.join(HERE, "syn_%s_sr96000.npz" % name)
+        np.savez_compressed(out, x=x, y=y, dc=dc, weights=np.asarray(w, dtype=np.float32), model=json.dumps(meta),
+                            info=json.dumps(info), external_sample_rate=np.int32(96000))
+        made.append(out)
+        os.remove(path)
+    return made
+
+
 def a2_num_weights(c):
     n = c + 1
     for k in O.A2_KERNEL_SIZES:
@@ -200,6 +238,12 @@ def main():
     O.build()
     tmpdir = os.path.join(HERE, "_tmp")
     os.makedirs(tmpdir, exist_ok=True)
+    if "--a2-oversampled-only" in sys.argv:
+        for m in a2_oversampled_vectors(tmpdir):
+            z = np.load(m)
+            print("%-48s |y|max=%.4f std=%.4f dc=%.6g info=%s" % (os.path.basename(m), np.abs(z["y"]).max(), z["y"].std(), z["dc"][-1], str(z["info"])))
+        os.rmdir(tmpdir)
+        return
     if "--oversampled-only" in sys.argv:
         for m in oversampled_vectors(tmpdir):
             z = np.load(m)

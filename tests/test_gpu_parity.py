@@ -572,7 +572,7 @@ def test_full_size_config_properties(na, O, tmp_path):
     assert torch.equal(torch.flip(yr, dims=[1]), yd)
 
 
-@pytest.mark.parametrize("name,streams", [("syn_a1_standard_sr96000", 20), ("syn_a1_nano_sr96000", 33)])
+@pytest.mark.parametrize("name,streams", [("syn_a1_standard_sr96000", 20), ("syn_a1_nano_sr96000", 33), ("syn_a2_full_sr96000", 21), ("syn_a2_lite_sr96000", 9)])
 def test_oversampled_batch_matches_oracle(na, O, name, streams, tmp_path):
     """Host at 96 kHz: every dilation doubles (OversampleNAMConfig, NeuralModel.cpp:92-130), the receptive field becomes 8184
     and the rings twice as long; the batch kernels run the doubled dilations as run-time values."""

@@ -122,6 +122,31 @@ def test_unsupported_models_fail_loudly(na, tmp_path):
         na.describe_model_file(str(p3))
 
 
+def test_a2_with_other_delays_loads_and_other_nam_core_features_do_not(na, tmp_path):
+    """SURVEY 8(f4), the part built: an A2 file whose only non-standard property is its timing (what OversampleNAMConfig makes of
+    an A2 model on a 96 kHz host: dilations and head dilation doubled, NeuralModel.cpp:92-130) is NAM Core's in the reference and
+    loads here with NAM Core's receptive field; every other NAM-Core-only feature is still refused loudly."""
+    g = load_golden(golden_files("syn_a2_full_sr96000")[0])
+    mf = model_file_for(g, tmp_path)
+    d48 = na.describe_model_file(mf, 48000)
+    assert d48["static"] is True and d48["receptive_field"] == 6346 and d48["kernel"] == "tcgen05_fp16_pairs"
+    d96 = na.describe_model_file(mf, 96000)
+    assert d96["static"] is False and d96["receptive_field"] == 2 * 6346 and d96["ring_lp"][-1] == 32     # head history: 15 x 2 frames
+    assert g["info"]["rf"] == 2 * 6346 + 1      # NAMModel::GetReceptiveFieldSize of the reference for the same load
+    base = json.loads(json.dumps(g["model"]))
+    base["weights"] = [float(x) for x in g["weights"]]
+    for key, val, why in (("head1x1", {"active": True, "out_channels": 1, "groups": 1}, "non-standard"),
+                          ("gating_mode", ["gated"] * 23, "non-standard"),
+                          ("conv_pre_film", {"active": True, "shift": True, "groups": 1}, "non-standard"),
+                          ("bottleneck", 4, "non-standard"), ("groups_input", 2, "non-standard")):
+        d = json.loads(json.dumps(base))
+        d["config"]["layers"][0][key] = val
+        p = tmp_path / ("a2_%s.nam" % key)
+        p.write_text(json.dumps(d))
+        with pytest.raises(na.NeuralAudioError, match=why):
+            na.describe_model_file(str(p))
+
+
 def test_oversampling_leaves_the_static_path(na, tmp_path):
     # OversampleNAMConfig (NeuralModel.cpp:92-130): at 96 kHz the dilations double, the file stops being an official shape
     g = load_golden(golden_files("syn_a1_nano")[0])
