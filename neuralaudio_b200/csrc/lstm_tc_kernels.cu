@@ -368,6 +368,7 @@ namespace nab200
 							asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(in + ss * inSS + t * inFS) : "memory");
 						else *dst = 0.0f;
 					}
+					cp_async_commit();   // (wait_group at the end of the tile counts committed groups only)
 				}
 				for (int f = 0; f < tn; f++)
 				{

@@ -11,7 +11,7 @@ ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import neuralaudio_b200 as na
-from conftest import golden_files, load_golden, model_file_for
+from conftest import golden_files, load_golden, model_file_for, external_sample_rate_of
 
 DEFAULT = ("syn_a1_standard.", "syn_a1_nano.", "syn_a2_full", "syn_dyn_20x10", "syn_lstm_1x16", "syn_lstm_2x8", "syn_dyn_lstm_3x18")
 for name in (sys.argv[1:] or DEFAULT):
@@ -19,6 +19,7 @@ for name in (sys.argv[1:] or DEFAULT):
     mf = model_file_for(g, pathlib.Path(tempfile.mkdtemp()))
     S = 70
     ld = na.NeuralModelLoader()
+    ld.SetExternalSampleRate(external_sample_rate_of(g))
     ld.SetDefaultNumStreams(S)
     m = ld.CreateFromFile(mf)
     x = np.random.default_rng(1).uniform(-0.5, 0.5, (3, S, 100)).astype(np.float32)
