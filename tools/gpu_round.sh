@@ -16,7 +16,7 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --c
 # full capture of the dominant kernel: skip the S = 1 launches of the prewarm settle pass (receptive field / 128 + 2 of them)
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:wavenet_h -s 36 -c 1 -f -o gpurun_out/prof_wavenet python bench.py --steps 4 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full.out 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:lstm_fwd -s 20 -c 1 -f -o gpurun_out/prof_lstm python bench.py --workload lstm_1x16 --steps 4 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full_lstm.out 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:wavenet_h -s 120 -c 1 -f -o gpurun_out/prof_a2 python bench.py --workload a2_full --steps 4 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full_a2.out 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:wavenet_h -s 60 -c 1 -f -o gpurun_out/prof_a2 python bench.py --workload a2_full --steps 4 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full_a2.out 2>&1
 # the tensor-core LSTM kernel: 2x16 at 8192 streams is its automatic choice (skip the 2048-step prewarm launch)
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:lstm_tc -s 1 -c 1 -f -o gpurun_out/prof_lstm_tc python tools/lstm_tc_check.py 8192 syn_lstm_2x16 > gpurun_out/ncu_full_lstm_tc.out 2>&1
 timeout 300 python tools/shape_table.py > gpurun_out/shape_table.txt 2>&1; tail -12 gpurun_out/shape_table.txt
