@@ -141,11 +141,12 @@ NA_EXTERN int NA_DescribeModelFile(const wchar_t* modelPath, int externalSampleR
  *   "use_one": 1 (default) single-stream calls of small WaveNets on the one-CTA kernel, 0 the batched kernels for every call;
  *   "lstm_kernel": 0 (default) by shape and stream-slot count, 1 gate rows in registers, 2 lane = stream with shared-memory
  *              matrices, 3 run-time-shaped, 4 tcgen05 gates (one or two layers, up to 32 units);
+ *   "lstm_tc_sets": 128-stream sets per CTA of the tcgen05 LSTM kernel, 1 or 2 (0 = two once the slots need more than one CTA per SM);
  *   "zero_copy_kfloats": blocking host calls of up to this many thousand samples run on the caller's page-locked buffers
  *              directly (default: every size; 0 = always staged through the copy engines);
  *   "async_zero_copy": 1 = NA_ProcessBatchAsync runs zero-copy too (default 0: staged, overlapped with the neighbouring calls).
  * The same knobs can be preset through NAB200_USE_TC / NAB200_H_CTAS / NAB200_TS_SPLIT / NAB200_USE_TMA / NAB200_MAX_GRID_CTAS /
- * NAB200_USE_ONE / NAB200_LSTM_KERNEL / NAB200_ZERO_COPY_KFLOATS / NAB200_ASYNC_ZERO_COPY. */
+ * NAB200_USE_ONE / NAB200_LSTM_KERNEL / NAB200_LSTM_TC_SETS / NAB200_ZERO_COPY_KFLOATS / NAB200_ASYNC_ZERO_COPY. */
 NA_EXTERN int NA_SetOption(const char* name, int value);
 /* the same knobs for the models ONE loader builds (copied into each model at load; nothing is read from globals at run time) */
 NA_EXTERN void NA_SetLoaderOption(NeuralModelLoader* loader, const char* name, int value);

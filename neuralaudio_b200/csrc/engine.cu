@@ -24,6 +24,7 @@ namespace nab200
 			env("NAB200_USE_TMA", v.useTma);
 			env("NAB200_MAX_GRID_CTAS", v.maxGridCtas);
 			env("NAB200_LSTM_KERNEL", v.lstmKernel);
+			env("NAB200_LSTM_TC_SETS", v.lstmTcSets);
 			env("NAB200_ASYNC_ZERO_COPY", v.asyncZeroCopy);
 			env("NAB200_ZERO_COPY_KFLOATS", v.zeroCopyKFloats);
 			return v;
@@ -43,6 +44,7 @@ namespace nab200
 		else if (strcmp(name, "use_one") == 0) { prev = o.useOne; o.useOne = value; }
 		else if (strcmp(name, "max_grid_ctas") == 0) { prev = o.maxGridCtas; o.maxGridCtas = value; }
 		else if (strcmp(name, "lstm_kernel") == 0) { prev = o.lstmKernel; o.lstmKernel = value; }
+		else if (strcmp(name, "lstm_tc_sets") == 0) { prev = o.lstmTcSets; o.lstmTcSets = value; }
 		else if (strcmp(name, "async_zero_copy") == 0) { prev = o.asyncZeroCopy; o.asyncZeroCopy = value; }
 		else if (strcmp(name, "zero_copy_kfloats") == 0) { prev = o.zeroCopyKFloats; o.zeroCopyKFloats = value; }
 		return prev;
@@ -702,6 +704,7 @@ namespace nab200
 		a.zeroInput = true;
 		a.generic = opt.useTc < 0;
 		a.kernel = opt.lstmKernel;
+		a.tcSets = opt.lstmTcSets;
 		a.numSMs = numSMs;
 		a.pickS = (int)numStreams;   // the template advances under the arithmetic its slots will run
 		a.stream = stream;
@@ -729,6 +732,7 @@ namespace nab200
 		a.zeroInput = false;
 		a.generic = opt.useTc < 0;
 		a.kernel = opt.lstmKernel;
+		a.tcSets = opt.lstmTcSets;
 		a.numSMs = numSMs;
 		a.pickS = (int)numStreams;
 		a.stream = stream;

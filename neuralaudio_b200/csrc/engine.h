@@ -33,6 +33,7 @@ namespace nab200
 		// kernels of the neighbouring calls (the default: the staged pipeline runs the kernels at their device-resident speed, which
 		// wins once calls are queued back to back: A1 Standard 2.65 vs 2.14 Gsamples/s; only A1 Nano gains from zero-copy, 3.5 vs 2.8)
 		int asyncZeroCopy = 0;
+		int lstmTcSets = 0;     // tensor-core LSTM kernel: 128-stream sets per CTA (0: two once the slots need more than one CTA per SM)
 		int lstmKernel = 0;     // LSTM kernel: 0 automatic, 1 gate rows in registers, 2 lane = stream (matrices in shared memory), 3 run-time-shaped, 4 tensor cores
 	};
 	Options& GetOptions();

@@ -40,31 +40,36 @@ namespace nab200
 
 	// (A CTA of 64 streams -- TMEM lane quarters 0 and 1 only -- was measured for batches that leave SMs without a CTA: no gain.  A warp
 	// reaches only the lane quarter of its own scheduler, so half the SM's fp32 pipes would sit idle, and those pipes are the bound.)
-	template <int UPT, int NWG, int L>
+	// SETS = independent 128-stream sets per CTA (1 or 2).  With two, a worker thread owns row r of both and alternates between them:
+	// one set's GEMM, commit and hand-off run behind the other set's activations (batches of more than one CTA per SM).
+	template <int UPT, int NWG, int L, int SETS>
 	struct TcCfg
 	{
 		static constexpr int Ut = UPT * NWG;              // hidden units, padded
 		static constexpr int N = 4 * Ut;                  // gate columns of one layer
-		static constexpr int kRows = 128;                 // streams per CTA
+		static constexpr int kRows = 128;                 // streams per set
 		static constexpr int kWorkers = 128 * NWG;
 		static constexpr int kThreads = kWorkers + 32;
 		static constexpr int kIssuerWarp = 4 * NWG;
-		static constexpr int kIssueBar = kWorkers + 32;     // threads on the workers -> issuer barrier
+		static constexpr int kIssueBar = kWorkers + 32;     // threads on a workers -> issuer barrier
 		__host__ __device__ static constexpr int ks(int l) { return 1 + (l + 1) * Ut / 8; }      // K steps of layer l: [x, 1 | h_0 .. h_l]
-		static constexpr uint32_t kABytes = 2u * ks(L - 1) * kTcGroupBytes;
+		static constexpr uint32_t kABytes = 2u * ks(L - 1) * kTcGroupBytes;   // one set's A operand
 		static constexpr uint32_t kTileBytes = 2u * N * 16u;                  // [2 k groups][N][8 halves]
 		__host__ __device__ static constexpr uint32_t bBytes(int l) { return (uint32_t)ks(l) * 2u * kTileBytes; }
-		static constexpr uint32_t kB0 = kABytes;
+		static constexpr uint32_t kB0 = SETS * kABytes;
 		static constexpr uint32_t kB1 = kB0 + bBytes(0);
-		static constexpr uint32_t kTin = kB1 + (L == 2 ? bBytes(1) : 0u);     // [2][tile][128] floats
+		static constexpr uint32_t kTin = kB1 + (L == 2 ? bBytes(1) : 0u);     // per set [2][tile][128] floats
 		// frame strides of the staged tiles, odd in banks: the tile is written stream-major by the steps and read frame-major by a
 		// [stream][frame] batch's coalesced copies (and the other way round), both conflict-free
 		static constexpr int kTinStride = kRows + 1, kTprodStride = NWG * kRows + 1;
-		static constexpr uint32_t kTprod = kTin + 2u * kTcTile * kTinStride * 4u;   // [tile][NWG][128] floats
-		static constexpr uint32_t kBars = ((kTprod + (uint32_t)kTcTile * kTprodStride * 4u + 15u) & ~15u);
+		static constexpr uint32_t kTinSet = 2u * kTcTile * kTinStride * 4u;
+		static constexpr uint32_t kTprod = kTin + SETS * kTinSet;             // per set [tile][NWG][128] floats
+		static constexpr uint32_t kTprodSet = (uint32_t)kTcTile * kTprodStride * 4u;
+		static constexpr uint32_t kBars = ((kTprod + SETS * kTprodSet + 15u) & ~15u);   // [set][layer] mbarriers, then the TMEM slot
 		static constexpr uint32_t kSmem = kBars + 64u;
-		static constexpr int kTmemCols = L * N <= 32 ? 32 : L * N <= 64 ? 64 : L * N <= 128 ? 128 : 256;
-		static_assert(Ut % 8 == 0 && L * N <= 256 && (L == 1 || L == 2)  && kThreads <= 1024, "shape");
+		static constexpr int kCols = SETS * L * N;
+		static constexpr int kTmemCols = kCols <= 32 ? 32 : kCols <= 64 ? 64 : kCols <= 128 ? 128 : kCols <= 256 ? 256 : 512;
+		static_assert(Ut % 8 == 0 && kCols <= 512 && (L == 1 || L == 2) && (SETS == 1 || SETS == 2) && kThreads <= 1024, "shape");
 	};
 
 	// weight of layer l that multiplies element e of K step ks, for gate q of unit u (zero where the layer has no such input)
@@ -87,10 +92,10 @@ namespace nab200
 		return __ldg(Wg + M.wOff[l] + (size_t)(q * colsP + col) * G + u);
 	}
 
-	template <int UPT, int NWG, int L>
+	template <int UPT, int NWG, int L, int SETS>
 	__device__ __forceinline__ void tc_build_b(const LstmModelDev& M, const float* __restrict__ Wg, unsigned char* smem, int l, int tid)
 	{
-		using C = TcCfg<UPT, NWG, L>;
+		using C = TcCfg<UPT, NWG, L, SETS>;
 		unsigned char* B = smem + (l == 0 ? C::kB0 : C::kB1);
 		const int Ks = C::ks(l);
 		for (int i = tid; i < Ks * C::N; i += C::kThreads)
@@ -214,7 +219,7 @@ namespace nab200
 		w2 |= 0x3C000000u;
 	}
 
-	constexpr int kTcBarIssue = 1, kTcBarWork = 2;
+	constexpr int kTcBarIssue = 1, kTcBarWork = 3;   // issue barriers: one per set (ids 1, 2)
 
 	// cycle stamps of one worker warp (timing builds only): [0] enter wait, [1] MMA done, [2] gates loaded, [3] cell + stores done, [4] arrived
 #ifdef NAB_TC_TIMING
@@ -223,35 +228,36 @@ namespace nab200
 #define NAB_TC_STAMP(i) do { } while (0)
 #endif
 
-	template <int UPT, int NWG, int L>
-	__global__ void __launch_bounds__(TcCfg<UPT, NWG, L>::kThreads, (UPT <= 4 && TcCfg<UPT, NWG, L>::kThreads <= 544) ? 2 : 1)
+	template <int I> struct TcInt { static constexpr int value = I; };
+
+	template <int UPT, int NWG, int L, int SETS>
+	__global__ void __launch_bounds__(TcCfg<UPT, NWG, L, SETS>::kThreads, (SETS == 1 && UPT <= 4 && TcCfg<UPT, NWG, L, SETS>::kThreads <= 544) ? 2 : 1)
 		lstm_tc_kernel(const __grid_constant__ LstmModelDev M, const float* __restrict__ Wg, float* __restrict__ state, const float* in,
 			float* out, long long inSS, long long inFS, long long outSS, long long outFS, int S, int n, int zeroInput)
 	{
-		using C = TcCfg<UPT, NWG, L>;
+		using C = TcCfg<UPT, NWG, L, SETS>;
 		extern __shared__ __align__(128) unsigned char smem[];
 		const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-		const uint32_t sA = smem_u32(smem);
-		const uint32_t sB0 = sA + C::kB0, sB1 = sA + C::kB1;
-		float* const tin = reinterpret_cast<float*>(smem + C::kTin);
-		float* const tprod = reinterpret_cast<float*>(smem + C::kTprod);
-		const uint32_t bar0 = sA + C::kBars, bar1 = bar0 + 8u;
-		uint32_t* const tmemSlot = reinterpret_cast<uint32_t*>(smem + C::kBars + 16);
+		const uint32_t sA0 = smem_u32(smem);
+		const uint32_t sB0 = sA0 + C::kB0, sB1 = sA0 + C::kB1;
+		const uint32_t bars = sA0 + C::kBars;                        // bar(set, layer) = bars + 8 * (2 * set + layer)
+		uint32_t* const tmemSlot = reinterpret_cast<uint32_t*>(smem + C::kBars + 32);
 		constexpr int kRows = C::kRows;
-		const long long base = (long long)blockIdx.x * kRows;
+		const long long base0 = (long long)blockIdx.x * (kRows * SETS);
 		const bool worker = warp < C::kIssuerWarp;
-		const int g = warp >> 2, row = ((warp & 3) << 5) | lane;    // workers: warpgroup, stream of the CTA (= TMEM lane)
-		const long long s = base + row;
-		const bool live = worker && s < S;
+		const int g = warp >> 2, row = ((warp & 3) << 5) | lane;    // workers: warpgroup, stream of the set (= TMEM lane)
 		const int u0 = g * UPT;                                     // first hidden unit of this thread
+		auto set_a = [&](int set) { return sA0 + (uint32_t)set * C::kABytes; };
+		auto set_tin = [&](int set) { return reinterpret_cast<float*>(smem + C::kTin + set * C::kTinSet); };
+		auto set_tprod = [&](int set) { return reinterpret_cast<float*>(smem + C::kTprod + set * C::kTprodSet); };
+		auto bar_of = [&](int set, int l) { return bars + 8u * (uint32_t)(2 * set + l); };
 
 		// ---- set-up: B operands, barriers, TMEM, the streams' state into registers and into A ----
-		tc_build_b<UPT, NWG, L>(M, Wg, smem, 0, tid);
-		if (L == 2) tc_build_b<UPT, NWG, L>(M, Wg, smem, 1, tid);
+		tc_build_b<UPT, NWG, L, SETS>(M, Wg, smem, 0, tid);
+		if (L == 2) tc_build_b<UPT, NWG, L, SETS>(M, Wg, smem, 1, tid);
 		if (tid == 0)
 		{
-			mbar_init(bar0, 1);
-			mbar_init(bar1, 1);
+			for (int i = 0; i < 4; i++) mbar_init(bars + 8u * (uint32_t)i, 1);
 			asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 		}
 		if (warp == C::kIssuerWarp)
@@ -259,44 +265,51 @@ namespace nab200
 			tmem_alloc<C::kTmemCols>(smem_u32(tmemSlot));
 			tmem_relinquish();
 		}
-		float c[L][UPT], h[L][UPT];
-		// A row address of this thread's units in layer l's a1 groups
-		const uint32_t aRow = sA + (uint32_t)row * 16u + (uint32_t)(u0 & 7) * 2u;
-		auto a_addr = [&](int l) { return aRow + 2u * (uint32_t)(1 + (l * C::Ut + u0) / 8) * kTcGroupBytes; };
+		float c[SETS][L][UPT], h[SETS][L][UPT];
+		// A row address of this thread's units in layer l's a1 groups (inside a set's operand)
+		const uint32_t aRow = (uint32_t)row * 16u + (uint32_t)(u0 & 7) * 2u;
+		auto a_addr = [&](int set, int l) { return set_a(set) + aRow + 2u * (uint32_t)(1 + (l * C::Ut + u0) / 8) * kTcGroupBytes; };
 		if (worker)
 		{
-			const float* st = state + (size_t)(live ? s : 0) * M.stateStride;
 #pragma unroll
-			for (int l = 0; l < L; l++)
+			for (int set = 0; set < SETS; set++)
 			{
+				const long long s = base0 + (long long)set * kRows + row;
+				const bool live = s < S;
+				const float* st = state + (size_t)(live ? s : 0) * M.stateStride;
 #pragma unroll
-				for (int j = 0; j < UPT; j++)
+				for (int l = 0; l < L; l++)
 				{
-					const bool ok = live && u0 + j < M.G;
-					h[l][j] = ok ? st[(2 * l) * M.G + u0 + j] : 0.0f;
-					c[l][j] = ok ? st[(2 * l + 1) * M.G + u0 + j] : 0.0f;
+#pragma unroll
+					for (int j = 0; j < UPT; j++)
+					{
+						const bool ok = live && u0 + j < M.G;
+						h[set][l][j] = ok ? st[(2 * l) * M.G + u0 + j] : 0.0f;
+						c[set][l][j] = ok ? st[(2 * l + 1) * M.G + u0 + j] : 0.0f;
+					}
+					tc_store_h<UPT>(a_addr(set, l), h[set][l]);
 				}
-				tc_store_h<UPT>(a_addr(l), h[l]);
-			}
-			if (g == 0)
-			{
-				const float x0 = (live && !zeroInput) ? in[s * inSS] : 0.0f;
-				uint32_t w1, w2;
-				tc_input_words(x0, w1, w2);
-				sts128(sA + (uint32_t)row * 16u, w1, 0u, 0u, 0u);
-				sts128(sA + kTcGroupBytes + (uint32_t)row * 16u, w2, 0u, 0u, 0u);
-			}
-			// tile 0 of the look-ahead inputs: tin[0][f][r] = x(1 + f)
-			for (int i = tid; i < kTcTile * kRows; i += C::kWorkers)
-			{
-				int r, f;
-				if (inFS == 1 || zeroInput) { r = i / kTcTile; f = i % kTcTile; }
-				else { r = i % kRows; f = i / kRows; }
-				const long long ss = base + r;
-				float v = 0.0f;
-				if (!zeroInput && ss < S && 1 + f < n) v = in[ss * inSS + (long long)(1 + f) * inFS];
-				tin[f * C::kTinStride + r] = v;
-				tin[kTcTile * C::kTinStride + f * C::kTinStride + r] = 0.0f;
+				if (g == 0)
+				{
+					const float x0 = (live && !zeroInput) ? in[s * inSS] : 0.0f;
+					uint32_t w1, w2;
+					tc_input_words(x0, w1, w2);
+					sts128(set_a(set) + (uint32_t)row * 16u, w1, 0u, 0u, 0u);
+					sts128(set_a(set) + kTcGroupBytes + (uint32_t)row * 16u, w2, 0u, 0u, 0u);
+				}
+				// tile 0 of the look-ahead inputs: tin[0][f][r] = x(1 + f)
+				float* const tin = set_tin(set);
+				for (int i = tid; i < kTcTile * kRows; i += C::kWorkers)
+				{
+					int r, f;
+					if (inFS == 1 || zeroInput) { r = i / kTcTile; f = i % kTcTile; }
+					else { r = i % kRows; f = i / kRows; }
+					const long long ss = base0 + (long long)set * kRows + r;
+					float v = 0.0f;
+					if (!zeroInput && ss < S && 1 + f < n) v = in[ss * inSS + (long long)(1 + f) * inFS];
+					tin[f * C::kTinStride + r] = v;
+					tin[kTcTile * C::kTinStride + f * C::kTinStride + r] = 0.0f;
+				}
 			}
 		}
 		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -310,28 +323,38 @@ namespace nab200
 			// =================================== issuer warp ===================================
 			if (lane == 0)
 			{
-				tc_issue_layer<C, 0>(sA, sB0, tm);
-				mma_commit(bar0);
+#pragma unroll
+				for (int set = 0; set < SETS; set++)
+				{
+					tc_issue_layer<C, 0>(set_a(set), sB0, tm + (uint32_t)(set * L * C::N));
+					mma_commit(bar_of(set, 0));
+				}
 			}
 			__syncwarp();
-			for (int t = 0; t < n; t++)
+			auto serve = [&](auto setc, int t)
 			{
-				nbar_sync<kTcBarIssue, C::kIssueBar>();   // h_0(t) and x(t + 1) are in A (and h_1(t - 1), written before it)
+				constexpr int set = decltype(setc)::value;
+				nbar_sync<kTcBarIssue + set, C::kIssueBar>();   // h_0(t) and x(t + 1) of this set are in A (and h_1(t - 1), written before it)
 				fence_after();
 				if (lane == 0)
 				{
 					if (L == 2)
 					{
-						tc_issue_layer<C, 1>(sA, sB1, tm + (uint32_t)C::N);
-						mma_commit(bar1);
+						tc_issue_layer<C, 1>(set_a(set), sB1, tm + (uint32_t)((set * L + 1) * C::N));
+						mma_commit(bar_of(set, 1));
 					}
 					if (t + 1 < n)
 					{
-						tc_issue_layer<C, 0>(sA, sB0, tm);
-						mma_commit(bar0);
+						tc_issue_layer<C, 0>(set_a(set), sB0, tm + (uint32_t)(set * L * C::N));
+						mma_commit(bar_of(set, 0));
 					}
 				}
 				__syncwarp();
+			};
+			for (int t = 0; t < n; t++)
+			{
+				serve(TcInt<0>(), t);
+				if constexpr (SETS == 2) serve(TcInt<1>(), t);
 			}
 		}
 		else
@@ -344,112 +367,119 @@ namespace nab200
 			const float headB = __ldg(Wg + M.headOff + M.G);
 			bool dead = false;
 			int tileIdx = 0;
-#ifdef NAB_TC_TIMING
-			long long tacc[5] = { 0, 0, 0, 0, 0 }, tlast = clock64();
-			const long long tstart = tlast;
-#endif
+			// one layer of one set for step t (frame f of the tile)
+			auto layer = [&](auto setc, auto lc, int t, int f, const float* tcur)
+			{
+				constexpr int set = decltype(setc)::value, l = decltype(lc)::value;
+				uint32_t r[4 * UPT];
+				if (!dead && !mbar_wait(bar_of(set, l), (uint32_t)t & 1u)) dead = true;
+				fence_after();
+				tc_load_gates<4 * UPT>(tmLane + (uint32_t)((set * L + l) * C::N), r);
+				tc_cell<UPT>(r, c[set][l], h[set][l]);
+				tc_store_h<UPT>(a_addr(set, l), h[set][l]);
+				if (l == 0 && g == 0)
+				{
+					uint32_t w1, w2;
+					tc_input_words(tcur[f * C::kTinStride + row], w1, w2);
+					asm volatile("st.shared.b32 [%0], %1;" ::"r"(set_a(set) + (uint32_t)row * 16u), "r"(w1) : "memory");
+					asm volatile("st.shared.b32 [%0], %1;" ::"r"(set_a(set) + kTcGroupBytes + (uint32_t)row * 16u), "r"(w2) : "memory");
+				}
+				asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+				if (l == 0)
+				{
+					fence_before();
+					nbar_arrive<kTcBarIssue + set, C::kIssueBar>();
+				}
+				if (l == L - 1)
+				{
+					// head: out = w_head . h_last + b_head (LSTM.h:184-188): this thread's share of the sum
+					float part = 0.0f;
+#pragma unroll
+					for (int j = 0; j < UPT; j++) part = fmaf(hw[j], h[set][l][j], part);
+					set_tprod(set)[f * C::kTprodStride + g * kRows + row] = part;
+				}
+			};
 			for (int t0 = 0; t0 < n; t0 += kTcTile, tileIdx++)
 			{
 				const int tn = min(kTcTile, n - t0);
-				const float* tcur = tin + (tileIdx & 1) * (kTcTile * C::kTinStride);
+				const int curOff = (tileIdx & 1) * (kTcTile * C::kTinStride), nextOff = ((tileIdx + 1) & 1) * (kTcTile * C::kTinStride);
 				// the next tile's look-ahead inputs, x(t0 + tile + 1 + f), on their way while this tile runs
 				if (!zeroInput && t0 + kTcTile < n)
 				{
-					float* tnext = tin + ((tileIdx + 1) & 1) * (kTcTile * C::kTinStride);
-					for (int i = tid; i < kTcTile * kRows; i += C::kWorkers)
+#pragma unroll
+					for (int set = 0; set < SETS; set++)
 					{
-						int r, f;
-						if (inFS == 1) { r = i / kTcTile; f = i % kTcTile; }
-						else { r = i % kRows; f = i / kRows; }
-						const long long ss = base + r;
-						const long long t = (long long)t0 + kTcTile + 1 + f;
-						float* dst = tnext + f * C::kTinStride + r;
-						if (ss < S && t < n)
-							asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(in + ss * inSS + t * inFS) : "memory");
-						else *dst = 0.0f;
+						float* tnext = set_tin(set) + nextOff;
+						for (int i = tid; i < kTcTile * kRows; i += C::kWorkers)
+						{
+							int r, f;
+							if (inFS == 1) { r = i / kTcTile; f = i % kTcTile; }
+							else { r = i % kRows; f = i / kRows; }
+							const long long ss = base0 + (long long)set * kRows + r;
+							const long long t = (long long)t0 + kTcTile + 1 + f;
+							float* dst = tnext + f * C::kTinStride + r;
+							if (ss < S && t < n)
+								asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(in + ss * inSS + t * inFS) : "memory");
+							else *dst = 0.0f;
+						}
 					}
 					cp_async_commit();   // (wait_group at the end of the tile counts committed groups only)
 				}
 				for (int f = 0; f < tn; f++)
 				{
 					const int t = t0 + f;
-					uint32_t r[4 * UPT];
-					// ---- layer 0 ----
-					NAB_TC_STAMP(0);
-					if (!dead && !mbar_wait(bar0, (uint32_t)t & 1u)) dead = true;
-					NAB_TC_STAMP(1);
-					fence_after();
-					tc_load_gates<4 * UPT>(tmLane, r);
-					NAB_TC_STAMP(2);
-					tc_cell<UPT>(r, c[0], h[0]);
-					tc_store_h<UPT>(a_addr(0), h[0]);
-					if (g == 0)
+					layer(TcInt<0>(), TcInt<0>(), t, f, set_tin(0) + curOff);
+					if constexpr (SETS == 2) layer(TcInt<1>(), TcInt<0>(), t, f, set_tin(1) + curOff);
+					if constexpr (L == 2)
 					{
-						uint32_t w1, w2;
-						tc_input_words(tcur[f * C::kTinStride + row], w1, w2);
-						asm volatile("st.shared.b32 [%0], %1;" ::"r"(sA + (uint32_t)row * 16u), "r"(w1) : "memory");
-						asm volatile("st.shared.b32 [%0], %1;" ::"r"(sA + kTcGroupBytes + (uint32_t)row * 16u), "r"(w2) : "memory");
+						layer(TcInt<0>(), TcInt<1>(), t, f, nullptr);
+						if constexpr (SETS == 2) layer(TcInt<1>(), TcInt<1>(), t, f, nullptr);
 					}
-					NAB_TC_STAMP(3);
-					asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-					fence_before();
-					nbar_arrive<kTcBarIssue, C::kIssueBar>();
-					NAB_TC_STAMP(4);
-					if (L == 2)
-					{
-						// ---- layer 1 ----
-						if (!dead && !mbar_wait(bar1, (uint32_t)t & 1u)) dead = true;
-						fence_after();
-						tc_load_gates<4 * UPT>(tmLane + (uint32_t)C::N, r);
-						tc_cell<UPT>(r, c[L - 1], h[L - 1]);
-						tc_store_h<UPT>(a_addr(L - 1), h[L - 1]);
-						asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-					}
-					// head: out = w_head . h_last + b_head (LSTM.h:184-188): this thread's share of the sum
-					float part = 0.0f;
-#pragma unroll
-					for (int j = 0; j < UPT; j++) part = fmaf(hw[j], h[L - 1][j], part);
-					tprod[f * C::kTprodStride + g * kRows + row] = part;
 				}
 				// ---- flush the tile's outputs ----
 				cp_async_wait_all();
 				nbar_sync<kTcBarWork, C::kWorkers>();
 				if (out != nullptr)
 				{
-					for (int i = tid; i < kTcTile * kRows; i += C::kWorkers)
-					{
-						int rr, f;
-						if (outFS == 1) { rr = i / kTcTile; f = i % kTcTile; }
-						else { rr = i % kRows; f = i / kRows; }
-						const long long ss = base + rr;
-						if (ss < S && f < tn)
-						{
-							float acc = tprod[f * C::kTprodStride + rr];
 #pragma unroll
-							for (int k = 1; k < NWG; k++) acc += tprod[f * C::kTprodStride + k * kRows + rr];
-							out[ss * outSS + (long long)(t0 + f) * outFS] = acc + headB;
+					for (int set = 0; set < SETS; set++)
+					{
+						const float* tprod = set_tprod(set);
+						for (int i = tid; i < kTcTile * kRows; i += C::kWorkers)
+						{
+							int rr, f;
+							if (outFS == 1) { rr = i / kTcTile; f = i % kTcTile; }
+							else { rr = i % kRows; f = i / kRows; }
+							const long long ss = base0 + (long long)set * kRows + rr;
+							if (ss < S && f < tn)
+							{
+								float acc = tprod[f * C::kTprodStride + rr];
+#pragma unroll
+								for (int k = 1; k < NWG; k++) acc += tprod[f * C::kTprodStride + k * kRows + rr];
+								out[ss * outSS + (long long)(t0 + f) * outFS] = acc + headB;
+							}
 						}
 					}
 				}
 				nbar_sync<kTcBarWork, C::kWorkers>();
 			}
-#ifdef NAB_TC_TIMING
-			if (blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 4 * NWG - 4) && n >= 128 && n <= 256)
-				printf("tc timing warp %d: per step wait %lld | ld %lld | cell+st %lld | fence+arrive %lld | layer1+head+loop %lld | total %lld cycles\n", warp, tacc[1] / n, tacc[2] / n,
-					tacc[3] / n, tacc[4] / n, ((clock64() - tstart) - tacc[1] - tacc[2] - tacc[3] - tacc[4]) / n, (clock64() - tstart) / n);
-#endif
-			if (live)
+#pragma unroll
+			for (int set = 0; set < SETS; set++)
 			{
-				float* st = state + (size_t)s * M.stateStride;
+				const long long s = base0 + (long long)set * kRows + row;
+				if (s < S)
+				{
+					float* st = state + (size_t)s * M.stateStride;
 #pragma unroll
-				for (int l = 0; l < L; l++)
+					for (int l = 0; l < L; l++)
 #pragma unroll
-					for (int j = 0; j < UPT; j++)
-						if (u0 + j < M.G)
-						{
-							st[(2 * l) * M.G + u0 + j] = h[l][j];
-							st[(2 * l + 1) * M.G + u0 + j] = c[l][j];
-						}
+						for (int j = 0; j < UPT; j++)
+							if (u0 + j < M.G)
+							{
+								st[(2 * l) * M.G + u0 + j] = h[set][l][j];
+								st[(2 * l + 1) * M.G + u0 + j] = c[set][l][j];
+							}
+				}
 			}
 		}
 		fence_before();
@@ -458,18 +488,34 @@ namespace nab200
 		if (warp == C::kIssuerWarp) tmem_dealloc<C::kTmemCols>(tm);
 	}
 
-	template <int UPT, int NWG, int L>
-	static cudaError_t lstm_tc_launch_variant(const LstmModelDev& M, const LstmLaunch& a)
+	template <int UPT, int NWG, int L, int SETS>
+	static cudaError_t lstm_tc_launch_sets(const LstmModelDev& M, const LstmLaunch& a)
 	{
-		using C = TcCfg<UPT, NWG, L>;
-		auto kfn = lstm_tc_kernel<UPT, NWG, L>;
+		using C = TcCfg<UPT, NWG, L, SETS>;
+		auto kfn = lstm_tc_kernel<UPT, NWG, L, SETS>;
 		static SmemGrant grant;
-		cudaError_t err = EnsureDynamicSmem(kfn, grant, C::kSmem);
+		cudaError_t err = EnsureDynamicSmem(kfn, grant, C::kSmem, true);   // (maximum shared-memory carve-out: two CTAs per SM where registers allow)
 		if (err != cudaSuccess) return err;
-		const int grid = (a.S + C::kRows - 1) / C::kRows;
+		const int per = C::kRows * SETS;
+		const int grid = (a.S + per - 1) / per;
 		kfn<<<grid, C::kThreads, C::kSmem, a.stream>>>(M, a.weights, a.state, a.in, a.out, a.inSS, a.inFS, a.outSS, a.outFS, a.S, a.n,
 			a.zeroInput ? 1 : 0);
 		return cudaGetLastError();
+	}
+
+	// two 128-stream sets per CTA once the model's slots need more than one single-set CTA per SM (and the shape's operands fit)
+	template <int UPT, int NWG, int L>
+	static cudaError_t lstm_tc_launch_variant(const LstmModelDev& M, const LstmLaunch& a)
+	{
+		constexpr bool fits2 = TcCfg<UPT, NWG, L, 2>::kSmem <= 227u * 1024u && 2 * L * 4 * UPT * NWG <= 512;
+		if constexpr (fits2)
+		{
+			const int Sp = a.pickS > 0 ? a.pickS : a.S;
+			const int sms = a.numSMs > 0 ? a.numSMs : 148;
+			const bool two = a.tcSets == 2 || (a.tcSets != 1 && Sp > 128 * sms);
+			if (two) return lstm_tc_launch_sets<UPT, NWG, L, 2>(M, a);
+		}
+		return lstm_tc_launch_sets<UPT, NWG, L, 1>(M, a);
 	}
 
 	bool lstm_tc_supported(const LstmModelDev& M)

@@ -79,6 +79,7 @@ namespace nab200
 		bool generic;           // force the run-time-shaped kernel (use_tc = -1)
 		int kernel;             // 0 automatic, 1 gate rows in registers, 2 lane = stream with shared-memory matrices, 3 run-time-shaped, 4 tensor cores (tcgen05)
 		int numSMs;
+		int tcSets;             // tensor-core kernel: 128-stream sets per CTA, 1 or 2 (0: by the model's slot count)
 		int pickS;              // streams the automatic kernel choice is made for (the model's slot count; 0: S)
 		cudaStream_t stream;
 	};

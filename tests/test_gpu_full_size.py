@@ -58,10 +58,11 @@ def test_full_size_cfg3_lstm_8192x128(na, O, tmp_path):
 
 def test_full_size_lstm_tensor_core_kernel(na, O, tmp_path):
     """The batches the automatic choice gives to the tcgen05 LSTM kernel: 2x16 at 8192 streams (64-stream CTAs, one per SM) and
-    1x16 at 16384 streams (128-stream CTAs, two per SM)."""
+    1x16 at 16384 streams (two CTAs per SM) and at 32768 (two 128-stream sets per CTA)."""
     assert na.describe_model_file(model_file_for(load_golden(golden_files("syn_lstm_2x16")[0]), tmp_path))["kernel"] == "lstm_tcgen05_gates"
     _patterned_full_size(na, O, tmp_path, "syn_lstm_2x16", 8192, 128, 4, LSTM_TOL, amplitude=0.5)
     _patterned_full_size(na, O, tmp_path, "syn_lstm_1x16", 16384, 128, 4, LSTM_TOL, amplitude=0.5)
+    _patterned_full_size(na, O, tmp_path, "syn_lstm_1x16", 32768, 128, 3, LSTM_TOL, amplitude=0.5)    # two 128-stream sets per CTA
 
 
 def test_full_size_cfg5_a2_full_4096x256(na, O, tmp_path):

@@ -432,10 +432,11 @@ def test_lane_per_stream_lstm_kernel(na, O, name, streams, tmp_path):
 
 
 @pytest.mark.parametrize("name,streams", [("syn_lstm_1x16", 70), ("syn_lstm_1x24", 65), ("syn_lstm_2x12", 37), ("syn_lstm_2x8", 129),
-                                          ("syn_lstm_2x16", 200), ("syn_dyn_lstm_2x32", 64), ("syn_lstm_1x8", 3), ("ref_BossLSTM_1x16", 131)])
+                                          ("syn_lstm_2x16", 200), ("syn_dyn_lstm_2x32", 64), ("syn_lstm_1x8", 3), ("ref_BossLSTM_1x16", 131),
+                                          ("syn_lstm_1x16", 300), ("syn_lstm_2x8", 257)])
 def test_tensor_core_lstm_kernel(na, O, name, streams, tmp_path):
     """The tcgen05 LSTM kernel (gates of 128 streams as one small GEMM per step and layer, fp16-pair operands; the default
-    for large batches) forced for every shape it covers: ragged stream counts around its 128-stream CTAs,
+    for large batches) forced for every shape it covers, with one and with two 128-stream sets per CTA: ragged stream counts around its CTAs,
     both layouts, odd call sizes across its 16-frame tiles, probed streams against their own oracle instances, the whole batch
     against the fp32 CUDA-core kernels, and bit-identical results however the samples are cut into calls."""
     g = load_golden(golden_files(name)[0])
@@ -447,8 +448,9 @@ def test_tensor_core_lstm_kernel(na, O, name, streams, tmp_path):
     xs = [(rng.uniform(-1, 1, (streams, n)) * 0.5).astype(np.float32) for n in sizes]
     xall = np.concatenate(xs, axis=1)
     outs = {}
-    for kern in (4, 0):
+    for kern, sets in ((4, 1), (4, 2), (0, 0)):
         prev = na.set_option("lstm_kernel", kern)
+        prev_sets = na.set_option("lstm_tc_sets", sets)
         try:
             m = _load(na, mf, streams=streams)
             m2 = _load(na, mf, streams=streams)
@@ -469,11 +471,14 @@ def test_tensor_core_lstm_kernel(na, O, name, streams, tmp_path):
                 assert np.array_equal(y1, yall), "the cut of the call sequence changed the result"
         finally:
             na.set_option("lstm_kernel", prev)
-        outs[kern] = y1
+            na.set_option("lstm_tc_sets", prev_sets)
+        outs[(kern, sets)] = y1
+    # one and two 128-stream sets per CTA: the same arithmetic per stream, bit for bit
+    assert np.array_equal(outs[(4, 1)], outs[(4, 2)])
     for s in sorted({0, streams // 2, streams - 1}):
         ref = O.PortModel.from_file(mf).process(xall[s])
-        assert float(np.abs(ref - outs[4][s]).max()) <= LSTM_TOL
-    assert float(np.abs(outs[4] - outs[0]).max()) <= LSTM_TOL
+        assert float(np.abs(ref - outs[(4, 1)][s]).max()) <= LSTM_TOL
+    assert float(np.abs(outs[(4, 1)] - outs[(0, 0)]).max()) <= LSTM_TOL
 
 
 @pytest.mark.parametrize("kind", ["zero", "huge", "tiny"])

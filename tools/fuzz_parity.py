@@ -39,7 +39,7 @@ def main():
             mf = C.model_file_for(g, tmp)
             sr = C.external_sample_rate_of(g)
             lstm = C.is_lstm_case(g)
-            S = int(rng.integers(1, 301 if force_tc else 41))
+            S = int(rng.integers(1, 601 if force_tc else 41))
             calls = int(rng.integers(2, 7))
             sizes = [int(rng.integers(1, 301)) for _ in range(calls)]
             if rng.random() < 0.3:
@@ -47,6 +47,7 @@ def main():
             layout = int(rng.integers(0, 2))
             on_device = bool(rng.integers(0, 2))
             prev_kernel = na.set_option("lstm_kernel", 4 if force_tc else 0)
+            prev_sets = na.set_option("lstm_tc_sets", int(rng.integers(1, 3)) if force_tc else 0)
             try:
                 ld = na.NeuralModelLoader()
                 ld.SetExternalSampleRate(sr)
@@ -54,6 +55,7 @@ def main():
                 m = ld.CreateFromFile(mf)
             finally:
                 na.set_option("lstm_kernel", prev_kernel)
+                na.set_option("lstm_tc_sets", prev_sets)
             amp = 0.5 if lstm else 1.0
             xs = [(rng.uniform(-1, 1, (S, n)) * amp).astype(np.float32) for n in sizes]
             ys = []
