@@ -23,7 +23,6 @@
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
 #include <stdint.h>
-#include <cstdio>
 #include "na_device.h"
 #include "na_kernels.h"
 #include "lstm_math.h"
@@ -221,12 +220,6 @@ namespace nab200
 
 	constexpr int kTcBarIssue = 1, kTcBarWork = 3;   // issue barriers: one per set (ids 1, 2)
 
-	// cycle stamps of one worker warp (timing builds only): [0] enter wait, [1] MMA done, [2] gates loaded, [3] cell + stores done, [4] arrived
-#ifdef NAB_TC_TIMING
-#define NAB_TC_STAMP(i) do { const long long now_ = clock64(); if ((i) > 0) tacc[i] += now_ - tlast; tlast = now_; } while (0)
-#else
-#define NAB_TC_STAMP(i) do { } while (0)
-#endif
 
 	template <int I> struct TcInt { static constexpr int value = I; };
 
