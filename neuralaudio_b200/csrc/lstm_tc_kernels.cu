@@ -19,6 +19,8 @@
 // with layer 1 of step t (it needs only h_0(t) and x(t + 1)), so with two layers one MMA latency per step is hidden.
 // The head dot product (LSTM.h:184-188) stays in fp32 on the CUDA cores: per-thread partial sums per frame in shared memory,
 // summed in a fixed order when a 16-frame tile is flushed; inputs arrive by cp.async one tile ahead.
+// Batches of more than one such CTA per SM: a CTA carries two independent 128-stream sets (own A operands, own accumulator columns) and a
+// worker alternates between row r of the one and of the other, so one set's GEMM, commit and hand-off run behind the other's activations.
 // Results do not depend on how a stream's samples are cut into calls (state = fp32 h and c; every accumulator starts per step).
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
