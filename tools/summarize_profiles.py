@@ -71,7 +71,7 @@ def main():
     tp = os.path.join(PROF, "roofline_traffic.json")
     if os.path.exists(tp):
         traffic = json.load(open(tp))
-    for name, workload in (("prof_wavenet", "a1_standard"), ("prof_lstm", "lstm_1x16"), ("prof_a2", "a2_full"), ("prof_lstm_tc", None), ("prof_nano", None)):
+    for name, workload in (("prof_wavenet", "a1_standard"), ("prof_lstm", "lstm_1x16"), ("prof_a2", "a2_full"), ("prof_lstm_tc", None), ("prof_lstm_tc2", None), ("prof_nano", None)):
         rep = os.path.join(OUT, name + ".ncu-rep")
         if not os.path.exists(rep):
             continue
